@@ -1,0 +1,143 @@
+"""ctypes binding of libmpshuffle.so -- the same C ABI a Rust/cgo/JNI host would bind."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "lib", "libmpshuffle.so")
+
+if not os.path.exists(lib_path):
+    raise ImportError(
+        f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  There is no CPU fallback for the hot path.")
+
+lib = ctypes.CDLL(lib_path)
+
+_vp, _i32, _u64, _cp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_char_p
+
+# name -> (restype, argtypes); must list every symbol include/mpshuffle.h declares
+SIGNATURES = {
+    "mp_ctx_create": (_i32, [ctypes.POINTER(_vp), _i32]),
+    "mp_ctx_destroy": (None, [_vp]),
+    "mp_ctx_stream": (_vp, [_vp]),
+    "mp_ctx_sync": (_i32, [_vp]),
+    "mp_last_error_string": (_cp, [_vp]),
+    "mp_verify_status_string": (_cp, [_i32]),
+    "mp_last_kernel_launches": (_i32, [_vp]),
+    "mp_msm_g1": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
+    "mp_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
+    "mp_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp_last_msm_ec_adds": (_u64, [_vp]),
+    "mp_last_msm_window": (_i32, [_vp]),
+    "mp_dbg_fq_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp_dbg_point_add": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp_dbg_scalar_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp_dbg_bench": (_i32, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class MpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mpshuffle error {code}: {msg}")
+        self.code = code
+
+
+def check(ctx_handle, code):
+    if code < 0:
+        msg = lib.mp_last_error_string(ctx_handle)
+        raise MpError(code, msg.decode() if msg else "")
+    return code
+
+
+class Context:
+    """Owns one `mp_ctx` (one CUDA device, one stream)."""
+
+    def __init__(self, device=0):
+        h = _vp()
+        rc = lib.mp_ctx_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise MpError(rc, f"mp_ctx_create(device={device}) failed: no usable CUDA device "
+                              "(the engine has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib.mp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- plumbing
+    @property
+    def stream(self):
+        return lib.mp_ctx_stream(self.h)
+
+    def sync(self):
+        check(self.h, lib.mp_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib.mp_last_kernel_launches(self.h)
+
+    # --- MSM (host buffers)
+    def msm_g1(self, bases: bytes, scalars: bytes, window_bits=0) -> bytes:
+        n = len(scalars) // 32
+        assert len(bases) == 64 * n and len(scalars) == 32 * n
+        out = ctypes.create_string_buffer(64)
+        check(self.h, lib.mp_msm_g1(self.h, bases, scalars, n, window_bits, out))
+        return out.raw
+
+    def ct_msm(self, deck: bytes, scalars: bytes, window_bits=0) -> bytes:
+        n = len(scalars) // 32
+        assert len(deck) == 128 * n
+        out = ctypes.create_string_buffer(128)
+        check(self.h, lib.mp_ct_msm(self.h, deck, scalars, n, window_bits, out))
+        return out.raw
+
+    # --- MSM (device pointers, asynchronous on self.stream)
+    def msm_g1_device(self, d_bases, d_scalars, n, d_out, window_bits=0):
+        check(self.h, lib.mp_msm_g1_device(self.h, d_bases, d_scalars, n, window_bits, d_out))
+
+    def ct_msm_device(self, d_deck, d_scalars, n, d_out, window_bits=0):
+        check(self.h, lib.mp_ct_msm_device(self.h, d_deck, d_scalars, n, window_bits, d_out))
+
+    @property
+    def last_msm_ec_adds(self):
+        return lib.mp_last_msm_ec_adds(self.h)
+
+    @property
+    def last_msm_window(self):
+        return lib.mp_last_msm_window(self.h)
+
+    # --- debug hooks
+    def dbg_fq_mul(self, a: bytes, b: bytes) -> bytes:
+        n = len(a) // 32
+        out = ctypes.create_string_buffer(32 * n)
+        check(self.h, lib.mp_dbg_fq_mul(self.h, a, b, n, out))
+        return out.raw
+
+    def dbg_point_add(self, p: bytes, q: bytes) -> bytes:
+        n = len(p) // 64
+        out = ctypes.create_string_buffer(64 * n)
+        check(self.h, lib.mp_dbg_point_add(self.h, p, q, n, out))
+        return out.raw
+
+    def dbg_scalar_mul(self, p: bytes, k: bytes) -> bytes:
+        n = len(p) // 64
+        out = ctypes.create_string_buffer(64 * n)
+        check(self.h, lib.mp_dbg_scalar_mul(self.h, p, k, n, out))
+        return out.raw
+
+    def dbg_bench(self, which, iters):
+        ms, ops = ctypes.c_float(), ctypes.c_double()
+        check(self.h, lib.mp_dbg_bench(self.h, which, iters, ctypes.byref(ms), ctypes.byref(ops)))
+        return ms.value, ops.value

@@ -1,0 +1,332 @@
+// extern "C" surface of libmpshuffle.so (declared in include/mpshuffle.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mpshuffle.h"
+#include "ctx.cuh"
+#include "msm.cuh"
+
+using namespace mp;
+
+// ------------------------------------------------------------------------------------------
+// context plumbing
+// ------------------------------------------------------------------------------------------
+int32_t mp_ctx::fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err = buf;
+  return code;
+}
+int32_t mp_ctx::cuda_fail(cudaError_t e, const char* where) {
+  return fail(MP_ERR_CUDA, "CUDA error in %s: %s", where, cudaGetErrorString(e));
+}
+
+extern "C" int32_t mp_ctx_create(mp_ctx** out, int32_t device) {
+  if (!out) return MP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    fprintf(stderr, "mpshuffle: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    return MP_ERR_CUDA;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return MP_ERR_CUDA;
+  mp_ctx* ctx = new mp_ctx();
+  ctx->device = device;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ctx; return MP_ERR_CUDA; }
+  ctx->ws = msm_workspace_create();
+  *out = ctx;
+  return MP_OK;
+}
+
+extern "C" void mp_ctx_destroy(mp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  msm_workspace_destroy(ctx->ws);
+  for (auto& b : ctx->bufs)
+    if (b.ptr) cudaFree(b.ptr);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" void* mp_ctx_stream(mp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int32_t mp_ctx_sync(mp_ctx* ctx) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_ctx_sync");
+  return MP_OK;
+}
+extern "C" const char* mp_last_error_string(mp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" const char* mp_verify_status_string(int32_t status) {
+  switch (status) {
+    case MP_OK: return "ok";
+    case MP_VERIFY_HADAMARD: return "Hadamard Product (5.1)";
+    case MP_VERIFY_ZERO: return "Zero Argument (5.2)";
+    case MP_VERIFY_SVP: return "Single Value Product (5.3)";
+    case MP_VERIFY_MULTIEXP: return "Multi Exponentiation (4)";
+    default: return "unknown";
+  }
+}
+extern "C" int32_t mp_last_kernel_launches(mp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t mp_last_msm_ec_adds(mp_ctx* ctx) { return ctx ? ctx->last_ec_adds : 0; }
+extern "C" int32_t mp_last_msm_window(mp_ctx* ctx) { return ctx ? ctx->last_window : 0; }
+
+void* mp_ctx::scratch(int slot, size_t bytes) {
+  if ((size_t)slot >= bufs.size()) bufs.resize(slot + 1);
+  auto& b = bufs[slot];
+  if (b.cap < bytes) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&b.ptr, want) != cudaSuccess) return nullptr;
+    b.cap = want;
+  }
+  return b.ptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// MSM entry points
+// ------------------------------------------------------------------------------------------
+static uint64_t scheduled_ec_adds(uint64_t n, int c, int ncomp) {
+  uint64_t W = (253 + c - 1) / c, B = 1ull << (c - 1);
+  return (uint64_t)ncomp * (W * (n + 2 * B) + W * (uint64_t)c);
+}
+
+// d_points canonical (n*ncomp points), d_scalars canonical, d_out canonical (ncomp points)
+static int32_t msm_device_common(mp_ctx* ctx, const void* d_points, const void* d_scalars,
+                                 uint64_t n, int ncomp, int32_t window_bits, void* d_out) {
+  if (!ctx || (!d_points && n) || (!d_scalars && n) || !d_out) return MP_ERR_INVALID_ARG;
+  if (n >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "MSM size %llu too large", (unsigned long long)n);
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  int c = window_bits > 0 ? window_bits : msm_pick_window(n);
+  if (c < 2 || c > 16) return ctx->fail(MP_ERR_INVALID_ARG, "window_bits %d out of range [2,16]", c);
+  ctx->last_window = c;
+  ctx->last_ec_adds = scheduled_ec_adds(n, c, ncomp);
+  affine* mont = (affine*)ctx->scratch(mp_ctx::kSlotPointsMont, sizeof(affine) * n * ncomp);
+  xyzz* res = (xyzz*)ctx->scratch(mp_ctx::kSlotMsmOut, sizeof(xyzz) * ncomp);
+  int* bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  if (!mont || !res || !bad) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "memset");
+  if ((e = points_to_mont((const uint32_t*)d_points, mont, n * ncomp, bad, ctx->stream)) != cudaSuccess)
+    return ctx->cuda_fail(e, "points_to_mont");
+  ctx->launches += n ? 1 : 0;
+  MsmJob job{0, 0, (uint32_t)n};
+  if ((e = msm_run(ctx->ws, (const uint32_t*)d_scalars, n, mont, ncomp, &job, 1, c, res, ctx->stream)) != cudaSuccess)
+    return ctx->cuda_fail(e, "msm_run");
+  ctx->launches += msm_last_launches(ctx->ws);
+  if ((e = xyzz_to_canonical(res, (uint32_t*)d_out, ncomp, ctx->stream)) != cudaSuccess)
+    return ctx->cuda_fail(e, "xyzz_to_canonical");
+  ctx->launches += 1;
+  return MP_OK;
+}
+
+static int32_t msm_host_common(mp_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n,
+                               int ncomp, int32_t window_bits, uint8_t* out) {
+  if (!ctx || (!points && n) || (!scalars && n) || !out) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  size_t pbytes = (size_t)n * 64 * ncomp, sbytes = (size_t)n * 32;
+  uint8_t* d_in = (uint8_t*)ctx->scratch(mp_ctx::kSlotStageIn, pbytes + sbytes + 256);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(mp_ctx::kSlotStageOut, 64 * ncomp);
+  if (!d_in || !d_out) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  cudaError_t e;
+  if (n) {
+    if ((e = cudaMemcpyAsync(d_in, points, pbytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+      return ctx->cuda_fail(e, "H2D points");
+    if ((e = cudaMemcpyAsync(d_in + pbytes, scalars, sbytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+      return ctx->cuda_fail(e, "H2D scalars");
+  }
+  int32_t st = msm_device_common(ctx, d_in, d_in + pbytes, n, ncomp, window_bits, d_out);
+  if (st != MP_OK) return st;
+  int bad = 0;
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  if ((e = cudaMemcpyAsync(out, d_out, 64 * ncomp, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
+    return ctx->cuda_fail(e, "D2H result");
+  if ((e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
+    return ctx->cuda_fail(e, "D2H flag");
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "MSM execution");
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not on the Stark curve");
+  return MP_OK;
+}
+
+extern "C" int32_t mp_msm_g1(mp_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, uint64_t n,
+                             int32_t window_bits, uint8_t* out) {
+  return msm_host_common(ctx, bases, scalars, n, 1, window_bits, out);
+}
+extern "C" int32_t mp_ct_msm(mp_ctx* ctx, const uint8_t* deck, const uint8_t* scalars, uint64_t n,
+                             int32_t window_bits, uint8_t* out) {
+  return msm_host_common(ctx, deck, scalars, n, 2, window_bits, out);
+}
+extern "C" int32_t mp_msm_g1_device(mp_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                                    int32_t window_bits, void* d_out) {
+  return msm_device_common(ctx, d_bases, d_scalars, n, 1, window_bits, d_out);
+}
+extern "C" int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
+                                    int32_t window_bits, void* d_out) {
+  return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / parity hooks
+// ------------------------------------------------------------------------------------------
+__global__ void k_dbg_fq_mul(const fq* a, const fq* b, fq* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fq_mul(a[i], b[i]);
+}
+__global__ void k_dbg_point_add(const uint32_t* p, const uint32_t* q, uint32_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  xyzz acc = xyzz_from_affine(affine_from_canonical(p + i * 16));
+  xyzz_madd(acc, affine_from_canonical(q + i * 16));
+  affine a = xyzz_to_affine(acc);
+  if (affine_is_identity(a)) { for (int k = 0; k < 16; k++) out[i * 16 + k] = 0; }
+  else affine_to_canonical(a, out + i * 16);
+}
+__global__ void k_dbg_scalar_mul(const uint32_t* p, const uint32_t* k, uint32_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  affine P = affine_from_canonical(p + i * 16);
+  xyzz acc = xyzz_identity();
+  for (int bit = 255; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((k[i * 8 + (bit >> 5)] >> (bit & 31)) & 1) xyzz_madd(acc, P);
+  }
+  affine a = xyzz_to_affine(acc);
+  if (affine_is_identity(a)) { for (int w = 0; w < 16; w++) out[i * 16 + w] = 0; }
+  else affine_to_canonical(a, out + i * 16);
+}
+
+template <typename K>
+static int32_t dbg_map(mp_ctx* ctx, const uint8_t* a, size_t abytes, const uint8_t* b, size_t bbytes,
+                       uint64_t n, uint8_t* out, size_t obytes, K launch) {
+  if (!ctx || !a || !b || !out) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  uint8_t* d = (uint8_t*)ctx->scratch(mp_ctx::kSlotStageIn, (abytes + bbytes + obytes) * n + 256);
+  if (!d) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  uint8_t *da = d, *db = d + abytes * n, *dout = db + bbytes * n;
+  cudaMemcpyAsync(da, a, abytes * n, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(db, b, bbytes * n, cudaMemcpyHostToDevice, ctx->stream);
+  launch(da, db, dout);
+  cudaMemcpyAsync(out, dout, obytes * n, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "debug kernel");
+  ctx->launches = 1;
+  return MP_OK;
+}
+
+extern "C" int32_t mp_dbg_fq_mul(mp_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+  return dbg_map(ctx, a, 32, b, 32, n, out, 32, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
+    k_dbg_fq_mul<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const fq*)da, (const fq*)db, (fq*)dout, n);
+  });
+}
+extern "C" int32_t mp_dbg_point_add(mp_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out) {
+  return dbg_map(ctx, p, 64, q, 64, n, out, 64, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
+    k_dbg_point_add<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t*)da, (const uint32_t*)db, (uint32_t*)dout, n);
+  });
+}
+extern "C" int32_t mp_dbg_scalar_mul(mp_ctx* ctx, const uint8_t* p, const uint8_t* k, uint64_t n, uint8_t* out) {
+  return dbg_map(ctx, p, 64, k, 32, n, out, 64, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
+    k_dbg_scalar_mul<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t*)da, (const uint32_t*)db, (uint32_t*)dout, n);
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// integer-pipe microbenchmarks (roofline denominators measured on the box)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bench_imad_wide(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  unsigned long long acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = k + a;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b + r));
+    }
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s ^= acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
+}
+__global__ void __launch_bounds__(256) k_bench_imad_lo(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  uint32_t acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = k + a;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b + r));
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s ^= acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(128) k_bench_fq_mul(uint32_t* out, int iters, uint32_t seed) {
+  fq x = fq_one(), y = fq_r2();
+  x.v[0] ^= seed + threadIdx.x;
+  y.v[0] ^= blockIdx.x;
+  x = fq_reduce_weak(x); y = fq_reduce_weak(y);
+  for (int it = 0; it < iters; it++) { x = fq_mul(x, y); y = fq_mul(y, x); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x.v[0] ^ y.v[7];
+}
+__global__ void __launch_bounds__(128) k_bench_madd(uint32_t* out, int iters, uint32_t seed) {
+  // G in canonical form -> Montgomery; acc walks G, 2G, 3G, ... (no special cases hit)
+  const uint32_t g[16] = {0xc943cfcau, 0x3d723d8bu, 0x0d1819e0u, 0xdeacfd9bu, 0x5a40f0c7u, 0x7beced41u,
+                          0x8599971bu, 0x01ef15c1u, 0x36e8dc1fu, 0x2873000cu, 0x1abe43a3u, 0xde53ecd1u,
+                          0xdf46ec62u, 0xb7be4801u, 0x0aa49730u, 0x00566806u};
+  affine P = affine_from_canonical(g);
+  xyzz acc = xyzz_dbl_affine(P);
+  if ((seed + threadIdx.x) == 0xffffffffu) acc = xyzz_dbl(acc);
+  for (int it = 0; it < iters; it++) xyzz_madd(acc, P);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.X.v[0] ^ acc.ZZZ.v[3];
+}
+
+extern "C" int32_t mp_dbg_bench(mp_ctx* ctx, int32_t which, int32_t iters, float* ms, double* ops) {
+  if (!ctx || !ms || !ops || iters <= 0) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  const int blocks = 148 * 8;
+  uint32_t* d = (uint32_t*)ctx->scratch(mp_ctx::kSlotStageOut, sizeof(uint32_t) * blocks * 256);
+  if (!d) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int rep = 0; rep < 2; rep++) {  // first pass = warm-up
+    cudaEventRecord(e0, ctx->stream);
+    switch (which) {
+      case 0: k_bench_imad_wide<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
+      case 1: k_bench_imad_lo<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
+      case 2: k_bench_fq_mul<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters * 2; break;
+      case 3: k_bench_madd<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters; break;
+      default: cudaEventDestroy(e0); cudaEventDestroy(e1); return MP_ERR_INVALID_ARG;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ctx->cuda_fail(e, "bench kernel"); }
+  }
+  cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->launches = 2;
+  return MP_OK;
+}

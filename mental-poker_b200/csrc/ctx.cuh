@@ -1,0 +1,30 @@
+// Engine context behind the opaque `mp_ctx` of include/mpshuffle.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace mp {
+struct MsmWorkspace;
+}
+
+struct mp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  mp::MsmWorkspace* ws = nullptr;
+  std::string err = "";
+  int launches = 0;
+  uint64_t last_ec_adds = 0;
+  int last_window = 0;
+
+  struct Buf { void* ptr = nullptr; size_t cap = 0; };
+  std::vector<Buf> bufs;
+  enum { kSlotStageIn = 0, kSlotStageOut, kSlotPointsMont, kSlotMsmOut, kSlotFlags, kSlotUser };
+  // growable device scratch; returns nullptr on allocation failure
+  void* scratch(int slot, size_t bytes);
+
+  int32_t fail(int32_t code, const char* fmt, ...);
+  int32_t cuda_fail(cudaError_t e, const char* where);
+};

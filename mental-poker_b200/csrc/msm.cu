@@ -1,0 +1,588 @@
+// Batched windowed-Pippenger MSM for sm_100a.  See msm.cuh for the pipeline overview and
+// DESIGN.md for the roofline model of each kernel.
+#include <stdio.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "msm.cuh"
+
+namespace mp {
+
+// ------------------------------------------------------------------------------------------
+// tunables
+// ------------------------------------------------------------------------------------------
+static constexpr int kChunk = 32;         // sorted entries per accumulate thread
+static constexpr int kAccThreads = 128;   // accumulate block size
+static constexpr int kSegLen = 16;        // buckets per k_reduce_seg thread
+static constexpr int kWinThreads = 256;   // k_reduce_win block size
+static constexpr uint32_t kNoDigit = 0xffffffffu;
+
+struct MsmWorkspace {
+  // growable device buffers
+  void* buf[16] = {nullptr};
+  size_t cap[16] = {0};
+  int launches = 0;
+  ~MsmWorkspace() {
+    for (int i = 0; i < 16; i++)
+      if (buf[i]) cudaFree(buf[i]);
+  }
+  template <typename T>
+  cudaError_t get(int slot, size_t count, T** out) {
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    if (cap[slot] < bytes) {
+      if (buf[slot]) cudaFree(buf[slot]);
+      buf[slot] = nullptr;
+      cap[slot] = 0;
+      size_t want = bytes + bytes / 8;
+      cudaError_t e = cudaMalloc(&buf[slot], want);
+      if (e != cudaSuccess) return e;
+      cap[slot] = want;
+    }
+    *out = reinterpret_cast<T*>(buf[slot]);
+    return cudaSuccess;
+  }
+};
+
+MsmWorkspace* msm_workspace_create() { return new MsmWorkspace(); }
+void msm_workspace_destroy(MsmWorkspace* ws) { delete ws; }
+int msm_last_launches(const MsmWorkspace* ws) { return ws->launches; }
+
+int msm_pick_window(uint64_t avg_len) {
+  // minimise W * (len + 2.8 * 2^(c-1)) over c, W = ceil(253 / c)
+  int best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= 16; c++) {
+    int W = (253 + c - 1) / c;
+    double cost = (double)W * ((double)avg_len + 2.8 * (double)(1u << (c - 1)));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void xyzz_add_ni(xyzz& acc, const xyzz& q) { xyzz_add(acc, q); }
+__device__ __noinline__ void xyzz_dbl_ni(xyzz& acc) { acc = xyzz_dbl(acc); }
+
+__device__ __forceinline__ xyzz xyzz_load(const xyzz* p) {
+  xyzz r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < 8; i++) d[i] = s[i];
+  return r;
+}
+__device__ __forceinline__ void xyzz_store(xyzz* p, const xyzz& v) {
+  uint4* d = reinterpret_cast<uint4*>(p);
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) d[i] = s[i];
+}
+__device__ __forceinline__ affine affine_load(const affine* p) {
+  affine r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) d[i] = __ldg(s + i);
+  return r;
+}
+__device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz& v, int delta) {
+  xyzz r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 32; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// ingest / export
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restrict__ in,
+                                                        affine* __restrict__ out, uint64_t n,
+                                                        int* __restrict__ bad) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[16];
+  const uint4* s = reinterpret_cast<const uint4*>(in + i * 16);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint4 v = __ldg(s + k);
+    w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+  }
+  affine p = affine_from_canonical(w);
+  if (bad != nullptr && !affine_on_curve(p)) atomicExch(bad, 1);
+  uint4* d = reinterpret_cast<uint4*>(out + i);
+  const uint4* ps = reinterpret_cast<const uint4*>(&p);
+#pragma unroll
+  for (int k = 0; k < 4; k++) d[k] = ps[k];
+}
+
+cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,
+                           cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  k_points_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_canonical, d_out, n, d_bad);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(64) k_xyzz_to_canonical(const xyzz* __restrict__ in,
+                                                          uint32_t* __restrict__ out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  xyzz p = xyzz_load(in + i);
+  affine a = xyzz_to_affine(p);
+  uint32_t w[16];
+  if (affine_is_identity(a)) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = 0;
+  } else {
+    affine_to_canonical(a, w);
+  }
+  uint4* d = reinterpret_cast<uint4*>(out + i * 16);
+#pragma unroll
+  for (int k = 0; k < 4; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
+cudaError_t xyzz_to_canonical(const xyzz* d_in, uint32_t* d_out, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  k_xyzz_to_canonical<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(d_in, d_out, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// digits
+// ------------------------------------------------------------------------------------------
+// digits[w * ns + i] = (|d| - 1) | (d < 0) << 31, or kNoDigit when d == 0.
+__global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars,
+                                                uint32_t* __restrict__ digits, uint64_t ns, int c,
+                                                int W) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  uint32_t s[9];
+  const uint4* p = reinterpret_cast<const uint4*>(scalars + i * 8);
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  s[8] = 0;
+  const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    int pos = w * c;
+    uint32_t raw = 0;
+    if (pos < 256) {
+      int word = pos >> 5, sh = pos & 31;
+      uint64_t two = (uint64_t)s[word] | ((uint64_t)s[word + 1] << 32);
+      raw = (uint32_t)(two >> sh) & mask;
+    }
+    raw += carry;
+    uint32_t enc;
+    if (raw > half) {  // negative digit raw - 2^c, magnitude 2^c - raw in [1, half-1]
+      enc = ((mask + 1u - raw) - 1u) | 0x80000000u;
+      carry = 1;
+    } else {
+      enc = raw == 0 ? kNoDigit : (raw - 1u);
+      carry = 0;
+    }
+    digits[(uint64_t)w * ns + i] = enc;
+  }
+}
+
+// grid.y = job; histogram of buckets
+__global__ void __launch_bounds__(256) k_count(const uint32_t* __restrict__ digits,
+                                               const MsmJob* __restrict__ jobs,
+                                               uint32_t* __restrict__ counts, uint64_t ns, int W,
+                                               uint32_t B) {
+  const MsmJob job = jobs[blockIdx.y];
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < job.len;
+       t += gridDim.x * blockDim.x) {
+    uint64_t si = (uint64_t)job.scalar_off + t;
+    for (int w = 0; w < W; w++) {
+      uint32_t d = digits[(uint64_t)w * ns + si];
+      if (d != kNoDigit) {
+        uint64_t bucket = ((uint64_t)blockIdx.y * W + w) * B + (d & 0x7fffffffu);
+        atomicAdd(&counts[bucket], 1u);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ digits,
+                                                 const MsmJob* __restrict__ jobs,
+                                                 uint32_t* __restrict__ cursor,
+                                                 uint32_t* __restrict__ sorted, uint64_t ns, int W,
+                                                 uint32_t B) {
+  const MsmJob job = jobs[blockIdx.y];
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < job.len;
+       t += gridDim.x * blockDim.x) {
+    uint64_t si = (uint64_t)job.scalar_off + t;
+    for (int w = 0; w < W; w++) {
+      uint32_t d = digits[(uint64_t)w * ns + si];
+      if (d != kNoDigit) {
+        uint64_t bucket = ((uint64_t)blockIdx.y * W + w) * B + (d & 0x7fffffffu);
+        uint32_t pos = atomicAdd(&cursor[bucket], 1u);
+        sorted[pos] = (job.point_off + t) | (d & 0x80000000u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan of bucket sizes: tiles of 2048 (256 threads x 8)
+// ------------------------------------------------------------------------------------------
+static constexpr int kScanTile = 2048;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[8];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    uint32_t s = warp_sums[w];
+    if (w < warp) base += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ counts,
+                                                        uint32_t* __restrict__ tile_sums,
+                                                        uint64_t n) {
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile + threadIdx.x * 8;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (base + k < n) s += counts[base + k];
+  uint32_t tot;
+  block_exclusive_scan_256(s, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single block: in-place exclusive scan of tile_sums[ntiles]; writes grand total to *total_out
+__global__ void __launch_bounds__(256) k_scan_top(uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                  uint32_t* __restrict__ total_out) {
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < ntiles; base += 256) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan_256(v, &tot);
+    if (i < ntiles) tile_sums[i] = running + ex;
+    running += tot;
+  }
+  if (threadIdx.x == 0) *total_out = running;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__ counts,
+                                                    const uint32_t* __restrict__ tile_sums,
+                                                    uint32_t* __restrict__ offsets,
+                                                    uint32_t* __restrict__ cursor, uint64_t n) {
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile + threadIdx.x * 8;
+  uint32_t v[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    v[k] = (base + k < n) ? counts[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan_256(s, &tot) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (base + k < n) {
+      offsets[base + k] = ex;
+      cursor[base + k] = ex;
+    }
+    ex += v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket accumulation (the hot kernel)
+// ------------------------------------------------------------------------------------------
+// Thread g handles component (g % ncomp) of chunk t = g / ncomp: sorted entries
+// [t*kChunk, min((t+1)*kChunk, E)).  Its first bucket run goes to part[g]; every later run
+// (which starts inside the chunk) goes to bucket_sums[bucket * ncomp + comp].
+template <int NCOMP>
+__global__ void __launch_bounds__(kAccThreads)
+    k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                 uint64_t nbuckets, const affine* __restrict__ points, xyzz* __restrict__ bucket_sums,
+                 xyzz* __restrict__ part) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t t = g / NCOMP;
+  const uint32_t comp = (uint32_t)(g % NCOMP);
+  const uint64_t E = offsets[nbuckets];
+  uint64_t pos = t * kChunk;
+  if (pos >= E) return;
+  const uint64_t end = min(pos + (uint64_t)kChunk, E);
+  // bucket containing entry `pos`: largest b with offsets[b] <= pos
+  uint64_t lo = 0, hi = nbuckets;  // invariant: offsets[lo] <= pos < offsets[hi]
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= pos) lo = mid; else hi = mid;
+  }
+  uint64_t b = lo;
+  uint64_t next = offsets[b + 1];
+  bool first = true;
+  xyzz acc = xyzz_identity();
+  uint32_t val = sorted[pos];
+  affine pt = affine_load(points + (uint64_t)(val & 0x7fffffffu) * NCOMP + comp);
+  while (true) {
+    // prefetch the next entry's point while this one is being added
+    uint32_t nval = val;
+    affine npt = pt;
+    if (pos + 1 < end) {
+      nval = sorted[pos + 1];
+      npt = affine_load(points + (uint64_t)(nval & 0x7fffffffu) * NCOMP + comp);
+    }
+    if (pos == next) {  // entering a new bucket: flush the finished run
+      if (first) xyzz_store(part + g, acc);
+      else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
+      first = false;
+      acc = xyzz_identity();
+      do { b++; next = offsets[b + 1]; } while (next <= pos);
+    }
+    if (val >> 31) pt = affine_neg(pt);
+    xyzz_madd(acc, pt);
+    pos++;
+    if (pos >= end) break;
+    val = nval;
+    pt = npt;
+  }
+  if (first) xyzz_store(part + g, acc);
+  else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
+}
+
+// Thread per (bucket, comp): total = [run that started mid-chunk] + sum of the `part`s of
+// every chunk whose first entry lies inside the bucket.
+__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ offsets,
+                                               uint64_t nbuckets, int ncomp,
+                                               xyzz* __restrict__ bucket_sums,
+                                               const xyzz* __restrict__ part) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nbuckets * ncomp) return;
+  uint64_t b = g / ncomp;
+  uint32_t comp = (uint32_t)(g % ncomp);
+  uint64_t o0 = offsets[b], o1 = offsets[b + 1];
+  xyzz acc = xyzz_identity();
+  if (o1 > o0) {
+    if (o0 % kChunk != 0) acc = xyzz_load(bucket_sums + g);
+    uint64_t t0 = (o0 + kChunk - 1) / kChunk, t1 = (o1 + kChunk - 1) / kChunk;
+    for (uint64_t t = t0; t < t1; t++) {
+      xyzz p = xyzz_load(part + t * ncomp + comp);
+      xyzz_add_ni(acc, p);
+    }
+  }
+  xyzz_store(bucket_sums + g, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket reduction
+// ------------------------------------------------------------------------------------------
+// Thread per (window, segment, comp): S = sum of the segment's L buckets,
+// T = sum_{i=0..L-1} (i+1) * B_i   (running-sum sweep from the top of the segment).
+__global__ void __launch_bounds__(128) k_reduce_seg(const xyzz* __restrict__ bucket_sums,
+                                                    uint64_t nwin, uint32_t B, uint32_t L,
+                                                    int ncomp, xyzz* __restrict__ segS,
+                                                    xyzz* __restrict__ segT) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nseg = B / L;
+  if (g >= nwin * nseg * ncomp) return;
+  uint32_t comp = (uint32_t)(g % ncomp);
+  uint64_t ws = g / ncomp;  // window * nseg + seg
+  uint64_t first_bucket = ws * L;
+  xyzz running = xyzz_identity(), acc = xyzz_identity();
+  for (int i = (int)L - 1; i >= 0; i--) {
+    xyzz bkt = xyzz_load(bucket_sums + (first_bucket + i) * ncomp + comp);
+    xyzz_add_ni(running, bkt);
+    xyzz_add_ni(acc, running);
+  }
+  xyzz_store(segS + g, running);
+  xyzz_store(segT + g, acc);
+}
+
+// block-wide sum of one xyzz per thread (kWinThreads threads); result valid in thread 0
+__device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem /* kWinThreads/32 entries */) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    xyzz o = xyzz_shfl_down(v, d);
+    if (lane < d) xyzz_add_ni(v, o);
+  }
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kWinThreads / 32; w++) xyzz_add_ni(v, smem[w]);
+  }
+  __syncthreads();
+  return v;
+}
+
+// Block per (window, comp):  out = sum_s T_s + L * sum_s s * S_s.
+// sum_s s*S_s = sum_{i>=0} Suf_A(i) with A[i] = S_{i+1}: block-wide suffix scan.
+__global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restrict__ segS,
+                                                            const xyzz* __restrict__ segT,
+                                                            uint32_t nseg, uint32_t L, int ncomp,
+                                                            xyzz* __restrict__ win_out) {
+  __shared__ xyzz smem[kWinThreads / 32];
+  const uint32_t comp = blockIdx.x % ncomp;
+  const uint64_t win = blockIdx.x / ncomp;
+  const xyzz* S = segS + win * nseg * ncomp + comp;
+  const xyzz* T = segT + win * nseg * ncomp + comp;
+  const uint32_t ipt = (nseg + kWinThreads - 1) / kWinThreads;  // power of two (nseg, threads are)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // local suffix sums over A[tid*ipt .. tid*ipt+ipt)
+  xyzz run = xyzz_identity(), lsum = xyzz_identity(), tsum = xyzz_identity();
+  for (int q = (int)ipt - 1; q >= 0; q--) {
+    uint32_t i = threadIdx.x * ipt + q;      // index into A
+    if (i + 1 < nseg) {
+      xyzz a = xyzz_load(S + (uint64_t)(i + 1) * ncomp);
+      xyzz_add_ni(run, a);
+    }
+    xyzz_add_ni(lsum, run);
+    if (i < nseg) {
+      xyzz tv = xyzz_load(T + (uint64_t)i * ncomp);
+      xyzz_add_ni(tsum, tv);
+    }
+  }
+  // exclusive suffix scan of `run` over threads: above = sum_{t' > tid} run_{t'}
+  xyzz inc = run;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    xyzz o = xyzz_shfl_down(inc, d);
+    if (lane + d < 32) xyzz_add_ni(inc, o);
+  }
+  if (lane == 0) smem[warp] = inc;  // warp total
+  xyzz above = xyzz_shfl_down(inc, 1);
+  if (lane == 31) above = xyzz_identity();
+  __syncthreads();
+  for (int w = warp + 1; w < kWinThreads / 32; w++) xyzz_add_ni(above, smem[w]);
+  __syncthreads();
+  // U_t = lsum + ipt * above
+  for (uint32_t k = 1; k < ipt; k <<= 1) xyzz_dbl_ni(above);
+  xyzz_add_ni(lsum, above);
+  xyzz U = block_sum_xyzz(lsum, smem);
+  xyzz Tt = block_sum_xyzz(tsum, smem);
+  if (threadIdx.x == 0) {
+    for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(U);
+    xyzz_add_ni(Tt, U);
+    xyzz_store(win_out + blockIdx.x, Tt);
+  }
+}
+
+// Thread per (job, comp): Horner over the job's W window sums.
+__global__ void __launch_bounds__(32) k_fold(const xyzz* __restrict__ win_out, int njobs, int W,
+                                             int c, int ncomp, xyzz* __restrict__ out) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= njobs * ncomp) return;
+  int job = g / ncomp, comp = g % ncomp;
+  xyzz acc = xyzz_load(win_out + ((uint64_t)(job * W + W - 1)) * ncomp + comp);
+  for (int w = W - 2; w >= 0; w--) {
+    for (int k = 0; k < c; k++) xyzz_dbl_ni(acc);
+    xyzz v = xyzz_load(win_out + ((uint64_t)(job * W + w)) * ncomp + comp);
+    xyzz_add_ni(acc, v);
+  }
+  xyzz_store(out + g, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------
+#define MP_CK(x)                          \
+  do {                                    \
+    cudaError_t _e = (x);                 \
+    if (_e != cudaSuccess) return _e;     \
+  } while (0)
+
+cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
+                    const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
+                    xyzz* d_out, cudaStream_t stream) {
+  ws->launches = 0;
+  if (njobs <= 0) return cudaSuccess;
+  if (ncomp != 1 && ncomp != 2) return cudaErrorInvalidValue;
+  if (c < 2 || c > 20) return cudaErrorInvalidValue;
+  const int W = (253 + c - 1) / c;
+  const uint32_t B = 1u << (c - 1);
+  const uint32_t L = std::min<uint32_t>(kSegLen, B);
+  const uint32_t nseg = B / L;
+  const uint64_t nwin = (uint64_t)njobs * W;
+  const uint64_t nbuckets = nwin * B;
+  uint64_t total_terms = 0;
+  uint32_t max_len = 0;
+  for (int j = 0; j < njobs; j++) {
+    total_terms += h_jobs[j].len;
+    max_len = std::max(max_len, h_jobs[j].len);
+    if ((uint64_t)h_jobs[j].scalar_off + h_jobs[j].len > n_scalars) return cudaErrorInvalidValue;
+  }
+  const uint64_t max_entries = total_terms * W;
+  if (max_entries >= (1ull << 32) || nbuckets >= (1ull << 32)) return cudaErrorInvalidValue;
+  const uint64_t max_chunks = (max_entries + kChunk - 1) / kChunk;
+  const uint64_t ntiles = (nbuckets + 1 + kScanTile - 1) / kScanTile;
+
+  uint32_t *digits, *counts, *offsets, *cursor, *sorted, *tile_sums;
+  MsmJob* d_jobs;
+  xyzz *bucket_sums, *part, *segS, *segT, *win_out;
+  MP_CK(ws->get(0, n_scalars * W, &digits));
+  MP_CK(ws->get(1, nbuckets + 1, &counts));
+  MP_CK(ws->get(2, nbuckets + 1, &offsets));
+  MP_CK(ws->get(3, nbuckets + 1, &cursor));
+  MP_CK(ws->get(4, max_entries, &sorted));
+  MP_CK(ws->get(5, ntiles + 1, &tile_sums));
+  MP_CK(ws->get(6, (size_t)njobs, &d_jobs));
+  MP_CK(ws->get(7, nbuckets * ncomp, &bucket_sums));
+  MP_CK(ws->get(8, max_chunks * ncomp, &part));
+  MP_CK(ws->get(9, nwin * nseg * ncomp, &segS));
+  MP_CK(ws->get(10, nwin * nseg * ncomp, &segT));
+  MP_CK(ws->get(11, nwin * ncomp, &win_out));
+
+  MP_CK(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(MsmJob) * njobs, cudaMemcpyHostToDevice, stream));
+  MP_CK(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nbuckets + 1), stream));
+
+  if (n_scalars > 0) {
+    k_digits<<<(unsigned)((n_scalars + 255) / 256), 256, 0, stream>>>(d_scalars, digits, n_scalars, c, W);
+    ws->launches++;
+  }
+  if (max_len > 0) {
+    dim3 grid((unsigned)std::min<uint64_t>((max_len + 255) / 256, 65535), (unsigned)njobs);
+    k_count<<<grid, 256, 0, stream>>>(digits, d_jobs, counts, n_scalars, W, B);
+    ws->launches++;
+  }
+  k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, stream>>>(counts, tile_sums, nbuckets + 1);
+  k_scan_top<<<1, 256, 0, stream>>>(tile_sums, (uint32_t)ntiles, tile_sums + ntiles);
+  k_scan_apply<<<(unsigned)ntiles, 256, 0, stream>>>(counts, tile_sums, offsets, cursor, nbuckets + 1);
+  ws->launches += 3;
+  if (max_len > 0) {
+    dim3 grid((unsigned)std::min<uint64_t>((max_len + 255) / 256, 65535), (unsigned)njobs);
+    k_scatter<<<grid, 256, 0, stream>>>(digits, d_jobs, cursor, sorted, n_scalars, W, B);
+    ws->launches++;
+  }
+  if (max_chunks > 0) {
+    uint64_t threads = max_chunks * ncomp;
+    unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
+    if (ncomp == 1)
+      k_accumulate<1><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part);
+    else
+      k_accumulate<2><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part);
+    ws->launches++;
+  }
+  k_fixup<<<(unsigned)((nbuckets * ncomp + 127) / 128), 128, 0, stream>>>(offsets, nbuckets, ncomp, bucket_sums, part);
+  k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(bucket_sums, nwin, B, L, ncomp, segS, segT);
+  k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
+  k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, W, c, ncomp, d_out);
+  ws->launches += 4;
+  return cudaGetLastError();
+}
+
+}  // namespace mp

@@ -1,0 +1,59 @@
+// Batched windowed-Pippenger variable-base MSM over the Stark curve (kernel family K1/K2 of
+// SURVEY.md section 2b).  Replaces the scalar-mul / dot-product loops that run inside
+// proof-essentials' `ShuffleArgument::{prove,verify}` (reference call sites
+// src/discrete_log_cards/mod.rs:409-415,437-442).
+//
+// One call evaluates `njobs` MSMs that share a scalar array and a point array; job k covers
+// scalars [scalar_off, scalar_off+len) against points [point_off, point_off+len) (x ncomp
+// interleaved components, ncomp = 2 for ElGamal ciphertexts: both components share digits
+// and the sorted index list).  Pipeline, all on one stream, no host synchronisation:
+//
+//   k_digits         signed c-bit digits of every scalar                 (HBM streaming)
+//   k_count          histogram of (job, window, |digit|) buckets         (global atomics)
+//   scan             exclusive prefix sum of bucket sizes                (3 small kernels)
+//   k_scatter        counting-sort scatter of point indices              (global atomics)
+//   k_accumulate     fixed-length chunks of the sorted list, XYZZ mixed adds, segmented by
+//                    bucket -> perfectly load balanced for ANY digit distribution
+//   k_fixup          stitch bucket runs that straddle chunk boundaries
+//   k_reduce_seg     per segment of L buckets: S = sum, T = sum (i+1) * B_i (running sums)
+//   k_reduce_win     per window: block-wide suffix scan over segment sums (warp shuffles)
+//   k_fold           per job: Horner over windows (c doublings each)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ec.cuh"
+
+namespace mp {
+
+struct MsmJob {
+  uint32_t scalar_off, point_off, len;
+};
+
+struct MsmWorkspace;  // opaque, owns device scratch that grows on demand
+
+MsmWorkspace* msm_workspace_create();
+void msm_workspace_destroy(MsmWorkspace*);
+
+// Heuristic window width for jobs of average length `avg_len`.
+int msm_pick_window(uint64_t avg_len);
+
+// d_scalars: canonical little-endian 256-bit scalars (< group order), 8 words each.
+// d_points : Montgomery-form affine points, index = point * ncomp + comp.
+// d_out    : njobs * ncomp XYZZ results (not normalised), index = job * ncomp + comp.
+// Returns cudaSuccess or the first CUDA error.  Asynchronous on `stream`.
+cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
+                    const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
+                    xyzz* d_out, cudaStream_t stream);
+
+// number of kernels the last msm_run launched / EC additions it performed (host-side count
+// of scheduled bucket additions, for EC-adds/s reporting)
+int msm_last_launches(const MsmWorkspace* ws);
+
+// canonical 64-byte points -> Montgomery affine (validating on-curve; bad points set *d_bad)
+cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,
+                           cudaStream_t stream);
+// XYZZ -> canonical 64-byte affine (x || y, all-zero = identity); one inversion per point
+cudaError_t xyzz_to_canonical(const xyzz* d_in, uint32_t* d_out, uint64_t n, cudaStream_t stream);
+
+}  // namespace mp
