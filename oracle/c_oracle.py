@@ -1,0 +1,84 @@
+"""ORACLE (test infrastructure only): ctypes loader for oracle/c/liboracle.so, the plain-C CPU
+restatement of the reference's shuffle hot path (see oracle/c/oracle.c).  Imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "c", "liboracle.so")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "c")])
+
+
+def load():
+    if not os.path.exists(_SO):
+        build()
+    lib = ctypes.CDLL(_SO)
+    cp, u64, i32, vp = ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p
+    lib.oc_msm.argtypes = [cp, cp, u64, i32, i32, cp]
+    lib.oc_remask.argtypes = [cp, cp, cp, vp, cp, u64, cp]
+    lib.oc_shuffle_prove.argtypes = [i32, i32, cp, cp, cp, cp, cp, cp, cp, vp, cp, cp, cp]
+    lib.oc_shuffle_verify.argtypes = [i32, i32, cp, cp, cp, cp, cp, cp, cp, cp]
+    lib.oc_pedersen_commit.argtypes = [i32, cp, cp, cp, i32, cp, cp]
+    lib.oc_proof_len.restype = ctypes.c_size_t
+    lib.oc_proof_len.argtypes = [i32, i32]
+    lib.oc_prover_randomness_len.restype = ctypes.c_size_t
+    lib.oc_prover_randomness_len.argtypes = [i32, i32]
+    lib.oc_fr_mul.argtypes = [cp, cp, cp]
+    lib.oc_fq_mul.argtypes = [cp, cp, cp]
+    lib.oc_blake2s.argtypes = [cp, u64, cp]
+    lib.oc_fs_challenges.argtypes = [cp, u64, i32, cp]
+    lib.oc_on_curve.argtypes = [cp]
+    lib.oracle_set_threads.argtypes = [i32]
+    lib.oracle_set_msm_mode.argtypes = [i32]
+    return lib
+
+
+class COracle:
+    """Byte-level interface (same layouts as include/mpshuffle.h)."""
+
+    def __init__(self, threads=1, msm_mode=0):
+        self.lib = load()
+        self.set(threads, msm_mode)
+
+    def set(self, threads=None, msm_mode=None):
+        if threads is not None:
+            self.lib.oracle_set_threads(threads)
+        if msm_mode is not None:
+            self.lib.oracle_set_msm_mode(msm_mode)
+
+    @property
+    def max_threads(self):
+        return self.lib.oracle_max_threads()
+
+    def msm(self, points, scalars, ncomp=1, mode=1):
+        n = len(scalars) // 32
+        out = ctypes.create_string_buffer(64 * ncomp)
+        self.lib.oc_msm(points, scalars, n, ncomp, mode, out)
+        return out.raw
+
+    def remask(self, enc_g, pk, deck, perm, rho):
+        n = len(perm)
+        arr = (ctypes.c_uint32 * n)(*perm)
+        out = ctypes.create_string_buffer(128 * n)
+        self.lib.oc_remask(enc_g, pk, deck, arr, rho, n, out)
+        return out.raw
+
+    def prove(self, m, n, enc_g, ck_g, ck_h, ghat, pk, deck, deck2, perm, rho, rand):
+        arr = (ctypes.c_uint32 * len(perm))(*perm)
+        out = ctypes.create_string_buffer(self.lib.oc_proof_len(m, n))
+        rc = self.lib.oc_shuffle_prove(m, n, enc_g, ck_g, ck_h, ghat, pk, deck, deck2, arr, rho, rand, out)
+        assert rc == 0
+        return out.raw
+
+    def verify(self, m, n, enc_g, ck_g, ck_h, ghat, pk, deck, deck2, proof):
+        assert len(proof) == self.lib.oc_proof_len(m, n)
+        return self.lib.oc_shuffle_verify(m, n, enc_g, ck_g, ck_h, ghat, pk, deck, deck2, proof)
+
+    def commit(self, n, ck_g, ck_h, values, r):
+        out = ctypes.create_string_buffer(64)
+        self.lib.oc_pedersen_commit(n, ck_g, ck_h, values, len(values) // 32, r, out)
+        return out.raw

@@ -1,0 +1,87 @@
+"""Word-level algorithms of csrc/fq.cuh + ec.cuh (sparse-prime Montgomery reduction, lazy
+bounds, XYZZ formulas) compiled for the HOST with g++ and checked against the oracle.  The
+same source is what nvcc compiles for the device; this catches logic errors without a GPU."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle.py import stark
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P, N = stark.P, stark.N
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "host_shim.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "host", "host_shim.cpp")])
+    return ctypes.CDLL(out)
+
+
+def w(x):
+    return (ctypes.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def rd(buf, n=8):
+    return sum(int(buf[i]) << (32 * i) for i in range(n))
+
+
+def pw(pt):
+    b = stark.point_to_bytes64(pt)
+    return (ctypes.c_uint32 * 16)(*[int.from_bytes(b[4 * i:4 * i + 4], "little") for i in range(16)])
+
+
+def test_fq_mul_lazy_bounds(shim):
+    rnd = random.Random(3)
+    Rinv = pow(1 << 256, -1, P)
+    cases = [(0, 0), (1, 1), (P - 1, P - 1), (P, 2 * P), (5 * P - 1, 6 * P - 1), (15 * P, 2 * P - 1)]
+    cases += [(rnd.randrange(5 * P), rnd.randrange(6 * P)) for _ in range(2000)]
+    out = (ctypes.c_uint32 * 8)()
+    for a, b in cases:
+        shim.h_fq_mul(w(a), w(b), out)
+        r = rd(out)
+        assert r < 2 * P and r % P == a * b * Rinv % P
+
+
+def test_reductions(shim):
+    rnd = random.Random(4)
+    out = (ctypes.c_uint32 * 8)()
+    for v in [0, P, 2 * P, (1 << 256) - 1, 31 * P] + [rnd.randrange(1 << 256) for _ in range(2000)]:
+        shim.h_fq_reduce_weak(w(v), out)
+        r = rd(out)
+        assert r < (1 << 252) and r % P == v % P
+        shim.h_fq_reduce_full(w(v), out)
+        assert rd(out) == v % P
+
+
+def test_inverse(shim):
+    rnd = random.Random(5)
+    out = (ctypes.c_uint32 * 8)()
+    for v in [1, 2, P - 1] + [rnd.randrange(1, P) for _ in range(20)]:
+        shim.h_fq_inv_canonical(w(v), out)
+        assert rd(out) * v % P == 1
+
+
+def test_point_ops(shim):
+    rnd = random.Random(6)
+    pts = [stark.mul(stark.G, rnd.randrange(1, N)) for _ in range(6)]
+    out = (ctypes.c_uint32 * 16)()
+    for a in pts:
+        assert shim.h_on_curve(pw(a)) == 1
+        for b in pts + [a, stark.neg(a), None]:
+            shim.h_point_add(pw(a), pw(b), out)
+            assert bytes(out) == stark.point_to_bytes64(stark.add(a, b))
+    bad = (ctypes.c_uint32 * 16)(*([5] + [0] * 7 + [7] + [0] * 7))
+    assert shim.h_on_curve(bad) == 0
+    for k in [0, 1, 2, N - 1, N, rnd.randrange(1 << 256), rnd.randrange(N)]:
+        shim.h_scalar_mul(pw(pts[0]), w(k), out)
+        assert bytes(out) == stark.point_to_bytes64(stark.mul(pts[0], k))
+    k1, k2 = rnd.randrange(N), rnd.randrange(N)
+    for q in (pts[1], pts[0]):  # distinct points, and the same point (general add -> doubling branch when k1 == k2)
+        for kk2 in (k2, k1, N - k1):
+            shim.h_lincomb2(pw(pts[0]), w(k1), pw(q), w(kk2), out)
+            assert bytes(out) == stark.point_to_bytes64(stark.add(stark.mul(pts[0], k1), stark.mul(q, kk2)))
