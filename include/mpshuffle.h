@@ -81,6 +81,67 @@ int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void* d_scalars,
 uint64_t mp_last_msm_ec_adds(mp_ctx* ctx);
 int32_t mp_last_msm_window(mp_ctx* ctx);
 
+/* ---- shuffle protocol (the reference's hot path) ------------------------------------------
+ * Data layouts.  A deck is N = m*n ElGamal ciphertexts, 128 bytes each (c1 || c2).  Scalars
+ * (masking factors, prover randomness) are 32-byte little-endian canonical integers < group
+ * order.  A permutation is N uint32, out[i] = in[perm[i]] (proof-essentials
+ * `Permutation::permute_array`, reference mod.rs:388).
+ *
+ * Flat proof layout (mp_proof_len(m, n) = (11m+8)*64 + (5n+9)*32 bytes), P = 64-byte point,
+ * F = 32-byte scalar, in the order of SURVEY.md Appendix B:
+ *   c_A[m]P  c_B[m]P                                   shuffle argument first messages
+ *   c_b P                                              product argument
+ *   c_B'[m]P                                           Hadamard argument
+ *   c_A0 P  c_B(m+1) P  c_D[2m+1]P  a[n]F b[n]F r F s F t F      zero argument
+ *   c_d P  c_delta P  c_Delta P  a~[n]F b~[n]F r~ F s~ F         single-value product argument
+ *   c_A0 P  c_B[2m]P  E[2m] (2P each)  a[n]F r F b F s F tau F   multi-exponentiation argument
+ *
+ * Prover randomness: the library never owns an RNG (the trait hands the caller's `rng` to the
+ * prover, reference lib.rs:181-188); the host draws mp_prover_randomness_len(m, n) = 11m + 5n
+ * scalars up front and passes them flat, consumed in this order: shuffle r[m], s[m]; product
+ * s; Hadamard s_2..s_{m-1}; zero a_0[n], b_{m+1}[n], r_0, s_{m+1}, t_k (k = 0..2m, k != m+1);
+ * single-value product d[n], r_d, delta_2..delta_{n-1}, s_1, s_x; multi-exp a_0[n], r_0,
+ * (b_k, s_k, tau_k) for k = 0..2m-1, k != m.
+ *
+ * Fiat-Shamir transcript (host side, ark-marlin FiatShamirRng<Blake2s> seeded with
+ * "Shuffle Proof", reference mod.rs:84,408,436): points are absorbed in the 65-byte ark-ec
+ * encoding x || y || infinity.  Absorb order: "shuffle_argument" g pk G_1..G_n H ghat deck
+ * deck' c_A -> x;  "shuffle_argument_b" c_B -> y, z;  "hadamard_argument" c_b c_B' -> x, y;
+ * "zero_argument" c_A0 c_B(m+1) c_D -> x;  "single_value_product_argument" c_d c_delta c_Delta
+ * -> x;  "multi_exponentiation_argument" c_A0 c_B E -> x.
+ */
+/* Binds DLCards `Parameters` (reference mod.rs:37-61, created by `setup`, mod.rs:105-121) to the
+ * context: ElGamal generator, Pedersen key G_1..G_n and H, extra generator ghat, and (m, n). */
+int32_t mp_ctx_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g /* 64 */,
+                          const uint8_t* ck_g /* n*64 */, const uint8_t* ck_h /* 64 */,
+                          const uint8_t* ghat /* 64 */);
+int32_t mp_params_m(mp_ctx* ctx);
+int32_t mp_params_n(mp_ctx* ctx);
+uint64_t mp_proof_len(int32_t m, int32_t n);
+uint64_t mp_prover_randomness_len(int32_t m, int32_t n);
+/* `MaskedCard::remask` over a permuted deck (reference mod.rs:388-395, remasking.rs:9-22):
+ * out[i] = deck[perm[i]] + (rho_i * g, rho_i * pk). */
+int32_t mp_remask_batch(mp_ctx* ctx, const uint8_t* pk /* 64 */, const uint8_t* deck /* N*128 */,
+                        const uint32_t* perm /* N */, const uint8_t* rho /* N*32 */, uint64_t n_cards,
+                        uint8_t* out_deck /* N*128 */);
+/* `PedersenCommitment::commit` for k vectors of `len` <= n values: out[i] = blinds[i]*H + sum_j
+ * values[i][j]*G_j. */
+int32_t mp_pedersen_commit_batch(mp_ctx* ctx, const uint8_t* values /* k*len*32 */,
+                                 const uint8_t* blinds /* k*32 */, uint64_t k, uint64_t len,
+                                 uint8_t* out /* k*64 */);
+/* `ShuffleArgument::prove` (reference call site mod.rs:409-415). */
+int32_t mp_shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
+                         const uint32_t* perm, const uint8_t* rho, const uint8_t* randomness,
+                         uint8_t* proof_out);
+/* `BarnettSmartProtocol::shuffle_and_remask` (reference lib.rs:181-188, mod.rs:380-418). */
+int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                              const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
+                              uint8_t* proof_out);
+/* `BarnettSmartProtocol::verify_shuffle` (reference lib.rs:191-197, mod.rs:420-443): returns
+ * MP_OK, a positive MP_VERIFY_* code naming the first failing sub-argument, or a negative error. */
+int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
+                          const uint8_t* proof);
+
 /* ---- debug / parity hooks (exercise single device primitives; not used by the protocol) */
 int32_t mp_dbg_fq_mul(mp_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 int32_t mp_dbg_point_add(mp_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out);

@@ -29,6 +29,16 @@ SIGNATURES = {
     "mp_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp_last_msm_ec_adds": (_u64, [_vp]),
     "mp_last_msm_window": (_i32, [_vp]),
+    "mp_ctx_set_params": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp]),
+    "mp_params_m": (_i32, [_vp]),
+    "mp_params_n": (_i32, [_vp]),
+    "mp_proof_len": (_u64, [_i32, _i32]),
+    "mp_prover_randomness_len": (_u64, [_i32, _i32]),
+    "mp_remask_batch": (_i32, [_vp, _cp, _cp, _vp, _cp, _u64, _cp]),
+    "mp_pedersen_commit_batch": (_i32, [_vp, _cp, _cp, _u64, _u64, _cp]),
+    "mp_shuffle_prove": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp]),
+    "mp_shuffle_and_remask": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp]),
+    "mp_shuffle_verify": (_i32, [_vp, _cp, _cp, _cp, _cp]),
     "mp_dbg_fq_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
     "mp_dbg_point_add": (_i32, [_vp, _cp, _cp, _u64, _cp]),
     "mp_dbg_scalar_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
@@ -117,6 +127,55 @@ class Context:
     @property
     def last_msm_window(self):
         return lib.mp_last_msm_window(self.h)
+
+    # --- shuffle protocol: mirrors BarnettSmartProtocol::{setup, shuffle_and_remask,
+    #     verify_shuffle} (reference src/lib.rs:74-78,181-197) at the byte level
+    def set_params(self, m, n, enc_g: bytes, ck_g: bytes, ck_h: bytes, ghat: bytes):
+        assert len(ck_g) == 64 * n
+        check(self.h, lib.mp_ctx_set_params(self.h, m, n, enc_g, ck_g, ck_h, ghat))
+        self.m, self.n = m, n
+
+    def remask(self, pk: bytes, deck: bytes, perm, rho: bytes) -> bytes:
+        n = len(perm)
+        arr = (ctypes.c_uint32 * n)(*perm)
+        out = ctypes.create_string_buffer(128 * n)
+        check(self.h, lib.mp_remask_batch(self.h, pk, deck, arr, rho, n, out))
+        return out.raw
+
+    def commit_batch(self, values: bytes, blinds: bytes, length: int) -> bytes:
+        k = len(blinds) // 32
+        assert len(values) == 32 * k * length
+        out = ctypes.create_string_buffer(64 * k)
+        check(self.h, lib.mp_pedersen_commit_batch(self.h, values, blinds, k, length, out))
+        return out.raw
+
+    def shuffle_prove(self, pk, deck, deck2, perm, rho, rand) -> bytes:
+        arr = (ctypes.c_uint32 * len(perm))(*perm)
+        assert len(rand) == 32 * lib.mp_prover_randomness_len(self.m, self.n)
+        out = ctypes.create_string_buffer(lib.mp_proof_len(self.m, self.n))
+        check(self.h, lib.mp_shuffle_prove(self.h, pk, deck, deck2, arr, rho, rand, out))
+        return out.raw
+
+    def shuffle_and_remask(self, pk, deck, perm, rho, rand):
+        """-> (shuffled deck bytes, proof bytes)"""
+        N = self.m * self.n
+        assert len(perm) == N and len(deck) == 128 * N and len(rho) == 32 * N
+        arr = (ctypes.c_uint32 * N)(*perm)
+        deck2 = ctypes.create_string_buffer(128 * N)
+        proof = ctypes.create_string_buffer(lib.mp_proof_len(self.m, self.n))
+        check(self.h, lib.mp_shuffle_and_remask(self.h, pk, deck, arr, rho, rand, deck2, proof))
+        return deck2.raw, proof.raw
+
+    def verify_shuffle(self, pk, deck, deck2, proof) -> int:
+        """0 = Ok(()), > 0 = CryptoError::ProofVerificationError(status string)."""
+        N = self.m * self.n
+        assert len(deck) == 128 * N and len(deck2) == 128 * N
+        assert len(proof) == lib.mp_proof_len(self.m, self.n)
+        return check(self.h, lib.mp_shuffle_verify(self.h, pk, deck, deck2, proof))
+
+    @staticmethod
+    def status_string(code):
+        return lib.mp_verify_status_string(code).decode()
 
     # --- debug hooks
     def dbg_fq_mul(self, a: bytes, b: bytes) -> bytes:

@@ -9,6 +9,7 @@
 #include "../../include/mpshuffle.h"
 #include "ctx.cuh"
 #include "msm.cuh"
+#include "shuffle.cuh"
 
 using namespace mp;
 
@@ -54,6 +55,7 @@ extern "C" void mp_ctx_destroy(mp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   msm_workspace_destroy(ctx->ws);
+  if (ctx->shuffle) shuffle_state_destroy(ctx->shuffle);
   for (auto& b : ctx->bufs)
     if (b.ptr) cudaFree(b.ptr);
   cudaStreamDestroy(ctx->stream);
@@ -177,6 +179,47 @@ extern "C" int32_t mp_msm_g1_device(mp_ctx* ctx, const void* d_bases, const void
 extern "C" int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
                                     int32_t window_bits, void* d_out) {
   return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// shuffle protocol entry points (bodies in shuffle.cu)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t mp_ctx_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
+                                     const uint8_t* ck_h, const uint8_t* ghat) {
+  return shuffle_set_params(ctx, m, n, enc_g, ck_g, ck_h, ghat);
+}
+extern "C" int32_t mp_params_m(mp_ctx* ctx) { return shuffle_m(ctx); }
+extern "C" int32_t mp_params_n(mp_ctx* ctx) { return shuffle_n(ctx); }
+extern "C" uint64_t mp_proof_len(int32_t m, int32_t n) { return shuffle_proof_len(m, n); }
+extern "C" uint64_t mp_prover_randomness_len(int32_t m, int32_t n) { return shuffle_randomness_len(m, n); }
+extern "C" int32_t mp_remask_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                   const uint8_t* rho, uint64_t n_cards, uint8_t* out_deck) {
+  return shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck);
+}
+extern "C" int32_t mp_pedersen_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k,
+                                            uint64_t len, uint8_t* out) {
+  return shuffle_commit_batch(ctx, values, blinds, k, len, out);
+}
+extern "C" int32_t mp_shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
+                                    const uint32_t* perm, const uint8_t* rho, const uint8_t* randomness,
+                                    uint8_t* proof_out) {
+  return shuffle_prove(ctx, pk, deck, shuffled_deck, perm, rho, randomness, proof_out);
+}
+extern "C" int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                         const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
+                                         uint8_t* proof_out) {
+  if (!ctx || !ctx->shuffle) return ctx ? ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called") : MP_ERR_INVALID_ARG;
+  uint64_t n_cards = (uint64_t)mp_params_m(ctx) * mp_params_n(ctx);
+  int32_t st = shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck);
+  if (st != MP_OK) return st;
+  int launches = ctx->launches;
+  st = shuffle_prove(ctx, pk, deck, out_deck, perm, rho, randomness, proof_out);
+  ctx->launches += launches;
+  return st;
+}
+extern "C" int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
+                                     const uint8_t* proof) {
+  return shuffle_verify(ctx, pk, deck, shuffled_deck, proof);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,189 @@
+// Scalar field F_n of the Stark curve (n = group order, 252 bits), 8 x 32-bit limbs,
+// Montgomery form with R = 2^256, always fully reduced (< n).  This is the field the
+// reference's protocol scalars live in (`C::ScalarField`, ark-ff 0.3 `Fp256`; reference
+// barnett-smart-card-protocol/src/lib.rs:43, Cargo.toml:12).  n has no
+// special shape, so this is generic CIOS Montgomery multiplication; it runs both in device
+// kernels (the O(N) and O(m^2 n) scalar-vector work of the shuffle argument) and on the host
+// (the O(m + n) glue around the Fiat-Shamir transcript).
+//
+// The Montgomery representation is bit-identical to ark-ff's (same R, same limbs viewed as
+// 4 x u64), which matters once: a Fiat-Shamir challenge is the raw ChaCha20 output
+// *interpreted as the Montgomery representation* (SURVEY.md A1), so it is loaded with
+// fr_from_raw_mont and never multiplied by R^2.
+#pragma once
+#include <stdint.h>
+
+#include "fq.cuh"
+
+namespace mp {
+
+struct fr {
+  uint32_t v[8];
+};
+
+#define MP_FR_NINV 0xe8bde631u
+
+MP_HD uint32_t fr_modulus_limb(int i) {
+  switch (i) {
+    case 0: return 0xadc64d2fu;
+    case 1: return 0x1e66a241u;
+    case 2: return 0xcae7b232u;
+    case 3: return 0xb781126du;
+    case 4: return 0xffffffffu;
+    case 5: return 0xffffffffu;
+    case 6: return 0x00000010u;
+    default: return 0x08000000u;
+  }
+}
+
+MP_HD fr fr_zero() {
+  fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+  return r;
+}
+MP_HD fr fr_one() {  // R mod n
+  fr r;
+  r.v[0] = 0xf4fca74fu; r.v[1] = 0x51925a0bu; r.v[2] = 0x6df16beeu; r.v[3] = 0xc75ec4b4u;
+  r.v[4] = 0x00000008u; r.v[5] = 0x00000000u; r.v[6] = 0xfffffdf1u; r.v[7] = 0x07ffffffu;
+  return r;
+}
+MP_HD fr fr_r2() {  // R^2 mod n
+  fr r;
+  r.v[0] = 0xea1c688du; r.v[1] = 0x6021b3f1u; r.v[2] = 0x14ce60b9u; r.v[3] = 0x509cf64du;
+  r.v[4] = 0xf78bbabbu; r.v[5] = 0xbaf0ab4cu; r.v[6] = 0x2333766eu; r.v[7] = 0x07d9e57cu;
+  return r;
+}
+
+MP_HD bool fr_is_zero(const fr& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i];
+  return o == 0;
+}
+MP_HD bool fr_eq(const fr& a, const fr& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+// r = a - n if a >= n else a      (a < 2n)
+MP_HD fr fr_cond_sub(const fr& a, uint32_t extra_carry) {
+  fr d;
+  int64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (int64_t)a.v[i] - (int64_t)fr_modulus_limb(i);
+    d.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  // borrow (c == -1) means a < n, unless the value carried a 257th bit
+  bool keep = (c != 0) && (extra_carry == 0);
+  fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = keep ? a.v[i] : d.v[i];
+  return r;
+}
+
+MP_HD fr fr_add(const fr& a, const fr& b) {
+  fr s;
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + b.v[i];
+    s.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return fr_cond_sub(s, (uint32_t)c);  // n < 2^252: the sum never carries, c == 0
+}
+MP_HD fr fr_sub(const fr& a, const fr& b) {
+  fr d;
+  int64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (int64_t)a.v[i] - (int64_t)b.v[i];
+    d.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  if (c != 0) {  // borrow: add n back
+    uint64_t k = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      k += (uint64_t)d.v[i] + fr_modulus_limb(i);
+      d.v[i] = (uint32_t)k;
+      k >>= 32;
+    }
+  }
+  return d;
+}
+MP_HD fr fr_neg(const fr& a) { return fr_sub(fr_zero(), a); }
+
+// CIOS Montgomery product, output fully reduced
+MP_HD fr fr_mul(const fr& a, const fr& b) {
+  uint32_t t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)t[j] + (uint64_t)a.v[j] * b.v[i];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[8] = (uint32_t)c;
+    t[9] = (uint32_t)(c >> 32);
+    uint32_t q = t[0] * MP_FR_NINV;
+    c = ((uint64_t)t[0] + (uint64_t)q * fr_modulus_limb(0)) >> 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)t[j] + (uint64_t)q * fr_modulus_limb(j);
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[7] = (uint32_t)c;
+    t[8] = t[9] + (uint32_t)(c >> 32);
+  }
+  fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  return fr_cond_sub(r, t[8]);
+}
+MP_HD fr fr_sqr(const fr& a) { return fr_mul(a, a); }
+
+// canonical integer (8 words LE, any 256-bit value) -> Montgomery.  fr_mul tolerates
+// unreduced inputs below 2^256 when the other operand is < n: the result is < 2n before the
+// final conditional subtraction.
+MP_HD fr fr_from_canonical(const uint32_t* w) {
+  fr a;
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.v[i] = w[i];
+  return fr_mul(a, fr_r2());
+}
+MP_HD void fr_to_canonical(const fr& a, uint32_t* w) {
+  fr one_raw = fr_zero();
+  one_raw.v[0] = 1;
+  fr c = fr_mul(a, one_raw);
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = c.v[i];
+}
+MP_HD fr fr_from_u64(uint64_t x) {
+  uint32_t w[8] = {(uint32_t)x, (uint32_t)(x >> 32), 0, 0, 0, 0, 0, 0};
+  return fr_from_canonical(w);
+}
+
+// a^e for a small exponent (square-and-multiply, MSB first)
+MP_HD fr fr_pow_u64(const fr& a, uint64_t e) {
+  fr r = fr_one();
+  for (int i = 63; i >= 0; i--) {
+    r = fr_sqr(r);
+    if ((e >> i) & 1) r = fr_mul(r, a);
+  }
+  return r;
+}
+
+}  // namespace mp

@@ -114,7 +114,17 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restri
     w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
   }
   affine p = affine_from_canonical(w);
-  if (bad != nullptr && !affine_on_curve(p)) atomicExch(bad, 1);
+  if (bad != nullptr) {
+    // coordinates must be canonical (< p) -- a non-canonical alias of a curve point is rejected,
+    // as ark-serialize would -- and the point must satisfy the curve equation
+    fq cx, cy;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { cx.v[k] = w[k]; cy.v[k] = w[8 + k]; }
+    uint32_t bx, by;
+    fq_sub_raw(cx, fq_kp(1), &bx);
+    fq_sub_raw(cy, fq_kp(1), &by);
+    if (!bx || !by || !affine_on_curve(p)) atomicExch(bad, 1);
+  }
   uint4* d = reinterpret_cast<uint4*>(out + i);
   const uint4* ps = reinterpret_cast<const uint4*>(&p);
 #pragma unroll

@@ -1,0 +1,964 @@
+// Host-side driver of the GPU shuffle argument.  See shuffle.cuh for the design notes.
+#include "shuffle.cuh"
+
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/mpshuffle.h"
+#include "ctx.cuh"
+#include "frvec.cuh"
+#include "msm.cuh"
+#include "transcript.hpp"
+
+namespace mp {
+
+// ------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------
+struct ShuffleState {
+  int m = 0, n = 0;
+  std::vector<uint8_t> ck64;  // (n+1) * 64 canonical: h, g_1 .. g_n   (MSM order of a commitment)
+  uint8_t enc_g[64], ghat[64], gsum[64];  // gsum = g_1 + .. + g_n  (com(c,..,c; 0) = c * gsum)
+  affine* d_ck = nullptr;     // device, Montgomery, n + 1 points
+  uint8_t* pinned = nullptr;  // small pinned staging for results
+  size_t pinned_cap = 0;
+  ~ShuffleState() {
+    if (d_ck) cudaFree(d_ck);
+    if (pinned) cudaFreeHost(pinned);
+  }
+};
+void shuffle_state_destroy(ShuffleState* s) { delete s; }
+int32_t shuffle_m(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->m : 0; }
+int32_t shuffle_n(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->n : 0; }
+
+uint64_t shuffle_proof_len(int32_t m, int32_t n) { return (uint64_t)(11 * m + 8) * 64 + (uint64_t)(5 * n + 9) * 32; }
+uint64_t shuffle_randomness_len(int32_t m, int32_t n) { return (uint64_t)11 * m + (uint64_t)5 * n; }
+
+enum Slot {  // ctx->scratch slots owned by this file
+  sSmallUp = mp_ctx::kSlotUser,
+  sG1Canon, sG1Mont, sG1Scal, sG1Out,
+  sCtCanon, sCtMont, sCtScal, sCtOut,
+  sResults, sPartials,
+  sFrA, sFrB, sFrD, sFrBv, sFrXpow, sFrAme, sFrTmp0, sFrTmp1, sFrTmp2, sFrPairs, sFrSmall,
+  sPerm, sRho, sCtOut2, sCanonOut,
+};
+
+#define CK(x)                                                    \
+  do {                                                           \
+    cudaError_t _e = (x);                                        \
+    if (_e != cudaSuccess) return ctx->cuda_fail(_e, #x);        \
+  } while (0)
+#define NEED(ptr)                                                                  \
+  do {                                                                             \
+    if (!(ptr)) return ctx->fail(MP_ERR_CUDA, "device allocation failed (%s)", #ptr); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// host-side scalar helpers
+// ------------------------------------------------------------------------------------------
+static inline fr h_fr(const uint8_t* b) {
+  uint32_t w[8];
+  memcpy(w, b, 32);
+  return fr_from_canonical(w);
+}
+static inline void h_fr_out(const fr& a, uint8_t* b) {
+  uint32_t w[8];
+  fr_to_canonical(a, w);
+  memcpy(b, w, 32);
+}
+static std::vector<fr> h_powers(const fr& x, int count) {  // x^0 .. x^(count-1)
+  std::vector<fr> p((size_t)std::max(count, 0));
+  if (count > 0) p[0] = fr_one();
+  for (int k = 1; k < count; k++) p[k] = fr_mul(p[k - 1], x);
+  return p;
+}
+static std::vector<fr> h_frs(const uint8_t* b, int count) {
+  std::vector<fr> v((size_t)count);
+  for (int i = 0; i < count; i++) v[i] = h_fr(b + 32 * (size_t)i);
+  return v;
+}
+static fr h_dot(const fr* a, const fr* b, int n) {
+  fr acc = fr_zero();
+  for (int i = 0; i < n; i++) acc = fr_add(acc, fr_mul(a[i], b[i]));
+  return acc;
+}
+static FrPow2Table h_pow2_table(const fr& x) {
+  FrPow2Table t;
+  t.p[0] = x;
+  for (int k = 1; k < 32; k++) t.p[k] = fr_sqr(t.p[k - 1]);
+  return t;
+}
+static bool all_zero(const uint8_t* p, size_t n) {
+  for (size_t i = 0; i < n; i++)
+    if (p[i]) return false;
+  return true;
+}
+
+// A batch of small G1 MSM jobs assembled on the host: job = list of (point, scalar) terms.
+struct TermList {
+  std::vector<uint8_t> pts;    // 64 B canonical per term
+  std::vector<uint32_t> scal;  // 8 words canonical per term
+  std::vector<MsmJob> jobs;
+  uint32_t start = 0;
+  uint32_t count() const { return (uint32_t)(scal.size() / 8); }
+  void term(const uint8_t* p64, const fr& s) {
+    pts.insert(pts.end(), p64, p64 + 64);
+    uint32_t w[8];
+    fr_to_canonical(s, w);
+    scal.insert(scal.end(), w, w + 8);
+  }
+  void close_job() {
+    jobs.push_back(MsmJob{start, start, count() - start});
+    start = count();
+  }
+};
+
+// packs small host arrays into one upload
+struct SmallUpload {
+  std::vector<uint8_t> bytes;
+  size_t add(const void* p, size_t len) {
+    size_t off = (bytes.size() + 31) & ~(size_t)31;
+    bytes.resize(off + len);
+    memcpy(bytes.data() + off, p, len);
+    return off;
+  }
+  size_t add_frs(const std::vector<fr>& v) { return add(v.data(), v.size() * sizeof(fr)); }
+};
+
+static uint8_t* pinned(ShuffleState* S, size_t bytes) {
+  if (S->pinned_cap < bytes) {
+    if (S->pinned) cudaFreeHost(S->pinned);
+    S->pinned = nullptr;
+    S->pinned_cap = 0;
+    size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+    if (cudaMallocHost(&S->pinned, want) != cudaSuccess) return nullptr;
+    S->pinned_cap = want;
+  }
+  return S->pinned;
+}
+
+// ------------------------------------------------------------------------------------------
+// small device kernels local to the protocol
+// ------------------------------------------------------------------------------------------
+// out[k*(n+1)] = blind[k]; out[k*(n+1) + 1 + j] = rows[k*stride + j]  (canonical), j < len; the
+// remaining n - len slots of a short row are zero.
+__global__ void __launch_bounds__(256) k_commit_scalars(const fr* __restrict__ rows, uint64_t stride,
+                                                        const fr* __restrict__ blinds, int count, int n, int len,
+                                                        uint32_t* __restrict__ out) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint64_t)count * (n + 1)) return;
+  uint64_t k = g / (n + 1);
+  int j = (int)(g % (n + 1));
+  fr v;
+  if (j == 0) v = blinds[k];
+  else if (j - 1 < len) v = rows[k * stride + (j - 1)];
+  else v = fr_zero();
+  uint32_t w[8];
+  fr_to_canonical(v, w);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[g * 8 + i] = w[i];
+}
+
+__global__ void __launch_bounds__(64) k_xyzz_add_pairs(const xyzz* __restrict__ a, const xyzz* __restrict__ b,
+                                                       xyzz* __restrict__ out, int count) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= count) return;
+  xyzz x = a[g], y = b[g];
+  xyzz_add(x, y);
+  out[g] = x;
+}
+
+// Remask (reference remasking.rs:9-22 -> masking.rs:10-20):  thread (i, comp) computes
+// out[i].comp = deck[perm[i]].comp + rho_i * base_comp with base = (g, pk).
+__global__ void __launch_bounds__(128) k_remask(const uint32_t* __restrict__ deck_canon, const uint32_t* __restrict__ perm,
+                                                const uint32_t* __restrict__ rho_canon, const uint32_t* __restrict__ bases_canon,
+                                                uint64_t N, uint32_t* __restrict__ out_canon, int* __restrict__ bad) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 2 * N) return;
+  uint64_t i = g >> 1;
+  int comp = (int)(g & 1);
+  affine base = affine_from_canonical(bases_canon + 16 * comp);
+  uint64_t src = perm[i];
+  if (src >= N) { atomicExch(bad, 2); return; }
+  affine card = affine_from_canonical(deck_canon + (src * 2 + comp) * 16);
+  if (!affine_on_curve(card) || !affine_on_curve(base)) atomicExch(bad, 1);
+  uint32_t k[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) k[w] = rho_canon[i * 8 + w];
+  xyzz acc = xyzz_identity();
+  for (int bit = 255; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((k[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, base);
+  }
+  xyzz_madd(acc, card);
+  affine r = xyzz_to_affine(acc);
+  uint32_t w[16];
+  if (affine_is_identity(r)) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) w[q] = 0;
+  } else {
+    affine_to_canonical(r, w);
+  }
+#pragma unroll
+  for (int q = 0; q < 16; q++) out_canon[g * 16 + q] = w[q];
+}
+
+// ------------------------------------------------------------------------------------------
+// set-up
+// ------------------------------------------------------------------------------------------
+static int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad) {
+  uint32_t T = tl.count();
+  int J = (int)tl.jobs.size();
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)T * 64 + 64);
+  affine* d_mont = (affine*)ctx->scratch(sG1Mont, (size_t)T * sizeof(affine) + 64);
+  uint32_t* d_scal = (uint32_t*)ctx->scratch(sG1Scal, (size_t)T * 32 + 64);
+  xyzz* d_out = (xyzz*)ctx->scratch(sG1Out, (size_t)J * sizeof(xyzz) + 64);
+  NEED(d_canon); NEED(d_mont); NEED(d_scal); NEED(d_out);
+  CK(cudaMemcpyAsync(d_canon, tl.pts.data(), (size_t)T * 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_scal, tl.scal.data(), (size_t)T * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(points_to_mont((const uint32_t*)d_canon, d_mont, T, d_bad, ctx->stream));
+  ctx->launches += 1;
+  int c = msm_pick_window(J ? T / J : 1);
+  CK(msm_run(ctx->ws, d_scal, T, d_mont, 1, tl.jobs.data(), J, c, d_out, ctx->stream));
+  ctx->launches += msm_last_launches(ctx->ws);
+  *d_out_ret = d_out;
+  return MP_OK;
+}
+
+int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
+                           const uint8_t* ck_h, const uint8_t* ghat) {
+  if (!ctx || !enc_g || !ck_g || !ck_h || !ghat) return MP_ERR_INVALID_ARG;
+  if (m < 2 || n < 2 || (uint64_t)m * n >= (1ull << 28))
+    return ctx->fail(MP_ERR_INVALID_ARG, "shuffle parameters need m >= 2, n >= 2, m*n < 2^28 (got m=%d n=%d)", m, n);
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  if (!ctx->shuffle) ctx->shuffle = new ShuffleState();
+  ShuffleState* S = ctx->shuffle;
+  S->m = 0;
+  S->n = 0;
+  S->ck64.resize((size_t)(n + 1) * 64);
+  memcpy(S->ck64.data(), ck_h, 64);
+  memcpy(S->ck64.data() + 64, ck_g, (size_t)n * 64);
+  memcpy(S->enc_g, enc_g, 64);
+  memcpy(S->ghat, ghat, 64);
+  if (S->d_ck) cudaFree(S->d_ck);
+  S->d_ck = nullptr;
+  CK(cudaMalloc(&S->d_ck, sizeof(affine) * (size_t)(n + 1)));
+  // validate every parameter point and compute gsum = sum g_j with one MSM of unit scalars
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_bad);
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  TermList tl;
+  for (int j = 1; j <= n; j++) tl.term(S->ck64.data() + 64 * (size_t)j, fr_one());
+  tl.close_job();
+  tl.term(ck_h, fr_one()); tl.term(enc_g, fr_one()); tl.term(ghat, fr_one());  // validation only
+  tl.close_job();
+  xyzz* d_out = nullptr;
+  int32_t st = run_g1_jobs(ctx, tl, &d_out, d_bad);
+  if (st != MP_OK) return st;
+  uint8_t* d_res = (uint8_t*)ctx->scratch(sCanonOut, 64 + 64);
+  NEED(d_res);
+  CK(xyzz_to_canonical(d_out, (uint32_t*)d_res, 1, ctx->stream));
+  ctx->launches += 1;
+  // Montgomery copy of the commit key for the prover's commitment jobs
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)(n + 1) * 64);
+  NEED(d_canon);
+  CK(cudaMemcpyAsync(d_canon, S->ck64.data(), (size_t)(n + 1) * 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(points_to_mont((const uint32_t*)d_canon, S->d_ck, (uint64_t)n + 1, d_bad, ctx->stream));
+  ctx->launches += 1;
+  int bad = 0;
+  CK(cudaMemcpyAsync(S->gsum, d_res, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a parameter point is not a canonical point of the Stark curve");
+  S->m = m;
+  S->n = n;
+  return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// proof layout (include/mpshuffle.h)
+// ------------------------------------------------------------------------------------------
+struct Layout {
+  size_t cA, cB, cb, hB, zpts, za, zb, zr, zs, zt, svpts, sva, svb, svr, svs, mepts, meE, mea, mer, meb, mes, metau, end;
+  Layout(int m, int n) {
+    const size_t P = 64, F = 32;
+    cA = 0; cB = cA + m * P; cb = cB + m * P; hB = cb + P; zpts = hB + m * P;
+    za = zpts + (2 * (size_t)m + 3) * P; zb = za + n * F; zr = zb + n * F; zs = zr + F; zt = zs + F;
+    svpts = zt + F; sva = svpts + 3 * P; svb = sva + n * F; svr = svb + n * F; svs = svr + F;
+    mepts = svs + F; meE = mepts + (2 * (size_t)m + 1) * P; mea = meE + 4 * (size_t)m * P;
+    mer = mea + n * F; meb = mer + F; mes = meb + F; metau = mes + F; end = metau + F;
+  }
+};
+
+static void absorb_statement(Transcript& fs, const ShuffleState* S, const uint8_t* pk, const uint8_t* deck,
+                             const uint8_t* deck2, size_t N, const uint8_t* cA) {
+  fs.begin();
+  fs.feed_label("shuffle_argument");
+  fs.feed_points64(S->enc_g, 1);
+  fs.feed_points64(pk, 1);
+  fs.feed_points64(S->ck64.data() + 64, (size_t)S->n);
+  fs.feed_points64(S->ck64.data(), 1);
+  fs.feed_points64(S->ghat, 1);
+  fs.feed_points64(deck, 2 * N);
+  fs.feed_points64(deck2, 2 * N);
+  fs.feed_points64(cA, (size_t)S->m);
+  fs.end();
+}
+
+// ------------------------------------------------------------------------------------------
+// verify
+// ------------------------------------------------------------------------------------------
+int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
+                       const uint8_t* proof) {
+  if (!ctx || !pk || !deck || !deck2 || !proof) return MP_ERR_INVALID_ARG;
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int m = S->m, n = S->n;
+  const size_t N = (size_t)m * n;
+  const Layout L(m, n);
+  const uint8_t* ck_h = S->ck64.data();
+  auto ck_g = [&](int j) { return S->ck64.data() + 64 * (size_t)(j + 1); };  // g_{j+1}, j = 0..n-1
+  auto P = [&](size_t off, size_t i) { return proof + off + 64 * i; };
+
+  // ---- 1. start moving the decks (independent of every challenge)
+  const size_t T = 2 * N + 2 * (size_t)m + 3;  // CT arena: deck | E_m | deck2 | E_0..E_{2m-1} | (g,pk) | (O,ghat)
+  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, T * 128);
+  affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, T * 2 * sizeof(affine));
+  uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, T * 32);
+  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 4 * sizeof(xyzz));
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_bad);
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon, deck, N * 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon + N * 128, proof + L.meE + 128 * (size_t)m, 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon + (N + 1) * 128, deck2, N * 128, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    std::vector<uint8_t> tail((2 * (size_t)m + 2) * 128, 0);
+    memcpy(tail.data(), proof + L.meE, 2 * (size_t)m * 128);
+    uint8_t* q = tail.data() + 2 * (size_t)m * 128;
+    memcpy(q, S->enc_g, 64);
+    memcpy(q + 64, pk, 64);
+    memcpy(q + 192, S->ghat, 64);  // (identity, ghat)
+    CK(cudaMemcpyAsync(d_ct_canon + (2 * N + 1) * 128, tail.data(), tail.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, T * 2, d_bad, ctx->stream));
+  ctx->launches += 1;
+
+  // ---- 2. transcript: every challenge derives from statement + proof bytes
+  Transcript fs;
+  absorb_statement(fs, S, pk, deck, deck2, N, proof + L.cA);
+  const fr x = fs.challenge();
+  fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof + L.cB, m); fs.end();
+  const fr y = fs.challenge();
+  const fr z = fs.challenge();
+  fs.begin(); fs.feed_label("hadamard_argument"); fs.feed_points64(proof + L.cb, 1); fs.feed_points64(proof + L.hB, m); fs.end();
+  const fr xh = fs.challenge();
+  const fr yh = fs.challenge();
+  fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof + L.zpts, 2 * (size_t)m + 3); fs.end();
+  const fr xz = fs.challenge();
+  fs.begin(); fs.feed_label("single_value_product_argument"); fs.feed_points64(proof + L.svpts, 3); fs.end();
+  const fr xs = fs.challenge();
+  fs.begin(); fs.feed_label("multi_exponentiation_argument");
+  fs.feed_points64(proof + L.mepts, 2 * (size_t)m + 1); fs.feed_points64(proof + L.meE, 4 * (size_t)m); fs.end();
+  const fr xm = fs.challenge();
+
+  // ---- 3. O(N) scalar vectors on the device
+  const std::vector<fr> me_a = h_frs(proof + L.mea, n);
+  const fr me_r = h_fr(proof + L.mer), me_b = h_fr(proof + L.meb), me_s = h_fr(proof + L.mes), me_tau = h_fr(proof + L.metau);
+  const std::vector<fr> xmp = h_powers(xm, 2 * m);
+  SmallUpload up;
+  fr yz[2] = {y, z};
+  size_t o_yz = up.add(yz, sizeof yz);
+  std::vector<fr> coef((size_t)m);
+  for (int i = 1; i <= m; i++) coef[i - 1] = fr_neg(xmp[m - i]);
+  size_t o_coef = up.add_frs(coef);
+  size_t o_mea = up.add_frs(me_a);
+  std::vector<uint32_t> tailsc((2 * (size_t)m + 2) * 8);
+  for (int k = 0; k < 2 * m; k++) fr_to_canonical(xmp[k], &tailsc[8 * (size_t)k]);
+  fr_to_canonical(fr_neg(me_tau), &tailsc[8 * (size_t)(2 * m)]);
+  fr_to_canonical(fr_neg(me_b), &tailsc[8 * (size_t)(2 * m + 1)]);
+  uint32_t minus_one[8];
+  fr_to_canonical(fr_neg(fr_one()), minus_one);
+  uint8_t* d_small = (uint8_t*)ctx->scratch(sSmallUp, up.bytes.size() + 64);
+  fr* d_partials = (fr*)ctx->scratch(sPartials, sizeof(fr) * (fr_powers_blocks(N) + 2));
+  NEED(d_small); NEED(d_partials);
+  CK(cudaMemcpyAsync(d_small, up.bytes.data(), up.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_scal + N * 8, minus_one, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_scal + (2 * N + 1) * 8, tailsc.data(), tailsc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  fr* d_bstar = d_partials + fr_powers_blocks(N);
+  CK(fr_powers(h_pow2_table(x), N, d_ct_scal, nullptr, (const fr*)(d_small + o_yz), d_partials, d_bstar, ctx->stream));
+  CK(fr_outer_canonical((const fr*)(d_small + o_coef), (const fr*)(d_small + o_mea), m, n, d_ct_scal + (N + 1) * 8, ctx->stream));
+  ctx->launches += 3;
+
+  // ---- 4. the two ciphertext checks (K1): 4 N-term G1 MSMs in one batched launch sequence
+  //   job 0:  sum x^i C_i - E_m                                        == O   (Chat == E_m)
+  //   job 1:  sum x^k E_k - Enc(b*ghat; tau) - sum (x^{m-i} a_j) C'_ij  == O
+  MsmJob ct_jobs[2] = {{0, 0, (uint32_t)(N + 1)}, {(uint32_t)(N + 1), (uint32_t)(N + 1), (uint32_t)(N + 2 * m + 2)}};
+  CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N), d_ct_out, ctx->stream));
+  ctx->launches += msm_last_launches(ctx->ws);
+
+  // ---- 5. the commitment-space checks as small G1 jobs (host builds O(m + n) scalars)
+  const std::vector<fr> xzp = h_powers(xz, 2 * m + 1);
+  const std::vector<fr> xhp = h_powers(xh, m);
+  const std::vector<fr> z_a = h_frs(proof + L.za, n), z_b = h_frs(proof + L.zb, n);
+  const fr z_r = h_fr(proof + L.zr), z_s = h_fr(proof + L.zs), z_t = h_fr(proof + L.zt);
+  const std::vector<fr> sv_a = h_frs(proof + L.sva, n), sv_b = h_frs(proof + L.svb, n);
+  const fr sv_r = h_fr(proof + L.svr), sv_s = h_fr(proof + L.svs);
+  const fr one = fr_one();
+  TermList tl;
+  // H1: hB[0] == c_D[0] = y*c_A[0] + c_B[0] - z*gsum
+  tl.term(P(L.cA, 0), y); tl.term(P(L.cB, 0), one); tl.term(S->gsum, fr_neg(z)); tl.term(P(L.hB, 0), fr_neg(one));
+  tl.close_job();
+  // Z1: c_A0 + sum_{i=1}^{m-1} xz^i c_D[i] + xz^m (-gsum) - com(a; r)
+  {
+    fr s1 = fr_zero();
+    tl.term(P(L.zpts, 0), one);
+    for (int i = 1; i < m; i++) {
+      tl.term(P(L.cA, i), fr_mul(xzp[i], y));
+      tl.term(P(L.cB, i), xzp[i]);
+      s1 = fr_add(s1, xzp[i]);
+    }
+    tl.term(S->gsum, fr_neg(fr_add(fr_mul(z, s1), xzp[m])));
+    tl.term(ck_h, fr_neg(z_r));
+    for (int j = 0; j < n; j++) tl.term(ck_g(j), fr_neg(z_a[j]));
+    tl.close_job();
+  }
+  // Z2: sum_{t=0}^{m-2} xz^{m-t} xh^{t+1} hB[t] + xz * sum_{i=1}^{m-1} xh^i hB[i] + c_Bm1 - com(b; s)
+  {
+    for (int t = 0; t < m; t++) {
+      fr c = fr_zero();
+      if (t <= m - 2) c = fr_add(c, fr_mul(xzp[m - t], fr_mul(xhp[t], xh)));
+      if (t >= 1) c = fr_add(c, fr_mul(xzp[1], xhp[t]));
+      tl.term(P(L.hB, t), c);
+    }
+    tl.term(P(L.zpts, 1), one);
+    tl.term(ck_h, fr_neg(z_s));
+    for (int j = 0; j < n; j++) tl.term(ck_g(j), fr_neg(z_b[j]));
+    tl.close_job();
+  }
+  // Z3: sum xz^k c_D_k - com(a * b; t)
+  {
+    fr ab = fr_zero(), yp = one;
+    for (int j = 0; j < n; j++) {
+      yp = fr_mul(yp, yh);
+      ab = fr_add(ab, fr_mul(fr_mul(z_a[j], z_b[j]), yp));
+    }
+    for (int k = 0; k <= 2 * m; k++) tl.term(P(L.zpts, 2 + k), xzp[k]);
+    tl.term(ck_h, fr_neg(z_t));
+    tl.term(ck_g(0), fr_neg(ab));
+    tl.close_job();
+  }
+  // S1: xs*c_b + c_d - com(a~; r~)
+  tl.term(P(L.cb, 0), xs); tl.term(P(L.svpts, 0), one); tl.term(ck_h, fr_neg(sv_r));
+  for (int j = 0; j < n; j++) tl.term(ck_g(j), fr_neg(sv_a[j]));
+  tl.close_job();
+  // S2: xs*c_Delta + c_delta - com((xs*b~_{i+1} - b~_i*a~_{i+1})_i; s~)
+  tl.term(P(L.svpts, 2), xs); tl.term(P(L.svpts, 1), one); tl.term(ck_h, fr_neg(sv_s));
+  for (int i = 0; i + 1 < n; i++)
+    tl.term(ck_g(i), fr_neg(fr_sub(fr_mul(xs, sv_b[i + 1]), fr_mul(sv_b[i], sv_a[i + 1]))));
+  tl.close_job();
+  // M1: c_A0 + sum_{j=1}^{m} xm^j c_B[j-1] - com(a; r)
+  tl.term(P(L.mepts, 0), one);
+  for (int j = 1; j <= m; j++) tl.term(P(L.cB, j - 1), xmp[j]);
+  tl.term(ck_h, fr_neg(me_r));
+  for (int j = 0; j < n; j++) tl.term(ck_g(j), fr_neg(me_a[j]));
+  tl.close_job();
+  // M2: sum xm^k c_B_k - com(b; s)
+  for (int k = 0; k < 2 * m; k++) tl.term(P(L.mepts, 1 + k), xmp[k]);
+  tl.term(ck_h, fr_neg(me_s));
+  tl.term(ck_g(0), fr_neg(me_b));
+  tl.close_job();
+  const int J = (int)tl.jobs.size();  // 8
+  xyzz* d_g1_out = nullptr;
+  int32_t st = run_g1_jobs(ctx, tl, &d_g1_out, d_bad);
+  if (st != MP_OK) return st;
+
+  // ---- 6. collect: [bstar | G1 results | CT results | bad flag]
+  const size_t res_bytes = sizeof(fr) + (size_t)(J + 4) * sizeof(xyzz) + 16;
+  uint8_t* h_res = pinned(S, res_bytes);
+  if (!h_res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  CK(cudaMemcpyAsync(h_res, d_bstar, sizeof(fr), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_res + sizeof(fr), d_g1_out, (size_t)J * sizeof(xyzz), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_res + sizeof(fr) + (size_t)J * sizeof(xyzz), d_ct_out, 4 * sizeof(xyzz), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_res + sizeof(fr) + (size_t)(J + 4) * sizeof(xyzz), d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int bad;
+  memcpy(&bad, h_res + sizeof(fr) + (size_t)(J + 4) * sizeof(xyzz), sizeof(int));
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck or proof point is not a canonical point of the Stark curve");
+  fr bstar;
+  memcpy(&bstar, h_res, sizeof(fr));
+  const xyzz* res = reinterpret_cast<const xyzz*>(h_res + sizeof(fr));
+  auto is_id = [&](int j) { return xyzz_is_identity(res[j]); };
+
+  // ---- 7. verdict, in the order the reference reaches the checks (product argument first:
+  //         Hadamard -> zero -> single-value product; then multi-exponentiation)
+  if (!is_id(0) || memcmp(P(L.hB, m - 1), P(L.cb, 0), 64) != 0) return MP_VERIFY_HADAMARD;
+  if (!all_zero(P(L.zpts, 2 + m + 1), 64) || !is_id(1) || !is_id(2) || !is_id(3)) return MP_VERIFY_ZERO;
+  if (!is_id(4) || !is_id(5) || !fr_eq(sv_b[0], sv_a[0]) || !fr_eq(sv_b[n - 1], fr_mul(xs, bstar))) return MP_VERIFY_SVP;
+  if (!all_zero(P(L.mepts, 1 + m), 64) || !is_id(J) || !is_id(J + 1) || !is_id(6) || !is_id(7) || !is_id(J + 2) || !is_id(J + 3))
+    return MP_VERIFY_MULTIEXP;
+  return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// remask + commitments (stand-alone entry points; the prover reuses the pieces)
+// ------------------------------------------------------------------------------------------
+int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm, const uint8_t* rho,
+                       uint64_t N, uint8_t* out_deck) {
+  if (!ctx || !pk || (N && (!deck || !perm || !rho || !out_deck))) return MP_ERR_INVALID_ARG;
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  if (N == 0) return MP_OK;
+  if (N >= (1ull << 28)) return ctx->fail(MP_ERR_INVALID_ARG, "deck too large");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  uint8_t* d_deck = (uint8_t*)ctx->scratch(sCtCanon, N * 128);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(sCtMont, N * 128);
+  uint32_t* d_perm = (uint32_t*)ctx->scratch(sPerm, N * 4);
+  uint8_t* d_rho = (uint8_t*)ctx->scratch(sRho, N * 32);
+  uint8_t* d_bases = (uint8_t*)ctx->scratch(sSmallUp, 256);
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_deck); NEED(d_out); NEED(d_perm); NEED(d_rho); NEED(d_bases); NEED(d_bad);
+  uint8_t bases[128];
+  memcpy(bases, S->enc_g, 64);
+  memcpy(bases + 64, pk, 64);
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  CK(cudaMemcpyAsync(d_deck, deck, N * 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_perm, perm, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_rho, rho, N * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_bases, bases, 128, cudaMemcpyHostToDevice, ctx->stream));
+  k_remask<<<(unsigned)((2 * N + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t*)d_deck, d_perm, (const uint32_t*)d_rho,
+                                                                     (const uint32_t*)d_bases, N, (uint32_t*)d_out, d_bad);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  int bad = 0;
+  CK(cudaMemcpyAsync(out_deck, d_out, N * 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad == 2) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry out of range");
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
+  return MP_OK;
+}
+
+// commitments of `count` rows that live on the device (Montgomery), result XYZZ on the device
+static int32_t commit_rows_device(mp_ctx* ctx, const fr* d_rows, uint64_t stride, const fr* d_blinds, int count, int len,
+                                  uint32_t* d_scal, xyzz* d_out) {
+  ShuffleState* S = ctx->shuffle;
+  const int n = S->n;
+  uint64_t total = (uint64_t)count * (n + 1);
+  k_commit_scalars<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_rows, stride, d_blinds, count, n, len, d_scal);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  std::vector<MsmJob> jobs((size_t)count);
+  for (int k = 0; k < count; k++) jobs[k] = MsmJob{(uint32_t)(k * (n + 1)), 0, (uint32_t)(n + 1)};
+  CK(msm_run(ctx->ws, d_scal, total, S->d_ck, 1, jobs.data(), count, msm_pick_window(n + 1), d_out, ctx->stream));
+  ctx->launches += msm_last_launches(ctx->ws);
+  return MP_OK;
+}
+
+int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k, uint64_t len,
+                             uint8_t* out) {
+  if (!ctx || (k && (!blinds || !out)) || (k && len && !values)) return MP_ERR_INVALID_ARG;
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  if (len > (uint64_t)S->n) return ctx->fail(MP_ERR_INVALID_ARG, "vector length %llu exceeds the commit key length %d",
+                                             (unsigned long long)len, S->n);
+  if (k == 0) return MP_OK;
+  if (k * (S->n + 1) >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "too many commitments in one batch");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  uint32_t* d_in = (uint32_t*)ctx->scratch(sFrTmp0, (k * len + k) * 32 + 64);
+  fr* d_rows = (fr*)ctx->scratch(sFrTmp1, (k * len + k) * 32 + 64);
+  uint32_t* d_scal = (uint32_t*)ctx->scratch(sG1Scal, k * (S->n + 1) * 32);
+  xyzz* d_res = (xyzz*)ctx->scratch(sG1Out, k * sizeof(xyzz));
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, k * 64);
+  NEED(d_in); NEED(d_rows); NEED(d_scal); NEED(d_res); NEED(d_canon);
+  if (len) CK(cudaMemcpyAsync(d_in, values, k * len * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in + k * len * 8, blinds, k * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(fr_from_canonical_vec(d_in, d_rows, k * len + k, ctx->stream));
+  ctx->launches += 1;
+  int32_t st = commit_rows_device(ctx, d_rows, len, d_rows + k * len, (int)k, (int)len, d_scal, d_res);
+  if (st != MP_OK) return st;
+  CK(xyzz_to_canonical(d_res, (uint32_t*)d_canon, k, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(out, d_canon, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// prove
+// ------------------------------------------------------------------------------------------
+struct RandCursor {
+  const uint8_t* p;
+  size_t i = 0;
+  fr one() { return h_fr(p + 32 * (i++)); }
+  std::vector<fr> vec(int k) {
+    std::vector<fr> v((size_t)k);
+    for (int j = 0; j < k; j++) v[j] = one();
+    return v;
+  }
+};
+
+int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint32_t* perm,
+                      const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out) {
+  if (!ctx || !pk || !deck || !deck2 || !perm || !rho || !rand || !proof_out) return MP_ERR_INVALID_ARG;
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int m = S->m, n = S->n;
+  const size_t N = (size_t)m * n;
+  const Layout L(m, n);
+  for (size_t i = 0; i < N; i++)
+    if (perm[i] >= N) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry %zu out of range", i);
+  RandCursor rc{rand};
+  cudaStream_t st = ctx->stream;
+  int32_t rcode;
+
+  // ---- device buffers
+  const size_t rows_max = (size_t)std::max(2 * m + 1, m + 3);
+  const size_t T2 = N + 2;  // CT arena: deck2 | (g, pk) | (O, ghat)
+  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, T2 * 128);
+  affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, T2 * 2 * sizeof(affine));
+  uint32_t* d_perm = (uint32_t*)ctx->scratch(sPerm, N * 4);
+  fr* d_rho = (fr*)ctx->scratch(sRho, N * 32 + 64);
+  fr* d_a = (fr*)ctx->scratch(sFrA, N * sizeof(fr));
+  fr* d_Ame = (fr*)ctx->scratch(sFrAme, (N + n) * sizeof(fr));        // rows: a0_me | b chunk 1..m
+  fr* d_b = d_Ame + n;
+  fr* d_Az = (fr*)ctx->scratch(sFrD, (N + n) * sizeof(fr));           // zero-arg rows: a0_z | d rows 1..m-1 | -1
+  fr* d_d0 = (fr*)ctx->scratch(sFrTmp2, N * sizeof(fr));              // d (all m rows)
+  fr* d_Bv = (fr*)ctx->scratch(sFrBv, N * sizeof(fr));
+  fr* d_Bz = (fr*)ctx->scratch(sFrB, (N + n) * sizeof(fr));           // zero-arg rows: x^i Bv[i-1] | dlast | b_{m+1}
+  fr* d_xpow = (fr*)ctx->scratch(sFrXpow, N * sizeof(fr));
+  fr* d_pairs = (fr*)ctx->scratch(sFrPairs, (size_t)(m + 1) * (m + 1) * sizeof(fr) + (4 * (size_t)m + 8) * sizeof(fr));
+  fr* d_partials = (fr*)ctx->scratch(sPartials, sizeof(fr) * (std::max(fr_powers_blocks(N), fr_reduce_blocks(N)) + 4));
+  fr* d_rows = (fr*)ctx->scratch(sFrTmp0, (4 * (size_t)n + 64) * sizeof(fr));  // svp rows (3 x n) + response vectors
+  uint32_t* d_g1_scal = (uint32_t*)ctx->scratch(sG1Scal, (rows_max * (n + 1) + 8 * (size_t)m + 64) * 32);
+  xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, (4 * (size_t)m + 16) * sizeof(xyzz));
+  uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, (N + n + 4 * (size_t)m + 8) * 32);
+  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 8 * (size_t)m * sizeof(xyzz));
+  xyzz* d_ct_out2 = (xyzz*)ctx->scratch(sCtOut2, 4 * (size_t)m * sizeof(xyzz));
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, (8 * (size_t)m + 16) * 64);
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_perm); NEED(d_rho); NEED(d_a); NEED(d_Ame); NEED(d_Az); NEED(d_d0);
+  NEED(d_Bv); NEED(d_Bz); NEED(d_xpow); NEED(d_pairs); NEED(d_partials); NEED(d_rows); NEED(d_g1_scal); NEED(d_g1_out);
+  NEED(d_ct_scal); NEED(d_ct_out); NEED(d_ct_out2); NEED(d_canon); NEED(d_bad);
+  const size_t pin_bytes = (8 * (size_t)m + 16) * 64 + (4 * (size_t)n + 4 * (size_t)m + 64) * 32;
+  uint8_t* h_pin = pinned(S, pin_bytes);
+  if (!h_pin) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+
+  // ---- uploads that do not depend on any challenge
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  CK(cudaMemcpyAsync(d_ct_canon, deck2, N * 128, cudaMemcpyHostToDevice, st));
+  {
+    uint8_t tail[256];
+    memset(tail, 0, sizeof tail);
+    memcpy(tail, S->enc_g, 64);
+    memcpy(tail + 64, pk, 64);
+    memcpy(tail + 192, S->ghat, 64);
+    CK(cudaMemcpyAsync(d_ct_canon + N * 128, tail, 256, cudaMemcpyHostToDevice, st));
+  }
+  CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, T2 * 2, d_bad, st));
+  CK(cudaMemcpyAsync(d_perm, perm, N * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_xpow, rho, N * 32, cudaMemcpyHostToDevice, st));  // staging: canonical rho
+  CK(fr_from_canonical_vec((const uint32_t*)d_xpow, d_rho, N, st));
+  ctx->launches += 2;
+
+  // ---- round A: c_A[k] = com(chunk_k(a); r_k),  a_i = perm[i] + 1
+  const std::vector<fr> r = rc.vec(m), s = rc.vec(m);
+  fr* d_blind = d_pairs;  // small scratch for blinding factors (<= 4m + 8 elements at the end of d_pairs)
+  d_blind = d_pairs + (size_t)(m + 1) * (m + 1);
+  CK(fr_perm_vectors(d_perm, nullptr, N, d_a, nullptr, st));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(d_blind, r.data(), sizeof(fr) * m, cudaMemcpyHostToDevice, st));
+  if ((rcode = commit_rows_device(ctx, d_a, n, d_blind, m, n, d_g1_scal, d_g1_out)) != MP_OK) return rcode;
+  CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, m, st));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(proof_out + L.cA, d_canon, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  Transcript fs;
+  absorb_statement(fs, S, pk, deck, deck2, N, proof_out + L.cA);
+  const fr x = fs.challenge();
+
+  // ---- round B: b_i = x^{perm[i]+1}, c_B[k] = com(chunk_k(b); s_k)
+  CK(fr_powers(h_pow2_table(x), N, nullptr, d_xpow, nullptr, d_partials, nullptr, st));
+  CK(fr_perm_vectors(d_perm, d_xpow, N, nullptr, d_b, st));
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(d_blind, s.data(), sizeof(fr) * m, cudaMemcpyHostToDevice, st));
+  if ((rcode = commit_rows_device(ctx, d_b, n, d_blind, m, n, d_g1_scal, d_g1_out)) != MP_OK) return rcode;
+  CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, m, st));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(proof_out + L.cB, d_canon, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof_out + L.cB, m); fs.end();
+  const fr y = fs.challenge();
+  const fr z = fs.challenge();
+
+  // ---- round C: everything whose commitments depend only on (x, y, z)
+  // C.1  d = y*a + b - z;  column prefix products Bv;  rho* = -sum rho_i b_i
+  std::vector<fr> t((size_t)m);
+  for (int k = 0; k < m; k++) t[k] = fr_add(fr_mul(y, r[k]), s[k]);
+  {
+    fr yz[2] = {y, z};
+    CK(cudaMemcpyAsync(d_blind, yz, sizeof yz, cudaMemcpyHostToDevice, st));
+    CK(fr_affine_comb(d_a, d_b, d_blind, N, d_d0, st));
+    CK(fr_column_prefix_products(d_d0, m, n, d_Bv, st));
+    CK(fr_dot(d_rho, d_b, N, d_partials, d_partials + fr_reduce_blocks(N), st));
+    ctx->launches += 4;
+  }
+  // bring the last product row (the SVP witness) and rho* to the host
+  fr* h_col = reinterpret_cast<fr*>(h_pin);
+  CK(cudaMemcpyAsync(h_col, d_Bv + (size_t)(m - 1) * n, sizeof(fr) * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_col + n, d_partials + fr_reduce_blocks(N), sizeof(fr), cudaMemcpyDeviceToHost, st));
+
+  // C.2  multi-exponentiation first message (B.5'): a0, r0, (b_k, s_k, tau_k); the 2m diagonal
+  //      ciphertext MSMs E_k (K2) are the prover's dominant cost and only need x.
+  const fr s_prod = rc.one();                                   // B.2: blinding of c_b
+  std::vector<fr> sv((size_t)m);                                // B.3: s_1 = t_1, s_m = s_prod, rest random
+  sv[0] = t[0];
+  for (int i = 1; i < m - 1; i++) sv[i] = rc.one();
+  sv[m - 1] = s_prod;
+  // B.4 randomness (drawn now to respect the B.6 order; used in round D)
+  const std::vector<fr> z_a0 = rc.vec(n), z_bm1 = rc.vec(n);
+  const fr z_r0 = rc.one(), z_sm1 = rc.one();
+  std::vector<fr> z_t((size_t)2 * m + 1);
+  for (int k = 0; k <= 2 * m; k++) z_t[k] = (k != m + 1) ? rc.one() : fr_zero();
+  // B.5 randomness
+  const std::vector<fr> sv_d = rc.vec(n);
+  const fr sv_rd = rc.one();
+  std::vector<fr> sv_delta((size_t)n);
+  sv_delta[0] = sv_d[0];
+  for (int i = 1; i < n - 1; i++) sv_delta[i] = rc.one();
+  sv_delta[n - 1] = fr_zero();
+  const fr sv_s1 = rc.one(), sv_sx = rc.one();
+  // B.5' randomness
+  const std::vector<fr> me_a0 = rc.vec(n);
+  const fr me_r0 = rc.one();
+  std::vector<fr> me_b((size_t)2 * m), me_s((size_t)2 * m), me_tau((size_t)2 * m);
+  for (int k = 0; k < 2 * m; k++) {
+    if (k == m) { me_b[k] = fr_zero(); me_s[k] = fr_zero(); me_tau[k] = fr_zero(); /* tau_m = rho*, set below */ }
+    else { me_b[k] = rc.one(); me_s[k] = rc.one(); me_tau[k] = rc.one(); }
+  }
+  if (rc.i != shuffle_randomness_len(m, n)) return ctx->fail(MP_ERR_INVALID_ARG, "internal: randomness count mismatch");
+
+  CK(cudaMemcpyAsync(d_Ame, me_a0.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
+  CK(fr_to_canonical_vec(d_Ame, d_ct_scal, N + n, st));  // scalar arena: rows a0 | b_1..b_m
+  ctx->launches += 1;
+  std::vector<MsmJob> diag((size_t)2 * m);
+  for (int k = 0; k < 2 * m; k++) {
+    int i0 = std::max(1, m - k), i1 = std::min(m, 2 * m - k);
+    diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
+  }
+  CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_mont, 2, diag.data(), 2 * m, msm_pick_window(N / 2), d_ct_out, st));
+  ctx->launches += msm_last_launches(ctx->ws);
+
+  // wait for col / rho* (the diagonal MSMs keep the GPU busy meanwhile)
+  // NOTE: the copy was enqueued before the MSM on the same stream, so an event marks its completion.
+  CK(cudaStreamSynchronize(st));
+  std::vector<fr> col(h_col, h_col + n);
+  const fr rho_star = fr_neg(h_col[n]);
+  me_tau[m] = rho_star;
+
+  // C.3  Enc(b_k*ghat; tau_k) = tau_k*(g, pk) + b_k*(O, ghat): 2m two-term ciphertext jobs, then E_k = diag_k + enc_k
+  {
+    std::vector<uint32_t> sc((size_t)4 * m * 8);
+    for (int k = 0; k < 2 * m; k++) {
+      fr_to_canonical(me_tau[k], &sc[(size_t)(2 * k) * 8]);
+      fr_to_canonical(me_b[k], &sc[(size_t)(2 * k + 1) * 8]);
+    }
+    uint32_t* d_enc_scal = d_ct_scal + (N + n) * 8;
+    CK(cudaMemcpyAsync(d_enc_scal, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<MsmJob> enc((size_t)2 * m);
+    for (int k = 0; k < 2 * m; k++) enc[k] = MsmJob{(uint32_t)(2 * k), (uint32_t)N, 2};
+    CK(msm_run(ctx->ws, d_enc_scal, 4 * (size_t)m, d_ct_mont, 2, enc.data(), 2 * m, 4, d_ct_out2, st));
+    ctx->launches += msm_last_launches(ctx->ws);
+    k_xyzz_add_pairs<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_ct_out2, d_ct_out, 4 * m);
+    CK(cudaGetLastError());
+    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canon, 4 * (size_t)m, st));
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(proof_out + L.meE, d_canon, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
+  }
+
+  // C.4  SVP first message on the host side of the scalars (O(n)), committed on the device
+  std::vector<fr> bk((size_t)n);
+  bk[0] = col[0];
+  for (int i = 1; i < n; i++) bk[i] = fr_mul(bk[i - 1], col[i]);
+  {
+    std::vector<fr> rows3((size_t)3 * n, fr_zero());
+    for (int i = 0; i < n; i++) rows3[i] = sv_d[i];
+    for (int i = 0; i + 1 < n; i++) {
+      rows3[(size_t)n + i] = fr_neg(fr_mul(sv_delta[i], sv_d[i + 1]));
+      rows3[(size_t)2 * n + i] = fr_sub(fr_sub(sv_delta[i + 1], fr_mul(col[i + 1], sv_delta[i])), fr_mul(bk[i], sv_d[i + 1]));
+    }
+    CK(cudaMemcpyAsync(d_rows, rows3.data(), sizeof(fr) * 3 * n, cudaMemcpyHostToDevice, st));
+  }
+  // C.5  one G1 batch: Hadamard c_B[0..m) = com(Bv[i]; sv[i]) (c_B[0] = c_D[0], c_B[m-1] = c_b),
+  //      SVP c_d, c_delta, c_Delta, multi-exp c_A0 and the 2m two-term c_B_k = com(b_k; s_k)
+  {
+    // scalar arena: (m + 4) rows of n + 1, then 2m pairs (s_k, b_k)
+    const int R = m + 4;
+    std::vector<fr> blinds((size_t)R);
+    for (int i = 0; i < m; i++) blinds[i] = sv[i];
+    blinds[m] = sv_rd; blinds[m + 1] = sv_s1; blinds[m + 2] = sv_sx; blinds[m + 3] = me_r0;
+    CK(cudaMemcpyAsync(d_blind, blinds.data(), sizeof(fr) * R, cudaMemcpyHostToDevice, st));
+    uint64_t tot = (uint64_t)(n + 1);
+    k_commit_scalars<<<(unsigned)((tot * m + 255) / 256), 256, 0, st>>>(d_Bv, n, d_blind, m, n, n, d_g1_scal);
+    k_commit_scalars<<<(unsigned)((tot * 3 + 255) / 256), 256, 0, st>>>(d_rows, n, d_blind + m, 3, n, n, d_g1_scal + tot * m * 8);
+    k_commit_scalars<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_Ame, n, d_blind + m + 3, 1, n, n, d_g1_scal + tot * (m + 3) * 8);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
+    std::vector<uint32_t> sc((size_t)4 * m * 8);
+    for (int k = 0; k < 2 * m; k++) {
+      fr_to_canonical(me_s[k], &sc[(size_t)(2 * k) * 8]);
+      fr_to_canonical(me_b[k], &sc[(size_t)(2 * k + 1) * 8]);
+    }
+    CK(cudaMemcpyAsync(d_g1_scal + tot * R * 8, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<MsmJob> jobs;
+    for (int k = 0; k < R; k++) jobs.push_back(MsmJob{(uint32_t)(k * tot), 0, (uint32_t)tot});
+    CK(msm_run(ctx->ws, d_g1_scal, tot * R, S->d_ck, 1, jobs.data(), R, msm_pick_window(n + 1), d_g1_out, st));
+    ctx->launches += msm_last_launches(ctx->ws);
+    std::vector<MsmJob> small;
+    for (int k = 0; k < 2 * m; k++) small.push_back(MsmJob{(uint32_t)(2 * k), 0, 2});
+    CK(msm_run(ctx->ws, d_g1_scal + tot * R * 8, 4 * (size_t)m, S->d_ck, 1, small.data(), 2 * m, 4, d_g1_out + R, st));
+    ctx->launches += msm_last_launches(ctx->ws);
+    uint8_t* d_canon2 = d_canon + 4 * (size_t)m * 64;
+    CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon2, (size_t)R + 2 * m, st));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(proof_out + L.hB, d_canon2, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(proof_out + L.svpts, d_canon2 + (size_t)m * 64, 3 * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(proof_out + L.mepts, d_canon2 + (size_t)(m + 3) * 64, (size_t)(2 * m + 1) * 64, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  memcpy(proof_out + L.cb, proof_out + L.hB + 64 * (size_t)(m - 1), 64);  // c_b = c_B[m-1]
+  fs.begin(); fs.feed_label("hadamard_argument"); fs.feed_points64(proof_out + L.cb, 1); fs.feed_points64(proof_out + L.hB, m); fs.end();
+  const fr xh = fs.challenge();
+  const fr yh = fs.challenge();
+
+  // ---- round D: zero argument (B.4) on A' = (a0 | d_2..d_m | -1), B' = (xh^i Bv_i | dlast | b_{m+1})
+  const std::vector<fr> xhp = h_powers(xh, m);
+  {
+    // A rows
+    CK(cudaMemcpyAsync(d_Az, z_a0.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_Az + n, d_d0 + n, sizeof(fr) * (N - n), cudaMemcpyDeviceToDevice, st));
+    std::vector<fr> m1((size_t)n, fr_neg(fr_one()));
+    CK(cudaMemcpyAsync(d_Az + N, m1.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
+    // B rows: row i-1 = xh^i * Bv[i-1] (i = 1..m-1); row m-1 = sum_{i=1}^{m-1} xh^i Bv[i]; row m = b_{m+1}
+    SmallUpload up;
+    std::vector<fr> coef(xhp.begin() + 1, xhp.end());  // xh^1 .. xh^{m-1}
+    size_t o_coef = up.add_frs(coef);
+    std::vector<fr> yp((size_t)n);
+    fr acc = fr_one();
+    for (int j = 0; j < n; j++) { acc = fr_mul(acc, yh); yp[j] = acc; }
+    size_t o_yp = up.add_frs(yp);
+    uint8_t* d_small = (uint8_t*)ctx->scratch(sSmallUp, up.bytes.size() + 64);
+    NEED(d_small);
+    CK(cudaMemcpyAsync(d_small, up.bytes.data(), up.bytes.size(), cudaMemcpyHostToDevice, st));
+    CK(fr_scale_rows(d_Bv, (const fr*)(d_small + o_coef), m - 1, n, d_Bz, st));
+    CK(fr_lincomb_rows(d_Bv + n, n, (const fr*)(d_small + o_coef), m - 1, n, d_Bz + (size_t)(m - 1) * n, st));
+    CK(cudaMemcpyAsync(d_Bz + N, z_bm1.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
+    fr* d_dk = d_pairs + (size_t)(m + 1) * (m + 1) + 2 * (size_t)m + 4;  // 2m+1 diagonal sums
+    CK(fr_bilinear_diagonals(d_Az, d_Bz, (const fr*)(d_small + o_yp), m + 1, n, d_pairs, d_dk, st));
+    ctx->launches += 4;
+    // commitments: c_A0 = com(a0; r0), c_Bm1 = com(b_{m+1}; s_{m+1}), c_D_k = com(d_k; t_k)
+    fr bl[2] = {z_r0, z_sm1};
+    CK(cudaMemcpyAsync(d_blind, bl, sizeof bl, cudaMemcpyHostToDevice, st));
+    uint64_t tot = (uint64_t)(n + 1);
+    k_commit_scalars<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_Az, n, d_blind, 1, n, n, d_g1_scal);
+    k_commit_scalars<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_Bz + N, n, d_blind + 1, 1, n, n, d_g1_scal + tot * 8);
+    CK(cudaGetLastError());
+    uint32_t* d_pairs_scal = d_g1_scal + 2 * tot * 8;  // (t_k, d_k) pairs
+    std::vector<uint32_t> tk((size_t)(2 * m + 1) * 8);
+    for (int k = 0; k <= 2 * m; k++) fr_to_canonical(z_t[k], &tk[(size_t)k * 8]);
+    // t_k at even slots (strided copy), d_k at odd slots
+    CK(cudaMemcpy2DAsync(d_pairs_scal, 64, tk.data(), 32, 32, 2 * (size_t)m + 1, cudaMemcpyHostToDevice, st));
+    CK(fr_scatter_canonical(d_dk, 2 * (size_t)m + 1, d_pairs_scal, 1, 2, st));
+    ctx->launches += 3;
+    std::vector<MsmJob> big = {MsmJob{0, 0, (uint32_t)tot}, MsmJob{(uint32_t)tot, 0, (uint32_t)tot}};
+    CK(msm_run(ctx->ws, d_g1_scal, 2 * tot, S->d_ck, 1, big.data(), 2, msm_pick_window(n + 1), d_g1_out, st));
+    ctx->launches += msm_last_launches(ctx->ws);
+    std::vector<MsmJob> small;
+    for (int k = 0; k <= 2 * m; k++) small.push_back(MsmJob{(uint32_t)(2 * k), 0, 2});
+    CK(msm_run(ctx->ws, d_pairs_scal, 2 * (2 * (size_t)m + 1), S->d_ck, 1, small.data(), 2 * m + 1, 4, d_g1_out + 2, st));
+    ctx->launches += msm_last_launches(ctx->ws);
+    CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, 2 * (size_t)m + 3, st));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(proof_out + L.zpts, d_canon, (2 * (size_t)m + 3) * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof_out + L.zpts, 2 * (size_t)m + 3); fs.end();
+  const fr xz = fs.challenge();
+  fs.begin(); fs.feed_label("single_value_product_argument"); fs.feed_points64(proof_out + L.svpts, 3); fs.end();
+  const fr xs = fs.challenge();
+  fs.begin(); fs.feed_label("multi_exponentiation_argument");
+  fs.feed_points64(proof_out + L.mepts, 2 * (size_t)m + 1); fs.feed_points64(proof_out + L.meE, 4 * (size_t)m); fs.end();
+  const fr xm = fs.challenge();
+
+  // ---- responses.  Device: the three O(N) row combinations; host: the O(m + n) rest.
+  const std::vector<fr> xzp = h_powers(xz, 2 * m + 1);
+  const std::vector<fr> xmp = h_powers(xm, 2 * m);
+  {
+    SmallUpload up;
+    std::vector<fr> ca(xzp.begin(), xzp.begin() + m + 1);       // a = sum_{i=0}^{m} xz^i A'_i
+    std::vector<fr> cb((size_t)m + 1);                          // b = sum_{j=0}^{m} xz^{m-j} B'_j
+    for (int j = 0; j <= m; j++) cb[j] = xzp[m - j];
+    std::vector<fr> cm(xmp.begin(), xmp.begin() + m + 1);       // a_me = sum_{j=0}^{m} xm^j Ame_j
+    size_t o_a = up.add_frs(ca), o_b = up.add_frs(cb), o_m = up.add_frs(cm);
+    uint8_t* d_small = (uint8_t*)ctx->scratch(sSmallUp, up.bytes.size() + 64);
+    NEED(d_small);
+    CK(cudaMemcpyAsync(d_small, up.bytes.data(), up.bytes.size(), cudaMemcpyHostToDevice, st));
+    fr* d_resp = d_rows;  // 3 x n
+    CK(fr_lincomb_rows(d_Az, n, (const fr*)(d_small + o_a), m + 1, n, d_resp, st));
+    CK(fr_lincomb_rows(d_Bz, n, (const fr*)(d_small + o_b), m + 1, n, d_resp + n, st));
+    CK(fr_lincomb_rows(d_Ame, n, (const fr*)(d_small + o_m), m + 1, n, d_resp + 2 * (size_t)n, st));
+    uint32_t* d_resp_canon = d_g1_scal;
+    CK(fr_to_canonical_vec(d_resp, d_resp_canon, 3 * (size_t)n, st));
+    ctx->launches += 4;
+    CK(cudaMemcpyAsync(proof_out + L.za, d_resp_canon, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(proof_out + L.zb, d_resp_canon + (size_t)n * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(proof_out + L.mea, d_resp_canon + 2 * (size_t)n * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  }
+  // zero-argument blinding responses: r' = (r0, t_2..t_m, 0), s' = (xh^i sv_i.., sum xh^i sv_{i+1}, s_{m+1})
+  {
+    std::vector<fr> rext((size_t)m + 1), sext((size_t)m + 1), xr((size_t)m + 1);
+    rext[0] = z_r0;
+    for (int i = 1; i < m; i++) rext[i] = t[i];
+    rext[m] = fr_zero();
+    for (int i = 1; i < m; i++) sext[i - 1] = fr_mul(xhp[i], sv[i - 1]);
+    sext[m - 1] = h_dot(xhp.data() + 1, sv.data() + 1, m - 1);
+    sext[m] = z_sm1;
+    for (int j = 0; j <= m; j++) xr[j] = xzp[m - j];
+    h_fr_out(h_dot(xzp.data(), rext.data(), m + 1), proof_out + L.zr);
+    h_fr_out(h_dot(xr.data(), sext.data(), m + 1), proof_out + L.zs);
+    h_fr_out(h_dot(xzp.data(), z_t.data(), 2 * m + 1), proof_out + L.zt);
+  }
+  // SVP responses
+  for (int i = 0; i < n; i++) {
+    h_fr_out(fr_add(fr_mul(xs, col[i]), sv_d[i]), proof_out + L.sva + 32 * (size_t)i);
+    h_fr_out(fr_add(fr_mul(xs, bk[i]), sv_delta[i]), proof_out + L.svb + 32 * (size_t)i);
+  }
+  h_fr_out(fr_add(fr_mul(xs, s_prod), sv_rd), proof_out + L.svr);
+  h_fr_out(fr_add(fr_mul(xs, sv_sx), sv_s1), proof_out + L.svs);
+  // multi-exp responses
+  {
+    std::vector<fr> rext((size_t)m + 1);
+    rext[0] = me_r0;
+    for (int j = 1; j <= m; j++) rext[j] = s[j - 1];
+    h_fr_out(h_dot(xmp.data(), rext.data(), m + 1), proof_out + L.mer);
+    h_fr_out(h_dot(xmp.data(), me_b.data(), 2 * m), proof_out + L.meb);
+    h_fr_out(h_dot(xmp.data(), me_s.data(), 2 * m), proof_out + L.mes);
+    h_fr_out(h_dot(xmp.data(), me_tau.data(), 2 * m), proof_out + L.metau);
+  }
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not a canonical point of the Stark curve");
+  return MP_OK;
+}
+
+}  // namespace mp

@@ -1,0 +1,43 @@
+// Bayer-Groth shuffle argument on the GPU: host-side protocol driver.
+//
+// Replaces, behind the C ABI, what the reference executes inside
+//   DLCards::shuffle_and_remask   reference src/discrete_log_cards/mod.rs:380-418
+//   DLCards::verify_shuffle       reference src/discrete_log_cards/mod.rs:420-443
+// i.e. `MaskedCard::remask` (remasking.rs:9-22) over the permuted deck and
+// `shuffle::ShuffleArgument::{prove,verify}` of the un-vendored proof-essentials crate
+// (algebra restated in SURVEY.md Appendix B; transcript/draw order Appendix B.6).
+//
+// Division of labour (BASELINE north_star): the host owns the Fiat-Shamir transcript and the
+// O(m + n) scalar glue; every group operation and every O(N) / O(m^2 n) scalar-vector
+// operation runs in CUDA kernels.  Verification needs NO device->host round trip before the
+// final verdict: all challenges derive from proof bytes, so the whole check is a handful of
+// batched MSM jobs that must each evaluate to the identity.  Proving needs four round trips
+// (c_A -> x, c_B -> y,z, the big commitment batch -> Hadamard challenges, zero-argument
+// commitments -> remaining challenges).
+#pragma once
+#include <stdint.h>
+
+struct mp_ctx;
+
+namespace mp {
+
+struct ShuffleState;
+void shuffle_state_destroy(ShuffleState*);
+
+int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
+                           const uint8_t* ck_h, const uint8_t* ghat);
+int32_t shuffle_m(const mp_ctx* ctx);
+int32_t shuffle_n(const mp_ctx* ctx);
+uint64_t shuffle_proof_len(int32_t m, int32_t n);
+uint64_t shuffle_randomness_len(int32_t m, int32_t n);
+
+int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                       const uint8_t* rho, uint64_t N, uint8_t* out_deck);
+int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k,
+                             uint64_t len, uint8_t* out);
+int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
+                      const uint32_t* perm, const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out);
+int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
+                       const uint8_t* proof);
+
+}  // namespace mp

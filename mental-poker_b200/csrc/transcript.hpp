@@ -1,0 +1,218 @@
+// Host-side Fiat-Shamir transcript of the shuffle argument.  By design (BASELINE north_star)
+// the transcript and protocol state stay on the host; the GPU only sees the challenges.
+//
+// Mirrors ark-marlin 0.3 `FiatShamirRng<Blake2s>` as the reference instantiates it
+// (reference src/discrete_log_cards/mod.rs:9,12 and the seed at mod.rs:84,408,436):
+//   from_seed(bytes):  seed = Blake2s-256(bytes);            rng = ChaCha20(seed)
+//   absorb(bytes):     seed = Blake2s-256(bytes || seed);    rng = ChaCha20(seed)   (stream restarts)
+//   challenge:         ark-ff 0.3 `Fp256::rand`: 4 x next_u64 taken as the raw MONTGOMERY
+//                      representation, top 4 bits cleared, rejection-sampled below the modulus
+// (SURVEY.md A1, A4, A5).  Point encoding inside absorbed data is ark-ec 0.3 `ToBytes`:
+// x || y || infinity-flag = 65 bytes, identity = (0, 1, true).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+
+#include "fr.cuh"
+
+namespace mp {
+
+class Blake2s {
+ public:
+  Blake2s() { reset(); }
+  void reset() {
+    static const uint32_t iv[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au,
+                                   0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    memcpy(h_, iv, 32);
+    h_[0] ^= 0x01010020u;  // 32-byte digest, unkeyed, sequential mode
+    t_ = 0;
+    fill_ = 0;
+  }
+  void update(const void* data, size_t len) {
+    const uint8_t* in = static_cast<const uint8_t*>(data);
+    if (len == 0) return;
+    if (fill_ > 0) {
+      size_t take = 64 - fill_;
+      if (take > len) take = len;
+      memcpy(buf_ + fill_, in, take);
+      fill_ += take;
+      in += take;
+      len -= take;
+      if (len == 0) return;  // keep a possibly-final block buffered
+      t_ += 64;
+      compress(buf_, false);
+      fill_ = 0;
+    }
+    while (len > 64) {  // strictly greater: the last block must go through finish()
+      t_ += 64;
+      compress(in, false);
+      in += 64;
+      len -= 64;
+    }
+    memcpy(buf_, in, len);
+    fill_ = len;
+  }
+  void finish(uint8_t out[32]) {
+    t_ += fill_;
+    memset(buf_ + fill_, 0, 64 - fill_);
+    compress(buf_, true);
+    memcpy(out, h_, 32);
+  }
+
+ private:
+  static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+  void compress(const uint8_t* block, bool last) {
+    static const uint32_t iv[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au,
+                                   0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    uint32_t m[16], v[16];
+    memcpy(m, block, 64);
+    for (int i = 0; i < 8; i++) { v[i] = h_[i]; v[i + 8] = iv[i]; }
+    v[12] ^= (uint32_t)t_;
+    v[13] ^= (uint32_t)(t_ >> 32);
+    if (last) v[14] = ~v[14];
+#define MP_G(a, b, c, d, x, y)                          \
+  do {                                                  \
+    v[a] = v[a] + v[b] + m[x]; v[d] = rotr(v[d] ^ v[a], 16); \
+    v[c] = v[c] + v[d];        v[b] = rotr(v[b] ^ v[c], 12); \
+    v[a] = v[a] + v[b] + m[y]; v[d] = rotr(v[d] ^ v[a], 8);  \
+    v[c] = v[c] + v[d];        v[b] = rotr(v[b] ^ v[c], 7);  \
+  } while (0)
+#define MP_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+  MP_G(0, 4, 8, 12, s0, s1); MP_G(1, 5, 9, 13, s2, s3); MP_G(2, 6, 10, 14, s4, s5);    \
+  MP_G(3, 7, 11, 15, s6, s7); MP_G(0, 5, 10, 15, s8, s9); MP_G(1, 6, 11, 12, s10, s11); \
+  MP_G(2, 7, 8, 13, s12, s13); MP_G(3, 4, 9, 14, s14, s15)
+    MP_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    MP_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    MP_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
+    MP_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
+    MP_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);
+    MP_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);
+    MP_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);
+    MP_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);
+    MP_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);
+    MP_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);
+#undef MP_ROUND
+#undef MP_G
+    for (int i = 0; i < 8; i++) h_[i] ^= v[i] ^ v[i + 8];
+  }
+  uint32_t h_[8];
+  uint64_t t_;
+  uint8_t buf_[64];
+  size_t fill_;
+};
+
+// rand_chacha `ChaCha20Rng`: 20 rounds, 64-bit block counter in words 12..13, stream id 0
+class ChaCha20Stream {
+ public:
+  void seed(const uint8_t key[32]) {
+    memcpy(key_, key, 32);
+    counter_ = 0;
+    pos_ = 16;
+  }
+  uint32_t next_u32() {
+    if (pos_ >= 16) refill();
+    return buf_[pos_++];
+  }
+  uint64_t next_u64() {
+    uint64_t lo = next_u32();
+    uint64_t hi = next_u32();
+    return lo | (hi << 32);
+  }
+
+ private:
+  static inline uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+  void refill() {
+    uint32_t s[16] = {0x61707865u, 0x3320646Eu, 0x79622D32u, 0x6B206574u};
+    memcpy(s + 4, key_, 32);
+    s[12] = (uint32_t)counter_;
+    s[13] = (uint32_t)(counter_ >> 32);
+    s[14] = 0;
+    s[15] = 0;
+    uint32_t x[16];
+    memcpy(x, s, 64);
+    auto qr = [&](int a, int b, int c, int d) {
+      x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16);
+      x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+      x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);
+      x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+    };
+    for (int i = 0; i < 10; i++) {
+      qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+      qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) buf_[i] = x[i] + s[i];
+    counter_++;
+    pos_ = 0;
+  }
+  uint32_t key_[8];
+  uint64_t counter_;
+  uint32_t buf_[16];
+  int pos_;
+};
+
+class Transcript {
+ public:
+  // FiatShamirRng::<Blake2s>::from_seed(&to_bytes![SHUFFLE_RNG_SEED])   mod.rs:84,408,436
+  Transcript() {
+    Blake2s h;
+    h.update("Shuffle Proof", 13);
+    h.finish(seed_);
+    rng_.seed(seed_);
+  }
+  // absorb = begin(); feed()...; end()
+  void begin() { pending_.reset(); }
+  void feed(const void* data, size_t len) { pending_.update(data, len); }
+  void feed_label(const char* s) { pending_.update(s, strlen(s)); }
+  // 64-byte C-ABI points (all-zero = identity) -> the 65-byte ark-ec encoding
+  void feed_points64(const uint8_t* pts, size_t count) {
+    uint8_t b[65];
+    for (size_t i = 0; i < count; i++) {
+      const uint8_t* p = pts + 64 * i;
+      bool inf = true;
+      for (int k = 0; k < 64; k++)
+        if (p[k]) { inf = false; break; }
+      if (inf) {
+        memset(b, 0, 65);
+        b[32] = 1;
+        b[64] = 1;
+      } else {
+        memcpy(b, p, 64);
+        b[64] = 0;
+      }
+      pending_.update(b, 65);
+    }
+  }
+  void end() {
+    pending_.update(seed_, 32);
+    pending_.finish(seed_);
+    rng_.seed(seed_);
+  }
+  fr challenge() {
+    for (;;) {
+      uint64_t l[4];
+      for (int i = 0; i < 4; i++) l[i] = rng_.next_u64();
+      l[3] &= 0xFFFFFFFFFFFFFFFFull >> 4;
+      fr c;
+      for (int i = 0; i < 4; i++) {
+        c.v[2 * i] = (uint32_t)l[i];
+        c.v[2 * i + 1] = (uint32_t)(l[i] >> 32);
+      }
+      // accept iff raw < n
+      bool lt = false;
+      for (int i = 7; i >= 0; i--) {
+        uint32_t mi = fr_modulus_limb(i);
+        if (c.v[i] != mi) { lt = c.v[i] < mi; break; }
+      }
+      if (lt) return c;  // raw value IS the Montgomery representation
+    }
+  }
+
+ private:
+  uint8_t seed_[32];
+  ChaCha20Stream rng_;
+  Blake2s pending_;
+};
+
+}  // namespace mp

@@ -49,3 +49,37 @@ void h_lincomb2(const uint32_t* p, const uint32_t* k1, const uint32_t* q, const 
   affine_to_canonical(xyzz_to_affine(a), out);
 }
 }
+
+// ---- scalar field + transcript (host side of csrc/fr.cuh, csrc/transcript.hpp)
+#include "../../mental-poker_b200/csrc/transcript.hpp"
+extern "C" {
+void h_fr_mul_canonical(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  fr x = fr_from_canonical(a), y = fr_from_canonical(b);
+  fr_to_canonical(fr_mul(x, y), out);
+}
+void h_fr_addsub_canonical(const uint32_t* a, const uint32_t* b, uint32_t* sum, uint32_t* diff, uint32_t* neg) {
+  fr x = fr_from_canonical(a), y = fr_from_canonical(b);
+  fr_to_canonical(fr_add(x, y), sum);
+  fr_to_canonical(fr_sub(x, y), diff);
+  fr_to_canonical(fr_neg(x), neg);
+}
+void h_blake2s(const uint8_t* data, uint64_t len, uint64_t split, uint8_t* out) {
+  Blake2s h;
+  if (split > len) split = len;
+  h.update(data, split);          // exercise the buffering paths
+  h.update(data + split, len - split);
+  h.finish(out);
+}
+// challenges after absorbing `data` (in two feeds) into a fresh "Shuffle Proof" transcript
+void h_fs_challenges(const uint8_t* data, uint64_t len, int count, uint8_t* out) {
+  Transcript fs;
+  if (len) { fs.begin(); fs.feed(data, len / 2); fs.feed(data + len / 2, len - len / 2); fs.end(); }
+  for (int i = 0; i < count; i++) { fr c = fs.challenge(); uint32_t w[8]; fr_to_canonical(c, w); memcpy(out + 32 * i, w, 32); }
+}
+// absorb `count` 64-byte points through feed_points64 and return one challenge
+void h_fs_points_challenge(const uint8_t* pts, uint64_t count, uint8_t* out) {
+  Transcript fs;
+  fs.begin(); fs.feed_label("label"); fs.feed_points64(pts, count); fs.end();
+  fr c = fs.challenge(); uint32_t w[8]; fr_to_canonical(c, w); memcpy(out, w, 32);
+}
+}

@@ -1,0 +1,159 @@
+"""GPU parity, protocol level: `shuffle_and_remask` / `verify_shuffle` through the C ABI against
+the oracle -- the reference's `test_shuffle` (tests.rs:175-227) plus byte-exact proof parity on
+identical decks, permutations and randomness."""
+import json
+import os
+import random
+
+import pytest
+
+from oracle import c_oracle
+from oracle.py import stark, bayer_groth as bg
+from _util import chain_points, instance, pb, b32
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.json")))
+h = bytes.fromhex
+
+
+def setup_ctx(ctx, fx):
+    ctx.set_params(fx["m"], fx["n"], h(fx["enc_g"]), h(fx["ck_g"]), h(fx["ck_h"]), h(fx["ghat"]))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_verify_accepts_golden_proofs(ctx, idx):
+    fx = GOLD["shuffle"][idx]
+    setup_ctx(ctx, fx)
+    assert ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), h(fx["deck2"]), h(fx["proof"])) == 0
+    assert ctx.launches > 0
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_prove_is_byte_exact_vs_golden(ctx, idx):
+    fx = GOLD["shuffle"][idx]
+    setup_ctx(ctx, fx)
+    deck2, proof = ctx.shuffle_and_remask(h(fx["pk"]), h(fx["deck"]), fx["perm"], h(fx["rho"]), h(fx["rand"]))
+    assert deck2.hex() == fx["deck2"]
+    assert proof.hex() == fx["proof"]
+    assert ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), deck2, proof) == 0
+
+
+def test_reference_test_shuffle_negative_case(ctx):
+    # tests.rs:213-226: verifying against a fresh random output deck => "Hadamard Product (5.1)"
+    fx = GOLD["shuffle"][2]
+    setup_ctx(ctx, fx)
+    _, _, pts, _ = chain_points(104, 99)
+    wrong = b"".join(pb(p) for p in pts)
+    st = ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), wrong, h(fx["proof"]))
+    assert st == 1 and ctx.status_string(st) == "Hadamard Product (5.1)"
+
+
+def test_tampering_matches_oracle_verdicts(ctx):
+    fx = GOLD["shuffle"][2]
+    setup_ctx(ctx, fx)
+    co = c_oracle.COracle()
+    m, n = fx["m"], fx["n"]
+    proof = h(fx["proof"])
+    rnd = random.Random(11)
+    args = (m, n, h(fx["enc_g"]), h(fx["ck_g"]), h(fx["ck_h"]), h(fx["ghat"]), h(fx["pk"]))
+    # flip one bit in every scalar of the proof in turn (scalars stay canonical: low bits only)
+    npts = 11 * m + 8
+    offsets = []
+    pos = 0
+    layout = [("P", 2 * m + 1 + m + 2 * m + 3), ("F", 2 * n + 3), ("P", 3), ("F", 2 * n + 2), ("P", 2 * m + 1 + 4 * m), ("F", n + 4)]
+    for kind, cnt in layout:
+        for _ in range(cnt):
+            if kind == "F":
+                offsets.append(pos)
+            pos += 64 if kind == "P" else 32
+    assert pos == len(proof)
+    seen = set()
+    for off in offsets:
+        p2 = bytearray(proof)
+        p2[off] ^= 1 << rnd.randrange(8)
+        want = co.verify(*args, h(fx["deck"]), h(fx["deck2"]), bytes(p2))
+        got = ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), h(fx["deck2"]), bytes(p2))
+        assert got == want != 0, off
+        seen.add(got)
+    assert seen == {2, 3, 4}
+    # swap two proof points (still on the curve): c_A[0] <-> c_A[1]
+    p2 = bytearray(proof)
+    p2[0:64], p2[64:128] = proof[64:128], proof[0:64]
+    want = co.verify(*args, h(fx["deck"]), h(fx["deck2"]), bytes(p2))
+    assert ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), h(fx["deck2"]), bytes(p2)) == want != 0
+    # a different valid remask of the same deck does not verify under this proof
+    perm2 = fx["perm"][1:] + fx["perm"][:1]
+    other = ctx.remask(h(fx["pk"]), h(fx["deck"]), perm2, h(fx["rho"]))
+    want = co.verify(*args, h(fx["deck"]), other, proof)
+    assert ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), other, proof) == want != 0
+
+
+def test_off_curve_inputs_are_rejected(ctx, pkg):
+    fx = GOLD["shuffle"][0]
+    setup_ctx(ctx, fx)
+    deck = bytearray(h(fx["deck"]))
+    deck[5] ^= 1
+    with pytest.raises(pkg.MpError) as e:
+        ctx.verify_shuffle(h(fx["pk"]), bytes(deck), h(fx["deck2"]), h(fx["proof"]))
+    assert e.value.code == -3
+    proof = bytearray(h(fx["proof"]))
+    proof[3] ^= 1
+    with pytest.raises(pkg.MpError):
+        ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), h(fx["deck2"]), bytes(proof))
+    with pytest.raises(pkg.MpError):
+        ctx.set_params(2, 2, b32(1) + b32(2), h(fx["ck_g"])[:128], h(fx["ck_h"]), h(fx["ghat"]))
+    setup_ctx(ctx, fx)
+
+
+def test_remask_and_commit_primitives(ctx):
+    fx = GOLD["shuffle"][1]
+    setup_ctx(ctx, fx)
+    co = c_oracle.COracle()
+    m, n = fx["m"], fx["n"]
+    assert ctx.remask(h(fx["pk"]), h(fx["deck"]), fx["perm"], h(fx["rho"])).hex() == fx["deck2"]
+    rnd = random.Random(3)
+    for length in (n, n - 1, 1, 0):
+        k = 5
+        vals = [[rnd.randrange(stark.N) for _ in range(length)] for _ in range(k)]
+        vals[0] = [0] * length
+        blinds = [rnd.randrange(stark.N) for _ in range(k)]
+        blinds[1] = 0
+        got = ctx.commit_batch(b"".join(b32(v) for row in vals for v in row), b"".join(map(b32, blinds)), length)
+        for i in range(k):
+            want = co.commit(n, h(fx["ck_g"]), h(fx["ck_h"]), b"".join(map(b32, vals[i])), b32(blinds[i]))
+            assert got[64 * i:64 * i + 64] == want, (length, i)
+
+
+@pytest.mark.parametrize("m,n,seed", [(2, 2, 5), (5, 3, 6), (8, 8, 7), (16, 32, 8)])
+def test_round_trip_other_shapes_vs_c_oracle(ctx, m, n, seed):
+    """Byte-exact against the C oracle at sizes the Python oracle would take minutes for."""
+    pp, pk, deck, perm, rho, rnd = instance(m, n, seed)
+    co = c_oracle.COracle(msm_mode=1)
+    enc_g, ck_g, ck_h, ghat = pb(pp.enc_g), b"".join(map(pb, pp.ck_g)), pb(pp.ck_h), pb(pp.ghat)
+    deck_b = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+    rho_b, rnd_b = b"".join(map(b32, rho)), b"".join(map(b32, rnd))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    deck2, proof = ctx.shuffle_and_remask(pb(pk), deck_b, perm, rho_b, rnd_b)
+    assert deck2 == co.remask(enc_g, pb(pk), deck_b, perm, rho_b)
+    assert proof == co.prove(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, perm, rho_b, rnd_b)
+    assert ctx.verify_shuffle(pb(pk), deck_b, deck2, proof) == 0
+    assert co.verify(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, proof) == 0
+
+
+def test_identity_and_duplicate_cards(ctx):
+    """Edge decks: identity ciphertext components, duplicated cards, rho = 0 and rho = n-1."""
+    m, n = 3, 4
+    pp, pk, deck, perm, rho, rnd = instance(m, n, 9)
+    deck[0] = (None, None)
+    deck[1] = (deck[2][0], None)
+    deck[5] = deck[4]
+    rho[0], rho[1] = 0, stark.N - 1
+    co = c_oracle.COracle(msm_mode=1)
+    enc_g, ck_g, ck_h, ghat = pb(pp.enc_g), b"".join(map(pb, pp.ck_g)), pb(pp.ck_h), pb(pp.ghat)
+    deck_b = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+    rho_b, rnd_b = b"".join(map(b32, rho)), b"".join(map(b32, rnd))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    deck2, proof = ctx.shuffle_and_remask(pb(pk), deck_b, perm, rho_b, rnd_b)
+    assert deck2 == co.remask(enc_g, pb(pk), deck_b, perm, rho_b)
+    assert proof == co.prove(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, perm, rho_b, rnd_b)
+    assert ctx.verify_shuffle(pb(pk), deck_b, deck2, proof) == 0

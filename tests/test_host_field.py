@@ -85,3 +85,42 @@ def test_point_ops(shim):
         for kk2 in (k2, k1, N - k1):
             shim.h_lincomb2(pw(pts[0]), w(k1), pw(q), w(kk2), out)
             assert bytes(out) == stark.point_to_bytes64(stark.add(stark.mul(pts[0], k1), stark.mul(q, kk2)))
+
+
+def test_fr_arithmetic(shim):
+    rnd = random.Random(8)
+    out, s, d, ng = [(ctypes.c_uint32 * 8)() for _ in range(4)]
+    cases = [(0, 0), (1, N - 1), (N - 1, N - 1), (N, 5), ((1 << 256) - 1, 3)]
+    cases += [(rnd.randrange(N), rnd.randrange(N)) for _ in range(1000)]
+    for a, b in cases:
+        shim.h_fr_mul_canonical(w(a), w(b), out)
+        assert rd(out) == a * b % N
+        shim.h_fr_addsub_canonical(w(a), w(b), s, d, ng)
+        assert rd(s) == (a + b) % N and rd(d) == (a - b) % N and rd(ng) == (-a) % N
+
+
+def test_host_transcript_matches_oracle(shim):
+    import hashlib
+    from oracle.py.transcript import FiatShamirRng
+    shim.h_blake2s.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p]
+    shim.h_fs_challenges.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p]
+    shim.h_fs_points_challenge.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    out = ctypes.create_string_buffer(32)
+    rnd = random.Random(9)
+    for ln in [0, 1, 63, 64, 65, 127, 128, 129, 1000, 4096]:
+        msg = bytes(rnd.randrange(256) for _ in range(ln))
+        for split in [0, 1, 64, ln // 2, ln]:
+            shim.h_blake2s(msg, ln, split, out)
+            assert out.raw == hashlib.blake2s(msg).digest(), (ln, split)
+    for data in [b"", b"abc", bytes(range(200))]:
+        buf = ctypes.create_string_buffer(32 * 4)
+        shim.h_fs_challenges(data, len(data), 4, buf)
+        fs = FiatShamirRng()
+        if data:
+            fs.absorb(data)
+        assert buf.raw == b"".join(stark.fe_to_bytes(fs.challenge()) for _ in range(4))
+    pts = [stark.mul(stark.G, 5), None, stark.mul(stark.G, 7)]
+    shim.h_fs_points_challenge(b"".join(stark.point_to_bytes64(p) for p in pts), 3, out)
+    fs = FiatShamirRng()
+    fs.absorb(b"label" + b"".join(stark.point_to_bytes65(p) for p in pts))
+    assert out.raw == stark.fe_to_bytes(fs.challenge())
