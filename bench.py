@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the shuffle-proof hot path (BASELINE.json metric: shuffle proofs/s, prove+verify,
+and MSM EC-adds/s, next to the CPU reference path on the same box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+One step = one `shuffle_and_remask`-style prove (ShuffleArgument::prove on a remasked deck) plus
+one `verify_shuffle` of a synthetic N-card deck.  Default workload: 2^16 cards, (m, n) =
+(128, 512) -- the configuration BASELINE.json's target is quoted on.  With --gpus N > 1 (under
+torchrun) every rank proves and verifies its own deck (proof-index split, weak scaling, no
+data-path collective).
+
+`value`  : proofs/s with both decks already resident in HBM (mp_shuffle_*_resident).
+`e2e`    : proofs/s through the host-buffer C ABI (mp_shuffle_prove + mp_shuffle_verify): decks,
+           permutation and scalars cross PCIe inside the timed region, proof bytes come back.
+In both, the Fiat-Shamir transcript (Blake2s over the serialized decks) runs on the host inside
+the timed region, as the reference design prescribes.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GX = 0x01EF15C18599971B7BECED415A40F0C7DEACFD9B0D1819E03D723D8BC943CFCA
+GY = 0x005668060AA49730B7BE4801DF46EC62DE53ECD11ABE43A32873000C36E8DC1F
+G64 = GX.to_bytes(32, "little") + GY.to_bytes(32, "little")
+METRIC = "shuffle proofs/sec (prove+verify)"
+UNIT = "proofs/s"
+
+
+# --------------------------------------------------------------------------------------------
+# work model: point-scalar terms per proof, used ONLY to extrapolate the
+# bounded CPU sample to the full workload
+# --------------------------------------------------------------------------------------------
+def work_terms(m, n):
+    N = m * n
+    prove_naive = 2 * N + 2 * m * (m + 1) * n + 4 * m * 2       # remask, diagonal CT-MSMs, Enc(b_k ghat; tau_k)
+    prove_pedersen = (3 * m + 6) * (n + 1) + (4 * m + 1) * 2     # commitments (Pippenger on the CPU)
+    verify_naive = 4 * N + 4 * m + 4 + (m + 1) + (m + 1) + (2 * m + 1) + (m + 1) + 2 * m + 3 * m + 6
+    verify_pedersen = 5 * (n + 1) + 2 * 2 + 2 * (n + 1)
+    return dict(prove_naive=prove_naive, prove_pedersen=prove_pedersen, verify_naive=verify_naive,
+                verify_pedersen=verify_pedersen)
+
+
+def rand_scalars(rng, k):
+    import numpy as np
+    a = rng.integers(0, 256, size=(k, 32), dtype=np.uint8)
+    a[:, 31] &= 0x07  # < 2^251 < group order
+    return a.tobytes()
+
+
+def make_instance(ctx, m, n, seed):
+    """Synthetic instance generated on the GPU: every point is s*G for a seeded scalar s."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    N = m * n
+    npts = (n + 3) + 2 * N
+    pts = ctx.dbg_scalar_mul(G64 * npts, rand_scalars(rng, npts))
+    P = lambda i: pts[64 * i:64 * (i + 1)]
+    inst = dict(m=m, n=n, N=N, enc_g=G64, ck_g=pts[:64 * n], ck_h=P(n), ghat=P(n + 1), pk=P(n + 2),
+                deck=pts[64 * (n + 3):], perm=[int(v) for v in rng.permutation(N)],
+                rho=rand_scalars(rng, N), rand=rand_scalars(rng, 11 * m + 5 * n))
+    return inst
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (oracle; the only place the bench executes oracle/)
+# --------------------------------------------------------------------------------------------
+def cpu_instance(m, n, seed):
+    """Small instance for the CPU sample, built with the C oracle itself (no GPU needed)."""
+    import numpy as np
+    from oracle import c_oracle
+    co = c_oracle.COracle(threads=os.cpu_count() or 1, msm_mode=1)
+    rng = np.random.default_rng(seed)
+    N = m * n
+    npts = (n + 3) + 2 * N
+    sc = rand_scalars(rng, npts)
+    pts = b"".join(co.msm(G64, sc[32 * i:32 * i + 32], 1, 0) for i in range(npts))
+    P = lambda i: pts[64 * i:64 * (i + 1)]
+    return dict(m=m, n=n, N=N, enc_g=G64, ck_g=pts[:64 * n], ck_h=P(n), ghat=P(n + 1), pk=P(n + 2),
+                deck=pts[64 * (n + 3):], perm=[int(v) for v in rng.permutation(N)],
+                rho=rand_scalars(rng, N), rand=rand_scalars(rng, 11 * m + 5 * n))
+
+
+def cpu_sample(m_full, n_full, sm, sn, threads, steps=1, warmup=0):
+    """Times the C restatement (faithful mode: per-term double-and-add for ciphertext sums, ark-ec
+    0.3 Pippenger for commitments) on an (sm, sn) deck and extrapolates to (m_full, n_full) by the
+    term counts of `work_terms`.  Returns (proofs/s at full size, description)."""
+    from oracle import c_oracle
+    inst = cpu_instance(sm, sn, 1)
+    co = c_oracle.COracle(threads=threads, msm_mode=0)  # after cpu_instance: the library's mode is global
+    a = (sm, sn, inst["enc_g"], inst["ck_g"], inst["ck_h"], inst["ghat"], inst["pk"])
+    tp = tv = 0.0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        deck2 = co.remask(inst["enc_g"], inst["pk"], inst["deck"], inst["perm"], inst["rho"])
+        proof = co.prove(*a, inst["deck"], deck2, inst["perm"], inst["rho"], inst["rand"])
+        t1 = time.perf_counter()
+        ok = co.verify(*a, inst["deck"], deck2, proof)
+        t2 = time.perf_counter()
+        assert ok == 0
+        if it >= warmup:
+            tp += t1 - t0
+            tv += t2 - t1
+    tp /= steps
+    tv /= steps
+    ws, wf = work_terms(sm, sn), work_terms(m_full, n_full)
+    # naive terms dominate both legs (> 95 %); scale each leg by its naive-term ratio
+    tp_full = tp * wf["prove_naive"] / ws["prove_naive"]
+    tv_full = tv * wf["verify_naive"] / ws["verify_naive"]
+    desc = (f"C restatement of the reference CPU path (oracle/c, not the Rust binary), {threads} thread(s): full "
+            f"prove+verify of a {sm * sn}-card deck (m={sm}, n={sn}) took {tp:.2f}s + {tv:.2f}s; extrapolated to "
+            f"(m={m_full}, n={n_full}) by point-scalar term count (prove x{wf['prove_naive'] / ws['prove_naive']:.0f}, "
+            f"verify x{wf['verify_naive'] / ws['verify_naive']:.0f}) -> {tp_full:.0f}s + {tv_full:.0f}s per proof")
+    return 1.0 / (tp_full + tv_full), desc, dict(prove_s=tp_full, verify_s=tv_full)
+
+
+def sample_shape(m, n, threads=1):
+    """CPU sample deck: same m:n aspect, sized for ~10-30 s of work on `threads` cores
+    (2^10 cards on one core, 2^12 from 8 threads, 2^14 from 48 threads)."""
+    cap = 1024 if threads < 8 else (4096 if threads < 48 else 16384)
+    sm, sn = m, n
+    while sm * sn > cap and sm > 2 and sn > 2:
+        if sm >= 4:
+            sm //= 2
+        if sm * sn > cap and sn >= 4:
+            sn //= 2
+    return max(sm, 2), max(sn, 2)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=128)
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--msm-logn", type=int, default=20, help="size of the MSM microbench reported beside the metric")
+    args = ap.parse_args()
+    m, n = args.m, args.n
+    N = m * n
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"{N}-card deck shuffle prove+verify, (m,n)=({m},{n}), Stark curve"
+    config = dict(workload=workload, m=m, n=n, cards=N, l2="flushed between steps (256 MiB write)",
+                  sharding="proof-index split: one independent deck per GPU" if world > 1 else "single GPU")
+
+    if args.impl == "reference":
+        # the reference's own CPU path (C restatement), all host threads, rank 0 only
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        sm, sn = sample_shape(m, n, threads)
+        t0 = time.perf_counter()
+        val, desc, legs = cpu_sample(m, n, sm, sn, threads, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+        line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=1000.0 / val, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
+                    data="synthetic", config=config, impl="reference",
+                    cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=desc),
+                    e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, wall_s=time.perf_counter() - t0)
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    lib = pkg.lib
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    inst = make_instance(ctx, m, n, seed=1 + rank)
+    ctx.set_params(m, n, inst["enc_g"], inst["ck_g"], inst["ck_h"], inst["ghat"])
+    perm_arr = (ctypes.c_uint32 * N)(*inst["perm"])
+    deck2_buf = ctypes.create_string_buffer(128 * N)
+    proof_buf = ctypes.create_string_buffer(lib.mp_proof_len(m, n))
+    pkg.check(ctx.h, lib.mp_remask_batch(ctx.h, inst["pk"], inst["deck"], perm_arr, inst["rho"], N, deck2_buf))
+    deck2 = deck2_buf.raw
+    d_deck = torch.frombuffer(bytearray(inst["deck"]), dtype=torch.uint8).to(dev)
+    d_deck2 = torch.frombuffer(bytearray(deck2), dtype=torch.uint8).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step(resident):
+        if resident:
+            rc = lib.mp_shuffle_prove_resident(ctx.h, inst["pk"], inst["deck"], deck2, perm_arr, inst["rho"], inst["rand"],
+                                               proof_buf, d_deck2.data_ptr())
+        else:
+            rc = lib.mp_shuffle_prove(ctx.h, inst["pk"], inst["deck"], deck2, perm_arr, inst["rho"], inst["rand"], proof_buf)
+        pkg.check(ctx.h, rc)
+        launches = ctx.launches
+        if resident:
+            rc = lib.mp_shuffle_verify_resident(ctx.h, inst["pk"], inst["deck"], deck2, proof_buf, d_deck.data_ptr(),
+                                                d_deck2.data_ptr())
+        else:
+            rc = lib.mp_shuffle_verify(ctx.h, inst["pk"], inst["deck"], deck2, proof_buf)
+        if pkg.check(ctx.h, rc) != 0:
+            raise SystemExit(f"bench: verify_shuffle rejected a valid proof (status {rc})")
+        return launches + ctx.launches
+
+    def timed_steps(resident, steps, split=False):
+        total_ms, launches = 0.0, 0
+        prove_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            launches += step(resident)
+            e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms, launches
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(True)
+        step(False)
+    # ---- `value`: decks resident in HBM
+    barrier()
+    ctx.profile_enable(True)
+    ctx.profile_collect()
+    with ClockSampler(local_rank) as clocks:
+        ms_res, launches = timed_steps(True, args.steps)
+    acc_ms, acc_adds, acc_launches = ctx.profile_collect()
+    ctx.profile_enable(False)
+    barrier()
+    # ---- `e2e`: host buffers through the public C ABI
+    ms_e2e, _ = timed_steps(False, args.steps)
+    barrier()
+    # prove / verify split (informational, resident)
+    t0 = time.perf_counter()
+    pkg.check(ctx.h, lib.mp_shuffle_prove_resident(ctx.h, inst["pk"], inst["deck"], deck2, perm_arr, inst["rho"], inst["rand"],
+                                                   proof_buf, d_deck2.data_ptr()))
+    t1 = time.perf_counter()
+    lib.mp_shuffle_verify_resident(ctx.h, inst["pk"], inst["deck"], deck2, proof_buf, d_deck.data_ptr(), d_deck2.data_ptr())
+    t2 = time.perf_counter()
+
+    if world > 1:
+        t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_res, ms_e2e = t.tolist()
+    value = world * args.steps / (ms_res / 1e3)
+    e2e = world * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        bytes_per_add = 68.0  # 64 B affine point gather + 4 B sorted index
+        achieved = bytes_per_add * acc_adds / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else None
+        roofline = dict(bound="hbm", kernel="k_accumulate (bucket accumulation, XYZZ mixed adds)", achieved=achieved,
+                        peak=peak, unit="GB/s", frac=(achieved / peak if achieved else None), traffic=None,
+                        peak_source=peak_src, launches=acc_launches,
+                        avg_launch_ms=(acc_ms / acc_launches if acc_launches else None),
+                        share_of_step=(acc_ms / ms_res if ms_res else None),
+                        ec_adds_per_s=(acc_adds / (acc_ms / 1e3) if acc_ms > 0 else None),
+                        note="integer-pipe bound kernel (~10 field multiplications of 64 IMAD.WIDE per 68 B): the HBM "
+                             "fraction is structurally low; see DESIGN.md for the IMAD-issue roofline")
+        h2d = 128 * N * 2 + 4 * N + 32 * N + 32 * (11 * m + 5 * n) + 128 * N * 2 + len(proof_buf)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="u32", data="synthetic", config=config,
+                    e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=len(proof_buf),
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, clocks=clocks.summary(), roofline=roofline,
+                    split=dict(prove_ms=(t1 - t0) * 1e3, verify_ms=(t2 - t1) * 1e3))
+        # MSM microbench (BASELINE config 5 at this GPU count = 1 rank's view)
+        try:
+            line["msm"] = msm_microbench(ctx, torch, dev, stream, args.msm_logn)
+        except Exception as e:  # never lose the headline line to the side measurement
+            line["msm"] = dict(error=repr(e))
+        if not args.no_cpu_baseline and world == 1:
+            sm, sn = sample_shape(m, n)
+            val, desc, legs = cpu_sample(m, n, sm, sn, threads=1)
+            line["cpu_baseline"] = dict(value=val, unit=UNIT, cores=1, kind="port", sample=desc)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def msm_microbench(ctx, torch, dev, stream, logn):
+    import numpy as np
+    n = 1 << logn
+    rng = np.random.default_rng(7)
+    base = ctx.dbg_scalar_mul(G64 * 4096, rand_scalars(rng, 4096))
+    bases = torch.frombuffer(bytearray(base), dtype=torch.uint8).to(dev).repeat(n // 4096).contiguous()
+    scal = torch.frombuffer(bytearray(rand_scalars(rng, n)), dtype=torch.uint8).to(dev)
+    out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    best = None
+    ctx.profile_enable(True)
+    ctx.profile_collect()
+    for it in range(6):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.msm_g1_device(bases.data_ptr(), scal.data_ptr(), n, out.data_ptr(), 0)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if it >= 3:
+            best = ms if best is None else min(best, ms)
+    acc_ms, acc_adds, acc_n = ctx.profile_collect()
+    ctx.profile_enable(False)
+    adds = ctx.last_msm_ec_adds
+    return dict(terms=n, window_bits=ctx.last_msm_window, ms=best, ec_adds=adds, ec_adds_per_s=adds / (best / 1e3),
+                accumulate_ms_avg=acc_ms / max(acc_n, 1), accumulate_adds_per_s=acc_adds / (acc_ms / 1e3) if acc_ms else None,
+                note="device-resident canonical inputs -> canonical affine result, includes Montgomery conversion + on-curve check")
+
+
+if __name__ == "__main__":
+    main()

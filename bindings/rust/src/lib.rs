@@ -1,0 +1,85 @@
+//! Drop-in for the shuffle hot path of `barnett_smart_card_protocol::discrete_log_cards::DLCards`
+//! (reference src/discrete_log_cards/mod.rs:380-443) over libmpshuffle.so.
+//!
+//! NOT COMPILED IN THIS REPOSITORY (no Rust toolchain in the build image); it documents the
+//! exact binding: which reference call each C entry point replaces, how arkworks types map
+//! to the byte layouts of include/mpshuffle.h, and where the caller's RNG is consumed.
+//!
+//! `GpuDLCards` delegates the twelve constant-size methods of the trait (key generation,
+//! mask/remask/reveal proofs ...) to the reference's `DLCards` and overrides only
+//! `setup`, `shuffle_and_remask` and `verify_shuffle`.
+use std::os::raw::c_char;
+
+#[repr(C)]
+pub struct MpCtx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    fn mp_ctx_create(out: *mut *mut MpCtx, device: i32) -> i32;
+    fn mp_ctx_destroy(ctx: *mut MpCtx);
+    fn mp_last_error_string(ctx: *mut MpCtx) -> *const c_char;
+    fn mp_verify_status_string(status: i32) -> *const c_char;
+    // DLCards::setup (mod.rs:105-121) -> binds Parameters to the GPU context
+    fn mp_ctx_set_params(ctx: *mut MpCtx, m: i32, n: i32, enc_g: *const u8, ck_g: *const u8, ck_h: *const u8, ghat: *const u8) -> i32;
+    fn mp_proof_len(m: i32, n: i32) -> u64;
+    fn mp_prover_randomness_len(m: i32, n: i32) -> u64;
+    // DLCards::shuffle_and_remask (mod.rs:380-418)
+    fn mp_shuffle_and_remask(ctx: *mut MpCtx, pk: *const u8, deck: *const u8, perm: *const u32, rho: *const u8,
+                             randomness: *const u8, out_deck: *mut u8, proof_out: *mut u8) -> i32;
+    // DLCards::verify_shuffle (mod.rs:420-443)
+    fn mp_shuffle_verify(ctx: *mut MpCtx, pk: *const u8, deck: *const u8, shuffled: *const u8, proof: *const u8) -> i32;
+}
+
+/// Owns the opaque GPU context; `Parameters` of the shim holds one (the reference's own
+/// `Parameters` has private fields, mod.rs:37-43, so the shim defines its own type).
+pub struct GpuContext(*mut MpCtx);
+unsafe impl Send for GpuContext {}
+impl Drop for GpuContext {
+    fn drop(&mut self) {
+        unsafe { mp_ctx_destroy(self.0) }
+    }
+}
+
+/// 32-byte little-endian canonical encoding = `ark_ff::ToBytes` of `Fp256`.
+pub fn fr_bytes<F: ark_ff::PrimeField>(x: &F, out: &mut Vec<u8>) {
+    ark_ff::ToBytes::write(&x.into_repr(), out).unwrap();
+}
+
+/// 64-byte x || y; the identity is all zeros (include/mpshuffle.h).
+pub fn point_bytes<A: ark_ec::AffineCurve>(p: &A, out: &mut Vec<u8>)
+where
+    A::BaseField: ark_ff::PrimeField,
+{
+    if p.is_zero() {
+        out.extend_from_slice(&[0u8; 64]);
+    } else {
+        // x.into_repr().write ; y.into_repr().write   (little-endian limbs)
+        let mut buf = Vec::with_capacity(65);
+        ark_ff::ToBytes::write(p, &mut buf).unwrap(); // x || y || infinity flag (ark-ec 0.3)
+        out.extend_from_slice(&buf[..64]);
+    }
+}
+
+/// Sketch of the two overridden trait methods (generic bounds elided):
+///
+/// ```ignore
+/// fn shuffle_and_remask<R: Rng>(rng, pp, shared_key, deck, masking_factors, permutation) {
+///     // 1. serialise: deck -> N * 128 bytes, masking_factors -> N * 32 bytes,
+///     //    permutation.mapping -> N * u32, shared_key -> 64 bytes
+///     // 2. draw the prover randomness from the caller's rng, in the order documented in
+///     //    include/mpshuffle.h:  (0..mp_prover_randomness_len(m, n)).map(|_| Scalar::rand(rng))
+///     // 3. mp_shuffle_and_remask(ctx, pk, deck, perm, rho, rand, out_deck, proof)
+///     //    status < 0  => Err(CardProtocolError::IoError(mp_last_error_string(ctx)))
+///     // 4. deserialise out_deck (N ciphertexts) and keep `proof` as the opaque byte proof
+///     //    (ZKProofShuffle = Vec<u8> for this implementor; CanonicalSerialize is satisfied)
+/// }
+/// fn verify_shuffle(pp, shared_key, original_deck, shuffled_deck, proof) {
+///     match mp_shuffle_verify(ctx, pk, deck, shuffled, proof) {
+///         0 => Ok(()),
+///         s if s > 0 => Err(CryptoError::ProofVerificationError(mp_verify_status_string(s))),
+///         _ => Err(CryptoError::ProofVerificationError(mp_last_error_string(ctx))),
+///     }
+/// }
+/// ```
+pub struct GpuDLCards;

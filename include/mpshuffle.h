@@ -142,6 +142,23 @@ int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* dec
 int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
                           const uint8_t* proof);
 
+/* Same as mp_shuffle_verify / mp_shuffle_prove for decks that are ALREADY resident in HBM
+ * (d_* = device pointers to the same canonical bytes): no deck crosses PCIe.  The host copies
+ * are still required -- the Fiat-Shamir transcript hashes them on the CPU. */
+int32_t mp_shuffle_verify_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
+                                   const uint8_t* shuffled_deck, const uint8_t* proof, const void* d_deck,
+                                   const void* d_shuffled_deck);
+int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
+                                  const uint8_t* shuffled_deck, const uint32_t* perm, const uint8_t* rho,
+                                  const uint8_t* randomness, uint8_t* proof_out, const void* d_shuffled_deck);
+
+/* ---- measurement ---------------------------------------------------------------------------
+ * Per-launch CUDA-event timing (on the context's stream) of the bucket-accumulation kernel, the
+ * dominant kernel of every MSM: collect returns the summed duration, the exact number of bucket
+ * additions (mixed XYZZ adds) those launches executed, and the launch count, then resets. */
+int32_t mp_profile_enable(mp_ctx* ctx, int32_t on);
+int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64_t* bucket_adds, uint64_t* launches);
+
 /* ---- debug / parity hooks (exercise single device primitives; not used by the protocol) */
 int32_t mp_dbg_fq_mul(mp_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 int32_t mp_dbg_point_add(mp_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out);

@@ -181,6 +181,19 @@ extern "C" int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void*
   return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
 }
 
+extern "C" int32_t mp_profile_enable(mp_ctx* ctx, int32_t on) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  msm_profile_enable(ctx->ws, on != 0);
+  return MP_OK;
+}
+extern "C" int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64_t* bucket_adds, uint64_t* launches) {
+  if (!ctx || !accumulate_ms || !bucket_adds || !launches) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = msm_profile_collect(ctx->ws, accumulate_ms, bucket_adds, launches);
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_profile_collect");
+  return MP_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // shuffle protocol entry points (bodies in shuffle.cu)
 // ------------------------------------------------------------------------------------------
@@ -220,6 +233,17 @@ extern "C" int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const u
 extern "C" int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
                                      const uint8_t* proof) {
   return shuffle_verify(ctx, pk, deck, shuffled_deck, proof);
+}
+
+extern "C" int32_t mp_shuffle_verify_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
+                                              const uint8_t* shuffled_deck, const uint8_t* proof, const void* d_deck,
+                                              const void* d_shuffled_deck) {
+  return shuffle_verify(ctx, pk, deck, shuffled_deck, proof, d_deck, d_shuffled_deck);
+}
+extern "C" int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
+                                             const uint8_t* shuffled_deck, const uint32_t* perm, const uint8_t* rho,
+                                             const uint8_t* randomness, uint8_t* proof_out, const void* d_shuffled_deck) {
+  return shuffle_prove(ctx, pk, deck, shuffled_deck, perm, rho, randomness, proof_out, d_shuffled_deck);
 }
 
 // ------------------------------------------------------------------------------------------

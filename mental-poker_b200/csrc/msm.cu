@@ -23,9 +23,17 @@ struct MsmWorkspace {
   void* buf[16] = {nullptr};
   size_t cap[16] = {0};
   int launches = 0;
+  // optional per-kernel timing of the bucket-accumulation kernel (roofline reporting)
+  bool profile = false;
+  struct Timed { cudaEvent_t e0, e1; int ncomp; uint32_t* entries; /* pinned: sorted-list length */ };
+  std::vector<Timed> timed;
+  uint32_t* pinned_counts = nullptr;
+  static constexpr int kMaxTimed = 8192;
   ~MsmWorkspace() {
     for (int i = 0; i < 16; i++)
       if (buf[i]) cudaFree(buf[i]);
+    for (auto& t : timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    if (pinned_counts) cudaFreeHost(pinned_counts);
   }
   template <typename T>
   cudaError_t get(int slot, size_t count, T** out) {
@@ -48,6 +56,21 @@ struct MsmWorkspace {
 MsmWorkspace* msm_workspace_create() { return new MsmWorkspace(); }
 void msm_workspace_destroy(MsmWorkspace* ws) { delete ws; }
 int msm_last_launches(const MsmWorkspace* ws) { return ws->launches; }
+void msm_profile_enable(MsmWorkspace* ws, bool on) { ws->profile = on; }
+cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, uint64_t* launches) {
+  *ms = 0; *adds = 0; *launches = 0;
+  cudaError_t err = cudaSuccess;
+  for (auto& t : ws->timed) {
+    cudaError_t e = cudaEventSynchronize(t.e1);
+    float f = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&f, t.e0, t.e1);
+    if (e != cudaSuccess) err = e;
+    *ms += f; *adds += (uint64_t)(*t.entries) * t.ncomp; *launches += 1;
+    cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+  }
+  ws->timed.clear();
+  return err;
+}
 
 int msm_pick_window(uint64_t avg_len) {
   // minimise W * (len + 2.8 * 2^(c-1)) over c, W = ceil(253 / c)
@@ -579,6 +602,18 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     ws->launches++;
   }
   if (max_chunks > 0) {
+    MsmWorkspace::Timed tm;
+    const bool timed = ws->profile && (int)ws->timed.size() < MsmWorkspace::kMaxTimed;
+    if (timed) {
+      if (!ws->pinned_counts) MP_CK(cudaMallocHost(&ws->pinned_counts, sizeof(uint32_t) * MsmWorkspace::kMaxTimed));
+      MP_CK(cudaEventCreate(&tm.e0));
+      MP_CK(cudaEventCreate(&tm.e1));
+      tm.ncomp = ncomp;
+      tm.entries = ws->pinned_counts + ws->timed.size();
+      // exact number of bucket additions = length of the sorted list (zero digits are skipped)
+      MP_CK(cudaMemcpyAsync(tm.entries, offsets + nbuckets, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      MP_CK(cudaEventRecord(tm.e0, stream));
+    }
     uint64_t threads = max_chunks * ncomp;
     unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
     if (ncomp == 1)
@@ -586,6 +621,10 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     else
       k_accumulate<2><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part);
     ws->launches++;
+    if (timed) {
+      MP_CK(cudaEventRecord(tm.e1, stream));
+      ws->timed.push_back(tm);
+    }
   }
   k_fixup<<<(unsigned)((nbuckets * ncomp + 127) / 128), 128, 0, stream>>>(offsets, nbuckets, ncomp, bucket_sums, part);
   k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(bucket_sums, nwin, B, L, ncomp, segS, segT);

@@ -49,6 +49,11 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
 // number of kernels the last msm_run launched / EC additions it performed (host-side count
 // of scheduled bucket additions, for EC-adds/s reporting)
 int msm_last_launches(const MsmWorkspace* ws);
+// Per-launch CUDA-event timing of k_accumulate (the dominant kernel) on the launch stream.
+// collect() waits for the recorded events, returns the summed duration, the bucket additions
+// those launches were scheduled with and the launch count, and clears the list.
+void msm_profile_enable(MsmWorkspace* ws, bool on);
+cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, uint64_t* launches);
 
 // canonical 64-byte points -> Montgomery affine (validating on-curve; bad points set *d_bad)
 cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,

@@ -312,8 +312,10 @@ static void absorb_statement(Transcript& fs, const ShuffleState* S, const uint8_
 // verify
 // ------------------------------------------------------------------------------------------
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                       const uint8_t* proof) {
+                       const uint8_t* proof, const void* deck_src, const void* deck2_src) {
   if (!ctx || !pk || !deck || !deck2 || !proof) return MP_ERR_INVALID_ARG;
+  if (!deck_src) deck_src = deck;     // host copy doubles as the transfer source
+  if (!deck2_src) deck2_src = deck2;  // (a device pointer here means the deck is already resident in HBM)
   ShuffleState* S = ctx->shuffle;
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
   cudaSetDevice(ctx->device);
@@ -334,9 +336,9 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_canon, deck, N * 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(d_ct_canon + N * 128, proof + L.meE + 128 * (size_t)m, 128, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_canon + (N + 1) * 128, deck2, N * 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon + (N + 1) * 128, deck2_src, N * 128, cudaMemcpyDefault, ctx->stream));
   {
     std::vector<uint8_t> tail((2 * (size_t)m + 2) * 128, 0);
     memcpy(tail.data(), proof + L.meE, 2 * (size_t)m * 128);
@@ -606,8 +608,9 @@ struct RandCursor {
 };
 
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint32_t* perm,
-                      const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out) {
+                      const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out, const void* deck2_src) {
   if (!ctx || !pk || !deck || !deck2 || !perm || !rho || !rand || !proof_out) return MP_ERR_INVALID_ARG;
+  if (!deck2_src) deck2_src = deck2;
   ShuffleState* S = ctx->shuffle;
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
   cudaSetDevice(ctx->device);
@@ -655,7 +658,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
 
   // ---- uploads that do not depend on any challenge
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-  CK(cudaMemcpyAsync(d_ct_canon, deck2, N * 128, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ct_canon, deck2_src, N * 128, cudaMemcpyDefault, st));
   {
     uint8_t tail[256];
     memset(tail, 0, sizeof tail);

@@ -18,6 +18,9 @@
 #include <stdint.h>
 
 struct mp_ctx;
+// `*_src` arguments: where the device copy of a deck is taken from -- the host buffer itself
+// (default) or a device pointer when the deck is already resident in HBM.  The host copy is
+// always needed: the transcript hashes it on the CPU.
 
 namespace mp {
 
@@ -36,8 +39,9 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
 int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k,
                              uint64_t len, uint8_t* out);
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                      const uint32_t* perm, const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out);
+                      const uint32_t* perm, const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out,
+                      const void* deck2_src = nullptr);
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                       const uint8_t* proof);
+                       const uint8_t* proof, const void* deck_src = nullptr, const void* deck2_src = nullptr);
 
 }  // namespace mp
