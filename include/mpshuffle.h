@@ -76,6 +76,15 @@ int32_t mp_msm_g1_device(mp_ctx* ctx, const void* d_bases, const void* d_scalars
                          int32_t window_bits, void* d_out);
 int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
                          int32_t window_bits, void* d_out);
+/* Window-range split of one large MSM across GPUs (BASELINE north_star):
+ * with W = mp_msm_num_windows(c) signed c-bit windows, this computes only windows
+ * [w_begin, w_begin + w_count) and returns  P = sum_w 2^(c*(w - w_begin)) * (window sum w),  so
+ *   full MSM = sum over ranks of 2^(c * w_begin_r) * P_r
+ * -- the ranks exchange 64-byte partials (all-gather) and fold them with one tiny MSM whose
+ * scalars are the powers 2^(c * w_begin_r).  Inputs are replicated on every rank. */
+int32_t mp_msm_num_windows(int32_t window_bits);
+int32_t mp_msm_g1_windows_device(mp_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                                 int32_t window_bits, int32_t w_begin, int32_t w_count, void* d_out);
 /* EC additions scheduled by the last MSM on this context (bucket adds + reduction adds),
  * and the window width it used. */
 uint64_t mp_last_msm_ec_adds(mp_ctx* ctx);
@@ -164,7 +173,9 @@ int32_t mp_dbg_fq_mul(mp_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t 
 int32_t mp_dbg_point_add(mp_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out);
 int32_t mp_dbg_scalar_mul(mp_ctx* ctx, const uint8_t* p, const uint8_t* k, uint64_t n, uint8_t* out);
 /* integer-pipe microbenchmarks: returns milliseconds for `iters` dependent-chain iterations
- * on a full-chip grid; *ops receives the number of counted operations executed. */
+ * on a full-chip grid; *ops receives the number of counted operations executed.  which: 0 IMAD.WIDE,
+ * 1 IMAD.LO, 2 fq_mul, 3 xyzz_madd, 4 fq_sqr, 5 carry-chained IMAD.WIDE pairs (counted as
+ * wide multiply-adds), 6 IMAD.WIDE + IADD 1:1 (counted as wide multiply-adds). */
 int32_t mp_dbg_bench(mp_ctx* ctx, int32_t which, int32_t iters, float* ms, double* ops);
 
 #ifdef __cplusplus

@@ -10,3 +10,4 @@ There is no CPU fallback: importing works without a GPU (so symbols can be inspe
 every compute entry point needs a CUDA device and raises otherwise.
 """
 from ._lib import lib, lib_path, MpError, check, Context  # noqa: F401
+from . import dist  # noqa: F401

@@ -27,6 +27,8 @@ SIGNATURES = {
     "mp_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
     "mp_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp_msm_num_windows": (_i32, [_i32]),
+    "mp_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
     "mp_last_msm_ec_adds": (_u64, [_vp]),
     "mp_last_msm_window": (_i32, [_vp]),
     "mp_ctx_set_params": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp]),
@@ -123,6 +125,9 @@ class Context:
 
     def ct_msm_device(self, d_deck, d_scalars, n, d_out, window_bits=0):
         check(self.h, lib.mp_ct_msm_device(self.h, d_deck, d_scalars, n, window_bits, d_out))
+
+    def msm_g1_windows_device(self, d_bases, d_scalars, n, d_out, window_bits, w_begin, w_count):
+        check(self.h, lib.mp_msm_g1_windows_device(self.h, d_bases, d_scalars, n, window_bits, w_begin, w_count, d_out))
 
     @property
     def last_msm_ec_adds(self):

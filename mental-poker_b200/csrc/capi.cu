@@ -108,7 +108,8 @@ static uint64_t scheduled_ec_adds(uint64_t n, int c, int ncomp) {
 
 // d_points canonical (n*ncomp points), d_scalars canonical, d_out canonical (ncomp points)
 static int32_t msm_device_common(mp_ctx* ctx, const void* d_points, const void* d_scalars,
-                                 uint64_t n, int ncomp, int32_t window_bits, void* d_out) {
+                                 uint64_t n, int ncomp, int32_t window_bits, void* d_out,
+                                 int w_begin = 0, int w_count = -1) {
   if (!ctx || (!d_points && n) || (!d_scalars && n) || !d_out) return MP_ERR_INVALID_ARG;
   if (n >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "MSM size %llu too large", (unsigned long long)n);
   cudaSetDevice(ctx->device);
@@ -116,7 +117,9 @@ static int32_t msm_device_common(mp_ctx* ctx, const void* d_points, const void* 
   int c = window_bits > 0 ? window_bits : msm_pick_window(n);
   if (c < 2 || c > 16) return ctx->fail(MP_ERR_INVALID_ARG, "window_bits %d out of range [2,16]", c);
   ctx->last_window = c;
-  ctx->last_ec_adds = scheduled_ec_adds(n, c, ncomp);
+  ctx->last_ec_adds = scheduled_ec_adds(n, c, ncomp) * (uint64_t)(w_count < 0 ? msm_num_windows(c) - w_begin : w_count) / msm_num_windows(c);
+  if (w_begin < 0 || (w_count >= 0 && w_begin + w_count > msm_num_windows(c)) || w_count == 0)
+    return ctx->fail(MP_ERR_INVALID_ARG, "window range [%d, +%d) outside [0, %d)", w_begin, w_count, msm_num_windows(c));
   affine* mont = (affine*)ctx->scratch(mp_ctx::kSlotPointsMont, sizeof(affine) * n * ncomp);
   xyzz* res = (xyzz*)ctx->scratch(mp_ctx::kSlotMsmOut, sizeof(xyzz) * ncomp);
   int* bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
@@ -127,7 +130,7 @@ static int32_t msm_device_common(mp_ctx* ctx, const void* d_points, const void* 
     return ctx->cuda_fail(e, "points_to_mont");
   ctx->launches += n ? 1 : 0;
   MsmJob job{0, 0, (uint32_t)n};
-  if ((e = msm_run(ctx->ws, (const uint32_t*)d_scalars, n, mont, ncomp, &job, 1, c, res, ctx->stream)) != cudaSuccess)
+  if ((e = msm_run(ctx->ws, (const uint32_t*)d_scalars, n, mont, ncomp, &job, 1, c, res, ctx->stream, w_begin, w_count)) != cudaSuccess)
     return ctx->cuda_fail(e, "msm_run");
   ctx->launches += msm_last_launches(ctx->ws);
   if ((e = xyzz_to_canonical(res, (uint32_t*)d_out, ncomp, ctx->stream)) != cudaSuccess)
@@ -246,6 +249,15 @@ extern "C" int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, con
   return shuffle_prove(ctx, pk, deck, shuffled_deck, perm, rho, randomness, proof_out, d_shuffled_deck);
 }
 
+extern "C" int32_t mp_msm_num_windows(int32_t window_bits) {
+  return (window_bits >= 2 && window_bits <= 16) ? msm_num_windows(window_bits) : 0;
+}
+extern "C" int32_t mp_msm_g1_windows_device(mp_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                                            int32_t window_bits, int32_t w_begin, int32_t w_count, void* d_out) {
+  if (window_bits < 2 || window_bits > 16) return ctx ? ctx->fail(MP_ERR_INVALID_ARG, "explicit window_bits required") : MP_ERR_INVALID_ARG;
+  return msm_device_common(ctx, d_bases, d_scalars, n, 1, window_bits, d_out, w_begin, w_count);
+}
+
 // ------------------------------------------------------------------------------------------
 // debug / parity hooks
 // ------------------------------------------------------------------------------------------
@@ -357,6 +369,55 @@ __global__ void __launch_bounds__(128) k_bench_fq_mul(uint32_t* out, int iters, 
   for (int it = 0; it < iters; it++) { x = fq_mul(x, y); y = fq_mul(y, x); }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x.v[0] ^ y.v[7];
 }
+__global__ void __launch_bounds__(128) k_bench_fq_sqr(uint32_t* out, int iters, uint32_t seed) {
+  fq x = fq_one(), y = fq_r2();
+  x.v[0] ^= seed + threadIdx.x;
+  y.v[0] ^= blockIdx.x;
+  x = fq_reduce_weak(x); y = fq_reduce_weak(y);
+  for (int it = 0; it < iters; it++) { x = fq_sqr(x); y = fq_sqr(y); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x.v[0] ^ y.v[7];
+}
+// carry-chained wide multiply-adds (the form fq_mul uses): 8 chains of 4 lo/hi pairs
+__global__ void __launch_bounds__(256) k_bench_imad_wide_cc(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  uint32_t acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) acc[k] = k + a;
+  for (int it = 0; it < iters; it++) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      MP_ROW_CHAIN(acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7], acc[8], a, a + 1, a + 2, a + 3, b + r);
+    }
+#endif
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 9; k++) s ^= acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// 1:1 mix of independent wide multiply-adds (FMA pipe) and 3-input adds (ALU pipe)
+__global__ void __launch_bounds__(256) k_bench_mix(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  unsigned long long acc[8];
+  uint32_t s[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { acc[k] = k + a; s[k] = k * b; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b + r));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(s[k]) : "r"(a + r));
+      }
+    }
+  }
+  unsigned long long x = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) x ^= acc[k] + s[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)x ^ (uint32_t)(x >> 32);
+}
 __global__ void __launch_bounds__(128) k_bench_madd(uint32_t* out, int iters, uint32_t seed) {
   // G in canonical form -> Montgomery; acc walks G, 2G, 3G, ... (no special cases hit)
   const uint32_t g[16] = {0xc943cfcau, 0x3d723d8bu, 0x0d1819e0u, 0xdeacfd9bu, 0x5a40f0c7u, 0x7beced41u,
@@ -385,6 +446,9 @@ extern "C" int32_t mp_dbg_bench(mp_ctx* ctx, int32_t which, int32_t iters, float
       case 1: k_bench_imad_lo<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
       case 2: k_bench_fq_mul<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters * 2; break;
       case 3: k_bench_madd<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters; break;
+      case 4: k_bench_fq_sqr<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters * 2; break;
+      case 5: k_bench_imad_wide_cc<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
+      case 6: k_bench_mix<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
       default: cudaEventDestroy(e0); cudaEventDestroy(e1); return MP_ERR_INVALID_ARG;
     }
     cudaEventRecord(e1, ctx->stream);

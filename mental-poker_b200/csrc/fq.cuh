@@ -286,6 +286,127 @@ inline void fq_mul_wide(uint32_t* T, const fq& a, const fq& b) {
 #endif
 
 // ------------------------------------------------------------------------------------------
+// Dedicated squaring: T[16] = a^2 with 28 off-diagonal + 8 diagonal products (36 IMAD.WIDE
+// instead of 64); the doubling and the diagonal add run on the ALU pipe, which has slack.
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define MP_CHAIN1(c0, c1, c2, a0, b)                      \
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"                 \
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"                \
+      "addc.u32 %2, %2, 0;"                               \
+      : "+r"(c0), "+r"(c1), "+r"(c2)                      \
+      : "r"(a0), "r"(b))
+#define MP_CHAIN2(c0, c1, c2, c3, c4, a0, a1, b)          \
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"                 \
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"                \
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"                \
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"                \
+      "addc.u32 %4, %4, 0;"                               \
+      : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)  \
+      : "r"(a0), "r"(a1), "r"(b))
+#define MP_CHAIN3(c0, c1, c2, c3, c4, c5, c6, a0, a1, a2, b)                  \
+  asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"                                    \
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"                                   \
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"                                   \
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"                                   \
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"                                   \
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"                                   \
+      "addc.u32 %6, %6, 0;"                                                   \
+      : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6)  \
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b))
+
+__device__ __forceinline__ void fq_sqr_wide(uint32_t* __restrict__ T, const fq& a) {
+  // ev[k] = word k of the off-diagonal products at even word offsets i + j;
+  // od[k] = word k + 1 of those at odd offsets (same convention as fq_mul_wide).
+  uint32_t ev[16], od[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
+  const uint32_t* v = a.v;
+  // row 0: odd offsets j = 1,3,5,7 -> od[0..7]; even offsets j = 2,4,6 -> ev[2..7]
+  MP_ROW_CHAIN(od[0], od[1], od[2], od[3], od[4], od[5], od[6], od[7], od[8], v[1], v[3], v[5], v[7], v[0]);
+  MP_CHAIN3(ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], v[2], v[4], v[6], v[0]);
+  // row 1: odd offsets j = 2,4,6 -> od[2..7]; even offsets j = 3,5,7 -> ev[4..9]
+  MP_CHAIN3(od[2], od[3], od[4], od[5], od[6], od[7], od[8], v[2], v[4], v[6], v[1]);
+  MP_CHAIN3(ev[4], ev[5], ev[6], ev[7], ev[8], ev[9], ev[10], v[3], v[5], v[7], v[1]);
+  // row 2: odd j = 3,5,7 -> od[4..9]; even j = 4,6 -> ev[6..9]
+  MP_CHAIN3(od[4], od[5], od[6], od[7], od[8], od[9], od[10], v[3], v[5], v[7], v[2]);
+  MP_CHAIN2(ev[6], ev[7], ev[8], ev[9], ev[10], v[4], v[6], v[2]);
+  // row 3: odd j = 4,6 -> od[6..9]; even j = 5,7 -> ev[8..11]
+  MP_CHAIN2(od[6], od[7], od[8], od[9], od[10], v[4], v[6], v[3]);
+  MP_CHAIN2(ev[8], ev[9], ev[10], ev[11], ev[12], v[5], v[7], v[3]);
+  // row 4: odd j = 5,7 -> od[8..11]; even j = 6 -> ev[10..11]
+  MP_CHAIN2(od[8], od[9], od[10], od[11], od[12], v[5], v[7], v[4]);
+  MP_CHAIN1(ev[10], ev[11], ev[12], v[6], v[4]);
+  // row 5: odd j = 6 -> od[10..11]; even j = 7 -> ev[12..13]
+  MP_CHAIN1(od[10], od[11], od[12], v[6], v[5]);
+  MP_CHAIN1(ev[12], ev[13], ev[14], v[7], v[5]);
+  // row 6: odd j = 7 -> od[12..13]
+  MP_CHAIN1(od[12], od[13], od[14], v[7], v[6]);
+  // off = ev + (od << 32): words 1..15 (word 0 is zero: the lowest off-diagonal offset is 1)
+  uint32_t off[16];
+  off[0] = 0;
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;"
+      : "=r"(off[1]), "=r"(off[2]), "=r"(off[3]), "=r"(off[4]), "=r"(off[5]), "=r"(off[6]), "=r"(off[7]),
+        "=r"(off[8]), "=r"(off[9]), "=r"(off[10]), "=r"(off[11]), "=r"(off[12]), "=r"(off[13]),
+        "=r"(off[14]), "=r"(off[15])
+      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]),
+        "r"(ev[14]), "r"(ev[15]), "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]),
+        "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]),
+        "r"(od[12]), "r"(od[13]), "r"(od[14]));
+  // dbl = 2 * off (funnel shifts), then T = dbl + sum a_i^2 * 2^(64 i)
+  uint32_t dbl[16];
+  dbl[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 16; i++) dbl[i] = __funnelshift_l(off[i - 1], off[i], 1);
+  uint32_t dl[8], dh[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    dl[i] = v[i] * v[i];
+    dh[i] = __umulhi(v[i], v[i]);
+  }
+  asm("add.cc.u32 %0, %16, %32;\n\t"
+      "addc.cc.u32 %1, %17, %33;\n\t"
+      "addc.cc.u32 %2, %18, %34;\n\t"
+      "addc.cc.u32 %3, %19, %35;\n\t"
+      "addc.cc.u32 %4, %20, %36;\n\t"
+      "addc.cc.u32 %5, %21, %37;\n\t"
+      "addc.cc.u32 %6, %22, %38;\n\t"
+      "addc.cc.u32 %7, %23, %39;\n\t"
+      "addc.cc.u32 %8, %24, %40;\n\t"
+      "addc.cc.u32 %9, %25, %41;\n\t"
+      "addc.cc.u32 %10, %26, %42;\n\t"
+      "addc.cc.u32 %11, %27, %43;\n\t"
+      "addc.cc.u32 %12, %28, %44;\n\t"
+      "addc.cc.u32 %13, %29, %45;\n\t"
+      "addc.cc.u32 %14, %30, %46;\n\t"
+      "addc.u32 %15, %31, %47;"
+      : "=r"(T[0]), "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]),
+        "=r"(T[8]), "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+      : "r"(dbl[0]), "r"(dbl[1]), "r"(dbl[2]), "r"(dbl[3]), "r"(dbl[4]), "r"(dbl[5]), "r"(dbl[6]), "r"(dbl[7]),
+        "r"(dbl[8]), "r"(dbl[9]), "r"(dbl[10]), "r"(dbl[11]), "r"(dbl[12]), "r"(dbl[13]), "r"(dbl[14]), "r"(dbl[15]),
+        "r"(dl[0]), "r"(dh[0]), "r"(dl[1]), "r"(dh[1]), "r"(dl[2]), "r"(dh[2]), "r"(dl[3]), "r"(dh[3]),
+        "r"(dl[4]), "r"(dh[4]), "r"(dl[5]), "r"(dh[5]), "r"(dl[6]), "r"(dh[6]), "r"(dl[7]), "r"(dh[7]));
+}
+#else
+inline void fq_sqr_wide(uint32_t* T, const fq& a) { fq_mul_wide(T, a, a); }
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Sparse-prime Montgomery reduction:  r = (T + M*p) / 2^256,  M = T_lo * (-p^-1) mod 2^256.
 //   k  = (17 + 2^59) * T_lo  mod 2^64                       (2 words)
 //   M  = k*2^192 - T_lo      mod 2^256,  e = borrow of that subtraction
@@ -429,7 +550,11 @@ MP_HD fq fq_mul(const fq& a, const fq& b) {
   fq_mul_wide(T, a, b);
   return fq_mont_reduce(T);
 }
-MP_HD fq fq_sqr(const fq& a) { return fq_mul(a, a); }
+MP_HD fq fq_sqr(const fq& a) {
+  uint32_t T[16];
+  fq_sqr_wide(T, a);
+  return fq_mont_reduce(T);
+}
 
 // canonical integer (< p, non-Montgomery)  ->  Montgomery [2]
 MP_HD fq fq_to_mont(const fq& a) { return fq_mul(a, fq_r2()); }

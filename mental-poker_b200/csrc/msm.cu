@@ -12,7 +12,8 @@ namespace mp {
 // ------------------------------------------------------------------------------------------
 // tunables
 // ------------------------------------------------------------------------------------------
-static constexpr int kChunk = 32;         // sorted entries per accumulate thread
+static constexpr int kChunkMin = 32;      // sorted entries per accumulate thread (small launches)
+static constexpr int kChunkMax = 128;     // ... when the launch still fills the chip several times over
 static constexpr int kAccThreads = 128;   // accumulate block size
 static constexpr int kSegLen = 16;        // buckets per k_reduce_seg thread
 static constexpr int kWinThreads = 256;   // k_reduce_win block size
@@ -191,7 +192,7 @@ cudaError_t xyzz_to_canonical(const xyzz* d_in, uint32_t* d_out, uint64_t n, cud
 // digits[w * ns + i] = (|d| - 1) | (d < 0) << 31, or kNoDigit when d == 0.
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars,
                                                 uint32_t* __restrict__ digits, uint64_t ns, int c,
-                                                int W) {
+                                                int w_begin, int W) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ns) return;
   uint32_t s[9];
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
   s[8] = 0;
   const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
   uint32_t carry = 0;
-  for (int w = 0; w < W; w++) {
+  for (int w = 0; w < w_begin + W; w++) {  // windows below w_begin only feed the carry
     int pos = w * c;
     uint32_t raw = 0;
     if (pos < 256) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
       enc = raw == 0 ? kNoDigit : (raw - 1u);
       carry = 0;
     }
-    digits[(uint64_t)w * ns + i] = enc;
+    if (w >= w_begin) digits[(uint64_t)(w - w_begin) * ns + i] = enc;
   }
 }
 
@@ -351,7 +352,7 @@ template <int NCOMP>
 __global__ void __launch_bounds__(kAccThreads)
     k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                  uint64_t nbuckets, const affine* __restrict__ points, xyzz* __restrict__ bucket_sums,
-                 xyzz* __restrict__ part) {
+                 xyzz* __restrict__ part, uint32_t* __restrict__ chunk_bucket, uint32_t kChunk) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t t = g / NCOMP;
   const uint32_t comp = (uint32_t)(g % NCOMP);
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kAccThreads)
     if (offsets[mid] <= pos) lo = mid; else hi = mid;
   }
   uint64_t b = lo;
+  if (comp == 0) chunk_bucket[t] = (uint32_t)b;
   uint64_t next = offsets[b + 1];
   bool first = true;
   xyzz acc = xyzz_identity();
@@ -397,38 +399,38 @@ __global__ void __launch_bounds__(kAccThreads)
   else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
 }
 
-// Thread per (bucket, comp): total = [run that started mid-chunk] + sum of the `part`s of
-// every chunk whose first entry lies inside the bucket.
-__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ offsets,
-                                               uint64_t nbuckets, int ncomp,
-                                               xyzz* __restrict__ bucket_sums,
-                                               const xyzz* __restrict__ part) {
-  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nbuckets * ncomp) return;
-  uint64_t b = g / ncomp;
-  uint32_t comp = (uint32_t)(g % ncomp);
-  uint64_t o0 = offsets[b], o1 = offsets[b + 1];
+// Stitch: thread per (chunk, comp).  A bucket whose entries straddle chunk boundaries has its sum
+// split between bucket_sums[b] (the run that started inside a chunk) and the `part` of every
+// chunk whose first entry lies in the bucket.  The first such chunk ("leader") folds the parts
+// into bucket_sums[b]; only buckets that contain a chunk boundary are touched at all.
+__global__ void __launch_bounds__(128) k_stitch(const uint32_t* __restrict__ offsets, uint64_t nbuckets,
+                                                const uint32_t* __restrict__ chunk_bucket, int ncomp,
+                                                xyzz* __restrict__ bucket_sums, const xyzz* __restrict__ part,
+                                                uint32_t kChunk) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t t = g / ncomp;
+  const uint32_t comp = (uint32_t)(g % ncomp);
+  const uint64_t E = offsets[nbuckets];
+  const uint64_t nchunks = (E + kChunk - 1) / kChunk;
+  if (t >= nchunks) return;
+  const uint32_t b = chunk_bucket[t];
+  if (t > 0 && chunk_bucket[t - 1] == b) return;  // not the first chunk starting in this bucket
   xyzz acc = xyzz_identity();
-  if (o1 > o0) {
-    if (o0 % kChunk != 0) acc = xyzz_load(bucket_sums + g);
-    uint64_t t0 = (o0 + kChunk - 1) / kChunk, t1 = (o1 + kChunk - 1) / kChunk;
-    for (uint64_t t = t0; t < t1; t++) {
-      xyzz p = xyzz_load(part + t * ncomp + comp);
-      xyzz_add_ni(acc, p);
-    }
+  if (offsets[b] % kChunk != 0) acc = xyzz_load(bucket_sums + (uint64_t)b * ncomp + comp);
+  for (uint64_t u = t; u < nchunks && chunk_bucket[u] == b; u++) {
+    xyzz p = xyzz_load(part + u * ncomp + comp);
+    xyzz_add_ni(acc, p);
   }
-  xyzz_store(bucket_sums + g, acc);
+  xyzz_store(bucket_sums + (uint64_t)b * ncomp + comp, acc);
 }
 
-// ------------------------------------------------------------------------------------------
-// bucket reduction
-// ------------------------------------------------------------------------------------------
-// Thread per (window, segment, comp): S = sum of the segment's L buckets,
-// T = sum_{i=0..L-1} (i+1) * B_i   (running-sum sweep from the top of the segment).
-__global__ void __launch_bounds__(128) k_reduce_seg(const xyzz* __restrict__ bucket_sums,
-                                                    uint64_t nwin, uint32_t B, uint32_t L,
-                                                    int ncomp, xyzz* __restrict__ segS,
-                                                    xyzz* __restrict__ segT) {
+// Thread per (window, segment, comp): running-sum sweep over the segment's L buckets from the top,
+//   S = sum of the segment's buckets,   T = sum_{i=0..L-1} (i+1) * B_i.
+// Empty buckets are recognised from the offsets (bucket_sums is never zero-filled).
+__global__ void __launch_bounds__(128, 3) k_reduce_seg(const uint32_t* __restrict__ offsets,
+                                                    const xyzz* __restrict__ bucket_sums, uint64_t nwin,
+                                                    uint32_t B, uint32_t L, int ncomp,
+                                                    xyzz* __restrict__ segS, xyzz* __restrict__ segT) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nseg = B / L;
   if (g >= nwin * nseg * ncomp) return;
@@ -436,13 +438,44 @@ __global__ void __launch_bounds__(128) k_reduce_seg(const xyzz* __restrict__ buc
   uint64_t ws = g / ncomp;  // window * nseg + seg
   uint64_t first_bucket = ws * L;
   xyzz running = xyzz_identity(), acc = xyzz_identity();
+  uint32_t o1 = offsets[first_bucket + L];
   for (int i = (int)L - 1; i >= 0; i--) {
-    xyzz bkt = xyzz_load(bucket_sums + (first_bucket + i) * ncomp + comp);
-    xyzz_add_ni(running, bkt);
-    xyzz_add_ni(acc, running);
+    const uint64_t b = first_bucket + i;
+    const uint32_t o0 = offsets[b];
+    if (o1 > o0) {
+      xyzz bkt = xyzz_load(bucket_sums + b * ncomp + comp);
+      xyzz_add(running, bkt);
+    }
+    xyzz_add(acc, running);
+    o1 = o0;
   }
   xyzz_store(segS + g, running);
   xyzz_store(segT + g, acc);
+}
+
+// Small-nseg variant of the per-window combine: thread per (window, comp), serial over the
+// window's segments.  out = sum_s T_s + L * sum_s s * S_s.
+__global__ void __launch_bounds__(64) k_reduce_win_serial(const xyzz* __restrict__ segS,
+                                                          const xyzz* __restrict__ segT, uint64_t nwincomp,
+                                                          uint32_t nseg, uint32_t L, int ncomp,
+                                                          xyzz* __restrict__ win_out) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nwincomp) return;
+  const uint32_t comp = (uint32_t)(g % ncomp);
+  const uint64_t win = g / ncomp;
+  const xyzz* S = segS + win * nseg * ncomp + comp;
+  const xyzz* T = segT + win * nseg * ncomp + comp;
+  xyzz run = xyzz_identity(), lsum = xyzz_identity(), tsum = xyzz_load(T);
+  for (uint32_t s = nseg - 1; s >= 1; s--) {
+    xyzz a = xyzz_load(S + (uint64_t)s * ncomp);
+    xyzz_add_ni(run, a);
+    xyzz_add_ni(lsum, run);
+    xyzz tv = xyzz_load(T + (uint64_t)s * ncomp);
+    xyzz_add_ni(tsum, tv);
+  }
+  for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(lsum);
+  xyzz_add_ni(tsum, lsum);
+  xyzz_store(win_out + g, tsum);
 }
 
 // block-wide sum of one xyzz per thread (kWinThreads threads); result valid in thread 0
@@ -515,17 +548,23 @@ __global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restri
   }
 }
 
-// Thread per (job, comp): Horner over the job's W window sums.
+// Thread per (job, comp): Horner over the job's W window sums.  253 dependent doublings are the
+// latency floor of every MSM call, so the group operations are inlined here (registers only,
+// no ABI calls) and the loop is kept rolled.
 __global__ void __launch_bounds__(32) k_fold(const xyzz* __restrict__ win_out, int njobs, int W,
                                              int c, int ncomp, xyzz* __restrict__ out) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= njobs * ncomp) return;
   int job = g / ncomp, comp = g % ncomp;
   xyzz acc = xyzz_load(win_out + ((uint64_t)(job * W + W - 1)) * ncomp + comp);
+#pragma unroll 1
   for (int w = W - 2; w >= 0; w--) {
-    for (int k = 0; k < c; k++) xyzz_dbl_ni(acc);
+    if (!xyzz_is_identity(acc)) {
+#pragma unroll 1
+      for (int k = 0; k < c; k++) acc = xyzz_dbl(acc);
+    }
     xyzz v = xyzz_load(win_out + ((uint64_t)(job * W + w)) * ncomp + comp);
-    xyzz_add_ni(acc, v);
+    xyzz_add(acc, v);
   }
   xyzz_store(out + g, acc);
 }
@@ -541,14 +580,20 @@ __global__ void __launch_bounds__(32) k_fold(const xyzz* __restrict__ win_out, i
 
 cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
                     const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
-                    xyzz* d_out, cudaStream_t stream) {
+                    xyzz* d_out, cudaStream_t stream, int w_begin, int w_count) {
   ws->launches = 0;
   if (njobs <= 0) return cudaSuccess;
   if (ncomp != 1 && ncomp != 2) return cudaErrorInvalidValue;
   if (c < 2 || c > 20) return cudaErrorInvalidValue;
-  const int W = (253 + c - 1) / c;
+  const int W_all = (253 + c - 1) / c;
+  if (w_count < 0) w_count = W_all - w_begin;
+  if (w_begin < 0 || w_count < 1 || w_begin + w_count > W_all) return cudaErrorInvalidValue;
+  const int W = w_count;  // windows handled by this call: [w_begin, w_begin + W)
   const uint32_t B = 1u << (c - 1);
-  const uint32_t L = std::min<uint32_t>(kSegLen, B);
+  // buckets per reduce_seg thread: as long as the chip stays full (>= ~150k threads), longer
+  // segments leave fewer segment sums for the per-window combine
+  uint32_t L = std::min<uint32_t>(kSegLen, B);
+  while (L < B && L < 256 && (uint64_t)njobs * W * ncomp * (B / (2 * L)) >= 150000) L *= 2;
   const uint32_t nseg = B / L;
   const uint64_t nwin = (uint64_t)njobs * W;
   const uint64_t nbuckets = nwin * B;
@@ -561,12 +606,16 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   }
   const uint64_t max_entries = total_terms * W;
   if (max_entries >= (1ull << 32) || nbuckets >= (1ull << 32)) return cudaErrorInvalidValue;
+  // chunk length: longer chunks mean fewer partial sums to stitch; keep >= ~600k threads in flight
+  uint32_t kChunk = kChunkMin;
+  while (kChunk < kChunkMax && max_entries * ncomp / (2 * kChunk) >= 600000) kChunk *= 2;
   const uint64_t max_chunks = (max_entries + kChunk - 1) / kChunk;
   const uint64_t ntiles = (nbuckets + 1 + kScanTile - 1) / kScanTile;
 
   uint32_t *digits, *counts, *offsets, *cursor, *sorted, *tile_sums;
   MsmJob* d_jobs;
   xyzz *bucket_sums, *part, *segS, *segT, *win_out;
+  uint32_t* chunk_bucket;
   MP_CK(ws->get(0, n_scalars * W, &digits));
   MP_CK(ws->get(1, nbuckets + 1, &counts));
   MP_CK(ws->get(2, nbuckets + 1, &offsets));
@@ -576,6 +625,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   MP_CK(ws->get(6, (size_t)njobs, &d_jobs));
   MP_CK(ws->get(7, nbuckets * ncomp, &bucket_sums));
   MP_CK(ws->get(8, max_chunks * ncomp, &part));
+  MP_CK(ws->get(12, max_chunks + 1, &chunk_bucket));
   MP_CK(ws->get(9, nwin * nseg * ncomp, &segS));
   MP_CK(ws->get(10, nwin * nseg * ncomp, &segT));
   MP_CK(ws->get(11, nwin * ncomp, &win_out));
@@ -584,7 +634,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   MP_CK(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nbuckets + 1), stream));
 
   if (n_scalars > 0) {
-    k_digits<<<(unsigned)((n_scalars + 255) / 256), 256, 0, stream>>>(d_scalars, digits, n_scalars, c, W);
+    k_digits<<<(unsigned)((n_scalars + 255) / 256), 256, 0, stream>>>(d_scalars, digits, n_scalars, c, w_begin, W);
     ws->launches++;
   }
   if (max_len > 0) {
@@ -617,20 +667,26 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     uint64_t threads = max_chunks * ncomp;
     unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
     if (ncomp == 1)
-      k_accumulate<1><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part);
+      k_accumulate<1><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk);
     else
-      k_accumulate<2><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part);
+      k_accumulate<2><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk);
     ws->launches++;
     if (timed) {
       MP_CK(cudaEventRecord(tm.e1, stream));
       ws->timed.push_back(tm);
     }
   }
-  k_fixup<<<(unsigned)((nbuckets * ncomp + 127) / 128), 128, 0, stream>>>(offsets, nbuckets, ncomp, bucket_sums, part);
-  k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(bucket_sums, nwin, B, L, ncomp, segS, segT);
-  k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
+  if (max_chunks > 0) {
+    k_stitch<<<(unsigned)((max_chunks * ncomp + 127) / 128), 128, 0, stream>>>(offsets, nbuckets, chunk_bucket, ncomp, bucket_sums, part, kChunk);
+    ws->launches++;
+  }
+  k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
+  if (nseg <= 32)
+    k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
+  else
+    k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
   k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, W, c, ncomp, d_out);
-  ws->launches += 4;
+  ws->launches += 3;
   return cudaGetLastError();
 }
 

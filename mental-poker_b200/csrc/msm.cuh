@@ -14,7 +14,7 @@
 //   k_scatter        counting-sort scatter of point indices              (global atomics)
 //   k_accumulate     fixed-length chunks of the sorted list, XYZZ mixed adds, segmented by
 //                    bucket -> perfectly load balanced for ANY digit distribution
-//   k_fixup          stitch bucket runs that straddle chunk boundaries
+//   k_stitch         fold the partial sums of bucket runs that straddle chunk boundaries
 //   k_reduce_seg     per segment of L buckets: S = sum, T = sum (i+1) * B_i (running sums)
 //   k_reduce_win     per window: block-wide suffix scan over segment sums (warp shuffles)
 //   k_fold           per job: Horner over windows (c doublings each)
@@ -44,7 +44,11 @@ int msm_pick_window(uint64_t avg_len);
 // Returns cudaSuccess or the first CUDA error.  Asynchronous on `stream`.
 cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
                     const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
-                    xyzz* d_out, cudaStream_t stream);
+                    xyzz* d_out, cudaStream_t stream, int w_begin = 0, int w_count = -1);
+// With a window range [w_begin, w_begin + w_count) of the W = ceil(253/c) windows the result is
+//   sum_{w in range} 2^(c*(w - w_begin)) * (window sum w)
+// so that  full MSM = sum over ranges of 2^(c*w_begin) * partial  (window-range split across GPUs).
+inline int msm_num_windows(int c) { return (253 + c - 1) / c; }
 
 // number of kernels the last msm_run launched / EC additions it performed (host-side count
 // of scheduled bucket additions, for EC-adds/s reporting)

@@ -21,12 +21,14 @@ struct ShuffleState {
   int m = 0, n = 0;
   std::vector<uint8_t> ck64;  // (n+1) * 64 canonical: h, g_1 .. g_n   (MSM order of a commitment)
   uint8_t enc_g[64], ghat[64], gsum[64];  // gsum = g_1 + .. + g_n  (com(c,..,c; 0) = c * gsum)
-  affine* d_ck = nullptr;     // device, Montgomery, n + 1 points
+  affine* d_ck = nullptr;     // device, Montgomery: h, g_1..g_n, then enc_g, ghat, pk (n + 4 points)
+  cudaEvent_t ev = nullptr;   // marks small device->host copies the host waits for mid-stream
   uint8_t* pinned = nullptr;  // small pinned staging for results
   size_t pinned_cap = 0;
   ~ShuffleState() {
     if (d_ck) cudaFree(d_ck);
     if (pinned) cudaFreeHost(pinned);
+    if (ev) cudaEventDestroy(ev);
   }
 };
 void shuffle_state_destroy(ShuffleState* s) { delete s; }
@@ -161,13 +163,14 @@ __global__ void __launch_bounds__(256) k_commit_scalars(const fr* __restrict__ r
   for (int i = 0; i < 8; i++) out[g * 8 + i] = w[i];
 }
 
-__global__ void __launch_bounds__(64) k_xyzz_add_pairs(const xyzz* __restrict__ a, const xyzz* __restrict__ b,
-                                                       xyzz* __restrict__ out, int count) {
+// E_k = diag_k + Enc(b_k*ghat; tau_k):  E[2k] += c1[k] (= tau_k*g),  E[2k+1] += c2[k] (= b_k*ghat + tau_k*pk)
+__global__ void __launch_bounds__(64) k_combine_E(xyzz* __restrict__ E, const xyzz* __restrict__ c1,
+                                                  const xyzz* __restrict__ c2, int two_m) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= count) return;
-  xyzz x = a[g], y = b[g];
+  if (g >= 2 * two_m) return;
+  xyzz x = E[g], y = (g & 1) ? c2[g >> 1] : c1[g >> 1];
   xyzz_add(x, y);
-  out[g] = x;
+  E[g] = x;
 }
 
 // Remask (reference remasking.rs:9-22 -> masking.rs:10-20):  thread (i, comp) computes
@@ -245,7 +248,8 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   memcpy(S->ghat, ghat, 64);
   if (S->d_ck) cudaFree(S->d_ck);
   S->d_ck = nullptr;
-  CK(cudaMalloc(&S->d_ck, sizeof(affine) * (size_t)(n + 1)));
+  CK(cudaMalloc(&S->d_ck, sizeof(affine) * (size_t)(n + 4)));
+  if (!S->ev) CK(cudaEventCreateWithFlags(&S->ev, cudaEventDisableTiming));
   // validate every parameter point and compute gsum = sum g_j with one MSM of unit scalars
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_bad);
@@ -263,10 +267,12 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   CK(xyzz_to_canonical(d_out, (uint32_t*)d_res, 1, ctx->stream));
   ctx->launches += 1;
   // Montgomery copy of the commit key for the prover's commitment jobs
-  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)(n + 1) * 64);
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)(n + 3) * 64);
   NEED(d_canon);
   CK(cudaMemcpyAsync(d_canon, S->ck64.data(), (size_t)(n + 1) * 64, cudaMemcpyHostToDevice, ctx->stream));
-  CK(points_to_mont((const uint32_t*)d_canon, S->d_ck, (uint64_t)n + 1, d_bad, ctx->stream));
+  CK(cudaMemcpyAsync(d_canon + (size_t)(n + 1) * 64, enc_g, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_canon + (size_t)(n + 2) * 64, ghat, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(points_to_mont((const uint32_t*)d_canon, S->d_ck, (uint64_t)n + 3, d_bad, ctx->stream));
   ctx->launches += 1;
   int bad = 0;
   CK(cudaMemcpyAsync(S->gsum, d_res, 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -625,7 +631,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   int32_t rcode;
 
   // ---- device buffers
-  const size_t rows_max = (size_t)std::max(2 * m + 1, m + 3);
+  const size_t rows_max = (size_t)std::max(2 * m + 1, m + 4);
   const size_t T2 = N + 2;  // CT arena: deck2 | (g, pk) | (O, ghat)
   uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, T2 * 128);
   affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, T2 * 2 * sizeof(affine));
@@ -642,16 +648,15 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   fr* d_pairs = (fr*)ctx->scratch(sFrPairs, (size_t)(m + 1) * (m + 1) * sizeof(fr) + (4 * (size_t)m + 8) * sizeof(fr));
   fr* d_partials = (fr*)ctx->scratch(sPartials, sizeof(fr) * (std::max(fr_powers_blocks(N), fr_reduce_blocks(N)) + 4));
   fr* d_rows = (fr*)ctx->scratch(sFrTmp0, (4 * (size_t)n + 64) * sizeof(fr));  // svp rows (3 x n) + response vectors
-  uint32_t* d_g1_scal = (uint32_t*)ctx->scratch(sG1Scal, (rows_max * (n + 1) + 8 * (size_t)m + 64) * 32);
-  xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, (4 * (size_t)m + 16) * sizeof(xyzz));
+  uint32_t* d_g1_scal = (uint32_t*)ctx->scratch(sG1Scal, (rows_max * (n + 1) + 12 * (size_t)m + 64) * 32);
+  xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, (8 * (size_t)m + 16) * sizeof(xyzz));
   uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, (N + n + 4 * (size_t)m + 8) * 32);
   xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 8 * (size_t)m * sizeof(xyzz));
-  xyzz* d_ct_out2 = (xyzz*)ctx->scratch(sCtOut2, 4 * (size_t)m * sizeof(xyzz));
   uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, (8 * (size_t)m + 16) * 64);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_perm); NEED(d_rho); NEED(d_a); NEED(d_Ame); NEED(d_Az); NEED(d_d0);
   NEED(d_Bv); NEED(d_Bz); NEED(d_xpow); NEED(d_pairs); NEED(d_partials); NEED(d_rows); NEED(d_g1_scal); NEED(d_g1_out);
-  NEED(d_ct_scal); NEED(d_ct_out); NEED(d_ct_out2); NEED(d_canon); NEED(d_bad);
+  NEED(d_ct_scal); NEED(d_ct_out); NEED(d_canon); NEED(d_bad);
   const size_t pin_bytes = (8 * (size_t)m + 16) * 64 + (4 * (size_t)n + 4 * (size_t)m + 64) * 32;
   uint8_t* h_pin = pinned(S, pin_bytes);
   if (!h_pin) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
@@ -668,6 +673,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(cudaMemcpyAsync(d_ct_canon + N * 128, tail, 256, cudaMemcpyHostToDevice, st));
   }
   CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, T2 * 2, d_bad, st));
+  CK(cudaMemcpyAsync(S->d_ck + (n + 3), d_ct_mont + 2 * N + 1, sizeof(affine), cudaMemcpyDeviceToDevice, st));  // pk
   CK(cudaMemcpyAsync(d_perm, perm, N * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_xpow, rho, N * 32, cudaMemcpyHostToDevice, st));  // staging: canonical rho
   CK(fr_from_canonical_vec((const uint32_t*)d_xpow, d_rho, N, st));
@@ -719,6 +725,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   fr* h_col = reinterpret_cast<fr*>(h_pin);
   CK(cudaMemcpyAsync(h_col, d_Bv + (size_t)(m - 1) * n, sizeof(fr) * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_col + n, d_partials + fr_reduce_blocks(N), sizeof(fr), cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(S->ev, st));
 
   // C.2  multi-exponentiation first message (B.5'): a0, r0, (b_k, s_k, tau_k); the 2m diagonal
   //      ciphertext MSMs E_k (K2) are the prover's dominant cost and only need x.
@@ -761,32 +768,12 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_mont, 2, diag.data(), 2 * m, msm_pick_window(N / 2), d_ct_out, st));
   ctx->launches += msm_last_launches(ctx->ws);
 
-  // wait for col / rho* (the diagonal MSMs keep the GPU busy meanwhile)
-  // NOTE: the copy was enqueued before the MSM on the same stream, so an event marks its completion.
-  CK(cudaStreamSynchronize(st));
+  // wait for col / rho* only (the event precedes the diagonal MSMs, which keep the GPU busy
+  // while the host prepares the next batch)
+  CK(cudaEventSynchronize(S->ev));
   std::vector<fr> col(h_col, h_col + n);
   const fr rho_star = fr_neg(h_col[n]);
   me_tau[m] = rho_star;
-
-  // C.3  Enc(b_k*ghat; tau_k) = tau_k*(g, pk) + b_k*(O, ghat): 2m two-term ciphertext jobs, then E_k = diag_k + enc_k
-  {
-    std::vector<uint32_t> sc((size_t)4 * m * 8);
-    for (int k = 0; k < 2 * m; k++) {
-      fr_to_canonical(me_tau[k], &sc[(size_t)(2 * k) * 8]);
-      fr_to_canonical(me_b[k], &sc[(size_t)(2 * k + 1) * 8]);
-    }
-    uint32_t* d_enc_scal = d_ct_scal + (N + n) * 8;
-    CK(cudaMemcpyAsync(d_enc_scal, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
-    std::vector<MsmJob> enc((size_t)2 * m);
-    for (int k = 0; k < 2 * m; k++) enc[k] = MsmJob{(uint32_t)(2 * k), (uint32_t)N, 2};
-    CK(msm_run(ctx->ws, d_enc_scal, 4 * (size_t)m, d_ct_mont, 2, enc.data(), 2 * m, 4, d_ct_out2, st));
-    ctx->launches += msm_last_launches(ctx->ws);
-    k_xyzz_add_pairs<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_ct_out2, d_ct_out, 4 * m);
-    CK(cudaGetLastError());
-    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canon, 4 * (size_t)m, st));
-    ctx->launches += 2;
-    CK(cudaMemcpyAsync(proof_out + L.meE, d_canon, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
-  }
 
   // C.4  SVP first message on the host side of the scalars (O(n)), committed on the device
   std::vector<fr> bk((size_t)n);
@@ -801,38 +788,49 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     }
     CK(cudaMemcpyAsync(d_rows, rows3.data(), sizeof(fr) * 3 * n, cudaMemcpyHostToDevice, st));
   }
-  // C.5  one G1 batch: Hadamard c_B[0..m) = com(Bv[i]; sv[i]) (c_B[0] = c_D[0], c_B[m-1] = c_b),
-  //      SVP c_d, c_delta, c_Delta, multi-exp c_A0 and the 2m two-term c_B_k = com(b_k; s_k)
+  // C.5  ONE G1 batch (one Pippenger launch sequence = one fold latency):
+  //      rows      Hadamard c_B[0..m) = com(Bv[i]; sv[i]) (c_B[0] = c_D[0], c_B[m-1] = c_b), SVP c_d,
+  //                c_delta, c_Delta, multi-exp c_A0                              (n+1 terms each)
+  //      pairs     multi-exp c_B_k = s_k*h + b_k*g_1                               (2 terms)
+  //      enc c1/c2 Enc(b_k*ghat; tau_k) = (tau_k*g, b_k*ghat + tau_k*pk)           (1 / 2 terms)
+  //      then E_k = diag_k + enc_k.
   {
-    // scalar arena: (m + 4) rows of n + 1, then 2m pairs (s_k, b_k)
     const int R = m + 4;
     std::vector<fr> blinds((size_t)R);
     for (int i = 0; i < m; i++) blinds[i] = sv[i];
     blinds[m] = sv_rd; blinds[m + 1] = sv_s1; blinds[m + 2] = sv_sx; blinds[m + 3] = me_r0;
     CK(cudaMemcpyAsync(d_blind, blinds.data(), sizeof(fr) * R, cudaMemcpyHostToDevice, st));
-    uint64_t tot = (uint64_t)(n + 1);
+    const uint64_t tot = (uint64_t)(n + 1);
     k_commit_scalars<<<(unsigned)((tot * m + 255) / 256), 256, 0, st>>>(d_Bv, n, d_blind, m, n, n, d_g1_scal);
     k_commit_scalars<<<(unsigned)((tot * 3 + 255) / 256), 256, 0, st>>>(d_rows, n, d_blind + m, 3, n, n, d_g1_scal + tot * m * 8);
     k_commit_scalars<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_Ame, n, d_blind + m + 3, 1, n, n, d_g1_scal + tot * (m + 3) * 8);
     CK(cudaGetLastError());
     ctx->launches += 3;
-    std::vector<uint32_t> sc((size_t)4 * m * 8);
+    const size_t nsmall = 10 * (size_t)m;  // 2m pairs + 2m singles + 2m pairs
+    std::vector<uint32_t> sc(nsmall * 8);
     for (int k = 0; k < 2 * m; k++) {
       fr_to_canonical(me_s[k], &sc[(size_t)(2 * k) * 8]);
       fr_to_canonical(me_b[k], &sc[(size_t)(2 * k + 1) * 8]);
+      fr_to_canonical(me_tau[k], &sc[(size_t)(4 * m + k) * 8]);
+      fr_to_canonical(me_b[k], &sc[(size_t)(6 * m + 2 * k) * 8]);
+      fr_to_canonical(me_tau[k], &sc[(size_t)(6 * m + 2 * k + 1) * 8]);
     }
-    CK(cudaMemcpyAsync(d_g1_scal + tot * R * 8, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t base = (uint32_t)(tot * R);
+    CK(cudaMemcpyAsync(d_g1_scal + (size_t)base * 8, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
     std::vector<MsmJob> jobs;
     for (int k = 0; k < R; k++) jobs.push_back(MsmJob{(uint32_t)(k * tot), 0, (uint32_t)tot});
-    CK(msm_run(ctx->ws, d_g1_scal, tot * R, S->d_ck, 1, jobs.data(), R, msm_pick_window(n + 1), d_g1_out, st));
+    for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 2 * k, 0, 2});                               // (h, g_1)
+    for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 4 * m + k, (uint32_t)(n + 1), 1});           // enc_g
+    for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 6 * m + 2 * k, (uint32_t)(n + 2), 2});       // (ghat, pk)
+    CK(msm_run(ctx->ws, d_g1_scal, base + nsmall, S->d_ck, 1, jobs.data(), (int)jobs.size(), msm_pick_window(n + 1), d_g1_out, st));
     ctx->launches += msm_last_launches(ctx->ws);
-    std::vector<MsmJob> small;
-    for (int k = 0; k < 2 * m; k++) small.push_back(MsmJob{(uint32_t)(2 * k), 0, 2});
-    CK(msm_run(ctx->ws, d_g1_scal + tot * R * 8, 4 * (size_t)m, S->d_ck, 1, small.data(), 2 * m, 4, d_g1_out + R, st));
-    ctx->launches += msm_last_launches(ctx->ws);
+    k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_g1_out + R + 2 * m, d_g1_out + R + 4 * m, 2 * m);
+    CK(cudaGetLastError());
+    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canon, 4 * (size_t)m, st));
     uint8_t* d_canon2 = d_canon + 4 * (size_t)m * 64;
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon2, (size_t)R + 2 * m, st));
-    ctx->launches += 1;
+    ctx->launches += 3;
+    CK(cudaMemcpyAsync(proof_out + L.meE, d_canon, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proof_out + L.hB, d_canon2, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proof_out + L.svpts, d_canon2 + (size_t)m * 64, 3 * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proof_out + L.mepts, d_canon2 + (size_t)(m + 3) * 64, (size_t)(2 * m + 1) * 64, cudaMemcpyDeviceToHost, st));
@@ -882,12 +880,10 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(cudaMemcpy2DAsync(d_pairs_scal, 64, tk.data(), 32, 32, 2 * (size_t)m + 1, cudaMemcpyHostToDevice, st));
     CK(fr_scatter_canonical(d_dk, 2 * (size_t)m + 1, d_pairs_scal, 1, 2, st));
     ctx->launches += 3;
-    std::vector<MsmJob> big = {MsmJob{0, 0, (uint32_t)tot}, MsmJob{(uint32_t)tot, 0, (uint32_t)tot}};
-    CK(msm_run(ctx->ws, d_g1_scal, 2 * tot, S->d_ck, 1, big.data(), 2, msm_pick_window(n + 1), d_g1_out, st));
-    ctx->launches += msm_last_launches(ctx->ws);
-    std::vector<MsmJob> small;
-    for (int k = 0; k <= 2 * m; k++) small.push_back(MsmJob{(uint32_t)(2 * k), 0, 2});
-    CK(msm_run(ctx->ws, d_pairs_scal, 2 * (2 * (size_t)m + 1), S->d_ck, 1, small.data(), 2 * m + 1, 4, d_g1_out + 2, st));
+    std::vector<MsmJob> jobs = {MsmJob{0, 0, (uint32_t)tot}, MsmJob{(uint32_t)tot, 0, (uint32_t)tot}};
+    for (int k = 0; k <= 2 * m; k++) jobs.push_back(MsmJob{(uint32_t)(2 * tot + 2 * k), 0, 2});
+    CK(msm_run(ctx->ws, d_g1_scal, 2 * tot + 2 * (2 * (size_t)m + 1), S->d_ck, 1, jobs.data(), (int)jobs.size(),
+               msm_pick_window(n + 1), d_g1_out, st));
     ctx->launches += msm_last_launches(ctx->ws);
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, 2 * (size_t)m + 3, st));
     ctx->launches += 1;

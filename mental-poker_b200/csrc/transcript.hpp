@@ -165,23 +165,29 @@ class Transcript {
   void begin() { pending_.reset(); }
   void feed(const void* data, size_t len) { pending_.update(data, len); }
   void feed_label(const char* s) { pending_.update(s, strlen(s)); }
-  // 64-byte C-ABI points (all-zero = identity) -> the 65-byte ark-ec encoding
+  // 64-byte C-ABI points (all-zero = identity) -> the 65-byte ark-ec encoding, serialized in
+  // blocks of 64 points so the hash sees few, large updates
   void feed_points64(const uint8_t* pts, size_t count) {
-    uint8_t b[65];
-    for (size_t i = 0; i < count; i++) {
-      const uint8_t* p = pts + 64 * i;
-      bool inf = true;
-      for (int k = 0; k < 64; k++)
-        if (p[k]) { inf = false; break; }
-      if (inf) {
-        memset(b, 0, 65);
-        b[32] = 1;
-        b[64] = 1;
-      } else {
-        memcpy(b, p, 64);
-        b[64] = 0;
+    uint8_t buf[64 * 65];
+    while (count > 0) {
+      size_t take = count < 64 ? count : 64;
+      uint8_t* b = buf;
+      for (size_t i = 0; i < take; i++, b += 65) {
+        const uint8_t* p = pts + 64 * i;
+        uint64_t w[8];
+        memcpy(w, p, 64);
+        if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
+          memset(b, 0, 65);  // identity = (0, 1, infinity)
+          b[32] = 1;
+          b[64] = 1;
+        } else {
+          memcpy(b, p, 64);
+          b[64] = 0;
+        }
       }
-      pending_.update(b, 65);
+      pending_.update(buf, take * 65);
+      pts += 64 * take;
+      count -= take;
     }
   }
   void end() {

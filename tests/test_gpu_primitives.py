@@ -121,3 +121,28 @@ def test_rejects_point_off_curve(ctx, pkg):
 def test_kernels_were_launched(ctx):
     msm_case(ctx, 64, 0)
     assert ctx.launches > 0
+
+
+@pytest.mark.parametrize("c,world", [(8, 1), (8, 3), (13, 2), (16, 8), (16, 5)])
+def test_msm_window_range_split(ctx, pkg, c, world):
+    """Window-range split (multi-GPU path) emulated on one GPU: per-'rank' partials + fold."""
+    import torch
+    n = 500
+    s0, s1, pts, st = chain_points(n, 21)
+    ks = scalars(st, n, "uniform")
+    ks[0], ks[1] = 0, N - 1
+    dev = torch.device("cuda:0")
+    d_pts = torch.frombuffer(bytearray(b"".join(map(pb, pts))), dtype=torch.uint8).to(dev)
+    d_sc = torch.frombuffer(bytearray(b"".join(map(b32, ks))), dtype=torch.uint8).to(dev)
+    d_out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    W = pkg.lib.mp_msm_num_windows(c)
+    points, scs = b"", b""
+    for r, s in pkg.dist.fold_scalars(c, W, world):
+        b, e = pkg.dist.window_range(W, r, world)
+        ctx.msm_g1_windows_device(d_pts.data_ptr(), d_sc.data_ptr(), n, d_out.data_ptr(), c, b, e - b)
+        ctx.sync()
+        points += bytes(d_out.cpu().numpy().tobytes())
+        scs += s
+    got = ctx.msm_g1(points, scs, 0)
+    e = sum(k * (s0 + i * s1) for i, k in enumerate(ks)) % N
+    assert got == pb(stark.mul(stark.G, e))
