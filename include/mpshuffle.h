@@ -151,6 +151,15 @@ int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* dec
 int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
                           const uint8_t* proof);
 
+/* `verify_shuffle` for `batch` independent proofs under the same parameters and public key
+ * (BASELINE config: batch of 52-card proofs).  decks / shuffled_decks / proofs are the per-proof
+ * buffers concatenated.  statuses[i] receives 0 or the MP_VERIFY_* code of proof i.  The
+ * transcripts run on `host_threads` CPU threads (0 = all hardware threads); every group equation
+ * of the whole batch is evaluated by two batched MSM launch sequences.  A point off the curve
+ * anywhere in the batch fails the call with MP_ERR_NOT_ON_CURVE. */
+int32_t mp_shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks,
+                                const uint8_t* shuffled_decks, const uint8_t* proofs, uint64_t batch,
+                                int32_t* statuses, int32_t host_threads);
 /* Same as mp_shuffle_verify / mp_shuffle_prove for decks that are ALREADY resident in HBM
  * (d_* = device pointers to the same canonical bytes): no deck crosses PCIe.  The host copies
  * are still required -- the Fiat-Shamir transcript hashes them on the CPU. */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mp_shuffle_prove": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp]),
     "mp_shuffle_and_remask": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp]),
     "mp_shuffle_verify": (_i32, [_vp, _cp, _cp, _cp, _cp]),
+    "mp_shuffle_verify_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
     "mp_shuffle_verify_resident": (_i32, [_vp, _cp, _cp, _cp, _cp, _vp, _vp]),
     "mp_shuffle_prove_resident": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp, _vp]),
     "mp_profile_enable": (_i32, [_vp, _i32]),
@@ -181,6 +182,15 @@ class Context:
         assert len(deck) == 128 * N and len(deck2) == 128 * N
         assert len(proof) == lib.mp_proof_len(self.m, self.n)
         return check(self.h, lib.mp_shuffle_verify(self.h, pk, deck, deck2, proof))
+
+    def verify_shuffle_batch(self, pk, decks, decks2, proofs, host_threads=0):
+        """-> list of per-proof statuses"""
+        plen = lib.mp_proof_len(self.m, self.n)
+        B = len(proofs) // plen
+        assert len(decks) == len(decks2) == 128 * self.m * self.n * B and len(proofs) == plen * B
+        st = (_i32 * B)()
+        check(self.h, lib.mp_shuffle_verify_batch(self.h, pk, decks, decks2, proofs, B, st, host_threads))
+        return list(st)
 
     @staticmethod
     def status_string(code):

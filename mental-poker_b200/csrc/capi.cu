@@ -238,6 +238,11 @@ extern "C" int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8
   return shuffle_verify(ctx, pk, deck, shuffled_deck, proof);
 }
 
+extern "C" int32_t mp_shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks,
+                                           const uint8_t* shuffled_decks, const uint8_t* proofs, uint64_t batch,
+                                           int32_t* statuses, int32_t host_threads) {
+  return shuffle_verify_batch(ctx, pk, decks, shuffled_decks, proofs, batch, statuses, host_threads);
+}
 extern "C" int32_t mp_shuffle_verify_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
                                               const uint8_t* shuffled_deck, const uint8_t* proof, const void* d_deck,
                                               const void* d_shuffled_deck) {

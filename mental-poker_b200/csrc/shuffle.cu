@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/mpshuffle.h"
@@ -315,110 +317,64 @@ static void absorb_statement(Transcript& fs, const ShuffleState* S, const uint8_
 }
 
 // ------------------------------------------------------------------------------------------
-// verify
+// verifier pieces shared by the single-proof and the batched entry points
 // ------------------------------------------------------------------------------------------
-int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                       const uint8_t* proof, const void* deck_src, const void* deck2_src) {
-  if (!ctx || !pk || !deck || !deck2 || !proof) return MP_ERR_INVALID_ARG;
-  if (!deck_src) deck_src = deck;     // host copy doubles as the transfer source
-  if (!deck2_src) deck2_src = deck2;  // (a device pointer here means the deck is already resident in HBM)
-  ShuffleState* S = ctx->shuffle;
-  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
-  cudaSetDevice(ctx->device);
-  ctx->launches = 0;
+struct Challenges {
+  fr x, y, z, xh, yh, xz, xs, xm;
+};
+
+// Every challenge derives from statement + proof bytes (no device round trip).
+static Challenges derive_challenges(const ShuffleState* S, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
+                                    size_t N, const uint8_t* proof, const Layout& L) {
+  const int m = S->m;
+  Challenges ch;
+  Transcript fs;
+  absorb_statement(fs, S, pk, deck, deck2, N, proof + L.cA);
+  ch.x = fs.challenge();
+  fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof + L.cB, m); fs.end();
+  ch.y = fs.challenge();
+  ch.z = fs.challenge();
+  fs.begin(); fs.feed_label("hadamard_argument"); fs.feed_points64(proof + L.cb, 1); fs.feed_points64(proof + L.hB, m); fs.end();
+  ch.xh = fs.challenge();
+  ch.yh = fs.challenge();
+  fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof + L.zpts, 2 * (size_t)m + 3); fs.end();
+  ch.xz = fs.challenge();
+  fs.begin(); fs.feed_label("single_value_product_argument"); fs.feed_points64(proof + L.svpts, 3); fs.end();
+  ch.xs = fs.challenge();
+  fs.begin(); fs.feed_label("multi_exponentiation_argument");
+  fs.feed_points64(proof + L.mepts, 2 * (size_t)m + 1); fs.feed_points64(proof + L.meE, 4 * (size_t)m); fs.end();
+  ch.xm = fs.challenge();
+  return ch;
+}
+
+// What the host still has to compare once the device reports which jobs are the identity.
+struct HostChecks {
+  bool hadamard_bytes_ok;   // c_B'[m-1] == c_b
+  bool zero_bytes_ok;       // zero-argument c_D[m+1] == O
+  bool svp_first_ok;        // b~_1 == a~_1
+  fr svp_last, xs;          // b~_n must equal xs * bstar
+  bool multiexp_bytes_ok;   // multi-exp c_B[m] == O
+};
+static const int kG1Checks = 8;  // H1, Z1, Z2, Z3, S1, S2, M1, M2 -- one MSM job each
+
+// Appends the eight commitment-space equations of the verifier as "sum scalar*point == O" jobs.
+static void append_g1_checks(TermList& tl, const ShuffleState* S, const uint8_t* proof, const Layout& L,
+                             const Challenges& ch, HostChecks* hc) {
   const int m = S->m, n = S->n;
-  const size_t N = (size_t)m * n;
-  const Layout L(m, n);
   const uint8_t* ck_h = S->ck64.data();
   auto ck_g = [&](int j) { return S->ck64.data() + 64 * (size_t)(j + 1); };  // g_{j+1}, j = 0..n-1
   auto P = [&](size_t off, size_t i) { return proof + off + 64 * i; };
-
-  // ---- 1. start moving the decks (independent of every challenge)
-  const size_t T = 2 * N + 2 * (size_t)m + 3;  // CT arena: deck | E_m | deck2 | E_0..E_{2m-1} | (g,pk) | (O,ghat)
-  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, T * 128);
-  affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, T * 2 * sizeof(affine));
-  uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, T * 32);
-  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 4 * sizeof(xyzz));
-  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
-  NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_bad);
-  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_canon, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_canon + N * 128, proof + L.meE + 128 * (size_t)m, 128, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_canon + (N + 1) * 128, deck2_src, N * 128, cudaMemcpyDefault, ctx->stream));
-  {
-    std::vector<uint8_t> tail((2 * (size_t)m + 2) * 128, 0);
-    memcpy(tail.data(), proof + L.meE, 2 * (size_t)m * 128);
-    uint8_t* q = tail.data() + 2 * (size_t)m * 128;
-    memcpy(q, S->enc_g, 64);
-    memcpy(q + 64, pk, 64);
-    memcpy(q + 192, S->ghat, 64);  // (identity, ghat)
-    CK(cudaMemcpyAsync(d_ct_canon + (2 * N + 1) * 128, tail.data(), tail.size(), cudaMemcpyHostToDevice, ctx->stream));
-  }
-  CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, T * 2, d_bad, ctx->stream));
-  ctx->launches += 1;
-
-  // ---- 2. transcript: every challenge derives from statement + proof bytes
-  Transcript fs;
-  absorb_statement(fs, S, pk, deck, deck2, N, proof + L.cA);
-  const fr x = fs.challenge();
-  fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof + L.cB, m); fs.end();
-  const fr y = fs.challenge();
-  const fr z = fs.challenge();
-  fs.begin(); fs.feed_label("hadamard_argument"); fs.feed_points64(proof + L.cb, 1); fs.feed_points64(proof + L.hB, m); fs.end();
-  const fr xh = fs.challenge();
-  const fr yh = fs.challenge();
-  fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof + L.zpts, 2 * (size_t)m + 3); fs.end();
-  const fr xz = fs.challenge();
-  fs.begin(); fs.feed_label("single_value_product_argument"); fs.feed_points64(proof + L.svpts, 3); fs.end();
-  const fr xs = fs.challenge();
-  fs.begin(); fs.feed_label("multi_exponentiation_argument");
-  fs.feed_points64(proof + L.mepts, 2 * (size_t)m + 1); fs.feed_points64(proof + L.meE, 4 * (size_t)m); fs.end();
-  const fr xm = fs.challenge();
-
-  // ---- 3. O(N) scalar vectors on the device
-  const std::vector<fr> me_a = h_frs(proof + L.mea, n);
-  const fr me_r = h_fr(proof + L.mer), me_b = h_fr(proof + L.meb), me_s = h_fr(proof + L.mes), me_tau = h_fr(proof + L.metau);
-  const std::vector<fr> xmp = h_powers(xm, 2 * m);
-  SmallUpload up;
-  fr yz[2] = {y, z};
-  size_t o_yz = up.add(yz, sizeof yz);
-  std::vector<fr> coef((size_t)m);
-  for (int i = 1; i <= m; i++) coef[i - 1] = fr_neg(xmp[m - i]);
-  size_t o_coef = up.add_frs(coef);
-  size_t o_mea = up.add_frs(me_a);
-  std::vector<uint32_t> tailsc((2 * (size_t)m + 2) * 8);
-  for (int k = 0; k < 2 * m; k++) fr_to_canonical(xmp[k], &tailsc[8 * (size_t)k]);
-  fr_to_canonical(fr_neg(me_tau), &tailsc[8 * (size_t)(2 * m)]);
-  fr_to_canonical(fr_neg(me_b), &tailsc[8 * (size_t)(2 * m + 1)]);
-  uint32_t minus_one[8];
-  fr_to_canonical(fr_neg(fr_one()), minus_one);
-  uint8_t* d_small = (uint8_t*)ctx->scratch(sSmallUp, up.bytes.size() + 64);
-  fr* d_partials = (fr*)ctx->scratch(sPartials, sizeof(fr) * (fr_powers_blocks(N) + 2));
-  NEED(d_small); NEED(d_partials);
-  CK(cudaMemcpyAsync(d_small, up.bytes.data(), up.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_scal + N * 8, minus_one, 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ct_scal + (2 * N + 1) * 8, tailsc.data(), tailsc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  fr* d_bstar = d_partials + fr_powers_blocks(N);
-  CK(fr_powers(h_pow2_table(x), N, d_ct_scal, nullptr, (const fr*)(d_small + o_yz), d_partials, d_bstar, ctx->stream));
-  CK(fr_outer_canonical((const fr*)(d_small + o_coef), (const fr*)(d_small + o_mea), m, n, d_ct_scal + (N + 1) * 8, ctx->stream));
-  ctx->launches += 3;
-
-  // ---- 4. the two ciphertext checks (K1): 4 N-term G1 MSMs in one batched launch sequence
-  //   job 0:  sum x^i C_i - E_m                                        == O   (Chat == E_m)
-  //   job 1:  sum x^k E_k - Enc(b*ghat; tau) - sum (x^{m-i} a_j) C'_ij  == O
-  MsmJob ct_jobs[2] = {{0, 0, (uint32_t)(N + 1)}, {(uint32_t)(N + 1), (uint32_t)(N + 1), (uint32_t)(N + 2 * m + 2)}};
-  CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N), d_ct_out, ctx->stream));
-  ctx->launches += msm_last_launches(ctx->ws);
-
-  // ---- 5. the commitment-space checks as small G1 jobs (host builds O(m + n) scalars)
-  const std::vector<fr> xzp = h_powers(xz, 2 * m + 1);
+  const fr &y = ch.y, &z = ch.z, &xh = ch.xh, &yh = ch.yh, &xs = ch.xs;
+  const std::vector<fr> xzp = h_powers(ch.xz, 2 * m + 1);
   const std::vector<fr> xhp = h_powers(xh, m);
+  const std::vector<fr> xmp = h_powers(ch.xm, 2 * m);
   const std::vector<fr> z_a = h_frs(proof + L.za, n), z_b = h_frs(proof + L.zb, n);
   const fr z_r = h_fr(proof + L.zr), z_s = h_fr(proof + L.zs), z_t = h_fr(proof + L.zt);
   const std::vector<fr> sv_a = h_frs(proof + L.sva, n), sv_b = h_frs(proof + L.svb, n);
   const fr sv_r = h_fr(proof + L.svr), sv_s = h_fr(proof + L.svs);
+  const std::vector<fr> me_a = h_frs(proof + L.mea, n);
+  const fr me_r = h_fr(proof + L.mer), me_b = h_fr(proof + L.meb), me_s = h_fr(proof + L.mes);
   const fr one = fr_one();
-  TermList tl;
   // H1: hB[0] == c_D[0] = y*c_A[0] + c_B[0] - z*gsum
   tl.term(P(L.cA, 0), y); tl.term(P(L.cB, 0), one); tl.term(S->gsum, fr_neg(z)); tl.term(P(L.hB, 0), fr_neg(one));
   tl.close_job();
@@ -481,6 +437,108 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   tl.term(ck_h, fr_neg(me_s));
   tl.term(ck_g(0), fr_neg(me_b));
   tl.close_job();
+  hc->hadamard_bytes_ok = memcmp(P(L.hB, m - 1), P(L.cb, 0), 64) == 0;
+  hc->zero_bytes_ok = all_zero(P(L.zpts, 2 + m + 1), 64);
+  hc->svp_first_ok = fr_eq(sv_b[0], sv_a[0]);
+  hc->svp_last = sv_b[n - 1];
+  hc->xs = xs;
+  hc->multiexp_bytes_ok = all_zero(P(L.mepts, 1 + m), 64);
+}
+
+// Verdict in the order the reference reaches the checks (product argument first: Hadamard ->
+// zero -> single-value product; then multi-exponentiation).  g1_id[0..8): H1 Z1 Z2 Z3 S1 S2 M1 M2;
+// ct_ok: both ciphertext equations (Chat == E_m and the multi-exp opening) hold.
+static int32_t verdict(const HostChecks& hc, const fr& bstar, const bool* g1_id, bool ct_ok) {
+  if (!g1_id[0] || !hc.hadamard_bytes_ok) return MP_VERIFY_HADAMARD;
+  if (!hc.zero_bytes_ok || !g1_id[1] || !g1_id[2] || !g1_id[3]) return MP_VERIFY_ZERO;
+  if (!g1_id[4] || !g1_id[5] || !hc.svp_first_ok || !fr_eq(hc.svp_last, fr_mul(hc.xs, bstar))) return MP_VERIFY_SVP;
+  if (!hc.multiexp_bytes_ok || !ct_ok || !g1_id[6] || !g1_id[7]) return MP_VERIFY_MULTIEXP;
+  return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// verify
+// ------------------------------------------------------------------------------------------
+int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
+                       const uint8_t* proof, const void* deck_src, const void* deck2_src) {
+  if (!ctx || !pk || !deck || !deck2 || !proof) return MP_ERR_INVALID_ARG;
+  if (!deck_src) deck_src = deck;     // host copy doubles as the transfer source
+  if (!deck2_src) deck2_src = deck2;  // (a device pointer here means the deck is already resident in HBM)
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int m = S->m, n = S->n;
+  const size_t N = (size_t)m * n;
+  const Layout L(m, n);
+
+  // ---- 1. start moving the decks (independent of every challenge)
+  const size_t T = 2 * N + 2 * (size_t)m + 3;  // CT arena: deck | E_m | deck2 | E_0..E_{2m-1} | (g,pk) | (O,ghat)
+  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, T * 128);
+  affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, T * 2 * sizeof(affine));
+  uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, T * 32);
+  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 4 * sizeof(xyzz));
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_bad);
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon + N * 128, proof + L.meE + 128 * (size_t)m, 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_canon + (N + 1) * 128, deck2_src, N * 128, cudaMemcpyDefault, ctx->stream));
+  {
+    std::vector<uint8_t> tail((2 * (size_t)m + 2) * 128, 0);
+    memcpy(tail.data(), proof + L.meE, 2 * (size_t)m * 128);
+    uint8_t* q = tail.data() + 2 * (size_t)m * 128;
+    memcpy(q, S->enc_g, 64);
+    memcpy(q + 64, pk, 64);
+    memcpy(q + 192, S->ghat, 64);  // (identity, ghat)
+    CK(cudaMemcpyAsync(d_ct_canon + (2 * N + 1) * 128, tail.data(), tail.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, T * 2, d_bad, ctx->stream));
+  ctx->launches += 1;
+
+  // ---- 2. transcript: every challenge derives from statement + proof bytes
+  const Challenges ch = derive_challenges(S, pk, deck, deck2, N, proof, L);
+  const fr &x = ch.x, &y = ch.y, &z = ch.z, &xm = ch.xm;
+
+  // ---- 3. O(N) scalar vectors on the device
+  const std::vector<fr> me_a = h_frs(proof + L.mea, n);
+  const fr me_r = h_fr(proof + L.mer), me_b = h_fr(proof + L.meb), me_s = h_fr(proof + L.mes), me_tau = h_fr(proof + L.metau);
+  const std::vector<fr> xmp = h_powers(xm, 2 * m);
+  SmallUpload up;
+  fr yz[2] = {y, z};
+  size_t o_yz = up.add(yz, sizeof yz);
+  std::vector<fr> coef((size_t)m);
+  for (int i = 1; i <= m; i++) coef[i - 1] = fr_neg(xmp[m - i]);
+  size_t o_coef = up.add_frs(coef);
+  size_t o_mea = up.add_frs(me_a);
+  std::vector<uint32_t> tailsc((2 * (size_t)m + 2) * 8);
+  for (int k = 0; k < 2 * m; k++) fr_to_canonical(xmp[k], &tailsc[8 * (size_t)k]);
+  fr_to_canonical(fr_neg(me_tau), &tailsc[8 * (size_t)(2 * m)]);
+  fr_to_canonical(fr_neg(me_b), &tailsc[8 * (size_t)(2 * m + 1)]);
+  uint32_t minus_one[8];
+  fr_to_canonical(fr_neg(fr_one()), minus_one);
+  uint8_t* d_small = (uint8_t*)ctx->scratch(sSmallUp, up.bytes.size() + 64);
+  fr* d_partials = (fr*)ctx->scratch(sPartials, sizeof(fr) * (fr_powers_blocks(N) + 2));
+  NEED(d_small); NEED(d_partials);
+  CK(cudaMemcpyAsync(d_small, up.bytes.data(), up.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_scal + N * 8, minus_one, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ct_scal + (2 * N + 1) * 8, tailsc.data(), tailsc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  fr* d_bstar = d_partials + fr_powers_blocks(N);
+  CK(fr_powers(h_pow2_table(x), N, d_ct_scal, nullptr, (const fr*)(d_small + o_yz), d_partials, d_bstar, ctx->stream));
+  CK(fr_outer_canonical((const fr*)(d_small + o_coef), (const fr*)(d_small + o_mea), m, n, d_ct_scal + (N + 1) * 8, ctx->stream));
+  ctx->launches += 3;
+
+  // ---- 4. the two ciphertext checks (K1): 4 N-term G1 MSMs in one batched launch sequence
+  //   job 0:  sum x^i C_i - E_m                                        == O   (Chat == E_m)
+  //   job 1:  sum x^k E_k - Enc(b*ghat; tau) - sum (x^{m-i} a_j) C'_ij  == O
+  MsmJob ct_jobs[2] = {{0, 0, (uint32_t)(N + 1)}, {(uint32_t)(N + 1), (uint32_t)(N + 1), (uint32_t)(N + 2 * m + 2)}};
+  CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N), d_ct_out, ctx->stream));
+  ctx->launches += msm_last_launches(ctx->ws);
+
+  // ---- 5. the commitment-space checks as small G1 jobs (host builds O(m + n) scalars)
+  TermList tl;
+  HostChecks hc;
+  append_g1_checks(tl, S, proof, L, ch, &hc);
   const int J = (int)tl.jobs.size();  // 8
   xyzz* d_g1_out = nullptr;
   int32_t st = run_g1_jobs(ctx, tl, &d_g1_out, d_bad);
@@ -503,13 +561,210 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   const xyzz* res = reinterpret_cast<const xyzz*>(h_res + sizeof(fr));
   auto is_id = [&](int j) { return xyzz_is_identity(res[j]); };
 
-  // ---- 7. verdict, in the order the reference reaches the checks (product argument first:
-  //         Hadamard -> zero -> single-value product; then multi-exponentiation)
-  if (!is_id(0) || memcmp(P(L.hB, m - 1), P(L.cb, 0), 64) != 0) return MP_VERIFY_HADAMARD;
-  if (!all_zero(P(L.zpts, 2 + m + 1), 64) || !is_id(1) || !is_id(2) || !is_id(3)) return MP_VERIFY_ZERO;
-  if (!is_id(4) || !is_id(5) || !fr_eq(sv_b[0], sv_a[0]) || !fr_eq(sv_b[n - 1], fr_mul(xs, bstar))) return MP_VERIFY_SVP;
-  if (!all_zero(P(L.mepts, 1 + m), 64) || !is_id(J) || !is_id(J + 1) || !is_id(6) || !is_id(7) || !is_id(J + 2) || !is_id(J + 3))
-    return MP_VERIFY_MULTIEXP;
+  // ---- 7. verdict
+  bool g1_id[kG1Checks];
+  for (int j = 0; j < kG1Checks; j++) g1_id[j] = is_id(j);
+  return verdict(hc, bstar, g1_id, is_id(J) && is_id(J + 1) && is_id(J + 2) && is_id(J + 3));
+}
+
+// ------------------------------------------------------------------------------------------
+// batched verify (BASELINE config "batch of independent 52-card proofs"): lockstep over B
+// proofs -- host threads derive the transcripts and the O(N) scalars of each proof, then ONE
+// ciphertext MSM launch sequence (4 jobs per proof) and ONE G1 launch sequence (8 jobs per proof)
+// evaluate every group equation of the whole sub-batch.
+// ------------------------------------------------------------------------------------------
+// flags[g * ncomp + comp] = (sum of the group's job outputs is the identity)
+__global__ void __launch_bounds__(64) k_group_identity(const xyzz* __restrict__ outs, int ncomp, int jobs_per_group,
+                                                       uint64_t ngroups, uint8_t* __restrict__ flags) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups * ncomp) return;
+  uint64_t group = g / ncomp;
+  int comp = (int)(g % ncomp);
+  xyzz acc = outs[(group * jobs_per_group) * ncomp + comp];
+  for (int j = 1; j < jobs_per_group; j++) {
+    xyzz v = outs[(group * jobs_per_group + j) * ncomp + comp];
+    xyzz_add(acc, v);
+  }
+  flags[g] = xyzz_is_identity(acc) ? 1 : 0;
+}
+
+static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
+                                const uint8_t* proofs, size_t Bs, int32_t* statuses, int threads) {
+  ShuffleState* S = ctx->shuffle;
+  const int m = S->m, n = S->n;
+  const size_t N = (size_t)m * n;
+  const Layout L(m, n);
+  const size_t plen = shuffle_proof_len(m, n);
+  const size_t T1 = 8 * (size_t)m + 5 * (size_t)n + 19;  // G1 terms per proof (see append_g1_checks)
+  const size_t SM = 2 * (size_t)m + 3;                   // small ciphertext entries per proof
+  const size_t ct_total = 2 * Bs * N + Bs * SM;
+  // host staging
+  std::vector<uint8_t> g1_pts(Bs * T1 * 64), sm_pts(Bs * SM * 128);
+  std::vector<uint32_t> g1_scal(Bs * T1 * 8), ct_scal(ct_total * 8);
+  std::vector<HostChecks> hcs(Bs);
+  std::vector<fr> bstars(Bs);
+  std::vector<int> bad_layout(Bs, 0);
+  uint32_t minus_one[8];
+  fr_to_canonical(fr_neg(fr_one()), minus_one);
+
+  auto work = [&](size_t p) {
+    const uint8_t* deck = decks + p * N * 128;
+    const uint8_t* deck2 = decks2 + p * N * 128;
+    const uint8_t* proof = proofs + p * plen;
+    const Challenges ch = derive_challenges(S, pk, deck, deck2, N, proof, L);
+    TermList tl;
+    append_g1_checks(tl, S, proof, L, ch, &hcs[p]);
+    if (tl.count() != T1) { bad_layout[p] = 1; return; }
+    memcpy(&g1_pts[p * T1 * 64], tl.pts.data(), T1 * 64);
+    memcpy(&g1_scal[p * T1 * 8], tl.scal.data(), T1 * 32);
+    // ciphertext scalars: x^i | -(xm^{m-i} a_j) | small: -1, xm^k, -tau, -b
+    uint32_t* sx = &ct_scal[(p * N) * 8];
+    uint32_t* s2 = &ct_scal[(Bs * N + p * N) * 8];
+    uint32_t* ss = &ct_scal[(2 * Bs * N + p * SM) * 8];
+    fr xi = fr_one(), yi = fr_zero(), prod = fr_one();
+    for (size_t i = 0; i < N; i++) {
+      xi = fr_mul(xi, ch.x);
+      yi = fr_add(yi, ch.y);
+      prod = fr_mul(prod, fr_sub(fr_add(yi, xi), ch.z));
+      fr_to_canonical(xi, sx + 8 * i);
+    }
+    bstars[p] = prod;
+    const std::vector<fr> xmp = h_powers(ch.xm, 2 * m);
+    const std::vector<fr> me_a = h_frs(proof + L.mea, n);
+    for (int i = 1; i <= m; i++) {
+      const fr cf = fr_neg(xmp[m - i]);
+      for (int j = 0; j < n; j++) fr_to_canonical(fr_mul(cf, me_a[j]), s2 + 8 * ((size_t)(i - 1) * n + j));
+    }
+    memcpy(ss, minus_one, 32);
+    for (int k = 0; k < 2 * m; k++) fr_to_canonical(xmp[k], ss + 8 * (size_t)(1 + k));
+    fr_to_canonical(fr_neg(h_fr(proof + L.metau)), ss + 8 * (size_t)(1 + 2 * m));
+    fr_to_canonical(fr_neg(h_fr(proof + L.meb)), ss + 8 * (size_t)(2 + 2 * m));
+    // small ciphertext points: E_m | E_0..E_{2m-1} | (g, pk) | (O, ghat)
+    uint8_t* q = &sm_pts[p * SM * 128];
+    memcpy(q, proof + L.meE + 128 * (size_t)m, 128);
+    memcpy(q + 128, proof + L.meE, 2 * (size_t)m * 128);
+    uint8_t* t = q + 128 * (size_t)(1 + 2 * m);
+    memcpy(t, S->enc_g, 64);
+    memcpy(t + 64, pk, 64);
+    memset(t + 128, 0, 64);
+    memcpy(t + 192, S->ghat, 64);
+  };
+  if (threads <= 1 || Bs < 4) {
+    for (size_t p = 0; p < Bs; p++) work(p);
+  } else {
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next{0};
+    for (int t = 0; t < threads; t++)
+      pool.emplace_back([&] {
+        for (size_t p = next.fetch_add(1); p < Bs; p = next.fetch_add(1)) work(p);
+      });
+    for (auto& th : pool) th.join();
+  }
+  for (size_t p = 0; p < Bs; p++)
+    if (bad_layout[p]) return ctx->fail(MP_ERR_INVALID_ARG, "internal: unexpected verifier term count");
+
+  // device buffers
+  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, ct_total * 128);
+  affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, ct_total * 2 * sizeof(affine));
+  uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, ct_total * 32);
+  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, Bs * 8 * sizeof(xyzz));
+  uint8_t* d_g1_canon = (uint8_t*)ctx->scratch(sG1Canon, Bs * T1 * 64);
+  affine* d_g1_mont = (affine*)ctx->scratch(sG1Mont, Bs * T1 * sizeof(affine));
+  uint32_t* d_g1_scal = (uint32_t*)ctx->scratch(sG1Scal, Bs * T1 * 32);
+  xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, Bs * kG1Checks * sizeof(xyzz));
+  uint8_t* d_flags = (uint8_t*)ctx->scratch(sResults, Bs * 12 + 64);
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_g1_canon); NEED(d_g1_mont);
+  NEED(d_g1_scal); NEED(d_g1_out); NEED(d_flags); NEED(d_bad);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  CK(cudaMemcpyAsync(d_ct_canon, decks, Bs * N * 128, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(d_ct_canon + Bs * N * 128, decks2, Bs * N * 128, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(d_ct_canon + 2 * Bs * N * 128, sm_pts.data(), sm_pts.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ct_scal, ct_scal.data(), ct_scal.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_g1_canon, g1_pts.data(), g1_pts.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_g1_scal, g1_scal.data(), g1_scal.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, ct_total * 2, d_bad, st));
+  CK(points_to_mont((const uint32_t*)d_g1_canon, d_g1_mont, Bs * T1, d_bad, st));
+  ctx->launches += 2;
+  // ciphertext jobs: per proof (deck, E_m) -> group 0, (deck', small tail) -> group 1
+  std::vector<MsmJob> jobs(Bs * 4);
+  for (size_t p = 0; p < Bs; p++) {
+    const uint32_t a = (uint32_t)(p * N), b = (uint32_t)(2 * Bs * N + p * SM), c2 = (uint32_t)(Bs * N + p * N);
+    jobs[4 * p + 0] = MsmJob{a, a, (uint32_t)N};
+    jobs[4 * p + 1] = MsmJob{b, b, 1};
+    jobs[4 * p + 2] = MsmJob{c2, c2, (uint32_t)N};
+    jobs[4 * p + 3] = MsmJob{b + 1, b + 1, (uint32_t)(2 * m + 2)};
+  }
+  CK(msm_run(ctx->ws, d_ct_scal, ct_total, d_ct_mont, 2, jobs.data(), (int)jobs.size(), msm_pick_window(N / 2 + 1), d_ct_out, st));
+  ctx->launches += msm_last_launches(ctx->ws);
+  k_group_identity<<<(unsigned)((Bs * 4 + 63) / 64), 64, 0, st>>>(d_ct_out, 2, 2, Bs * 2, d_flags);
+  // G1 jobs: 8 per proof, contiguous terms
+  std::vector<MsmJob> g1jobs(Bs * kG1Checks);
+  {
+    // per-proof job boundaries are identical: take them from a dry layout
+    const uint32_t lens[kG1Checks] = {4u, (uint32_t)(2 * m + n + 1), (uint32_t)(m + n + 2), (uint32_t)(2 * m + 3),
+                                      (uint32_t)(n + 3), (uint32_t)(n + 2), (uint32_t)(m + n + 2), (uint32_t)(2 * m + 2)};
+    for (size_t p = 0; p < Bs; p++) {
+      uint32_t off = (uint32_t)(p * T1);
+      for (int j = 0; j < kG1Checks; j++) {
+        g1jobs[p * kG1Checks + j] = MsmJob{off, off, lens[j]};
+        off += lens[j];
+      }
+    }
+  }
+  CK(msm_run(ctx->ws, d_g1_scal, Bs * T1, d_g1_mont, 1, g1jobs.data(), (int)g1jobs.size(), msm_pick_window(T1 / kG1Checks), d_g1_out, st));
+  ctx->launches += msm_last_launches(ctx->ws);
+  k_group_identity<<<(unsigned)((Bs * kG1Checks + 63) / 64), 64, 0, st>>>(d_g1_out, 1, 1, Bs * kG1Checks, d_flags + Bs * 4);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  std::vector<uint8_t> flags(Bs * 12);
+  int bad = 0;
+  CK(cudaMemcpyAsync(flags.data(), d_flags, Bs * 12, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck or proof point in the batch is not a canonical point of the Stark curve");
+  for (size_t p = 0; p < Bs; p++) {
+    bool g1_id[kG1Checks];
+    for (int j = 0; j < kG1Checks; j++) g1_id[j] = flags[Bs * 4 + p * kG1Checks + j] != 0;
+    const uint8_t* cf = &flags[p * 4];
+    statuses[p] = verdict(hcs[p], bstars[p], g1_id, cf[0] && cf[1] && cf[2] && cf[3]);
+  }
+  return MP_OK;
+}
+
+int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
+                             const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads) {
+  if (!ctx || !pk || (B && (!decks || !decks2 || !proofs || !statuses))) return MP_ERR_INVALID_ARG;
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int m = S->m, n = S->n;
+  const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n);
+  if (N > 8192) {  // large decks: the single-proof path already fills the GPU
+    int launches = 0;
+    for (uint64_t p = 0; p < B; p++) {
+      int32_t st = shuffle_verify(ctx, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen);
+      launches += ctx->launches;
+      if (st < 0) return st;
+      statuses[p] = st;
+    }
+    ctx->launches = launches;
+    return MP_OK;
+  }
+  int threads = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+  threads = std::max(1, std::min(threads, 64));
+  // sub-batches bounded by the job grid (<= 65535 jobs per launch) and ~2^25 ciphertext terms
+  size_t sub = std::min<size_t>(4096, std::max<size_t>(1, ((size_t)1 << 24) / N));
+  for (uint64_t p0 = 0; p0 < B; p0 += sub) {
+    size_t Bs = (size_t)std::min<uint64_t>(sub, B - p0);
+    int launches = ctx->launches;
+    int32_t st = verify_sub_batch(ctx, pk, decks + p0 * N * 128, decks2 + p0 * N * 128, proofs + p0 * plen, Bs,
+                                  statuses + p0, threads);
+    (void)launches;
+    if (st != MP_OK) return st;
+  }
   return MP_OK;
 }
 

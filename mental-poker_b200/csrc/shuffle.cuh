@@ -44,4 +44,8 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
                        const uint8_t* proof, const void* deck_src = nullptr, const void* deck2_src = nullptr);
 
+// B independent proofs under the same parameters and public key, verified in lockstep.
+int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
+                             const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads);
+
 }  // namespace mp

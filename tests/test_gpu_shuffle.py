@@ -157,3 +157,41 @@ def test_identity_and_duplicate_cards(ctx):
     assert deck2 == co.remask(enc_g, pb(pk), deck_b, perm, rho_b)
     assert proof == co.prove(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, perm, rho_b, rnd_b)
     assert ctx.verify_shuffle(pb(pk), deck_b, deck2, proof) == 0
+
+
+def _batch(m, n, seeds):
+    co = c_oracle.COracle(msm_mode=1)
+    pp0 = None
+    decks = decks2 = proofs = b""
+    for s in seeds:
+        pp, pk, deck, perm, rho, rnd = instance(m, n, s)
+        if pp0 is None:
+            pp0, pk0 = pp, pk
+        enc_g, ck_g, ck_h, ghat = pb(pp0.enc_g), b"".join(map(pb, pp0.ck_g)), pb(pp0.ck_h), pb(pp0.ghat)
+        deck_b = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+        rho_b, rnd_b = b"".join(map(b32, rho)), b"".join(map(b32, rnd))
+        d2 = co.remask(enc_g, pb(pk0), deck_b, perm, rho_b)
+        pf = co.prove(m, n, enc_g, ck_g, ck_h, ghat, pb(pk0), deck_b, d2, perm, rho_b, rnd_b)
+        decks += deck_b; decks2 += d2; proofs += pf
+    return (enc_g, ck_g, ck_h, ghat, pb(pk0)), decks, decks2, proofs
+
+
+@pytest.mark.parametrize("m,n,B", [(3, 4, 7), (4, 13, 5)])
+def test_verify_batch_matches_single_and_oracle(ctx, m, n, B):
+    (enc_g, ck_g, ck_h, ghat, pk), decks, decks2, proofs = _batch(m, n, list(range(30, 30 + B)))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    plen, dlen = len(proofs) // B, 128 * m * n
+    assert ctx.verify_shuffle_batch(pk, decks, decks2, proofs) == [0] * B
+    # tamper: proof 1 gets a flipped response scalar, proof 2 the (valid) shuffled deck of proof 3
+    bad = bytearray(proofs)
+    bad[plen * 2 - 1 - 32 * 3] ^= 1          # multi-exp response r of proof 1
+    bad_decks2 = bytearray(decks2)
+    bad_decks2[2 * dlen:3 * dlen] = decks2[3 * dlen:4 * dlen]
+    got = ctx.verify_shuffle_batch(pk, decks, bytes(bad_decks2), bytes(bad), host_threads=3)
+    co = c_oracle.COracle(msm_mode=1)
+    want = [co.verify(m, n, enc_g, ck_g, ck_h, ghat, pk, decks[i * dlen:(i + 1) * dlen],
+                      bytes(bad_decks2[i * dlen:(i + 1) * dlen]), bytes(bad[i * plen:(i + 1) * plen])) for i in range(B)]
+    assert got == want and want[1] == 4 and want[2] == 1 and want.count(0) == B - 2
+    single = [ctx.verify_shuffle(pk, decks[i * dlen:(i + 1) * dlen], bytes(bad_decks2[i * dlen:(i + 1) * dlen]),
+                                 bytes(bad[i * plen:(i + 1) * plen])) for i in range(B)]
+    assert single == want
