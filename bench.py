@@ -4,8 +4,8 @@ and MSM EC-adds/s, next to the CPU reference path on the same box).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
 
-One step = one `shuffle_and_remask`-style prove (ShuffleArgument::prove on a remasked deck) plus
-one `verify_shuffle` of a synthetic N-card deck.  Default workload: 2^16 cards, (m, n) =
+One step = one `shuffle_and_remask` (permute + remask + ShuffleArgument::prove) plus one
+`verify_shuffle` of its output, of a synthetic N-card deck.  Default workload: 2^16 cards, (m, n) =
 (128, 512) -- the configuration BASELINE.json's target is quoted on.  With --gpus N > 1 (under
 torchrun) every rank proves and verifies its own deck (proof-index split, weak scaling, no
 data-path collective).
@@ -243,18 +243,21 @@ def main():
     torch.cuda.synchronize()
 
     def step(resident):
+        # BarnettSmartProtocol::shuffle_and_remask (permute + remask + prove) ...
         if resident:
-            rc = lib.mp_shuffle_prove_resident(ctx.h, inst["pk"], inst["deck"], deck2, perm_arr, inst["rho"], inst["rand"],
-                                               proof_buf, d_deck2.data_ptr())
+            rc = lib.mp_shuffle_and_remask_resident(ctx.h, inst["pk"], inst["deck"], perm_arr, inst["rho"], inst["rand"],
+                                                    deck2_buf, proof_buf, d_deck.data_ptr())
         else:
-            rc = lib.mp_shuffle_prove(ctx.h, inst["pk"], inst["deck"], deck2, perm_arr, inst["rho"], inst["rand"], proof_buf)
+            rc = lib.mp_shuffle_and_remask(ctx.h, inst["pk"], inst["deck"], perm_arr, inst["rho"], inst["rand"],
+                                           deck2_buf, proof_buf)
         pkg.check(ctx.h, rc)
         launches = ctx.launches
+        # ... then BarnettSmartProtocol::verify_shuffle on its output
         if resident:
-            rc = lib.mp_shuffle_verify_resident(ctx.h, inst["pk"], inst["deck"], deck2, proof_buf, d_deck.data_ptr(),
+            rc = lib.mp_shuffle_verify_resident(ctx.h, inst["pk"], inst["deck"], deck2_buf, proof_buf, d_deck.data_ptr(),
                                                 d_deck2.data_ptr())
         else:
-            rc = lib.mp_shuffle_verify(ctx.h, inst["pk"], inst["deck"], deck2, proof_buf)
+            rc = lib.mp_shuffle_verify(ctx.h, inst["pk"], inst["deck"], deck2_buf, proof_buf)
         if pkg.check(ctx.h, rc) != 0:
             raise SystemExit(f"bench: verify_shuffle rejected a valid proof (status {rc})")
         return launches + ctx.launches
@@ -295,8 +298,8 @@ def main():
     barrier()
     # prove / verify split (informational, resident)
     t0 = time.perf_counter()
-    pkg.check(ctx.h, lib.mp_shuffle_prove_resident(ctx.h, inst["pk"], inst["deck"], deck2, perm_arr, inst["rho"], inst["rand"],
-                                                   proof_buf, d_deck2.data_ptr()))
+    pkg.check(ctx.h, lib.mp_shuffle_and_remask_resident(ctx.h, inst["pk"], inst["deck"], perm_arr, inst["rho"], inst["rand"],
+                                                        deck2_buf, proof_buf, d_deck.data_ptr()))
     t1 = time.perf_counter()
     lib.mp_shuffle_verify_resident(ctx.h, inst["pk"], inst["deck"], deck2, proof_buf, d_deck.data_ptr(), d_deck2.data_ptr())
     t2 = time.perf_counter()
@@ -325,11 +328,12 @@ def main():
                         ec_adds_per_s=(acc_adds / (acc_ms / 1e3) if acc_ms > 0 else None),
                         note="integer-pipe bound kernel (~10 field multiplications of 64 IMAD.WIDE per 68 B): the HBM "
                              "fraction is structurally low; see DESIGN.md for the IMAD-issue roofline")
-        h2d = 128 * N * 2 + 4 * N + 32 * N + 32 * (11 * m + 5 * n) + 128 * N * 2 + len(proof_buf)
+        # prove: deck, perm, rho, randomness; verify: deck, shuffled deck, proof
+        h2d = 128 * N + 4 * N + 32 * N + 32 * (11 * m + 5 * n) + 128 * N * 2 + len(proof_buf)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="u32", data="synthetic", config=config,
-                    e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=len(proof_buf),
+                    e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=128 * N + len(proof_buf),
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=clocks.summary(), roofline=roofline,
                     split=dict(prove_ms=(t1 - t0) * 1e3, verify_ms=(t2 - t1) * 1e3))

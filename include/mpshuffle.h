@@ -166,6 +166,9 @@ int32_t mp_shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
 int32_t mp_shuffle_verify_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
                                    const uint8_t* shuffled_deck, const uint8_t* proof, const void* d_deck,
                                    const void* d_shuffled_deck);
+int32_t mp_shuffle_and_remask_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                       const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
+                                       uint8_t* proof_out, const void* d_deck);
 int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
                                   const uint8_t* shuffled_deck, const uint32_t* perm, const uint8_t* rho,
                                   const uint8_t* randomness, uint8_t* proof_out, const void* d_shuffled_deck);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "mp_shuffle_verify": (_i32, [_vp, _cp, _cp, _cp, _cp]),
     "mp_shuffle_verify_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
     "mp_shuffle_verify_resident": (_i32, [_vp, _cp, _cp, _cp, _cp, _vp, _vp]),
+    "mp_shuffle_and_remask_resident": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp, _vp]),
     "mp_shuffle_prove_resident": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp, _vp]),
     "mp_profile_enable": (_i32, [_vp, _i32]),
     "mp_profile_collect": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),

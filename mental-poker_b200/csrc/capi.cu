@@ -221,17 +221,28 @@ extern "C" int32_t mp_shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_
                                     uint8_t* proof_out) {
   return shuffle_prove(ctx, pk, deck, shuffled_deck, perm, rho, randomness, proof_out);
 }
+static int32_t shuffle_and_remask_common(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                         const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
+                                         uint8_t* proof_out, const void* d_deck) {
+  if (!ctx || !ctx->shuffle) return ctx ? ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called") : MP_ERR_INVALID_ARG;
+  uint64_t n_cards = (uint64_t)mp_params_m(ctx) * mp_params_n(ctx);
+  const void* d_shuffled = nullptr;
+  int32_t st = shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck, d_deck, &d_shuffled);
+  if (st != MP_OK) return st;
+  int launches = ctx->launches;
+  st = shuffle_prove(ctx, pk, deck, out_deck, perm, rho, randomness, proof_out, d_shuffled);
+  ctx->launches += launches;
+  return st;
+}
 extern "C" int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
                                          const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
                                          uint8_t* proof_out) {
-  if (!ctx || !ctx->shuffle) return ctx ? ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called") : MP_ERR_INVALID_ARG;
-  uint64_t n_cards = (uint64_t)mp_params_m(ctx) * mp_params_n(ctx);
-  int32_t st = shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck);
-  if (st != MP_OK) return st;
-  int launches = ctx->launches;
-  st = shuffle_prove(ctx, pk, deck, out_deck, perm, rho, randomness, proof_out);
-  ctx->launches += launches;
-  return st;
+  return shuffle_and_remask_common(ctx, pk, deck, perm, rho, randomness, out_deck, proof_out, nullptr);
+}
+extern "C" int32_t mp_shuffle_and_remask_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                                  const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
+                                                  uint8_t* proof_out, const void* d_deck) {
+  return shuffle_and_remask_common(ctx, pk, deck, perm, rho, randomness, out_deck, proof_out, d_deck);
 }
 extern "C" int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
                                      const uint8_t* proof) {

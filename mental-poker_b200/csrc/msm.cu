@@ -1,6 +1,7 @@
 // Batched windowed-Pippenger MSM for sm_100a.  See msm.cuh for the pipeline overview and
 // DESIGN.md for the roofline model of each kernel.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -348,8 +349,8 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__
 // Thread g handles component (g % ncomp) of chunk t = g / ncomp: sorted entries
 // [t*kChunk, min((t+1)*kChunk, E)).  Its first bucket run goes to part[g]; every later run
 // (which starts inside the chunk) goes to bucket_sums[bucket * ncomp + comp].
-template <int NCOMP>
-__global__ void __launch_bounds__(kAccThreads)
+template <int NCOMP, int MINBLOCKS>
+__global__ void __launch_bounds__(kAccThreads, MINBLOCKS)
     k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                  uint64_t nbuckets, const affine* __restrict__ points, xyzz* __restrict__ bucket_sums,
                  xyzz* __restrict__ part, uint32_t* __restrict__ chunk_bucket, uint32_t kChunk) {
@@ -666,10 +667,16 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     }
     uint64_t threads = max_chunks * ncomp;
     unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
-    if (ncomp == 1)
-      k_accumulate<1><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk);
-    else
-      k_accumulate<2><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk);
+    // occupancy experiment knob: resident blocks per SM the kernel is compiled for (register cap)
+    static const int acc_mb = [] { const char* e = getenv("MP_ACC_MINBLOCKS"); return e ? atoi(e) : 4; }();
+#define MP_LAUNCH_ACC(NC, MB) \
+  k_accumulate<NC, MB><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk)
+    if (ncomp == 1) {
+      if (acc_mb >= 6) MP_LAUNCH_ACC(1, 6); else if (acc_mb == 5) MP_LAUNCH_ACC(1, 5); else MP_LAUNCH_ACC(1, 4);
+    } else {
+      if (acc_mb >= 6) MP_LAUNCH_ACC(2, 6); else if (acc_mb == 5) MP_LAUNCH_ACC(2, 5); else MP_LAUNCH_ACC(2, 4);
+    }
+#undef MP_LAUNCH_ACC
     ws->launches++;
     if (timed) {
       MP_CK(cudaEventRecord(tm.e1, stream));

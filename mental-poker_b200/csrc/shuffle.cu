@@ -25,12 +25,17 @@ struct ShuffleState {
   uint8_t enc_g[64], ghat[64], gsum[64];  // gsum = g_1 + .. + g_n  (com(c,..,c; 0) = c * gsum)
   affine* d_ck = nullptr;     // device, Montgomery: h, g_1..g_n, then enc_g, ghat, pk (n + 4 points)
   cudaEvent_t ev = nullptr;   // marks small device->host copies the host waits for mid-stream
+  // fixed-base tables for remasking: tab[base][j][d-1] = d * 2^(8j) * base, base 0 = g, 1 = pk
+  affine* d_tab = nullptr;
+  uint8_t tab_pk[64];
+  bool tab_pk_valid = false;
   uint8_t* pinned = nullptr;  // small pinned staging for results
   size_t pinned_cap = 0;
   ~ShuffleState() {
     if (d_ck) cudaFree(d_ck);
     if (pinned) cudaFreeHost(pinned);
     if (ev) cudaEventDestroy(ev);
+    if (d_tab) cudaFree(d_tab);
   }
 };
 void shuffle_state_destroy(ShuffleState* s) { delete s; }
@@ -175,29 +180,62 @@ __global__ void __launch_bounds__(64) k_combine_E(xyzz* __restrict__ E, const xy
   E[g] = x;
 }
 
+// Fixed-base window tables for remasking (kernel family K4): tab[j * 255 + d - 1] = d * 2^(8j) * P
+// for j < 32, d = 1..255, affine Montgomery.  One thread per entry: the scalar d * 2^(8j) has its
+// set bits in [8j, 8j + 8), so the double-and-add runs over 8j + 8 bits only.
+static constexpr int kTabWin = 32, kTabDigits = 255, kTabSize = kTabWin * kTabDigits;
+__global__ void __launch_bounds__(128) k_build_table(const uint32_t* __restrict__ base_canon, affine* __restrict__ tab,
+                                                     int* __restrict__ bad) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= kTabSize) return;
+  int j = g / kTabDigits;
+  uint32_t d = (uint32_t)(g % kTabDigits) + 1;
+  affine P = affine_from_canonical(base_canon);
+  if (g == 0 && !affine_on_curve(P)) atomicExch(bad, 1);
+  xyzz acc = xyzz_identity();
+  for (int bit = 7; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((d >> bit) & 1) xyzz_madd(acc, P);
+  }
+  for (int k = 0; k < 8 * j; k++) acc = xyzz_dbl(acc);
+  tab[g] = xyzz_to_affine(acc);  // identity -> (0, 0)
+}
+
 // Remask (reference remasking.rs:9-22 -> masking.rs:10-20):  thread (i, comp) computes
-// out[i].comp = deck[perm[i]].comp + rho_i * base_comp with base = (g, pk).
+// out[i].comp = deck[perm[i]].comp + rho_i * base_comp, base = (g, pk), as 32 table lookups + adds.
 __global__ void __launch_bounds__(128) k_remask(const uint32_t* __restrict__ deck_canon, const uint32_t* __restrict__ perm,
-                                                const uint32_t* __restrict__ rho_canon, const uint32_t* __restrict__ bases_canon,
+                                                const uint32_t* __restrict__ rho_canon, const affine* __restrict__ tab,
                                                 uint64_t N, uint32_t* __restrict__ out_canon, int* __restrict__ bad) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= 2 * N) return;
   uint64_t i = g >> 1;
   int comp = (int)(g & 1);
-  affine base = affine_from_canonical(bases_canon + 16 * comp);
   uint64_t src = perm[i];
   if (src >= N) { atomicExch(bad, 2); return; }
   affine card = affine_from_canonical(deck_canon + (src * 2 + comp) * 16);
-  if (!affine_on_curve(card) || !affine_on_curve(base)) atomicExch(bad, 1);
+  if (!affine_on_curve(card)) atomicExch(bad, 1);
   uint32_t k[8];
-#pragma unroll
-  for (int w = 0; w < 8; w++) k[w] = rho_canon[i * 8 + w];
-  xyzz acc = xyzz_identity();
-  for (int bit = 255; bit >= 0; bit--) {
-    acc = xyzz_dbl(acc);
-    if ((k[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, base);
+  {
+    // reduce rho below the group order is the caller's contract; a 256-bit value still works
+    // because the table covers all 32 bytes
+    const uint4* p = reinterpret_cast<const uint4*>(rho_canon + i * 8);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
   }
-  xyzz_madd(acc, card);
+  const affine* T = tab + (size_t)comp * kTabSize;
+  xyzz acc = xyzz_from_affine(card);
+#pragma unroll 1
+  for (int j = 0; j < kTabWin; j++) {
+    uint32_t d = (k[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+    if (d) {
+      const uint4* s = reinterpret_cast<const uint4*>(T + j * kTabDigits + (d - 1));
+      affine e;
+      uint4* dst = reinterpret_cast<uint4*>(&e);
+#pragma unroll
+      for (int q = 0; q < 4; q++) dst[q] = __ldg(s + q);
+      xyzz_madd(acc, e);
+    }
+  }
   affine r = xyzz_to_affine(acc);
   uint32_t w[16];
   if (affine_is_identity(r)) {
@@ -206,8 +244,19 @@ __global__ void __launch_bounds__(128) k_remask(const uint32_t* __restrict__ dec
   } else {
     affine_to_canonical(r, w);
   }
+  uint4* o = reinterpret_cast<uint4*>(out_canon + g * 16);
 #pragma unroll
-  for (int q = 0; q < 16; q++) out_canon[g * 16 + q] = w[q];
+  for (int q = 0; q < 4; q++) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+// (re)builds the table of base `which` (0 = g, 1 = pk) from 64 canonical bytes already on the device
+static cudaError_t build_table(ShuffleState* S, int which, const uint8_t* d_base_canon, int* d_bad, cudaStream_t st) {
+  if (!S->d_tab) {
+    cudaError_t e = cudaMalloc(&S->d_tab, sizeof(affine) * 2 * (size_t)kTabSize);
+    if (e != cudaSuccess) return e;
+  }
+  k_build_table<<<(kTabSize + 127) / 128, 128, 0, st>>>((const uint32_t*)d_base_canon, S->d_tab + (size_t)which * kTabSize, d_bad);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -275,7 +324,9 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   CK(cudaMemcpyAsync(d_canon + (size_t)(n + 1) * 64, enc_g, 64, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_canon + (size_t)(n + 2) * 64, ghat, 64, cudaMemcpyHostToDevice, ctx->stream));
   CK(points_to_mont((const uint32_t*)d_canon, S->d_ck, (uint64_t)n + 3, d_bad, ctx->stream));
-  ctx->launches += 1;
+  CK(build_table(S, 0, d_canon + (size_t)(n + 1) * 64, d_bad, ctx->stream));  // remask table of g
+  S->tab_pk_valid = false;
+  ctx->launches += 2;
   int bad = 0;
   CK(cudaMemcpyAsync(S->gsum, d_res, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -772,7 +823,9 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
 // remask + commitments (stand-alone entry points; the prover reuses the pieces)
 // ------------------------------------------------------------------------------------------
 int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm, const uint8_t* rho,
-                       uint64_t N, uint8_t* out_deck) {
+                       uint64_t N, uint8_t* out_deck, const void* deck_src, const void** d_out_ret) {
+  if (!deck_src) deck_src = deck;
+  if (d_out_ret) *d_out_ret = nullptr;
   if (!ctx || !pk || (N && (!deck || !perm || !rho || !out_deck))) return MP_ERR_INVALID_ARG;
   ShuffleState* S = ctx->shuffle;
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
@@ -780,23 +833,28 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   if (N >= (1ull << 28)) return ctx->fail(MP_ERR_INVALID_ARG, "deck too large");
   cudaSetDevice(ctx->device);
   ctx->launches = 0;
-  uint8_t* d_deck = (uint8_t*)ctx->scratch(sCtCanon, N * 128);
-  uint8_t* d_out = (uint8_t*)ctx->scratch(sCtMont, N * 128);
+  // input deck staged in the sCtMont slot, output in sCtCanon: exactly where shuffle_prove wants
+  // the shuffled deck, so shuffle_and_remask does not move it twice
+  uint8_t* d_deck = (uint8_t*)ctx->scratch(sCtMont, (N + 2) * 2 * sizeof(affine));
+  uint8_t* d_out = (uint8_t*)ctx->scratch(sCtCanon, (N + 2) * 128);
   uint32_t* d_perm = (uint32_t*)ctx->scratch(sPerm, N * 4);
-  uint8_t* d_rho = (uint8_t*)ctx->scratch(sRho, N * 32);
-  uint8_t* d_bases = (uint8_t*)ctx->scratch(sSmallUp, 256);
+  uint8_t* d_rho = (uint8_t*)ctx->scratch(sRho, N * 32 + 64);
+  uint8_t* d_pk = (uint8_t*)ctx->scratch(sSmallUp, 256);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
-  NEED(d_deck); NEED(d_out); NEED(d_perm); NEED(d_rho); NEED(d_bases); NEED(d_bad);
-  uint8_t bases[128];
-  memcpy(bases, S->enc_g, 64);
-  memcpy(bases + 64, pk, 64);
+  NEED(d_deck); NEED(d_out); NEED(d_perm); NEED(d_rho); NEED(d_pk); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  CK(cudaMemcpyAsync(d_deck, deck, N * 128, cudaMemcpyHostToDevice, ctx->stream));
+  if (!S->tab_pk_valid || memcmp(S->tab_pk, pk, 64) != 0) {  // the pk table is cached across calls
+    CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, ctx->stream));
+    CK(build_table(S, 1, d_pk, d_bad, ctx->stream));
+    memcpy(S->tab_pk, pk, 64);
+    S->tab_pk_valid = true;
+    ctx->launches += 1;
+  }
+  CK(cudaMemcpyAsync(d_deck, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(d_perm, perm, N * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_rho, rho, N * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_bases, bases, 128, cudaMemcpyHostToDevice, ctx->stream));
   k_remask<<<(unsigned)((2 * N + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t*)d_deck, d_perm, (const uint32_t*)d_rho,
-                                                                     (const uint32_t*)d_bases, N, (uint32_t*)d_out, d_bad);
+                                                                     S->d_tab, N, (uint32_t*)d_out, d_bad);
   CK(cudaGetLastError());
   ctx->launches += 1;
   int bad = 0;
@@ -804,7 +862,11 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (bad == 2) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry out of range");
-  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
+  if (bad) {
+    S->tab_pk_valid = false;
+    return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
+  }
+  if (d_out_ret) *d_out_ret = d_out;
   return MP_OK;
 }
 
@@ -918,7 +980,8 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
 
   // ---- uploads that do not depend on any challenge
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-  CK(cudaMemcpyAsync(d_ct_canon, deck2_src, N * 128, cudaMemcpyDefault, st));
+  if (deck2_src != (const void*)d_ct_canon)  // (shuffle_and_remask leaves the remasked deck right here)
+    CK(cudaMemcpyAsync(d_ct_canon, deck2_src, N * 128, cudaMemcpyDefault, st));
   {
     uint8_t tail[256];
     memset(tail, 0, sizeof tail);

@@ -35,7 +35,8 @@ uint64_t shuffle_proof_len(int32_t m, int32_t n);
 uint64_t shuffle_randomness_len(int32_t m, int32_t n);
 
 int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
-                       const uint8_t* rho, uint64_t N, uint8_t* out_deck);
+                       const uint8_t* rho, uint64_t N, uint8_t* out_deck, const void* deck_src = nullptr,
+                       const void** d_out_ret = nullptr);
 int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k,
                              uint64_t len, uint8_t* out);
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
