@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--m", type=int, default=128)
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch52", type=int, default=512, help="proofs in the 52-card batch measurement (0 = skip)")
     ap.add_argument("--msm-logn", type=int, default=20, help="size of the MSM microbench reported beside the metric")
     args = ap.parse_args()
     m, n = args.m, args.n
@@ -316,6 +317,14 @@ def main():
         msm_res = msm_microbench(ctx, torch, dev, stream, args.msm_logn, pkg, world, rank)
     except Exception as e:  # never lose the headline line to the side measurement
         msm_res = dict(error=repr(e))
+    try:
+        b52 = batch52_bench(pkg, ctx, torch, stream, args.batch52, rank) if args.batch52 > 0 else None
+        if b52 is not None and world > 1:
+            t = torch.tensor([b52["prove_s"] + b52["verify_s"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            b52["proofs_per_s_all_gpus"] = world * b52["batch"] / t.item()
+    except Exception as e:
+        b52 = dict(error=repr(e))
     if rank == 0:
         peak, peak_src = load_peaks()
         bytes_per_add = 68.0  # 64 B affine point gather + 4 B sorted index
@@ -338,6 +347,7 @@ def main():
                     gpu_launches=launches, clocks=clocks.summary(), roofline=roofline,
                     split=dict(prove_ms=(t1 - t0) * 1e3, verify_ms=(t2 - t1) * 1e3))
         line["msm"] = msm_res
+        line["batch52"] = b52
         if not args.no_cpu_baseline and world == 1:
             sm, sn = sample_shape(m, n)
             val, desc, legs = cpu_sample(m, n, sm, sn, threads=1)
@@ -347,6 +357,43 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def batch52_bench(pkg, ctx, torch, stream, batch, rank):
+    """BASELINE config "batch of independent 52-card proofs": `batch` decks of (m, n) = (4, 13)
+    -- the reference's own test shape (tests.rs:178-179) -- proved by mp_shuffle_and_remask_batch
+    and verified by mp_shuffle_verify_batch (this rank's shard of the proof-index split)."""
+    import numpy as np
+    m, n = 4, 13
+    N = m * n
+    inst = make_instance(ctx, m, n, seed=100 + rank)
+    ctx2 = pkg.Context(ctx.device)
+    ctx2.set_params(m, n, inst["enc_g"], inst["ck_g"], inst["ck_h"], inst["ghat"])
+    rng = np.random.default_rng(200 + rank)
+    npts = 2 * N * batch
+    decks = ctx.dbg_scalar_mul(G64 * npts, rand_scalars(rng, npts))
+    perms = np.concatenate([rng.permutation(N) for _ in range(batch)]).astype(np.uint32)
+    rhos = rand_scalars(rng, N * batch)
+    rands = rand_scalars(rng, (11 * m + 5 * n) * batch)
+    perm_arr = perms.ctypes.data_as(ctypes.c_void_p)
+    out_decks = ctypes.create_string_buffer(128 * N * batch)
+    proofs = ctypes.create_string_buffer(pkg.lib.mp_proof_len(m, n) * batch)
+    statuses = (ctypes.c_int32 * batch)()
+    lib = pkg.lib
+    res = {}
+    for it in range(2):  # first pass warms the worker contexts
+        t0 = time.perf_counter()
+        pkg.check(ctx2.h, lib.mp_shuffle_and_remask_batch(ctx2.h, inst["pk"], decks, perm_arr, rhos, rands, batch, out_decks, proofs, 0))
+        t1 = time.perf_counter()
+        launches = ctx2.launches
+        pkg.check(ctx2.h, lib.mp_shuffle_verify_batch(ctx2.h, inst["pk"], decks, out_decks, proofs, batch, statuses, 0))
+        t2 = time.perf_counter()
+        launches += ctx2.launches
+        res = dict(batch=batch, m=m, n=n, prove_s=t1 - t0, verify_s=t2 - t1, proofs_per_s=batch / (t2 - t0),
+                   prove_per_s=batch / (t1 - t0), verify_per_s=batch / (t2 - t1), all_verified=all(s == 0 for s in statuses),
+                   gpu_launches=launches, host_threads=os.cpu_count(), timing="host wall clock around the two C-ABI calls (host buffers)")
+    ctx2.close()
+    return res
 
 
 def msm_microbench(ctx, torch, dev, stream, logn, pkg=None, world=1, rank=0):

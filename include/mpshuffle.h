@@ -151,6 +151,13 @@ int32_t mp_shuffle_and_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* dec
 int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
                           const uint8_t* proof);
 
+/* `shuffle_and_remask` for `batch` independent decks under the same parameters and public key
+ * (per-proof buffers concatenated; randomness is batch * mp_prover_randomness_len scalars).  Runs
+ * up to `host_threads` (0 = all hardware threads, at most 32) worker contexts concurrently on the
+ * context's device; every proof is byte-identical to the single-call result. */
+int32_t mp_shuffle_and_remask_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                                    const uint8_t* rhos, const uint8_t* randomness, uint64_t batch,
+                                    uint8_t* out_decks, uint8_t* proofs, int32_t host_threads);
 /* `verify_shuffle` for `batch` independent proofs under the same parameters and public key
  * (BASELINE config: batch of 52-card proofs).  decks / shuffled_decks / proofs are the per-proof
  * buffers concatenated.  statuses[i] receives 0 or the MP_VERIFY_* code of proof i.  The

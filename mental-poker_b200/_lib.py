@@ -41,6 +41,7 @@ SIGNATURES = {
     "mp_shuffle_prove": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp]),
     "mp_shuffle_and_remask": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp]),
     "mp_shuffle_verify": (_i32, [_vp, _cp, _cp, _cp, _cp]),
+    "mp_shuffle_and_remask_batch": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _u64, _cp, _cp, _i32]),
     "mp_shuffle_verify_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
     "mp_shuffle_verify_resident": (_i32, [_vp, _cp, _cp, _cp, _cp, _vp, _vp]),
     "mp_shuffle_and_remask_resident": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp, _vp]),
@@ -183,6 +184,18 @@ class Context:
         assert len(deck) == 128 * N and len(deck2) == 128 * N
         assert len(proof) == lib.mp_proof_len(self.m, self.n)
         return check(self.h, lib.mp_shuffle_verify(self.h, pk, deck, deck2, proof))
+
+    def shuffle_and_remask_batch(self, pk, decks, perms, rhos, rands, host_threads=0):
+        """perms: flat list of B*N indices.  -> (shuffled decks bytes, proofs bytes)"""
+        N = self.m * self.n
+        B = len(perms) // N
+        assert len(decks) == 128 * N * B and len(rhos) == 32 * N * B
+        assert len(rands) == 32 * B * lib.mp_prover_randomness_len(self.m, self.n)
+        arr = (ctypes.c_uint32 * (N * B))(*perms)
+        out = ctypes.create_string_buffer(128 * N * B)
+        proofs = ctypes.create_string_buffer(lib.mp_proof_len(self.m, self.n) * B)
+        check(self.h, lib.mp_shuffle_and_remask_batch(self.h, pk, decks, arr, rhos, rands, B, out, proofs, host_threads))
+        return out.raw, proofs.raw
 
     def verify_shuffle_batch(self, pk, decks, decks2, proofs, host_threads=0):
         """-> list of per-proof statuses"""

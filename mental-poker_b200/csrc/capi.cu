@@ -249,6 +249,11 @@ extern "C" int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8
   return shuffle_verify(ctx, pk, deck, shuffled_deck, proof);
 }
 
+extern "C" int32_t mp_shuffle_and_remask_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                                               const uint8_t* rhos, const uint8_t* randomness, uint64_t batch,
+                                               uint8_t* out_decks, uint8_t* proofs, int32_t host_threads) {
+  return shuffle_prove_batch(ctx, pk, decks, perms, rhos, randomness, batch, out_decks, proofs, host_threads);
+}
 extern "C" int32_t mp_shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks,
                                            const uint8_t* shuffled_decks, const uint8_t* proofs, uint64_t batch,
                                            int32_t* statuses, int32_t host_threads) {

@@ -29,6 +29,10 @@ struct ShuffleState {
   affine* d_tab = nullptr;
   uint8_t tab_pk[64];
   bool tab_pk_valid = false;
+  // worker contexts of mp_shuffle_prove_batch (own stream / workspace each; same parameters)
+  std::vector<mp_ctx*> workers;
+  uint64_t params_gen = 0;            // bumped by every set_params
+  std::vector<uint64_t> worker_gen;   // generation each worker was configured for
   uint8_t* pinned = nullptr;  // small pinned staging for results
   size_t pinned_cap = 0;
   ~ShuffleState() {
@@ -36,6 +40,7 @@ struct ShuffleState {
     if (pinned) cudaFreeHost(pinned);
     if (ev) cudaEventDestroy(ev);
     if (d_tab) cudaFree(d_tab);
+    for (mp_ctx* w : workers) mp_ctx_destroy(w);
   }
 };
 void shuffle_state_destroy(ShuffleState* s) { delete s; }
@@ -334,6 +339,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a parameter point is not a canonical point of the Stark curve");
   S->m = m;
   S->n = n;
+  S->params_gen++;
   return MP_OK;
 }
 
@@ -817,6 +823,72 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
     if (st != MP_OK) return st;
   }
   return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched prove: B independent shuffle_and_remask calls under the same parameters and key.
+// Small-deck proofs are latency-bound (a chain of ~5 dependent MSM launches with a 253-doubling
+// fold each), so the batch runs P worker contexts concurrently -- one host thread, CUDA stream
+// and workspace each -- and the GPU overlaps their kernels.  Proof i is byte-identical to what
+// mp_shuffle_and_remask produces for the same inputs.
+// ------------------------------------------------------------------------------------------
+int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                            const uint8_t* rhos, const uint8_t* rands, uint64_t B, uint8_t* out_decks,
+                            uint8_t* proofs, int32_t host_threads) {
+  if (!ctx || !pk || (B && (!decks || !perms || !rhos || !rands || !out_decks || !proofs))) return MP_ERR_INVALID_ARG;
+  ShuffleState* S = ctx->shuffle;
+  if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int m = S->m, n = S->n;
+  const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n), rlen = shuffle_randomness_len(m, n) * 32;
+  int P = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+  P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, 32, B}));
+  if (N > 8192) P = 1;  // large decks fill the GPU on their own
+  while ((int)S->workers.size() < P) {
+    mp_ctx* w = nullptr;
+    if (mp_ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");
+    S->workers.push_back(w);
+    S->worker_gen.push_back(0);
+  }
+  for (int t = 0; t < P; t++) {
+    if (S->worker_gen[t] == S->params_gen) continue;
+    int32_t st = shuffle_set_params(S->workers[t], m, n, S->enc_g, S->ck64.data() + 64, S->ck64.data(), S->ghat);
+    if (st != MP_OK) return ctx->fail(st, "worker set_params failed: %s", mp_last_error_string(S->workers[t]));
+    S->worker_gen[t] = S->params_gen;
+  }
+  std::atomic<uint64_t> next{0};
+  std::atomic<int32_t> first_err{MP_OK};
+  std::atomic<int> launches{0};
+  auto run = [&](int t) {
+    mp_ctx* w = S->workers[t];
+    cudaSetDevice(w->device);
+    for (uint64_t i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+      if (first_err.load() != MP_OK) break;
+      const void* d_shuffled = nullptr;
+      int32_t st = shuffle_remask(w, pk, decks + i * N * 128, perms + i * N, rhos + i * N * 32, N, out_decks + i * N * 128,
+                                  nullptr, &d_shuffled);
+      int l = w->launches;
+      if (st == MP_OK)
+        st = shuffle_prove(w, pk, decks + i * N * 128, out_decks + i * N * 128, perms + i * N, rhos + i * N * 32,
+                           rands + i * rlen, proofs + i * plen, d_shuffled);
+      launches.fetch_add(l + w->launches);
+      if (st != MP_OK) {
+        int32_t expected = MP_OK;
+        if (first_err.compare_exchange_strong(expected, st)) ctx->fail(st, "proof %llu: %s", (unsigned long long)i, mp_last_error_string(w));
+        break;
+      }
+    }
+  };
+  if (P == 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < P; t++) pool.emplace_back(run, t);
+    for (auto& th : pool) th.join();
+  }
+  ctx->launches = launches.load();
+  return first_err.load();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -195,3 +195,38 @@ def test_verify_batch_matches_single_and_oracle(ctx, m, n, B):
     single = [ctx.verify_shuffle(pk, decks[i * dlen:(i + 1) * dlen], bytes(bad_decks2[i * dlen:(i + 1) * dlen]),
                                  bytes(bad[i * plen:(i + 1) * plen])) for i in range(B)]
     assert single == want
+
+
+def test_prove_batch_is_byte_identical_to_single_calls(ctx):
+    m, n, B = 3, 4, 9
+    co = c_oracle.COracle(msm_mode=1)
+    pp0, pk0, *_ = instance(m, n, 50)
+    enc_g, ck_g, ck_h, ghat, pk = pb(pp0.enc_g), b"".join(map(pb, pp0.ck_g)), pb(pp0.ck_h), pb(pp0.ghat), pb(pk0)
+    decks = rhos = rands = b""
+    perms = []
+    for s in range(50, 50 + B):
+        _, _, deck, perm, rho, rnd = instance(m, n, s)
+        decks += b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+        perms += perm
+        rhos += b"".join(map(b32, rho))
+        rands += b"".join(map(b32, rnd))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    out_decks, proofs = ctx.shuffle_and_remask_batch(pk, decks, perms, rhos, rands, host_threads=4)
+    assert ctx.launches > 0
+    N, plen, rl = m * n, len(proofs) // B, len(rands) // B
+    for i in range(B):
+        d, p = ctx.shuffle_and_remask(pk, decks[128 * N * i:128 * N * (i + 1)], perms[N * i:N * (i + 1)],
+                                      rhos[32 * N * i:32 * N * (i + 1)], rands[rl * i:rl * (i + 1)])
+        assert d == out_decks[128 * N * i:128 * N * (i + 1)] and p == proofs[plen * i:plen * (i + 1)]
+    i = 4
+    want = co.prove(m, n, enc_g, ck_g, ck_h, ghat, pk, decks[128 * N * i:128 * N * (i + 1)],
+                    out_decks[128 * N * i:128 * N * (i + 1)], perms[N * i:N * (i + 1)],
+                    rhos[32 * N * i:32 * N * (i + 1)], rands[rl * i:rl * (i + 1)])
+    assert want == proofs[plen * i:plen * (i + 1)]
+    assert ctx.verify_shuffle_batch(pk, decks, out_decks, proofs) == [0] * B
+    # a permutation entry out of range is a usage error, not a crash
+    import pytest as _pt
+    bad = list(perms)
+    bad[5] = 10 ** 6
+    with _pt.raises(Exception):
+        ctx.shuffle_and_remask_batch(pk, decks, bad, rhos, rands, host_threads=2)
