@@ -86,6 +86,12 @@ int msm_pick_window(uint64_t avg_len) {
   return best;
 }
 
+#define MP_CK(x)                          \
+  do {                                    \
+    cudaError_t _e = (x);                 \
+    if (_e != cudaSuccess) return _e;     \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------
@@ -188,6 +194,58 @@ cudaError_t xyzz_to_canonical(const xyzz* d_in, uint32_t* d_out, uint64_t n, cud
 }
 
 // ------------------------------------------------------------------------------------------
+// fixed-base tables (kernel family K3 of SURVEY.md 2b): table[w * nb + i] = 2^(c*w) * base_i
+// ------------------------------------------------------------------------------------------
+// thread per base: the chain of c*(W-1) doublings, every window's value kept in XYZZ
+__global__ void __launch_bounds__(64) k_table_shift(const affine* __restrict__ bases, uint32_t nb, uint32_t first,
+                                                    uint32_t count, int c, int W, xyzz* __restrict__ tmp) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  affine P = affine_load(bases + first + i);
+  xyzz cur = xyzz_from_affine(P);
+  for (int w = 0; w < W; w++) {
+    xyzz_store(tmp + (size_t)w * count + i, cur);
+    if (w + 1 < W)
+      for (int k = 0; k < c; k++) cur = xyzz_dbl(cur);
+  }
+}
+// thread per entry: normalise to affine Montgomery (identity stays (0,0))
+__global__ void __launch_bounds__(64) k_table_normalise(const xyzz* __restrict__ tmp, uint32_t nb, uint32_t first,
+                                                        uint32_t count, int W, affine* __restrict__ table) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= count * (uint32_t)W) return;
+  uint32_t w = g / count, i = g % count;
+  affine a = xyzz_to_affine(xyzz_load(tmp + g));
+  uint4* d = reinterpret_cast<uint4*>(table + (size_t)w * nb + first + i);
+  const uint4* s = reinterpret_cast<const uint4*>(&a);
+#pragma unroll
+  for (int k = 0; k < 4; k++) d[k] = s[k];
+}
+
+cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb, uint32_t first, uint32_t count,
+                            int c, affine* d_table, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  const int W = (253 + c - 1) / c;
+  xyzz* tmp;
+  MP_CK(ws->get(13, (size_t)W * count, &tmp));
+  k_table_shift<<<(count + 63) / 64, 64, 0, stream>>>(d_bases, nb, first, count, c, W, tmp);
+  k_table_normalise<<<(count * W + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
+  return cudaGetLastError();
+}
+
+int msm_pick_table_window(uint64_t typical_len) {
+  // one bucket set per job: minimise W * len + 2.8 * 2^(c-1)
+  int best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= 13; c++) {
+    int W = (253 + c - 1) / c;
+    double cost = (double)W * (double)typical_len + 2.8 * (double)(1u << (c - 1));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------
 // digits
 // ------------------------------------------------------------------------------------------
 // digits[w * ns + i] = (|d| - 1) | (d < 0) << 31, or kNoDigit when d == 0.
@@ -229,7 +287,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 __global__ void __launch_bounds__(256) k_count(const uint32_t* __restrict__ digits,
                                                const MsmJob* __restrict__ jobs,
                                                uint32_t* __restrict__ counts, uint64_t ns, int W,
-                                               uint32_t B) {
+                                               uint32_t B, int Wb) {
   const MsmJob job = jobs[blockIdx.y];
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < job.len;
        t += gridDim.x * blockDim.x) {
@@ -237,7 +295,8 @@ __global__ void __launch_bounds__(256) k_count(const uint32_t* __restrict__ digi
     for (int w = 0; w < W; w++) {
       uint32_t d = digits[(uint64_t)w * ns + si];
       if (d != kNoDigit) {
-        uint64_t bucket = ((uint64_t)blockIdx.y * W + w) * B + (d & 0x7fffffffu);
+        // Wb == W: one bucket set per window; Wb == 1 (fixed-base tables): all windows share one
+        uint64_t bucket = ((uint64_t)blockIdx.y * Wb + (Wb == 1 ? 0 : w)) * B + (d & 0x7fffffffu);
         atomicAdd(&counts[bucket], 1u);
       }
     }
@@ -248,7 +307,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ di
                                                  const MsmJob* __restrict__ jobs,
                                                  uint32_t* __restrict__ cursor,
                                                  uint32_t* __restrict__ sorted, uint64_t ns, int W,
-                                                 uint32_t B) {
+                                                 uint32_t B, int Wb, uint32_t tab_nb) {
   const MsmJob job = jobs[blockIdx.y];
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < job.len;
        t += gridDim.x * blockDim.x) {
@@ -256,9 +315,10 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ di
     for (int w = 0; w < W; w++) {
       uint32_t d = digits[(uint64_t)w * ns + si];
       if (d != kNoDigit) {
-        uint64_t bucket = ((uint64_t)blockIdx.y * W + w) * B + (d & 0x7fffffffu);
+        uint64_t bucket = ((uint64_t)blockIdx.y * Wb + (Wb == 1 ? 0 : w)) * B + (d & 0x7fffffffu);
         uint32_t pos = atomicAdd(&cursor[bucket], 1u);
-        sorted[pos] = (job.point_off + t) | (d & 0x80000000u);
+        // table mode: the point is the precomputed 2^(c*w) * base, stored window-major
+        sorted[pos] = ((uint32_t)w * tab_nb + job.point_off + t) | (d & 0x80000000u);
       }
     }
   }
@@ -573,15 +633,10 @@ __global__ void __launch_bounds__(32) k_fold(const xyzz* __restrict__ win_out, i
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
-#define MP_CK(x)                          \
-  do {                                    \
-    cudaError_t _e = (x);                 \
-    if (_e != cudaSuccess) return _e;     \
-  } while (0)
 
 cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
                     const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
-                    xyzz* d_out, cudaStream_t stream, int w_begin, int w_count) {
+                    xyzz* d_out, cudaStream_t stream, int w_begin, int w_count, uint32_t table_nb) {
   ws->launches = 0;
   if (njobs <= 0) return cudaSuccess;
   if (ncomp != 1 && ncomp != 2) return cudaErrorInvalidValue;
@@ -590,13 +645,18 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   if (w_count < 0) w_count = W_all - w_begin;
   if (w_begin < 0 || w_count < 1 || w_begin + w_count > W_all) return cudaErrorInvalidValue;
   const int W = w_count;  // windows handled by this call: [w_begin, w_begin + W)
+  // fixed-base table mode (table_nb = bases per window of a table built by msm_build_table with
+  // the same c): every window's digits index ONE bucket set per job and the entries point at the
+  // pre-shifted bases, so there is one bucket reduction per job and no fold doublings at all
+  if (table_nb && (w_begin != 0 || W != W_all)) return cudaErrorInvalidValue;
+  const int Wb = table_nb ? 1 : W;
   const uint32_t B = 1u << (c - 1);
   // buckets per reduce_seg thread: as long as the chip stays full (>= ~150k threads), longer
   // segments leave fewer segment sums for the per-window combine
   uint32_t L = std::min<uint32_t>(kSegLen, B);
-  while (L < B && L < 256 && (uint64_t)njobs * W * ncomp * (B / (2 * L)) >= 150000) L *= 2;
+  while (L < B && L < 256 && (uint64_t)njobs * Wb * ncomp * (B / (2 * L)) >= 150000) L *= 2;
   const uint32_t nseg = B / L;
-  const uint64_t nwin = (uint64_t)njobs * W;
+  const uint64_t nwin = (uint64_t)njobs * Wb;
   const uint64_t nbuckets = nwin * B;
   uint64_t total_terms = 0;
   uint32_t max_len = 0;
@@ -640,7 +700,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   }
   if (max_len > 0) {
     dim3 grid((unsigned)std::min<uint64_t>((max_len + 255) / 256, 65535), (unsigned)njobs);
-    k_count<<<grid, 256, 0, stream>>>(digits, d_jobs, counts, n_scalars, W, B);
+    k_count<<<grid, 256, 0, stream>>>(digits, d_jobs, counts, n_scalars, W, B, Wb);
     ws->launches++;
   }
   k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, stream>>>(counts, tile_sums, nbuckets + 1);
@@ -649,7 +709,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   ws->launches += 3;
   if (max_len > 0) {
     dim3 grid((unsigned)std::min<uint64_t>((max_len + 255) / 256, 65535), (unsigned)njobs);
-    k_scatter<<<grid, 256, 0, stream>>>(digits, d_jobs, cursor, sorted, n_scalars, W, B);
+    k_scatter<<<grid, 256, 0, stream>>>(digits, d_jobs, cursor, sorted, n_scalars, W, B, Wb, table_nb);
     ws->launches++;
   }
   if (max_chunks > 0) {
@@ -692,7 +752,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
   else
     k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
-  k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, W, c, ncomp, d_out);
+  k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, Wb, c, ncomp, d_out);
   ws->launches += 3;
   return cudaGetLastError();
 }

@@ -44,11 +44,20 @@ int msm_pick_window(uint64_t avg_len);
 // Returns cudaSuccess or the first CUDA error.  Asynchronous on `stream`.
 cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
                     const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
-                    xyzz* d_out, cudaStream_t stream, int w_begin = 0, int w_count = -1);
+                    xyzz* d_out, cudaStream_t stream, int w_begin = 0, int w_count = -1, uint32_t table_nb = 0);
 // With a window range [w_begin, w_begin + w_count) of the W = ceil(253/c) windows the result is
 //   sum_{w in range} 2^(c*(w - w_begin)) * (window sum w)
 // so that  full MSM = sum over ranges of 2^(c*w_begin) * partial  (window-range split across GPUs).
 inline int msm_num_windows(int c) { return (253 + c - 1) / c; }
+
+// Fixed-base mode (Pedersen commitments over a constant key).  msm_build_table fills
+//   d_table[w * nb + first + i] = 2^(c*w) * d_bases[first + i],  w < msm_num_windows(c), i < count
+// (affine Montgomery; rebuild a sub-range when one base changes, e.g. the public key).  msm_run with
+// table_nb = nb, d_points = d_table and the same c then needs ONE bucket set per job: entries of
+// all windows go to bucket |digit|, the reduction runs once per job and no fold doublings remain.
+cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb, uint32_t first, uint32_t count,
+                            int c, affine* d_table, cudaStream_t stream);
+int msm_pick_table_window(uint64_t typical_len);
 
 // number of kernels the last msm_run launched / EC additions it performed (host-side count
 // of scheduled bucket additions, for EC-adds/s reporting)

@@ -24,6 +24,11 @@ struct ShuffleState {
   std::vector<uint8_t> ck64;  // (n+1) * 64 canonical: h, g_1 .. g_n   (MSM order of a commitment)
   uint8_t enc_g[64], ghat[64], gsum[64];  // gsum = g_1 + .. + g_n  (com(c,..,c; 0) = c * gsum)
   affine* d_ck = nullptr;     // device, Montgomery: h, g_1..g_n, then enc_g, ghat, pk (n + 4 points)
+  // fixed-base table of those n + 4 bases for the commitment jobs: tab_ck[w*(n+4) + i] = 2^(c*w) * base_i
+  affine* d_tab_ck = nullptr;
+  int tab_c = 0;
+  uint8_t ck_pk[64];          // public key currently in slot n + 3 of d_ck / d_tab_ck
+  bool ck_pk_valid = false;
   cudaEvent_t ev = nullptr;   // marks small device->host copies the host waits for mid-stream
   // fixed-base tables for remasking: tab[base][j][d-1] = d * 2^(8j) * base, base 0 = g, 1 = pk
   affine* d_tab = nullptr;
@@ -37,6 +42,7 @@ struct ShuffleState {
   size_t pinned_cap = 0;
   ~ShuffleState() {
     if (d_ck) cudaFree(d_ck);
+    if (d_tab_ck) cudaFree(d_tab_ck);
     if (pinned) cudaFreeHost(pinned);
     if (ev) cudaEventDestroy(ev);
     if (d_tab) cudaFree(d_tab);
@@ -331,7 +337,15 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   CK(points_to_mont((const uint32_t*)d_canon, S->d_ck, (uint64_t)n + 3, d_bad, ctx->stream));
   CK(build_table(S, 0, d_canon + (size_t)(n + 1) * 64, d_bad, ctx->stream));  // remask table of g
   S->tab_pk_valid = false;
-  ctx->launches += 2;
+  // fixed-base table for the commitment jobs (the pk column is filled per call)
+  S->tab_c = msm_pick_table_window((uint64_t)n + 1);
+  if (S->d_tab_ck) cudaFree(S->d_tab_ck);
+  S->d_tab_ck = nullptr;
+  CK(cudaMalloc(&S->d_tab_ck, sizeof(affine) * (size_t)msm_num_windows(S->tab_c) * (size_t)(n + 4)));
+  CK(cudaMemsetAsync(S->d_tab_ck, 0, sizeof(affine) * (size_t)msm_num_windows(S->tab_c) * (size_t)(n + 4), ctx->stream));
+  CK(msm_build_table(ctx->ws, S->d_ck, (uint32_t)(n + 4), 0, (uint32_t)(n + 3), S->tab_c, S->d_tab_ck, ctx->stream));
+  S->ck_pk_valid = false;
+  ctx->launches += 4;
   int bad = 0;
   CK(cudaMemcpyAsync(S->gsum, d_res, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -953,7 +967,8 @@ static int32_t commit_rows_device(mp_ctx* ctx, const fr* d_rows, uint64_t stride
   ctx->launches += 1;
   std::vector<MsmJob> jobs((size_t)count);
   for (int k = 0; k < count; k++) jobs[k] = MsmJob{(uint32_t)(k * (n + 1)), 0, (uint32_t)(n + 1)};
-  CK(msm_run(ctx->ws, d_scal, total, S->d_ck, 1, jobs.data(), count, msm_pick_window(n + 1), d_out, ctx->stream));
+  CK(msm_run(ctx->ws, d_scal, total, S->d_tab_ck, 1, jobs.data(), count, S->tab_c, d_out, ctx->stream, 0, -1,
+             (uint32_t)(n + 4)));
   ctx->launches += msm_last_launches(ctx->ws);
   return MP_OK;
 }
@@ -1063,7 +1078,13 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(cudaMemcpyAsync(d_ct_canon + N * 128, tail, 256, cudaMemcpyHostToDevice, st));
   }
   CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, T2 * 2, d_bad, st));
-  CK(cudaMemcpyAsync(S->d_ck + (n + 3), d_ct_mont + 2 * N + 1, sizeof(affine), cudaMemcpyDeviceToDevice, st));  // pk
+  if (!S->ck_pk_valid || memcmp(S->ck_pk, pk, 64) != 0) {  // pk column of the fixed-base table (cached)
+    CK(cudaMemcpyAsync(S->d_ck + (n + 3), d_ct_mont + 2 * N + 1, sizeof(affine), cudaMemcpyDeviceToDevice, st));
+    CK(msm_build_table(ctx->ws, S->d_ck, (uint32_t)(n + 4), (uint32_t)(n + 3), 1, S->tab_c, S->d_tab_ck, st));
+    memcpy(S->ck_pk, pk, 64);
+    S->ck_pk_valid = true;
+    ctx->launches += 2;
+  }
   CK(cudaMemcpyAsync(d_perm, perm, N * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_xpow, rho, N * 32, cudaMemcpyHostToDevice, st));  // staging: canonical rho
   CK(fr_from_canonical_vec((const uint32_t*)d_xpow, d_rho, N, st));
@@ -1212,7 +1233,8 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 2 * k, 0, 2});                               // (h, g_1)
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 4 * m + k, (uint32_t)(n + 1), 1});           // enc_g
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 6 * m + 2 * k, (uint32_t)(n + 2), 2});       // (ghat, pk)
-    CK(msm_run(ctx->ws, d_g1_scal, base + nsmall, S->d_ck, 1, jobs.data(), (int)jobs.size(), msm_pick_window(n + 1), d_g1_out, st));
+    CK(msm_run(ctx->ws, d_g1_scal, base + nsmall, S->d_tab_ck, 1, jobs.data(), (int)jobs.size(), S->tab_c, d_g1_out, st, 0, -1,
+               (uint32_t)(n + 4)));
     ctx->launches += msm_last_launches(ctx->ws);
     k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_g1_out + R + 2 * m, d_g1_out + R + 4 * m, 2 * m);
     CK(cudaGetLastError());
@@ -1272,8 +1294,8 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     ctx->launches += 3;
     std::vector<MsmJob> jobs = {MsmJob{0, 0, (uint32_t)tot}, MsmJob{(uint32_t)tot, 0, (uint32_t)tot}};
     for (int k = 0; k <= 2 * m; k++) jobs.push_back(MsmJob{(uint32_t)(2 * tot + 2 * k), 0, 2});
-    CK(msm_run(ctx->ws, d_g1_scal, 2 * tot + 2 * (2 * (size_t)m + 1), S->d_ck, 1, jobs.data(), (int)jobs.size(),
-               msm_pick_window(n + 1), d_g1_out, st));
+    CK(msm_run(ctx->ws, d_g1_scal, 2 * tot + 2 * (2 * (size_t)m + 1), S->d_tab_ck, 1, jobs.data(), (int)jobs.size(),
+               S->tab_c, d_g1_out, st, 0, -1, (uint32_t)(n + 4)));
     ctx->launches += msm_last_launches(ctx->ws);
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, 2 * (size_t)m + 3, st));
     ctx->launches += 1;
