@@ -209,27 +209,50 @@ __global__ void __launch_bounds__(64) k_table_shift(const affine* __restrict__ b
       for (int k = 0; k < c; k++) cur = xyzz_dbl(cur);
   }
 }
-// thread per entry: normalise to affine Montgomery (identity stays (0,0))
+// thread per base: normalise its W shifted copies to affine Montgomery with ONE inversion
+// (Montgomery's trick over the W values of ZZ*ZZZ); the identity stays (0,0)
+static constexpr int kMaxTableWindows = 64;
 __global__ void __launch_bounds__(64) k_table_normalise(const xyzz* __restrict__ tmp, uint32_t nb, uint32_t first,
                                                         uint32_t count, int W, affine* __restrict__ table) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= count * (uint32_t)W) return;
-  uint32_t w = g / count, i = g % count;
-  affine a = xyzz_to_affine(xyzz_load(tmp + g));
-  uint4* d = reinterpret_cast<uint4*>(table + (size_t)w * nb + first + i);
-  const uint4* s = reinterpret_cast<const uint4*>(&a);
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  fq pre[kMaxTableWindows];  // pre[w] = product of z_0 .. z_w (z = ZZ*ZZZ, or 1 for the identity)
+  fq acc = fq_one();
+  for (int w = 0; w < W; w++) {
+    xyzz p = xyzz_load(tmp + (size_t)w * count + i);
+    if (!xyzz_is_identity(p)) acc = fq_mul(acc, fq_mul(p.ZZ, p.ZZZ));
+    pre[w] = acc;
+  }
+  fq inv = fq_inv(acc);  // 1 / (z_0 * ... * z_{W-1})
+  for (int w = W - 1; w >= 0; w--) {
+    xyzz p = xyzz_load(tmp + (size_t)w * count + i);
+    affine a;
+    if (xyzz_is_identity(p)) {
+      a.x = fq_zero();
+      a.y = fq_zero();
+    } else {
+      fq z = fq_mul(p.ZZ, p.ZZZ);
+      fq iz = w > 0 ? fq_mul(inv, pre[w - 1]) : inv;  // 1 / z_w
+      inv = fq_mul(inv, z);                            // drop z_w from the running inverse
+      a.x = fq_reduce_full(fq_mul(p.X, fq_mul(iz, p.ZZZ)));
+      a.y = fq_reduce_full(fq_mul(p.Y, fq_mul(iz, p.ZZ)));
+    }
+    uint4* d = reinterpret_cast<uint4*>(table + (size_t)w * nb + first + i);
+    const uint4* s = reinterpret_cast<const uint4*>(&a);
 #pragma unroll
-  for (int k = 0; k < 4; k++) d[k] = s[k];
+    for (int k = 0; k < 4; k++) d[k] = s[k];
+  }
 }
 
 cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb, uint32_t first, uint32_t count,
                             int c, affine* d_table, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   const int W = (253 + c - 1) / c;
+  if (W > kMaxTableWindows) return cudaErrorInvalidValue;
   xyzz* tmp;
   MP_CK(ws->get(13, (size_t)W * count, &tmp));
   k_table_shift<<<(count + 63) / 64, 64, 0, stream>>>(d_bases, nb, first, count, c, W, tmp);
-  k_table_normalise<<<(count * W + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
+  k_table_normalise<<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
   return cudaGetLastError();
 }
 
@@ -237,7 +260,7 @@ int msm_pick_table_window(uint64_t typical_len) {
   // one bucket set per job: minimise W * len + 2.8 * 2^(c-1)
   int best = 4;
   double best_cost = 1e300;
-  for (int c = 4; c <= 13; c++) {
+  for (int c = 4; c <= 16; c++) {
     int W = (253 + c - 1) / c;
     double cost = (double)W * (double)typical_len + 2.8 * (double)(1u << (c - 1));
     if (cost < best_cost) { best_cost = cost; best = c; }
