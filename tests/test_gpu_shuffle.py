@@ -197,8 +197,12 @@ def test_verify_batch_matches_single_and_oracle(ctx, m, n, B):
     assert single == want
 
 
-def test_prove_batch_is_byte_identical_to_single_calls(ctx):
-    m, n, B = 3, 4, 9
+@pytest.mark.parametrize("m,n,B,workers", [(3, 4, 9, False), (3, 4, 9, True), (4, 13, 6, False), (2, 2, 3, False)])
+def test_prove_batch_is_byte_identical_to_single_calls(ctx, m, n, B, workers, monkeypatch):
+    # two implementations behind mp_shuffle_and_remask_batch: the lockstep prover (default for
+    # small decks) and concurrent worker contexts (large decks, or forced by MP_BATCH_WORKERS)
+    if workers:
+        monkeypatch.setenv("MP_BATCH_WORKERS", "1")
     co = c_oracle.COracle(msm_mode=1)
     pp0, pk0, *_ = instance(m, n, 50)
     enc_g, ck_g, ck_h, ghat, pk = pb(pp0.enc_g), b"".join(map(pb, pp0.ck_g)), pb(pp0.ck_h), pb(pp0.ghat), pb(pk0)
@@ -218,7 +222,7 @@ def test_prove_batch_is_byte_identical_to_single_calls(ctx):
         d, p = ctx.shuffle_and_remask(pk, decks[128 * N * i:128 * N * (i + 1)], perms[N * i:N * (i + 1)],
                                       rhos[32 * N * i:32 * N * (i + 1)], rands[rl * i:rl * (i + 1)])
         assert d == out_decks[128 * N * i:128 * N * (i + 1)] and p == proofs[plen * i:plen * (i + 1)]
-    i = 4
+    i = B - 1
     want = co.prove(m, n, enc_g, ck_g, ck_h, ghat, pk, decks[128 * N * i:128 * N * (i + 1)],
                     out_decks[128 * N * i:128 * N * (i + 1)], perms[N * i:N * (i + 1)],
                     rhos[32 * N * i:32 * N * (i + 1)], rands[rl * i:rl * (i + 1)])
