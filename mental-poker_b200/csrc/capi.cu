@@ -226,6 +226,8 @@ static int32_t shuffle_and_remask_common(mp_ctx* ctx, const uint8_t* pk, const u
                                          uint8_t* proof_out, const void* d_deck) {
   if (!ctx || !ctx->shuffle) return ctx ? ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called") : MP_ERR_INVALID_ARG;
   uint64_t n_cards = (uint64_t)mp_params_m(ctx) * mp_params_n(ctx);
+  if (!d_deck && shuffle_uses_small_deck_path(n_cards))  // small decks: the lockstep prover with a batch of one
+    return shuffle_prove_batch(ctx, pk, deck, perm, rho, randomness, 1, out_deck, proof_out, 1);
   const void* d_shuffled = nullptr;
   int32_t st = shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck, d_deck, &d_shuffled);
   if (st != MP_OK) return st;

@@ -271,6 +271,14 @@ static cudaError_t build_table(ShuffleState* S, int which, const uint8_t* d_base
   return cudaGetLastError();
 }
 
+// Decks up to this many cards take the host-scalar lockstep prover / batched verifier (every
+// group operation still runs on the GPU); larger decks use the device scalar kernels.  The
+// environment override exists so the tests can drive both implementations at the same sizes.
+static size_t small_deck_max() {
+  const char* e = getenv("MP_SMALL_DECK_MAX");
+  return e ? (size_t)strtoull(e, nullptr, 10) : 8192;
+}
+
 // ------------------------------------------------------------------------------------------
 // set-up
 // ------------------------------------------------------------------------------------------
@@ -814,7 +822,7 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
   ctx->launches = 0;
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n);
-  if (N > 8192) {  // large decks: the single-proof path already fills the GPU
+  if (N > small_deck_max()) {  // large decks: the single-proof path already fills the GPU
     int launches = 0;
     for (uint64_t p = 0; p < B; p++) {
       int32_t st = shuffle_verify(ctx, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen);
@@ -847,6 +855,8 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
 // and workspace each -- and the GPU overlaps their kernels.  Proof i is byte-identical to what
 // mp_shuffle_and_remask produces for the same inputs.
 // ------------------------------------------------------------------------------------------
+bool shuffle_uses_small_deck_path(uint64_t n_cards) { return n_cards <= small_deck_max() && !getenv("MP_BATCH_WORKERS"); }
+
 static int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                                const uint8_t* rhos, const uint8_t* rands, size_t Bs, uint8_t* out_decks, uint8_t* proofs,
                                int threads);
@@ -862,7 +872,7 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n), rlen = shuffle_randomness_len(m, n) * 32;
   int P = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
-  if (N <= 8192 && !getenv("MP_BATCH_WORKERS")) {
+  if (N <= small_deck_max() && !getenv("MP_BATCH_WORKERS")) {
     // small decks: lockstep over sub-batches (job grid <= 65535 per launch; bounded staging memory)
     const int threads = std::max(1, std::min(P, 64));
     const size_t per_proof_jobs = (size_t)(m + 4 + 6 * m);
@@ -881,7 +891,7 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
   }
   // large decks (or MP_BATCH_WORKERS set): concurrent worker contexts running the single-proof path
   P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, 32, B}));
-  if (N > 8192) P = 1;  // large decks fill the GPU on their own
+  if (N > small_deck_max()) P = 1;  // large decks fill the GPU on their own
   while ((int)S->workers.size() < P) {
     mp_ctx* w = nullptr;
     if (mp_ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");

@@ -49,6 +49,7 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
 int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
                              const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads);
 
+bool shuffle_uses_small_deck_path(uint64_t n_cards);
 int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                             const uint8_t* rhos, const uint8_t* rands, uint64_t B, uint8_t* out_decks,
                             uint8_t* proofs, int32_t host_threads);

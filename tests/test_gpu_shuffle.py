@@ -28,8 +28,17 @@ def test_verify_accepts_golden_proofs(ctx, idx):
     assert ctx.launches > 0
 
 
+@pytest.fixture(params=["host_scalars", "device_scalars"])
+def scalar_path(request, monkeypatch):
+    """Small decks default to the host-scalar lockstep prover; MP_SMALL_DECK_MAX=0 forces the
+    device scalar kernels (the 2^16-card implementation) at the same sizes."""
+    if request.param == "device_scalars":
+        monkeypatch.setenv("MP_SMALL_DECK_MAX", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("idx", [0, 1, 2, 3])
-def test_prove_is_byte_exact_vs_golden(ctx, idx):
+def test_prove_is_byte_exact_vs_golden(ctx, idx, scalar_path):
     fx = GOLD["shuffle"][idx]
     setup_ctx(ctx, fx)
     deck2, proof = ctx.shuffle_and_remask(h(fx["pk"]), h(fx["deck"]), fx["perm"], h(fx["rho"]), h(fx["rand"]))
@@ -125,7 +134,7 @@ def test_remask_and_commit_primitives(ctx):
 
 
 @pytest.mark.parametrize("m,n,seed", [(2, 2, 5), (5, 3, 6), (8, 8, 7), (16, 32, 8)])
-def test_round_trip_other_shapes_vs_c_oracle(ctx, m, n, seed):
+def test_round_trip_other_shapes_vs_c_oracle(ctx, m, n, seed, scalar_path):
     """Byte-exact against the C oracle at sizes the Python oracle would take minutes for."""
     pp, pk, deck, perm, rho, rnd = instance(m, n, seed)
     co = c_oracle.COracle(msm_mode=1)
@@ -140,7 +149,7 @@ def test_round_trip_other_shapes_vs_c_oracle(ctx, m, n, seed):
     assert co.verify(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, proof) == 0
 
 
-def test_identity_and_duplicate_cards(ctx):
+def test_identity_and_duplicate_cards(ctx, scalar_path):
     """Edge decks: identity ciphertext components, duplicated cards, rho = 0 and rho = n-1."""
     m, n = 3, 4
     pp, pk, deck, perm, rho, rnd = instance(m, n, 9)
