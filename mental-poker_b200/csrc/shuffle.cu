@@ -279,6 +279,51 @@ static size_t small_deck_max() {
   return e ? (size_t)strtoull(e, nullptr, 10) : 8192;
 }
 
+// Runs fn(worker, i) for i in [0, B) on P worker contexts (own stream / workspace / tables each),
+// one host thread per worker.  Returns the first error; ctx->launches = total kernel launches.
+template <typename F>
+static int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn) {
+  ShuffleState* S = ctx->shuffle;
+  while ((int)S->workers.size() < P) {
+    mp_ctx* w = nullptr;
+    if (mp_ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");
+    S->workers.push_back(w);
+    S->worker_gen.push_back(0);
+  }
+  for (int t = 0; t < P; t++) {
+    if (S->worker_gen[t] == S->params_gen) continue;
+    int32_t st = shuffle_set_params(S->workers[t], S->m, S->n, S->enc_g, S->ck64.data() + 64, S->ck64.data(), S->ghat);
+    if (st != MP_OK) return ctx->fail(st, "worker set_params failed: %s", mp_last_error_string(S->workers[t]));
+    S->worker_gen[t] = S->params_gen;
+  }
+  std::atomic<uint64_t> next{0};
+  std::atomic<int32_t> first_err{MP_OK};
+  std::atomic<int> launches{0};
+  auto run = [&](int t) {
+    mp_ctx* w = S->workers[t];
+    cudaSetDevice(w->device);
+    for (uint64_t i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+      if (first_err.load() != MP_OK) break;
+      int32_t st = fn(w, i);
+      launches.fetch_add(w->launches);
+      if (st < 0) {
+        int32_t expected = MP_OK;
+        if (first_err.compare_exchange_strong(expected, st)) ctx->fail(st, "item %llu: %s", (unsigned long long)i, mp_last_error_string(w));
+        break;
+      }
+    }
+  };
+  if (P == 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < P; t++) pool.emplace_back(run, t);
+    for (auto& th : pool) th.join();
+  }
+  ctx->launches = launches.load();
+  return first_err.load();
+}
+
 // ------------------------------------------------------------------------------------------
 // set-up
 // ------------------------------------------------------------------------------------------
@@ -822,16 +867,16 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
   ctx->launches = 0;
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n);
-  if (N > small_deck_max()) {  // large decks: the single-proof path already fills the GPU
-    int launches = 0;
-    for (uint64_t p = 0; p < B; p++) {
-      int32_t st = shuffle_verify(ctx, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen);
-      launches += ctx->launches;
-      if (st < 0) return st;
-      statuses[p] = st;
-    }
-    ctx->launches = launches;
-    return MP_OK;
+  if (N > small_deck_max()) {
+    // large decks: the single-proof verifier per deck, on a few worker contexts so that one
+    // proof's serial statement hash (host) overlaps the other proofs' MSMs (device)
+    int P = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+    P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, 8, B}));
+    return run_on_workers(ctx, P, B, [&](mp_ctx* w, uint64_t p) {
+      int32_t st = shuffle_verify(w, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen);
+      if (st >= 0) statuses[p] = st;
+      return st < 0 ? st : MP_OK;
+    });
   }
   int threads = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
   threads = std::max(1, std::min(threads, 64));
@@ -889,53 +934,22 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
     ctx->launches = total;
     return MP_OK;
   }
-  // large decks (or MP_BATCH_WORKERS set): concurrent worker contexts running the single-proof path
-  P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, 32, B}));
-  if (N > small_deck_max()) P = 1;  // large decks fill the GPU on their own
-  while ((int)S->workers.size() < P) {
-    mp_ctx* w = nullptr;
-    if (mp_ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");
-    S->workers.push_back(w);
-    S->worker_gen.push_back(0);
-  }
-  for (int t = 0; t < P; t++) {
-    if (S->worker_gen[t] == S->params_gen) continue;
-    int32_t st = shuffle_set_params(S->workers[t], m, n, S->enc_g, S->ck64.data() + 64, S->ck64.data(), S->ghat);
-    if (st != MP_OK) return ctx->fail(st, "worker set_params failed: %s", mp_last_error_string(S->workers[t]));
-    S->worker_gen[t] = S->params_gen;
-  }
-  std::atomic<uint64_t> next{0};
-  std::atomic<int32_t> first_err{MP_OK};
-  std::atomic<int> launches{0};
-  auto run = [&](int t) {
-    mp_ctx* w = S->workers[t];
-    cudaSetDevice(w->device);
-    for (uint64_t i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
-      if (first_err.load() != MP_OK) break;
-      const void* d_shuffled = nullptr;
-      int32_t st = shuffle_remask(w, pk, decks + i * N * 128, perms + i * N, rhos + i * N * 32, N, out_decks + i * N * 128,
-                                  nullptr, &d_shuffled);
-      int l = w->launches;
-      if (st == MP_OK)
-        st = shuffle_prove(w, pk, decks + i * N * 128, out_decks + i * N * 128, perms + i * N, rhos + i * N * 32,
-                           rands + i * rlen, proofs + i * plen, d_shuffled);
-      launches.fetch_add(l + w->launches);
-      if (st != MP_OK) {
-        int32_t expected = MP_OK;
-        if (first_err.compare_exchange_strong(expected, st)) ctx->fail(st, "proof %llu: %s", (unsigned long long)i, mp_last_error_string(w));
-        break;
-      }
+  // large decks (or MP_BATCH_WORKERS set): concurrent worker contexts running the single-proof path.
+  // For 2^16-card decks a few workers are enough to hide each proof's serial Blake2s statement
+  // absorb (host) behind the other proofs' kernels (device).
+  P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, (uint64_t)(N > small_deck_max() ? 3 : 32), B}));
+  return run_on_workers(ctx, P, B, [&](mp_ctx* w, uint64_t i) {
+    const void* d_shuffled = nullptr;
+    int32_t st = shuffle_remask(w, pk, decks + i * N * 128, perms + i * N, rhos + i * N * 32, N, out_decks + i * N * 128,
+                                nullptr, &d_shuffled);
+    int l = w->launches;
+    if (st == MP_OK) {
+      st = shuffle_prove(w, pk, decks + i * N * 128, out_decks + i * N * 128, perms + i * N, rhos + i * N * 32,
+                         rands + i * rlen, proofs + i * plen, d_shuffled);
+      w->launches += l;
     }
-  };
-  if (P == 1) {
-    run(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < P; t++) pool.emplace_back(run, t);
-    for (auto& th : pool) th.join();
-  }
-  ctx->launches = launches.load();
-  return first_err.load();
+    return st;
+  });
 }
 
 // ------------------------------------------------------------------------------------------
