@@ -491,6 +491,7 @@ MP_HD fq fq_mont_reduce(const uint32_t* T) {
       : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
         "r"(ev[8]), "r"(ev[9]), "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]),
         "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]));
+  (void)w1;  // word 1 of V only feeds the carry into word 2
   // r = T_hi + V + e
   asm("add.cc.u32 %0, %8, %16;\n\t"
       "addc.cc.u32 %1, %9, %17;\n\t"

@@ -63,7 +63,7 @@ enum Slot {  // ctx->scratch slots owned by this file
   sCtCanon, sCtMont, sCtScal, sCtOut,
   sResults, sPartials,
   sFrA, sFrB, sFrD, sFrBv, sFrXpow, sFrAme, sFrTmp0, sFrTmp1, sFrTmp2, sFrPairs, sFrSmall,
-  sPerm, sRho, sCtOut2, sCanonOut, sCtTable,
+  sPerm, sRho, sCanonOut, sCtTable,
 };
 
 #define CK(x)                                                    \
@@ -627,7 +627,7 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
 
   // ---- 3. O(N) scalar vectors on the device
   const std::vector<fr> me_a = h_frs(proof + L.mea, n);
-  const fr me_r = h_fr(proof + L.mer), me_b = h_fr(proof + L.meb), me_s = h_fr(proof + L.mes), me_tau = h_fr(proof + L.metau);
+  const fr me_b = h_fr(proof + L.meb), me_tau = h_fr(proof + L.metau);
   const std::vector<fr> xmp = h_powers(xm, 2 * m);
   SmallUpload up;
   fr yz[2] = {y, z};
