@@ -191,6 +191,8 @@ int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64_t* bucket_
 int32_t mp_dbg_fq_mul(mp_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 int32_t mp_dbg_point_add(mp_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out);
 int32_t mp_dbg_scalar_mul(mp_ctx* ctx, const uint8_t* p, const uint8_t* k, uint64_t n, uint8_t* out);
+/* host-side probe: milliseconds the Fiat-Shamir transcript needs to absorb n_points points */
+double mp_dbg_transcript_ms(uint64_t n_points);
 /* integer-pipe microbenchmarks: returns milliseconds for `iters` dependent-chain iterations
  * on a full-chip grid; *ops receives the number of counted operations executed.  which: 0 IMAD.WIDE,
  * 1 IMAD.LO, 2 fq_mul, 3 xyzz_madd, 4 fq_sqr, 5 carry-chained IMAD.WIDE pairs (counted as

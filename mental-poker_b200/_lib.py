@@ -51,6 +51,7 @@ SIGNATURES = {
     "mp_dbg_fq_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
     "mp_dbg_point_add": (_i32, [_vp, _cp, _cp, _u64, _cp]),
     "mp_dbg_scalar_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp_dbg_transcript_ms": (ctypes.c_double, [_u64]),
     "mp_dbg_bench": (_i32, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

@@ -10,6 +10,8 @@
 #include "ctx.cuh"
 #include "msm.cuh"
 #include "shuffle.cuh"
+#include "transcript.hpp"
+#include <chrono>
 
 using namespace mp;
 
@@ -343,6 +345,20 @@ extern "C" int32_t mp_dbg_scalar_mul(mp_ctx* ctx, const uint8_t* p, const uint8_
   return dbg_map(ctx, p, 64, k, 32, n, out, 64, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
     k_dbg_scalar_mul<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t*)da, (const uint32_t*)db, (uint32_t*)dout, n);
   });
+}
+
+// host-side probe: milliseconds to absorb `n_points` 64-byte points into a transcript (the
+// statement absorb of a proof is 4 * cards + n + m + 4 points)
+extern "C" double mp_dbg_transcript_ms(uint64_t n_points) {
+  std::vector<uint8_t> pts(n_points * 64, 7);
+  auto t0 = std::chrono::steady_clock::now();
+  Transcript fs;
+  fs.begin();
+  fs.feed_points64(pts.data(), n_points);
+  fs.end();
+  volatile uint32_t sink = fs.challenge().v[0];
+  (void)sink;
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // ------------------------------------------------------------------------------------------

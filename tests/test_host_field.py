@@ -14,10 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P, N = stark.P, stark.N
 
 
-@pytest.fixture(scope="module")
-def shim(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("shim") / "host_shim.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", out,
+@pytest.fixture(scope="module", params=["default", "scalar_blake2s"])
+def shim(request, tmp_path_factory):
+    # "scalar_blake2s" forces the portable compression function (the default build picks the
+    # AVX2 row formulation at run time on x86 hosts)
+    out = str(tmp_path_factory.mktemp("shim") / f"host_shim_{request.param}.so")
+    flags = ["-DMP_BLAKE2S_FORCE_SCALAR"] if request.param == "scalar_blake2s" else []
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", *flags, "-o", out,
                            os.path.join(ROOT, "tests", "host", "host_shim.cpp")])
     return ctypes.CDLL(out)
 
