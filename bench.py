@@ -226,9 +226,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the single JSON line: NCCL_DEBUG=VERSION/INFO prints a banner on stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("MP_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the single JSON line: whatever NCCL_DEBUG level the box sets, its banner /
+        # log goes to stderr instead of stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)
     lib = pkg.lib

@@ -1148,7 +1148,18 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, m, st));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(proof_out + L.cA, d_canon, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(S->ev, st));
+  // Every shuffled-deck point is multiplied by m + 1 scalar rows in the diagonal MSMs, so
+  // pre-shifting it once (table[w] = 2^(c w) * point) pays: all windows of a job then share ONE
+  // bucket set -- one bucket reduction per job instead of W, no fold doublings, and a wider
+  // window (fewer entries).  The table depends on no challenge: it is queued behind c_A and
+  // runs on the GPU while the host hashes the statement.
+  const int c_diag = msm_pick_table_window(N / 2 + 1);
+  affine* d_ct_tab = (affine*)ctx->scratch(sCtTable, (size_t)msm_num_windows(c_diag) * T2 * 2 * sizeof(affine));
+  NEED(d_ct_tab);
+  CK(msm_build_table(ctx->ws, d_ct_mont, (uint32_t)(T2 * 2), 0, (uint32_t)(N * 2), c_diag, d_ct_tab, st));
+  ctx->launches += 2;
+  CK(cudaEventSynchronize(S->ev));  // c_A is on the host; the table build continues
   Transcript fs;
   absorb_statement(fs, S, pk, deck, deck2, N, proof_out + L.cA);
   const fr x = fs.challenge();
@@ -1223,18 +1234,8 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     int i0 = std::max(1, m - k), i1 = std::min(m, 2 * m - k);
     diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
   }
-  // Every shuffled-deck point is used by m + 1 scalar rows, so pre-shifting it once
-  // (table[w] = 2^(c w) * point) pays: all windows of a job then share ONE bucket set -- one
-  // bucket reduction per job instead of W, no fold doublings, and a wider window (fewer entries).
-  {
-    const int c_diag = msm_pick_table_window(N / 2 + 1);
-    const int W_diag = msm_num_windows(c_diag);
-    affine* d_ct_tab = (affine*)ctx->scratch(sCtTable, (size_t)W_diag * T2 * 2 * sizeof(affine));
-    NEED(d_ct_tab);
-    CK(msm_build_table(ctx->ws, d_ct_mont, (uint32_t)(T2 * 2), 0, (uint32_t)(N * 2), c_diag, d_ct_tab, st));
-    CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_tab, 2, diag.data(), 2 * m, c_diag, d_ct_out, st, 0, -1, (uint32_t)T2));
-    ctx->launches += 2 + msm_last_launches(ctx->ws);
-  }
+  CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_tab, 2, diag.data(), 2 * m, c_diag, d_ct_out, st, 0, -1, (uint32_t)T2));
+  ctx->launches += msm_last_launches(ctx->ws);
 
   // wait for col / rho* only (the event precedes the diagonal MSMs, which keep the GPU busy
   // while the host prepares the next batch)
