@@ -432,55 +432,108 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__
 // Thread g handles component (g % ncomp) of chunk t = g / ncomp: sorted entries
 // [t*kChunk, min((t+1)*kChunk, E)).  Its first bucket run goes to part[g]; every later run
 // (which starts inside the chunk) goes to bucket_sums[bucket * ncomp + comp].
+// Every warp owns one tile of 32 / NCOMP consecutive chunks.  The tile's slice of the sorted index
+// list is one contiguous run, so the warp stages it into shared memory with a single TMA bulk copy
+// (cp.async.bulk, completion signalled on the warp's mbarrier) instead of per-thread strided
+// loads; the 64-byte points themselves are a data-dependent gather and are fetched with 128-bit
+// loads, software-prefetched one entry ahead.  The grid is NOT persistent on purpose: with
+// identical code a chip-sized persistent grid (static tile -> block assignment) measured 8.08 G
+// additions/s against 8.54 G/s for one tile per warp under the hardware block scheduler.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 template <int NCOMP, int MINBLOCKS>
 __global__ void __launch_bounds__(kAccThreads, MINBLOCKS)
     k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                  uint64_t nbuckets, const affine* __restrict__ points, xyzz* __restrict__ bucket_sums,
                  xyzz* __restrict__ part, uint32_t* __restrict__ chunk_bucket, uint32_t kChunk) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t t = g / NCOMP;
-  const uint32_t comp = (uint32_t)(g % NCOMP);
+  extern __shared__ __align__(128) uint32_t s_idx[];  // [warp][tile] sorted indices
+  constexpr uint32_t kWarps = kAccThreads / 32;
+  __shared__ __align__(8) uint64_t s_bar[kWarps];
+  constexpr uint32_t kChunksPerTile = 32 / NCOMP;
+  const uint32_t tile_entries = kChunksPerTile * kChunk, tile_bytes = tile_entries * 4u;
   const uint64_t E = offsets[nbuckets];
-  uint64_t pos = t * kChunk;
-  if (pos >= E) return;
-  const uint64_t end = min(pos + (uint64_t)kChunk, E);
-  // bucket containing entry `pos`: largest b with offsets[b] <= pos
-  uint64_t lo = 0, hi = nbuckets;  // invariant: offsets[lo] <= pos < offsets[hi]
-  while (hi - lo > 1) {
-    uint64_t mid = (lo + hi) >> 1;
-    if (offsets[mid] <= pos) lo = mid; else hi = mid;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t tile = (uint64_t)blockIdx.x * kWarps + warp;
+  if (tile * tile_entries >= E) return;  // whole warp: nothing sorted into this tile
+  const uint32_t bar = smem_u32(&s_bar[warp]);
+  uint32_t* const my_tile = s_idx + (size_t)warp * tile_entries;
+  if (lane == 0) {
+    // the elected lane arms the mbarrier with the byte count and issues the bulk copy
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(my_tile)),
+                 "l"(sorted + tile * tile_entries), "r"(tile_bytes), "r"(bar)
+                 : "memory");
   }
-  uint64_t b = lo;
-  if (comp == 0) chunk_bucket[t] = (uint32_t)b;
-  uint64_t next = offsets[b + 1];
-  bool first = true;
-  xyzz acc = xyzz_identity();
-  uint32_t val = sorted[pos];
-  affine pt = affine_load(points + (uint64_t)(val & 0x7fffffffu) * NCOMP + comp);
-  while (true) {
-    // prefetch the next entry's point while this one is being added
-    uint32_t nval = val;
-    affine npt = pt;
-    if (pos + 1 < end) {
-      nval = sorted[pos + 1];
-      npt = affine_load(points + (uint64_t)(nval & 0x7fffffffu) * NCOMP + comp);
+  __syncwarp();
+  const uint32_t lc = lane / NCOMP;
+  const uint32_t comp = lane % NCOMP;
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
     }
-    if (pos == next) {  // entering a new bucket: flush the finished run
+  }
+  {
+    const uint64_t t = tile * kChunksPerTile + lc;
+    const uint64_t g = t * NCOMP + comp;
+    uint64_t pos = t * kChunk;
+    if (pos < E) {
+      const uint32_t* my = my_tile + lc * kChunk;
+      const uint64_t first_pos = pos;
+      const uint64_t end = min(pos + (uint64_t)kChunk, E);
+      // bucket containing entry `pos`: largest b with offsets[b] <= pos
+      uint64_t lo = 0, hi = nbuckets;  // invariant: offsets[lo] <= pos < offsets[hi]
+      while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= pos) lo = mid; else hi = mid;
+      }
+      uint64_t b = lo;
+      if (comp == 0) chunk_bucket[t] = (uint32_t)b;
+      uint64_t next = offsets[b + 1];
+      bool first = true;
+      xyzz acc = xyzz_identity();
+      // indices come out of shared memory 4 at a time: every lane's chunk starts at the same
+      // bank, so 128-bit reads cut the (inevitable, the tile is copied linearly) bank conflicts 4x
+      const uint4* my4 = reinterpret_cast<const uint4*>(my);
+      uint4 cur4 = my4[0];
+      uint32_t val = cur4.x;
+      affine pt = affine_load(points + (uint64_t)(val & 0x7fffffffu) * NCOMP + comp);
+      while (true) {
+        // prefetch the next entry's point while this one is being added
+        uint32_t nval = val;
+        affine npt = pt;
+        if (pos + 1 < end) {
+          const uint32_t j = (uint32_t)(pos + 1 - first_pos);
+          if ((j & 3u) == 0) cur4 = my4[j >> 2];
+          nval = (j & 3u) == 0 ? cur4.x : ((j & 3u) == 1 ? cur4.y : ((j & 3u) == 2 ? cur4.z : cur4.w));
+          npt = affine_load(points + (uint64_t)(nval & 0x7fffffffu) * NCOMP + comp);
+        }
+        if (pos == next) {  // entering a new bucket: flush the finished run
+          if (first) xyzz_store(part + g, acc);
+          else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
+          first = false;
+          acc = xyzz_identity();
+          do { b++; next = offsets[b + 1]; } while (next <= pos);
+        }
+        if (val >> 31) pt = affine_neg(pt);
+        xyzz_madd(acc, pt);
+        pos++;
+        if (pos >= end) break;
+        val = nval;
+        pt = npt;
+      }
       if (first) xyzz_store(part + g, acc);
       else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
-      first = false;
-      acc = xyzz_identity();
-      do { b++; next = offsets[b + 1]; } while (next <= pos);
     }
-    if (val >> 31) pt = affine_neg(pt);
-    xyzz_madd(acc, pt);
-    pos++;
-    if (pos >= end) break;
-    val = nval;
-    pt = npt;
   }
-  if (first) xyzz_store(part + g, acc);
-  else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
 }
 
 // Stitch: thread per (chunk, comp).  A bucket whose entries straddle chunk boundaries has its sum
@@ -692,7 +745,8 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   if (max_entries >= (1ull << 32) || nbuckets >= (1ull << 32)) return cudaErrorInvalidValue;
   // chunk length: longer chunks mean fewer partial sums to stitch; keep >= ~600k threads in flight
   uint32_t kChunk = kChunkMin;
-  while (kChunk < kChunkMax && max_entries * ncomp / (2 * kChunk) >= 600000) kChunk *= 2;
+  const uint32_t chunk_cap = ncomp == 1 ? kChunkMax / 2 : kChunkMax;  // a warp's staged tile stays <= 8 KB of smem
+  while (kChunk < chunk_cap && max_entries * ncomp / (2 * kChunk) >= 600000) kChunk *= 2;
   const uint64_t max_chunks = (max_entries + kChunk - 1) / kChunk;
   const uint64_t ntiles = (nbuckets + 1 + kScanTile - 1) / kScanTile;
 
@@ -704,7 +758,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   MP_CK(ws->get(1, nbuckets + 1, &counts));
   MP_CK(ws->get(2, nbuckets + 1, &offsets));
   MP_CK(ws->get(3, nbuckets + 1, &cursor));
-  MP_CK(ws->get(4, max_entries, &sorted));
+  MP_CK(ws->get(4, max_entries + (size_t)kAccThreads * kChunkMax, &sorted));  // padded: tiles are copied whole
   MP_CK(ws->get(5, ntiles + 1, &tile_sums));
   MP_CK(ws->get(6, (size_t)njobs, &d_jobs));
   MP_CK(ws->get(7, nbuckets * ncomp, &bucket_sums));
@@ -752,8 +806,9 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
     // occupancy experiment knob: resident blocks per SM the kernel is compiled for (register cap)
     static const int acc_mb = [] { const char* e = getenv("MP_ACC_MINBLOCKS"); return e ? atoi(e) : 4; }();
+    const size_t smem = (size_t)(kAccThreads / ncomp) * kChunk * sizeof(uint32_t);  // one staged tile per warp
 #define MP_LAUNCH_ACC(NC, MB) \
-  k_accumulate<NC, MB><<<blocks, kAccThreads, 0, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk)
+  k_accumulate<NC, MB><<<blocks, kAccThreads, smem, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk)
     if (ncomp == 1) {
       if (acc_mb >= 6) MP_LAUNCH_ACC(1, 6); else if (acc_mb == 5) MP_LAUNCH_ACC(1, 5); else MP_LAUNCH_ACC(1, 4);
     } else {
