@@ -1234,8 +1234,20 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     int i0 = std::max(1, m - k), i1 = std::min(m, 2 * m - k);
     diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
   }
-  CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_tab, 2, diag.data(), 2 * m, c_diag, d_ct_out, st, 0, -1, (uint32_t)T2));
-  ctx->launches += msm_last_launches(ctx->ws);
+  {
+    // one launch sequence normally; very large decks are split so that a call stays below the
+    // 2^32-entry limit of the sort (entries = terms * windows)
+    const uint64_t max_terms = ((1ull << 31) / (uint64_t)msm_num_windows(c_diag));
+    for (int k0 = 0; k0 < 2 * m;) {
+      int k1 = k0;
+      uint64_t terms = 0;
+      while (k1 < 2 * m && (k1 == k0 || terms + diag[k1].len <= max_terms)) terms += diag[k1++].len;
+      CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_tab, 2, diag.data() + k0, k1 - k0, c_diag, d_ct_out + 2 * (size_t)k0, st, 0, -1,
+                 (uint32_t)T2));
+      ctx->launches += msm_last_launches(ctx->ws);
+      k0 = k1;
+    }
+  }
 
   // wait for col / rho* only (the event precedes the diagonal MSMs, which keep the GPU busy
   // while the host prepares the next batch)

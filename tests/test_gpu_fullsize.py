@@ -107,3 +107,23 @@ def test_usage_errors(ctx, pkg):
         ctx.commit_batch(rand_scalars(rng, 5), rand_scalars(rng, 1), 5)
     assert ctx.commit_batch(b"", b"", 3) == b""                              # empty batch
     assert ctx.remask(pts[384:448], b"", [], b"") == b""                     # empty deck
+
+
+def test_shuffle_2p18_round_trip(ctx):
+    """Beyond the BASELINE sizes: 2^18 cards, (m, n) = (256, 1024) -- 67 M diagonal terms, several
+    GB of sort and bucket space -- still proves, verifies and rejects a tampered deck."""
+    m, n = 256, 1024
+    Nc = m * n
+    rng = np.random.default_rng(6)
+    npts = (n + 3) + 2 * Nc
+    pts = ctx.dbg_scalar_mul(G64 * npts, rand_scalars(rng, npts))
+    P = lambda i: pts[64 * i:64 * (i + 1)]
+    ck_g, ck_h, ghat, pk, deck = pts[:64 * n], P(n), P(n + 1), P(n + 2), pts[64 * (n + 3):]
+    perm = [int(v) for v in rng.permutation(Nc)]
+    rho, rand = rand_scalars(rng, Nc), rand_scalars(rng, 11 * m + 5 * n)
+    ctx.set_params(m, n, G64, ck_g, ck_h, ghat)
+    deck2, proof = ctx.shuffle_and_remask(pk, deck, perm, rho, rand)
+    assert ctx.verify_shuffle(pk, deck, deck2, proof) == 0
+    sw = bytearray(deck2)
+    sw[0:128], sw[128:256] = deck2[128:256], deck2[0:128]
+    assert ctx.verify_shuffle(pk, deck, bytes(sw), proof) != 0
