@@ -23,12 +23,10 @@
 #include <stdint.h>
 
 #include "ec.cuh"
+#include "msm_job.h"
 
 namespace mp {
 
-struct MsmJob {
-  uint32_t scalar_off, point_off, len;
-};
 
 struct MsmWorkspace;  // opaque, owns device scratch that grows on demand
 

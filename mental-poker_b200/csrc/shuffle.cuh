@@ -17,6 +17,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "shuffle_host.hpp"  // shuffle_proof_len / shuffle_randomness_len and the host-only verifier pieces
+
 struct mp_ctx;
 // `*_src` arguments: where the device copy of a deck is taken from -- the host buffer itself
 // (default) or a device pointer when the deck is already resident in HBM.  The host copy is
@@ -31,8 +33,6 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
                            const uint8_t* ck_h, const uint8_t* ghat);
 int32_t shuffle_m(const mp_ctx* ctx);
 int32_t shuffle_n(const mp_ctx* ctx);
-uint64_t shuffle_proof_len(int32_t m, int32_t n);
-uint64_t shuffle_randomness_len(int32_t m, int32_t n);
 
 int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
                        const uint8_t* rho, uint64_t N, uint8_t* out_deck, const void* deck_src = nullptr,

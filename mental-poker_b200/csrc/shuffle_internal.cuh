@@ -1,0 +1,178 @@
+// Shared internals of the shuffle_*.cu translation units: device-side state, scratch slots,
+// error macros and the few helpers more than one of them needs.
+#pragma once
+#include <stdlib.h>
+
+#include <atomic>
+#include <thread>
+
+#include "ctx.cuh"
+#include "frvec.cuh"
+#include "msm.cuh"
+#include "shuffle.cuh"
+#include "shuffle_host.hpp"
+
+namespace mp {
+
+// ------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------
+struct ShuffleState : ShuffleParamsHost {
+  affine* d_ck = nullptr;     // device, Montgomery: h, g_1..g_n, then enc_g, ghat, pk (n + 4 points)
+  // fixed-base table of those n + 4 bases for the commitment jobs: tab_ck[w*(n+4) + i] = 2^(c*w) * base_i
+  affine* d_tab_ck = nullptr;
+  int tab_c = 0;
+  uint8_t ck_pk[64];          // public key currently in slot n + 3 of d_ck / d_tab_ck
+  bool ck_pk_valid = false;
+  cudaEvent_t ev = nullptr;   // marks small device->host copies the host waits for mid-stream
+  // fixed-base tables for remasking: tab[base][j][d-1] = d * 2^(8j) * base, base 0 = g, 1 = pk
+  affine* d_tab = nullptr;
+  uint8_t tab_pk[64];
+  bool tab_pk_valid = false;
+  // worker contexts of mp_shuffle_prove_batch (own stream / workspace each; same parameters)
+  std::vector<mp_ctx*> workers;
+  uint64_t params_gen = 0;            // bumped by every set_params
+  std::vector<uint64_t> worker_gen;   // generation each worker was configured for
+  uint8_t* pinned = nullptr;  // small pinned staging for results
+  size_t pinned_cap = 0;
+  ~ShuffleState() {
+    if (d_ck) cudaFree(d_ck);
+    if (d_tab_ck) cudaFree(d_tab_ck);
+    if (pinned) cudaFreeHost(pinned);
+    if (ev) cudaEventDestroy(ev);
+    if (d_tab) cudaFree(d_tab);
+    for (mp_ctx* w : workers) mp_ctx_destroy(w);
+  }
+};
+
+enum Slot {  // ctx->scratch slots owned by this file
+  sSmallUp = mp_ctx::kSlotUser,
+  sG1Canon, sG1Mont, sG1Scal, sG1Out,
+  sCtCanon, sCtMont, sCtScal, sCtOut,
+  sResults, sPartials,
+  sFrA, sFrB, sFrD, sFrBv, sFrXpow, sFrAme, sFrTmp0, sFrTmp1, sFrTmp2, sFrPairs, sFrSmall,
+  sPerm, sRho, sCanonOut, sCtTable,
+};
+
+#define CK(x)                                                    \
+  do {                                                           \
+    cudaError_t _e = (x);                                        \
+    if (_e != cudaSuccess) return ctx->cuda_fail(_e, #x);        \
+  } while (0)
+#define NEED(ptr)                                                                  \
+  do {                                                                             \
+    if (!(ptr)) return ctx->fail(MP_ERR_CUDA, "device allocation failed (%s)", #ptr); \
+  } while (0)
+
+inline FrPow2Table h_pow2_table(const fr& x) {
+  FrPow2Table t;
+  t.p[0] = x;
+  for (int k = 1; k < 32; k++) t.p[k] = fr_sqr(t.p[k - 1]);
+  return t;
+}
+
+// packs small host arrays into one upload
+struct SmallUpload {
+  std::vector<uint8_t> bytes;
+  size_t add(const void* p, size_t len) {
+    size_t off = (bytes.size() + 31) & ~(size_t)31;
+    bytes.resize(off + len);
+    memcpy(bytes.data() + off, p, len);
+    return off;
+  }
+  size_t add_frs(const std::vector<fr>& v) { return add(v.data(), v.size() * sizeof(fr)); }
+};
+
+inline uint8_t* pinned(ShuffleState* S, size_t bytes) {
+  if (S->pinned_cap < bytes) {
+    if (S->pinned) cudaFreeHost(S->pinned);
+    S->pinned = nullptr;
+    S->pinned_cap = 0;
+    size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+    if (cudaMallocHost(&S->pinned, want) != cudaSuccess) return nullptr;
+    S->pinned_cap = want;
+  }
+  return S->pinned;
+}
+
+// Decks up to this many cards take the host-scalar lockstep prover / batched verifier (every
+// group operation still runs on the GPU); larger decks use the device scalar kernels.  The
+// environment override exists so the tests can drive both implementations at the same sizes.
+inline size_t small_deck_max() {
+  const char* e = getenv("MP_SMALL_DECK_MAX");
+  return e ? (size_t)strtoull(e, nullptr, 10) : 8192;
+}
+
+// Runs fn(worker, i) for i in [0, B) on P worker contexts (own stream / workspace / tables each),
+// one host thread per worker.  Returns the first error; ctx->launches = total kernel launches.
+template <typename F>
+int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn) {
+  ShuffleState* S = ctx->shuffle;
+  while ((int)S->workers.size() < P) {
+    mp_ctx* w = nullptr;
+    if (mp_ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");
+    S->workers.push_back(w);
+    S->worker_gen.push_back(0);
+  }
+  for (int t = 0; t < P; t++) {
+    if (S->worker_gen[t] == S->params_gen) continue;
+    int32_t st = shuffle_set_params(S->workers[t], S->m, S->n, S->enc_g, S->ck64.data() + 64, S->ck64.data(), S->ghat);
+    if (st != MP_OK) return ctx->fail(st, "worker set_params failed: %s", mp_last_error_string(S->workers[t]));
+    S->worker_gen[t] = S->params_gen;
+  }
+  std::atomic<uint64_t> next{0};
+  std::atomic<int32_t> first_err{MP_OK};
+  std::atomic<int> launches{0};
+  auto run = [&](int t) {
+    mp_ctx* w = S->workers[t];
+    cudaSetDevice(w->device);
+    for (uint64_t i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+      if (first_err.load() != MP_OK) break;
+      int32_t st = fn(w, i);
+      launches.fetch_add(w->launches);
+      if (st < 0) {
+        int32_t expected = MP_OK;
+        if (first_err.compare_exchange_strong(expected, st)) ctx->fail(st, "item %llu: %s", (unsigned long long)i, mp_last_error_string(w));
+        break;
+      }
+    }
+  };
+  if (P == 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < P; t++) pool.emplace_back(run, t);
+    for (auto& th : pool) th.join();
+  }
+  ctx->launches = launches.load();
+  return first_err.load();
+}
+
+
+template <typename F>
+void parallel_for(size_t count, int threads, F&& fn) {
+  if (threads <= 1 || count < 2) {
+    for (size_t i = 0; i < count; i++) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++)
+    pool.emplace_back([&] {
+      for (size_t i = next.fetch_add(1); i < count; i = next.fetch_add(1)) fn(i);
+    });
+  for (auto& th : pool) th.join();
+}
+
+// shuffle_setup.cu
+int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad);
+int32_t commit_rows_device(mp_ctx* ctx, const fr* d_rows, uint64_t stride, const fr* d_blinds, int count, int len,
+                           uint32_t* d_scal, xyzz* d_out);
+// out[k*(n+1)] = blinds[k], out[k*(n+1) + 1 + j] = rows[k*stride + j] (canonical; short rows zero padded)
+cudaError_t commit_scalars_launch(const fr* d_rows, uint64_t stride, const fr* d_blinds, int count, int n, int len,
+                                  uint32_t* d_out, cudaStream_t stream);
+// shuffle_prove_batch.cu
+int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms, const uint8_t* rhos,
+                        const uint8_t* rands, size_t Bs, uint8_t* out_decks, uint8_t* proofs, int threads);
+
+}  // namespace mp

@@ -83,3 +83,46 @@ void h_fs_points_challenge(const uint8_t* pts, uint64_t count, uint8_t* out) {
   fr c = fs.challenge(); uint32_t w[8]; fr_to_canonical(c, w); memcpy(out, w, 32);
 }
 }
+
+// ---- host-only verifier plan (csrc/shuffle_host.hpp): challenges, the eight commitment-space
+// jobs and the two ciphertext equations of one proof, returned as flat (point, scalar) lists
+#include "../../mental-poker_b200/csrc/shuffle_host.hpp"
+extern "C" {
+// g1_pts: T1*64, g1_scal: T1*32, job_lens: 8 ints; ct arrays as documented at build_ct_plan.
+// host_flags[5]: hadamard bytes, zero bytes, svp first, svp last (vs bstar), multi-exp bytes.
+int h_verify_plan(int m, int n, const uint8_t* enc_g, const uint8_t* ck_g, const uint8_t* ck_h, const uint8_t* ghat,
+                  const uint8_t* gsum, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint8_t* proof,
+                  uint8_t* g1_pts, uint8_t* g1_scal, int* job_lens, uint8_t* sx, uint8_t* s2, uint8_t* ss, uint8_t* small_pts,
+                  int* host_flags) {
+  ShuffleParamsHost S;
+  S.m = m; S.n = n;
+  S.ck64.resize((size_t)(n + 1) * 64);
+  memcpy(S.ck64.data(), ck_h, 64);
+  memcpy(S.ck64.data() + 64, ck_g, (size_t)n * 64);
+  memcpy(S.enc_g, enc_g, 64); memcpy(S.ghat, ghat, 64); memcpy(S.gsum, gsum, 64);
+  const Layout L(m, n);
+  const size_t N = (size_t)m * n;
+  const Challenges ch = derive_challenges(&S, pk, deck, deck2, N, proof, L);
+  TermList tl;
+  HostChecks hc;
+  append_g1_checks(tl, &S, proof, L, ch, &hc);
+  memcpy(g1_pts, tl.pts.data(), tl.pts.size());
+  memcpy(g1_scal, tl.scal.data(), tl.scal.size() * 4);
+  for (int j = 0; j < kG1Checks; j++) job_lens[j] = (int)tl.jobs[j].len;
+  fr bstar;
+  build_ct_plan(&S, pk, proof, L, ch, (uint32_t*)sx, (uint32_t*)s2, (uint32_t*)ss, small_pts, &bstar);
+  host_flags[0] = hc.hadamard_bytes_ok; host_flags[1] = hc.zero_bytes_ok; host_flags[2] = hc.svp_first_ok;
+  host_flags[3] = fr_eq(hc.svp_last, fr_mul(hc.xs, bstar)); host_flags[4] = hc.multiexp_bytes_ok;
+  return (int)tl.count();
+}
+int h_verdict(const int* g1_id, int ct_ok, const int* host_flags) {
+  HostChecks hc;
+  hc.hadamard_bytes_ok = host_flags[0]; hc.zero_bytes_ok = host_flags[1]; hc.svp_first_ok = host_flags[2];
+  hc.multiexp_bytes_ok = host_flags[4];
+  // svp_last check is passed pre-evaluated: encode it as (svp_last, xs, bstar) = (1, 1, 1) or (0, 1, 1)
+  hc.xs = fr_one(); hc.svp_last = host_flags[3] ? fr_mul(fr_one(), fr_one()) : fr_zero();
+  bool ids[kG1Checks];
+  for (int j = 0; j < kG1Checks; j++) ids[j] = g1_id[j] != 0;
+  return verdict(hc, fr_one(), ids, ct_ok != 0);
+}
+}

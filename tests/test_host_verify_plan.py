@@ -1,0 +1,95 @@
+"""CPU test of the HOST half of the GPU verifier (csrc/shuffle_host.hpp, compiled with g++): the
+transcript schedule, the rewriting of every verifier check into "sum scalar*point == O" jobs and
+the verdict order -- evaluated here with the Python oracle's group arithmetic instead of the GPU.
+For a valid proof every job must sum to the identity; for tampered proofs the verdict must be the
+oracle's."""
+import ctypes
+import json
+import os
+import subprocess
+
+import pytest
+
+from oracle.py import stark, bayer_groth as bg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json")))
+h = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "host_shim.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "host", "host_shim.cpp")])
+    return ctypes.CDLL(out)
+
+
+def pts(buf):
+    return [stark.point_from_bytes64(buf[64 * i:64 * i + 64]) for i in range(len(buf) // 64)]
+
+
+def scs(buf):
+    return [int.from_bytes(buf[32 * i:32 * i + 32], "little") for i in range(len(buf) // 32)]
+
+
+def run_plan(shim, fx, deck2=None, proof=None):
+    m, n = fx["m"], fx["n"]
+    N = m * n
+    ck_g = h(fx["ck_g"])
+    gsum = None
+    for p in pts(ck_g):
+        gsum = stark.add(gsum, p)
+    T1 = 8 * m + 5 * n + 19
+    g1_pts, g1_scal = ctypes.create_string_buffer(T1 * 64), ctypes.create_string_buffer(T1 * 32)
+    lens, flags = (ctypes.c_int * 8)(), (ctypes.c_int * 5)()
+    sx, s2 = ctypes.create_string_buffer(N * 32), ctypes.create_string_buffer(N * 32)
+    ss, small = ctypes.create_string_buffer((2 * m + 3) * 32), ctypes.create_string_buffer((2 * m + 3) * 128)
+    deck, deck2 = h(fx["deck"]), deck2 or h(fx["deck2"])
+    cnt = shim.h_verify_plan(m, n, h(fx["enc_g"]), ck_g, h(fx["ck_h"]), h(fx["ghat"]), stark.point_to_bytes64(gsum),
+                             h(fx["pk"]), deck, deck2, proof or h(fx["proof"]), g1_pts, g1_scal, lens, sx, s2, ss, small, flags)
+    assert cnt == T1 and sum(lens) == T1
+    # evaluate the eight G1 jobs with the oracle
+    P, K, ids, off = pts(g1_pts.raw), scs(g1_scal.raw), [], 0
+    for ln in lens:
+        ids.append(int(stark.msm(P[off:off + ln], K[off:off + ln]) is stark.INF))
+        off += ln
+    # and the two ciphertext equations, component-wise
+    D, D2, SM = pts(deck), pts(deck2), pts(small.raw)
+    kx, k2, ks = scs(sx.raw), scs(s2.raw), scs(ss.raw)
+    ct_ok = True
+    for comp in (0, 1):
+        e0 = stark.add(stark.msm(D[comp::2], kx), stark.mul(SM[comp], ks[0]))
+        e1 = stark.add(stark.msm(D2[comp::2], k2), stark.msm(SM[2 + comp::2], ks[1:]))
+        ct_ok = ct_ok and e0 is stark.INF and e1 is stark.INF
+    return shim.h_verdict((ctypes.c_int * 8)(*ids), int(ct_ok), flags), ids, ct_ok, list(flags)
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_valid_proof_all_jobs_are_identity(shim, idx):
+    status, ids, ct_ok, flags = run_plan(shim, GOLD["shuffle"][idx])
+    assert ids == [1] * 8 and ct_ok and flags == [1] * 5 and status == 0
+
+
+def test_verdicts_match_oracle_on_bad_inputs(shim):
+    fx = GOLD["shuffle"][1]
+    m, n = fx["m"], fx["n"]
+    pp = bg.Params(m, n, stark.point_from_bytes64(h(fx["enc_g"])), pts(h(fx["ck_g"])), stark.point_from_bytes64(h(fx["ck_h"])),
+                   stark.point_from_bytes64(h(fx["ghat"])))
+    pk = stark.point_from_bytes64(h(fx["pk"]))
+    deck = [tuple(pts(h(fx["deck"]))[2 * i:2 * i + 2]) for i in range(m * n)]
+    good2 = h(fx["deck2"])
+    # wrong shuffled deck (rotate the cards): reference negative case -> Hadamard
+    wrong = good2[128:] + good2[:128]
+    proof = h(fx["proof"])
+    cases = [(wrong, proof)]
+    for off in (len(proof) - 1 - 32 * 3, len(proof) - 32 * (n + 4) - 1):   # multi-exp r, multi-exp a_n
+        p2 = bytearray(proof)
+        p2[off] ^= 1
+        cases.append((good2, bytes(p2)))
+    for d2, pf in cases:
+        d2_pts = pts(d2)
+        want = bg.shuffle_verify(pp, pk, deck, [tuple(d2_pts[2 * i:2 * i + 2]) for i in range(m * n)],
+                                 bg.proof_from_bytes(pf, m, n))
+        got, *_ = run_plan(shim, fx, d2, pf)
+        assert got == want != 0
