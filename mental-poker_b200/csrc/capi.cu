@@ -200,7 +200,7 @@ extern "C" int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64
 }
 
 // ------------------------------------------------------------------------------------------
-// shuffle protocol entry points (bodies in shuffle.cu)
+// shuffle protocol entry points (bodies in shuffle_*.cu)
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t mp_ctx_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
                                      const uint8_t* ck_h, const uint8_t* ghat) {

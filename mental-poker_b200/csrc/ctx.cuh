@@ -15,7 +15,7 @@ struct mp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   mp::MsmWorkspace* ws = nullptr;
-  mp::ShuffleState* shuffle = nullptr;  // protocol parameters + staging (shuffle.cu)
+  mp::ShuffleState* shuffle = nullptr;  // protocol parameters + staging (shuffle_internal.cuh)
   std::string err = "";
   int launches = 0;
   uint64_t last_ec_adds = 0;
