@@ -1,0 +1,34 @@
+"""Host-side logic of bench.py that needs no GPU: work model, CPU-sample shapes, the reference arm."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_work_model_matches_survey_appendix_c():
+    w = bench.work_terms(128, 512)
+    # diagonals 16 908 288, K1 262 144 (verify)
+    assert 2 * 128 * 129 * 512 == 16908288 and w["prove_naive"] >= 16908288 + 2 * 65536
+    assert w["verify_naive"] >= 4 * 65536 and w["verify_naive"] < 4 * 65536 + 4000
+
+
+def test_sample_shapes_keep_aspect_and_budget():
+    assert bench.sample_shape(128, 512, 1) == (16, 64)
+    assert bench.sample_shape(128, 512, 16) == (32, 128)
+    assert bench.sample_shape(128, 512, 96) == (64, 256)
+    assert bench.sample_shape(4, 13, 1) == (4, 13)
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--m", "4", "--n", "13"], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "proofs/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["metric"] == bench.METRIC and d["higher_is_better"] is True
