@@ -278,7 +278,8 @@ typedef struct { const fe* s; size_t i; } rand_t; /* flat prover randomness, App
 static fe rnd1(rand_t* r) { return r->s[r->i++]; }
 static void rndv(rand_t* r, fe* out, int k) { for (int i = 0; i < k; i++) out[i] = rnd1(r); }
 
-#define NEW(T, count) ((T*)calloc((size_t)(count) ? (size_t)(count) : 1, sizeof(T)))
+static inline void* new_array(size_t count, size_t size) { return calloc(count ? count : 1, size); }
+#define NEW(T, count) ((T*)new_array((size_t)(count), sizeof(T)))
 
 enum { OK = 0, ERR_HADAMARD = 1, ERR_ZERO = 2, ERR_SVP = 3, ERR_MULTIEXP = 4 };
 
