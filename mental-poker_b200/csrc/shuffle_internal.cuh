@@ -25,6 +25,11 @@ struct ShuffleState : ShuffleParamsHost {
   uint8_t ck_pk[64];          // public key currently in slot n + 3 of d_ck / d_tab_ck
   bool ck_pk_valid = false;
   cudaEvent_t ev = nullptr;   // marks small device->host copies the host waits for mid-stream
+  // second stream + MSM workspace: independent launch sequences (the verifier's commitment-space
+  // jobs next to its ciphertext MSMs) run concurrently instead of paying their fold latencies in turn
+  cudaStream_t aux = nullptr;
+  MsmWorkspace* aux_ws = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // fixed-base tables for remasking: tab[base][j][d-1] = d * 2^(8j) * base, base 0 = g, 1 = pk
   affine* d_tab = nullptr;
   uint8_t tab_pk[64];
@@ -40,6 +45,10 @@ struct ShuffleState : ShuffleParamsHost {
     if (d_tab_ck) cudaFree(d_tab_ck);
     if (pinned) cudaFreeHost(pinned);
     if (ev) cudaEventDestroy(ev);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (aux) cudaStreamDestroy(aux);
+    if (aux_ws) msm_workspace_destroy(aux_ws);
     if (d_tab) cudaFree(d_tab);
     for (mp_ctx* w : workers) mp_ctx_destroy(w);
   }
@@ -165,7 +174,9 @@ void parallel_for(size_t count, int threads, F&& fn) {
 }
 
 // shuffle_setup.cu
-int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad);
+// stream / ws default to the context's; pass the auxiliary pair to overlap with other work
+int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad, cudaStream_t stream = nullptr,
+                    MsmWorkspace* ws = nullptr);
 int32_t commit_rows_device(mp_ctx* ctx, const fr* d_rows, uint64_t stride, const fr* d_blinds, int count, int len,
                            uint32_t* d_scal, xyzz* d_out);
 // out[k*(n+1)] = blinds[k], out[k*(n+1) + 1 + j] = rows[k*stride + j] (canonical; short rows zero padded)

@@ -186,6 +186,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     int i0 = std::max(1, m - k), i1 = std::min(m, 2 * m - k);
     diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
   }
+  CK(cudaEventRecord(S->ev_fork, st));  // everything the commitment batch reads is queued before this point
   {
     // one launch sequence normally; very large decks are split so that a call stays below the
     // 2^32-entry limit of the sort (entries = terms * windows)
@@ -208,7 +209,10 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   const fr rho_star = fr_neg(h_col[n]);
   me_tau[m] = rho_star;
 
-  // C.4  SVP first message on the host side of the scalars (O(n)), committed on the device
+  // C.4  SVP first message on the host side of the scalars (O(n)), committed on the device.  The whole
+  //      commitment batch (C.4 + C.5) is issued on the auxiliary stream: it overlaps the diagonal MSMs.
+  cudaStream_t sa = S->aux;
+  CK(cudaStreamWaitEvent(sa, S->ev_fork, 0));
   std::vector<fr> bk((size_t)n);
   bk[0] = col[0];
   for (int i = 1; i < n; i++) bk[i] = fr_mul(bk[i - 1], col[i]);
@@ -219,7 +223,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
       rows3[(size_t)n + i] = fr_neg(fr_mul(sv_delta[i], sv_d[i + 1]));
       rows3[(size_t)2 * n + i] = fr_sub(fr_sub(sv_delta[i + 1], fr_mul(col[i + 1], sv_delta[i])), fr_mul(bk[i], sv_d[i + 1]));
     }
-    CK(cudaMemcpyAsync(d_rows, rows3.data(), sizeof(fr) * 3 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_rows, rows3.data(), sizeof(fr) * 3 * n, cudaMemcpyHostToDevice, sa));
   }
   // C.5  ONE G1 batch (one Pippenger launch sequence = one fold latency):
   //      rows      Hadamard c_B[0..m) = com(Bv[i]; sv[i]) (c_B[0] = c_D[0], c_B[m-1] = c_b), SVP c_d,
@@ -232,11 +236,11 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     std::vector<fr> blinds((size_t)R);
     for (int i = 0; i < m; i++) blinds[i] = sv[i];
     blinds[m] = sv_rd; blinds[m + 1] = sv_s1; blinds[m + 2] = sv_sx; blinds[m + 3] = me_r0;
-    CK(cudaMemcpyAsync(d_blind, blinds.data(), sizeof(fr) * R, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_blind, blinds.data(), sizeof(fr) * R, cudaMemcpyHostToDevice, sa));
     const uint64_t tot = (uint64_t)(n + 1);
-    CK(commit_scalars_launch(d_Bv, n, d_blind, m, n, n, d_g1_scal, st));
-    CK(commit_scalars_launch(d_rows, n, d_blind + m, 3, n, n, d_g1_scal + tot * m * 8, st));
-    CK(commit_scalars_launch(d_Ame, n, d_blind + m + 3, 1, n, n, d_g1_scal + tot * (m + 3) * 8, st));
+    CK(commit_scalars_launch(d_Bv, n, d_blind, m, n, n, d_g1_scal, sa));
+    CK(commit_scalars_launch(d_rows, n, d_blind + m, 3, n, n, d_g1_scal + tot * m * 8, sa));
+    CK(commit_scalars_launch(d_Ame, n, d_blind + m + 3, 1, n, n, d_g1_scal + tot * (m + 3) * 8, sa));
     ctx->launches += 3;
     const size_t nsmall = 10 * (size_t)m;  // 2m pairs + 2m singles + 2m pairs
     std::vector<uint32_t> sc(nsmall * 8);
@@ -248,15 +252,17 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
       fr_to_canonical(me_tau[k], &sc[(size_t)(6 * m + 2 * k + 1) * 8]);
     }
     const uint32_t base = (uint32_t)(tot * R);
-    CK(cudaMemcpyAsync(d_g1_scal + (size_t)base * 8, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_g1_scal + (size_t)base * 8, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, sa));
     std::vector<MsmJob> jobs;
     for (int k = 0; k < R; k++) jobs.push_back(MsmJob{(uint32_t)(k * tot), 0, (uint32_t)tot});
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 2 * k, 0, 2});                               // (h, g_1)
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 4 * m + k, (uint32_t)(n + 1), 1});           // enc_g
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 6 * m + 2 * k, (uint32_t)(n + 2), 2});       // (ghat, pk)
-    CK(msm_run(ctx->ws, d_g1_scal, base + nsmall, S->d_tab_ck, 1, jobs.data(), (int)jobs.size(), S->tab_c, d_g1_out, st, 0, -1,
+    CK(msm_run(S->aux_ws, d_g1_scal, base + nsmall, S->d_tab_ck, 1, jobs.data(), (int)jobs.size(), S->tab_c, d_g1_out, sa, 0, -1,
                (uint32_t)(n + 4)));
-    ctx->launches += msm_last_launches(ctx->ws);
+    ctx->launches += msm_last_launches(S->aux_ws);
+    CK(cudaEventRecord(S->ev_join, sa));
+    CK(cudaStreamWaitEvent(st, S->ev_join, 0));  // join: E_k needs both the diagonals and the Enc parts
     k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_g1_out + R + 2 * m, d_g1_out + R + 4 * m, 2 * m);
     CK(cudaGetLastError());
     CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canon, 4 * (size_t)m, st));

@@ -122,7 +122,9 @@ static cudaError_t build_table(ShuffleState* S, int which, const uint8_t* d_base
 // ------------------------------------------------------------------------------------------
 // set-up
 // ------------------------------------------------------------------------------------------
-int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad) {
+int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad, cudaStream_t stream, MsmWorkspace* ws) {
+  if (!stream) stream = ctx->stream;
+  if (!ws) ws = ctx->ws;
   uint32_t T = tl.count();
   int J = (int)tl.jobs.size();
   uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)T * 64 + 64);
@@ -130,13 +132,13 @@ int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_ba
   uint32_t* d_scal = (uint32_t*)ctx->scratch(sG1Scal, (size_t)T * 32 + 64);
   xyzz* d_out = (xyzz*)ctx->scratch(sG1Out, (size_t)J * sizeof(xyzz) + 64);
   NEED(d_canon); NEED(d_mont); NEED(d_scal); NEED(d_out);
-  CK(cudaMemcpyAsync(d_canon, tl.pts.data(), (size_t)T * 64, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_scal, tl.scal.data(), (size_t)T * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(points_to_mont((const uint32_t*)d_canon, d_mont, T, d_bad, ctx->stream));
+  CK(cudaMemcpyAsync(d_canon, tl.pts.data(), (size_t)T * 64, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d_scal, tl.scal.data(), (size_t)T * 32, cudaMemcpyHostToDevice, stream));
+  CK(points_to_mont((const uint32_t*)d_canon, d_mont, T, d_bad, stream));
   ctx->launches += 1;
   int c = msm_pick_window(J ? T / J : 1);
-  CK(msm_run(ctx->ws, d_scal, T, d_mont, 1, tl.jobs.data(), J, c, d_out, ctx->stream));
-  ctx->launches += msm_last_launches(ctx->ws);
+  CK(msm_run(ws, d_scal, T, d_mont, 1, tl.jobs.data(), J, c, d_out, stream));
+  ctx->launches += msm_last_launches(ws);
   *d_out_ret = d_out;
   return MP_OK;
 }
@@ -161,6 +163,12 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   S->d_ck = nullptr;
   CK(cudaMalloc(&S->d_ck, sizeof(affine) * (size_t)(n + 4)));
   if (!S->ev) CK(cudaEventCreateWithFlags(&S->ev, cudaEventDisableTiming));
+  if (!S->aux) {
+    CK(cudaStreamCreateWithFlags(&S->aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
+    S->aux_ws = msm_workspace_create();
+  }
   // validate every parameter point and compute gsum = sum g_j with one MSM of unit scalars
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_bad);

@@ -30,6 +30,7 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  CK(cudaEventRecord(S->ev_fork, ctx->stream));  // the auxiliary stream may touch d_bad after this point
   CK(cudaMemcpyAsync(d_ct_canon, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(d_ct_canon + N * 128, proof + L.meE + 128 * (size_t)m, 128, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_ct_canon + (N + 1) * 128, deck2_src, N * 128, cudaMemcpyDefault, ctx->stream));
@@ -49,7 +50,19 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   const Challenges ch = derive_challenges(S, pk, deck, deck2, N, proof, L);
   const fr &x = ch.x, &y = ch.y, &z = ch.z, &xm = ch.xm;
 
-  // ---- 3. O(N) scalar vectors on the device
+  // ---- 3. the commitment-space checks as small G1 jobs (host builds O(m + n) scalars), issued on
+  //         the auxiliary stream so that they overlap the ciphertext MSMs below
+  TermList tl;
+  HostChecks hc;
+  append_g1_checks(tl, S, proof, L, ch, &hc);
+  const int J = (int)tl.jobs.size();  // 8
+  xyzz* d_g1_out = nullptr;
+  CK(cudaStreamWaitEvent(S->aux, S->ev_fork, 0));
+  int32_t st = run_g1_jobs(ctx, tl, &d_g1_out, d_bad, S->aux, S->aux_ws);
+  if (st != MP_OK) return st;
+  CK(cudaEventRecord(S->ev_join, S->aux));
+
+  // ---- 4. O(N) scalar vectors on the device
   const std::vector<fr> me_a = h_frs(proof + L.mea, n);
   const fr me_b = h_fr(proof + L.meb), me_tau = h_fr(proof + L.metau);
   const std::vector<fr> xmp = h_powers(xm, 2 * m);
@@ -77,21 +90,14 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(fr_outer_canonical((const fr*)(d_small + o_coef), (const fr*)(d_small + o_mea), m, n, d_ct_scal + (N + 1) * 8, ctx->stream));
   ctx->launches += 3;
 
-  // ---- 4. the two ciphertext checks (K1): 4 N-term G1 MSMs in one batched launch sequence
+  // ---- 5. the two ciphertext checks (K1): 4 N-term G1 MSMs in one batched launch sequence
   //   job 0:  sum x^i C_i - E_m                                        == O   (Chat == E_m)
   //   job 1:  sum x^k E_k - Enc(b*ghat; tau) - sum (x^{m-i} a_j) C'_ij  == O
   MsmJob ct_jobs[2] = {{0, 0, (uint32_t)(N + 1)}, {(uint32_t)(N + 1), (uint32_t)(N + 1), (uint32_t)(N + 2 * m + 2)}};
   CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N), d_ct_out, ctx->stream));
   ctx->launches += msm_last_launches(ctx->ws);
 
-  // ---- 5. the commitment-space checks as small G1 jobs (host builds O(m + n) scalars)
-  TermList tl;
-  HostChecks hc;
-  append_g1_checks(tl, S, proof, L, ch, &hc);
-  const int J = (int)tl.jobs.size();  // 8
-  xyzz* d_g1_out = nullptr;
-  int32_t st = run_g1_jobs(ctx, tl, &d_g1_out, d_bad);
-  if (st != MP_OK) return st;
+  CK(cudaStreamWaitEvent(ctx->stream, S->ev_join, 0));  // join: G1 results are ready for the copies below
 
   // ---- 6. collect: [bstar | G1 results | CT results | bad flag]
   const size_t res_bytes = sizeof(fr) + (size_t)(J + 4) * sizeof(xyzz) + 16;
