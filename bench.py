@@ -295,7 +295,7 @@ def main():
     ctx.profile_collect()
     with ClockSampler(local_rank) as clocks:
         ms_res, launches = timed_steps(True, args.steps)
-    acc_ms, acc_adds, acc_launches = ctx.profile_collect()
+    acc_ms, acc_adds, acc_launches = ctx.profile_collect_dominant()  # the prover's diagonal-MSM launches
     ctx.profile_enable(False)
     barrier()
     # ---- `e2e`: host buffers through the public C ABI
@@ -337,8 +337,16 @@ def main():
         peak, peak_src = load_peaks()
         bytes_per_add = 68.0  # 64 B affine point gather + 4 B sorted index
         achieved = bytes_per_add * acc_adds / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else None
-        roofline = dict(bound="hbm", kernel="k_accumulate (bucket accumulation, XYZZ mixed adds)", achieved=achieved,
-                        peak=peak, unit="GB/s", frac=(achieved / peak if achieved else None), traffic=None,
+        traffic, traffic_src = None, None
+        try:  # dram bytes per launch of the same kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            if (m, n) == (tj["m"], tj["n"]):
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
+        roofline = dict(bound="hbm", kernel="k_accumulate<2> (bucket accumulation of the prover's diagonal ciphertext MSMs, XYZZ mixed adds)",
+                        achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak if achieved else None), traffic=traffic,
+                        traffic_source=traffic_src, algorithmic_bytes_per_launch=(bytes_per_add * acc_adds / acc_launches if acc_launches else None),
                         peak_source=peak_src, launches=acc_launches,
                         avg_launch_ms=(acc_ms / acc_launches if acc_launches else None),
                         share_of_step=(acc_ms / ms_res if ms_res else None),

@@ -186,6 +186,9 @@ int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t*
  * additions (mixed XYZZ adds) those launches executed, and the launch count, then resets. */
 int32_t mp_profile_enable(mp_ctx* ctx, int32_t on);
 int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64_t* bucket_adds, uint64_t* launches);
+/* Same, restricted to the dominant launches (those within a factor two of the largest by additions):
+ * what a per-kernel roofline should be quoted on when a step mixes one huge MSM with many tiny ones. */
+int32_t mp_profile_collect_dominant(mp_ctx* ctx, double* ms, uint64_t* bucket_adds, uint64_t* launches);
 
 /* ---- debug / parity hooks (exercise single device primitives; not used by the protocol) */
 int32_t mp_dbg_fq_mul(mp_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);

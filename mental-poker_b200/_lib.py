@@ -47,6 +47,7 @@ SIGNATURES = {
     "mp_shuffle_and_remask_resident": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp, _vp]),
     "mp_shuffle_prove_resident": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp, _vp]),
     "mp_profile_enable": (_i32, [_vp, _i32]),
+    "mp_profile_collect_dominant": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "mp_profile_collect": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "mp_dbg_fq_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
     "mp_dbg_point_add": (_i32, [_vp, _cp, _cp, _u64, _cp]),
@@ -214,6 +215,12 @@ class Context:
     # --- measurement
     def profile_enable(self, on=True):
         check(self.h, lib.mp_profile_enable(self.h, 1 if on else 0))
+
+    def profile_collect_dominant(self):
+        """-> (ms, bucket additions, launches) of the dominant accumulate launches since the last collect"""
+        ms, adds, n = ctypes.c_double(), _u64(), _u64()
+        check(self.h, lib.mp_profile_collect_dominant(self.h, ctypes.byref(ms), ctypes.byref(adds), ctypes.byref(n)))
+        return ms.value, adds.value, n.value
 
     def profile_collect(self):
         """-> (accumulate-kernel ms, bucket additions, launches) since the last collect"""

@@ -199,6 +199,15 @@ extern "C" int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64
   return MP_OK;
 }
 
+extern "C" int32_t mp_profile_collect_dominant(mp_ctx* ctx, double* ms, uint64_t* bucket_adds, uint64_t* launches) {
+  if (!ctx || !ms || !bucket_adds || !launches) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  double all_ms; uint64_t all_adds, all_launches;
+  cudaError_t e = msm_profile_collect(ctx->ws, &all_ms, &all_adds, &all_launches, ms, bucket_adds, launches);
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_profile_collect_dominant");
+  return MP_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // shuffle protocol entry points (bodies in shuffle_*.cu)
 // ------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "msm.cuh"
@@ -59,18 +60,30 @@ MsmWorkspace* msm_workspace_create() { return new MsmWorkspace(); }
 void msm_workspace_destroy(MsmWorkspace* ws) { delete ws; }
 int msm_last_launches(const MsmWorkspace* ws) { return ws->launches; }
 void msm_profile_enable(MsmWorkspace* ws, bool on) { ws->profile = on; }
-cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, uint64_t* launches) {
+cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, uint64_t* launches, double* big_ms,
+                                uint64_t* big_adds, uint64_t* big_launches) {
   *ms = 0; *adds = 0; *launches = 0;
   cudaError_t err = cudaSuccess;
+  std::vector<std::pair<float, uint64_t>> all;
   for (auto& t : ws->timed) {
     cudaError_t e = cudaEventSynchronize(t.e1);
     float f = 0;
     if (e == cudaSuccess) e = cudaEventElapsedTime(&f, t.e0, t.e1);
     if (e != cudaSuccess) err = e;
-    *ms += f; *adds += (uint64_t)(*t.entries) * t.ncomp; *launches += 1;
+    all.emplace_back(f, (uint64_t)(*t.entries) * t.ncomp);
+    *ms += f; *adds += all.back().second; *launches += 1;
     cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
   }
   ws->timed.clear();
+  // the dominant launches: those within a factor two of the largest (by additions)
+  uint64_t mx = 0;
+  for (auto& a : all) mx = std::max(mx, a.second);
+  double bm = 0; uint64_t ba = 0, bl = 0;
+  for (auto& a : all)
+    if (mx && a.second * 2 >= mx) { bm += a.first; ba += a.second; bl++; }
+  if (big_ms) *big_ms = bm;
+  if (big_adds) *big_adds = ba;
+  if (big_launches) *big_launches = bl;
   return err;
 }
 

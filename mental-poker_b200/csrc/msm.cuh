@@ -64,7 +64,9 @@ int msm_last_launches(const MsmWorkspace* ws);
 // collect() waits for the recorded events, returns the summed duration, the bucket additions
 // those launches were scheduled with and the launch count, and clears the list.
 void msm_profile_enable(MsmWorkspace* ws, bool on);
-cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, uint64_t* launches);
+cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, uint64_t* launches, double* big_ms = nullptr,
+                                uint64_t* big_adds = nullptr, uint64_t* big_launches = nullptr);
+// (big_*: the same sums restricted to the dominant launches -- within a factor two of the largest)
 
 // canonical 64-byte points -> Montgomery affine (validating on-curve; bad points set *d_bad)
 cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,
