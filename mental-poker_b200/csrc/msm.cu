@@ -760,6 +760,9 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   uint32_t kChunk = kChunkMin;
   const uint32_t chunk_cap = ncomp == 1 ? kChunkMax / 2 : kChunkMax;  // a warp's staged tile stays <= 8 KB of smem
   while (kChunk < chunk_cap && max_entries * ncomp / (2 * kChunk) >= 600000) kChunk *= 2;
+  // small launches are latency-bound (a thread adds its chunk serially): shorter chunks put more
+  // threads to work as long as fewer than ~4 warps per SM would be busy otherwise
+  while (kChunk > 8 && max_entries * ncomp / kChunk < 20000) kChunk /= 2;
   const uint64_t max_chunks = (max_entries + kChunk - 1) / kChunk;
   const uint64_t ntiles = (nbuckets + 1 + kScanTile - 1) / kScanTile;
 
