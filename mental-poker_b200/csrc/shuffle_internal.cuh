@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "ctx.cuh"
+#include "diag.cuh"
 #include "frvec.cuh"
 #include "msm.cuh"
 #include "shuffle.cuh"
@@ -38,6 +39,7 @@ struct ShuffleState : ShuffleParamsHost {
   std::vector<mp_ctx*> workers;
   uint64_t params_gen = 0;            // bumped by every set_params
   std::vector<uint64_t> worker_gen;   // generation each worker was configured for
+  DiagDevice* diag = nullptr;  // Karatsuba plan of the prover's diagonal products (diag.cu), built on first use
   uint8_t* pinned = nullptr;  // small pinned staging for results
   size_t pinned_cap = 0;
   ~ShuffleState() {
@@ -50,6 +52,7 @@ struct ShuffleState : ShuffleParamsHost {
     if (aux) cudaStreamDestroy(aux);
     if (aux_ws) msm_workspace_destroy(aux_ws);
     if (d_tab) cudaFree(d_tab);
+    if (diag) diag_device_destroy(diag);
     for (mp_ctx* w : workers) mp_ctx_destroy(w);
   }
 };
@@ -61,6 +64,7 @@ enum Slot {  // ctx->scratch slots owned by this file
   sResults, sPartials,
   sFrA, sFrB, sFrD, sFrBv, sFrXpow, sFrAme, sFrTmp0, sFrTmp1, sFrTmp2, sFrPairs, sFrSmall,
   sPerm, sRho, sCanonOut, sCtTable,
+  sKaraTmp, sKaraPts, sKaraScal, sKaraOut,
 };
 
 #define CK(x)                                                    \

@@ -107,10 +107,18 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   // window (fewer entries).  The table depends on no challenge: it is queued behind c_A and
   // runs on the GPU while the host hashes the statement.
   const int c_diag = msm_pick_table_window(N / 2 + 1);
-  affine* d_ct_tab = (affine*)ctx->scratch(sCtTable, (size_t)msm_num_windows(c_diag) * T2 * 2 * sizeof(affine));
-  NEED(d_ct_tab);
-  CK(msm_build_table(ctx->ws, d_ct_mont, (uint32_t)(T2 * 2), 0, (uint32_t)(N * 2), c_diag, d_ct_tab, st));
-  ctx->launches += 2;
+  // From m ~ 16 on, Karatsuba on the row index (diag.cu) needs fewer bucket additions than the
+  // m(m+1) row products of the schoolbook form; its leaf point rows depend on no challenge either.
+  const bool kara = diag_karatsuba_selected(m, n, c_diag);
+  affine* d_ct_tab = nullptr;
+  if (kara) {
+    if ((rcode = diag_karatsuba_points(ctx, d_ct_mont, st)) != MP_OK) return rcode;
+  } else {
+    d_ct_tab = (affine*)ctx->scratch(sCtTable, (size_t)msm_num_windows(c_diag) * T2 * 2 * sizeof(affine));
+    NEED(d_ct_tab);
+    CK(msm_build_table(ctx->ws, d_ct_mont, (uint32_t)(T2 * 2), 0, (uint32_t)(N * 2), c_diag, d_ct_tab, st));
+    ctx->launches += 2;
+  }
   CK(cudaEventSynchronize(S->ev));  // c_A is on the host; the table build continues
   Transcript fs;
   absorb_statement(fs, S, pk, deck, deck2, N, proof_out + L.cA);
@@ -187,7 +195,9 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
   }
   CK(cudaEventRecord(S->ev_fork, st));  // everything the commitment batch reads is queued before this point
-  {
+  if (kara) {
+    if ((rcode = diag_karatsuba_products(ctx, d_ct_scal, d_ct_out, st)) != MP_OK) return rcode;
+  } else {
     // one launch sequence normally; very large decks are split so that a call stays below the
     // 2^32-entry limit of the sort (entries = terms * windows)
     const uint64_t max_terms = ((1ull << 31) / (uint64_t)msm_num_windows(c_diag));

@@ -126,3 +126,21 @@ int h_verdict(const int* g1_id, int ct_ok, const int* host_flags) {
   return verdict(hc, fr_one(), ids, ct_ok != 0);
 }
 }
+
+// ---- host-only plan of the prover's Karatsuba diagonal products (csrc/diag_plan.hpp)
+#include "../../mental-poker_b200/csrc/diag_plan.hpp"
+extern "C" {
+// sizes[0] = nleaf, sizes[1] = number of CSR entries; arrays may be null to query the sizes
+void h_diag_plan(int m, uint32_t* sizes, uint32_t* leaf_mask, uint32_t* leaf_val, uint32_t* single, uint32_t* row_start,
+                 uint32_t* entries) {
+  const DiagPlan p = diag_plan_build(m);
+  sizes[0] = p.nleaf();
+  sizes[1] = (uint32_t)p.entries.size();
+  if (!leaf_mask) return;
+  memcpy(leaf_mask, p.leaf_mask.data(), 4 * p.leaf_mask.size());
+  memcpy(leaf_val, p.leaf_val.data(), 4 * p.leaf_val.size());
+  memcpy(single, p.single.data(), 4 * p.single.size());
+  memcpy(row_start, p.row_start.data(), 4 * p.row_start.size());
+  memcpy(entries, p.entries.data(), 4 * p.entries.size());
+}
+}

@@ -53,7 +53,7 @@ def test_msm_2p20_known_discrete_logs(ctx, pkg):
     assert ctx.msm_g1(points, scs, 0) == want
 
 
-def test_shuffle_2p16_round_trip_and_negative(ctx, pkg):
+def test_shuffle_2p16_round_trip_and_negative(ctx, pkg, monkeypatch):
     m, n = 128, 512
     Nc = m * n
     rng = np.random.default_rng(5)
@@ -76,6 +76,12 @@ def test_shuffle_2p16_round_trip_and_negative(ctx, pkg):
     # determinism: same inputs -> same bytes
     deck2b, proofb = ctx.shuffle_and_remask(pk, deck, perm, rho, rand)
     assert deck2b == deck2 and proofb == proof
+    # the two forms of the diagonal products (Karatsuba leaves, the default here, and the
+    # schoolbook row products over the pre-shifted deck table) give the same proof bytes
+    monkeypatch.setenv("MP_DIAG_KARATSUBA", "0")
+    deck2c, proofc = ctx.shuffle_and_remask(pk, deck, perm, rho, rand)
+    monkeypatch.delenv("MP_DIAG_KARATSUBA")
+    assert deck2c == deck2 and proofc == proof
     # reference negative case (tests.rs:213-226): an unrelated output deck fails in the Hadamard argument
     wrong = deck[128:] + deck[:128]
     assert ctx.verify_shuffle(pk, deck, wrong, proof) == 1

@@ -168,6 +168,37 @@ def test_identity_and_duplicate_cards(ctx, scalar_path):
     assert ctx.verify_shuffle(pb(pk), deck_b, deck2, proof) == 0
 
 
+@pytest.mark.parametrize("m,n,seed", [(2, 2, 5), (3, 4, 9), (5, 3, 6), (8, 8, 7), (13, 5, 10), (16, 32, 8)])
+@pytest.mark.parametrize("form", ["schoolbook", "karatsuba"])
+def test_diagonal_products_both_forms_vs_c_oracle(ctx, m, n, seed, form, monkeypatch):
+    """The prover's E_k (multi-exponentiation argument) have two device implementations: m(m+1) row
+    products over the pre-shifted deck table, and Karatsuba on the row index (csrc/diag.cu, the
+    default from m ~ 16).  Both must give the oracle's bytes, including decks with identity
+    components and duplicated cards (leaf rows then hit the doubling / cancellation branches) and
+    row counts that are not powers of two."""
+    monkeypatch.setenv("MP_SMALL_DECK_MAX", "0")
+    monkeypatch.setenv("MP_DIAG_KARATSUBA", "1" if form == "karatsuba" else "0")
+    pp, pk, deck, perm, rho, rnd = instance(m, n, seed)
+    if (m, n) == (3, 4):
+        # shuffled-deck coincidences inside one column (the rows a leaf adds up): positions 0 and 4
+        # hold the SAME ciphertext, positions 1 and 9 opposite ones, position 2 the identity
+        deck[perm[4]] = deck[perm[0]]
+        rho[4] = rho[0]
+        deck[perm[9]] = (stark.neg(deck[perm[1]][0]), stark.neg(deck[perm[1]][1]))
+        rho[9] = (stark.N - rho[1]) % stark.N
+        deck[perm[2]] = (None, None)
+        rho[2] = 0
+    co = c_oracle.COracle(msm_mode=1)
+    enc_g, ck_g, ck_h, ghat = pb(pp.enc_g), b"".join(map(pb, pp.ck_g)), pb(pp.ck_h), pb(pp.ghat)
+    deck_b = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+    rho_b, rnd_b = b"".join(map(b32, rho)), b"".join(map(b32, rnd))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    deck2, proof = ctx.shuffle_and_remask(pb(pk), deck_b, perm, rho_b, rnd_b)
+    assert deck2 == co.remask(enc_g, pb(pk), deck_b, perm, rho_b)
+    assert proof == co.prove(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, perm, rho_b, rnd_b)
+    assert ctx.verify_shuffle(pb(pk), deck_b, deck2, proof) == 0
+
+
 def _batch(m, n, seeds):
     co = c_oracle.COracle(msm_mode=1)
     pp0 = None
