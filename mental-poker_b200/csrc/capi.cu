@@ -240,10 +240,11 @@ static int32_t shuffle_and_remask_common(mp_ctx* ctx, const uint8_t* pk, const u
   if (!d_deck && shuffle_uses_small_deck_path(n_cards))  // small decks: the lockstep prover with a batch of one
     return shuffle_prove_batch(ctx, pk, deck, perm, rho, randomness, 1, out_deck, proof_out, 1);
   const void* d_shuffled = nullptr;
-  int32_t st = shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck, d_deck, &d_shuffled);
+  Transcript fs;  // its statement absorb starts while the remask kernel runs
+  int32_t st = shuffle_remask(ctx, pk, deck, perm, rho, n_cards, out_deck, d_deck, &d_shuffled, &fs);
   if (st != MP_OK) return st;
   int launches = ctx->launches;
-  st = shuffle_prove(ctx, pk, deck, out_deck, perm, rho, randomness, proof_out, d_shuffled);
+  st = shuffle_prove(ctx, pk, deck, out_deck, perm, rho, randomness, proof_out, d_shuffled, &fs);
   ctx->launches += launches;
   return st;
 }

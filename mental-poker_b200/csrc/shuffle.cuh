@@ -36,12 +36,14 @@ int32_t shuffle_n(const mp_ctx* ctx);
 
 int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
                        const uint8_t* rho, uint64_t N, uint8_t* out_deck, const void* deck_src = nullptr,
-                       const void** d_out_ret = nullptr);
+                       const void** d_out_ret = nullptr, Transcript* fs_head = nullptr);
+// (fs_head: when given, the head of the statement absorb -- parameters, pk, input deck -- is hashed
+//  into it while the remask kernel and its copies run; pass the same transcript to shuffle_prove)
 int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k,
                              uint64_t len, uint8_t* out);
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
                       const uint32_t* perm, const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out,
-                      const void* deck2_src = nullptr);
+                      const void* deck2_src = nullptr, Transcript* fs_started = nullptr);
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
                        const uint8_t* proof, const void* deck_src = nullptr, const void* deck2_src = nullptr);
 

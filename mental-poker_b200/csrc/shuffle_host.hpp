@@ -100,8 +100,11 @@ struct Layout {
   }
 };
 
-inline void absorb_statement(Transcript& fs, const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* deck,
-                             const uint8_t* deck2, size_t N, const uint8_t* cA) {
+// The statement absorb is ONE Blake2s over  label | parameters | pk | deck | deck' | c_A | seed  --
+// serial by construction and, at 2^16 cards, 17 MB.  It is fed in two parts so that the prover can
+// hash what it already has (everything up to the input deck, then the shuffled deck) while the GPU
+// is still remasking / committing, and only then wait for c_A.
+inline void absorb_statement_head(Transcript& fs, const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* deck, size_t N) {
   fs.begin();
   fs.feed_label("shuffle_argument");
   fs.feed_points64(S->enc_g, 1);
@@ -110,9 +113,17 @@ inline void absorb_statement(Transcript& fs, const ShuffleParamsHost* S, const u
   fs.feed_points64(S->ck64.data(), 1);
   fs.feed_points64(S->ghat, 1);
   fs.feed_points64(deck, 2 * N);
-  fs.feed_points64(deck2, 2 * N);
-  fs.feed_points64(cA, (size_t)S->m);
+}
+inline void absorb_statement_deck2(Transcript& fs, const uint8_t* deck2, size_t N) { fs.feed_points64(deck2, 2 * N); }
+inline void absorb_statement_tail(Transcript& fs, const uint8_t* cA, int m) {
+  fs.feed_points64(cA, (size_t)m);
   fs.end();
+}
+inline void absorb_statement(Transcript& fs, const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* deck,
+                             const uint8_t* deck2, size_t N, const uint8_t* cA) {
+  absorb_statement_head(fs, S, pk, deck, N);
+  absorb_statement_deck2(fs, deck2, N);
+  absorb_statement_tail(fs, cA, S->m);
 }
 
 // ------------------------------------------------------------------------------------------

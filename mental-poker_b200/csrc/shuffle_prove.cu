@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(64) k_combine_E(xyzz* __restrict__ E, const xy
 
 
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint32_t* perm,
-                      const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out, const void* deck2_src) {
+                      const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out, const void* deck2_src, Transcript* fs_started) {
   if (!ctx || !pk || !deck || !deck2 || !perm || !rho || !rand || !proof_out) return MP_ERR_INVALID_ARG;
   if (!deck2_src) deck2_src = deck2;
   ShuffleState* S = ctx->shuffle;
@@ -119,9 +119,14 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(msm_build_table(ctx->ws, d_ct_mont, (uint32_t)(T2 * 2), 0, (uint32_t)(N * 2), c_diag, d_ct_tab, st));
     ctx->launches += 2;
   }
-  CK(cudaEventSynchronize(S->ev));  // c_A is on the host; the table build continues
-  Transcript fs;
-  absorb_statement(fs, S, pk, deck, deck2, N, proof_out + L.cA);
+  // The statement hash (17 MB through one Blake2s chain at 2^16 cards) is the longest serial item of
+  // the whole proof: everything but c_A is hashed before the host waits for the GPU.
+  Transcript fs_local;
+  Transcript& fs = fs_started ? *fs_started : fs_local;
+  if (!fs_started) absorb_statement_head(fs, S, pk, deck, N);
+  absorb_statement_deck2(fs, deck2, N);
+  CK(cudaEventSynchronize(S->ev));  // c_A is on the host; the table / leaf-row kernels continue
+  absorb_statement_tail(fs, proof_out + L.cA, m);
   const fr x = fs.challenge();
 
   // ---- round B: b_i = x^{perm[i]+1}, c_B[k] = com(chunk_k(b); s_k)

@@ -423,12 +423,13 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
   P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, (uint64_t)(N > small_deck_max() ? 3 : 32), B}));
   return run_on_workers(ctx, P, B, [&](mp_ctx* w, uint64_t i) {
     const void* d_shuffled = nullptr;
+    Transcript fs;
     int32_t st = shuffle_remask(w, pk, decks + i * N * 128, perms + i * N, rhos + i * N * 32, N, out_decks + i * N * 128,
-                                nullptr, &d_shuffled);
+                                nullptr, &d_shuffled, &fs);
     int l = w->launches;
     if (st == MP_OK) {
       st = shuffle_prove(w, pk, decks + i * N * 128, out_decks + i * N * 128, perms + i * N, rhos + i * N * 32,
-                         rands + i * rlen, proofs + i * plen, d_shuffled);
+                         rands + i * rlen, proofs + i * plen, d_shuffled, &fs);
       w->launches += l;
     }
     return st;

@@ -218,7 +218,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
 // remask + commitments (stand-alone entry points; the prover reuses the pieces)
 // ------------------------------------------------------------------------------------------
 int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm, const uint8_t* rho,
-                       uint64_t N, uint8_t* out_deck, const void* deck_src, const void** d_out_ret) {
+                       uint64_t N, uint8_t* out_deck, const void* deck_src, const void** d_out_ret, Transcript* fs_head) {
   if (!deck_src) deck_src = deck;
   if (d_out_ret) *d_out_ret = nullptr;
   if (!ctx || !pk || (N && (!deck || !perm || !rho || !out_deck))) return MP_ERR_INVALID_ARG;
@@ -255,6 +255,7 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   int bad = 0;
   CK(cudaMemcpyAsync(out_deck, d_out, N * 128, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (fs_head) absorb_statement_head(*fs_head, S, pk, deck, N);  // host hashing overlaps the copies and the kernel
   CK(cudaStreamSynchronize(ctx->stream));
   if (bad == 2) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry out of range");
   if (bad) {

@@ -11,6 +11,7 @@
 // x || y || infinity-flag = 65 bytes, identity = (0, 1, true).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -50,6 +51,14 @@ class Blake2s {
       compress(buf_, false);
       fill_ = 0;
     }
+#ifdef MP_BLAKE2S_X86
+    if (len > 64 && use_avx512()) {  // all full blocks but the last in one call: the state stays in registers
+      const size_t nblocks = (len - 1) / 64;
+      compress_blocks_avx512(in, nblocks);
+      in += 64 * nblocks;
+      len -= 64 * nblocks;
+    }
+#endif
     while (len > 64) {  // strictly greater: the last block must go through finish()
       t_ += 64;
       compress(in, false);
@@ -83,6 +92,88 @@ class Blake2s {
     compress_scalar(block, last);
   }
 #ifdef MP_BLAKE2S_X86
+  static bool use_avx512() {
+#ifdef MP_BLAKE2S_NO_AVX512
+    return false;
+#else
+    static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") &&
+                           getenv("MP_BLAKE2S_NO_AVX512") == nullptr;
+    return ok;
+#endif
+  }
+  // AVX-512VL form for long inputs.  The compression function is one dependent chain
+  // (a -> d -> c -> b twice per G layer, 20 layers per block), so throughput is set by the latency of
+  // that chain and nothing else; this version takes everything else off it:
+  //   * rotations are single VPRORD instructions (AVX2 needs shift + shift + or for 12 and 7);
+  //   * the whole message block sits in one ZMM register and each round's 16 words come out of ONE
+  //     VPERMD with a per-round index vector (no scalar gathers);
+  //   * the message word is added into row a BEFORE row b is ready (the asm barrier stops the compiler
+  //     from re-associating a + m + b into (b + m) + a);
+  //   * diagonalisation rotates rows a, c, d and leaves b -- the value computed last -- in place; the
+  //     per-round index vectors are rotated to match.
+  // 6 dependent single-cycle instructions per G layer = 240 cycles per 64-byte block.
+  __attribute__((target("avx512f,avx512vl"))) void compress_blocks_avx512(const uint8_t* in, size_t nblocks) {
+    alignas(64) static const uint32_t perm[10][16] = {
+#define MP_R(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+  {s0, s2, s4, s6, s1, s3, s5, s7, s14, s8, s10, s12, s15, s9, s11, s13},
+        MP_R(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15) MP_R(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+        MP_R(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4) MP_R(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+        MP_R(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13) MP_R(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+        MP_R(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11) MP_R(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+        MP_R(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5) MP_R(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
+#undef MP_R
+    };
+    const __m128i iv_lo = _mm_setr_epi32((int)0x6A09E667u, (int)0xBB67AE85u, (int)0x3C6EF372u, (int)0xA54FF53Au);
+    const __m128i iv_hi = _mm_setr_epi32((int)0x510E527Fu, (int)0x9B05688Cu, (int)0x1F83D9ABu, (int)0x5BE0CD19u);
+    __m128i h_lo = _mm_loadu_si128((const __m128i*)&h_[0]), h_hi = _mm_loadu_si128((const __m128i*)&h_[4]);
+    uint64_t t = t_;
+#define MP_PIN(x) __asm__("" : "+x"(x))
+#define MP_G(ra, rb)                                          \
+  row1 = _mm_add_epi32(row1, row2);                           \
+  row4 = _mm_ror_epi32(_mm_xor_si128(row4, row1), ra);        \
+  row3 = _mm_add_epi32(row3, row4);                           \
+  row2 = _mm_ror_epi32(_mm_xor_si128(row2, row3), rb);
+    for (size_t blk = 0; blk < nblocks; blk++, in += 64) {
+      t += 64;
+      const __m512i M = _mm512_loadu_si512((const void*)in);
+      __m128i row1 = h_lo, row2 = h_hi, row3 = iv_lo;
+      __m128i row4 = _mm_xor_si128(iv_hi, _mm_setr_epi32((int)(uint32_t)t, (int)(uint32_t)(t >> 32), 0, 0));
+      __m512i P = _mm512_permutexvar_epi32(_mm512_load_si512((const void*)perm[0]), M);
+      row1 = _mm_add_epi32(row1, _mm512_castsi512_si128(P));
+      MP_PIN(row1);
+#pragma GCC unroll 10
+      for (int r = 0; r < 10; r++) {
+        MP_G(16, 12)
+        row1 = _mm_add_epi32(row1, _mm512_extracti32x4_epi32(P, 1));
+        MP_PIN(row1);
+        MP_G(8, 7)
+        row1 = _mm_shuffle_epi32(row1, _MM_SHUFFLE(2, 1, 0, 3));
+        row3 = _mm_shuffle_epi32(row3, _MM_SHUFFLE(0, 3, 2, 1));
+        row4 = _mm_shuffle_epi32(row4, _MM_SHUFFLE(1, 0, 3, 2));
+        row1 = _mm_add_epi32(row1, _mm512_extracti32x4_epi32(P, 2));
+        MP_PIN(row1);
+        MP_G(16, 12)
+        row1 = _mm_add_epi32(row1, _mm512_extracti32x4_epi32(P, 3));
+        MP_PIN(row1);
+        MP_G(8, 7)
+        row1 = _mm_shuffle_epi32(row1, _MM_SHUFFLE(0, 3, 2, 1));
+        row3 = _mm_shuffle_epi32(row3, _MM_SHUFFLE(2, 1, 0, 3));
+        row4 = _mm_shuffle_epi32(row4, _MM_SHUFFLE(1, 0, 3, 2));
+        if (r < 9) {
+          P = _mm512_permutexvar_epi32(_mm512_load_si512((const void*)perm[r + 1]), M);
+          row1 = _mm_add_epi32(row1, _mm512_castsi512_si128(P));
+          MP_PIN(row1);
+        }
+      }
+      h_lo = _mm_xor_si128(h_lo, _mm_xor_si128(row1, row3));
+      h_hi = _mm_xor_si128(h_hi, _mm_xor_si128(row2, row4));
+    }
+#undef MP_G
+#undef MP_PIN
+    _mm_storeu_si128((__m128i*)&h_[0], h_lo);
+    _mm_storeu_si128((__m128i*)&h_[4], h_hi);
+    t_ = t;
+  }
   __attribute__((target("avx2,ssse3"))) void compress_avx(const uint8_t* block, bool last) {
     const __m128i r16 = _mm_setr_epi8(2, 3, 0, 1, 6, 7, 4, 5, 10, 11, 8, 9, 14, 15, 12, 13);
     const __m128i r8 = _mm_setr_epi8(1, 2, 3, 0, 5, 6, 7, 4, 9, 10, 11, 8, 13, 14, 15, 12);

@@ -14,12 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P, N = stark.P, stark.N
 
 
-@pytest.fixture(scope="module", params=["default", "scalar_blake2s"])
+@pytest.fixture(scope="module", params=["default", "avx2_blake2s", "scalar_blake2s"])
 def shim(request, tmp_path_factory):
-    # "scalar_blake2s" forces the portable compression function (the default build picks the
-    # AVX2 row formulation at run time on x86 hosts)
+    # the default build picks the compression function at run time on x86 hosts (AVX-512VL multi-block
+    # form, else the AVX2 row formulation); "avx2_blake2s" rules out the first, "scalar_blake2s"
+    # forces the portable code
     out = str(tmp_path_factory.mktemp("shim") / f"host_shim_{request.param}.so")
-    flags = ["-DMP_BLAKE2S_FORCE_SCALAR"] if request.param == "scalar_blake2s" else []
+    flags = {"scalar_blake2s": ["-DMP_BLAKE2S_FORCE_SCALAR"], "avx2_blake2s": ["-DMP_BLAKE2S_NO_AVX512"]}.get(request.param, [])
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", *flags, "-o", out,
                            os.path.join(ROOT, "tests", "host", "host_shim.cpp")])
     return ctypes.CDLL(out)
@@ -110,7 +111,7 @@ def test_host_transcript_matches_oracle(shim):
     shim.h_fs_points_challenge.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
     out = ctypes.create_string_buffer(32)
     rnd = random.Random(9)
-    for ln in [0, 1, 63, 64, 65, 127, 128, 129, 1000, 4096]:
+    for ln in [0, 1, 63, 64, 65, 127, 128, 129, 191, 192, 193, 1000, 4096, 4097]:
         msg = bytes(rnd.randrange(256) for _ in range(ln))
         for split in [0, 1, 64, ln // 2, ln]:
             shim.h_blake2s(msg, ln, split, out)
