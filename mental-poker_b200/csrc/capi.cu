@@ -45,7 +45,11 @@ extern "C" int32_t mp_ctx_create(mp_ctx** out, int32_t device) {
   if (e != cudaSuccess) return MP_ERR_CUDA;
   mp_ctx* ctx = new mp_ctx();
   ctx->device = device;
-  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  // the main stream carries the latency-critical launch chains: highest priority, so that its small
+  // kernels get the next free SM slots when a bulk launch (ShuffleState::bulk) fills the chip
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
   if (e != cudaSuccess) { delete ctx; return MP_ERR_CUDA; }
   ctx->ws = msm_workspace_create();
   *out = ctx;
@@ -189,6 +193,7 @@ extern "C" int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void*
 extern "C" int32_t mp_profile_enable(mp_ctx* ctx, int32_t on) {
   if (!ctx) return MP_ERR_INVALID_ARG;
   msm_profile_enable(ctx->ws, on != 0);
+  if (MsmWorkspace* b = shuffle_bulk_workspace(ctx)) msm_profile_enable(b, on != 0);
   return MP_OK;
 }
 extern "C" int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64_t* bucket_adds, uint64_t* launches) {
@@ -196,6 +201,12 @@ extern "C" int32_t mp_profile_collect(mp_ctx* ctx, double* accumulate_ms, uint64
   cudaSetDevice(ctx->device);
   cudaError_t e = msm_profile_collect(ctx->ws, accumulate_ms, bucket_adds, launches);
   if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_profile_collect");
+  if (MsmWorkspace* b = shuffle_bulk_workspace(ctx)) {  // the prover's diagonal products run on their own workspace
+    double ms = 0; uint64_t adds = 0, n = 0;
+    e = msm_profile_collect(b, &ms, &adds, &n);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_profile_collect");
+    *accumulate_ms += ms; *bucket_adds += adds; *launches += n;
+  }
   return MP_OK;
 }
 
@@ -203,8 +214,16 @@ extern "C" int32_t mp_profile_collect_dominant(mp_ctx* ctx, double* ms, uint64_t
   if (!ctx || !ms || !bucket_adds || !launches) return MP_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   double all_ms; uint64_t all_adds, all_launches;
+  // the dominant launches are the prover's diagonal products when a proof ran (bulk workspace)
+  MsmWorkspace* b = shuffle_bulk_workspace(ctx);
   cudaError_t e = msm_profile_collect(ctx->ws, &all_ms, &all_adds, &all_launches, ms, bucket_adds, launches);
   if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_profile_collect_dominant");
+  if (b) {
+    double bms = 0; uint64_t badds = 0, bn = 0;
+    e = msm_profile_collect(b, &all_ms, &all_adds, &all_launches, &bms, &badds, &bn);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "mp_profile_collect_dominant");
+    if (bn && badds / bn >= (*launches ? *bucket_adds / *launches : 0)) { *ms = bms; *bucket_adds = badds; *launches = bn; }
+  }
   return MP_OK;
 }
 

@@ -222,7 +222,7 @@ int32_t diag_karatsuba_points(mp_ctx* ctx, const affine* d_deck2, cudaStream_t s
   return MP_OK;
 }
 
-int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz* d_E, cudaStream_t st) {
+int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz* d_E, cudaStream_t st, MsmWorkspace* ws) {
   ShuffleState* S = ctx->shuffle;
   DiagDevice* D;
   int32_t rc = diag_device(ctx, &D);
@@ -246,8 +246,8 @@ int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz*
   const uint64_t max_jobs = std::max<uint64_t>(1, ((1ull << 31) / (uint64_t)msm_num_windows(c)) / n);
   for (uint64_t j0 = 0; j0 < jobs.size(); j0 += max_jobs) {
     const uint64_t cnt = std::min<uint64_t>(max_jobs, jobs.size() - j0);
-    CK(msm_run(ctx->ws, scal, nscal, pts, 2, jobs.data() + j0, (int)cnt, c, R + 2 * j0, st));
-    ctx->launches += msm_last_launches(ctx->ws);
+    CK(msm_run(ws, scal, nscal, pts, 2, jobs.data() + j0, (int)cnt, c, R + 2 * j0, st));
+    ctx->launches += msm_last_launches(ws);
   }
   k_kara_combine<<<4 * m, kCombThreads, 0, st>>>(R, D->d_row_start, D->d_entries, d_E);
   CK(cudaGetLastError());

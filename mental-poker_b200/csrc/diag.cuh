@@ -21,7 +21,8 @@ bool diag_karatsuba_selected(int m, int n, int c_table);
 // ciphertexts).  Independent of every challenge.
 int32_t diag_karatsuba_points(mp_ctx* ctx, const affine* d_deck2, cudaStream_t st);
 // d_rows_canon: canonical scalar rows a0 | b_1 .. b_m ((m+1)*n scalars).  Writes the 2m diagonal
-// products (without their Enc(b_k; tau_k) terms) to d_E[2k + comp].
-int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz* d_E, cudaStream_t st);
+// products (without their Enc(b_k; tau_k) terms) to d_E[2k + comp].  Runs on `st` with workspace `ws`.
+struct MsmWorkspace;
+int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz* d_E, cudaStream_t st, MsmWorkspace* ws);
 
 }  // namespace mp

@@ -27,10 +27,12 @@ struct mp_ctx;
 namespace mp {
 
 struct ShuffleState;
+struct MsmWorkspace;
 void shuffle_state_destroy(ShuffleState*);
 
 int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
                            const uint8_t* ck_h, const uint8_t* ghat);
+MsmWorkspace* shuffle_bulk_workspace(const mp_ctx* ctx);  // nullptr before set_params
 int32_t shuffle_m(const mp_ctx* ctx);
 int32_t shuffle_n(const mp_ctx* ctx);
 

@@ -31,6 +31,12 @@ struct ShuffleState : ShuffleParamsHost {
   cudaStream_t aux = nullptr;
   MsmWorkspace* aux_ws = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // low-priority stream + workspace for the prover's diagonal ciphertext products: they only need the
+  // first challenge and their result only enters the LAST transcript absorb, so they run beside the
+  // chain of small, latency-bound launches of rounds B, C and D (which keep the main stream)
+  cudaStream_t bulk = nullptr;
+  MsmWorkspace* bulk_ws = nullptr;
+  cudaEvent_t ev_bulk_go = nullptr, ev_bulk_done = nullptr;
   // fixed-base tables for remasking: tab[base][j][d-1] = d * 2^(8j) * base, base 0 = g, 1 = pk
   affine* d_tab = nullptr;
   uint8_t tab_pk[64];
@@ -51,6 +57,10 @@ struct ShuffleState : ShuffleParamsHost {
     if (ev_join) cudaEventDestroy(ev_join);
     if (aux) cudaStreamDestroy(aux);
     if (aux_ws) msm_workspace_destroy(aux_ws);
+    if (ev_bulk_go) cudaEventDestroy(ev_bulk_go);
+    if (ev_bulk_done) cudaEventDestroy(ev_bulk_done);
+    if (bulk) cudaStreamDestroy(bulk);
+    if (bulk_ws) msm_workspace_destroy(bulk_ws);
     if (d_tab) cudaFree(d_tab);
     if (diag) diag_device_destroy(diag);
     for (mp_ctx* w : workers) mp_ctx_destroy(w);

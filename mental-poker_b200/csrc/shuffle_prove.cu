@@ -55,6 +55,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, (8 * (size_t)m + 16) * sizeof(xyzz));
   uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, (N + n + 4 * (size_t)m + 8) * 32);
   xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 8 * (size_t)m * sizeof(xyzz));
+  xyzz* d_enc = d_ct_out + 4 * (size_t)m;  // Enc(b_k*ghat; tau_k) parts: 2m c1 values, then 2m c2 values
   uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, (8 * (size_t)m + 16) * 64);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_perm); NEED(d_rho); NEED(d_a); NEED(d_Ame); NEED(d_Az); NEED(d_d0);
@@ -65,6 +66,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   if (!h_pin) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
 
   // ---- uploads that do not depend on any challenge
+  CK(cudaStreamWaitEvent(st, S->ev_bulk_done, 0));  // (bulk work of a call that failed midway, if any)
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
   if (deck2_src != (const void*)d_ct_canon)  // (shuffle_and_remask leaves the remasked deck right here)
     CK(cudaMemcpyAsync(d_ct_canon, deck2_src, N * 128, cudaMemcpyDefault, st));
@@ -91,6 +93,35 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
 
   // ---- round A: c_A[k] = com(chunk_k(a); r_k),  a_i = perm[i] + 1
   const std::vector<fr> r = rc.vec(m), s = rc.vec(m);
+  // all remaining prover randomness, drawn now in the B.6 order (the draws depend on no challenge)
+  const fr s_prod = rc.one();                                   // B.2: blinding of c_b
+  std::vector<fr> sv((size_t)m);                                // B.3: s_1 = t_1, s_m = s_prod, rest random
+  // sv[0] = t[0] is filled in once y is known (round C)
+  for (int i = 1; i < m - 1; i++) sv[i] = rc.one();
+  sv[m - 1] = s_prod;
+  // B.4 randomness (drawn now to respect the B.6 order; used in round D)
+  const std::vector<fr> z_a0 = rc.vec(n), z_bm1 = rc.vec(n);
+  const fr z_r0 = rc.one(), z_sm1 = rc.one();
+  std::vector<fr> z_t((size_t)2 * m + 1);
+  for (int k = 0; k <= 2 * m; k++) z_t[k] = (k != m + 1) ? rc.one() : fr_zero();
+  // B.5 randomness
+  const std::vector<fr> sv_d = rc.vec(n);
+  const fr sv_rd = rc.one();
+  std::vector<fr> sv_delta((size_t)n);
+  sv_delta[0] = sv_d[0];
+  for (int i = 1; i < n - 1; i++) sv_delta[i] = rc.one();
+  sv_delta[n - 1] = fr_zero();
+  const fr sv_s1 = rc.one(), sv_sx = rc.one();
+  // B.5' randomness
+  const std::vector<fr> me_a0 = rc.vec(n);
+  const fr me_r0 = rc.one();
+  std::vector<fr> me_b((size_t)2 * m), me_s((size_t)2 * m), me_tau((size_t)2 * m);
+  for (int k = 0; k < 2 * m; k++) {
+    if (k == m) { me_b[k] = fr_zero(); me_s[k] = fr_zero(); me_tau[k] = fr_zero(); /* tau_m = rho*, set below */ }
+    else { me_b[k] = rc.one(); me_s[k] = rc.one(); me_tau[k] = rc.one(); }
+  }
+  if (rc.i != shuffle_randomness_len(m, n)) return ctx->fail(MP_ERR_INVALID_ARG, "internal: randomness count mismatch");
+
   fr* d_blind = d_pairs;  // small scratch for blinding factors (<= 4m + 8 elements at the end of d_pairs)
   d_blind = d_pairs + (size_t)(m + 1) * (m + 1);
   CK(fr_perm_vectors(d_perm, nullptr, N, d_a, nullptr, st));
@@ -133,6 +164,39 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(fr_powers(h_pow2_table(x), N, nullptr, d_xpow, nullptr, d_partials, nullptr, st));
   CK(fr_perm_vectors(d_perm, d_xpow, N, nullptr, d_b, st));
   ctx->launches += 2;
+
+  // ---- the 2m diagonal ciphertext products E_k (K2; multi-exponentiation first message, B.5') are the
+  // prover's dominant device cost.  They need x and nothing else, and their result only enters the
+  // LAST transcript absorb -- so they go to the low-priority bulk stream now and run beside the whole
+  // chain of small launches and host round trips of rounds B, C and D on the main stream.
+  CK(cudaMemcpyAsync(d_Ame, me_a0.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
+  CK(fr_to_canonical_vec(d_Ame, d_ct_scal, N + n, st));  // scalar arena: rows a0 | b_1..b_m
+  ctx->launches += 1;
+  CK(cudaEventRecord(S->ev_bulk_go, st));
+  CK(cudaStreamWaitEvent(S->bulk, S->ev_bulk_go, 0));
+  if (kara) {
+    if ((rcode = diag_karatsuba_products(ctx, d_ct_scal, d_ct_out, S->bulk, S->bulk_ws)) != MP_OK) return rcode;
+  } else {
+    std::vector<MsmJob> diag((size_t)2 * m);
+    for (int k = 0; k < 2 * m; k++) {
+      int i0 = std::max(1, m - k), i1 = std::min(m, 2 * m - k);
+      diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
+    }
+    // one launch sequence normally; very large decks are split so that a call stays below the
+    // 2^32-entry limit of the sort (entries = terms * windows)
+    const uint64_t max_terms = ((1ull << 31) / (uint64_t)msm_num_windows(c_diag));
+    for (int k0 = 0; k0 < 2 * m;) {
+      int k1 = k0;
+      uint64_t terms = 0;
+      while (k1 < 2 * m && (k1 == k0 || terms + diag[k1].len <= max_terms)) terms += diag[k1++].len;
+      CK(msm_run(S->bulk_ws, d_ct_scal, N + n, d_ct_tab, 2, diag.data() + k0, k1 - k0, c_diag, d_ct_out + 2 * (size_t)k0, S->bulk, 0, -1,
+                 (uint32_t)T2));
+      ctx->launches += msm_last_launches(S->bulk_ws);
+      k0 = k1;
+    }
+  }
+  CK(cudaEventRecord(S->ev_bulk_done, S->bulk));
+
   CK(cudaMemcpyAsync(d_blind, s.data(), sizeof(fr) * m, cudaMemcpyHostToDevice, st));
   if ((rcode = commit_rows_device(ctx, d_b, n, d_blind, m, n, d_g1_scal, d_g1_out)) != MP_OK) return rcode;
   CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, m, st));
@@ -147,6 +211,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   // C.1  d = y*a + b - z;  column prefix products Bv;  rho* = -sum rho_i b_i
   std::vector<fr> t((size_t)m);
   for (int k = 0; k < m; k++) t[k] = fr_add(fr_mul(y, r[k]), s[k]);
+  sv[0] = t[0];
   {
     fr yz[2] = {y, z};
     CK(cudaMemcpyAsync(d_blind, yz, sizeof yz, cudaMemcpyHostToDevice, st));
@@ -161,73 +226,13 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(cudaMemcpyAsync(h_col + n, d_partials + fr_reduce_blocks(N), sizeof(fr), cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(S->ev, st));
 
-  // C.2  multi-exponentiation first message (B.5'): a0, r0, (b_k, s_k, tau_k); the 2m diagonal
-  //      ciphertext MSMs E_k (K2) are the prover's dominant cost and only need x.
-  const fr s_prod = rc.one();                                   // B.2: blinding of c_b
-  std::vector<fr> sv((size_t)m);                                // B.3: s_1 = t_1, s_m = s_prod, rest random
-  sv[0] = t[0];
-  for (int i = 1; i < m - 1; i++) sv[i] = rc.one();
-  sv[m - 1] = s_prod;
-  // B.4 randomness (drawn now to respect the B.6 order; used in round D)
-  const std::vector<fr> z_a0 = rc.vec(n), z_bm1 = rc.vec(n);
-  const fr z_r0 = rc.one(), z_sm1 = rc.one();
-  std::vector<fr> z_t((size_t)2 * m + 1);
-  for (int k = 0; k <= 2 * m; k++) z_t[k] = (k != m + 1) ? rc.one() : fr_zero();
-  // B.5 randomness
-  const std::vector<fr> sv_d = rc.vec(n);
-  const fr sv_rd = rc.one();
-  std::vector<fr> sv_delta((size_t)n);
-  sv_delta[0] = sv_d[0];
-  for (int i = 1; i < n - 1; i++) sv_delta[i] = rc.one();
-  sv_delta[n - 1] = fr_zero();
-  const fr sv_s1 = rc.one(), sv_sx = rc.one();
-  // B.5' randomness
-  const std::vector<fr> me_a0 = rc.vec(n);
-  const fr me_r0 = rc.one();
-  std::vector<fr> me_b((size_t)2 * m), me_s((size_t)2 * m), me_tau((size_t)2 * m);
-  for (int k = 0; k < 2 * m; k++) {
-    if (k == m) { me_b[k] = fr_zero(); me_s[k] = fr_zero(); me_tau[k] = fr_zero(); /* tau_m = rho*, set below */ }
-    else { me_b[k] = rc.one(); me_s[k] = rc.one(); me_tau[k] = rc.one(); }
-  }
-  if (rc.i != shuffle_randomness_len(m, n)) return ctx->fail(MP_ERR_INVALID_ARG, "internal: randomness count mismatch");
-
-  CK(cudaMemcpyAsync(d_Ame, me_a0.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
-  CK(fr_to_canonical_vec(d_Ame, d_ct_scal, N + n, st));  // scalar arena: rows a0 | b_1..b_m
-  ctx->launches += 1;
-  std::vector<MsmJob> diag((size_t)2 * m);
-  for (int k = 0; k < 2 * m; k++) {
-    int i0 = std::max(1, m - k), i1 = std::min(m, 2 * m - k);
-    diag[k] = MsmJob{(uint32_t)((size_t)(k - m + i0) * n), (uint32_t)((size_t)(i0 - 1) * n), (uint32_t)((size_t)(i1 - i0 + 1) * n)};
-  }
-  CK(cudaEventRecord(S->ev_fork, st));  // everything the commitment batch reads is queued before this point
-  if (kara) {
-    if ((rcode = diag_karatsuba_products(ctx, d_ct_scal, d_ct_out, st)) != MP_OK) return rcode;
-  } else {
-    // one launch sequence normally; very large decks are split so that a call stays below the
-    // 2^32-entry limit of the sort (entries = terms * windows)
-    const uint64_t max_terms = ((1ull << 31) / (uint64_t)msm_num_windows(c_diag));
-    for (int k0 = 0; k0 < 2 * m;) {
-      int k1 = k0;
-      uint64_t terms = 0;
-      while (k1 < 2 * m && (k1 == k0 || terms + diag[k1].len <= max_terms)) terms += diag[k1++].len;
-      CK(msm_run(ctx->ws, d_ct_scal, N + n, d_ct_tab, 2, diag.data() + k0, k1 - k0, c_diag, d_ct_out + 2 * (size_t)k0, st, 0, -1,
-                 (uint32_t)T2));
-      ctx->launches += msm_last_launches(ctx->ws);
-      k0 = k1;
-    }
-  }
-
-  // wait for col / rho* only (the event precedes the diagonal MSMs, which keep the GPU busy
-  // while the host prepares the next batch)
-  CK(cudaEventSynchronize(S->ev));
+  CK(cudaEventSynchronize(S->ev));  // col / rho* are on the host
   std::vector<fr> col(h_col, h_col + n);
   const fr rho_star = fr_neg(h_col[n]);
   me_tau[m] = rho_star;
 
-  // C.4  SVP first message on the host side of the scalars (O(n)), committed on the device.  The whole
-  //      commitment batch (C.4 + C.5) is issued on the auxiliary stream: it overlaps the diagonal MSMs.
-  cudaStream_t sa = S->aux;
-  CK(cudaStreamWaitEvent(sa, S->ev_fork, 0));
+  // C.4  SVP first message on the host side of the scalars (O(n)), committed on the device.
+  cudaStream_t sa = st;
   std::vector<fr> bk((size_t)n);
   bk[0] = col[0];
   for (int i = 1; i < n; i++) bk[i] = fr_mul(bk[i - 1], col[i]);
@@ -245,7 +250,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   //                c_delta, c_Delta, multi-exp c_A0                              (n+1 terms each)
   //      pairs     multi-exp c_B_k = s_k*h + b_k*g_1                               (2 terms)
   //      enc c1/c2 Enc(b_k*ghat; tau_k) = (tau_k*g, b_k*ghat + tau_k*pk)           (1 / 2 terms)
-  //      then E_k = diag_k + enc_k.
+  //      (kept in d_enc: E_k = diag_k + enc_k is formed once the bulk stream has delivered diag_k)
   {
     const int R = m + 4;
     std::vector<fr> blinds((size_t)R);
@@ -273,18 +278,13 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 2 * k, 0, 2});                               // (h, g_1)
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 4 * m + k, (uint32_t)(n + 1), 1});           // enc_g
     for (int k = 0; k < 2 * m; k++) jobs.push_back(MsmJob{base + 6 * m + 2 * k, (uint32_t)(n + 2), 2});       // (ghat, pk)
-    CK(msm_run(S->aux_ws, d_g1_scal, base + nsmall, S->d_tab_ck, 1, jobs.data(), (int)jobs.size(), S->tab_c, d_g1_out, sa, 0, -1,
+    CK(msm_run(ctx->ws, d_g1_scal, base + nsmall, S->d_tab_ck, 1, jobs.data(), (int)jobs.size(), S->tab_c, d_g1_out, sa, 0, -1,
                (uint32_t)(n + 4)));
-    ctx->launches += msm_last_launches(S->aux_ws);
-    CK(cudaEventRecord(S->ev_join, sa));
-    CK(cudaStreamWaitEvent(st, S->ev_join, 0));  // join: E_k needs both the diagonals and the Enc parts
-    k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_g1_out + R + 2 * m, d_g1_out + R + 4 * m, 2 * m);
-    CK(cudaGetLastError());
-    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canon, 4 * (size_t)m, st));
+    ctx->launches += msm_last_launches(ctx->ws);
+    CK(cudaMemcpyAsync(d_enc, d_g1_out + R + 2 * m, 4 * (size_t)m * sizeof(xyzz), cudaMemcpyDeviceToDevice, st));
     uint8_t* d_canon2 = d_canon + 4 * (size_t)m * 64;
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon2, (size_t)R + 2 * m, st));
-    ctx->launches += 3;
-    CK(cudaMemcpyAsync(proof_out + L.meE, d_canon, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
+    ctx->launches += 1;
     CK(cudaMemcpyAsync(proof_out + L.hB, d_canon2, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proof_out + L.svpts, d_canon2 + (size_t)m * 64, 3 * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proof_out + L.mepts, d_canon2 + (size_t)(m + 3) * 64, (size_t)(2 * m + 1) * 64, cudaMemcpyDeviceToHost, st));
@@ -342,6 +342,14 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, 2 * (size_t)m + 3, st));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(proof_out + L.zpts, d_canon, (2 * (size_t)m + 3) * 64, cudaMemcpyDeviceToHost, st));
+    // join the bulk stream: E_k = diag_k + Enc(b_k*ghat; tau_k), needed for the last absorb below
+    CK(cudaStreamWaitEvent(st, S->ev_bulk_done, 0));
+    k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_enc, d_enc + 2 * m, 2 * m);
+    CK(cudaGetLastError());
+    uint8_t* d_canonE = d_canon + (2 * (size_t)m + 4) * 64;
+    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canonE, 4 * (size_t)m, st));
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(proof_out + L.meE, d_canonE, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
   fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof_out + L.zpts, 2 * (size_t)m + 3); fs.end();

@@ -6,6 +6,7 @@
 namespace mp {
 
 void shuffle_state_destroy(ShuffleState* s) { delete s; }
+MsmWorkspace* shuffle_bulk_workspace(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->bulk_ws : nullptr; }
 int32_t shuffle_m(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->m : 0; }
 int32_t shuffle_n(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->n : 0; }
 bool shuffle_uses_small_deck_path(uint64_t n_cards) { return n_cards <= small_deck_max() && !getenv("MP_BATCH_WORKERS"); }
@@ -168,6 +169,14 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
     CK(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
     S->aux_ws = msm_workspace_create();
+  }
+  if (!S->bulk) {
+    int lo = 0, hi = 0;  // lo = least priority (numerically greatest); the context's main stream is created with hi
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&S->bulk, cudaStreamNonBlocking, lo));
+    CK(cudaEventCreateWithFlags(&S->ev_bulk_go, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S->ev_bulk_done, cudaEventDisableTiming));
+    S->bulk_ws = msm_workspace_create();
   }
   // validate every parameter point and compute gsum = sum g_j with one MSM of unit scalars
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
