@@ -295,7 +295,7 @@ def main():
     ctx.profile_collect()
     with ClockSampler(local_rank) as clocks:
         ms_res, launches = timed_steps(True, args.steps)
-    acc_ms, acc_adds, acc_launches = ctx.profile_collect_dominant()  # the prover's diagonal-MSM launches
+    acc_ms, acc_adds, acc_launches = ctx.profile_collect_dominant()  # the prover's diagonal-product launches (bulk stream)
     ctx.profile_enable(False)
     barrier()
     # ---- `e2e`: host buffers through the public C ABI
@@ -344,7 +344,7 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
-        roofline = dict(bound="hbm", kernel="k_accumulate<2> (bucket accumulation of the prover's diagonal ciphertext MSMs, XYZZ mixed adds)",
+        roofline = dict(bound="hbm", kernel="k_accumulate<2> (bucket accumulation of the prover's diagonal ciphertext products -- Karatsuba leaf jobs, XYZZ mixed adds)",
                         achieved=achieved, peak=peak, unit="GB/s", frac=(achieved / peak if achieved else None), traffic=traffic,
                         traffic_source=traffic_src, algorithmic_bytes_per_launch=(bytes_per_add * acc_adds / acc_launches if acc_launches else None),
                         peak_source=peak_src, launches=acc_launches,

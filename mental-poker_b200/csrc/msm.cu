@@ -534,7 +534,26 @@ __global__ void __launch_bounds__(kAccThreads, MINBLOCKS)
           else xyzz_store(bucket_sums + b * NCOMP + comp, acc);
           first = false;
           acc = xyzz_identity();
-          do { b++; next = offsets[b + 1]; } while (next <= pos);
+          b++;
+          next = offsets[b + 1];
+          if (next <= pos) {
+            // a run of empty buckets (sparse jobs: a 2-term commitment still owns a whole bucket set):
+            // gallop, then bisect, instead of one dependent load per empty bucket.
+            // invariant: offsets[lo2 + 1] <= pos < offsets[hi2 + 1]   (offsets[nbuckets] = E > pos)
+            uint64_t lo2 = b, hi2 = b, step = 1;
+            for (;;) {
+              hi2 = min(lo2 + step, nbuckets - 1);
+              if (offsets[hi2 + 1] > pos) break;
+              lo2 = hi2;
+              step <<= 1;
+            }
+            while (hi2 - lo2 > 1) {
+              const uint64_t mid = (lo2 + hi2) >> 1;
+              if (offsets[mid + 1] <= pos) lo2 = mid; else hi2 = mid;
+            }
+            b = hi2;
+            next = offsets[b + 1];
+          }
         }
         if (val >> 31) pt = affine_neg(pt);
         xyzz_madd(acc, pt);
@@ -740,10 +759,30 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   if (table_nb && (w_begin != 0 || W != W_all)) return cudaErrorInvalidValue;
   const int Wb = table_nb ? 1 : W;
   const uint32_t B = 1u << (c - 1);
-  // buckets per reduce_seg thread: as long as the chip stays full (>= ~150k threads), longer
-  // segments leave fewer segment sums for the per-window combine
+  // buckets per reduce_seg thread.  A thread's running-sum sweep is a serial chain of 2L additions and
+  // the kernel holds 3 blocks per SM, so a launch costs (number of block waves) x L: among the segment
+  // lengths that still give the chip enough threads, take the one with the cheapest whole number of
+  // waves (2315 jobs x 37 windows x 2 components at L = 64 is 3.02 waves -- a fourth, almost empty wave
+  // would cost a quarter of the kernel); longer segments win ties (fewer segment sums to combine).
   uint32_t L = std::min<uint32_t>(kSegLen, B);
-  while (L < B && L < 256 && (uint64_t)njobs * Wb * ncomp * (B / (2 * L)) >= 150000) L *= 2;
+  {
+    static const uint64_t seg_threads = [] { const char* e = getenv("MP_SEG_THREADS"); return e ? strtoull(e, nullptr, 10) : 150000ull; }();
+    static const uint64_t wave = [] {  // resident blocks of k_reduce_seg (launch bounds: 128 threads, 3 per SM)
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      return (uint64_t)sms * 3;
+    }();
+    auto cost = [&](uint32_t len) {
+      const uint64_t blocks = ((uint64_t)njobs * Wb * ncomp * (B / len) + 127) / 128;
+      return ((blocks + wave - 1) / wave) * len;
+    };
+    uint64_t best = cost(L);
+    for (uint32_t cand = 2 * L; cand <= B && cand <= 256; cand *= 2) {
+      if ((uint64_t)njobs * Wb * ncomp * (B / cand) < seg_threads) break;  // keep the chip full
+      if (cost(cand) <= best) { best = cost(cand); L = cand; }
+    }
+  }
   const uint32_t nseg = B / L;
   const uint64_t nwin = (uint64_t)njobs * Wb;
   const uint64_t nbuckets = nwin * B;
@@ -758,7 +797,9 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   if (max_entries >= (1ull << 32) || nbuckets >= (1ull << 32)) return cudaErrorInvalidValue;
   // chunk length: longer chunks mean fewer partial sums to stitch; keep >= ~600k threads in flight
   uint32_t kChunk = kChunkMin;
-  const uint32_t chunk_cap = ncomp == 1 ? kChunkMax / 2 : kChunkMax;  // a warp's staged tile stays <= 8 KB of smem
+  static const uint32_t chunk_cap_env = [] { const char* e = getenv("MP_ACC_CHUNK_CAP"); return e ? (uint32_t)atoi(e) : 0u; }();
+  uint32_t chunk_cap = ncomp == 1 ? kChunkMax / 2 : kChunkMax;  // a warp's staged tile stays <= 8 KB of smem
+  if (chunk_cap_env) chunk_cap = std::min(chunk_cap, std::max(kChunk, chunk_cap_env));
   while (kChunk < chunk_cap && max_entries * ncomp / (2 * kChunk) >= 600000) kChunk *= 2;
   // small launches are latency-bound (a thread adds its chunk serially): shorter chunks put more
   // threads to work as long as fewer than ~4 warps per SM would be busy otherwise

@@ -31,9 +31,9 @@ struct ShuffleState : ShuffleParamsHost {
   cudaStream_t aux = nullptr;
   MsmWorkspace* aux_ws = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // low-priority stream + workspace for the prover's diagonal ciphertext products: they only need the
-  // first challenge and their result only enters the LAST transcript absorb, so they run beside the
-  // chain of small, latency-bound launches of rounds B, C and D (which keep the main stream)
+  // own stream + workspace for the prover's diagonal ciphertext products: they only need the first
+  // challenge and their result only enters the LAST transcript absorb, so they are queued as soon as x
+  // is known and the small launches of rounds B, C and D (main stream) fill in around them
   cudaStream_t bulk = nullptr;
   MsmWorkspace* bulk_ws = nullptr;
   cudaEvent_t ev_bulk_go = nullptr, ev_bulk_done = nullptr;

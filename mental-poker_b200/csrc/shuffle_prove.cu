@@ -1,5 +1,7 @@
 // ShuffleArgument::prove for one deck with device-side scalar vectors (the 2^16-card path;
 // reference call site mod.rs:409-415).  See shuffle.cuh for the design notes.
+#include <chrono>
+
 #include "shuffle_internal.cuh"
 
 namespace mp {
@@ -16,6 +18,15 @@ __global__ void __launch_bounds__(64) k_combine_E(xyzz* __restrict__ E, const xy
 
 
 
+// MP_TRACE=1: host-side timestamps (ms since entry) of the prover's synchronisation points, on stderr
+struct ProveTrace {
+  bool on = getenv("MP_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) const {
+    if (on) fprintf(stderr, "[prove] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+  }
+};
+
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint32_t* perm,
                       const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out, const void* deck2_src, Transcript* fs_started) {
   if (!ctx || !pk || !deck || !deck2 || !perm || !rho || !rand || !proof_out) return MP_ERR_INVALID_ARG;
@@ -24,6 +35,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
   cudaSetDevice(ctx->device);
   ctx->launches = 0;
+  const ProveTrace trace;
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n;
   const Layout L(m, n);
@@ -157,6 +169,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   if (!fs_started) absorb_statement_head(fs, S, pk, deck, N);
   absorb_statement_deck2(fs, deck2, N);
   CK(cudaEventSynchronize(S->ev));  // c_A is on the host; the table / leaf-row kernels continue
+  trace.mark("statement hashed up to c_A; c_A on host");
   absorb_statement_tail(fs, proof_out + L.cA, m);
   const fr x = fs.challenge();
 
@@ -167,13 +180,14 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
 
   // ---- the 2m diagonal ciphertext products E_k (K2; multi-exponentiation first message, B.5') are the
   // prover's dominant device cost.  They need x and nothing else, and their result only enters the
-  // LAST transcript absorb -- so they go to the low-priority bulk stream now and run beside the whole
-  // chain of small launches and host round trips of rounds B, C and D on the main stream.
+  // LAST transcript absorb -- so they go to the bulk stream now; the small launches and host round
+  // trips of rounds B, C and D (main stream) fill in around them.
   CK(cudaMemcpyAsync(d_Ame, me_a0.data(), sizeof(fr) * n, cudaMemcpyHostToDevice, st));
   CK(fr_to_canonical_vec(d_Ame, d_ct_scal, N + n, st));  // scalar arena: rows a0 | b_1..b_m
   ctx->launches += 1;
   CK(cudaEventRecord(S->ev_bulk_go, st));
   CK(cudaStreamWaitEvent(S->bulk, S->ev_bulk_go, 0));
+  trace.mark("x known; b rows queued");
   if (kara) {
     if ((rcode = diag_karatsuba_products(ctx, d_ct_scal, d_ct_out, S->bulk, S->bulk_ws)) != MP_OK) return rcode;
   } else {
@@ -196,6 +210,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     }
   }
   CK(cudaEventRecord(S->ev_bulk_done, S->bulk));
+  trace.mark("diagonal products queued (bulk stream)");
 
   CK(cudaMemcpyAsync(d_blind, s.data(), sizeof(fr) * m, cudaMemcpyHostToDevice, st));
   if ((rcode = commit_rows_device(ctx, d_b, n, d_blind, m, n, d_g1_scal, d_g1_out)) != MP_OK) return rcode;
@@ -203,6 +218,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   ctx->launches += 1;
   CK(cudaMemcpyAsync(proof_out + L.cB, d_canon, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  trace.mark("round B: c_B on host");
   fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof_out + L.cB, m); fs.end();
   const fr y = fs.challenge();
   const fr z = fs.challenge();
@@ -227,6 +243,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(cudaEventRecord(S->ev, st));
 
   CK(cudaEventSynchronize(S->ev));  // col / rho* are on the host
+  trace.mark("round C.1: product column on host");
   std::vector<fr> col(h_col, h_col + n);
   const fr rho_star = fr_neg(h_col[n]);
   me_tau[m] = rho_star;
@@ -290,6 +307,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(cudaMemcpyAsync(proof_out + L.mepts, d_canon2 + (size_t)(m + 3) * 64, (size_t)(2 * m + 1) * 64, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  trace.mark("round C.5: commitment batch on host");
   memcpy(proof_out + L.cb, proof_out + L.hB + 64 * (size_t)(m - 1), 64);  // c_b = c_B[m-1]
   fs.begin(); fs.feed_label("hadamard_argument"); fs.feed_points64(proof_out + L.cb, 1); fs.feed_points64(proof_out + L.hB, m); fs.end();
   const fr xh = fs.challenge();
@@ -342,6 +360,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, 2 * (size_t)m + 3, st));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(proof_out + L.zpts, d_canon, (2 * (size_t)m + 3) * 64, cudaMemcpyDeviceToHost, st));
+    if (trace.on) { CK(cudaStreamSynchronize(st)); trace.mark("round D: zero-argument commitments on host"); }
     // join the bulk stream: E_k = diag_k + Enc(b_k*ghat; tau_k), needed for the last absorb below
     CK(cudaStreamWaitEvent(st, S->ev_bulk_done, 0));
     k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_enc, d_enc + 2 * m, 2 * m);
@@ -352,6 +371,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(cudaMemcpyAsync(proof_out + L.meE, d_canonE, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  trace.mark("round D + E_k on host");
   fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof_out + L.zpts, 2 * (size_t)m + 3); fs.end();
   const fr xz = fs.challenge();
   fs.begin(); fs.feed_label("single_value_product_argument"); fs.feed_points64(proof_out + L.svpts, 3); fs.end();
@@ -418,6 +438,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  trace.mark("responses on host");
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not a canonical point of the Stark curve");
   return MP_OK;
 }

@@ -171,9 +171,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
     S->aux_ws = msm_workspace_create();
   }
   if (!S->bulk) {
-    int lo = 0, hi = 0;  // lo = least priority (numerically greatest); the context's main stream is created with hi
-    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&S->bulk, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithFlags(&S->bulk, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&S->ev_bulk_go, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&S->ev_bulk_done, cudaEventDisableTiming));
     S->bulk_ws = msm_workspace_create();
