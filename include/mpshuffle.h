@@ -44,6 +44,10 @@ typedef struct mp_ctx mp_ctx;
 #define MP_VERIFY_ZERO 2
 #define MP_VERIFY_SVP 3
 #define MP_VERIFY_MULTIEXP 4
+/* sigma protocols either side of the shuffle: "Chaum-Pedersen" (reference masking.rs:103-105,
+ * remasking.rs:110-112, reveal.rs:80-82) and "Schnorr Identification" (tests.rs:72-77) */
+#define MP_VERIFY_CHAUM_PEDERSEN 5
+#define MP_VERIFY_SCHNORR 6
 /* usage / runtime errors */
 #define MP_ERR_INVALID_ARG (-1)
 #define MP_ERR_CUDA (-2)
@@ -179,6 +183,47 @@ int32_t mp_shuffle_and_remask_resident(mp_ctx* ctx, const uint8_t* pk, const uin
 int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
                                   const uint8_t* shuffled_deck, const uint32_t* perm, const uint8_t* rho,
                                   const uint8_t* randomness, uint8_t* proof_out, const void* d_shuffled_deck);
+
+/* ---- batched sigma protocols either side of the shuffle -----------
+ * n independent items per call; item i uses the i-th entry of every array.  The generator g is the
+ * ElGamal generator of mp_ctx_set_params.  Proof bytes: Chaum-Pedersen = a (64) | b (64) | r (32) =
+ * 160 bytes, Schnorr = commit (64) | opening (32) = 96 bytes.  `omega` is the prover's randomness (one
+ * scalar per proof, drawn by the caller from its own RNG in item order -- the library never owns an
+ * RNG).  statuses[i] receives MP_OK or MP_VERIFY_CHAUM_PEDERSEN / MP_VERIFY_SCHNORR.  The per-proof
+ * Fiat-Shamir transcripts run on `host_threads` CPU threads (0 = all hardware threads); a point off
+ * the curve anywhere in the batch fails the call with MP_ERR_NOT_ON_CURVE.
+ *
+ *   mp_mask_batch / mp_verify_mask_batch       BarnettSmartProtocol::mask / verify_mask
+ *                                              reference src/lib.rs:115-133, impl mod.rs:182-240
+ *   mp_remask_prove_batch / mp_verify_remask_batch   ::remask / verify_remask
+ *                                              reference src/lib.rs:136-154, impl mod.rs:242-299
+ *   mp_reveal_batch / mp_verify_reveal_batch   ::compute_reveal_token / verify_reveal (one player,
+ *                                              n masked cards)  src/lib.rs:157-175, impl mod.rs:301-354
+ *   mp_key_ownership_prove_batch / _verify_batch   ::prove_key_ownership / verify_key_ownership
+ *                                              src/lib.rs:88-104, impl mod.rs:132-165; info_offsets has
+ *                                              n + 1 entries into the concatenated public-info bytes */
+int32_t mp_mask_batch(mp_ctx* ctx, const uint8_t* shared_key /* 64 */, const uint8_t* cards /* n*64 */,
+                      const uint8_t* r /* n*32 */, const uint8_t* omega /* n*32 */, uint64_t n,
+                      uint8_t* out_masked /* n*128 */, uint8_t* out_proofs /* n*160 */, int32_t host_threads);
+int32_t mp_verify_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* masked,
+                             const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t mp_remask_prove_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck /* n*128 */,
+                              const uint8_t* alpha /* n*32 */, const uint8_t* omega /* n*32 */, uint64_t n,
+                              uint8_t* out_deck /* n*128 */, uint8_t* out_proofs /* n*160 */, int32_t host_threads);
+int32_t mp_verify_remask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* remasked,
+                               const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t mp_reveal_batch(mp_ctx* ctx, const uint8_t* sk /* 32 */, const uint8_t* pk /* 64 */,
+                        const uint8_t* masked /* n*128 */, const uint8_t* omega /* n*32 */, uint64_t n,
+                        uint8_t* out_tokens /* n*64 */, uint8_t* out_proofs /* n*160 */, int32_t host_threads);
+int32_t mp_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* tokens, const uint8_t* masked,
+                               const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t mp_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks /* n*64 */, const uint8_t* sks /* n*32 */,
+                                     const uint8_t* infos, const uint64_t* info_offsets /* n+1 */,
+                                     const uint8_t* omega /* n*32 */, uint64_t n, uint8_t* out_proofs /* n*96 */,
+                                     int32_t host_threads);
+int32_t mp_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* infos,
+                                      const uint64_t* info_offsets, const uint8_t* proofs, uint64_t n,
+                                      int32_t* statuses, int32_t host_threads);
 
 /* ---- measurement ---------------------------------------------------------------------------
  * Per-launch CUDA-event timing (on the context's stream) of the bucket-accumulation kernel, the

@@ -46,6 +46,14 @@ SIGNATURES = {
     "mp_shuffle_verify_resident": (_i32, [_vp, _cp, _cp, _cp, _cp, _vp, _vp]),
     "mp_shuffle_and_remask_resident": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp, _vp]),
     "mp_shuffle_prove_resident": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp, _vp]),
+    "mp_mask_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, _cp, _cp, _i32]),
+    "mp_verify_mask_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp_remask_prove_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, _cp, _cp, _i32]),
+    "mp_verify_remask_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp_reveal_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, _cp, _cp, _i32]),
+    "mp_verify_reveal_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp_key_ownership_prove_batch": (_i32, [_vp, _cp, _cp, _cp, ctypes.POINTER(_u64), _cp, _u64, _cp, _i32]),
+    "mp_key_ownership_verify_batch": (_i32, [_vp, _cp, _cp, ctypes.POINTER(_u64), _cp, _u64, ctypes.POINTER(_i32), _i32]),
     "mp_profile_enable": (_i32, [_vp, _i32]),
     "mp_profile_collect_dominant": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "mp_profile_collect": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
@@ -207,6 +215,73 @@ class Context:
         st = (_i32 * B)()
         check(self.h, lib.mp_shuffle_verify_batch(self.h, pk, decks, decks2, proofs, B, st, host_threads))
         return list(st)
+
+    # --- batched sigma protocols either side of the shuffle (reference mod.rs:132-354)
+    def _statuses(self, fn, n, *args, host_threads=0):
+        st = (_i32 * max(n, 1))()
+        check(self.h, fn(self.h, *args, n, st, host_threads))
+        return list(st)[:n]
+
+    def mask_batch(self, shared_key, cards, r, omega, host_threads=0):
+        """-> (masked cards n*128, Chaum-Pedersen proofs n*160)"""
+        n = len(r) // 32
+        assert len(cards) == 64 * n and len(omega) == 32 * n
+        out, proofs = ctypes.create_string_buffer(128 * n), ctypes.create_string_buffer(160 * n)
+        check(self.h, lib.mp_mask_batch(self.h, shared_key, cards, r, omega, n, out, proofs, host_threads))
+        return out.raw, proofs.raw
+
+    def verify_mask_batch(self, shared_key, cards, masked, proofs, host_threads=0):
+        n = len(proofs) // 160
+        assert len(cards) == 64 * n and len(masked) == 128 * n
+        return self._statuses(lib.mp_verify_mask_batch, n, shared_key, cards, masked, proofs, host_threads=host_threads)
+
+    def remask_prove_batch(self, shared_key, deck, alpha, omega, host_threads=0):
+        n = len(alpha) // 32
+        assert len(deck) == 128 * n and len(omega) == 32 * n
+        out, proofs = ctypes.create_string_buffer(128 * n), ctypes.create_string_buffer(160 * n)
+        check(self.h, lib.mp_remask_prove_batch(self.h, shared_key, deck, alpha, omega, n, out, proofs, host_threads))
+        return out.raw, proofs.raw
+
+    def verify_remask_batch(self, shared_key, deck, remasked, proofs, host_threads=0):
+        n = len(proofs) // 160
+        assert len(deck) == len(remasked) == 128 * n
+        return self._statuses(lib.mp_verify_remask_batch, n, shared_key, deck, remasked, proofs, host_threads=host_threads)
+
+    def reveal_batch(self, sk, pk, masked, omega, host_threads=0):
+        """-> (reveal tokens n*64, Chaum-Pedersen proofs n*160) of one player for n masked cards"""
+        n = len(omega) // 32
+        assert len(masked) == 128 * n and len(sk) == 32 and len(pk) == 64
+        tokens, proofs = ctypes.create_string_buffer(64 * n), ctypes.create_string_buffer(160 * n)
+        check(self.h, lib.mp_reveal_batch(self.h, sk, pk, masked, omega, n, tokens, proofs, host_threads))
+        return tokens.raw, proofs.raw
+
+    def verify_reveal_batch(self, pk, tokens, masked, proofs, host_threads=0):
+        n = len(proofs) // 160
+        assert len(tokens) == 64 * n and len(masked) == 128 * n
+        return self._statuses(lib.mp_verify_reveal_batch, n, pk, tokens, masked, proofs, host_threads=host_threads)
+
+    @staticmethod
+    def _infos(infos):
+        off = [0]
+        for b in infos:
+            off.append(off[-1] + len(b))
+        return b"".join(infos), (_u64 * len(off))(*off)
+
+    def key_ownership_prove_batch(self, pks, sks, infos, omega, host_threads=0):
+        n = len(infos)
+        assert len(pks) == 64 * n and len(sks) == 32 * n and len(omega) == 32 * n
+        blob, off = self._infos(infos)
+        proofs = ctypes.create_string_buffer(96 * n)
+        check(self.h, lib.mp_key_ownership_prove_batch(self.h, pks, sks, blob, off, omega, n, proofs, host_threads))
+        return proofs.raw
+
+    def key_ownership_verify_batch(self, pks, infos, proofs, host_threads=0):
+        n = len(infos)
+        assert len(pks) == 64 * n and len(proofs) == 96 * n
+        blob, off = self._infos(infos)
+        st = (_i32 * max(n, 1))()
+        check(self.h, lib.mp_key_ownership_verify_batch(self.h, pks, blob, off, proofs, n, st, host_threads))
+        return list(st)[:n]
 
     @staticmethod
     def status_string(code):

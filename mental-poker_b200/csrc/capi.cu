@@ -83,6 +83,8 @@ extern "C" const char* mp_verify_status_string(int32_t status) {
     case MP_VERIFY_ZERO: return "Zero Argument (5.2)";
     case MP_VERIFY_SVP: return "Single Value Product (5.3)";
     case MP_VERIFY_MULTIEXP: return "Multi Exponentiation (4)";
+    case MP_VERIFY_CHAUM_PEDERSEN: return "Chaum-Pedersen";
+    case MP_VERIFY_SCHNORR: return "Schnorr Identification";
     default: return "unknown";
   }
 }
@@ -301,6 +303,43 @@ extern "C" int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, con
                                              const uint8_t* shuffled_deck, const uint32_t* perm, const uint8_t* rho,
                                              const uint8_t* randomness, uint8_t* proof_out, const void* d_shuffled_deck) {
   return shuffle_prove(ctx, pk, deck, shuffled_deck, perm, rho, randomness, proof_out, d_shuffled_deck);
+}
+
+// ---- batched sigma protocols (bodies in sigma.cu)
+extern "C" int32_t mp_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* r,
+                                 const uint8_t* omega, uint64_t n, uint8_t* out_masked, uint8_t* out_proofs, int32_t host_threads) {
+  return sigma_mask_batch(ctx, shared_key, cards, r, omega, n, out_masked, out_proofs, host_threads);
+}
+extern "C" int32_t mp_verify_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* masked,
+                                        const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  return sigma_verify_mask_batch(ctx, shared_key, cards, masked, proofs, n, statuses, host_threads);
+}
+extern "C" int32_t mp_remask_prove_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* alpha,
+                                         const uint8_t* omega, uint64_t n, uint8_t* out_deck, uint8_t* out_proofs,
+                                         int32_t host_threads) {
+  return sigma_remask_prove_batch(ctx, shared_key, deck, alpha, omega, n, out_deck, out_proofs, host_threads);
+}
+extern "C" int32_t mp_verify_remask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* remasked,
+                                          const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  return sigma_verify_remask_batch(ctx, shared_key, deck, remasked, proofs, n, statuses, host_threads);
+}
+extern "C" int32_t mp_reveal_batch(mp_ctx* ctx, const uint8_t* sk, const uint8_t* pk, const uint8_t* masked, const uint8_t* omega,
+                                   uint64_t n, uint8_t* out_tokens, uint8_t* out_proofs, int32_t host_threads) {
+  return sigma_reveal_batch(ctx, sk, pk, masked, omega, n, out_tokens, out_proofs, host_threads);
+}
+extern "C" int32_t mp_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* tokens, const uint8_t* masked,
+                                          const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  return sigma_verify_reveal_batch(ctx, pk, tokens, masked, proofs, n, statuses, host_threads);
+}
+extern "C" int32_t mp_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* sks, const uint8_t* infos,
+                                                const uint64_t* info_offsets, const uint8_t* omega, uint64_t n,
+                                                uint8_t* out_proofs, int32_t host_threads) {
+  return sigma_key_ownership_prove_batch(ctx, pks, sks, infos, info_offsets, omega, n, out_proofs, host_threads);
+}
+extern "C" int32_t mp_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* infos,
+                                                 const uint64_t* info_offsets, const uint8_t* proofs, uint64_t n,
+                                                 int32_t* statuses, int32_t host_threads) {
+  return sigma_key_ownership_verify_batch(ctx, pks, infos, info_offsets, proofs, n, statuses, host_threads);
 }
 
 extern "C" int32_t mp_msm_num_windows(int32_t window_bits) {

@@ -53,6 +53,25 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
 int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
                              const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads);
 
+// Batched sigma protocols either side of the shuffle (sigma.cu)
+int32_t sigma_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* r, const uint8_t* omega,
+                         uint64_t n, uint8_t* out_masked, uint8_t* out_proofs, int32_t host_threads);
+int32_t sigma_verify_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* masked,
+                                const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t sigma_remask_prove_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* alpha,
+                                 const uint8_t* omega, uint64_t n, uint8_t* out_deck, uint8_t* out_proofs, int32_t host_threads);
+int32_t sigma_verify_remask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* remasked,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t sigma_reveal_batch(mp_ctx* ctx, const uint8_t* sk, const uint8_t* pk, const uint8_t* masked, const uint8_t* omega,
+                           uint64_t n, uint8_t* out_tokens, uint8_t* out_proofs, int32_t host_threads);
+int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* tokens, const uint8_t* masked,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t sigma_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* sks, const uint8_t* infos,
+                                        const uint64_t* info_off, const uint8_t* omega, uint64_t n, uint8_t* out_proofs,
+                                        int32_t host_threads);
+int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* infos, const uint64_t* info_off,
+                                         const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+
 bool shuffle_uses_small_deck_path(uint64_t n_cards);
 int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                             const uint8_t* rhos, const uint8_t* rands, uint64_t B, uint8_t* out_decks,

@@ -188,6 +188,8 @@ void parallel_for(size_t count, int threads, F&& fn) {
 }
 
 // shuffle_setup.cu
+// makes table 1 of ShuffleState::d_tab (8-bit fixed-base windows) the table of `pk` (cached across calls)
+int32_t shuffle_ensure_pk_table(mp_ctx* ctx, const uint8_t* pk);
 // stream / ws default to the context's; pass the auxiliary pair to overlap with other work
 int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_bad, cudaStream_t stream = nullptr,
                     MsmWorkspace* ws = nullptr);

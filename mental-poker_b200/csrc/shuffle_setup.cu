@@ -120,6 +120,26 @@ static cudaError_t build_table(ShuffleState* S, int which, const uint8_t* d_base
   return cudaGetLastError();
 }
 
+int32_t shuffle_ensure_pk_table(mp_ctx* ctx, const uint8_t* pk) {
+  ShuffleState* S = ctx->shuffle;
+  if (S->tab_pk_valid && memcmp(S->tab_pk, pk, 64) == 0) return MP_OK;
+  uint8_t* d_pk = (uint8_t*)ctx->scratch(sSmallUp, 256);
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_pk); NEED(d_bad);
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(build_table(S, 1, d_pk, d_bad, ctx->stream));
+  ctx->launches += 1;
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  S->tab_pk_valid = false;
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not on the Stark curve");
+  memcpy(S->tab_pk, pk, 64);
+  S->tab_pk_valid = true;
+  return MP_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // set-up
 // ------------------------------------------------------------------------------------------

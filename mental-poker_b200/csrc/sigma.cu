@@ -1,0 +1,528 @@
+// Batched sigma protocols either side of the shuffle in a Barnett-Smart round (SURVEY.md section
+// 8(f), rank 1): mask / remask / reveal with their Chaum-Pedersen proofs and the Schnorr key-ownership
+// proof, for n independent items per call.  Reference call sites: src/discrete_log_cards/mod.rs:132-354
+// (one proof per call, each 2-4 scalar multiplications inside the un-vendored proof-essentials crate).
+//
+// Division of labour as for the shuffle: the host owns the per-proof Fiat-Shamir transcripts
+// (sigma_host.hpp; n small Blake2s + ChaCha20 evaluations spread over host threads) and the response
+// scalars; every group operation runs in ONE kernel family, k_lincomb: a thread evaluates
+//     out = k0*P0 + k1*P1 + f0*g + f1*pk + A - S
+// with P0, P1, A, S points of a per-call arena (variable bases: interleaved double-and-add over the two
+// scalars), g / pk through the 8-bit fixed-base window tables the remask kernel already uses (32 table
+// additions per scalar).  Provers read results back as canonical points; verifiers only need "is it
+// the identity", so their check jobs never invert.  Jobs are laid out kind-major (all c1 jobs, then
+// all c2 jobs, ...) so a warp runs one shape.
+#include <thread>
+
+#include "shuffle_internal.cuh"
+#include "sigma_host.hpp"
+
+namespace mp {
+
+static constexpr uint32_t kNone = 0xffffffffu;
+struct LcJob {
+  uint32_t var_pt[2];  // arena indices of the variable bases (kNone = unused)
+  uint32_t var_sc[2];  // scalar indices for them
+  uint32_t fix_sc[2];  // scalar indices for the fixed bases g (0) and pk (1)
+  uint32_t add_pt, sub_pt;  // arena points added with coefficient +1 / -1
+  uint32_t out_pt;     // arena slot that receives the (affine) result, or kNone
+};
+
+static constexpr int kTabWin8 = 32, kTabDigits8 = 255, kTabSize8 = kTabWin8 * kTabDigits8;  // layout of ShuffleState::d_tab
+
+__device__ __forceinline__ void ld_scalar(const uint32_t* scal, uint32_t idx, uint32_t k[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(scal + (size_t)idx * 8);
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
+}
+__device__ __forceinline__ affine ld_point(const affine* p) {
+  affine r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) d[i] = s[i];
+  return r;
+}
+static __device__ __noinline__ void madd_call(xyzz& acc, const affine& q) { xyzz_madd(acc, q); }
+static __device__ __noinline__ void dbl_call(xyzz& acc) { acc = xyzz_dbl(acc); }
+
+// flags: 1 = write canonical bytes to out_canon[job], 2 = write identity flag to out_flag[job]
+__global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs, uint32_t njobs, affine* __restrict__ arena,
+                                                 const uint32_t* __restrict__ scal, const affine* __restrict__ tab, int flags,
+                                                 uint32_t* __restrict__ out_canon, uint8_t* __restrict__ out_flag) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= njobs) return;
+  const LcJob j = jobs[g];
+  xyzz acc = xyzz_identity();
+  if (j.var_pt[0] != kNone) {
+    uint32_t k0[8], k1[8];
+    ld_scalar(scal, j.var_sc[0], k0);
+    const affine P0 = ld_point(arena + j.var_pt[0]);
+    affine P1 = P0;
+    const bool two = j.var_pt[1] != kNone;
+    if (two) {
+      ld_scalar(scal, j.var_sc[1], k1);
+      P1 = ld_point(arena + j.var_pt[1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) k1[i] = 0;
+    }
+    int top = -1;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+      const uint32_t w = k0[i] | k1[i];
+      if (top < 0 && w) top = 32 * i + 31 - __clz(w);
+    }
+#pragma unroll 1
+    for (int bit = top; bit >= 0; bit--) {
+      dbl_call(acc);
+      if ((k0[bit >> 5] >> (bit & 31)) & 1) madd_call(acc, P0);
+      if ((k1[bit >> 5] >> (bit & 31)) & 1) madd_call(acc, P1);
+    }
+  }
+#pragma unroll 1
+  for (int f = 0; f < 2; f++) {
+    if (j.fix_sc[f] == kNone) continue;
+    uint32_t k[8];
+    ld_scalar(scal, j.fix_sc[f], k);
+    const affine* T = tab + (size_t)f * kTabSize8;
+#pragma unroll 1
+    for (int w = 0; w < kTabWin8; w++) {
+      const uint32_t d = (k[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+      if (d) {
+        affine e;
+        const uint4* s = reinterpret_cast<const uint4*>(T + w * kTabDigits8 + (d - 1));
+        uint4* dst = reinterpret_cast<uint4*>(&e);
+#pragma unroll
+        for (int q = 0; q < 4; q++) dst[q] = __ldg(s + q);
+        madd_call(acc, e);
+      }
+    }
+  }
+  if (j.add_pt != kNone) madd_call(acc, ld_point(arena + j.add_pt));
+  if (j.sub_pt != kNone) madd_call(acc, affine_neg(ld_point(arena + j.sub_pt)));
+  if (flags & 2) out_flag[g] = xyzz_is_identity(acc) ? 1 : 0;
+  if ((flags & 1) || j.out_pt != kNone) {
+    const affine r = xyzz_to_affine(acc);  // identity -> (0, 0)
+    if (j.out_pt != kNone) {
+      uint4* d = reinterpret_cast<uint4*>(arena + j.out_pt);
+      const uint4* s = reinterpret_cast<const uint4*>(&r);
+#pragma unroll
+      for (int q = 0; q < 4; q++) d[q] = s[q];
+    }
+    if (flags & 1) {
+      uint32_t w[16];
+      if (affine_is_identity(r)) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) w[q] = 0;
+      } else {
+        affine_to_canonical(r, w);
+      }
+      uint4* o = reinterpret_cast<uint4*>(out_canon + (size_t)g * 16);
+#pragma unroll
+      for (int q = 0; q < 4; q++) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags };
+
+static LcJob job_none() {
+  LcJob j;
+  j.var_pt[0] = j.var_pt[1] = j.var_sc[0] = j.var_sc[1] = j.fix_sc[0] = j.fix_sc[1] = kNone;
+  j.add_pt = j.sub_pt = j.out_pt = kNone;
+  return j;
+}
+
+// One batched call: a point arena (uploaded canonical points -> Montgomery, plus reserved result slots),
+// a scalar array, and launches of k_lincomb over host-built job lists.
+struct SigmaCall {
+  mp_ctx* ctx;
+  ShuffleState* S;
+  cudaStream_t st;
+  uint64_t n_in = 0, n_arena = 0, n_scal = 0;
+  uint8_t* d_canon = nullptr;
+  affine* d_arena = nullptr;
+  uint32_t* d_scal = nullptr;
+  int* d_bad = nullptr;
+
+  int32_t init(mp_ctx* c, uint64_t in_points, uint64_t reserved_points, uint64_t scalars) {
+    ctx = c;
+    S = c->shuffle;
+    st = c->stream;
+    n_in = in_points;
+    n_arena = in_points + reserved_points;
+    n_scal = scalars;
+    d_canon = (uint8_t*)ctx->scratch(sSigCanon, n_in * 64 + 64);
+    d_arena = (affine*)ctx->scratch(sSigArena, n_arena * sizeof(affine) + 64);
+    d_scal = (uint32_t*)ctx->scratch(sSigScal, n_scal * 32 + 64);
+    d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+    NEED(d_canon); NEED(d_arena); NEED(d_scal); NEED(d_bad);
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    return MP_OK;
+  }
+  // `count` points, `src_pitch` bytes apart, `width` = 64 * (points per record), into arena slot `first`
+  int32_t put_points(uint64_t first, const uint8_t* src, uint64_t records, size_t width, size_t src_pitch) {
+    if (!records) return MP_OK;
+    CK(cudaMemcpy2DAsync(d_canon + first * 64, width, src, src_pitch, width, records, cudaMemcpyHostToDevice, st));
+    return MP_OK;
+  }
+  int32_t put_scalars(uint64_t first, const uint8_t* src, uint64_t count, size_t src_pitch = 32) {
+    if (!count) return MP_OK;
+    CK(cudaMemcpy2DAsync(d_scal + first * 8, 32, src, src_pitch, 32, count, cudaMemcpyHostToDevice, st));
+    return MP_OK;
+  }
+  int32_t ingest() {  // canonical -> Montgomery, canonical + on-curve validation
+    CK(points_to_mont((const uint32_t*)d_canon, d_arena, n_in, d_bad, st));
+    ctx->launches += 1;
+    return MP_OK;
+  }
+  // runs the jobs; canonical results (64 B per job) to h_canon and/or identity flags to h_flags
+  int32_t run(const std::vector<LcJob>& jobs, uint8_t* h_canon, uint8_t* h_flags) {
+    const uint32_t nj = (uint32_t)jobs.size();
+    if (!nj) return MP_OK;
+    LcJob* d_jobs = (LcJob*)ctx->scratch(sSigJobs, (size_t)nj * sizeof(LcJob));
+    uint32_t* d_out = h_canon ? (uint32_t*)ctx->scratch(sSigOut, (size_t)nj * 64) : nullptr;
+    uint8_t* d_flags = h_flags ? (uint8_t*)ctx->scratch(sSigFlags, (size_t)nj + 64) : nullptr;
+    NEED(d_jobs);
+    if (h_canon) NEED(d_out);
+    if (h_flags) NEED(d_flags);
+    CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(LcJob), cudaMemcpyHostToDevice, st));
+    k_lincomb<<<(nj + 127) / 128, 128, 0, st>>>(d_jobs, nj, d_arena, d_scal, S->d_tab, (h_canon ? 1 : 0) | (h_flags ? 2 : 0), d_out,
+                                                d_flags);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    if (h_canon) CK(cudaMemcpyAsync(h_canon, d_out, (size_t)nj * 64, cudaMemcpyDeviceToHost, st));
+    if (h_flags) CK(cudaMemcpyAsync(h_flags, d_flags, (size_t)nj, cudaMemcpyDeviceToHost, st));
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of the Stark curve");
+    return MP_OK;
+  }
+};
+
+static int32_t sigma_begin(mp_ctx* ctx, uint64_t n) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  if (!ctx->shuffle || ctx->shuffle->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
+  if (n >= (1ull << 27)) return ctx->fail(MP_ERR_INVALID_ARG, "batch too large");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  return MP_OK;
+}
+static int host_thread_count(int32_t host_threads, uint64_t n) {
+  int t = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+  t = std::max(1, std::min(t, 64));
+  return (int)std::min<uint64_t>((uint64_t)t, std::max<uint64_t>(1, n / 64));
+}
+// fn(i) for i < n on `threads` host threads, contiguous ranges
+template <typename F>
+static void for_items(uint64_t n, int threads, F&& fn) {
+  if (threads <= 1) {
+    for (uint64_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++)
+    pool.emplace_back([&, t] {
+      const uint64_t b = n * t / threads, e = n * (t + 1) / threads;
+      for (uint64_t i = b; i < e; i++) fn(i);
+    });
+  for (auto& th : pool) th.join();
+}
+
+// ---- Chaum-Pedersen over the fixed parameters (g, pk): mask and remask ------------------------
+// remask = false: statement (c1, c2 - card), outputs masked = (r g, card + r pk)       (mod.rs:182-214)
+// remask = true : statement (a g, a pk) = out - in, outputs out = in + (a g, a pk)      (mod.rs:242-272)
+static int32_t cp_fixed_prove(mp_ctx* ctx, bool remask, const uint8_t* pk, const uint8_t* in, const uint8_t* wit,
+                              const uint8_t* omega, uint64_t n, uint8_t* out, uint8_t* proofs, int32_t host_threads) {
+  int32_t rc = sigma_begin(ctx, n);
+  if (rc != MP_OK) return rc;
+  if (!pk || (n && (!in || !wit || !omega || !out || !proofs))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MP_OK;
+  if ((rc = shuffle_ensure_pk_table(ctx, pk)) != MP_OK) return rc;
+  const uint64_t per = remask ? 2 : 1;  // input points per item
+  SigmaCall sc;
+  if ((rc = sc.init(ctx, per * n, 0, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.put_points(0, in, n, 64 * per, 64 * per)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(0, wit, n)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(n, omega, n)) != MP_OK) return rc;
+  if ((rc = sc.ingest()) != MP_OK) return rc;
+  // kinds: 0 s0 = w g | 1 s1 = w pk | 2 a = omega g | 3 b = omega pk | 4 out.c1 | 5 out.c2
+  //   mask:   out.c1 = s0 (no extra job), out.c2 = card + w pk
+  //   remask: out.c1 = in.c1 + w g,       out.c2 = in.c2 + w pk
+  const int kinds = remask ? 6 : 5;
+  std::vector<LcJob> jobs((size_t)kinds * n, job_none());
+  for (uint64_t i = 0; i < n; i++) {
+    const uint32_t w = (uint32_t)i, om = (uint32_t)(n + i);
+    jobs[0 * n + i].fix_sc[0] = w;
+    jobs[1 * n + i].fix_sc[1] = w;
+    jobs[2 * n + i].fix_sc[0] = om;
+    jobs[3 * n + i].fix_sc[1] = om;
+    if (remask) {
+      jobs[4 * n + i].fix_sc[0] = w; jobs[4 * n + i].add_pt = (uint32_t)(2 * i);
+      jobs[5 * n + i].fix_sc[1] = w; jobs[5 * n + i].add_pt = (uint32_t)(2 * i + 1);
+    } else {
+      jobs[4 * n + i].fix_sc[1] = w; jobs[4 * n + i].add_pt = (uint32_t)i;
+    }
+  }
+  std::vector<uint8_t> res((size_t)kinds * n * 64);
+  if ((rc = sc.run(jobs, res.data(), nullptr)) != MP_OK) return rc;
+  const ShuffleState* S = ctx->shuffle;
+  const char* seed = remask ? kSeedRemasking : kSeedMasking;
+  const Transcript seeded(seed, strlen(seed));
+  auto R = [&](int kind, uint64_t i) { return res.data() + ((size_t)kind * n + i) * 64; };
+  for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
+    const fr c = cp_challenge(seeded, S->enc_g, pk, R(0, i), R(1, i), R(2, i), R(3, i));
+    const fr r = fr_add(fr_from_bytes(omega + 32 * i), fr_mul(c, fr_from_bytes(wit + 32 * i)));
+    uint8_t* p = proofs + kCpProofLen * i;
+    memcpy(p, R(2, i), 64);
+    memcpy(p + 64, R(3, i), 64);
+    fr_to_bytes(r, p + 128);
+    if (remask) {
+      memcpy(out + 128 * i, R(4, i), 64);
+      memcpy(out + 128 * i + 64, R(5, i), 64);
+    } else {
+      memcpy(out + 128 * i, R(0, i), 64);
+      memcpy(out + 128 * i + 64, R(4, i), 64);
+    }
+  });
+  return MP_OK;
+}
+
+static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, const uint8_t* in, const uint8_t* out,
+                               const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  int32_t rc = sigma_begin(ctx, n);
+  if (rc != MP_OK) return rc;
+  if (!pk || (n && (!in || !out || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MP_OK;
+  if ((rc = shuffle_ensure_pk_table(ctx, pk)) != MP_OK) return rc;
+  // arena: [inputs: n or 2n] [outputs: 2n] [a, b: 2n] | reserved statement slots [s0, s1: 2n]
+  const uint64_t per = remask ? 2 : 1;
+  const uint64_t oIn = 0, oOut = per * n, oAB = oOut + 2 * n, oS = oAB + 2 * n;
+  SigmaCall sc;
+  if ((rc = sc.init(ctx, oS, 2 * n, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oIn, in, n, 64 * per, 64 * per)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oOut, out, n, 128, 128)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oAB, proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(0, proofs + 128, n, kCpProofLen)) != MP_OK) return rc;  // responses r
+  if ((rc = sc.ingest()) != MP_OK) return rc;
+  // pass 1: the statement.  mask: s0 = out.c1 (no job), s1 = out.c2 - card;  remask: s = out - in
+  std::vector<LcJob> jobs;
+  std::vector<uint8_t> stmt;
+  if (remask) {
+    jobs.assign(2 * n, job_none());
+    for (uint64_t i = 0; i < n; i++)
+      for (int k = 0; k < 2; k++) {
+        LcJob& j = jobs[(size_t)k * n + i];
+        j.add_pt = (uint32_t)(oOut + 2 * i + k);
+        j.sub_pt = (uint32_t)(oIn + 2 * i + k);
+        j.out_pt = (uint32_t)(oS + (size_t)k * n + i);
+      }
+  } else {
+    jobs.assign(n, job_none());
+    for (uint64_t i = 0; i < n; i++) {
+      jobs[i].add_pt = (uint32_t)(oOut + 2 * i + 1);
+      jobs[i].sub_pt = (uint32_t)(oIn + i);
+      jobs[i].out_pt = (uint32_t)(oS + n + i);
+    }
+  }
+  stmt.resize(jobs.size() * 64);
+  if ((rc = sc.run(jobs, stmt.data(), nullptr)) != MP_OK) return rc;
+  // challenges (host), uploaded negated:  r g - c s0 - a == O  and  r pk - c s1 - b == O
+  const ShuffleState* S = ctx->shuffle;
+  const char* seed = remask ? kSeedRemasking : kSeedMasking;
+  const Transcript seeded(seed, strlen(seed));
+  std::vector<uint8_t> negc((size_t)n * 32);
+  std::vector<uint8_t> canon_ok((size_t)n);
+  for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
+    const uint8_t* p = proofs + kCpProofLen * i;
+    const uint8_t* s0 = remask ? stmt.data() + 64 * i : out + 128 * i;
+    const uint8_t* s1 = remask ? stmt.data() + 64 * (n + i) : stmt.data() + 64 * i;
+    const fr c = cp_challenge(seeded, S->enc_g, pk, s0, s1, p, p + 64);
+    fr_to_bytes(fr_neg(c), negc.data() + 32 * i);
+    canon_ok[i] = fr_bytes_canonical(p + 128);
+  });
+  if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;
+  jobs.assign(2 * n, job_none());
+  for (uint64_t i = 0; i < n; i++) {
+    LcJob& j0 = jobs[i];
+    j0.fix_sc[0] = (uint32_t)i;
+    j0.var_pt[0] = remask ? (uint32_t)(oS + i) : (uint32_t)(oOut + 2 * i);
+    j0.var_sc[0] = (uint32_t)(n + i);
+    j0.sub_pt = (uint32_t)(oAB + 2 * i);
+    LcJob& j1 = jobs[n + i];
+    j1.fix_sc[1] = (uint32_t)i;
+    j1.var_pt[0] = (uint32_t)(oS + n + i);
+    j1.var_sc[0] = (uint32_t)(n + i);
+    j1.sub_pt = (uint32_t)(oAB + 2 * i + 1);
+  }
+  std::vector<uint8_t> flags(2 * n);
+  if ((rc = sc.run(jobs, nullptr, flags.data())) != MP_OK) return rc;
+  for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
+  return MP_OK;
+}
+
+int32_t sigma_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* r, const uint8_t* omega,
+                         uint64_t n, uint8_t* out_masked, uint8_t* out_proofs, int32_t host_threads) {
+  return cp_fixed_prove(ctx, false, shared_key, cards, r, omega, n, out_masked, out_proofs, host_threads);
+}
+int32_t sigma_verify_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* masked,
+                                const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  return cp_fixed_verify(ctx, false, shared_key, cards, masked, proofs, n, statuses, host_threads);
+}
+int32_t sigma_remask_prove_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* alpha,
+                                 const uint8_t* omega, uint64_t n, uint8_t* out_deck, uint8_t* out_proofs, int32_t host_threads) {
+  return cp_fixed_prove(ctx, true, shared_key, deck, alpha, omega, n, out_deck, out_proofs, host_threads);
+}
+int32_t sigma_verify_remask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* remasked,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  return cp_fixed_verify(ctx, true, shared_key, deck, remasked, proofs, n, statuses, host_threads);
+}
+
+// ---- reveal tokens of one player (mod.rs:301-354): parameters (masked.c1, g), statement (token, pk) ----
+int32_t sigma_reveal_batch(mp_ctx* ctx, const uint8_t* sk, const uint8_t* pk, const uint8_t* masked, const uint8_t* omega,
+                           uint64_t n, uint8_t* out_tokens, uint8_t* out_proofs, int32_t host_threads) {
+  int32_t rc = sigma_begin(ctx, n);
+  if (rc != MP_OK) return rc;
+  if (!sk || !pk || (n && (!masked || !omega || !out_tokens || !out_proofs))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MP_OK;
+  SigmaCall sc;
+  if ((rc = sc.init(ctx, n, 0, n + 1)) != MP_OK) return rc;
+  if ((rc = sc.put_points(0, masked, n, 64, 128)) != MP_OK) return rc;  // c1 of every card
+  if ((rc = sc.put_scalars(0, omega, n)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(n, sk, 1)) != MP_OK) return rc;
+  if ((rc = sc.ingest()) != MP_OK) return rc;
+  std::vector<LcJob> jobs(3 * n, job_none());  // kinds: token = sk c1 | a = omega c1 | b = omega g
+  for (uint64_t i = 0; i < n; i++) {
+    jobs[i].var_pt[0] = (uint32_t)i; jobs[i].var_sc[0] = (uint32_t)n;
+    jobs[n + i].var_pt[0] = (uint32_t)i; jobs[n + i].var_sc[0] = (uint32_t)i;
+    jobs[2 * n + i].fix_sc[0] = (uint32_t)i;
+  }
+  std::vector<uint8_t> res(3 * n * 64);
+  if ((rc = sc.run(jobs, res.data(), nullptr)) != MP_OK) return rc;
+  const ShuffleState* S = ctx->shuffle;
+  const Transcript seeded(kSeedReveal, strlen(kSeedReveal));
+  const fr skf = fr_from_bytes(sk);
+  for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
+    const uint8_t *tok = res.data() + 64 * i, *a = res.data() + 64 * (n + i), *b = res.data() + 64 * (2 * n + i);
+    const fr c = cp_challenge(seeded, masked + 128 * i, S->enc_g, tok, pk, a, b);
+    const fr r = fr_add(fr_from_bytes(omega + 32 * i), fr_mul(c, skf));
+    memcpy(out_tokens + 64 * i, tok, 64);
+    uint8_t* p = out_proofs + kCpProofLen * i;
+    memcpy(p, a, 64);
+    memcpy(p + 64, b, 64);
+    fr_to_bytes(r, p + 128);
+  });
+  return MP_OK;
+}
+
+int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* tokens, const uint8_t* masked,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  int32_t rc = sigma_begin(ctx, n);
+  if (rc != MP_OK) return rc;
+  if (!pk || (n && (!tokens || !masked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MP_OK;
+  // arena: [c1: n] [tokens: n] [a, b: 2n] [pk]
+  const uint64_t oC1 = 0, oTok = n, oAB = 2 * n, oPk = 4 * n;
+  SigmaCall sc;
+  if ((rc = sc.init(ctx, 4 * n + 1, 0, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oC1, masked, n, 64, 128)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oTok, tokens, n, 64, 64)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oAB, proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oPk, pk, 1, 64, 64)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(0, proofs + 128, n, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.ingest()) != MP_OK) return rc;
+  const ShuffleState* S = ctx->shuffle;
+  const Transcript seeded(kSeedReveal, strlen(kSeedReveal));
+  std::vector<uint8_t> negc((size_t)n * 32), canon_ok((size_t)n);
+  for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {  // overlaps the uploads
+    const uint8_t* p = proofs + kCpProofLen * i;
+    const fr c = cp_challenge(seeded, masked + 128 * i, S->enc_g, tokens + 64 * i, pk, p, p + 64);
+    fr_to_bytes(fr_neg(c), negc.data() + 32 * i);
+    canon_ok[i] = fr_bytes_canonical(p + 128);
+  });
+  if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;
+  std::vector<LcJob> jobs(2 * n, job_none());  // r c1 - c token - a  |  r g - c pk - b
+  for (uint64_t i = 0; i < n; i++) {
+    LcJob& j0 = jobs[i];
+    j0.var_pt[0] = (uint32_t)(oC1 + i); j0.var_sc[0] = (uint32_t)i;
+    j0.var_pt[1] = (uint32_t)(oTok + i); j0.var_sc[1] = (uint32_t)(n + i);
+    j0.sub_pt = (uint32_t)(oAB + 2 * i);
+    LcJob& j1 = jobs[n + i];
+    j1.fix_sc[0] = (uint32_t)i;
+    j1.var_pt[0] = (uint32_t)oPk; j1.var_sc[0] = (uint32_t)(n + i);
+    j1.sub_pt = (uint32_t)(oAB + 2 * i + 1);
+  }
+  std::vector<uint8_t> flags(2 * n);
+  if ((rc = sc.run(jobs, nullptr, flags.data())) != MP_OK) return rc;
+  for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
+  return MP_OK;
+}
+
+// ---- Schnorr key ownership (mod.rs:132-165) --------------------------------------------------------
+int32_t sigma_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* sks, const uint8_t* infos,
+                                        const uint64_t* info_off, const uint8_t* omega, uint64_t n, uint8_t* out_proofs,
+                                        int32_t host_threads) {
+  int32_t rc = sigma_begin(ctx, n);
+  if (rc != MP_OK) return rc;
+  if (n && (!pks || !sks || !info_off || !omega || !out_proofs)) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MP_OK;
+  SigmaCall sc;
+  if ((rc = sc.init(ctx, 0, 0, n)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(0, omega, n)) != MP_OK) return rc;
+  std::vector<LcJob> jobs(n, job_none());  // commit = omega g
+  for (uint64_t i = 0; i < n; i++) jobs[i].fix_sc[0] = (uint32_t)i;
+  std::vector<uint8_t> res(n * 64);
+  if ((rc = sc.run(jobs, res.data(), nullptr)) != MP_OK) return rc;
+  const ShuffleState* S = ctx->shuffle;
+  for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
+    const uint8_t* commit = res.data() + 64 * i;
+    const fr c = schnorr_challenge(infos ? infos + info_off[i] : nullptr, (size_t)(info_off[i + 1] - info_off[i]), S->enc_g,
+                                   pks + 64 * i, commit);
+    const fr op = fr_sub(fr_from_bytes(omega + 32 * i), fr_mul(c, fr_from_bytes(sks + 32 * i)));
+    uint8_t* p = out_proofs + kSchnorrProofLen * i;
+    memcpy(p, commit, 64);
+    fr_to_bytes(op, p + 64);
+  });
+  return MP_OK;
+}
+
+int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* infos, const uint64_t* info_off,
+                                         const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  int32_t rc = sigma_begin(ctx, n);
+  if (rc != MP_OK) return rc;
+  if (n && (!pks || !info_off || !proofs || !statuses)) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MP_OK;
+  SigmaCall sc;  // arena: [pk: n] [commit: n];  scalars: [opening: n] [c: n]
+  if ((rc = sc.init(ctx, 2 * n, 0, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.put_points(0, pks, n, 64, 64)) != MP_OK) return rc;
+  if ((rc = sc.put_points(n, proofs, n, 64, kSchnorrProofLen)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(0, proofs + 64, n, kSchnorrProofLen)) != MP_OK) return rc;
+  if ((rc = sc.ingest()) != MP_OK) return rc;
+  const ShuffleState* S = ctx->shuffle;
+  std::vector<uint8_t> cs((size_t)n * 32), canon_ok((size_t)n);
+  for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
+    const uint8_t* p = proofs + kSchnorrProofLen * i;
+    const fr c = schnorr_challenge(infos ? infos + info_off[i] : nullptr, (size_t)(info_off[i + 1] - info_off[i]), S->enc_g,
+                                   pks + 64 * i, p);
+    fr_to_bytes(c, cs.data() + 32 * i);
+    canon_ok[i] = fr_bytes_canonical(p + 64);
+  });
+  if ((rc = sc.put_scalars(n, cs.data(), n)) != MP_OK) return rc;
+  std::vector<LcJob> jobs(n, job_none());  // opening g + c pk - commit == O
+  for (uint64_t i = 0; i < n; i++) {
+    jobs[i].fix_sc[0] = (uint32_t)i;
+    jobs[i].var_pt[0] = (uint32_t)i; jobs[i].var_sc[0] = (uint32_t)(n + i);
+    jobs[i].sub_pt = (uint32_t)(n + i);
+  }
+  std::vector<uint8_t> flags(n);
+  if ((rc = sc.run(jobs, nullptr, flags.data())) != MP_OK) return rc;
+  for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && canon_ok[i]) ? MP_OK : MP_VERIFY_SCHNORR;
+  return MP_OK;
+}
+
+}  // namespace mp

@@ -317,9 +317,11 @@ class ChaCha20Stream {
 class Transcript {
  public:
   // FiatShamirRng::<Blake2s>::from_seed(&to_bytes![SHUFFLE_RNG_SEED])   mod.rs:84,408,436
-  Transcript() {
+  Transcript() : Transcript("Shuffle Proof", 13) {}
+  // from_seed for the other proof types (mod.rs:80-83: "Key Ownership Proof" || info, "Masking Proof", ...)
+  Transcript(const void* seed, size_t len) {
     Blake2s h;
-    h.update("Shuffle Proof", 13);
+    h.update(seed, len);
     h.finish(seed_);
     rng_.seed(seed_);
   }

@@ -922,3 +922,202 @@ void oc_fs_challenges(const uint8_t* data, uint64_t len, int count, uint8_t* out
   if (len) { fs_absorb_begin(&fs); fs_absorb_feed(&fs, data, len); fs_absorb_end(&fs); }
   for (int i = 0; i < count; i++) { fe c; fs_challenge(&fs, &c, &FR); fe_to_bytes(out + 32 * i, &c, &FR); }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Sigma protocols either side of the shuffle: Schnorr key ownership
+ * (reference mod.rs:132-165) and Chaum-Pedersen DL equality behind mask / remask / reveal
+ * (mod.rs:182-354; seeds mod.rs:80-83).  Bodies restated as in oracle/py/sigma.py
+ * [UPSTREAM-RECALL]; PARITY UNPINNED against upstream bytes.  Batch entry points, one proof per
+ * item, OpenMP over items: the CPU baseline of the batched GPU entry points.
+ * ------------------------------------------------------------------------------------------ */
+static void pt_sub(aff* out, const aff* a, const aff* b) {
+  aff nb = *b;
+  if (!nb.inf) fe_neg(&nb.y, &nb.y, &FQ);
+  pt_add(out, a, &nb);
+}
+static void cp_challenge(fe* c, const char* seed, const aff* g, const aff* h, const aff* s0, const aff* s1, const aff* a,
+                         const aff* b) {
+  fsrng_t fs;
+  fs_from_seed(&fs, (const uint8_t*)seed, strlen(seed));
+  fs_absorb_begin(&fs);
+  feed_label(&fs, "chaum_pedersen");
+  feed_pts(&fs, g, 1); feed_pts(&fs, h, 1); feed_pts(&fs, s0, 1); feed_pts(&fs, s1, 1); feed_pts(&fs, a, 1); feed_pts(&fs, b, 1);
+  fs_absorb_end(&fs);
+  fs_challenge(&fs, c, &FR);
+}
+/* proof = a (64) | b (64) | r (32) */
+static void cp_prove(uint8_t* proof, const char* seed, const aff* g, const aff* h, const aff* s0, const aff* s1, const fe* x,
+                     const fe* omega) {
+  aff a, b;
+  fe c, r;
+  pt_mul(&a, g, omega);
+  pt_mul(&b, h, omega);
+  cp_challenge(&c, seed, g, h, s0, s1, &a, &b);
+  fe_mul(&r, &c, x, &FR);
+  fe_add(&r, &r, omega, &FR);
+  aff_to_bytes64(proof, &a);
+  aff_to_bytes64(proof + 64, &b);
+  fe_to_bytes(proof + 128, &r, &FR);
+}
+static int cp_verify(const uint8_t* proof, const char* seed, const aff* g, const aff* h, const aff* s0, const aff* s1) {
+  aff a, b, l, t, rr;
+  fe c, r;
+  aff_from_bytes64(&a, proof);
+  aff_from_bytes64(&b, proof + 64);
+  fe_from_bytes(&r, proof + 128, &FR);
+  cp_challenge(&c, seed, g, h, s0, s1, &a, &b);
+  pt_mul(&l, g, &r); pt_mul(&t, s0, &c); pt_add(&rr, &a, &t);
+  if (!aff_eq(&l, &rr)) return 5;
+  pt_mul(&l, h, &r); pt_mul(&t, s1, &c); pt_add(&rr, &b, &t);
+  return aff_eq(&l, &rr) ? 0 : 5;
+}
+
+#define SIGMA_FOR(i, n) _Pragma("omp parallel for schedule(dynamic, 8) num_threads(g_threads)") for (int64_t i = 0; i < (int64_t)(n); i++)
+
+/* mask: masked_i = (r_i*g, card_i + r_i*pk); proof of mod.rs:182-214 */
+int oc_mask_batch(const uint8_t* g64, const uint8_t* pk64, const uint8_t* cards, const uint8_t* rs, const uint8_t* omegas,
+                  uint64_t n, uint8_t* out_masked, uint8_t* out_proofs) {
+  oracle_init();
+  aff g, pk;
+  aff_from_bytes64(&g, g64); aff_from_bytes64(&pk, pk64);
+  SIGMA_FOR(i, n) {
+    aff card, c1, t, c2;
+    fe r, om;
+    aff_from_bytes64(&card, cards + 64 * i);
+    fe_from_bytes(&r, rs + 32 * i, &FR); fe_from_bytes(&om, omegas + 32 * i, &FR);
+    pt_mul(&c1, &g, &r); pt_mul(&t, &pk, &r); pt_add(&c2, &card, &t);
+    aff_to_bytes64(out_masked + 128 * i, &c1); aff_to_bytes64(out_masked + 128 * i + 64, &c2);
+    cp_prove(out_proofs + 160 * i, "Masking Proof", &g, &pk, &c1, &t, &r, &om);
+  }
+  return 0;
+}
+int oc_verify_mask_batch(const uint8_t* g64, const uint8_t* pk64, const uint8_t* cards, const uint8_t* masked,
+                         const uint8_t* proofs, uint64_t n, int32_t* statuses) {
+  oracle_init();
+  aff g, pk;
+  aff_from_bytes64(&g, g64); aff_from_bytes64(&pk, pk64);
+  SIGMA_FOR(i, n) {
+    aff card, c1, c2, s1;
+    aff_from_bytes64(&card, cards + 64 * i);
+    aff_from_bytes64(&c1, masked + 128 * i); aff_from_bytes64(&c2, masked + 128 * i + 64);
+    pt_sub(&s1, &c2, &card);
+    statuses[i] = cp_verify(proofs + 160 * i, "Masking Proof", &g, &pk, &c1, &s1);
+  }
+  return 0;
+}
+/* remask (no permutation: the reference's per-card remask, mod.rs:242-272) */
+int oc_remask_prove_batch(const uint8_t* g64, const uint8_t* pk64, const uint8_t* deck, const uint8_t* alphas,
+                          const uint8_t* omegas, uint64_t n, uint8_t* out_deck, uint8_t* out_proofs) {
+  oracle_init();
+  aff g, pk;
+  aff_from_bytes64(&g, g64); aff_from_bytes64(&pk, pk64);
+  SIGMA_FOR(i, n) {
+    aff c1, c2, s0, s1, o1, o2;
+    fe al, om;
+    aff_from_bytes64(&c1, deck + 128 * i); aff_from_bytes64(&c2, deck + 128 * i + 64);
+    fe_from_bytes(&al, alphas + 32 * i, &FR); fe_from_bytes(&om, omegas + 32 * i, &FR);
+    pt_mul(&s0, &g, &al); pt_mul(&s1, &pk, &al);
+    pt_add(&o1, &c1, &s0); pt_add(&o2, &c2, &s1);
+    aff_to_bytes64(out_deck + 128 * i, &o1); aff_to_bytes64(out_deck + 128 * i + 64, &o2);
+    cp_prove(out_proofs + 160 * i, "Remasking Proof", &g, &pk, &s0, &s1, &al, &om);
+  }
+  return 0;
+}
+int oc_verify_remask_batch(const uint8_t* g64, const uint8_t* pk64, const uint8_t* deck, const uint8_t* remasked,
+                           const uint8_t* proofs, uint64_t n, int32_t* statuses) {
+  oracle_init();
+  aff g, pk;
+  aff_from_bytes64(&g, g64); aff_from_bytes64(&pk, pk64);
+  SIGMA_FOR(i, n) {
+    aff c1, c2, o1, o2, s0, s1;
+    aff_from_bytes64(&c1, deck + 128 * i); aff_from_bytes64(&c2, deck + 128 * i + 64);
+    aff_from_bytes64(&o1, remasked + 128 * i); aff_from_bytes64(&o2, remasked + 128 * i + 64);
+    pt_sub(&s0, &o1, &c1); pt_sub(&s1, &o2, &c2);
+    statuses[i] = cp_verify(proofs + 160 * i, "Remasking Proof", &g, &pk, &s0, &s1);
+  }
+  return 0;
+}
+/* reveal tokens of ONE player for n masked cards (mod.rs:301-328) */
+int oc_reveal_batch(const uint8_t* g64, const uint8_t* sk32, const uint8_t* pk64, const uint8_t* masked, const uint8_t* omegas,
+                    uint64_t n, uint8_t* out_tokens, uint8_t* out_proofs) {
+  oracle_init();
+  aff g, pk;
+  fe sk;
+  aff_from_bytes64(&g, g64); aff_from_bytes64(&pk, pk64);
+  fe_from_bytes(&sk, sk32, &FR);
+  SIGMA_FOR(i, n) {
+    aff c1, tok;
+    fe om;
+    aff_from_bytes64(&c1, masked + 128 * i);
+    fe_from_bytes(&om, omegas + 32 * i, &FR);
+    pt_mul(&tok, &c1, &sk);
+    aff_to_bytes64(out_tokens + 64 * i, &tok);
+    cp_prove(out_proofs + 160 * i, "Reveal Proof", &c1, &g, &tok, &pk, &sk, &om);
+  }
+  return 0;
+}
+int oc_verify_reveal_batch(const uint8_t* g64, const uint8_t* pk64, const uint8_t* tokens, const uint8_t* masked,
+                           const uint8_t* proofs, uint64_t n, int32_t* statuses) {
+  oracle_init();
+  aff g, pk;
+  aff_from_bytes64(&g, g64); aff_from_bytes64(&pk, pk64);
+  SIGMA_FOR(i, n) {
+    aff c1, tok;
+    aff_from_bytes64(&c1, masked + 128 * i);
+    aff_from_bytes64(&tok, tokens + 64 * i);
+    statuses[i] = cp_verify(proofs + 160 * i, "Reveal Proof", &c1, &g, &tok, &pk);
+  }
+  return 0;
+}
+/* Schnorr key ownership (mod.rs:132-165): seed = "Key Ownership Proof" || info_i;
+ * proof = commit (64) | opening (32), opening = omega - c*sk */
+static void schnorr_challenge(fe* c, const uint8_t* info, size_t info_len, const aff* g, const aff* pk, const aff* commit) {
+  static const char kSeed[] = "Key Ownership Proof";
+  uint8_t* seed = (uint8_t*)malloc(sizeof(kSeed) - 1 + info_len + 1);
+  memcpy(seed, kSeed, sizeof(kSeed) - 1);
+  memcpy(seed + sizeof(kSeed) - 1, info, info_len);
+  fsrng_t fs;
+  fs_from_seed(&fs, seed, sizeof(kSeed) - 1 + info_len);
+  free(seed);
+  fs_absorb_begin(&fs);
+  feed_label(&fs, "schnorr_identity");
+  feed_pts(&fs, g, 1); feed_pts(&fs, pk, 1); feed_pts(&fs, commit, 1);
+  fs_absorb_end(&fs);
+  fs_challenge(&fs, c, &FR);
+}
+int oc_key_ownership_prove_batch(const uint8_t* g64, const uint8_t* pks, const uint8_t* sks, const uint8_t* infos,
+                                 const uint64_t* info_off, const uint8_t* omegas, uint64_t n, uint8_t* out_proofs) {
+  oracle_init();
+  aff g;
+  aff_from_bytes64(&g, g64);
+  SIGMA_FOR(i, n) {
+    aff pk, commit;
+    fe sk, om, c, op;
+    aff_from_bytes64(&pk, pks + 64 * i);
+    fe_from_bytes(&sk, sks + 32 * i, &FR); fe_from_bytes(&om, omegas + 32 * i, &FR);
+    pt_mul(&commit, &g, &om);
+    schnorr_challenge(&c, infos + info_off[i], (size_t)(info_off[i + 1] - info_off[i]), &g, &pk, &commit);
+    fe_mul(&op, &c, &sk, &FR);
+    fe_sub(&op, &om, &op, &FR);
+    aff_to_bytes64(out_proofs + 96 * i, &commit);
+    fe_to_bytes(out_proofs + 96 * i + 64, &op, &FR);
+  }
+  return 0;
+}
+int oc_key_ownership_verify_batch(const uint8_t* g64, const uint8_t* pks, const uint8_t* infos, const uint64_t* info_off,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses) {
+  oracle_init();
+  aff g;
+  aff_from_bytes64(&g, g64);
+  SIGMA_FOR(i, n) {
+    aff pk, commit, l, t, s;
+    fe op, c;
+    aff_from_bytes64(&pk, pks + 64 * i);
+    aff_from_bytes64(&commit, proofs + 96 * i);
+    fe_from_bytes(&op, proofs + 96 * i + 64, &FR);
+    schnorr_challenge(&c, infos + info_off[i], (size_t)(info_off[i + 1] - info_off[i]), &g, &pk, &commit);
+    pt_mul(&l, &g, &op); pt_mul(&t, &pk, &c); pt_add(&s, &l, &t);
+    statuses[i] = aff_eq(&s, &commit) ? 0 : 6;
+  }
+  return 0;
+}

@@ -32,6 +32,14 @@ def load():
     lib.oc_blake2s.argtypes = [cp, u64, cp]
     lib.oc_fs_challenges.argtypes = [cp, u64, i32, cp]
     lib.oc_on_curve.argtypes = [cp]
+    lib.oc_mask_batch.argtypes = [cp, cp, cp, cp, cp, u64, cp, cp]
+    lib.oc_verify_mask_batch.argtypes = [cp, cp, cp, cp, cp, u64, vp]
+    lib.oc_remask_prove_batch.argtypes = [cp, cp, cp, cp, cp, u64, cp, cp]
+    lib.oc_verify_remask_batch.argtypes = [cp, cp, cp, cp, cp, u64, vp]
+    lib.oc_reveal_batch.argtypes = [cp, cp, cp, cp, cp, u64, cp, cp]
+    lib.oc_verify_reveal_batch.argtypes = [cp, cp, cp, cp, cp, u64, vp]
+    lib.oc_key_ownership_prove_batch.argtypes = [cp, cp, cp, cp, vp, cp, u64, cp]
+    lib.oc_key_ownership_verify_batch.argtypes = [cp, cp, cp, vp, cp, u64, vp]
     lib.oracle_set_threads.argtypes = [i32]
     lib.oracle_set_msm_mode.argtypes = [i32]
     return lib
@@ -82,3 +90,57 @@ class COracle:
         out = ctypes.create_string_buffer(64)
         self.lib.oc_pedersen_commit(n, ck_g, ck_h, values, len(values) // 32, r, out)
         return out.raw
+
+    # ---- sigma protocols either side of the shuffle (oracle/py/sigma.py; reference mod.rs:132-354)
+    def mask_batch(self, g, pk, cards, rs, omegas):
+        n = len(rs) // 32
+        masked, proofs = ctypes.create_string_buffer(128 * n), ctypes.create_string_buffer(160 * n)
+        self.lib.oc_mask_batch(g, pk, cards, rs, omegas, n, masked, proofs)
+        return masked.raw, proofs.raw
+
+    def _statuses(self, fn, n, *args):
+        st = (ctypes.c_int32 * max(n, 1))()
+        fn(*args, n, st)
+        return list(st)[:n]
+
+    def verify_mask_batch(self, g, pk, cards, masked, proofs):
+        return self._statuses(self.lib.oc_verify_mask_batch, len(proofs) // 160, g, pk, cards, masked, proofs)
+
+    def remask_prove_batch(self, g, pk, deck, alphas, omegas):
+        n = len(alphas) // 32
+        out, proofs = ctypes.create_string_buffer(128 * n), ctypes.create_string_buffer(160 * n)
+        self.lib.oc_remask_prove_batch(g, pk, deck, alphas, omegas, n, out, proofs)
+        return out.raw, proofs.raw
+
+    def verify_remask_batch(self, g, pk, deck, remasked, proofs):
+        return self._statuses(self.lib.oc_verify_remask_batch, len(proofs) // 160, g, pk, deck, remasked, proofs)
+
+    def reveal_batch(self, g, sk, pk, masked, omegas):
+        n = len(omegas) // 32
+        tokens, proofs = ctypes.create_string_buffer(64 * n), ctypes.create_string_buffer(160 * n)
+        self.lib.oc_reveal_batch(g, sk, pk, masked, omegas, n, tokens, proofs)
+        return tokens.raw, proofs.raw
+
+    def verify_reveal_batch(self, g, pk, tokens, masked, proofs):
+        return self._statuses(self.lib.oc_verify_reveal_batch, len(proofs) // 160, g, pk, tokens, masked, proofs)
+
+    @staticmethod
+    def _infos(infos):
+        off = [0]
+        for b in infos:
+            off.append(off[-1] + len(b))
+        return b"".join(infos), (ctypes.c_uint64 * len(off))(*off)
+
+    def key_ownership_prove_batch(self, g, pks, sks, infos, omegas):
+        n = len(infos)
+        blob, off = self._infos(infos)
+        proofs = ctypes.create_string_buffer(96 * n)
+        self.lib.oc_key_ownership_prove_batch(g, pks, sks, blob, off, omegas, n, proofs)
+        return proofs.raw
+
+    def key_ownership_verify_batch(self, g, pks, infos, proofs):
+        n = len(infos)
+        blob, off = self._infos(infos)
+        st = (ctypes.c_int32 * max(n, 1))()
+        self.lib.oc_key_ownership_verify_batch(g, pks, blob, off, proofs, n, st)
+        return list(st)[:n]

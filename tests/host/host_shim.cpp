@@ -144,3 +144,19 @@ void h_diag_plan(int m, uint32_t* sizes, uint32_t* leaf_mask, uint32_t* leaf_val
   memcpy(entries, p.entries.data(), 4 * p.entries.size());
 }
 }
+
+// ---- host-only half of the batched sigma protocols (csrc/sigma_host.hpp)
+#include "../../mental-poker_b200/csrc/sigma_host.hpp"
+extern "C" {
+// which: 0 masking, 1 remasking, 2 reveal seeds
+void h_cp_challenge(int which, const uint8_t* g, const uint8_t* h, const uint8_t* s0, const uint8_t* s1, const uint8_t* a,
+                    const uint8_t* b, uint8_t* out) {
+  const char* seed = which == 0 ? kSeedMasking : which == 1 ? kSeedRemasking : kSeedReveal;
+  fr_to_bytes(cp_challenge(Transcript(seed, strlen(seed)), g, h, s0, s1, a, b), out);
+}
+void h_schnorr_challenge(const uint8_t* info, uint64_t info_len, const uint8_t* g, const uint8_t* pk, const uint8_t* commit,
+                         uint8_t* out) {
+  fr_to_bytes(schnorr_challenge(info, info_len, g, pk, commit), out);
+}
+int h_fr_bytes_canonical(const uint8_t* b) { return fr_bytes_canonical(b); }
+}

@@ -30,6 +30,9 @@ def test_status_strings(pkg):
     # the reference's pinned message (tests.rs:223-225)
     assert pkg.lib.mp_verify_status_string(1) == b"Hadamard Product (5.1)"
     assert pkg.lib.mp_verify_status_string(0) == b"ok"
+    # masking.rs:103-105 / tests.rs:72-77
+    assert pkg.lib.mp_verify_status_string(5) == b"Chaum-Pedersen"
+    assert pkg.lib.mp_verify_status_string(6) == b"Schnorr Identification"
 
 
 def test_no_cpu_fallback_without_device(pkg):
