@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch52", type=int, default=512, help="proofs in the 52-card batch measurement (0 = skip)")
     ap.add_argument("--pipeline-decks", type=int, default=6, help="decks in the overlapped-batch measurement (0 = skip)")
+    ap.add_argument("--sigma-cards", type=int, default=65536,
+                    help="cards in the batched mask / remask / reveal measurement (SURVEY 8(f) rank 1; 0 = skip)")
     ap.add_argument("--msm-logn", type=int, default=20, help="size of the MSM microbench reported beside the metric")
     args = ap.parse_args()
     m, n = args.m, args.n
@@ -333,6 +335,10 @@ def main():
             b52["proofs_per_s_all_gpus"] = world * b52["batch"] / t.item()
     except Exception as e:
         b52 = dict(error=repr(e))
+    try:
+        sig = sigma_bench(pkg, ctx, args.sigma_cards, not args.no_cpu_baseline and rank == 0) if args.sigma_cards > 0 else None
+    except Exception as e:
+        sig = dict(error=repr(e))
     if rank == 0:
         peak, peak_src = load_peaks()
         bytes_per_add = 68.0  # 64 B affine point gather + 4 B sorted index
@@ -365,6 +371,7 @@ def main():
         line["msm"] = msm_res
         line["batch52"] = b52
         line["pipelined"] = piped
+        line["sigma"] = sig
         if not args.no_cpu_baseline and world == 1:
             sm, sn = sample_shape(m, n)
             val, desc, legs = cpu_sample(m, n, sm, sn, threads=1)
@@ -424,6 +431,53 @@ def batch52_bench(pkg, ctx, torch, stream, batch, rank):
             best = cur if best is None or cur["prove_ms"] + cur["verify_ms"] < best["prove_ms"] + best["verify_ms"] else best
     res["single_proof_latency"] = best
     ctx2.close()
+    return res
+
+
+def sigma_bench(pkg, ctx, n, cpu_baseline):
+    """the sigma protocols either side of the shuffle, batched over a whole
+    deck -- mask + proof, verify_mask, remask + proof, verify_remask, reveal token + proof (one player),
+    verify_reveal for `n` cards through the C ABI with host buffers (host wall clock), beside the C
+    restatement of the reference's per-card CPU path on a bounded sample."""
+    import numpy as np
+    rng = np.random.default_rng(300)
+    sk = rand_scalars(rng, 1)
+    pk = ctx.dbg_scalar_mul(G64, sk)
+    cards = ctx.dbg_scalar_mul(G64 * n, rand_scalars(rng, n))
+    r, om = rand_scalars(rng, n), [rand_scalars(rng, n) for _ in range(3)]
+    alpha = rand_scalars(rng, n)
+    res = {"cards": n, "timing": "host wall clock around each C-ABI call (host buffers)", "host_threads": os.cpu_count()}
+    launches = 0
+    for it in range(2):  # first pass warms the scratch buffers and the pk table
+        t = [time.perf_counter()]
+        masked, p1 = ctx.mask_batch(pk, cards, r, om[0]); t.append(time.perf_counter()); launches = ctx.launches
+        s1 = ctx.verify_mask_batch(pk, cards, masked, p1); t.append(time.perf_counter()); launches += ctx.launches
+        out, p2 = ctx.remask_prove_batch(pk, masked, alpha, om[1]); t.append(time.perf_counter()); launches += ctx.launches
+        s2 = ctx.verify_remask_batch(pk, masked, out, p2); t.append(time.perf_counter()); launches += ctx.launches
+        tok, p3 = ctx.reveal_batch(sk, pk, out, om[2]); t.append(time.perf_counter()); launches += ctx.launches
+        s3 = ctx.verify_reveal_batch(pk, tok, out, p3); t.append(time.perf_counter()); launches += ctx.launches
+    names = ["mask", "verify_mask", "remask", "verify_remask", "reveal", "verify_reveal"]
+    for k, name in enumerate(names):
+        res[name + "_per_s"] = n / (t[k + 1] - t[k])
+    res["all_verified"] = not (any(s1) or any(s2) or any(s3))
+    res["gpu_launches"] = launches
+    res["proofs_per_s"] = 3 * n / (t[6] - t[0])  # three proofs made and checked per card
+    if cpu_baseline:
+        from oracle import c_oracle
+        co = c_oracle.COracle(threads=1)
+        k = min(n, 256)
+        t0 = time.perf_counter()
+        m2, q1 = co.mask_batch(G64, pk, cards[:64 * k], r[:32 * k], om[0][:32 * k])
+        ok = co.verify_mask_batch(G64, pk, cards[:64 * k], m2, q1)
+        o2, q2 = co.remask_prove_batch(G64, pk, m2, alpha[:32 * k], om[1][:32 * k])
+        ok += co.verify_remask_batch(G64, pk, m2, o2, q2)
+        t2, q3 = co.reveal_batch(G64, sk, pk, o2, om[2][:32 * k])
+        ok += co.verify_reveal_batch(G64, pk, t2, o2, q3)
+        dt = time.perf_counter() - t0
+        same = (m2, q1, o2, q2, t2, q3) == (masked[:128 * k], p1[:160 * k], out[:128 * k], p2[:160 * k], tok[:64 * k], p3[:160 * k])
+        res["cpu_baseline"] = dict(value=3 * k / dt, unit="proofs/s", cores=1, kind="port",
+                                   sample=f"C restatement (oracle/c), 1 thread, the same six calls on the first {k} cards: {dt:.2f} s",
+                                   bytes_identical_to_gpu=bool(same and not any(ok)))
     return res
 
 

@@ -5,9 +5,10 @@
 //! exact binding: which reference call each C entry point replaces, how arkworks types map
 //! to the byte layouts of include/mpshuffle.h, and where the caller's RNG is consumed.
 //!
-//! `GpuDLCards` delegates the twelve constant-size methods of the trait (key generation,
-//! mask/remask/reveal proofs ...) to the reference's `DLCards` and overrides only
-//! `setup`, `shuffle_and_remask` and `verify_shuffle`.
+//! `GpuDLCards` overrides `setup`, `shuffle_and_remask` and `verify_shuffle`, offers deck-wide
+//! `mask_all` / `remask_all` / `reveal_all` helpers over the batched sigma-protocol entry points, and
+//! delegates the remaining constant-size methods of the trait (key generation, aggregate key, unmask,
+//! single-card mask / remask / reveal) to the reference's `DLCards`.
 use std::os::raw::c_char;
 
 #[repr(C)]
@@ -29,6 +30,28 @@ extern "C" {
                              randomness: *const u8, out_deck: *mut u8, proof_out: *mut u8) -> i32;
     // DLCards::verify_shuffle (mod.rs:420-443)
     fn mp_shuffle_verify(ctx: *mut MpCtx, pk: *const u8, deck: *const u8, shuffled: *const u8, proof: *const u8) -> i32;
+    // Batched sigma protocols either side of the shuffle (one call per deck instead of one trait call per card):
+    // DLCards::mask / verify_mask (mod.rs:182-240)
+    fn mp_mask_batch(ctx: *mut MpCtx, shared_key: *const u8, cards: *const u8, r: *const u8, omega: *const u8, n: u64,
+                     out_masked: *mut u8, out_proofs: *mut u8, host_threads: i32) -> i32;
+    fn mp_verify_mask_batch(ctx: *mut MpCtx, shared_key: *const u8, cards: *const u8, masked: *const u8, proofs: *const u8,
+                            n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    // DLCards::remask / verify_remask (mod.rs:242-299)
+    fn mp_remask_prove_batch(ctx: *mut MpCtx, shared_key: *const u8, deck: *const u8, alpha: *const u8, omega: *const u8,
+                             n: u64, out_deck: *mut u8, out_proofs: *mut u8, host_threads: i32) -> i32;
+    fn mp_verify_remask_batch(ctx: *mut MpCtx, shared_key: *const u8, deck: *const u8, remasked: *const u8,
+                              proofs: *const u8, n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    // DLCards::compute_reveal_token / verify_reveal (mod.rs:301-354), one player, n masked cards
+    fn mp_reveal_batch(ctx: *mut MpCtx, sk: *const u8, pk: *const u8, masked: *const u8, omega: *const u8, n: u64,
+                       out_tokens: *mut u8, out_proofs: *mut u8, host_threads: i32) -> i32;
+    fn mp_verify_reveal_batch(ctx: *mut MpCtx, pk: *const u8, tokens: *const u8, masked: *const u8, proofs: *const u8,
+                              n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    // DLCards::prove_key_ownership / verify_key_ownership (mod.rs:132-165)
+    fn mp_key_ownership_prove_batch(ctx: *mut MpCtx, pks: *const u8, sks: *const u8, infos: *const u8,
+                                    info_offsets: *const u64, omega: *const u8, n: u64, out_proofs: *mut u8,
+                                    host_threads: i32) -> i32;
+    fn mp_key_ownership_verify_batch(ctx: *mut MpCtx, pks: *const u8, infos: *const u8, info_offsets: *const u64,
+                                     proofs: *const u8, n: u64, statuses: *mut i32, host_threads: i32) -> i32;
 }
 
 /// Owns the opaque GPU context; `Parameters` of the shim holds one (the reference's own
