@@ -198,7 +198,11 @@ static int32_t diag_device(mp_ctx* ctx, DiagDevice** out) {
 bool diag_karatsuba_selected(int m, int n, int c_table) {
   if (const char* e = getenv("MP_DIAG_KARATSUBA")) return atoi(e) != 0 && m >= 2;
   if (m < 8) return false;
-  const int c_leaf = msm_pick_window((uint64_t)n);
+  int L = 0;
+  while ((1 << L) < m) L++;
+  uint64_t leaves = 1;
+  for (int b = 0; b < L; b++) leaves *= 3;
+  const int c_leaf = msm_pick_window((uint64_t)n, leaves + m);
   return diag_use_karatsuba(m, n, msm_num_windows(c_table), msm_num_windows(c_leaf), c_leaf);
 }
 
@@ -241,7 +245,7 @@ int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz*
   std::vector<MsmJob> jobs((size_t)P.njobs());
   for (uint32_t l = 0; l < nleaf; l++) jobs[l] = MsmJob{l * n, l * n, n};
   for (uint32_t i = 1; i <= m; i++) jobs[nleaf + i - 1] = MsmJob{nleaf * n, P.single[m - i] * n, n};  // <C_i, a0>, C_i = P_{m-i}
-  const int c = msm_pick_window((uint64_t)n);
+  const int c = msm_pick_window((uint64_t)n, jobs.size());
   // a launch sequence stays below the 2^32-entry limit of the sort (entries = terms * windows)
   const uint64_t max_jobs = std::max<uint64_t>(1, ((1ull << 31) / (uint64_t)msm_num_windows(c)) / n);
   for (uint64_t j0 = 0; j0 < jobs.size(); j0 += max_jobs) {

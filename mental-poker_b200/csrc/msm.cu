@@ -87,13 +87,22 @@ cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, ui
   return err;
 }
 
-int msm_pick_window(uint64_t avg_len) {
-  // minimise W * (len + 2.8 * 2^(c-1)) over c, W = ceil(253 / c)
+int msm_pick_window(uint64_t avg_len, uint64_t njobs) {
+  // minimise W * (len + 2.8 * 2^(c-1)) over c, W = ceil(253 / c), plus the serial tail a SHORT top
+  // window causes: with t = 253 - (W-1)c bits its digits fall into 2^(t-1) buckets only, each bucket's
+  // run is cut into chunks and one k_stitch thread adds the chunk partials one after the other
+  // (~10 us per addition at that occupancy, i.e. ~90 k bucket additions of chip throughput each; a
+  // latency paid once per launch, so it is spread over the jobs of the launch).
+  // At 2 jobs of 65 537 terms c = 13 (t = 6: 32 buckets of 2 048 entries, 0.7 ms of stitching) loses to
+  // c = 11 (t = 11, 23 full windows) although the first term alone rates them equal.
   int best = 4;
   double best_cost = 1e300;
   for (int c = 4; c <= 16; c++) {
-    int W = (253 + c - 1) / c;
-    double cost = (double)W * ((double)avg_len + 2.8 * (double)(1u << (c - 1)));
+    const int W = (253 + c - 1) / c;
+    const int t = 253 - (W - 1) * c;
+    const double top_run = (double)avg_len / (double)(1u << (t - 1));  // entries per top-window bucket
+    const double stitch = top_run > 2.0 * kChunkMax ? (top_run / kChunkMax) * 90000.0 / (double)(njobs ? njobs : 1) : 0.0;
+    const double cost = (double)W * ((double)avg_len + 2.8 * (double)(1u << (c - 1))) + stitch;
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;

@@ -33,8 +33,8 @@ struct MsmWorkspace;  // opaque, owns device scratch that grows on demand
 MsmWorkspace* msm_workspace_create();
 void msm_workspace_destroy(MsmWorkspace*);
 
-// Heuristic window width for jobs of average length `avg_len`.
-int msm_pick_window(uint64_t avg_len);
+// Heuristic window width for a launch of `njobs` jobs of average length `avg_len`.
+int msm_pick_window(uint64_t avg_len, uint64_t njobs = 1);
 
 // d_scalars: canonical little-endian 256-bit scalars (< group order), 8 words each.
 // d_points : Montgomery-form affine points, index = point * ncomp + comp.

@@ -245,7 +245,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
                                      (uint32_t)((size_t)(i1 - i0 + 1) * n)};
       }
     CK(cudaMemcpyAsync(d_ct_scal, h_ct_scal.data(), h_ct_scal.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(msm_run(ctx->ws, d_ct_scal, Bs * (N + n), d_ct_mont, 2, diag.data(), (int)diag.size(), msm_pick_window(N / 2 + 1), d_ct_out, st));
+    CK(msm_run(ctx->ws, d_ct_scal, Bs * (N + n), d_ct_mont, 2, diag.data(), (int)diag.size(), msm_pick_window(N / 2 + 1, diag.size()), d_ct_out, st));
     launches += msm_last_launches(ctx->ws);
   }
   jobs.clear();

@@ -157,7 +157,7 @@ int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_ba
   CK(cudaMemcpyAsync(d_scal, tl.scal.data(), (size_t)T * 32, cudaMemcpyHostToDevice, stream));
   CK(points_to_mont((const uint32_t*)d_canon, d_mont, T, d_bad, stream));
   ctx->launches += 1;
-  int c = msm_pick_window(J ? T / J : 1);
+  int c = msm_pick_window(J ? T / J : 1, J);
   CK(msm_run(ws, d_scal, T, d_mont, 1, tl.jobs.data(), J, c, d_out, stream));
   ctx->launches += msm_last_launches(ws);
   *d_out_ret = d_out;

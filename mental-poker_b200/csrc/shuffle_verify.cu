@@ -94,7 +94,7 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   //   job 0:  sum x^i C_i - E_m                                        == O   (Chat == E_m)
   //   job 1:  sum x^k E_k - Enc(b*ghat; tau) - sum (x^{m-i} a_j) C'_ij  == O
   MsmJob ct_jobs[2] = {{0, 0, (uint32_t)(N + 1)}, {(uint32_t)(N + 1), (uint32_t)(N + 1), (uint32_t)(N + 2 * m + 2)}};
-  CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N), d_ct_out, ctx->stream));
+  CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N, 2), d_ct_out, ctx->stream));
   ctx->launches += msm_last_launches(ctx->ws);
 
   CK(cudaStreamWaitEvent(ctx->stream, S->ev_join, 0));  // join: G1 results are ready for the copies below
@@ -219,7 +219,7 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
     jobs[4 * p + 2] = MsmJob{c2, c2, (uint32_t)N};
     jobs[4 * p + 3] = MsmJob{b + 1, b + 1, (uint32_t)(2 * m + 2)};
   }
-  CK(msm_run(ctx->ws, d_ct_scal, ct_total, d_ct_mont, 2, jobs.data(), (int)jobs.size(), msm_pick_window(N / 2 + 1), d_ct_out, st));
+  CK(msm_run(ctx->ws, d_ct_scal, ct_total, d_ct_mont, 2, jobs.data(), (int)jobs.size(), msm_pick_window(N / 2 + 1, jobs.size()), d_ct_out, st));
   ctx->launches += msm_last_launches(ctx->ws);
   k_group_identity<<<(unsigned)((Bs * 4 + 63) / 64), 64, 0, st>>>(d_ct_out, 2, 2, Bs * 2, d_flags);
   // G1 jobs: 8 per proof, contiguous terms
@@ -236,7 +236,7 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
       }
     }
   }
-  CK(msm_run(ctx->ws, d_g1_scal, Bs * T1, d_g1_mont, 1, g1jobs.data(), (int)g1jobs.size(), msm_pick_window(T1 / kG1Checks), d_g1_out, st));
+  CK(msm_run(ctx->ws, d_g1_scal, Bs * T1, d_g1_mont, 1, g1jobs.data(), (int)g1jobs.size(), msm_pick_window(T1 / kG1Checks, g1jobs.size()), d_g1_out, st));
   ctx->launches += msm_last_launches(ctx->ws);
   k_group_identity<<<(unsigned)((Bs * kG1Checks + 63) / 64), 64, 0, st>>>(d_g1_out, 1, 1, Bs * kG1Checks, d_flags + Bs * 4);
   CK(cudaGetLastError());
