@@ -16,10 +16,11 @@ KEYS = [
 ]
 
 
-def load(path):
+def load_all(path):
+    """one dict per captured launch"""
     rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    return {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    hdr, units = rows[0], rows[1]
+    return [{h: (v, u) for h, u, v in zip(hdr, units, vals)} for vals in rows[2:]]
 
 
 def fmt(v, u):
@@ -48,9 +49,11 @@ def main(d):
     print("| kernel | " + " | ".join(k[1] for k in KEYS) + " |")
     print("|---|" + "---|" * len(KEYS))
     for p in sorted(glob.glob(os.path.join(d, "*_raw.csv"))):
-        m = load(p)
-        cells = [fmt(*m[k]) if k in m else "-" for k, _ in KEYS]
-        print(f"| {os.path.basename(p)[:-8]} | " + " | ".join(cells) + " |")
+        launches = load_all(p)
+        for i, m in enumerate(launches):
+            cells = [fmt(*m[k]) if k in m else "-" for k, _ in KEYS]
+            tag = os.path.basename(p)[:-8] + (f" #{i}" if len(launches) > 1 else "")
+            print(f"| {tag} | " + " | ".join(cells) + " |")
 
 
 if __name__ == "__main__":
