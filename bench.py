@@ -71,23 +71,54 @@ def make_instance(ctx, m, n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons of this rank's GPU sampled DURING the timed region.  In-process NVML
+    (nvidia-ml-py) every 20 ms: a sample costs microseconds, where spawning `nvidia-smi` from every rank
+    ten times a second competes with the statement hash for the host cores -- that alone cost the
+    8-GPU run 10 % (eight serial Blake2s chains share 16 vCPUs).  `nvidia-smi` stays as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip()]
+        return int(ids[index]) if ids and all(v.strip().isdigit() for v in ids) and index < len(ids) else index
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+            return [str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for b in bits]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        return [c.strip() for c in out.strip().split(",")]
 
     def run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                self.rows.append(self.sample())
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02 if self.nvml is not None else 0.25)
 
     def __enter__(self):
         self.t.start()
@@ -100,10 +131,9 @@ class ClockSampler:
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [nm for i, nm in enumerate(self.NAMES) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+                    samples=len(sm), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def load_peaks():

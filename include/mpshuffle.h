@@ -244,7 +244,8 @@ double mp_dbg_transcript_ms(uint64_t n_points);
 /* integer-pipe microbenchmarks: returns milliseconds for `iters` dependent-chain iterations
  * on a full-chip grid; *ops receives the number of counted operations executed.  which: 0 IMAD.WIDE,
  * 1 IMAD.LO, 2 fq_mul, 3 xyzz_madd, 4 fq_sqr, 5 carry-chained IMAD.WIDE pairs (counted as
- * wide multiply-adds), 6 IMAD.WIDE + IADD 1:1 (counted as wide multiply-adds). */
+ * wide multiply-adds), 6 IMAD.WIDE + IADD 1:1 (counted as wide multiply-adds), 7 DFMA (fma.rz.f64),
+ * 8 DFMA + IMAD.WIDE 1:1 (counted as DFMAs), 9 DFMA + 32-bit add 1:1 (counted as DFMAs). */
 int32_t mp_dbg_bench(mp_ctx* ctx, int32_t which, int32_t iters, float* ms, double* ops);
 
 #ifdef __cplusplus

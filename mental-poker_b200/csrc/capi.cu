@@ -525,6 +525,34 @@ __global__ void __launch_bounds__(256) k_bench_mix(uint32_t* out, int iters, uin
   for (int k = 0; k < 8; k++) x ^= acc[k] + s[k];
   out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)x ^ (uint32_t)(x >> 32);
 }
+// FP64 pipe probes (is the DFMA pipe free next to the integer multiplier?  52-bit-limb products through
+// fma.rz.f64 are the known alternative to 32x32 IMAD.WIDE for wide modular arithmetic):
+// MODE 0: DFMA only; 1: DFMA + IMAD.WIDE 1:1; 2: DFMA + 32-bit add 1:1.  Counted op = one DFMA.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_bench_dfma(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  double f[8];
+  unsigned long long acc[8];
+  uint32_t s[8];
+  const double m = 1.0 + 1e-9 * (double)(threadIdx.x & 7), c = 1e-3 * (double)(blockIdx.x & 3);
+#pragma unroll
+  for (int k = 0; k < 8; k++) { f[k] = 1.0 + k; acc[k] = k + a; s[k] = k * b; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(f[k]) : "d"(m), "d"(c));
+        if (MODE == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b + r));
+        if (MODE == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(s[k]) : "r"(a + r));
+      }
+    }
+  }
+  unsigned long long x = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) x ^= acc[k] + s[k] + (unsigned long long)__double_as_longlong(f[k]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)x ^ (uint32_t)(x >> 32);
+}
 __global__ void __launch_bounds__(128) k_bench_madd(uint32_t* out, int iters, uint32_t seed) {
   // G in canonical form -> Montgomery; acc walks G, 2G, 3G, ... (no special cases hit)
   const uint32_t g[16] = {0xc943cfcau, 0x3d723d8bu, 0x0d1819e0u, 0xdeacfd9bu, 0x5a40f0c7u, 0x7beced41u,
@@ -556,6 +584,9 @@ extern "C" int32_t mp_dbg_bench(mp_ctx* ctx, int32_t which, int32_t iters, float
       case 4: k_bench_fq_sqr<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters * 2; break;
       case 5: k_bench_imad_wide_cc<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
       case 6: k_bench_mix<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
+      case 7: k_bench_dfma<0><<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
+      case 8: k_bench_dfma<1><<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
+      case 9: k_bench_dfma<2><<<blocks, 256, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 256 * iters * 64; break;
       default: cudaEventDestroy(e0); cudaEventDestroy(e1); return MP_ERR_INVALID_ARG;
     }
     cudaEventRecord(e1, ctx->stream);
