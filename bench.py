@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--batch52", type=int, default=512, help="proofs in the 52-card batch measurement (0 = skip)")
     ap.add_argument("--pipeline-decks", type=int, default=6, help="decks in the overlapped-batch measurement (0 = skip)")
     ap.add_argument("--sigma-cards", type=int, default=65536,
-                    help="cards in the batched mask / remask / reveal measurement (SURVEY 8(f) rank 1; 0 = skip)")
+                    help="cards in the batched mask / remask / reveal and the wire-format measurements (SURVEY 8(f) ranks 1-2; 0 = skip)")
     ap.add_argument("--msm-logn", type=int, default=20, help="size of the MSM microbench reported beside the metric")
     args = ap.parse_args()
     m, n = args.m, args.n
@@ -369,6 +369,10 @@ def main():
         sig = sigma_bench(pkg, ctx, args.sigma_cards, not args.no_cpu_baseline and rank == 0) if args.sigma_cards > 0 else None
     except Exception as e:
         sig = dict(error=repr(e))
+    try:
+        wir = wire_bench(pkg, ctx, args.sigma_cards, not args.no_cpu_baseline and rank == 0) if args.sigma_cards > 0 else None
+    except Exception as e:
+        wir = dict(error=repr(e))
     if rank == 0:
         peak, peak_src = load_peaks()
         bytes_per_add = 68.0  # 64 B affine point gather + 4 B sorted index
@@ -402,6 +406,7 @@ def main():
         line["batch52"] = b52
         line["pipelined"] = piped
         line["sigma"] = sig
+        line["wire"] = wir
         if not args.no_cpu_baseline and world == 1:
             sm, sn = sample_shape(m, n)
             val, desc, legs = cpu_sample(m, n, sm, sn, threads=1)
@@ -508,6 +513,35 @@ def sigma_bench(pkg, ctx, n, cpu_baseline):
         res["cpu_baseline"] = dict(value=3 * k / dt, unit="proofs/s", cores=1, kind="port",
                                    sample=f"C restatement (oracle/c), 1 thread, the same six calls on the first {k} cards: {dt:.2f} s",
                                    bytes_identical_to_gpu=bool(same and not any(ok)))
+    return res
+
+
+def wire_bench(pkg, ctx, n_cards, cpu_baseline):
+    """serialise a deck to the ark-serialize wire format (host) and
+    deserialise it (GPU: one square root in F_p per point), host buffers, wall clock; beside the C
+    restatement of the CPU path (Tonelli-Shanks as in ark-ff) on a bounded sample."""
+    import numpy as np
+    rng = np.random.default_rng(400)
+    deck = ctx.dbg_scalar_mul(G64 * (2 * n_cards), rand_scalars(rng, 2 * n_cards))
+    res = {"cards": n_cards, "points": 2 * n_cards, "timing": "host wall clock around each C-ABI call (host buffers)"}
+    for it in range(2):
+        t0 = time.perf_counter()
+        ser = ctx.deck_serialize(deck)
+        t1 = time.perf_counter()
+        back = ctx.deck_deserialize(ser)
+        t2 = time.perf_counter()
+    res.update(serialize_points_per_s=2 * n_cards / (t1 - t0), deserialize_points_per_s=2 * n_cards / (t2 - t1),
+               deserialize_ms=(t2 - t1) * 1e3, round_trip_ok=back == deck, gpu_launches=ctx.launches, wire_bytes=len(ser))
+    if cpu_baseline:
+        from oracle import c_oracle
+        co = c_oracle.COracle(threads=1)
+        k = min(2 * n_cards, 512)
+        t0 = time.perf_counter()
+        out, st = co.points_decompress(ser[8:8 + 32 * k])
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = dict(value=k / dt, unit="points/s", cores=1, kind="port",
+                                   sample=f"C restatement (oracle/c, Tonelli-Shanks), 1 thread, first {k} points: {dt:.2f} s",
+                                   bytes_identical_to_gpu=bool(out == deck[:64 * k] and not any(st)))
     return res
 
 

@@ -225,6 +225,29 @@ int32_t mp_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const uin
                                       const uint64_t* info_offsets, const uint8_t* proofs, uint64_t n,
                                       int32_t* statuses, int32_t host_threads);
 
+/* ---- wire format (Appendix A3) -------------------------------------
+ * ark-serialize 0.3 encodings of what crosses the network in a round -- every public type of the trait
+ * is bound by CanonicalSerialize + CanonicalDeserialize (reference src/lib.rs:45-71) and proof sizes are
+ * measured with `serialized_size` (examples/parameter_selection.rs:95):
+ *   compressed point = x (32 bytes LE) with flags in the top bits of the last byte: bit 7 = y is the
+ *   larger of (y, -y), bit 6 = infinity;  Vec<T> = u64 LE length | items;  ciphertext = c1 | c2.
+ * Serialisation is byte handling and runs on the host; DEserialisation needs one square root in F_p per
+ * point (Tonelli-Shanks with a 192-bit two-adic part) and runs on the GPU.  mp_points_decompress fills
+ * statuses[i] (may be NULL) with 0 ok, 1 malformed encoding, 2 x not on the curve and returns
+ * MP_ERR_NOT_ON_CURVE if any item is rejected (rejected items are written as 64 zero bytes). */
+int32_t mp_points_compress(const uint8_t* points /* n*64 */, uint64_t n, uint8_t* out /* n*32 */);
+int32_t mp_points_decompress(mp_ctx* ctx, const uint8_t* in /* n*32 */, uint64_t n, uint8_t* out /* n*64 */,
+                             int32_t* statuses /* n or NULL */);
+/* Vec<MaskedCard>: 8 + 64 * n_cards bytes */
+uint64_t mp_deck_serialized_len(uint64_t n_cards);
+int32_t mp_deck_serialize(const uint8_t* deck /* n_cards*128 */, uint64_t n_cards, uint8_t* out);
+/* *n_cards: in = capacity of out_deck in cards, out = cards in the buffer */
+int32_t mp_deck_deserialize(mp_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards);
+/* the flat proof with every point compressed: (11m+8)*32 + (5n+9)*32 bytes */
+uint64_t mp_proof_serialized_len(int32_t m, int32_t n);
+int32_t mp_proof_serialize(int32_t m, int32_t n, const uint8_t* proof, uint8_t* out);
+int32_t mp_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof);
+
 /* ---- measurement ---------------------------------------------------------------------------
  * Per-launch CUDA-event timing (on the context's stream) of the bucket-accumulation kernel, the
  * dominant kernel of every MSM: collect returns the summed duration, the exact number of bucket

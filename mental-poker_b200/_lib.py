@@ -54,6 +54,14 @@ SIGNATURES = {
     "mp_verify_reveal_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
     "mp_key_ownership_prove_batch": (_i32, [_vp, _cp, _cp, _cp, ctypes.POINTER(_u64), _cp, _u64, _cp, _i32]),
     "mp_key_ownership_verify_batch": (_i32, [_vp, _cp, _cp, ctypes.POINTER(_u64), _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp_points_compress": (_i32, [_cp, _u64, _cp]),
+    "mp_points_decompress": (_i32, [_vp, _cp, _u64, _cp, ctypes.POINTER(_i32)]),
+    "mp_deck_serialized_len": (_u64, [_u64]),
+    "mp_deck_serialize": (_i32, [_cp, _u64, _cp]),
+    "mp_deck_deserialize": (_i32, [_vp, _cp, _u64, _cp, ctypes.POINTER(_u64)]),
+    "mp_proof_serialized_len": (_u64, [_i32, _i32]),
+    "mp_proof_serialize": (_i32, [_i32, _i32, _cp, _cp]),
+    "mp_proof_deserialize": (_i32, [_vp, _i32, _i32, _cp, _cp]),
     "mp_profile_enable": (_i32, [_vp, _i32]),
     "mp_profile_collect_dominant": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "mp_profile_collect": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
@@ -282,6 +290,51 @@ class Context:
         st = (_i32 * max(n, 1))()
         check(self.h, lib.mp_key_ownership_verify_batch(self.h, pks, blob, off, proofs, n, st, host_threads))
         return list(st)[:n]
+
+    # --- wire format (ark-serialize 0.3 compressed encodings; decompression on the GPU)
+    @staticmethod
+    def points_compress(points: bytes) -> bytes:
+        n = len(points) // 64
+        out = ctypes.create_string_buffer(32 * n)
+        assert lib.mp_points_compress(points, n, out) == 0
+        return out.raw
+
+    def points_decompress(self, data: bytes, want_statuses=False):
+        """-> points (n*64); with want_statuses=True -> (points, statuses, return code) without raising"""
+        n = len(data) // 32
+        out = ctypes.create_string_buffer(64 * n)
+        st = (_i32 * max(n, 1))()
+        rc = lib.mp_points_decompress(self.h, data, n, out, st)
+        if want_statuses:
+            return out.raw, list(st)[:n], rc
+        check(self.h, rc)
+        return out.raw
+
+    @staticmethod
+    def deck_serialize(deck: bytes) -> bytes:
+        n = len(deck) // 128
+        out = ctypes.create_string_buffer(lib.mp_deck_serialized_len(n))
+        assert lib.mp_deck_serialize(deck, n, out) == 0
+        return out.raw
+
+    def deck_deserialize(self, data: bytes) -> bytes:
+        cap = max((len(data) - 8) // 64, 0)
+        out = ctypes.create_string_buffer(128 * max(cap, 1))
+        n = _u64(cap)
+        check(self.h, lib.mp_deck_deserialize(self.h, data, len(data), out, ctypes.byref(n)))
+        return out.raw[:128 * n.value]
+
+    @staticmethod
+    def proof_serialize(m, n, proof: bytes) -> bytes:
+        out = ctypes.create_string_buffer(lib.mp_proof_serialized_len(m, n))
+        assert lib.mp_proof_serialize(m, n, proof, out) == 0
+        return out.raw
+
+    def proof_deserialize(self, m, n, data: bytes) -> bytes:
+        assert len(data) == lib.mp_proof_serialized_len(m, n)
+        out = ctypes.create_string_buffer(lib.mp_proof_len(m, n))
+        check(self.h, lib.mp_proof_deserialize(self.h, m, n, data, out))
+        return out.raw
 
     @staticmethod
     def status_string(code):

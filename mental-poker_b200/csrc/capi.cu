@@ -10,6 +10,7 @@
 #include "ctx.cuh"
 #include "msm.cuh"
 #include "shuffle.cuh"
+#include "wire_host.hpp"
 #include "transcript.hpp"
 #include <chrono>
 
@@ -340,6 +341,35 @@ extern "C" int32_t mp_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks
                                                  const uint64_t* info_offsets, const uint8_t* proofs, uint64_t n,
                                                  int32_t* statuses, int32_t host_threads) {
   return sigma_key_ownership_verify_batch(ctx, pks, infos, info_offsets, proofs, n, statuses, host_threads);
+}
+
+// ---- wire format (host half in wire_host.hpp, device half in wire.cu)
+extern "C" int32_t mp_points_compress(const uint8_t* points, uint64_t n, uint8_t* out) {
+  if (n && (!points || !out)) return MP_ERR_INVALID_ARG;
+  for (uint64_t i = 0; i < n; i++) wire_compress_point(points + 64 * i, out + 32 * i);
+  return MP_OK;
+}
+extern "C" int32_t mp_points_decompress(mp_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, int32_t* statuses) {
+  return wire_points_decompress(ctx, in, n, out, statuses);
+}
+extern "C" uint64_t mp_deck_serialized_len(uint64_t n_cards) { return wire_deck_len(n_cards); }
+extern "C" int32_t mp_deck_serialize(const uint8_t* deck, uint64_t n_cards, uint8_t* out) {
+  if (!out || (n_cards && !deck)) return MP_ERR_INVALID_ARG;
+  memcpy(out, &n_cards, 8);
+  for (uint64_t i = 0; i < 2 * n_cards; i++) wire_compress_point(deck + 64 * i, out + 8 + 32 * i);
+  return MP_OK;
+}
+extern "C" int32_t mp_deck_deserialize(mp_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards) {
+  return wire_deck_deserialize(ctx, in, in_len, out_deck, n_cards);
+}
+extern "C" uint64_t mp_proof_serialized_len(int32_t m, int32_t n) { return wire_proof_len(m, n); }
+extern "C" int32_t mp_proof_serialize(int32_t m, int32_t n, const uint8_t* proof, uint8_t* out) {
+  if (!proof || !out || m < 1 || n < 1) return MP_ERR_INVALID_ARG;
+  wire_proof_serialize(m, n, proof, out);
+  return MP_OK;
+}
+extern "C" int32_t mp_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof) {
+  return wire_proof_deserialize(ctx, m, n, in, out_proof);
 }
 
 extern "C" int32_t mp_msm_num_windows(int32_t window_bits) {

@@ -20,6 +20,7 @@ struct mp_ctx {
   int launches = 0;
   uint64_t last_ec_adds = 0;
   int last_window = 0;
+  bool wire_table_ready = false;  // sqrt table of wire.cu built in its scratch slot
 
   struct Buf { void* ptr = nullptr; size_t cap = 0; };
   std::vector<Buf> bufs;

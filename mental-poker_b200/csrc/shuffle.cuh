@@ -72,6 +72,11 @@ int32_t sigma_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks, const u
 int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const uint8_t* infos, const uint64_t* info_off,
                                          const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
 
+// Wire format, device half (wire.cu): batched point decompression
+int32_t wire_points_decompress(mp_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, int32_t* statuses);
+int32_t wire_deck_deserialize(mp_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards);
+int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof);
+
 bool shuffle_uses_small_deck_path(uint64_t n_cards);
 int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                             const uint8_t* rhos, const uint8_t* rands, uint64_t B, uint8_t* out_decks,

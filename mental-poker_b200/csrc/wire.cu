@@ -1,0 +1,172 @@
+// Wire format, device half: batched decompression of ark-serialize 0.3
+// compressed points -- y = sqrt(x^3 + x + b) in F_p, sign chosen by the "larger" flag.  The Stark prime
+// has p - 1 = 2^192 * (2^59 + 17), so the square root is Tonelli-Shanks with a 192-bit two-adic part:
+// the reference's CPU path (ark-ff 0.3 `SquareRootField::sqrt` behind `CanonicalDeserialize`, reached
+// from every type bound at reference src/lib.rs:45-71) spends ~10^4 field multiplications per point.
+//
+// k_decompress: one thread per point.
+//   w = a^((t-1)/2) (58 squarings + 4 multiplications), x = a w, b = x w = a^t;
+//   while b != 1:  k = order exponent of b (k squarings);  non-residue if k reaches v;
+//                  x *= T[191-k], b *= T[192-k], v = k      with T[i] = root^(2^i) precomputed
+// The table of the 192 powers of the root of unity replaces the textbook inner loop that squares the
+// running root v-k-1 times per round: ~4.6 k squarings per point instead of ~9 k.  Lanes of a warp
+// need different k, so the loops diverge; the work per lane is what it is (data dependent).
+#include "fq_sqrt.cuh"
+#include "shuffle_internal.cuh"
+#include "wire_host.hpp"
+
+namespace mp {
+
+__global__ void k_sqrt_table(fq* __restrict__ T) { fq_sqrt_table(T); }
+
+// status: 0 ok, 1 malformed (x not canonical / stray flag bits), 2 x is not the abscissa of a curve point
+__global__ void __launch_bounds__(128) k_decompress(const uint32_t* __restrict__ in, uint64_t n, const fq* __restrict__ T,
+                                                    uint32_t* __restrict__ out, uint8_t* __restrict__ status, int* __restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[8];
+  {
+    const uint4* p = reinterpret_cast<const uint4*>(in + i * 8);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+  }
+  const uint32_t flags = w[7] >> 30;  // bit 1 = larger, bit 0 = infinity
+  w[7] &= 0x3fffffffu;
+  uint32_t res[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) res[k] = 0;
+  uint8_t st = 0;
+  fq xc;
+#pragma unroll
+  for (int k = 0; k < 8; k++) xc.v[k] = w[k];
+  if (flags & 1u) {
+    if (!fq_is_zero_raw(xc) || (flags & 2u)) st = 1;
+  } else {
+    uint32_t borrow;
+    fq_sub_raw(xc, fq_kp(1), &borrow);
+    if (!borrow) {
+      st = 1;  // x >= p
+    } else {
+      const fq xm = fq_reduce_full(fq_to_mont(xc));
+      const fq rhs = fq_add(fq_add(fq_mul(fq_sqr(xm), xm), xm), fq_curve_b());  // [2] + [1] + [1]
+      bool ok;
+      const fq y = fq_sqrt(fq_reduce_weak(rhs), T, &ok);
+      if (!ok) {
+        st = 2;
+      } else {
+        fq yc = fq_from_mont(y);  // canonical
+        // larger of (y, p - y)  <=>  y > (p - 1) / 2
+        fq half;
+        half.v[0] = 0; half.v[1] = 0; half.v[2] = 0; half.v[3] = 0; half.v[4] = 0;
+        half.v[5] = 0x80000000u; half.v[6] = 0x00000008u; half.v[7] = 0x04000000u;
+        uint32_t le;  // borrow of half - y: set iff y > half
+        fq_sub_raw(half, yc, &le);
+        if ((le != 0) != ((flags & 2u) != 0)) {
+          uint32_t bw;
+          yc = fq_is_zero_raw(yc) ? yc : fq_sub_raw(fq_kp(1), yc, &bw);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { res[k] = w[k]; res[8 + k] = yc.v[k]; }
+      }
+    }
+  }
+  if (st) atomicExch(bad, 1);
+  if (status) status[i] = st;
+  uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+#pragma unroll
+  for (int q = 0; q < 4; q++) o[q] = make_uint4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+enum WireSlot { sWireIn = 200, sWireOut, sWireStatus, sWireTable };
+
+// device-resident decompression: d_in n*32 bytes -> d_out n*64 bytes (+ per-item status), asynchronous
+static int32_t decompress_device(mp_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint8_t* d_status, int* d_bad) {
+  fq* T = (fq*)ctx->scratch(sWireTable, sizeof(fq) * kTwoAdicity + 64);
+  NEED(T);
+  if (!ctx->wire_table_ready) {
+    k_sqrt_table<<<1, 1, 0, ctx->stream>>>(T);
+    ctx->wire_table_ready = true;
+    ctx->launches += 1;
+  }
+  k_decompress<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t*)d_in, n, T, (uint32_t*)d_out, d_status, d_bad);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return MP_OK;
+}
+
+int32_t wire_points_decompress(mp_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, int32_t* statuses) {
+  if (!ctx || (n && (!in || !out))) return MP_ERR_INVALID_ARG;
+  if (n >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "too many points");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  if (n == 0) return MP_OK;
+  uint8_t* d_in = (uint8_t*)ctx->scratch(sWireIn, n * 32);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(sWireOut, n * 64);
+  uint8_t* d_status = (uint8_t*)ctx->scratch(sWireStatus, n + 64);
+  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  NEED(d_in); NEED(d_out); NEED(d_status); NEED(d_bad);
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  CK(cudaMemcpyAsync(d_in, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = decompress_device(ctx, d_in, n, d_out, d_status, d_bad);
+  if (rc != MP_OK) return rc;
+  CK(cudaMemcpyAsync(out, d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint8_t> st;
+  if (statuses) {
+    st.resize(n);
+    CK(cudaMemcpyAsync(st.data(), d_status, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (statuses)
+    for (uint64_t i = 0; i < n; i++) statuses[i] = st[i];
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a compressed point is malformed or not on the Stark curve");
+  return MP_OK;
+}
+
+int32_t wire_deck_deserialize(mp_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards) {
+  if (!ctx || !in || !n_cards) return MP_ERR_INVALID_ARG;
+  if (in_len < 8) return ctx->fail(MP_ERR_INVALID_ARG, "serialized deck shorter than its length prefix");
+  uint64_t n;
+  memcpy(&n, in, 8);
+  if (n >= (1ull << 28) || in_len != wire_deck_len(n)) return ctx->fail(MP_ERR_INVALID_ARG, "length prefix %llu does not match the buffer", (unsigned long long)n);
+  if (*n_cards < n) { *n_cards = n; return ctx->fail(MP_ERR_INVALID_ARG, "output deck too small for %llu cards", (unsigned long long)n); }
+  *n_cards = n;
+  if (n && !out_deck) return MP_ERR_INVALID_ARG;
+  return wire_points_decompress(ctx, in + 8, 2 * n, out_deck, nullptr);
+}
+
+int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof) {
+  if (!ctx || !in || !out_proof || m < 1 || n < 1) return MP_ERR_INVALID_ARG;
+  // gather the compressed points, decompress them in one launch, scatter into the flat layout
+  const size_t npts = 11 * (size_t)m + 8;
+  std::vector<uint8_t> comp(npts * 32), pts(npts * 64);
+  {
+    const uint8_t* p = in;
+    uint8_t* c = comp.data();
+    for (const WireRun& r : wire_proof_runs(m, n)) {
+      if (r.points) { memcpy(c, p, 32 * r.count); c += 32 * r.count; }
+      p += 32 * r.count;
+    }
+  }
+  int32_t rc = wire_points_decompress(ctx, comp.data(), npts, pts.data(), nullptr);
+  if (rc != MP_OK) return rc;
+  const uint8_t *p = in, *q = pts.data();
+  for (const WireRun& r : wire_proof_runs(m, n)) {
+    if (r.points) {
+      memcpy(out_proof, q, 64 * r.count);
+      q += 64 * r.count;
+      out_proof += 64 * r.count;
+    } else {
+      memcpy(out_proof, p, 32 * r.count);
+      out_proof += 32 * r.count;
+    }
+    p += 32 * r.count;
+  }
+  return MP_OK;
+}
+
+}  // namespace mp

@@ -1121,3 +1121,102 @@ int oc_key_ownership_verify_batch(const uint8_t* g64, const uint8_t* pks, const 
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * ark-serialize 0.3 wire format [UPSTREAM-RECALL]:
+ * compressed SW affine = x (32 B LE) | flags in the top bits of the last byte (bit 7: y is the larger
+ * of (y, -y); bit 6: infinity).  Decompression = Tonelli-Shanks over F_p, p - 1 = 2^192 * (2^59 + 17),
+ * the algorithm ark-ff 0.3 runs for `sqrt` [UPSTREAM-RECALL].  As in oracle/py/wire.py.
+ * ------------------------------------------------------------------------------------------ */
+static fe SQRT_ROOT; /* 3^t, a primitive 2^192-th root of unity (Montgomery form) */
+static int g_sqrt_inited = 0;
+static void sqrt_init(void) {
+  if (g_sqrt_inited) return;
+  static const uint64_t T[4] = {0x0800000000000011ull, 0, 0, 0}; /* t = (p - 1) / 2^192 */
+  fe three;
+  fe_from_u64(&three, 3, &FQ);
+  fe_pow(&SQRT_ROOT, &three, T, &FQ);
+  g_sqrt_inited = 1;
+}
+/* returns 1 and a root in *r, or 0 if a is a non-residue */
+static int fe_sqrt(fe* r, const fe* a) {
+  if (fe_is_zero(a)) { fe_set_zero(r); return 1; }
+  static const uint64_t E[4] = {0x0400000000000008ull, 0, 0, 0}; /* (t - 1) / 2 */
+  fe w, x, b, z = SQRT_ROOT;
+  fe_pow(&w, a, E, &FQ);
+  fe_mul(&x, a, &w, &FQ);
+  fe_mul(&b, &x, &w, &FQ);
+  int v = 192;
+  while (!fe_eq(&b, &FQ.one)) {
+    int k = 0;
+    fe t2 = b;
+    while (!fe_eq(&t2, &FQ.one)) {
+      fe_sqr(&t2, &t2, &FQ);
+      if (++k == v) return 0;
+    }
+    fe ww = z;
+    for (int i = 0; i < v - k - 1; i++) fe_sqr(&ww, &ww, &FQ);
+    fe_sqr(&z, &ww, &FQ);
+    fe_mul(&b, &b, &z, &FQ);
+    fe_mul(&x, &x, &ww, &FQ);
+    v = k;
+  }
+  *r = x;
+  return 1;
+}
+/* canonical y > p - y ?  <=>  y > (p - 1) / 2 */
+static int y_is_larger(const fe* y) {
+  static const uint64_t HALF[4] = {0, 0, 0x8000000000000000ull, 0x0400000000000008ull};
+  uint64_t c[4];
+  fe_to_raw(c, y, &FQ);
+  for (int i = 3; i >= 0; i--)
+    if (c[i] != HALF[i]) return c[i] > HALF[i];
+  return 0;
+}
+int oc_points_compress(const uint8_t* points, uint64_t n, uint8_t* out) {
+  oracle_init();
+  for (uint64_t i = 0; i < n; i++) {
+    aff a;
+    aff_from_bytes64(&a, points + 64 * i);
+    uint8_t* o = out + 32 * i;
+    if (a.inf) { memset(o, 0, 32); o[31] = 0x40; continue; }
+    fe_to_bytes(o, &a.x, &FQ);
+    if (y_is_larger(&a.y)) o[31] |= 0x80;
+  }
+  return 0;
+}
+/* statuses[i] = 0 ok, 1 malformed (non-canonical x / stray flags), 2 x not on the curve */
+int oc_points_decompress(const uint8_t* in, uint64_t n, uint8_t* out, int32_t* statuses) {
+  oracle_init();
+  sqrt_init();
+  _Pragma("omp parallel for schedule(dynamic, 8) num_threads(g_threads)")
+  for (int64_t i = 0; i < (int64_t)n; i++) {
+    uint8_t xb[32];
+    memcpy(xb, in + 32 * i, 32);
+    const int flags = xb[31] & 0xC0;
+    xb[31] &= 0x3F;
+    uint8_t* o = out + 64 * i;
+    memset(o, 0, 64);
+    statuses[i] = 0;
+    int zero = 1;
+    for (int k = 0; k < 32; k++) zero &= xb[k] == 0;
+    if (flags & 0x40) { statuses[i] = (zero && !(flags & 0x80)) ? 0 : 1; continue; }
+    /* canonical: x < p */
+    static const uint8_t PB[32] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x11, 0, 0, 0, 0, 0, 0, 0x08};
+    int lt = 0;
+    for (int k = 31; k >= 0; k--)
+      if (xb[k] != PB[k]) { lt = xb[k] < PB[k]; break; }
+    if (!lt) { statuses[i] = 1; continue; }
+    fe x, rhs, y;
+    fe_from_bytes(&x, xb, &FQ);
+    fe_sqr(&rhs, &x, &FQ);
+    fe_mul(&rhs, &rhs, &x, &FQ);
+    fe_add(&rhs, &rhs, &x, &FQ);
+    fe_add(&rhs, &rhs, &CURVE_B, &FQ);
+    if (!fe_sqrt(&y, &rhs)) { statuses[i] = 2; continue; }
+    if (y_is_larger(&y) != ((flags & 0x80) != 0)) fe_neg(&y, &y, &FQ);
+    fe_to_bytes(o, &x, &FQ);
+    fe_to_bytes(o + 32, &y, &FQ);
+  }
+  return 0;
+}

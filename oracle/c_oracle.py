@@ -40,6 +40,8 @@ def load():
     lib.oc_verify_reveal_batch.argtypes = [cp, cp, cp, cp, cp, u64, vp]
     lib.oc_key_ownership_prove_batch.argtypes = [cp, cp, cp, cp, vp, cp, u64, cp]
     lib.oc_key_ownership_verify_batch.argtypes = [cp, cp, cp, vp, cp, u64, vp]
+    lib.oc_points_compress.argtypes = [cp, u64, cp]
+    lib.oc_points_decompress.argtypes = [cp, u64, cp, vp]
     lib.oracle_set_threads.argtypes = [i32]
     lib.oracle_set_msm_mode.argtypes = [i32]
     return lib
@@ -144,3 +146,18 @@ class COracle:
         st = (ctypes.c_int32 * max(n, 1))()
         self.lib.oc_key_ownership_verify_batch(g, pks, blob, off, proofs, n, st)
         return list(st)[:n]
+
+    # ---- wire format (oracle/py/wire.py)
+    def points_compress(self, points):
+        n = len(points) // 64
+        out = ctypes.create_string_buffer(32 * n)
+        self.lib.oc_points_compress(points, n, out)
+        return out.raw
+
+    def points_decompress(self, data):
+        """-> (points n*64 with zeros for rejected items, statuses: 0 ok, 1 malformed, 2 not on the curve)"""
+        n = len(data) // 32
+        out = ctypes.create_string_buffer(64 * n)
+        st = (ctypes.c_int32 * max(n, 1))()
+        self.lib.oc_points_decompress(data, n, out, st)
+        return out.raw, list(st)[:n]

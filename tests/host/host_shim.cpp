@@ -160,3 +160,28 @@ void h_schnorr_challenge(const uint8_t* info, uint64_t info_len, const uint8_t* 
 }
 int h_fr_bytes_canonical(const uint8_t* b) { return fr_bytes_canonical(b); }
 }
+
+// ---- wire format: square roots (csrc/fq_sqrt.cuh) and compression (csrc/wire_host.hpp)
+#include "../../mental-poker_b200/csrc/fq_sqrt.cuh"
+#include "../../mental-poker_b200/csrc/wire_host.hpp"
+extern "C" {
+// canonical a -> canonical root; returns 1 if a is a square, 0 otherwise
+int h_fq_sqrt(const uint32_t* a, uint32_t* out) {
+  static fq T[kTwoAdicity];
+  static bool ready = false;
+  if (!ready) { fq_sqrt_table(T); ready = true; }
+  fq x; memcpy(x.v, a, 32);
+  bool ok;
+  fq r = fq_sqrt(fq_reduce_full(fq_to_mont(x)), T, &ok);
+  fq c = fq_from_mont(r);
+  memcpy(out, c.v, 32);
+  return ok ? 1 : 0;
+}
+void h_wire_compress(const uint8_t* points, uint64_t n, uint8_t* out) {
+  for (uint64_t i = 0; i < n; i++) wire_compress_point(points + 64 * i, out + 32 * i);
+}
+uint64_t h_wire_proof_serialize(int m, int n, const uint8_t* proof, uint8_t* out) {
+  wire_proof_serialize(m, n, proof, out);
+  return wire_proof_len(m, n);
+}
+}

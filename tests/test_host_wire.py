@@ -1,0 +1,65 @@
+"""CPU test of the host-compiled halves of the wire format: the word-level Tonelli-Shanks of
+csrc/fq_sqrt.cuh (the device algorithm, compiled with g++) against the oracle's big-int square root,
+and the host-side compression / proof serialisation of csrc/wire_host.hpp against oracle/py/wire.py."""
+import ctypes
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle.py import stark, wire
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "wire_vectors.json")))
+SHUF = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json")))["shuffle"]
+h = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "host_shim.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "host", "host_shim.cpp")])
+    return ctypes.CDLL(out)
+
+
+def test_word_level_sqrt_matches_the_oracle(shim):
+    rnd = random.Random(4)
+    out = (ctypes.c_uint32 * 8)()
+    w = lambda x: (ctypes.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+    squares = nonsquares = 0
+    cases = [0, 1, 4, stark.P - 1, 2, 3] + [rnd.randrange(stark.P) for _ in range(60)] + [rnd.randrange(stark.P) ** 2 % stark.P for _ in range(20)]
+    for a in cases:
+        ok = shim.h_fq_sqrt(w(a), out)
+        r = sum(int(out[i]) << (32 * i) for i in range(8))
+        want = stark.fq_sqrt(a)
+        assert bool(ok) == (want is not None), a
+        if ok:
+            assert r * r % stark.P == a and r < stark.P
+            squares += 1
+        else:
+            nonsquares += 1
+    assert squares >= 30 and nonsquares >= 15
+
+
+def test_compression_and_proof_serialisation(shim):
+    pts = b"".join(h(fx["point"]) for fx in GOLD["points"])
+    out = ctypes.create_string_buffer(32 * len(GOLD["points"]))
+    shim.h_wire_compress(pts, ctypes.c_uint64(len(GOLD["points"])), out)
+    assert out.raw == b"".join(h(fx["compressed"]) for fx in GOLD["points"])
+    for fx in SHUF:
+        m, n, proof = fx["m"], fx["n"], h(fx["proof"])
+        buf = ctypes.create_string_buffer((11 * m + 8) * 32 + (5 * n + 9) * 32)
+        shim.h_wire_proof_serialize.restype = ctypes.c_uint64
+        assert shim.h_wire_proof_serialize(m, n, proof, buf) == len(buf.raw)
+        # walk the flat layout (include/mpshuffle.h) with the oracle's compressor
+        want, pos = b"", 0
+        for is_pt, cnt in [(1, 5 * m + 4), (0, 2 * n + 3), (1, 3), (0, 2 * n + 2), (1, 6 * m + 1), (0, n + 4)]:
+            for _ in range(cnt):
+                if is_pt:
+                    want += wire.compress(stark.point_from_bytes64(proof[pos:pos + 64])); pos += 64
+                else:
+                    want += proof[pos:pos + 32]; pos += 32
+        assert pos == len(proof) and buf.raw == want
