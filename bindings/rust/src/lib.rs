@@ -50,6 +50,13 @@ extern "C" {
     fn mp_key_ownership_prove_batch(ctx: *mut MpCtx, pks: *const u8, sks: *const u8, infos: *const u8,
                                     info_offsets: *const u64, omega: *const u8, n: u64, out_proofs: *mut u8,
                                     host_threads: i32) -> i32;
+    // CanonicalSerialize / CanonicalDeserialize of decks and proofs (bounds at src/lib.rs:45-71)
+    fn mp_deck_serialized_len(n_cards: u64) -> u64;
+    fn mp_deck_serialize(deck: *const u8, n_cards: u64, out: *mut u8) -> i32;
+    fn mp_deck_deserialize(ctx: *mut MpCtx, input: *const u8, in_len: u64, out_deck: *mut u8, n_cards: *mut u64) -> i32;
+    fn mp_proof_serialized_len(m: i32, n: i32) -> u64;
+    fn mp_proof_serialize(m: i32, n: i32, proof: *const u8, out: *mut u8) -> i32;
+    fn mp_proof_deserialize(ctx: *mut MpCtx, m: i32, n: i32, input: *const u8, out_proof: *mut u8) -> i32;
     fn mp_key_ownership_verify_batch(ctx: *mut MpCtx, pks: *const u8, infos: *const u8, info_offsets: *const u64,
                                      proofs: *const u8, n: u64, statuses: *mut i32, host_threads: i32) -> i32;
 }
