@@ -140,3 +140,21 @@ def test_full_deck_round_trip_2p16(sctx):
     wrong = bytearray(out); wrong[128 * 4242:128 * 4243] = out[128 * 4243:128 * 4244]
     st = sctx.verify_remask_batch(pk, masked, bytes(wrong), rproofs)
     assert st[4242] == 5 and st.count(0) == n - 1
+
+
+def test_scalars_above_the_group_order_act_modulo_n(sctx):
+    """Prover scalars are the caller's to reduce, but any 256-bit value must still act as its residue:
+    the fixed-base tables cover all 32 bytes and the variable-base window recoding carries out of the
+    top nibble."""
+    rng = np.random.default_rng(14)
+    pk = sctx.dbg_scalar_mul(G64, rand_scalars(rng, 1))
+    card = sctx.dbg_scalar_mul(G64, rand_scalars(rng, 1))
+    for big in (2 ** 256 - 1, 2 ** 255 + 12345, stark.N, stark.N + 1, 0xF << 252):
+        kb = big.to_bytes(32, "little")
+        want_c1 = pb(stark.mul(stark.G, big % stark.N))
+        masked, _ = sctx.mask_batch(pk, card, kb, b32(7))
+        assert masked[:64] == want_c1                                   # fixed base
+        c1 = stark.point_from_bytes64(masked[:64]) if big % stark.N else stark.G
+        deck = pb(c1) + card
+        tok, _ = sctx.reveal_batch(kb, pk, deck, b32(9))                # variable base: token = sk * c1
+        assert tok == pb(stark.mul(c1, big % stark.N))
