@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
       for (int w = 0; w < 64; w++) {
         uint32_t raw = ((k[w >> 3] >> ((w & 7) * 4)) & 0xfu) + carry;
         uint32_t enc;
-        if (raw > 8u) { enc = (16u - raw - 1u) | 8u; carry = 1u; }   // digit raw - 16 in [-7, -1]
+        if (raw == 16u) { enc = 0xfu; carry = 1u; }                  // nibble f + carry: digit 0, carry on
+        else if (raw > 8u) { enc = (16u - raw - 1u) | 8u; carry = 1u; }  // digit raw - 16 in [-7, -1]
         else { enc = raw ? raw - 1u : 0xfu; carry = 0u; }            // digit raw in [0, 8]
         if (enc != 0xfu && w > top) top = w;
         const uint32_t sh = (w & 7) * 4;
