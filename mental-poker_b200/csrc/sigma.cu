@@ -27,6 +27,34 @@ struct LcJob {
   uint32_t add_pt, sub_pt;  // arena points added with coefficient +1 / -1
   uint32_t out_pt;     // arena slot that receives the (affine) result, or kNone
 };
+// Jobs are regular: job i of a kind has field = base + stride * i (or none).  The host describes each
+// kind with 18 words and k_make_jobs expands them on the device -- the first version built and uploaded
+// 36 bytes per job (14 MB for a deck's worth of mask proofs).
+enum LcField { fVarPt0, fVarPt1, fVarSc0, fVarSc1, fFixSc0, fFixSc1, fAddPt, fSubPt, fOutPt, kLcFields };
+struct JobKind {
+  uint32_t base[kLcFields], stride[kLcFields];
+  JobKind() {
+    for (int f = 0; f < kLcFields; f++) { base[f] = kNone; stride[f] = 0; }
+  }
+  JobKind& set(LcField f, uint64_t b, uint32_t st = 1) {
+    base[f] = (uint32_t)b;
+    stride[f] = st;
+    return *this;
+  }
+};
+static_assert(sizeof(LcJob) == kLcFields * sizeof(uint32_t), "LcJob is an array of its fields");
+
+__global__ void __launch_bounds__(256) k_make_jobs(const JobKind* __restrict__ kinds, uint32_t nkinds, uint32_t n,
+                                                   uint32_t* __restrict__ jobs) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint64_t)nkinds * n) return;
+  const uint32_t k = (uint32_t)(g / n), i = (uint32_t)(g % n);
+#pragma unroll
+  for (int f = 0; f < kLcFields; f++) {
+    const uint32_t b = kinds[k].base[f];
+    jobs[g * kLcFields + f] = b == kNone ? kNone : b + kinds[k].stride[f] * i;
+  }
+}
 
 static constexpr int kTabWin8 = 32, kTabDigits8 = 255, kTabSize8 = kTabWin8 * kTabDigits8;  // layout of ShuffleState::d_tab
 
@@ -162,17 +190,13 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags };
-
-static LcJob job_none() {
-  LcJob j;
-  j.var_pt[0] = j.var_pt[1] = j.var_sc[0] = j.var_sc[1] = j.fix_sc[0] = j.fix_sc[1] = kNone;
-  j.add_pt = j.sub_pt = j.out_pt = kNone;
-  return j;
-}
+enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags, sSigKinds, sSigStage0, sSigStage1, sSigStage2 };
 
 // One batched call: a point arena (uploaded canonical points -> Montgomery, plus reserved result slots),
-// a scalar array, and launches of k_lincomb over host-built job lists.
+// a scalar array, and launches of k_lincomb over job lists expanded on the device.  Caller buffers are
+// pageable and often strided (160-byte proof records): they are uploaded whole, once, and picked apart
+// by device-to-device 2D copies -- a strided host-to-device copy of 32-byte rows is an order of magnitude
+// slower than the contiguous copy of the same records.
 struct SigmaCall {
   mp_ctx* ctx;
   ShuffleState* S;
@@ -198,15 +222,34 @@ struct SigmaCall {
     CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
     return MP_OK;
   }
-  // `count` points, `src_pitch` bytes apart, `width` = 64 * (points per record), into arena slot `first`
-  int32_t put_points(uint64_t first, const uint8_t* src, uint64_t records, size_t width, size_t src_pitch) {
-    if (!records) return MP_OK;
-    CK(cudaMemcpy2DAsync(d_canon + first * 64, width, src, src_pitch, width, records, cudaMemcpyHostToDevice, st));
+  // uploads a caller buffer whole into staging slot `which` (0..2); *d receives the device copy
+  int32_t stage(int which, const uint8_t* src, size_t bytes, const uint8_t** d) {
+    uint8_t* p = (uint8_t*)ctx->scratch(sSigStage0 + which, bytes + 64);
+    NEED(p);
+    CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st));
+    *d = p;
     return MP_OK;
   }
-  int32_t put_scalars(uint64_t first, const uint8_t* src, uint64_t count, size_t src_pitch = 32) {
+  // `records` rows of `width` bytes, `pitch` bytes apart in a staged (device) buffer -> arena slot / scalar `first`
+  int32_t points_from(uint64_t first, const uint8_t* d_src, uint64_t records, size_t width, size_t pitch) {
+    if (!records) return MP_OK;
+    CK(cudaMemcpy2DAsync(d_canon + first * 64, width, d_src, pitch, width, records, cudaMemcpyDeviceToDevice, st));
+    return MP_OK;
+  }
+  int32_t scalars_from(uint64_t first, const uint8_t* d_src, uint64_t count, size_t pitch) {
     if (!count) return MP_OK;
-    CK(cudaMemcpy2DAsync(d_scal + first * 8, 32, src, src_pitch, 32, count, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(d_scal + first * 8, 32, d_src, pitch, 32, count, cudaMemcpyDeviceToDevice, st));
+    return MP_OK;
+  }
+  // contiguous caller buffers go straight to their place
+  int32_t put_points(uint64_t first, const uint8_t* src, uint64_t count) {
+    if (!count) return MP_OK;
+    CK(cudaMemcpyAsync(d_canon + first * 64, src, count * 64, cudaMemcpyHostToDevice, st));
+    return MP_OK;
+  }
+  int32_t put_scalars(uint64_t first, const uint8_t* src, uint64_t count) {
+    if (!count) return MP_OK;
+    CK(cudaMemcpyAsync(d_scal + first * 8, src, count * 32, cudaMemcpyHostToDevice, st));
     return MP_OK;
   }
   int32_t ingest() {  // canonical -> Montgomery, canonical + on-curve validation
@@ -214,21 +257,25 @@ struct SigmaCall {
     ctx->launches += 1;
     return MP_OK;
   }
-  // runs the jobs; canonical results (64 B per job) to h_canon and/or identity flags to h_flags
-  int32_t run(const std::vector<LcJob>& jobs, uint8_t* h_canon, uint8_t* h_flags) {
-    const uint32_t nj = (uint32_t)jobs.size();
+  // runs kinds.size() * n jobs (kind-major); canonical results (64 B per job) to h_canon and/or identity
+  // flags to h_flags (host pointers, ideally pinned)
+  int32_t run(const std::vector<JobKind>& kinds, uint64_t n, uint8_t* h_canon, uint8_t* h_flags) {
+    const uint32_t nk = (uint32_t)kinds.size(), nj = (uint32_t)(nk * n);
     if (!nj) return MP_OK;
+    JobKind* d_kinds = (JobKind*)ctx->scratch(sSigKinds, sizeof(JobKind) * 16);
     LcJob* d_jobs = (LcJob*)ctx->scratch(sSigJobs, (size_t)nj * sizeof(LcJob));
     uint32_t* d_out = h_canon ? (uint32_t*)ctx->scratch(sSigOut, (size_t)nj * 64) : nullptr;
     uint8_t* d_flags = h_flags ? (uint8_t*)ctx->scratch(sSigFlags, (size_t)nj + 64) : nullptr;
-    NEED(d_jobs);
+    NEED(d_kinds); NEED(d_jobs);
+    if (nk > 16) return ctx->fail(MP_ERR_INVALID_ARG, "internal: too many job kinds");
     if (h_canon) NEED(d_out);
     if (h_flags) NEED(d_flags);
-    CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(LcJob), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_kinds, kinds.data(), sizeof(JobKind) * nk, cudaMemcpyHostToDevice, st));
+    k_make_jobs<<<(nj + 255) / 256, 256, 0, st>>>(d_kinds, nk, (uint32_t)n, (uint32_t*)d_jobs);
     k_lincomb<<<(nj + 127) / 128, 128, 0, st>>>(d_jobs, nj, d_arena, d_scal, S->d_tab, (h_canon ? 1 : 0) | (h_flags ? 2 : 0), d_out,
                                                 d_flags);
     CK(cudaGetLastError());
-    ctx->launches += 1;
+    ctx->launches += 2;
     if (h_canon) CK(cudaMemcpyAsync(h_canon, d_out, (size_t)nj * 64, cudaMemcpyDeviceToHost, st));
     if (h_flags) CK(cudaMemcpyAsync(h_flags, d_flags, (size_t)nj, cudaMemcpyDeviceToHost, st));
     int bad = 0;
@@ -281,34 +328,31 @@ static int32_t cp_fixed_prove(mp_ctx* ctx, bool remask, const uint8_t* pk, const
   const uint64_t per = remask ? 2 : 1;  // input points per item
   SigmaCall sc;
   if ((rc = sc.init(ctx, per * n, 0, 2 * n)) != MP_OK) return rc;
-  if ((rc = sc.put_points(0, in, n, 64 * per, 64 * per)) != MP_OK) return rc;
-  if ((rc = sc.put_scalars(0, wit, n)) != MP_OK) return rc;
-  if ((rc = sc.put_scalars(n, omega, n)) != MP_OK) return rc;
+  if ((rc = sc.put_points(0, in, per * n)) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(0, wit, n)) != MP_OK) return rc;       // scalars [0, n): witness w
+  if ((rc = sc.put_scalars(n, omega, n)) != MP_OK) return rc;     // scalars [n, 2n): omega
   if ((rc = sc.ingest()) != MP_OK) return rc;
   // kinds: 0 s0 = w g | 1 s1 = w pk | 2 a = omega g | 3 b = omega pk | 4 out.c1 | 5 out.c2
   //   mask:   out.c1 = s0 (no extra job), out.c2 = card + w pk
   //   remask: out.c1 = in.c1 + w g,       out.c2 = in.c2 + w pk
-  const int kinds = remask ? 6 : 5;
-  std::vector<LcJob> jobs((size_t)kinds * n, job_none());
-  for (uint64_t i = 0; i < n; i++) {
-    const uint32_t w = (uint32_t)i, om = (uint32_t)(n + i);
-    jobs[0 * n + i].fix_sc[0] = w;
-    jobs[1 * n + i].fix_sc[1] = w;
-    jobs[2 * n + i].fix_sc[0] = om;
-    jobs[3 * n + i].fix_sc[1] = om;
-    if (remask) {
-      jobs[4 * n + i].fix_sc[0] = w; jobs[4 * n + i].add_pt = (uint32_t)(2 * i);
-      jobs[5 * n + i].fix_sc[1] = w; jobs[5 * n + i].add_pt = (uint32_t)(2 * i + 1);
-    } else {
-      jobs[4 * n + i].fix_sc[1] = w; jobs[4 * n + i].add_pt = (uint32_t)i;
-    }
+  std::vector<JobKind> kinds(remask ? 6 : 5);
+  kinds[0].set(fFixSc0, 0);
+  kinds[1].set(fFixSc1, 0);
+  kinds[2].set(fFixSc0, n);
+  kinds[3].set(fFixSc1, n);
+  if (remask) {
+    kinds[4].set(fFixSc0, 0).set(fAddPt, 0, 2);
+    kinds[5].set(fFixSc1, 0).set(fAddPt, 1, 2);
+  } else {
+    kinds[4].set(fFixSc1, 0).set(fAddPt, 0);
   }
-  std::vector<uint8_t> res((size_t)kinds * n * 64);
-  if ((rc = sc.run(jobs, res.data(), nullptr)) != MP_OK) return rc;
-  const ShuffleState* S = ctx->shuffle;
+  ShuffleState* S = ctx->shuffle;
+  uint8_t* res = pinned(S, kinds.size() * n * 64);
+  if (!res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  if ((rc = sc.run(kinds, n, res, nullptr)) != MP_OK) return rc;
   const char* seed = remask ? kSeedRemasking : kSeedMasking;
   const Transcript seeded(seed, strlen(seed));
-  auto R = [&](int kind, uint64_t i) { return res.data() + ((size_t)kind * n + i) * 64; };
+  auto R = [&](int kind, uint64_t i) { return res + ((size_t)kind * n + i) * 64; };
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
     const fr c = cp_challenge(seeded, S->enc_g, pk, R(0, i), R(1, i), R(2, i), R(3, i));
     const fr r = fr_add(fr_from_bytes(omega + 32 * i), fr_mul(c, fr_from_bytes(wit + 32 * i)));
@@ -334,68 +378,51 @@ static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, cons
   if (!pk || (n && (!in || !out || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
   if (n == 0) return MP_OK;
   if ((rc = shuffle_ensure_pk_table(ctx, pk)) != MP_OK) return rc;
-  // arena: [inputs: n or 2n] [outputs: 2n] [a, b: 2n] | reserved statement slots [s0, s1: 2n]
+  // arena: [inputs: n or 2n] [outputs: 2n] [a, b: 2n] | reserved statement slots [s0: n] [s1: n]
   const uint64_t per = remask ? 2 : 1;
   const uint64_t oIn = 0, oOut = per * n, oAB = oOut + 2 * n, oS = oAB + 2 * n;
   SigmaCall sc;
   if ((rc = sc.init(ctx, oS, 2 * n, 2 * n)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oIn, in, n, 64 * per, 64 * per)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oOut, out, n, 128, 128)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oAB, proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
-  if ((rc = sc.put_scalars(0, proofs + 128, n, kCpProofLen)) != MP_OK) return rc;  // responses r
+  const uint8_t* d_proofs;
+  if ((rc = sc.put_points(oIn, in, per * n)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oOut, out, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.stage(0, proofs, n * kCpProofLen, &d_proofs)) != MP_OK) return rc;
+  if ((rc = sc.points_from(oAB, d_proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.scalars_from(0, d_proofs + 128, n, kCpProofLen)) != MP_OK) return rc;  // scalars [0, n): responses r
   if ((rc = sc.ingest()) != MP_OK) return rc;
   // pass 1: the statement.  mask: s0 = out.c1 (no job), s1 = out.c2 - card;  remask: s = out - in
-  std::vector<LcJob> jobs;
-  std::vector<uint8_t> stmt;
+  std::vector<JobKind> kinds;
   if (remask) {
-    jobs.assign(2 * n, job_none());
-    for (uint64_t i = 0; i < n; i++)
-      for (int k = 0; k < 2; k++) {
-        LcJob& j = jobs[(size_t)k * n + i];
-        j.add_pt = (uint32_t)(oOut + 2 * i + k);
-        j.sub_pt = (uint32_t)(oIn + 2 * i + k);
-        j.out_pt = (uint32_t)(oS + (size_t)k * n + i);
-      }
+    kinds.resize(2);
+    for (int k = 0; k < 2; k++) kinds[k].set(fAddPt, oOut + k, 2).set(fSubPt, oIn + k, 2).set(fOutPt, oS + (uint64_t)k * n);
   } else {
-    jobs.assign(n, job_none());
-    for (uint64_t i = 0; i < n; i++) {
-      jobs[i].add_pt = (uint32_t)(oOut + 2 * i + 1);
-      jobs[i].sub_pt = (uint32_t)(oIn + i);
-      jobs[i].out_pt = (uint32_t)(oS + n + i);
-    }
+    kinds.resize(1);
+    kinds[0].set(fAddPt, oOut + 1, 2).set(fSubPt, oIn).set(fOutPt, oS + n);
   }
-  stmt.resize(jobs.size() * 64);
-  if ((rc = sc.run(jobs, stmt.data(), nullptr)) != MP_OK) return rc;
+  ShuffleState* S = ctx->shuffle;
+  const size_t stmt_bytes = kinds.size() * n * 64;
+  uint8_t* pin = pinned(S, stmt_bytes + 2 * n + 64);
+  if (!pin) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  uint8_t *stmt = pin, *flags = pin + stmt_bytes;
+  if ((rc = sc.run(kinds, n, stmt, nullptr)) != MP_OK) return rc;
   // challenges (host), uploaded negated:  r g - c s0 - a == O  and  r pk - c s1 - b == O
-  const ShuffleState* S = ctx->shuffle;
   const char* seed = remask ? kSeedRemasking : kSeedMasking;
   const Transcript seeded(seed, strlen(seed));
-  std::vector<uint8_t> negc((size_t)n * 32);
-  std::vector<uint8_t> canon_ok((size_t)n);
+  std::vector<uint8_t> negc((size_t)n * 32), canon_ok((size_t)n);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
     const uint8_t* p = proofs + kCpProofLen * i;
-    const uint8_t* s0 = remask ? stmt.data() + 64 * i : out + 128 * i;
-    const uint8_t* s1 = remask ? stmt.data() + 64 * (n + i) : stmt.data() + 64 * i;
+    const uint8_t* s0 = remask ? stmt + 64 * i : out + 128 * i;
+    const uint8_t* s1 = remask ? stmt + 64 * (n + i) : stmt + 64 * i;
     const fr c = cp_challenge(seeded, S->enc_g, pk, s0, s1, p, p + 64);
     fr_to_bytes(fr_neg(c), negc.data() + 32 * i);
     canon_ok[i] = fr_bytes_canonical(p + 128);
   });
-  if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;
-  jobs.assign(2 * n, job_none());
-  for (uint64_t i = 0; i < n; i++) {
-    LcJob& j0 = jobs[i];
-    j0.fix_sc[0] = (uint32_t)i;
-    j0.var_pt[0] = remask ? (uint32_t)(oS + i) : (uint32_t)(oOut + 2 * i);
-    j0.var_sc[0] = (uint32_t)(n + i);
-    j0.sub_pt = (uint32_t)(oAB + 2 * i);
-    LcJob& j1 = jobs[n + i];
-    j1.fix_sc[1] = (uint32_t)i;
-    j1.var_pt[0] = (uint32_t)(oS + n + i);
-    j1.var_sc[0] = (uint32_t)(n + i);
-    j1.sub_pt = (uint32_t)(oAB + 2 * i + 1);
-  }
-  std::vector<uint8_t> flags(2 * n);
-  if ((rc = sc.run(jobs, nullptr, flags.data())) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;  // scalars [n, 2n): -c
+  kinds.assign(2, JobKind());
+  kinds[0].set(fFixSc0, 0).set(fVarSc0, n).set(fSubPt, oAB, 2);
+  if (remask) kinds[0].set(fVarPt0, oS); else kinds[0].set(fVarPt0, oOut, 2);
+  kinds[1].set(fFixSc1, 0).set(fVarPt0, oS + n).set(fVarSc0, n).set(fSubPt, oAB + 1, 2);
+  if ((rc = sc.run(kinds, n, nullptr, flags)) != MP_OK) return rc;
   for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
   return MP_OK;
 }
@@ -426,23 +453,24 @@ int32_t sigma_reveal_batch(mp_ctx* ctx, const uint8_t* sk, const uint8_t* pk, co
   if (n == 0) return MP_OK;
   SigmaCall sc;
   if ((rc = sc.init(ctx, n, 0, n + 1)) != MP_OK) return rc;
-  if ((rc = sc.put_points(0, masked, n, 64, 128)) != MP_OK) return rc;  // c1 of every card
+  const uint8_t* d_masked;
+  if ((rc = sc.stage(0, masked, n * 128, &d_masked)) != MP_OK) return rc;
+  if ((rc = sc.points_from(0, d_masked, n, 64, 128)) != MP_OK) return rc;  // c1 of every card
   if ((rc = sc.put_scalars(0, omega, n)) != MP_OK) return rc;
   if ((rc = sc.put_scalars(n, sk, 1)) != MP_OK) return rc;
   if ((rc = sc.ingest()) != MP_OK) return rc;
-  std::vector<LcJob> jobs(3 * n, job_none());  // kinds: token = sk c1 | a = omega c1 | b = omega g
-  for (uint64_t i = 0; i < n; i++) {
-    jobs[i].var_pt[0] = (uint32_t)i; jobs[i].var_sc[0] = (uint32_t)n;
-    jobs[n + i].var_pt[0] = (uint32_t)i; jobs[n + i].var_sc[0] = (uint32_t)i;
-    jobs[2 * n + i].fix_sc[0] = (uint32_t)i;
-  }
-  std::vector<uint8_t> res(3 * n * 64);
-  if ((rc = sc.run(jobs, res.data(), nullptr)) != MP_OK) return rc;
-  const ShuffleState* S = ctx->shuffle;
+  std::vector<JobKind> kinds(3);  // token = sk c1 | a = omega c1 | b = omega g
+  kinds[0].set(fVarPt0, 0).set(fVarSc0, n, 0);
+  kinds[1].set(fVarPt0, 0).set(fVarSc0, 0);
+  kinds[2].set(fFixSc0, 0);
+  ShuffleState* S = ctx->shuffle;
+  uint8_t* res = pinned(S, 3 * n * 64);
+  if (!res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  if ((rc = sc.run(kinds, n, res, nullptr)) != MP_OK) return rc;
   const Transcript seeded(kSeedReveal, strlen(kSeedReveal));
   const fr skf = fr_from_bytes(sk);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
-    const uint8_t *tok = res.data() + 64 * i, *a = res.data() + 64 * (n + i), *b = res.data() + 64 * (2 * n + i);
+    const uint8_t *tok = res + 64 * i, *a = res + 64 * (n + i), *b = res + 64 * (2 * n + i);
     const fr c = cp_challenge(seeded, masked + 128 * i, S->enc_g, tok, pk, a, b);
     const fr r = fr_add(fr_from_bytes(omega + 32 * i), fr_mul(c, skf));
     memcpy(out_tokens + 64 * i, tok, 64);
@@ -464,13 +492,16 @@ int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t*
   const uint64_t oC1 = 0, oTok = n, oAB = 2 * n, oPk = 4 * n;
   SigmaCall sc;
   if ((rc = sc.init(ctx, 4 * n + 1, 0, 2 * n)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oC1, masked, n, 64, 128)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oTok, tokens, n, 64, 64)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oAB, proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
-  if ((rc = sc.put_points(oPk, pk, 1, 64, 64)) != MP_OK) return rc;
-  if ((rc = sc.put_scalars(0, proofs + 128, n, kCpProofLen)) != MP_OK) return rc;
+  const uint8_t *d_masked, *d_proofs;
+  if ((rc = sc.stage(0, masked, n * 128, &d_masked)) != MP_OK) return rc;
+  if ((rc = sc.stage(1, proofs, n * kCpProofLen, &d_proofs)) != MP_OK) return rc;
+  if ((rc = sc.points_from(oC1, d_masked, n, 64, 128)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oTok, tokens, n)) != MP_OK) return rc;
+  if ((rc = sc.points_from(oAB, d_proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.put_points(oPk, pk, 1)) != MP_OK) return rc;
+  if ((rc = sc.scalars_from(0, d_proofs + 128, n, kCpProofLen)) != MP_OK) return rc;  // scalars [0, n): r
   if ((rc = sc.ingest()) != MP_OK) return rc;
-  const ShuffleState* S = ctx->shuffle;
+  ShuffleState* S = ctx->shuffle;
   const Transcript seeded(kSeedReveal, strlen(kSeedReveal));
   std::vector<uint8_t> negc((size_t)n * 32), canon_ok((size_t)n);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {  // overlaps the uploads
@@ -479,20 +510,13 @@ int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t*
     fr_to_bytes(fr_neg(c), negc.data() + 32 * i);
     canon_ok[i] = fr_bytes_canonical(p + 128);
   });
-  if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;
-  std::vector<LcJob> jobs(2 * n, job_none());  // r c1 - c token - a  |  r g - c pk - b
-  for (uint64_t i = 0; i < n; i++) {
-    LcJob& j0 = jobs[i];
-    j0.var_pt[0] = (uint32_t)(oC1 + i); j0.var_sc[0] = (uint32_t)i;
-    j0.var_pt[1] = (uint32_t)(oTok + i); j0.var_sc[1] = (uint32_t)(n + i);
-    j0.sub_pt = (uint32_t)(oAB + 2 * i);
-    LcJob& j1 = jobs[n + i];
-    j1.fix_sc[0] = (uint32_t)i;
-    j1.var_pt[0] = (uint32_t)oPk; j1.var_sc[0] = (uint32_t)(n + i);
-    j1.sub_pt = (uint32_t)(oAB + 2 * i + 1);
-  }
-  std::vector<uint8_t> flags(2 * n);
-  if ((rc = sc.run(jobs, nullptr, flags.data())) != MP_OK) return rc;
+  if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;  // scalars [n, 2n): -c
+  std::vector<JobKind> kinds(2);  // r c1 - c token - a  |  r g - c pk - b
+  kinds[0].set(fVarPt0, oC1).set(fVarSc0, 0).set(fVarPt1, oTok).set(fVarSc1, n).set(fSubPt, oAB, 2);
+  kinds[1].set(fFixSc0, 0).set(fVarPt0, oPk, 0).set(fVarSc0, n).set(fSubPt, oAB + 1, 2);
+  uint8_t* flags = pinned(S, 2 * n + 64);
+  if (!flags) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  if ((rc = sc.run(kinds, n, nullptr, flags)) != MP_OK) return rc;
   for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
   return MP_OK;
 }
@@ -508,13 +532,14 @@ int32_t sigma_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks, const u
   SigmaCall sc;
   if ((rc = sc.init(ctx, 0, 0, n)) != MP_OK) return rc;
   if ((rc = sc.put_scalars(0, omega, n)) != MP_OK) return rc;
-  std::vector<LcJob> jobs(n, job_none());  // commit = omega g
-  for (uint64_t i = 0; i < n; i++) jobs[i].fix_sc[0] = (uint32_t)i;
-  std::vector<uint8_t> res(n * 64);
-  if ((rc = sc.run(jobs, res.data(), nullptr)) != MP_OK) return rc;
-  const ShuffleState* S = ctx->shuffle;
+  std::vector<JobKind> kinds(1);  // commit = omega g
+  kinds[0].set(fFixSc0, 0);
+  ShuffleState* S = ctx->shuffle;
+  uint8_t* res = pinned(S, n * 64);
+  if (!res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  if ((rc = sc.run(kinds, n, res, nullptr)) != MP_OK) return rc;
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
-    const uint8_t* commit = res.data() + 64 * i;
+    const uint8_t* commit = res + 64 * i;
     const fr c = schnorr_challenge(infos ? infos + info_off[i] : nullptr, (size_t)(info_off[i + 1] - info_off[i]), S->enc_g,
                                    pks + 64 * i, commit);
     const fr op = fr_sub(fr_from_bytes(omega + 32 * i), fr_mul(c, fr_from_bytes(sks + 32 * i)));
@@ -533,11 +558,13 @@ int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const 
   if (n == 0) return MP_OK;
   SigmaCall sc;  // arena: [pk: n] [commit: n];  scalars: [opening: n] [c: n]
   if ((rc = sc.init(ctx, 2 * n, 0, 2 * n)) != MP_OK) return rc;
-  if ((rc = sc.put_points(0, pks, n, 64, 64)) != MP_OK) return rc;
-  if ((rc = sc.put_points(n, proofs, n, 64, kSchnorrProofLen)) != MP_OK) return rc;
-  if ((rc = sc.put_scalars(0, proofs + 64, n, kSchnorrProofLen)) != MP_OK) return rc;
+  const uint8_t* d_proofs;
+  if ((rc = sc.put_points(0, pks, n)) != MP_OK) return rc;
+  if ((rc = sc.stage(0, proofs, n * kSchnorrProofLen, &d_proofs)) != MP_OK) return rc;
+  if ((rc = sc.points_from(n, d_proofs, n, 64, kSchnorrProofLen)) != MP_OK) return rc;
+  if ((rc = sc.scalars_from(0, d_proofs + 64, n, kSchnorrProofLen)) != MP_OK) return rc;
   if ((rc = sc.ingest()) != MP_OK) return rc;
-  const ShuffleState* S = ctx->shuffle;
+  ShuffleState* S = ctx->shuffle;
   std::vector<uint8_t> cs((size_t)n * 32), canon_ok((size_t)n);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
     const uint8_t* p = proofs + kSchnorrProofLen * i;
@@ -547,14 +574,11 @@ int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const 
     canon_ok[i] = fr_bytes_canonical(p + 64);
   });
   if ((rc = sc.put_scalars(n, cs.data(), n)) != MP_OK) return rc;
-  std::vector<LcJob> jobs(n, job_none());  // opening g + c pk - commit == O
-  for (uint64_t i = 0; i < n; i++) {
-    jobs[i].fix_sc[0] = (uint32_t)i;
-    jobs[i].var_pt[0] = (uint32_t)i; jobs[i].var_sc[0] = (uint32_t)(n + i);
-    jobs[i].sub_pt = (uint32_t)(n + i);
-  }
-  std::vector<uint8_t> flags(n);
-  if ((rc = sc.run(jobs, nullptr, flags.data())) != MP_OK) return rc;
+  std::vector<JobKind> kinds(1);  // opening g + c pk - commit == O
+  kinds[0].set(fFixSc0, 0).set(fVarPt0, 0).set(fVarSc0, n).set(fSubPt, n);
+  uint8_t* flags = pinned(S, n + 64);
+  if (!flags) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
+  if ((rc = sc.run(kinds, n, nullptr, flags)) != MP_OK) return rc;
   for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && canon_ok[i]) ? MP_OK : MP_VERIFY_SCHNORR;
   return MP_OK;
 }
