@@ -28,16 +28,29 @@ inline constexpr size_t kSchnorrProofLen = 96;   // commit (64) | opening (32)
 
 // c = challenge after absorbing  "chaum_pedersen" | g | h | s0 | s1 | a | b  into a transcript seeded
 // with `seeded` (passed by value: from_seed is hashed once per batch, not once per proof)
+// 64-byte C-ABI point (all-zero = identity) -> the 65-byte ark-ec encoding the transcript absorbs
+inline void point65(const uint8_t* p64, uint8_t* out65) {
+  uint64_t w[8];
+  memcpy(w, p64, 64);
+  if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
+    memset(out65, 0, 65);  // identity = (0, 1, infinity)
+    out65[32] = 1;
+    out65[64] = 1;
+  } else {
+    memcpy(out65, p64, 64);
+    out65[64] = 0;
+  }
+}
+
 inline fr cp_challenge(Transcript seeded, const uint8_t* g, const uint8_t* h, const uint8_t* s0, const uint8_t* s1,
                        const uint8_t* a, const uint8_t* b) {
+  // one 404-byte message, fed in one piece: the long-input Blake2s path takes six of its seven blocks
+  uint8_t msg[14 + 6 * 65];
+  memcpy(msg, "chaum_pedersen", 14);
+  const uint8_t* pts[6] = {g, h, s0, s1, a, b};
+  for (int k = 0; k < 6; k++) point65(pts[k], msg + 14 + 65 * k);
   seeded.begin();
-  seeded.feed_label("chaum_pedersen");
-  seeded.feed_points64(g, 1);
-  seeded.feed_points64(h, 1);
-  seeded.feed_points64(s0, 1);
-  seeded.feed_points64(s1, 1);
-  seeded.feed_points64(a, 1);
-  seeded.feed_points64(b, 1);
+  seeded.feed(msg, sizeof msg);
   seeded.end();
   return seeded.challenge();
 }

@@ -177,6 +177,36 @@ int h_fq_sqrt(const uint32_t* a, uint32_t* out) {
   memcpy(out, c.v, 32);
   return ok ? 1 : 0;
 }
+// the windowed form the GPU runs; returns 1 if a is a square.  *distinct_keys = number of distinct lut keys (must be 256)
+int h_fq_sqrt_win(const uint32_t* a, uint32_t* out, int* distinct_keys) {
+  static fq T[kTwoAdicity], Tinv[kTwoAdicity];
+  static std::vector<fq> U(kSqrtUCount), V(kSqrtVCount);
+  static std::vector<uint8_t> lut(65536, 0xff), hit(65536, 0);
+  static bool ready = false;
+  static int keys = 0;
+  if (!ready) {
+    fq_sqrt_table(T);
+    fq_sqrt_inverse_table(T, Tinv);
+    for (size_t g = 0; g < kSqrtUCount + kSqrtVCount + kSqrtRadix; g++) fq_sqrt_fill_entry(T, Tinv, g, U.data(), V.data(), lut.data());
+    // the 256 roots of unity must land on 256 distinct lut keys
+    for (uint32_t j = 0; j < (uint32_t)kSqrtRadix; j++) {
+      fq acc = fq_one();
+      for (int k = 0; k < kSqrtWin; k++)
+        if ((j >> k) & 1u) acc = fq_mul(acc, T[kTwoAdicity - kSqrtWin + k]);
+      uint32_t key = fq_sqrt_key(fq_reduce_full(acc));
+      if (!hit[key]) { hit[key] = 1; keys++; }
+    }
+    ready = true;
+  }
+  *distinct_keys = keys;
+  fq x; memcpy(x.v, a, 32);
+  bool ok;
+  SqrtTables tb{U.data(), V.data(), lut.data()};
+  fq r = fq_sqrt_win(fq_reduce_full(fq_to_mont(x)), tb, &ok);
+  fq c = fq_from_mont(r);
+  memcpy(out, c.v, 32);
+  return ok ? 1 : 0;
+}
 void h_wire_compress(const uint8_t* points, uint64_t n, uint8_t* out) {
   for (uint64_t i = 0; i < n; i++) wire_compress_point(points + 64 * i, out + 32 * i);
 }

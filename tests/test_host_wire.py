@@ -44,6 +44,31 @@ def test_word_level_sqrt_matches_the_oracle(shim):
     assert squares >= 30 and nonsquares >= 15
 
 
+def test_windowed_sqrt_matches_the_oracle(shim):
+    """The uniform-control-flow form the GPU runs (8-bit windows over the 192-bit discrete log)."""
+    rnd = random.Random(5)
+    out = (ctypes.c_uint32 * 8)()
+    keys = ctypes.c_int(0)
+    w = lambda x: (ctypes.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+    squares = nonsquares = 0
+    cases = [0, 1, 4, stark.P - 1, 2, 3] + [rnd.randrange(stark.P) for _ in range(80)] + [rnd.randrange(stark.P) ** 2 % stark.P for _ in range(40)]
+    # elements of small 2-power order: every window of the discrete log but a few is zero
+    t = (stark.P - 1) >> 192
+    zeta = pow(3, t, stark.P)
+    cases += [pow(zeta, 1 << s, stark.P) for s in (1, 7, 8, 9, 100, 183, 184, 190, 191)]
+    for a in cases:
+        ok = shim.h_fq_sqrt_win(w(a), out, ctypes.byref(keys))
+        assert keys.value == 256
+        r = sum(int(out[i]) << (32 * i) for i in range(8))
+        assert bool(ok) == (stark.fq_sqrt(a) is not None), a
+        if ok:
+            assert r * r % stark.P == a and r < stark.P
+            squares += 1
+        else:
+            nonsquares += 1
+    assert squares >= 60 and nonsquares >= 20
+
+
 def test_compression_and_proof_serialisation(shim):
     pts = b"".join(h(fx["point"]) for fx in GOLD["points"])
     out = ctypes.create_string_buffer(32 * len(GOLD["points"]))
