@@ -9,7 +9,7 @@
 // multiplications -- 242 squarings + 304 multiplications with the same control flow in every lane.  The
 // first version ran the textbook loop (order exponent of b by repeated squaring, per round): ~4 600
 // data-dependent squarings per point, lanes diverging on every round -- 16.2 ms for the 131 072 points of
-// a deck against 2.9 ms now (profiles/).
+// a deck against 0.79 ms now (ncu, profiles/).
 #include "fq_sqrt.cuh"
 #include "shuffle_internal.cuh"
 #include "wire_host.hpp"
