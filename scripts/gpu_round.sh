@@ -20,5 +20,6 @@ cap() {  # name regex skip count
 }
 cap k_accumulate_2 "k_accumulate<.int.2" 0 1
 cap k_decompress "k_decompress" 1 1
-rm -f gpurun_out/ncu/prof_k_decompress.ncu-rep
+cap k_lincomb "k_lincomb" 6 6
+rm -f gpurun_out/ncu/prof_k_decompress.ncu-rep gpurun_out/ncu/prof_k_lincomb.ncu-rep
 ls -la gpurun_out/ncu | tail -6
