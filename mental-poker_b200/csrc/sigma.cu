@@ -78,8 +78,7 @@ static __device__ __noinline__ void add_call(xyzz& acc, const xyzz& q) { xyzz_ad
 // flags: 1 = write canonical bytes to out_canon[job], 2 = write identity flag to out_flag[job]
 __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs, uint32_t njobs, affine* __restrict__ arena,
                                                  const uint32_t* __restrict__ scal, const affine* __restrict__ tab, int flags,
-                                                 uint32_t* __restrict__ out_canon, uint8_t* __restrict__ out_flag,
-                                                 xyzz* __restrict__ mult_all) {
+                                                 uint32_t* __restrict__ out_canon, uint8_t* __restrict__ out_flag) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= njobs) return;
   const LcJob j = jobs[g];
@@ -88,12 +87,9 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
     // Variable bases: fixed signed 4-bit windows, MSB first.  Every lane runs the same schedule -- four
     // doublings, then one table addition per base -- where a per-bit double-and-add makes the whole warp
     // pay for a mixed addition whenever ANY lane has the bit set (measured: 24.7 of 32 lanes active).
-    // Per base: multiples 1..8 in XYZZ, digits in [-7, 8] recoded once.  The 2 KB of multiples live in a
-    // per-thread slice of GLOBAL memory: as a local array the hardware interleaves them across lanes, and
-    // lane-divergent digits then turn every 128-byte entry into 32 scattered words (ncu: 8.6 GB of DRAM
-    // traffic for a deck's worth of two-base checks).
+    // Per base: multiples 1..8 in XYZZ (1 KB of local memory), digits in [-7, 8] recoded once.
     const bool two = j.var_pt[1] != kNone;
-    xyzz (*mult)[8] = reinterpret_cast<xyzz (*)[8]>(mult_all + (size_t)g * 16);  // mult[t][q] = (q + 1) * P_t
+    xyzz mult[2][8];     // mult[t][q] = (q + 1) * P_t
     uint32_t dig[2][8];  // 64 nibbles per scalar: (magnitude - 1) | sign << 3, or 0xf for a zero digit
     uint32_t hi = 0;     // bit t: scalar t carries out of nibble 63 (only a non-canonical 256-bit value can)
     int top = -1;
@@ -194,7 +190,7 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags, sSigKinds, sSigStage0, sSigStage1, sSigStage2, sSigMult };
+enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags, sSigKinds, sSigStage0, sSigStage1, sSigStage2 };
 
 // One batched call: a point arena (uploaded canonical points -> Montgomery, plus reserved result slots),
 // a scalar array, and launches of k_lincomb over job lists expanded on the device.  Caller buffers are
@@ -274,17 +270,10 @@ struct SigmaCall {
     if (nk > 16) return ctx->fail(MP_ERR_INVALID_ARG, "internal: too many job kinds");
     if (h_canon) NEED(d_out);
     if (h_flags) NEED(d_flags);
-    xyzz* d_mult = nullptr;
-    bool any_var = false;
-    for (const JobKind& k : kinds) any_var |= k.base[fVarPt0] != kNone;
-    if (any_var) {
-      d_mult = (xyzz*)ctx->scratch(sSigMult, (size_t)nj * 16 * sizeof(xyzz));
-      NEED(d_mult);
-    }
     CK(cudaMemcpyAsync(d_kinds, kinds.data(), sizeof(JobKind) * nk, cudaMemcpyHostToDevice, st));
     k_make_jobs<<<(nj + 255) / 256, 256, 0, st>>>(d_kinds, nk, (uint32_t)n, (uint32_t*)d_jobs);
     k_lincomb<<<(nj + 127) / 128, 128, 0, st>>>(d_jobs, nj, d_arena, d_scal, S->d_tab, (h_canon ? 1 : 0) | (h_flags ? 2 : 0), d_out,
-                                                d_flags, d_mult);
+                                                d_flags);
     CK(cudaGetLastError());
     ctx->launches += 2;
     if (h_canon) CK(cudaMemcpyAsync(h_canon, d_out, (size_t)nj * 64, cudaMemcpyDeviceToHost, st));
