@@ -1,0 +1,80 @@
+/* mpshuffle_bls12_377.h -- C ABI of the BLS12-377 G1 instantiation inside libmpshuffle.so.
+ *
+ * The reference's card protocol is generic over the curve, `DLCards<C: ProjectiveCurve>`
+ * (reference src/discrete_log_cards/mod.rs:86), and its benchmark harness instantiates it over
+ * `ark_bls12_377::G1Projective` / `ark_bls12_377::Fr` (examples/parameter_selection.rs:25-26).
+ * These entry points are the group layer of that instantiation: the
+ * variable-base MSM, the 2-component ciphertext MSM and the fixed-base batched Pedersen commitment
+ * that ShuffleArgument::{prove,verify} / MultiExponentiationArgument / PedersenCommitment::commit
+ * reduce to (call sites mod.rs:397-415,427-442; commit key setup mod.rs:111).  The protocol driver
+ * above them (mp_shuffle_*) is Stark-curve only so far.
+ *
+ * Conventions are those of mpshuffle.h with the sizes of this curve:
+ *   - base-field element: 48 bytes little-endian canonical (ark-ff 0.3 `Fp384` `ToBytes`);
+ *   - scalar: 32 bytes little-endian canonical, < r (253 bits);
+ *   - affine G1 point: 96 bytes x || y, identity = 96 zero bytes ((0,0) is not on y^2 = x^3 + 1);
+ *     ciphertext = c1 || c2 = 192 bytes.  Points are checked to be canonical and on the curve
+ *     (not for subgroup membership: G1 has cofactor 0x170b5d44300000000000000000000000);
+ *   - status codes MP_OK / MP_ERR_* of mpshuffle.h; no CPU fallback.
+ */
+#ifndef MPSHUFFLE_BLS12_377_H
+#define MPSHUFFLE_BLS12_377_H
+
+#include "mpshuffle.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mp377_ctx mp377_ctx;
+
+#define MP377_FQ_BYTES 48
+#define MP377_POINT_BYTES 96
+#define MP377_SCALAR_BYTES 32
+
+int32_t mp377_ctx_create(mp377_ctx** out, int32_t device);
+void mp377_ctx_destroy(mp377_ctx* ctx);
+void* mp377_ctx_stream(mp377_ctx* ctx);
+int32_t mp377_ctx_sync(mp377_ctx* ctx);
+const char* mp377_last_error_string(mp377_ctx* ctx);
+int32_t mp377_last_kernel_launches(mp377_ctx* ctx);
+/* EC additions the last MSM call scheduled / the window width it used / windows for a width */
+uint64_t mp377_last_msm_ec_adds(mp377_ctx* ctx);
+int32_t mp377_last_msm_window(mp377_ctx* ctx);
+int32_t mp377_msm_num_windows(int32_t window_bits);
+
+/* out = sum_i scalars[i] * bases[i]  (replaces ark-ec 0.3 VariableBaseMSM / scalar-mul loops) */
+int32_t mp377_msm_g1(mp377_ctx* ctx, const uint8_t* bases /* n*96 */, const uint8_t* scalars /* n*32 */,
+                     uint64_t n, int32_t window_bits, uint8_t* out /* 96 */);
+/* ciphertext MSM: component-wise over (c1, c2) pairs, both components share digits and sort */
+int32_t mp377_ct_msm(mp377_ctx* ctx, const uint8_t* deck /* n*192 */, const uint8_t* scalars /* n*32 */,
+                     uint64_t n, int32_t window_bits, uint8_t* out /* 192 */);
+/* device-resident inputs / outputs (same byte layout), asynchronous on the context's stream */
+int32_t mp377_msm_g1_device(mp377_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                            int32_t window_bits, void* d_out);
+int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
+                            int32_t window_bits, void* d_out);
+
+/* Pedersen commitments over a constant key (PedersenCommitment::setup / commit):
+ * ck = h || G_1 .. G_len ((len+1)*96 bytes); builds the fixed-base window table once. */
+int32_t mp377_set_commit_key(mp377_ctx* ctx, const uint8_t* ck, uint64_t len);
+/* out[j] = blinds[j]*h + sum_i values[j*len + i]*G_{i+1},  j < k,  len <= key length */
+int32_t mp377_pedersen_commit_batch(mp377_ctx* ctx, const uint8_t* values /* k*len*32 */,
+                                    const uint8_t* blinds /* k*32 */, uint64_t k, uint64_t len,
+                                    uint8_t* out /* k*96 */);
+
+/* CUDA-event timing of the bucket-accumulation kernel on the launch stream (bench.py) */
+int32_t mp377_profile_enable(mp377_ctx* ctx, int32_t on);
+int32_t mp377_profile_collect(mp377_ctx* ctx, double* accumulate_ms, uint64_t* bucket_adds, uint64_t* launches);
+
+/* parity helpers: one device field / group operation per element (tests only) */
+int32_t mp377_dbg_fq_mul(mp377_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+int32_t mp377_dbg_point_add(mp377_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out);
+int32_t mp377_dbg_scalar_mul(mp377_ctx* ctx, const uint8_t* p, const uint8_t* k, uint64_t n, uint8_t* out);
+/* microbenchmarks: which = 0 fq_mul, 1 XYZZ mixed addition; returns ms and the operation count */
+int32_t mp377_dbg_bench(mp377_ctx* ctx, int32_t which, int32_t iters, float* ms, double* ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

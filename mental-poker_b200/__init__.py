@@ -11,3 +11,4 @@ every compute entry point needs a CUDA device and raises otherwise.
 """
 from ._lib import lib, lib_path, MpError, check, Context  # noqa: F401
 from . import dist  # noqa: F401
+from . import bls12_377  # noqa: F401  (second curve: BLS12-377 G1 group layer)

@@ -1,0 +1,155 @@
+"""ctypes binding of the BLS12-377 G1 entry points of libmpshuffle.so (include/mpshuffle_bls12_377.h):
+the group layer of the reference's second instantiation, `DLCards<ark_bls12_377::G1Projective>`
+(reference examples/parameter_selection.rs:25-29).  Same conventions as `_lib.Context`, with 48-byte
+coordinates / 96-byte points.  No CPU fallback: the context needs a CUDA device."""
+import ctypes
+
+from ._lib import lib, MpError
+
+_vp, _i32, _u64, _cp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_char_p
+_pd, _pu64 = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64)
+
+FQ_BYTES, POINT_BYTES, SCALAR_BYTES = 48, 96, 32
+
+# name -> (restype, argtypes); must list every symbol include/mpshuffle_bls12_377.h declares
+SIGNATURES = {
+    "mp377_ctx_create": (_i32, [ctypes.POINTER(_vp), _i32]),
+    "mp377_ctx_destroy": (None, [_vp]),
+    "mp377_ctx_stream": (_vp, [_vp]),
+    "mp377_ctx_sync": (_i32, [_vp]),
+    "mp377_last_error_string": (_cp, [_vp]),
+    "mp377_last_kernel_launches": (_i32, [_vp]),
+    "mp377_last_msm_ec_adds": (_u64, [_vp]),
+    "mp377_last_msm_window": (_i32, [_vp]),
+    "mp377_msm_num_windows": (_i32, [_i32]),
+    "mp377_msm_g1": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
+    "mp377_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
+    "mp377_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp377_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp377_set_commit_key": (_i32, [_vp, _cp, _u64]),
+    "mp377_pedersen_commit_batch": (_i32, [_vp, _cp, _cp, _u64, _u64, _cp]),
+    "mp377_profile_enable": (_i32, [_vp, _i32]),
+    "mp377_profile_collect": (_i32, [_vp, _pd, _pu64, _pu64]),
+    "mp377_dbg_fq_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp377_dbg_point_add": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp377_dbg_scalar_mul": (_i32, [_vp, _cp, _cp, _u64, _cp]),
+    "mp377_dbg_bench": (_i32, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_float), _pd]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def _check(h, code):
+    if code < 0:
+        msg = lib.mp377_last_error_string(h)
+        raise MpError(code, msg.decode() if msg else "")
+    return code
+
+
+class Context:
+    """Owns one `mp377_ctx` (one CUDA device, one stream, one MSM workspace)."""
+
+    def __init__(self, device=0):
+        h = _vp()
+        rc = lib.mp377_ctx_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise MpError(rc, f"mp377_ctx_create(device={device}) failed: no usable CUDA device "
+                              "(the engine has no CPU fallback)")
+        self.h, self.device = h, device
+
+    def close(self):
+        if self.h:
+            lib.mp377_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib.mp377_ctx_stream(self.h)
+
+    def sync(self):
+        _check(self.h, lib.mp377_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib.mp377_last_kernel_launches(self.h)
+
+    @property
+    def last_msm_ec_adds(self):
+        return lib.mp377_last_msm_ec_adds(self.h)
+
+    @property
+    def last_msm_window(self):
+        return lib.mp377_last_msm_window(self.h)
+
+    # --- MSM
+    def msm_g1(self, bases: bytes, scalars: bytes, window_bits=0) -> bytes:
+        n = len(scalars) // SCALAR_BYTES
+        assert len(bases) == POINT_BYTES * n and len(scalars) == SCALAR_BYTES * n
+        out = ctypes.create_string_buffer(POINT_BYTES)
+        _check(self.h, lib.mp377_msm_g1(self.h, bases, scalars, n, window_bits, out))
+        return out.raw
+
+    def ct_msm(self, deck: bytes, scalars: bytes, window_bits=0) -> bytes:
+        n = len(scalars) // SCALAR_BYTES
+        assert len(deck) == 2 * POINT_BYTES * n
+        out = ctypes.create_string_buffer(2 * POINT_BYTES)
+        _check(self.h, lib.mp377_ct_msm(self.h, deck, scalars, n, window_bits, out))
+        return out.raw
+
+    def msm_g1_device(self, d_bases, d_scalars, n, d_out, window_bits=0):
+        _check(self.h, lib.mp377_msm_g1_device(self.h, d_bases, d_scalars, n, window_bits, d_out))
+
+    def ct_msm_device(self, d_deck, d_scalars, n, d_out, window_bits=0):
+        _check(self.h, lib.mp377_ct_msm_device(self.h, d_deck, d_scalars, n, window_bits, d_out))
+
+    # --- Pedersen
+    def set_commit_key(self, ck: bytes):
+        assert len(ck) % POINT_BYTES == 0 and len(ck) >= 2 * POINT_BYTES
+        _check(self.h, lib.mp377_set_commit_key(self.h, ck, len(ck) // POINT_BYTES - 1))
+
+    def pedersen_commit_batch(self, values: bytes, blinds: bytes, length: int) -> bytes:
+        k = len(blinds) // SCALAR_BYTES
+        assert len(values) == k * length * SCALAR_BYTES
+        out = ctypes.create_string_buffer(max(1, POINT_BYTES * k))
+        _check(self.h, lib.mp377_pedersen_commit_batch(self.h, values, blinds, k, length, out))
+        return out.raw[:POINT_BYTES * k]
+
+    # --- measurement / debug hooks
+    def profile_enable(self, on=True):
+        _check(self.h, lib.mp377_profile_enable(self.h, 1 if on else 0))
+
+    def profile_collect(self):
+        ms, adds, n = ctypes.c_double(), _u64(), _u64()
+        _check(self.h, lib.mp377_profile_collect(self.h, ctypes.byref(ms), ctypes.byref(adds), ctypes.byref(n)))
+        return ms.value, adds.value, n.value
+
+    def dbg_fq_mul(self, a: bytes, b: bytes) -> bytes:
+        n = len(a) // FQ_BYTES
+        out = ctypes.create_string_buffer(FQ_BYTES * n)
+        _check(self.h, lib.mp377_dbg_fq_mul(self.h, a, b, n, out))
+        return out.raw
+
+    def dbg_point_add(self, p: bytes, q: bytes) -> bytes:
+        n = len(p) // POINT_BYTES
+        out = ctypes.create_string_buffer(POINT_BYTES * n)
+        _check(self.h, lib.mp377_dbg_point_add(self.h, p, q, n, out))
+        return out.raw
+
+    def dbg_scalar_mul(self, p: bytes, k: bytes) -> bytes:
+        n = len(p) // POINT_BYTES
+        out = ctypes.create_string_buffer(POINT_BYTES * n)
+        _check(self.h, lib.mp377_dbg_scalar_mul(self.h, p, k, n, out))
+        return out.raw
+
+    def dbg_bench(self, which, iters):
+        ms, ops = ctypes.c_float(), ctypes.c_double()
+        _check(self.h, lib.mp377_dbg_bench(self.h, which, iters, ctypes.byref(ms), ctypes.byref(ops)))
+        return ms.value, ops.value

@@ -1,0 +1,380 @@
+// extern "C" surface of the BLS12-377 G1 instantiation (declared in include/mpshuffle_bls12_377.h).
+//
+// the reference's protocol is generic over `C: ProjectiveCurve`
+// (src/discrete_log_cards/mod.rs:86) and its only benchmark harness instantiates it over
+// `ark_bls12_377::G1Projective` (examples/parameter_selection.rs:25-26).  This translation unit and a
+// second copy of msm.cu are compiled with -DMP_CURVE_BLS12_377 -Dmp=mp_bls12_377: the same Pippenger
+// pipeline (msm.cu), the same XYZZ group law (ec.cuh, a = 0 branch) over the 12-limb field of
+// fq_bls12_377.cuh, linked into libmpshuffle.so next to the Stark-curve build.  Built so far: the group
+// layer under the protocol -- variable-base MSM, ciphertext (2-component) MSM, fixed-base batched
+// Pedersen commitments -- i.e. the kernels all of ShuffleArgument::{prove,verify} reduce to; the
+// protocol driver above them is still Stark-only (its byte layouts are 32-byte coordinates).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mpshuffle_bls12_377.h"
+#include "msm.cuh"
+
+#ifndef MP_CURVE_BLS12_377
+#error "capi_bls12_377.cu must be compiled with -DMP_CURVE_BLS12_377 -Dmp=mp_bls12_377"
+#endif
+
+using namespace mp;
+
+static constexpr size_t kFe = 4 * kFqLimbs;  // 48 bytes per coordinate
+static constexpr size_t kPt = 2 * kFe;       // 96 bytes per affine point
+
+struct mp377_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  MsmWorkspace* ws = nullptr;
+  std::string err;
+  int launches = 0;
+  uint64_t last_ec_adds = 0;
+  int last_window = 0;
+  // commit key (h, G_1 .. G_len) as a window-major fixed-base table
+  uint32_t ck_nb = 0;
+  int ck_c = 0;
+  struct Buf { void* ptr = nullptr; size_t cap = 0; };
+  enum { kStageIn = 0, kStageOut, kPointsMont, kMsmOut, kFlags, kCkBases, kCkTable, kScal, kSlots };
+  Buf bufs[kSlots];
+
+  void* scratch(int slot, size_t bytes) {
+    Buf& b = bufs[slot];
+    if (b.cap < bytes) {
+      if (b.ptr) cudaFree(b.ptr);
+      b.ptr = nullptr;
+      b.cap = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      if (cudaMalloc(&b.ptr, want) != cudaSuccess) return nullptr;
+      b.cap = want;
+    }
+    return b.ptr;
+  }
+  int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  int32_t cuda_fail(cudaError_t e, const char* where) {
+    return fail(MP_ERR_CUDA, "CUDA error in %s: %s", where, cudaGetErrorString(e));
+  }
+};
+
+#define CK377(call, where)                                   \
+  do {                                                       \
+    cudaError_t _e = (call);                                 \
+    if (_e != cudaSuccess) return ctx->cuda_fail(_e, where); \
+  } while (0)
+
+extern "C" int32_t mp377_ctx_create(mp377_ctx** out, int32_t device) {
+  if (!out) return MP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    fprintf(stderr, "mpshuffle: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    return MP_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return MP_ERR_CUDA;
+  mp377_ctx* ctx = new mp377_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MP_ERR_CUDA; }
+  ctx->ws = msm_workspace_create();
+  *out = ctx;
+  return MP_OK;
+}
+extern "C" void mp377_ctx_destroy(mp377_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  msm_workspace_destroy(ctx->ws);
+  for (auto& b : ctx->bufs)
+    if (b.ptr) cudaFree(b.ptr);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+extern "C" void* mp377_ctx_stream(mp377_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int32_t mp377_ctx_sync(mp377_ctx* ctx) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  CK377(cudaStreamSynchronize(ctx->stream), "mp377_ctx_sync");
+  return MP_OK;
+}
+extern "C" const char* mp377_last_error_string(mp377_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int32_t mp377_last_kernel_launches(mp377_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t mp377_last_msm_ec_adds(mp377_ctx* ctx) { return ctx ? ctx->last_ec_adds : 0; }
+extern "C" int32_t mp377_last_msm_window(mp377_ctx* ctx) { return ctx ? ctx->last_window : 0; }
+extern "C" int32_t mp377_msm_num_windows(int32_t window_bits) {
+  return window_bits >= 2 && window_bits <= 16 ? msm_num_windows(window_bits) : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// MSM entry points
+// ------------------------------------------------------------------------------------------
+static uint64_t scheduled_ec_adds(uint64_t n, int c, int ncomp) {
+  const uint64_t W = msm_num_windows(c), B = 1ull << (c - 1);
+  return (uint64_t)ncomp * (W * (n + 2 * B) + W * (uint64_t)c);
+}
+
+static int32_t msm_device_common(mp377_ctx* ctx, const void* d_points, const void* d_scalars, uint64_t n, int ncomp,
+                                 int32_t window_bits, void* d_out) {
+  if (!ctx || (!d_points && n) || (!d_scalars && n) || !d_out) return MP_ERR_INVALID_ARG;
+  if (n >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "MSM size %llu too large", (unsigned long long)n);
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int c = window_bits > 0 ? window_bits : msm_pick_window(n);
+  if (c < 2 || c > 16) return ctx->fail(MP_ERR_INVALID_ARG, "window_bits %d out of range [2,16]", c);
+  ctx->last_window = c;
+  ctx->last_ec_adds = scheduled_ec_adds(n, c, ncomp);
+  affine* mont = (affine*)ctx->scratch(mp377_ctx::kPointsMont, sizeof(affine) * n * ncomp);
+  xyzz* res = (xyzz*)ctx->scratch(mp377_ctx::kMsmOut, sizeof(xyzz) * ncomp);
+  int* bad = (int*)ctx->scratch(mp377_ctx::kFlags, 256);
+  if (!mont || !res || !bad) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  CK377(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream), "memset");
+  CK377(points_to_mont((const uint32_t*)d_points, mont, n * ncomp, bad, ctx->stream), "points_to_mont");
+  ctx->launches += n ? 1 : 0;
+  MsmJob job{0, 0, (uint32_t)n};
+  CK377(msm_run(ctx->ws, (const uint32_t*)d_scalars, n, mont, ncomp, &job, 1, c, res, ctx->stream), "msm_run");
+  ctx->launches += msm_last_launches(ctx->ws);
+  CK377(xyzz_to_canonical(res, (uint32_t*)d_out, ncomp, ctx->stream), "xyzz_to_canonical");
+  ctx->launches += 1;
+  return MP_OK;
+}
+
+static int32_t msm_host_common(mp377_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, int ncomp,
+                               int32_t window_bits, uint8_t* out) {
+  if (!ctx || (!points && n) || (!scalars && n) || !out) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  const size_t pbytes = (size_t)n * kPt * ncomp, sbytes = (size_t)n * 32;
+  uint8_t* d_in = (uint8_t*)ctx->scratch(mp377_ctx::kStageIn, pbytes + sbytes + 256);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(mp377_ctx::kStageOut, kPt * ncomp);
+  if (!d_in || !d_out) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  if (n) {
+    CK377(cudaMemcpyAsync(d_in, points, pbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D points");
+    CK377(cudaMemcpyAsync(d_in + pbytes, scalars, sbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D scalars");
+  }
+  int32_t st = msm_device_common(ctx, d_in, d_in + pbytes, n, ncomp, window_bits, d_out);
+  if (st != MP_OK) return st;
+  int bad = 0;
+  int* d_bad = (int*)ctx->scratch(mp377_ctx::kFlags, 256);
+  CK377(cudaMemcpyAsync(out, d_out, kPt * ncomp, cudaMemcpyDeviceToHost, ctx->stream), "D2H result");
+  CK377(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H flag");
+  CK377(cudaStreamSynchronize(ctx->stream), "MSM execution");
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of BLS12-377 G1");
+  return MP_OK;
+}
+
+extern "C" int32_t mp377_msm_g1(mp377_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, uint64_t n,
+                                int32_t window_bits, uint8_t* out) {
+  return msm_host_common(ctx, bases, scalars, n, 1, window_bits, out);
+}
+extern "C" int32_t mp377_ct_msm(mp377_ctx* ctx, const uint8_t* deck, const uint8_t* scalars, uint64_t n,
+                                int32_t window_bits, uint8_t* out) {
+  return msm_host_common(ctx, deck, scalars, n, 2, window_bits, out);
+}
+extern "C" int32_t mp377_msm_g1_device(mp377_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                                       int32_t window_bits, void* d_out) {
+  return msm_device_common(ctx, d_bases, d_scalars, n, 1, window_bits, d_out);
+}
+extern "C" int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
+                                       int32_t window_bits, void* d_out) {
+  return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
+}
+
+extern "C" int32_t mp377_profile_enable(mp377_ctx* ctx, int32_t on) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  msm_profile_enable(ctx->ws, on != 0);
+  return MP_OK;
+}
+extern "C" int32_t mp377_profile_collect(mp377_ctx* ctx, double* accumulate_ms, uint64_t* bucket_adds, uint64_t* launches) {
+  if (!ctx || !accumulate_ms || !bucket_adds || !launches) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  CK377(msm_profile_collect(ctx->ws, accumulate_ms, bucket_adds, launches), "mp377_profile_collect");
+  return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pedersen commitments over a constant key (PedersenCommitment::{setup, commit}; reference type at
+// src/discrete_log_cards/mod.rs:18,89, setup call mod.rs:111): fixed-base table mode of msm.cu
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t mp377_set_commit_key(mp377_ctx* ctx, const uint8_t* ck, uint64_t len) {
+  if (!ctx || !ck) return MP_ERR_INVALID_ARG;
+  if (len == 0 || len >= (1u << 24)) return ctx->fail(MP_ERR_INVALID_ARG, "commit key length %llu out of range", (unsigned long long)len);
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const uint32_t nb = (uint32_t)len + 1;
+  const int c = msm_pick_table_window(nb);
+  const int W = msm_num_windows(c);
+  uint8_t* d_in = (uint8_t*)ctx->scratch(mp377_ctx::kStageIn, (size_t)nb * kPt);
+  affine* bases = (affine*)ctx->scratch(mp377_ctx::kCkBases, sizeof(affine) * nb);
+  affine* table = (affine*)ctx->scratch(mp377_ctx::kCkTable, sizeof(affine) * nb * W);
+  int* bad = (int*)ctx->scratch(mp377_ctx::kFlags, 256);
+  if (!d_in || !bases || !table || !bad) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  ctx->ck_nb = 0;
+  CK377(cudaMemcpyAsync(d_in, ck, (size_t)nb * kPt, cudaMemcpyHostToDevice, ctx->stream), "H2D commit key");
+  CK377(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream), "memset");
+  CK377(points_to_mont((const uint32_t*)d_in, bases, nb, bad, ctx->stream), "points_to_mont");
+  CK377(msm_build_table(ctx->ws, bases, nb, 0, nb, c, table, ctx->stream), "msm_build_table");
+  ctx->launches = 3;
+  int h_bad = 0;
+  CK377(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H flag");
+  CK377(cudaStreamSynchronize(ctx->stream), "commit key table");
+  if (h_bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a commit-key point is not a canonical point of BLS12-377 G1");
+  ctx->ck_nb = nb;
+  ctx->ck_c = c;
+  return MP_OK;
+}
+
+extern "C" int32_t mp377_pedersen_commit_batch(mp377_ctx* ctx, const uint8_t* values, const uint8_t* blinds, uint64_t k,
+                                               uint64_t len, uint8_t* out) {
+  if (!ctx || (k && (!blinds || !out)) || (k && len && !values)) return MP_ERR_INVALID_ARG;
+  if (!ctx->ck_nb) return ctx->fail(MP_ERR_NO_PARAMS, "mp377_set_commit_key has not been called");
+  if (len + 1 > ctx->ck_nb) return ctx->fail(MP_ERR_INVALID_ARG, "vector length %llu exceeds the commit key length %u",
+                                             (unsigned long long)len, ctx->ck_nb - 1);
+  if (k == 0) return MP_OK;
+  if (k * (len + 1) >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "too many commitments in one batch");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  // job j: scalars [blind_j, values_j[0 .. len)] against table columns [0, len]  (column 0 is h)
+  const size_t row = (len + 1) * 32;
+  std::vector<uint8_t> h_scal(k * row);
+  std::vector<MsmJob> jobs(k);
+  for (uint64_t j = 0; j < k; j++) {
+    memcpy(h_scal.data() + j * row, blinds + j * 32, 32);
+    if (len) memcpy(h_scal.data() + j * row + 32, values + j * len * 32, len * 32);
+    jobs[j] = MsmJob{(uint32_t)(j * (len + 1)), 0u, (uint32_t)(len + 1)};
+  }
+  uint32_t* d_scal = (uint32_t*)ctx->scratch(mp377_ctx::kScal, k * row);
+  xyzz* res = (xyzz*)ctx->scratch(mp377_ctx::kMsmOut, sizeof(xyzz) * k);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(mp377_ctx::kStageOut, kPt * k);
+  if (!d_scal || !res || !d_out) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  CK377(cudaMemcpyAsync(d_scal, h_scal.data(), k * row, cudaMemcpyHostToDevice, ctx->stream), "H2D scalars");
+  CK377(msm_run(ctx->ws, d_scal, k * (len + 1), (const affine*)ctx->bufs[mp377_ctx::kCkTable].ptr, 1, jobs.data(), (int)k,
+                ctx->ck_c, res, ctx->stream, 0, -1, ctx->ck_nb), "msm_run (fixed-base)");
+  ctx->launches += msm_last_launches(ctx->ws);
+  CK377(xyzz_to_canonical(res, (uint32_t*)d_out, k, ctx->stream), "xyzz_to_canonical");
+  ctx->launches += 1;
+  CK377(cudaMemcpyAsync(out, d_out, kPt * k, cudaMemcpyDeviceToHost, ctx->stream), "D2H commitments");
+  CK377(cudaStreamSynchronize(ctx->stream), "commit batch");
+  return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / parity helpers: device field and group arithmetic exposed one operation per thread, so that
+// the PTX carry chains (which the host tests cannot reach) are checked against the oracle directly
+// ------------------------------------------------------------------------------------------
+__global__ void k377_dbg_fq_mul(const fq* a, const fq* b, fq* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fq_mul(a[i], b[i]);
+}
+__global__ void k377_dbg_point_add(const uint32_t* p, const uint32_t* q, uint32_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int PW = 2 * kFqLimbs;
+  xyzz acc = xyzz_from_affine(affine_from_canonical(p + i * PW));
+  xyzz_madd(acc, affine_from_canonical(q + i * PW));
+  affine a = xyzz_to_affine(acc);
+  if (affine_is_identity(a)) { for (int k = 0; k < PW; k++) out[i * PW + k] = 0; }
+  else affine_to_canonical(a, out + i * PW);
+}
+__global__ void k377_dbg_scalar_mul(const uint32_t* p, const uint32_t* k, uint32_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int PW = 2 * kFqLimbs;
+  affine P = affine_from_canonical(p + i * PW);
+  xyzz acc = xyzz_identity();
+  for (int bit = 255; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((k[i * 8 + (bit >> 5)] >> (bit & 31)) & 1) xyzz_madd(acc, P);
+  }
+  affine a = xyzz_to_affine(acc);
+  if (affine_is_identity(a)) { for (int w = 0; w < PW; w++) out[i * PW + w] = 0; }
+  else affine_to_canonical(a, out + i * PW);
+}
+
+template <typename K>
+static int32_t dbg_map(mp377_ctx* ctx, const uint8_t* a, size_t abytes, const uint8_t* b, size_t bbytes, uint64_t n,
+                       uint8_t* out, size_t obytes, K launch) {
+  if (!ctx || !a || !b || !out) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  uint8_t* d = (uint8_t*)ctx->scratch(mp377_ctx::kStageIn, (abytes + bbytes + obytes) * n + 256);
+  if (!d) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  uint8_t *da = d, *db = d + abytes * n, *dout = db + bbytes * n;
+  cudaMemcpyAsync(da, a, abytes * n, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(db, b, bbytes * n, cudaMemcpyHostToDevice, ctx->stream);
+  launch(da, db, dout);
+  cudaMemcpyAsync(out, dout, obytes * n, cudaMemcpyDeviceToHost, ctx->stream);
+  CK377(cudaStreamSynchronize(ctx->stream), "debug kernel");
+  ctx->launches = 1;
+  return MP_OK;
+}
+extern "C" int32_t mp377_dbg_fq_mul(mp377_ctx* ctx, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+  return dbg_map(ctx, a, kFe, b, kFe, n, out, kFe, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
+    k377_dbg_fq_mul<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const fq*)da, (const fq*)db, (fq*)dout, n);
+  });
+}
+extern "C" int32_t mp377_dbg_point_add(mp377_ctx* ctx, const uint8_t* p, const uint8_t* q, uint64_t n, uint8_t* out) {
+  return dbg_map(ctx, p, kPt, q, kPt, n, out, kPt, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
+    k377_dbg_point_add<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t*)da, (const uint32_t*)db, (uint32_t*)dout, n);
+  });
+}
+extern "C" int32_t mp377_dbg_scalar_mul(mp377_ctx* ctx, const uint8_t* p, const uint8_t* k, uint64_t n, uint8_t* out) {
+  return dbg_map(ctx, p, kPt, k, 32, n, out, kPt, [&](uint8_t* da, uint8_t* db, uint8_t* dout) {
+    k377_dbg_scalar_mul<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t*)da, (const uint32_t*)db, (uint32_t*)dout, n);
+  });
+}
+
+// integer-pipe microbenchmarks of the 12-limb field: 0 = fq_mul, 1 = XYZZ mixed addition
+__global__ void __launch_bounds__(128) k377_bench_fq_mul(uint32_t* out, int iters, uint32_t seed) {
+  fq x = fq_one(), y = fq_r2();
+  x.v[0] ^= seed + threadIdx.x;
+  y.v[0] ^= blockIdx.x;
+  x = fq_reduce_weak(x); y = fq_reduce_weak(y);
+  for (int it = 0; it < iters; it++) { x = fq_mul(x, y); y = fq_mul(y, x); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x.v[0] ^ y.v[7];
+}
+__global__ void __launch_bounds__(128) k377_bench_madd(uint32_t* out, int iters, uint32_t seed) {
+  // the generator in canonical form -> Montgomery; acc walks 2G, 3G, ... (no special cases hit)
+  const uint32_t g[24] = {0xb21be9efu, 0xeab9b16eu, 0xffcd394eu, 0xd5481512u, 0xbd37cb5cu, 0x188282c8u,
+                          0xaa9d41bbu, 0x85951e2cu, 0xbf87ff54u, 0xc8fc6225u, 0xfe740a67u, 0x008848deu,
+                          0x559c8ea6u, 0xfd82de55u, 0x34a9591au, 0xc2fe3d36u, 0x4fb82305u, 0x6d182ad4u,
+                          0xca3e52d9u, 0xbd7fb348u, 0x30afeec4u, 0x1f674f5du, 0xc5102effu, 0x01914a69u};
+  affine P = affine_from_canonical(g);
+  xyzz acc = xyzz_dbl_affine(P);
+  if ((seed + threadIdx.x) == 0xffffffffu) acc = xyzz_dbl(acc);
+  for (int it = 0; it < iters; it++) xyzz_madd(acc, P);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.X.v[0] ^ acc.ZZZ.v[3];
+}
+extern "C" int32_t mp377_dbg_bench(mp377_ctx* ctx, int32_t which, int32_t iters, float* ms, double* ops) {
+  if (!ctx || !ms || !ops || iters <= 0) return MP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  const int blocks = 148 * 8;
+  uint32_t* d = (uint32_t*)ctx->scratch(mp377_ctx::kStageOut, sizeof(uint32_t) * blocks * 128);
+  if (!d) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int rep = 0; rep < 2; rep++) {  // first pass = warm-up
+    cudaEventRecord(e0, ctx->stream);
+    if (which == 0) { k377_bench_fq_mul<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters * 2; }
+    else if (which == 1) { k377_bench_madd<<<blocks, 128, 0, ctx->stream>>>(d, iters, 1234u); *ops = (double)blocks * 128 * iters; }
+    else { cudaEventDestroy(e0); cudaEventDestroy(e1); return MP_ERR_INVALID_ARG; }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ctx->cuda_fail(e, "bench kernel"); }
+  }
+  cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->launches = 2;
+  return MP_OK;
+}

@@ -1,4 +1,5 @@
-// Stark-curve group arithmetic in extended Jacobian ("XYZZ") coordinates:
+// Short-Weierstrass group arithmetic in extended Jacobian ("XYZZ") coordinates, for the curve whose
+// base field fq.cuh selects (the Stark curve, a = 1; or BLS12-377 G1, a = 0, under MP_CURVE_BLS12_377):
 //   x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity <=> ZZ == 0 (stored as exact zero words).
 // Replaces, for the shuffle hot path, the ark-ec 0.3 short-Weierstrass group the reference
 // reaches through `C: ProjectiveCurve` (reference src/discrete_log_cards/mod.rs:86;
@@ -46,7 +47,11 @@ MP_HD xyzz xyzz_dbl_affine(const affine& p) {
   fq W = fq_mul(U, V);                          // [2]
   fq S = fq_mul(p.x, V);                        // [2]
   fq XX = fq_sqr(p.x);                          // [2]
+#if MP_CURVE_A_IS_ZERO
+  fq M = fq_add(fq_add(XX, XX), XX);            // 3*XX -> [6]
+#else
   fq M = fq_add(fq_add(XX, XX), fq_add(XX, fq_one()));  // 3*XX + a, a = 1 -> [8]
+#endif
   M = fq_reduce_weak(M);                        // [2]
   fq X3 = fq_sub(fq_sqr(M), fq_add(S, S), 4);   // [2] + 4p - [4] -> [6]
   X3 = fq_reduce_weak(X3);                      // [2]
@@ -64,8 +69,12 @@ MP_HD xyzz xyzz_dbl(const xyzz& p) {
   fq W = fq_mul(U, V);                          // [2]
   fq S = fq_mul(p.X, V);                        // [2]
   fq XX = fq_sqr(p.X);                          // [2]
+#if MP_CURVE_A_IS_ZERO
+  fq M = fq_add(fq_add(XX, XX), XX);            // [6]  (a = 0: no ZZ^2 term)
+#else
   fq ZZ2 = fq_sqr(p.ZZ);                        // [2]  (a * ZZ^2, a = 1)
   fq M = fq_add(fq_add(XX, XX), fq_add(XX, ZZ2));  // [8]
+#endif
   M = fq_reduce_weak(M);
   fq X3 = fq_reduce_weak(fq_sub(fq_sqr(M), fq_add(S, S), 4));
   fq Y3 = fq_sub(fq_mul(M, fq_sub(S, X3, 2)), fq_mul(W, p.Y), 2);
@@ -160,12 +169,12 @@ MP_HD affine xyzz_to_affine(const xyzz& p) {
   return r;
 }
 
-// 64-byte canonical little-endian x || y (non-Montgomery) <-> affine Montgomery
-MP_HD affine affine_from_canonical(const uint32_t* w) {  // 16 words
+// canonical little-endian x || y (non-Montgomery, 2 * kFqLimbs words) <-> affine Montgomery
+MP_HD affine affine_from_canonical(const uint32_t* w) {
   affine r;
   fq x, y;
 #pragma unroll
-  for (int i = 0; i < 8; i++) { x.v[i] = w[i]; y.v[i] = w[8 + i]; }
+  for (int i = 0; i < kFqLimbs; i++) { x.v[i] = w[i]; y.v[i] = w[kFqLimbs + i]; }
   if (fq_is_zero_raw(x) & fq_is_zero_raw(y)) { r.x = x; r.y = y; return r; }
   r.x = fq_reduce_full(fq_to_mont(x));
   r.y = fq_reduce_full(fq_to_mont(y));
@@ -174,17 +183,19 @@ MP_HD affine affine_from_canonical(const uint32_t* w) {  // 16 words
 MP_HD void affine_to_canonical(const affine& p, uint32_t* w) {
   fq x = fq_from_mont(p.x), y = fq_from_mont(p.y);
 #pragma unroll
-  for (int i = 0; i < 8; i++) { w[i] = x.v[i]; w[8 + i] = y.v[i]; }
+  for (int i = 0; i < kFqLimbs; i++) { w[i] = x.v[i]; w[kFqLimbs + i] = y.v[i]; }
 }
 
-// y^2 == x^3 + x + b ?  (Montgomery inputs)
+// y^2 == x^3 + a*x + b ?  (Montgomery inputs)
 MP_HD bool affine_on_curve(const affine& p) {
   if (affine_is_identity(p)) return true;
-  fq bm;  // b * R mod p
-  bm.v[0] = 0xb59a21cau; bm.v[1] = 0x359ddd67u; bm.v[2] = 0x7aab9006u; bm.v[3] = 0x6725f223u;
-  bm.v[4] = 0x2a41f947u; bm.v[5] = 0xab8a1e00u; bm.v[6] = 0x1774247fu; bm.v[7] = 0x01393165u;
+  const fq bm = fq_curve_b();  // b * R mod p
   fq lhs = fq_sqr(p.y);
+#if MP_CURVE_A_IS_ZERO
+  fq rhs = fq_add(fq_mul(fq_sqr(p.x), p.x), bm);               // [2]+[1]
+#else
   fq rhs = fq_add(fq_add(fq_mul(fq_sqr(p.x), p.x), p.x), bm);  // [2]+[2]+[1]
+#endif
   return fq_eq_raw(fq_reduce_full(lhs), fq_reduce_full(rhs));
 }
 

@@ -18,6 +18,11 @@
 // same word-level algorithm runs on uint64 arithmetic so the logic is unit-testable without
 // a GPU (tests/host_field_test.cpp is NOT part of the product path).
 #pragma once
+#ifdef MP_CURVE_BLS12_377
+// second curve: same function names over a 12-limb field; the translation units
+// of that build are compiled with -Dmp=mp_bls12_377 so both instantiations link into one library
+#include "fq_bls12_377.cuh"
+#else
 #include <stdint.h>
 
 #ifdef __CUDACC__
@@ -28,7 +33,14 @@
 #define MP_D inline
 #endif
 
+#define MP_CURVE_NAME "Stark curve"
+#define MP_CURVE_A_IS_ZERO 0
+
 namespace mp {
+
+static constexpr int kFqLimbs = 8;
+// bits the signed-digit recoding must cover: bit length of the group order (252) + 1 for the carry
+static constexpr int kScalarBits = 253;
 
 struct fq {
   uint32_t v[8];
@@ -66,6 +78,14 @@ MP_HD fq fq_r2() {
   fq r;
   r.v[0] = 0x7e000401u; r.v[1] = 0xfffffd73u; r.v[2] = 0x330fffffu; r.v[3] = 0x00000001u;
   r.v[4] = 0xff6f8000u; r.v[5] = 0xffffffffu; r.v[6] = 0x5e008810u; r.v[7] = 0x07ffd4abu;
+  return r;
+}
+
+// curve coefficient b in Montgomery form (b * R mod p)
+MP_HD fq fq_curve_b() {
+  fq r;
+  r.v[0] = 0xb59a21cau; r.v[1] = 0x359ddd67u; r.v[2] = 0x7aab9006u; r.v[3] = 0x6725f223u;
+  r.v[4] = 0x2a41f947u; r.v[5] = 0xab8a1e00u; r.v[6] = 0x1774247fu; r.v[7] = 0x01393165u;
   return r;
 }
 
@@ -593,3 +613,4 @@ MP_HD fq fq_inv(const fq& a) {
 }
 
 }  // namespace mp
+#endif  // MP_CURVE_BLS12_377

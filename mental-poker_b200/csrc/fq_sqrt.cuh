@@ -17,12 +17,7 @@ MP_HD fq fq_sqrt_root() {
   r.v[4] = 0x60505574u; r.v[5] = 0x0a35c5beu; r.v[6] = 0xc47afc26u; r.v[7] = 0x07222e32u;
   return r;
 }
-MP_HD fq fq_curve_b() {  // b * R mod p
-  fq bm;
-  bm.v[0] = 0xb59a21cau; bm.v[1] = 0x359ddd67u; bm.v[2] = 0x7aab9006u; bm.v[3] = 0x6725f223u;
-  bm.v[4] = 0x2a41f947u; bm.v[5] = 0xab8a1e00u; bm.v[6] = 0x1774247fu; bm.v[7] = 0x01393165u;
-  return bm;
-}
+// (the curve coefficient b * R mod p is fq_curve_b() of fq.cuh)
 
 // T[i] = root^(2^i), fully reduced (191 dependent squarings, once per context)
 MP_HD void fq_sqrt_table(fq* T) {

@@ -20,6 +20,11 @@ static constexpr int kAccThreads = 128;   // accumulate block size
 static constexpr int kSegLen = 16;        // buckets per k_reduce_seg thread
 static constexpr int kWinThreads = 256;   // k_reduce_win block size
 static constexpr uint32_t kNoDigit = 0xffffffffu;
+// record sizes of the curve selected in fq.cuh (Stark: 8-limb coordinates, BLS12-377: 12)
+static constexpr int kPointWords = 2 * kFqLimbs;                 // canonical x || y
+static constexpr int kAffVec = (int)(sizeof(affine) / 16);       // 128-bit words per affine point
+static constexpr int kXyzzVec = (int)(sizeof(xyzz) / 16);        // ... per XYZZ accumulator
+static_assert(sizeof(affine) == 8 * kFqLimbs && sizeof(xyzz) == 16 * kFqLimbs && kFqLimbs % 4 == 0, "record layout");
 
 struct MsmWorkspace {
   // growable device buffers
@@ -98,8 +103,8 @@ int msm_pick_window(uint64_t avg_len, uint64_t njobs) {
   int best = 4;
   double best_cost = 1e300;
   for (int c = 4; c <= 16; c++) {
-    const int W = (253 + c - 1) / c;
-    const int t = 253 - (W - 1) * c;
+    const int W = (kScalarBits + c - 1) / c;
+    const int t = kScalarBits - (W - 1) * c;
     const double top_run = (double)avg_len / (double)(1u << (t - 1));  // entries per top-window bucket
     const double stitch = top_run > 2.0 * kChunkMax ? (top_run / kChunkMax) * 90000.0 / (double)(njobs ? njobs : 1) : 0.0;
     const double cost = (double)W * ((double)avg_len + 2.8 * (double)(1u << (c - 1))) + stitch;
@@ -125,21 +130,21 @@ __device__ __forceinline__ xyzz xyzz_load(const xyzz* p) {
   const uint4* s = reinterpret_cast<const uint4*>(p);
   uint4* d = reinterpret_cast<uint4*>(&r);
 #pragma unroll
-  for (int i = 0; i < 8; i++) d[i] = s[i];
+  for (int i = 0; i < kXyzzVec; i++) d[i] = s[i];
   return r;
 }
 __device__ __forceinline__ void xyzz_store(xyzz* p, const xyzz& v) {
   uint4* d = reinterpret_cast<uint4*>(p);
   const uint4* s = reinterpret_cast<const uint4*>(&v);
 #pragma unroll
-  for (int i = 0; i < 8; i++) d[i] = s[i];
+  for (int i = 0; i < kXyzzVec; i++) d[i] = s[i];
 }
 __device__ __forceinline__ affine affine_load(const affine* p) {
   affine r;
   const uint4* s = reinterpret_cast<const uint4*>(p);
   uint4* d = reinterpret_cast<uint4*>(&r);
 #pragma unroll
-  for (int i = 0; i < 4; i++) d[i] = __ldg(s + i);
+  for (int i = 0; i < kAffVec; i++) d[i] = __ldg(s + i);
   return r;
 }
 __device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz& v, int delta) {
@@ -147,7 +152,7 @@ __device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz& v, int delta) {
   const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
   uint32_t* d = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-  for (int i = 0; i < 32; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  for (int i = 0; i < 4 * kXyzzVec; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
   return r;
 }
 
@@ -159,10 +164,10 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restri
                                                         int* __restrict__ bad) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t w[16];
-  const uint4* s = reinterpret_cast<const uint4*>(in + i * 16);
+  uint32_t w[kPointWords];
+  const uint4* s = reinterpret_cast<const uint4*>(in + i * kPointWords);
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < kAffVec; k++) {
     uint4 v = __ldg(s + k);
     w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
   }
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restri
     // as ark-serialize would -- and the point must satisfy the curve equation
     fq cx, cy;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { cx.v[k] = w[k]; cy.v[k] = w[8 + k]; }
+    for (int k = 0; k < kFqLimbs; k++) { cx.v[k] = w[k]; cy.v[k] = w[kFqLimbs + k]; }
     uint32_t bx, by;
     fq_sub_raw(cx, fq_kp(1), &bx);
     fq_sub_raw(cy, fq_kp(1), &by);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restri
   uint4* d = reinterpret_cast<uint4*>(out + i);
   const uint4* ps = reinterpret_cast<const uint4*>(&p);
 #pragma unroll
-  for (int k = 0; k < 4; k++) d[k] = ps[k];
+  for (int k = 0; k < kAffVec; k++) d[k] = ps[k];
 }
 
 cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,
@@ -197,16 +202,16 @@ __global__ void __launch_bounds__(64) k_xyzz_to_canonical(const xyzz* __restrict
   if (i >= n) return;
   xyzz p = xyzz_load(in + i);
   affine a = xyzz_to_affine(p);
-  uint32_t w[16];
+  uint32_t w[kPointWords];
   if (affine_is_identity(a)) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) w[k] = 0;
+    for (int k = 0; k < kPointWords; k++) w[k] = 0;
   } else {
     affine_to_canonical(a, w);
   }
-  uint4* d = reinterpret_cast<uint4*>(out + i * 16);
+  uint4* d = reinterpret_cast<uint4*>(out + i * kPointWords);
 #pragma unroll
-  for (int k = 0; k < 4; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+  for (int k = 0; k < kAffVec; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
 }
 
 cudaError_t xyzz_to_canonical(const xyzz* d_in, uint32_t* d_out, uint64_t n, cudaStream_t stream) {
@@ -262,14 +267,14 @@ __global__ void __launch_bounds__(64) k_table_normalise(const xyzz* __restrict__
     uint4* d = reinterpret_cast<uint4*>(table + (size_t)w * nb + first + i);
     const uint4* s = reinterpret_cast<const uint4*>(&a);
 #pragma unroll
-    for (int k = 0; k < 4; k++) d[k] = s[k];
+    for (int k = 0; k < kAffVec; k++) d[k] = s[k];
   }
 }
 
 cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb, uint32_t first, uint32_t count,
                             int c, affine* d_table, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
-  const int W = (253 + c - 1) / c;
+  const int W = (kScalarBits + c - 1) / c;
   if (W > kMaxTableWindows) return cudaErrorInvalidValue;
   xyzz* tmp;
   MP_CK(ws->get(13, (size_t)W * count, &tmp));
@@ -283,7 +288,7 @@ int msm_pick_table_window(uint64_t typical_len) {
   int best = 4;
   double best_cost = 1e300;
   for (int c = 4; c <= 16; c++) {
-    int W = (253 + c - 1) / c;
+    int W = (kScalarBits + c - 1) / c;
     double cost = (double)W * (double)typical_len + 2.8 * (double)(1u << (c - 1));
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
@@ -758,7 +763,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   if (njobs <= 0) return cudaSuccess;
   if (ncomp != 1 && ncomp != 2) return cudaErrorInvalidValue;
   if (c < 2 || c > 20) return cudaErrorInvalidValue;
-  const int W_all = (253 + c - 1) / c;
+  const int W_all = (kScalarBits + c - 1) / c;
   if (w_count < 0) w_count = W_all - w_begin;
   if (w_begin < 0 || w_count < 1 || w_begin + w_count > W_all) return cudaErrorInvalidValue;
   const int W = w_count;  // windows handled by this call: [w_begin, w_begin + W)
@@ -870,15 +875,18 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     }
     uint64_t threads = max_chunks * ncomp;
     unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
-    // occupancy experiment knob: resident blocks per SM the kernel is compiled for (register cap)
-    static const int acc_mb = [] { const char* e = getenv("MP_ACC_MINBLOCKS"); return e ? atoi(e) : 4; }();
+    // occupancy knob: resident blocks per SM the kernel is compiled for (register cap).  The 8-limb field
+    // runs best at 4 blocks (128 registers); the 12-limb accumulator + prefetched point need ~2x the
+    // registers, so that build defaults to 2 blocks (255 registers) instead of spilling.
+    constexpr int kMB0 = kFqLimbs > 8 ? 2 : 4;
+    static const int acc_mb = [] { const char* e = getenv("MP_ACC_MINBLOCKS"); return e ? atoi(e) : kMB0; }();
     const size_t smem = (size_t)(kAccThreads / ncomp) * kChunk * sizeof(uint32_t);  // one staged tile per warp
 #define MP_LAUNCH_ACC(NC, MB) \
   k_accumulate<NC, MB><<<blocks, kAccThreads, smem, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk)
     if (ncomp == 1) {
-      if (acc_mb >= 6) MP_LAUNCH_ACC(1, 6); else if (acc_mb == 5) MP_LAUNCH_ACC(1, 5); else MP_LAUNCH_ACC(1, 4);
+      if (acc_mb >= kMB0 + 2) MP_LAUNCH_ACC(1, kMB0 + 2); else if (acc_mb == kMB0 + 1) MP_LAUNCH_ACC(1, kMB0 + 1); else MP_LAUNCH_ACC(1, kMB0);
     } else {
-      if (acc_mb >= 6) MP_LAUNCH_ACC(2, 6); else if (acc_mb == 5) MP_LAUNCH_ACC(2, 5); else MP_LAUNCH_ACC(2, 4);
+      if (acc_mb >= kMB0 + 2) MP_LAUNCH_ACC(2, kMB0 + 2); else if (acc_mb == kMB0 + 1) MP_LAUNCH_ACC(2, kMB0 + 1); else MP_LAUNCH_ACC(2, kMB0);
     }
 #undef MP_LAUNCH_ACC
     ws->launches++;

@@ -46,7 +46,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
 // With a window range [w_begin, w_begin + w_count) of the W = ceil(253/c) windows the result is
 //   sum_{w in range} 2^(c*(w - w_begin)) * (window sum w)
 // so that  full MSM = sum over ranges of 2^(c*w_begin) * partial  (window-range split across GPUs).
-inline int msm_num_windows(int c) { return (253 + c - 1) / c; }
+inline int msm_num_windows(int c) { return (kScalarBits + c - 1) / c; }
 
 // Fixed-base mode (Pedersen commitments over a constant key).  msm_build_table fills
 //   d_table[w * nb + first + i] = 2^(c*w) * d_bases[first + i],  w < msm_num_windows(c), i < count

@@ -1,0 +1,197 @@
+"""GPU parity, second curve: the BLS12-377 G1 group layer -- 12-limb device field
+arithmetic, XYZZ group law with a = 0, the Pippenger MSM (1 and 2 components) and fixed-base batched
+Pedersen commitments -- called through the C ABI (include/mpshuffle_bls12_377.h), bit-exact against the
+big-int oracle and the committed golden vectors."""
+import json
+import os
+import random
+
+import pytest
+
+from oracle.py import bls12_377 as bls
+from _util_bls12_377 import Stream, chain_points, scalars, pb, b32
+
+pytestmark = pytest.mark.gpu
+Q, R = bls.P, bls.N
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_vectors.json")))
+rnd = random.Random(5)
+PTS = [bls.mul(bls.G, rnd.randrange(1, R)) for _ in range(12)]
+b48 = bls.fe_to_bytes
+
+
+@pytest.fixture(scope="module")
+def ctx377(pkg):
+    c = pkg.bls12_377.Context(0)  # raises without a CUDA device: no CPU fallback
+    yield c
+    c.close()
+
+
+def test_fq_mul(ctx377):
+    # the PTX carry chains (fq_mul_wide over mp_mad6, the parity-split word-serial reduction)
+    Rinv = pow(1 << 384, -1, Q)
+    n = 8192
+    a = [rnd.randrange(0, 5 * Q) for _ in range(n)]
+    b = [rnd.randrange(0, 6 * Q) for _ in range(n)]
+    a[:8] = [0, 1, Q - 1, Q, 2 * Q, 5 * Q - 1, (1 << 380) - 1, 15 * Q]
+    b[:8] = [0, 1, Q - 1, Q, 6 * Q - 1, 2 * Q, 1, 2 * Q - 1]
+    # words of all ones / all zeros push carries through every position of the chains
+    for k in range(11):
+        a[8 + k] = int("ffffffff" * (k + 1), 16) << (32 * ((3 * k) % (11 - k) if k < 10 else 0))
+        a[8 + k] %= 8 * Q
+        b[8 + k] = (1 << (32 * (k + 1))) - 1
+    out = ctx377.dbg_fq_mul(b"".join(map(b48, a)), b"".join(map(b48, b)))
+    for i in range(n):
+        r = int.from_bytes(out[48 * i:48 * i + 48], "little")
+        assert r < 2 * Q and r % Q == a[i] * b[i] * Rinv % Q, i
+
+
+def test_point_add_complete(ctx377):
+    ps, qs, want = [], [], []
+    for a in PTS[:6]:
+        for b in PTS[6:]:
+            ps.append(a); qs.append(b); want.append(bls.add(a, b))
+        for b in (a, bls.neg(a), None):
+            ps.append(a); qs.append(b); want.append(bls.add(a, b))
+        ps.append(None); qs.append(a); want.append(a)
+    out = ctx377.dbg_point_add(b"".join(map(pb, ps)), b"".join(map(pb, qs)))
+    for i, w in enumerate(want):
+        assert out[96 * i:96 * i + 96] == pb(w), i
+
+
+def test_scalar_mul(ctx377):
+    ks = [0, 1, 2, R - 1, R, R + 1] + [rnd.randrange(0, 1 << 256) for _ in range(10)]
+    ps = [PTS[i % 12] for i in range(len(ks))]
+    out = ctx377.dbg_scalar_mul(b"".join(map(pb, ps)), b"".join(k.to_bytes(32, "little") for k in ks))
+    for i, (p, k) in enumerate(zip(ps, ks)):
+        assert out[96 * i:96 * i + 96] == pb(bls.mul(p, k)), i
+
+
+def msm_case(ctx377, n, c, seed=1, kind="uniform"):
+    s0, s1, pts, st = chain_points(n, seed)
+    ks = scalars(st, n, kind)
+    e = sum(k * (s0 + i * s1) for i, k in enumerate(ks)) % R
+    got = ctx377.msm_g1(b"".join(map(pb, pts)), b"".join(map(b32, ks)), c)
+    assert got == pb(bls.mul(bls.G, e)), (n, c, kind)
+
+
+@pytest.mark.parametrize("n,c", [(1, 4), (2, 4), (7, 4), (33, 5), (100, 6), (300, 0), (300, 8), (1000, 9), (1000, 0)])
+def test_msm_small(ctx377, n, c):
+    msm_case(ctx377, n, c)
+
+
+@pytest.mark.parametrize("kind", ["zero", "max", "small", "same"])
+def test_msm_scalar_edges(ctx377, kind):
+    # "max" = r - 1 has bit 252 set: the signed-digit recoding needs the 254th bit (kScalarBits)
+    for c in (6, 11, 0):
+        msm_case(ctx377, 200, c, kind=kind)
+
+
+def test_msm_empty(ctx377):
+    assert ctx377.msm_g1(b"", b"", 0) == bytes(96)
+
+
+def test_msm_golden(ctx377):
+    for fx in GOLD["msm"]:
+        fn = ctx377.msm_g1 if fx["ncomp"] == 1 else ctx377.ct_msm
+        assert fn(bytes.fromhex(fx["points"]), bytes.fromhex(fx["scalars"]), 0).hex() == fx["result"]
+    assert ctx377.msm_g1(bytes.fromhex(GOLD["generator"]), b32(R - 1), 0).hex() == GOLD["multiples"][str(R - 1)]
+
+
+def test_msm_point_edges(ctx377):
+    st = Stream(3)
+    Pt = PTS[0]
+    n = 150
+    ks = [st.scalar() for _ in range(n)]
+    for name, pts in [("equal", [Pt] * n), ("pm", [Pt if i % 2 == 0 else bls.neg(Pt) for i in range(n)]),
+                      ("ident", [None if i % 3 == 0 else PTS[i % 12] for i in range(n)])]:
+        want = pb(bls.msm(pts, ks))
+        for c in (4, 7, 0):
+            assert ctx377.msm_g1(b"".join(map(pb, pts)), b"".join(map(b32, ks)), c) == want, (name, c)
+    # one heavy bucket spanning many accumulate chunks
+    assert ctx377.msm_g1(pb(Pt) * 500, b32(12345) * 500, 8) == pb(bls.mul(Pt, 12345 * 500))
+
+
+def test_ct_msm(ctx377):
+    s0, s1, pts, st = chain_points(400, 9)
+    n = 200
+    ks = [st.scalar() for _ in range(n)]
+    deck = b"".join(pb(pts[2 * i]) + pb(pts[2 * i + 1]) for i in range(n))
+    e1 = sum(k * (s0 + (2 * i) * s1) for i, k in enumerate(ks)) % R
+    e2 = sum(k * (s0 + (2 * i + 1) * s1) for i, k in enumerate(ks)) % R
+    for c in (5, 0):
+        got = ctx377.ct_msm(deck, b"".join(map(b32, ks)), c)
+        assert got == pb(bls.mul(bls.G, e1)) + pb(bls.mul(bls.G, e2)), c
+
+
+@pytest.mark.parametrize("n,c", [(4096, 0), (4096, 12), (65536, 0), (65536, 16)])
+def test_msm_mid(ctx377, n, c):
+    msm_case(ctx377, n, c, seed=2)
+
+
+def test_rejects_bad_points(ctx377, pkg):
+    with pytest.raises(pkg.MpError) as e:  # not on the curve
+        ctx377.msm_g1(b48(5) + b48(7), b32(3), 4)
+    assert e.value.code == -3
+    g = bls.G
+    with pytest.raises(pkg.MpError) as e:  # non-canonical alias x + q of a curve point
+        ctx377.msm_g1(b48(g[0] + Q) + b48(g[1]), b32(3), 4)
+    assert e.value.code == -3
+
+
+def test_pedersen_commit_batch(ctx377, pkg):
+    fx = GOLD["pedersen"][0]
+    ctx377.set_commit_key(bytes.fromhex(fx["ck"]))
+    assert ctx377.pedersen_commit_batch(bytes.fromhex(fx["values"]), bytes.fromhex(fx["blinds"]), fx["len"]).hex() == fx["result"]
+    # the reference benchmark's key lengths (parameter_selection.rs:42-43: n in 150, 50, 30, 25, 10), short rows
+    s0, s1, ck, st = chain_points(151, 11)
+    ctx377.set_commit_key(b"".join(map(pb, ck)))
+    logs = [(s0 + i * s1) % R for i in range(151)]
+    for length, k in [(150, 4), (30, 7), (1, 3), (0, 2)]:
+        vals = [[st.scalar() for _ in range(length)] for _ in range(k)]
+        vals[0] = [0] * length
+        blinds = [st.scalar() for _ in range(k)]
+        got = ctx377.pedersen_commit_batch(b"".join(b32(x) for v in vals for x in v), b"".join(map(b32, blinds)), length)
+        for j in range(k):
+            e = (blinds[j] * logs[0] + sum(v * l for v, l in zip(vals[j], logs[1:]))) % R
+            assert got[96 * j:96 * j + 96] == pb(bls.mul(bls.G, e)), (length, j)
+    with pytest.raises(pkg.MpError):
+        ctx377.pedersen_commit_batch(b32(1) * 151, b32(1), 151)  # longer than the key
+
+
+def test_kernels_were_launched(ctx377):
+    msm_case(ctx377, 64, 0)
+    assert ctx377.launches > 0
+
+
+def test_msm_2p18_linearity(ctx377):
+    """Full-size property (no oracle at this size): MSM(P, k) + MSM(P, k') = MSM(P, k + k')."""
+    import torch
+    n = 1 << 18
+    dev = torch.device("cuda:0")
+    s0, s1, pts, st = chain_points(512, 31)
+    base = torch.frombuffer(bytearray(b"".join(map(pb, pts))), dtype=torch.uint8).reshape(512, 96)
+    idx = torch.arange(n) % 512
+    d_pts = base[idx].contiguous().to(dev)
+    g = torch.Generator().manual_seed(7)
+    k1 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, generator=g)
+    k2 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, generator=g)
+    k1[:, 31] &= 0x07  # < 2^251 < r, and k1 + k2 < 2^252 < r: no reduction needed for the sum
+    k2[:, 31] &= 0x07
+    a = k1.to(torch.int32).reshape(n, 32)
+    b = k2.to(torch.int32).reshape(n, 32)
+    s = a + b
+    carry = torch.zeros(n, dtype=torch.int32)
+    out = torch.zeros(n, 32, dtype=torch.uint8)
+    for j in range(32):
+        t = s[:, j] + carry
+        out[:, j] = (t & 0xFF).to(torch.uint8)
+        carry = t >> 8
+    res = []
+    d_out = torch.zeros(96, dtype=torch.uint8, device=dev)
+    for ks in (k1, k2, out):
+        d_k = ks.contiguous().to(dev)
+        ctx377.msm_g1_device(d_pts.data_ptr(), d_k.data_ptr(), n, d_out.data_ptr(), 0)
+        ctx377.sync()
+        res.append(bls.point_from_bytes(bytes(d_out.cpu().numpy())))
+    assert bls.is_on_curve(res[0]) and res[0] is not None
+    assert bls.add(res[0], res[1]) == res[2]

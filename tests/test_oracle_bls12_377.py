@@ -1,0 +1,65 @@
+"""The BLS12-377 oracle against mathematics (curve-family identities, group laws) and against its committed
+golden fixtures (tests/golden/bls12_377_vectors.json)."""
+import json
+import os
+import random
+
+from sympy import isprime
+
+from oracle.py import bls12_377 as bls
+from _util_bls12_377 import chain_points, pb, b32
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_vectors.json")))
+
+
+def test_curve_constants():
+    x = bls.X_PARAM
+    # BLS12 family: r = x^4 - x^2 + 1, q = (x - 1)^2 r / 3 + x; G1: y^2 = x^3 + 1 of order h * r
+    assert bls.N == x ** 4 - x ** 2 + 1 and bls.P == (x - 1) ** 2 * bls.N // 3 + x
+    assert isprime(bls.P) and isprime(bls.N)
+    assert bls.P.bit_length() == 377 and bls.N.bit_length() == 253
+    assert bls.COFACTOR == (x - 1) ** 2 // 3
+    # the trace of Frobenius t = x + 1 gives #E(F_q) = q + 1 - t = h * r
+    assert bls.P + 1 - (x + 1) == bls.COFACTOR * bls.N
+    assert bls.is_on_curve(bls.G) and bls.mul(bls.G, bls.N) is None
+    assert bls.CURVE.mul.__self__.N == bls.N
+
+
+def test_group_laws():
+    rnd = random.Random(1)
+    a, b, c = (bls.mul(bls.G, rnd.randrange(1, bls.N)) for _ in range(3))
+    assert bls.add(a, b) == bls.add(b, a)
+    assert bls.add(bls.add(a, b), c) == bls.add(a, bls.add(b, c))
+    assert bls.add(a, bls.neg(a)) is None and bls.add(a, None) == a
+    k1, k2 = rnd.randrange(bls.N), rnd.randrange(bls.N)
+    assert bls.add(bls.mul(a, k1), bls.mul(a, k2)) == bls.mul(a, (k1 + k2) % bls.N)
+    assert bls.mul(bls.mul(a, k1), k2) == bls.mul(a, k1 * k2 % bls.N)
+    assert bls.point_from_bytes(pb(a)) == a and bls.point_from_bytes(pb(None)) is None
+
+
+def test_chain_points_have_known_logs():
+    s0, s1, pts, st = chain_points(6, 9)
+    for i, p in enumerate(pts):
+        assert p == bls.mul(bls.G, (s0 + i * s1) % bls.N)
+
+
+def test_golden_vectors():
+    assert pb(bls.G).hex() == GOLD["generator"]
+    for k, v in GOLD["multiples"].items():
+        assert pb(bls.mul(bls.G, int(k))).hex() == v
+    for fx in GOLD["msm"]:
+        nc = fx["ncomp"]
+        pts = [bls.point_from_bytes(bytes.fromhex(fx["points"])[96 * i:96 * i + 96]) for i in range(fx["n"] * nc)]
+        ks = [int.from_bytes(bytes.fromhex(fx["scalars"])[32 * i:32 * i + 32], "little") for i in range(fx["n"])]
+        assert b"".join(pb(bls.msm(pts[c::nc], ks)) for c in range(nc)).hex() == fx["result"]
+    for fx in GOLD["pedersen"]:
+        L, k = fx["len"], fx["k"]
+        ck = [bls.point_from_bytes(bytes.fromhex(fx["ck"])[96 * i:96 * i + 96]) for i in range(L + 1)]
+        vals = bytes.fromhex(fx["values"])
+        blinds = bytes.fromhex(fx["blinds"])
+        out = b""
+        for j in range(k):
+            v = [int.from_bytes(vals[32 * (j * L + i):32 * (j * L + i) + 32], "little") for i in range(L)]
+            r = int.from_bytes(blinds[32 * j:32 * j + 32], "little")
+            out += pb(bls.add(bls.mul(ck[0], r), bls.msm(ck[1:], v)))
+        assert out.hex() == fx["result"]
