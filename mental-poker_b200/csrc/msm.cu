@@ -661,6 +661,39 @@ __global__ void __launch_bounds__(64) k_reduce_win_serial(const xyzz* __restrict
   xyzz_store(win_out + g, tsum);
 }
 
+// Hierarchical form of the same combine: thread per (window, group of G consecutive segments, comp) folds
+// its group into ONE segment of length L*G,
+//   S' = sum_i S_i,   T' = sum_i T_i + L * sum_i i * S_i     (i = index inside the group),
+// because a bucket at offset j of sub-segment i has weight i*L + (j+1) in the merged segment.  Applying it
+// until one segment per window is left yields T' = the window sum.  Serial per thread, no cross-lane
+// traffic: used by the 12-limb build, where the block-wide kernel below does not reproduce it (see DESIGN).
+__global__ void __launch_bounds__(64) k_reduce_group(const xyzz* __restrict__ segS, const xyzz* __restrict__ segT,
+                                                     uint64_t nwin, uint32_t nseg, uint32_t G, uint32_t L, int ncomp,
+                                                     xyzz* __restrict__ outS, xyzz* __restrict__ outT) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ngroups = nseg / G;
+  if (g >= nwin * ngroups * ncomp) return;
+  const uint32_t comp = (uint32_t)(g % ncomp);
+  const uint64_t wg = g / ncomp;  // window * ngroups + group
+  const uint64_t win = wg / ngroups, grp = wg % ngroups;
+  const xyzz* S = segS + (win * nseg + grp * G) * ncomp + comp;
+  const xyzz* T = segT + (win * nseg + grp * G) * ncomp + comp;
+  xyzz run = xyzz_identity(), lsum = xyzz_identity(), tsum = xyzz_load(T);
+  for (uint32_t i = G - 1; i >= 1; i--) {
+    xyzz a = xyzz_load(S + (uint64_t)i * ncomp);
+    xyzz_add_ni(run, a);
+    xyzz_add_ni(lsum, run);
+    xyzz tv = xyzz_load(T + (uint64_t)i * ncomp);
+    xyzz_add_ni(tsum, tv);
+  }
+  xyzz s0 = xyzz_load(S);
+  xyzz_add_ni(run, s0);  // S' includes sub-segment 0 (weight 0 in lsum)
+  for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(lsum);
+  xyzz_add_ni(tsum, lsum);
+  xyzz_store(outS + g, run);
+  xyzz_store(outT + g, tsum);
+}
+
 // block-wide sum of one xyzz per thread (kWinThreads threads); result valid in thread 0
 __device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem /* kWinThreads/32 entries */) {
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -900,10 +933,34 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     ws->launches++;
   }
   k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
-  if (nseg <= 32)
+  static const bool force_serial = [] { const char* e = getenv("MP_WIN_SERIAL"); return e && atoi(e) != 0; }();
+  if (nseg <= 32) {
     k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
-  else
+  } else if (kFqLimbs > 8 || force_serial) {
+    // fold groups of 32 segments until at most 32 are left (2048 -> 64 -> 2 for c = 16), then the serial combine
+    xyzz *gS[2], *gT[2];
+    const size_t lvl0 = nwin * (nseg / 32) * ncomp, lvl1 = nwin * (nseg / 1024 + 1) * ncomp;
+    MP_CK(ws->get(14, lvl0 + lvl1, &gS[0]));
+    MP_CK(ws->get(15, lvl0 + lvl1, &gT[0]));
+    gS[1] = gS[0] + lvl0;  // the second level is written behind the first (which it reads)
+    gT[1] = gT[0] + lvl0;
+    const xyzz *curS = segS, *curT = segT;
+    uint32_t cur_nseg = nseg, cur_L = L;
+    int level = 0;
+    while (cur_nseg > 32) {
+      xyzz* oS = level == 0 ? gS[0] : gS[1];
+      xyzz* oT = level == 0 ? gT[0] : gT[1];
+      const uint64_t threads = nwin * (cur_nseg / 32) * ncomp;
+      k_reduce_group<<<(unsigned)((threads + 63) / 64), 64, 0, stream>>>(curS, curT, nwin, cur_nseg, 32, cur_L, ncomp, oS, oT);
+      ws->launches++;
+      curS = oS; curT = oT;
+      cur_nseg /= 32; cur_L *= 32;
+      if (++level > 2) return cudaErrorInvalidValue;  // nseg <= 2048 * 16: never more than two levels
+    }
+    k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(curS, curT, nwin * ncomp, cur_nseg, cur_L, ncomp, win_out);
+  } else {
     k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
+  }
   k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, Wb, c, ncomp, d_out);
   ws->launches += 3;
   return cudaGetLastError();
