@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 GX = 0x01EF15C18599971B7BECED415A40F0C7DEACFD9B0D1819E03D723D8BC943CFCA
 GY = 0x005668060AA49730B7BE4801DF46EC62DE53ECD11ABE43A32873000C36E8DC1F
 G64 = GX.to_bytes(32, "little") + GY.to_bytes(32, "little")
+# BLS12-377 G1 generator, x || y as 48-byte little-endian coordinates (include/mpshuffle_bls12_377.h)
+GEN_BLS12_377 = (0x008848DEFE740A67C8FC6225BF87FF5485951E2CAA9D41BB188282C8BD37CB5CD5481512FFCD394EEAB9B16EB21BE9EF.to_bytes(48, "little")
+                 + 0x01914A69C5102EFF1F674F5D30AFEEC4BD7FB348CA3E52D96D182AD44FB82305C2FE3D3634A9591AFD82DE55559C8EA6.to_bytes(48, "little")).hex()
 METRIC = "shuffle proofs/sec (prove+verify)"
 UNIT = "proofs/s"
 
@@ -223,6 +226,8 @@ def main():
     ap.add_argument("--sigma-cards", type=int, default=65536,
                     help="cards in the batched mask / remask / reveal and the wire-format measurements (SURVEY 8(f) ranks 1-2; 0 = skip)")
     ap.add_argument("--msm-logn", type=int, default=20, help="size of the MSM microbench reported beside the metric")
+    ap.add_argument("--bls12-377-logn", type=int, default=20,
+                    help="size of the BLS12-377 G1 MSM measurement (second curve, SURVEY 8(f) rank 3; 0 = skip)")
     args = ap.parse_args()
     m, n = args.m, args.n
     N = m * n
@@ -373,6 +378,11 @@ def main():
         wir = wire_bench(pkg, ctx, args.sigma_cards, not args.no_cpu_baseline and rank == 0) if args.sigma_cards > 0 else None
     except Exception as e:
         wir = dict(error=repr(e))
+    try:
+        bls = (bls12_377_bench(pkg, torch, dev, args.bls12_377_logn, not args.no_cpu_baseline)
+               if args.bls12_377_logn > 0 and rank == 0 else None)
+    except Exception as e:
+        bls = dict(error=repr(e))
     if rank == 0:
         peak, peak_src = load_peaks()
         bytes_per_add = 68.0  # 64 B affine point gather + 4 B sorted index
@@ -407,6 +417,7 @@ def main():
         line["pipelined"] = piped
         line["sigma"] = sig
         line["wire"] = wir
+        line["bls12_377"] = bls
         if not args.no_cpu_baseline and world == 1:
             sm, sn = sample_shape(m, n)
             val, desc, legs = cpu_sample(m, n, sm, sn, threads=1)
@@ -569,6 +580,105 @@ def pipelined_bench(pkg, ctx, inst, q):
         res = dict(decks=q, prove_s=t1 - t0, verify_s=t2 - t1, proofs_per_s=q / (t2 - t0), prove_per_s=q / (t1 - t0),
                    verify_per_s=q / (t2 - t1), all_verified=all(s == 0 for s in statuses),
                    note="mp_shuffle_and_remask_batch + mp_shuffle_verify_batch, host buffers, wall clock")
+    return res
+
+
+def bls12_377_bench(pkg, torch, dev, logn, cpu_baseline):
+    """SURVEY.md section 8(f) rank 3 (group layer of the reference's second instantiation,
+    `DLCards<ark_bls12_377::G1Projective>`, examples/parameter_selection.rs:25-29): a 2^logn-term G1 MSM with
+    device-resident inputs (CUDA events on the context's stream, L2 flushed between iterations), the
+    ciphertext MSM of a 2^16-card verify_shuffle, one batch of (m, n) = (128, 512) Pedersen commitments with
+    host buffers, the field microbenchmarks, and the C restatement (oracle/c/bls12_377.c, ark-style
+    Pippenger) on a bounded sample."""
+    import numpy as np
+    ctx = pkg.bls12_377.Context(dev.index or 0)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    rng = np.random.default_rng(11)
+    g96 = bytes.fromhex(GEN_BLS12_377)
+    n = 1 << logn
+    nb = 4096
+    base = ctx.dbg_scalar_mul(g96 * nb, rand_scalars(rng, nb))
+    bases = torch.frombuffer(bytearray(base), dtype=torch.uint8).to(dev).repeat(n // nb).contiguous()
+    scal_h = rand_scalars(rng, n)
+    scal = torch.frombuffer(bytearray(scal_h), dtype=torch.uint8).to(dev)
+    out = torch.zeros(192, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {"curve": "BLS12-377 G1 (48-byte coordinates, 12 x 32-bit limbs)"}
+
+    def timed(fn, reps=5):
+        ts = []
+        for it in range(reps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    c = 16 if logn >= 19 else (13 if logn >= 15 else 10)
+    ctx.profile_enable(True)
+    ctx.profile_collect()
+    ms = timed(lambda: ctx.msm_g1_device(bases.data_ptr(), scal.data_ptr(), n, out.data_ptr(), c))
+    acc_ms, acc_adds, acc_n = ctx.profile_collect()
+    ctx.profile_enable(False)
+    adds = ctx.last_msm_ec_adds
+    launches = ctx.launches
+    peak, peak_src = load_peaks()
+    acc_rate = acc_adds / (acc_ms / 1e3) if acc_ms else None
+    res["msm"] = dict(terms=n, window_bits=c, ms=ms, ec_adds=adds, ec_adds_per_s=adds / (ms / 1e3), terms_per_s=n / (ms / 1e3),
+                      accumulate_ms_avg=acc_ms / max(acc_n, 1), accumulate_adds_per_s=acc_rate, gpu_launches=launches,
+                      roofline=dict(bound="hbm", kernel="k_accumulate<1> (12-limb build)", unit="GB/s", peak=peak, peak_source=peak_src,
+                                    achieved=(100.0 * acc_rate / 1e9 if acc_rate else None),
+                                    frac=(100.0 * acc_rate / 1e9 / peak if acc_rate else None),
+                                    note="algorithmic bytes per bucket addition: 96 B affine point + 4 B sorted index; "
+                                         "integer-pipe bound (~10 field multiplications of 276 IMAD.WIDE each per addition)"),
+                      result_x_prefix=bytes(out[:96].cpu().numpy().tobytes()).hex()[:16])
+    # the verifier's dominant job at 2^16 cards: an N-term ciphertext MSM (2 components share digits and sort)
+    nct = min(1 << 16, n // 2)
+    msc = timed(lambda: ctx.ct_msm_device(bases.data_ptr(), scal.data_ptr(), nct, out.data_ptr(), 0))
+    res["ct_msm"] = dict(ciphertexts=nct, window_bits=ctx.last_msm_window, ms=msc, ec_adds=ctx.last_msm_ec_adds,
+                         ec_adds_per_s=ctx.last_msm_ec_adds / (msc / 1e3))
+    # Pedersen commitments, (m, n) = (128, 512): m rows of n values over the constant key, host buffers
+    m_rows, n_len = 128, 512
+    ctx.set_commit_key(base[:96 * (n_len + 1)])
+    vals, blinds = rand_scalars(rng, m_rows * n_len), rand_scalars(rng, m_rows)
+    com = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        com = ctx.pedersen_commit_batch(vals, blinds, n_len)
+        dt = time.perf_counter() - t0
+    res["pedersen"] = dict(rows=m_rows, length=n_len, ms=dt * 1e3, commitments_per_s=m_rows / dt, terms_per_s=m_rows * (n_len + 1) / dt,
+                           gpu_launches=ctx.launches, timing="host wall clock around the C-ABI call (host buffers)")
+    mb = {}
+    for which, name, iters in [(0, "fq_mul", 1000), (1, "madd", 300)]:
+        best = 0
+        for rep in range(2):
+            t_ms, ops = ctx.dbg_bench(which, iters)
+            best = max(best, ops / t_ms / 1e6)
+        mb[name + "_G_per_s"] = best
+    res["microbench"] = mb
+    if cpu_baseline:
+        from oracle import c_oracle
+        co = c_oracle.COracleBls12_377(threads=1)
+        k = min(n, 1 << 13)
+        pts_h = base[:96 * min(k, nb)] * (k // min(k, nb))
+        t0 = time.perf_counter()
+        want = co.msm(pts_h, scal_h[:32 * k], 1, 1)
+        dt = time.perf_counter() - t0
+        got = ctx.msm_g1(pts_h, scal_h[:32 * k], 0)
+        t0 = time.perf_counter()
+        wantc = co.msm(base[:96 * (n_len + 1)], blinds[:32] + vals[:32 * n_len], 1, 1)
+        dtc = time.perf_counter() - t0
+        res["cpu_baseline"] = dict(value=k / dt, unit="MSM terms/s", cores=1, kind="port",
+                                   sample=f"C restatement (oracle/c/bls12_377.c: ark-ff-style 6 x u64 Montgomery, ark-ec 0.3 "
+                                          f"VariableBaseMSM), 1 thread, {k}-term G1 MSM: {dt:.2f} s; one ({n_len}+1)-term commitment: {dtc * 1e3:.1f} ms",
+                                   commitments_per_s=1.0 / dtc,
+                                   bytes_identical_to_gpu=bool(got == want and com[:96] == wantc))
+    ctx.close()
     return res
 
 

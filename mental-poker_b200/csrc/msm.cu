@@ -271,6 +271,21 @@ __global__ void __launch_bounds__(64) k_table_normalise(const xyzz* __restrict__
   }
 }
 
+// thread per (window, base): one inversion per table entry.  W x more inversions than the kernel above
+// (a table is built once per key: 513 bases x 43 windows x ~470 multiplications is ~1 ms), no per-thread
+// prefix array
+__global__ void __launch_bounds__(64) k_table_normalise_each(const xyzz* __restrict__ tmp, uint32_t nb, uint32_t first,
+                                                             uint32_t count, int W, affine* __restrict__ table) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint64_t)W * count) return;
+  const uint32_t w = (uint32_t)(g / count), i = (uint32_t)(g % count);
+  const affine a = xyzz_to_affine(xyzz_load(tmp + g));
+  uint4* d = reinterpret_cast<uint4*>(table + (size_t)w * nb + first + i);
+  const uint4* s = reinterpret_cast<const uint4*>(&a);
+#pragma unroll
+  for (int k = 0; k < kAffVec; k++) d[k] = s[k];
+}
+
 cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb, uint32_t first, uint32_t count,
                             int c, affine* d_table, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
@@ -279,7 +294,11 @@ cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb
   xyzz* tmp;
   MP_CK(ws->get(13, (size_t)W * count, &tmp));
   k_table_shift<<<(count + 63) / 64, 64, 0, stream>>>(d_bases, nb, first, count, c, W, tmp);
-  k_table_normalise<<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
+  static const bool trick = [] { const char* e = getenv("MP_TABLE_TRICK"); return e ? atoi(e) != 0 : kFqLimbs <= 8; }();
+  if (trick)
+    k_table_normalise<<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
+  else
+    k_table_normalise_each<<<(unsigned)(((uint64_t)W * count + 63) / 64), 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
   return cudaGetLastError();
 }
 
@@ -934,9 +953,10 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   }
   k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
   static const bool force_serial = [] { const char* e = getenv("MP_WIN_SERIAL"); return e && atoi(e) != 0; }();
+  static const bool force_block = [] { const char* e = getenv("MP_WIN_BLOCK"); return e && atoi(e) != 0; }();
   if (nseg <= 32) {
     k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
-  } else if (kFqLimbs > 8 || force_serial) {
+  } else if ((kFqLimbs > 8 && !force_block) || force_serial) {
     // fold groups of 32 segments until at most 32 are left (2048 -> 64 -> 2 for c = 16), then the serial combine
     xyzz *gS[2], *gT[2];
     const size_t lvl0 = nwin * (nseg / 32) * ncomp, lvl1 = nwin * (nseg / 1024 + 1) * ncomp;

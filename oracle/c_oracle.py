@@ -161,3 +161,35 @@ class COracle:
         st = (ctypes.c_int32 * max(n, 1))()
         self.lib.oc_points_decompress(data, n, out, st)
         return out.raw, list(st)[:n]
+
+
+class COracleBls12_377:
+    """oracle/c/bls12_377.c: the CPU group arithmetic of the reference's BLS12-377 instantiation
+    (48-byte coordinates, 96-byte points; include/mpshuffle_bls12_377.h layouts)."""
+
+    def __init__(self, threads=1):
+        so = os.path.join(_HERE, "c", "liboracle_bls12_377.so")
+        if not os.path.exists(so):
+            build()
+        self.lib = ctypes.CDLL(so)
+        cp, u64, i32 = ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int
+        self.lib.oc377_msm.argtypes = [cp, cp, u64, i32, i32, cp]
+        self.lib.oc377_fq_mul.argtypes = [cp, cp, cp]
+        self.lib.oc377_set_threads.argtypes = [i32]
+        self.lib.oc377_set_threads(threads)
+
+    def set_threads(self, threads):
+        self.lib.oc377_set_threads(threads)
+
+    def msm(self, points: bytes, scalars: bytes, ncomp=1, mode=1) -> bytes:
+        """mode 0: per-term double-and-add; mode 1: ark-ec 0.3 VariableBaseMSM."""
+        n = len(scalars) // 32
+        assert len(points) == 96 * n * ncomp
+        out = ctypes.create_string_buffer(96 * ncomp)
+        self.lib.oc377_msm(points, scalars, n, ncomp, mode, out)
+        return out.raw
+
+    def fq_mul(self, a: bytes, b: bytes) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        self.lib.oc377_fq_mul(a, b, out)
+        return out.raw
