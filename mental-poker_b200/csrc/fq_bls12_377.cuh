@@ -229,10 +229,9 @@ MP_HD bool fq_eq_raw(const fq& a, const fq& b) {
 // semantics, so the index bookkeeping of the product and of the reduction below -- written once, in
 // plain C++ over these primitives -- is what the host tests exercise.
 // ------------------------------------------------------------------------------------------
-// c[0..11] += {a0 .. a5} * b laid out as six adjacent 64-bit products; returns the carry out of c[11]
-MP_HD uint32_t mp_mad6(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
-                       uint32_t a5, uint32_t b) {
-  uint32_t carry;
+// c[0..11] += {a0 .. a5} * b laid out as six adjacent 64-bit products; top += the carry out of c[11]
+MP_HD void mp_mad6(uint32_t* c, uint32_t& top, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                   uint32_t a5, uint32_t b) {
 #ifdef __CUDA_ARCH__
   asm("mad.lo.cc.u32 %0, %13, %19, %0;\n\t"
       "madc.hi.cc.u32 %1, %13, %19, %1;\n\t"
@@ -246,9 +245,9 @@ MP_HD uint32_t mp_mad6(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint3
       "madc.hi.cc.u32 %9, %17, %19, %9;\n\t"
       "madc.lo.cc.u32 %10, %18, %19, %10;\n\t"
       "madc.hi.cc.u32 %11, %18, %19, %11;\n\t"
-      "addc.u32 %12, 0, 0;"
+      "addc.u32 %12, %12, 0;"
       : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]),
-        "+r"(c[7]), "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "=r"(carry)
+        "+r"(c[7]), "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(top)
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(b));
 #else
   const uint32_t a[6] = {a0, a1, a2, a3, a4, a5};
@@ -262,14 +261,12 @@ MP_HD uint32_t mp_mad6(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint3
     c[2 * k + 1] = (uint32_t)cy;
     cy >>= 32;
   }
-  carry = (uint32_t)cy;
+  top += (uint32_t)cy;
 #endif
-  return carry;
 }
-
-// c[0..9] += {a0 .. a4} * b as five adjacent 64-bit products; returns the carry out of c[9]
-MP_HD uint32_t mp_mad5(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t b) {
-  uint32_t carry;
+// c[0..9] += {a0 .. a4} * b as five adjacent 64-bit products; top += the carry out of c[9]
+MP_HD void mp_mad5(uint32_t* c, uint32_t& top, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                   uint32_t b) {
 #ifdef __CUDA_ARCH__
   asm("mad.lo.cc.u32 %0, %11, %16, %0;\n\t"
       "madc.hi.cc.u32 %1, %11, %16, %1;\n\t"
@@ -281,9 +278,9 @@ MP_HD uint32_t mp_mad5(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint3
       "madc.hi.cc.u32 %7, %14, %16, %7;\n\t"
       "madc.lo.cc.u32 %8, %15, %16, %8;\n\t"
       "madc.hi.cc.u32 %9, %15, %16, %9;\n\t"
-      "addc.u32 %10, 0, 0;"
+      "addc.u32 %10, %10, 0;"
       : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]),
-        "+r"(c[7]), "+r"(c[8]), "+r"(c[9]), "=r"(carry)
+        "+r"(c[7]), "+r"(c[8]), "+r"(c[9]), "+r"(top)
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(b));
 #else
   const uint32_t a[5] = {a0, a1, a2, a3, a4};
@@ -297,26 +294,53 @@ MP_HD uint32_t mp_mad5(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint3
     c[2 * k + 1] = (uint32_t)cy;
     cy >>= 32;
   }
-  carry = (uint32_t)cy;
+  top += (uint32_t)cy;
 #endif
-  return carry;
 }
 
-// c[0..9] += m * (q2 + q4*2^64 + ... + q10*2^256)  (even limbs of q above limb 0); returns the carry out
-MP_HD uint32_t mp_red_even(uint32_t* c, uint32_t m) {
-  return mp_mad5(c, fq_modulus_limb(2), fq_modulus_limb(4), fq_modulus_limb(6), fq_modulus_limb(8),
-                 fq_modulus_limb(10), m);
+// c[0..9] += m * (q2 + q4*2^64 + ... + q10*2^256)  (even limbs of q above limb 0); top += carry out
+MP_HD void mp_red_even(uint32_t* c, uint32_t& top, uint32_t m) {
+  mp_mad5(c, top, fq_modulus_limb(2), fq_modulus_limb(4), fq_modulus_limb(6), fq_modulus_limb(8), fq_modulus_limb(10), m);
 }
-// c[0..11] += m * (q1 + q3*2^64 + ... + q11*2^320)  (the odd limbs of q); returns the carry out
-MP_HD uint32_t mp_red_odd(uint32_t* c, uint32_t m) {
-  return mp_mad6(c, fq_modulus_limb(1), fq_modulus_limb(3), fq_modulus_limb(5), fq_modulus_limb(7),
-                 fq_modulus_limb(9), fq_modulus_limb(11), m);
+// c[0..11] += m * (q1 + q3*2^64 + ... + q11*2^320)  (the odd limbs of q); top += carry out
+MP_HD void mp_red_odd(uint32_t* c, uint32_t& top, uint32_t m) {
+  mp_mad6(c, top, fq_modulus_limb(1), fq_modulus_limb(3), fq_modulus_limb(5), fq_modulus_limb(7), fq_modulus_limb(9),
+          fq_modulus_limb(11), m);
 }
 
-// r[0..n) = x[0..n) + y[0..n) (+ cin), carry out dropped (callers know the bound)
+// One reduction round's word: w = t + o + p (the three accumulators' shares of word i).  Returns
+// m = -w mod 2^32 and adds to `up` what moves into word i+1: the carries of the sum, plus one more when
+// w != 0 mod 2^32, because w + m*q0 = w + m = 2^32 exactly (q0 = 1).
+MP_HD uint32_t mp_fold(uint32_t t, uint32_t o, uint32_t p, uint32_t& up) {
+  uint32_t m;
+#ifdef __CUDA_ARCH__
+  // volatile: the negation must stay hidden from the compiler -- seen as `0 - w` it is folded into the
+  // multiplications as a negated operand, which the 64-bit IMAD.WIDE form does not have, and every product
+  // of the reduction then costs an IMAD + an IMAD.HI (measured in SASS) instead of one IMAD.WIDE
+  uint32_t w, hi;
+  asm volatile("add.cc.u32 %0, %4, %5;\n\t"
+               "addc.u32 %1, 0, 0;\n\t"
+               "add.cc.u32 %0, %0, %6;\n\t"
+               "addc.u32 %1, %1, 0;\n\t"
+               "add.cc.u32 %2, %0, 0xffffffff;\n\t"  // carry out  <=>  w != 0
+               "addc.u32 %1, %1, 0;\n\t"
+               "sub.u32 %2, 0, %0;\n\t"
+               "add.u32 %3, %3, %1;"
+               : "=&r"(w), "=&r"(hi), "=&r"(m), "+r"(up)
+               : "r"(t), "r"(o), "r"(p));
+#else
+  const uint64_t s = (uint64_t)t + o + p;
+  const uint32_t w = (uint32_t)s;
+  m = 0u - w;
+  up += (uint32_t)(s >> 32) + (w != 0u ? 1u : 0u);
+#endif
+  return m;
+}
+
+// r[0..N) = x[0..N) + y[0..N), carry out dropped (callers know the bound)
 template <int N>
-MP_HD void mp_add_words(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin = 0) {
-  uint64_t c = cin;
+MP_HD void mp_add_words(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+  uint64_t c = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) {
     c += (uint64_t)x[i] + y[i];
@@ -324,6 +348,64 @@ MP_HD void mp_add_words(uint32_t* r, const uint32_t* x, const uint32_t* y, uint3
     c >>= 32;
   }
 }
+#ifdef __CUDA_ARCH__
+template <>
+__device__ __forceinline__ void mp_add_words<12>(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+  asm("add.cc.u32 %0, %12, %24;\n\t"
+      "addc.cc.u32 %1, %13, %25;\n\t"
+      "addc.cc.u32 %2, %14, %26;\n\t"
+      "addc.cc.u32 %3, %15, %27;\n\t"
+      "addc.cc.u32 %4, %16, %28;\n\t"
+      "addc.cc.u32 %5, %17, %29;\n\t"
+      "addc.cc.u32 %6, %18, %30;\n\t"
+      "addc.cc.u32 %7, %19, %31;\n\t"
+      "addc.cc.u32 %8, %20, %32;\n\t"
+      "addc.cc.u32 %9, %21, %33;\n\t"
+      "addc.cc.u32 %10, %22, %34;\n\t"
+      "addc.u32 %11, %23, %35;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(x[8]),
+        "r"(x[9]), "r"(x[10]), "r"(x[11]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]),
+        "r"(y[6]), "r"(y[7]), "r"(y[8]), "r"(y[9]), "r"(y[10]), "r"(y[11]));
+}
+template <>
+__device__ __forceinline__ void mp_add_words<23>(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+  asm("add.cc.u32 %0, %23, %46;\n\t"
+      "addc.cc.u32 %1, %24, %47;\n\t"
+      "addc.cc.u32 %2, %25, %48;\n\t"
+      "addc.cc.u32 %3, %26, %49;\n\t"
+      "addc.cc.u32 %4, %27, %50;\n\t"
+      "addc.cc.u32 %5, %28, %51;\n\t"
+      "addc.cc.u32 %6, %29, %52;\n\t"
+      "addc.cc.u32 %7, %30, %53;\n\t"
+      "addc.cc.u32 %8, %31, %54;\n\t"
+      "addc.cc.u32 %9, %32, %55;\n\t"
+      "addc.cc.u32 %10, %33, %56;\n\t"
+      "addc.cc.u32 %11, %34, %57;\n\t"
+      "addc.cc.u32 %12, %35, %58;\n\t"
+      "addc.cc.u32 %13, %36, %59;\n\t"
+      "addc.cc.u32 %14, %37, %60;\n\t"
+      "addc.cc.u32 %15, %38, %61;\n\t"
+      "addc.cc.u32 %16, %39, %62;\n\t"
+      "addc.cc.u32 %17, %40, %63;\n\t"
+      "addc.cc.u32 %18, %41, %64;\n\t"
+      "addc.cc.u32 %19, %42, %65;\n\t"
+      "addc.cc.u32 %20, %43, %66;\n\t"
+      "addc.cc.u32 %21, %44, %67;\n\t"
+      "addc.u32 %22, %45, %68;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22])
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),
+        "r"(x[8]), "r"(x[9]), "r"(x[10]), "r"(x[11]), "r"(x[12]), "r"(x[13]), "r"(x[14]), "r"(x[15]),
+        "r"(x[16]), "r"(x[17]), "r"(x[18]), "r"(x[19]), "r"(x[20]), "r"(x[21]), "r"(x[22]),
+        "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]),
+        "r"(y[8]), "r"(y[9]), "r"(y[10]), "r"(y[11]), "r"(y[12]), "r"(y[13]), "r"(y[14]), "r"(y[15]),
+        "r"(y[16]), "r"(y[17]), "r"(y[18]), "r"(y[19]), "r"(y[20]), "r"(y[21]), "r"(y[22]));
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // 12 x 12 schoolbook product, T[24] = a * b  (144 IMAD.WIDE on the device)
@@ -331,7 +413,7 @@ MP_HD void mp_add_words(uint32_t* r, const uint32_t* x, const uint32_t* y, uint3
 // ev[k] = word k of the sum of the products at even word offsets; od[k] = word k + 1 of the sum of the
 // products at odd word offsets -- so the lo/hi halves of one product are adjacent in either array and
 // a whole row is one carry chain.  The carry out of a chain lands in a word that so far holds only
-// such carries (it is the top of the partial sum), hence the plain +=.
+// such carries (it is the top of the partial sum), so it is added without a further ripple.
 MP_HD void fq_mul_wide(uint32_t* __restrict__ T, const fq& a, const fq& b) {
   uint32_t ev[26], od[24];
 #pragma unroll
@@ -341,12 +423,12 @@ MP_HD void fq_mul_wide(uint32_t* __restrict__ T, const fq& a, const fq& b) {
 #pragma unroll
   for (int i = 0; i < 12; i += 2) {
     // row i (even): even-j products at offset i + j (even) -> ev[i ..]; odd-j -> od[i ..]
-    ev[i + 12] += mp_mad6(ev + i, a.v[0], a.v[2], a.v[4], a.v[6], a.v[8], a.v[10], b.v[i]);
-    od[i + 12] += mp_mad6(od + i, a.v[1], a.v[3], a.v[5], a.v[7], a.v[9], a.v[11], b.v[i]);
+    mp_mad6(ev + i, ev[i + 12], a.v[0], a.v[2], a.v[4], a.v[6], a.v[8], a.v[10], b.v[i]);
+    mp_mad6(od + i, od[i + 12], a.v[1], a.v[3], a.v[5], a.v[7], a.v[9], a.v[11], b.v[i]);
     // row i + 1 (odd): even-j products at offset i + 1 + j (odd) -> od[i ..];
     //                  odd-j products at offset i + 1 + j (even) -> ev[i + 2 ..]
-    od[i + 12] += mp_mad6(od + i, a.v[0], a.v[2], a.v[4], a.v[6], a.v[8], a.v[10], b.v[i + 1]);
-    ev[i + 14] += mp_mad6(ev + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], a.v[9], a.v[11], b.v[i + 1]);
+    mp_mad6(od + i, od[i + 12], a.v[0], a.v[2], a.v[4], a.v[6], a.v[8], a.v[10], b.v[i + 1]);
+    mp_mad6(ev + i + 2, ev[i + 14], a.v[1], a.v[3], a.v[5], a.v[7], a.v[9], a.v[11], b.v[i + 1]);
   }
   // T = ev + (od << 32); the product is < 2^768, nothing is carried out of word 23
   T[0] = ev[0];
@@ -374,25 +456,13 @@ MP_HD fq fq_mont_reduce(uint32_t* T) {
   for (int i = 0; i < 26; i++) pend[i] = 0;
 #pragma unroll
   for (int i = 0; i < 12; i++) {
-    const uint64_t s = (uint64_t)T[i] + pend[i] + (i > 0 ? od[i - 1] : 0u);
-    const uint32_t lo = (uint32_t)s;
-#ifdef __CUDA_ARCH__
-    // the negation is hidden from the compiler: seen as `0 - lo` it is folded into the multiplications
-    // as a negated operand, which the 64-bit IMAD.WIDE form does not have -- every product of the
-    // reduction then costs an IMAD + an IMAD.HI (measured in SASS) instead of one IMAD.WIDE
-    uint32_t m;
-    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(lo));
-#else
-    const uint32_t m = 0u - lo;
-#endif
-    // word i + m*q0 = lo + m = 2^32 (or 0 when lo == 0): word i is cleared, one carry moves up
-    pend[i + 1] += (uint32_t)(s >> 32) + (lo != 0u ? 1u : 0u);
+    const uint32_t m = mp_fold(T[i], i > 0 ? od[i - 1] : 0u, pend[i], pend[i + 1]);
     if ((i & 1) == 0) {
-      pend[i + 12] += mp_red_even(T + i + 2, m);   // words i+2 .. i+11
-      pend[i + 13] += mp_red_odd(od + i, m);       // words i+1 .. i+12
+      mp_red_even(T + i + 2, pend[i + 12], m);   // words i+2 .. i+11
+      mp_red_odd(od + i, pend[i + 13], m);       // words i+1 .. i+12
     } else {
-      pend[i + 12] += mp_red_even(od + i + 1, m);  // words i+2 .. i+11 (odd-aligned pairs)
-      pend[i + 13] += mp_red_odd(T + i + 1, m);    // words i+1 .. i+12 (even-aligned pairs)
+      mp_red_even(od + i + 1, pend[i + 12], m);  // words i+2 .. i+11 (odd-aligned pairs)
+      mp_red_odd(T + i + 1, pend[i + 13], m);    // words i+1 .. i+12 (even-aligned pairs)
     }
   }
   // r = words 12 .. 23 of  T + (od << 32) + pend;  word 24 is empty by the bound

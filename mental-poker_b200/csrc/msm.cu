@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(64) k_reduce_win_serial(const xyzz* __restrict
 }
 
 // Hierarchical form of the same combine: thread per (window, group of G consecutive segments, comp) folds
-// its group into ONE segment of length L*G,
+// its group into ONE segment of length L*G (G a power of two),
 //   S' = sum_i S_i,   T' = sum_i T_i + L * sum_i i * S_i     (i = index inside the group),
 // because a bucket at offset j of sub-segment i has weight i*L + (j+1) in the merged segment.  Applying it
 // until one segment per window is left yields T' = the window sum.  Serial per thread, no cross-lane
@@ -928,10 +928,11 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     uint64_t threads = max_chunks * ncomp;
     unsigned blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
     // occupancy knob: resident blocks per SM the kernel is compiled for (register cap).  The 8-limb field
-    // runs best at 4 blocks (128 registers); the 12-limb accumulator + prefetched point need ~2x the
-    // registers, so that build defaults to 2 blocks (255 registers) instead of spilling.
-    constexpr int kMB0 = kFqLimbs > 8 ? 2 : 4;
-    static const int acc_mb = [] { const char* e = getenv("MP_ACC_MINBLOCKS"); return e ? atoi(e) : kMB0; }();
+    // runs best at 4 blocks (128 registers); so does the 12-limb one now that its multiplication is a call
+    // (the caller keeps the accumulator and the prefetched point in callee-saved registers or on the stack).
+    constexpr int kMB0 = kFqLimbs > 8 ? 3 : 4;  // lowest compiled variant (kMB0, kMB0 + 1, kMB0 + 2)
+    constexpr int kMBDefault = 4;              // measured, 12 limbs: 1.59 / 1.73 / 1.99 G adds/s at 2 / 3 / 4 blocks
+    static const int acc_mb = [] { const char* e = getenv("MP_ACC_MINBLOCKS"); return e ? atoi(e) : kMBDefault; }();
     const size_t smem = (size_t)(kAccThreads / ncomp) * kChunk * sizeof(uint32_t);  // one staged tile per warp
 #define MP_LAUNCH_ACC(NC, MB) \
   k_accumulate<NC, MB><<<blocks, kAccThreads, smem, stream>>>(sorted, offsets, nbuckets, d_points, bucket_sums, part, chunk_bucket, kChunk)
@@ -954,30 +955,33 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
   static const bool force_serial = [] { const char* e = getenv("MP_WIN_SERIAL"); return e && atoi(e) != 0; }();
   static const bool force_block = [] { const char* e = getenv("MP_WIN_BLOCK"); return e && atoi(e) != 0; }();
-  if (nseg <= 32) {
-    k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
-  } else if ((kFqLimbs > 8 && !force_block) || force_serial) {
-    // fold groups of 32 segments until at most 32 are left (2048 -> 64 -> 2 for c = 16), then the serial combine
-    xyzz *gS[2], *gT[2];
-    const size_t lvl0 = nwin * (nseg / 32) * ncomp, lvl1 = nwin * (nseg / 1024 + 1) * ncomp;
-    MP_CK(ws->get(14, lvl0 + lvl1, &gS[0]));
-    MP_CK(ws->get(15, lvl0 + lvl1, &gT[0]));
-    gS[1] = gS[0] + lvl0;  // the second level is written behind the first (which it reads)
-    gT[1] = gT[0] + lvl0;
+  // 12-limb build (and MP_WIN_SERIAL=1 on either curve, which cross-checks it against the block-wide kernel):
+  // fold groups of 4 segments, level after level, until one segment per window is left -- its T' is the
+  // window sum.  A level is 4 iterations of 3 additions per thread; the serial combine of 32 segments
+  // (96 dependent additions of ~14 field multiplications at ~1.2 us each) took 1.4 ms, two levels of 32
+  // took 2.1 ms each -- 2048 segments now fold in six levels of ~0.2 ms.
+  const bool hier = ((kFqLimbs > 8 && !force_block) || force_serial) && nseg > 4;
+  if (hier) {
+    xyzz *ping, *pong;
+    const size_t lvl = nwin * (nseg / 4) * ncomp;  // outputs of the first (largest) level
+    MP_CK(ws->get(14, 2 * lvl, &ping));            // [S | T] of the even levels
+    MP_CK(ws->get(15, 2 * lvl, &pong));            // [S | T] of the odd levels
     const xyzz *curS = segS, *curT = segT;
     uint32_t cur_nseg = nseg, cur_L = L;
-    int level = 0;
-    while (cur_nseg > 32) {
-      xyzz* oS = level == 0 ? gS[0] : gS[1];
-      xyzz* oT = level == 0 ? gT[0] : gT[1];
-      const uint64_t threads = nwin * (cur_nseg / 32) * ncomp;
-      k_reduce_group<<<(unsigned)((threads + 63) / 64), 64, 0, stream>>>(curS, curT, nwin, cur_nseg, 32, cur_L, ncomp, oS, oT);
+    for (int level = 0; cur_nseg > 1; level++) {
+      const uint32_t G = std::min<uint32_t>(4, cur_nseg);
+      xyzz* buf = (level & 1) ? pong : ping;
+      const bool last = cur_nseg == G;
+      const uint64_t threads = nwin * (cur_nseg / G) * ncomp;
+      k_reduce_group<<<(unsigned)((threads + 63) / 64), 64, 0, stream>>>(curS, curT, nwin, cur_nseg, G, cur_L, ncomp, buf,
+                                                                         last ? win_out : buf + lvl);
       ws->launches++;
-      curS = oS; curT = oT;
-      cur_nseg /= 32; cur_L *= 32;
-      if (++level > 2) return cudaErrorInvalidValue;  // nseg <= 2048 * 16: never more than two levels
+      curS = buf; curT = buf + lvl;
+      cur_nseg /= G; cur_L *= G;
     }
-    k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(curS, curT, nwin * ncomp, cur_nseg, cur_L, ncomp, win_out);
+    ws->launches -= 1;  // the tally below counts one combine launch
+  } else if (nseg <= 32) {
+    k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
   } else {
     k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
   }
