@@ -91,6 +91,22 @@ where
     }
 }
 
+/// Second curve (include/mpshuffle_bls12_377.h): the group layer of `DLCards<ark_bls12_377::G1Projective>`
+/// (reference examples/parameter_selection.rs:25-29).  48-byte coordinates, 96-byte points, 32-byte scalars.
+#[repr(C)]
+pub struct Mp377Ctx {
+    _private: [u8; 0],
+}
+extern "C" {
+    pub fn mp377_ctx_create(out: *mut *mut Mp377Ctx, device: i32) -> i32;
+    pub fn mp377_ctx_destroy(ctx: *mut Mp377Ctx);
+    pub fn mp377_last_error_string(ctx: *mut Mp377Ctx) -> *const c_char;
+    pub fn mp377_msm_g1(ctx: *mut Mp377Ctx, bases: *const u8, scalars: *const u8, n: u64, window_bits: i32, out: *mut u8) -> i32;
+    pub fn mp377_ct_msm(ctx: *mut Mp377Ctx, deck: *const u8, scalars: *const u8, n: u64, window_bits: i32, out: *mut u8) -> i32;
+    pub fn mp377_set_commit_key(ctx: *mut Mp377Ctx, ck: *const u8, len: u64) -> i32;
+    pub fn mp377_pedersen_commit_batch(ctx: *mut Mp377Ctx, values: *const u8, blinds: *const u8, k: u64, len: u64, out: *mut u8) -> i32;
+}
+
 /// Sketch of the two overridden trait methods (generic bounds elided):
 ///
 /// ```ignore
