@@ -55,6 +55,13 @@ int32_t mp377_msm_g1_device(mp377_ctx* ctx, const void* d_bases, const void* d_s
 int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
                             int32_t window_bits, void* d_out);
 
+/* Window-range split of ONE MSM across GPUs: rank r computes the windows
+ * [w_begin, w_begin + w_count) of the mp377_msm_num_windows(window_bits) windows end to end and returns
+ *   P_r = sum_w 2^(c (w - w_begin)) * (window sum w);   MSM = sum_r 2^(c * w_begin_r) * P_r
+ * after an all-gather of the 96-byte partials (mental-poker_b200/dist.py).  window_bits must be explicit. */
+int32_t mp377_msm_g1_windows_device(mp377_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                                    int32_t window_bits, int32_t w_begin, int32_t w_count, void* d_out);
+
 /* Pedersen commitments over a constant key (PedersenCommitment::setup / commit):
  * ck = h || G_1 .. G_len ((len+1)*96 bytes); builds the fixed-base window table once. */
 int32_t mp377_set_commit_key(mp377_ctx* ctx, const uint8_t* ck, uint64_t len);

@@ -26,6 +26,7 @@ SIGNATURES = {
     "mp377_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
     "mp377_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp377_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp377_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
     "mp377_set_commit_key": (_i32, [_vp, _cp, _u64]),
     "mp377_pedersen_commit_batch": (_i32, [_vp, _cp, _cp, _u64, _u64, _cp]),
     "mp377_profile_enable": (_i32, [_vp, _i32]),
@@ -109,6 +110,13 @@ class Context:
 
     def ct_msm_device(self, d_deck, d_scalars, n, d_out, window_bits=0):
         _check(self.h, lib.mp377_ct_msm_device(self.h, d_deck, d_scalars, n, window_bits, d_out))
+
+    def msm_g1_windows_device(self, d_bases, d_scalars, n, d_out, window_bits, w_begin, w_count):
+        _check(self.h, lib.mp377_msm_g1_windows_device(self.h, d_bases, d_scalars, n, window_bits, w_begin, w_count, d_out))
+
+    @staticmethod
+    def msm_num_windows(window_bits):
+        return lib.mp377_msm_num_windows(window_bits)
 
     # --- Pedersen
     def set_commit_key(self, ck: bytes):

@@ -126,7 +126,7 @@ static uint64_t scheduled_ec_adds(uint64_t n, int c, int ncomp) {
 }
 
 static int32_t msm_device_common(mp377_ctx* ctx, const void* d_points, const void* d_scalars, uint64_t n, int ncomp,
-                                 int32_t window_bits, void* d_out) {
+                                 int32_t window_bits, void* d_out, int w_begin = 0, int w_count = -1) {
   if (!ctx || (!d_points && n) || (!d_scalars && n) || !d_out) return MP_ERR_INVALID_ARG;
   if (n >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "MSM size %llu too large", (unsigned long long)n);
   cudaSetDevice(ctx->device);
@@ -134,7 +134,9 @@ static int32_t msm_device_common(mp377_ctx* ctx, const void* d_points, const voi
   const int c = window_bits > 0 ? window_bits : msm_pick_window(n);
   if (c < 2 || c > 16) return ctx->fail(MP_ERR_INVALID_ARG, "window_bits %d out of range [2,16]", c);
   ctx->last_window = c;
-  ctx->last_ec_adds = scheduled_ec_adds(n, c, ncomp);
+  if (w_begin < 0 || (w_count >= 0 && w_begin + w_count > msm_num_windows(c)) || w_count == 0)
+    return ctx->fail(MP_ERR_INVALID_ARG, "window range [%d, +%d) outside [0, %d)", w_begin, w_count, msm_num_windows(c));
+  ctx->last_ec_adds = scheduled_ec_adds(n, c, ncomp) * (uint64_t)(w_count < 0 ? msm_num_windows(c) - w_begin : w_count) / msm_num_windows(c);
   affine* mont = (affine*)ctx->scratch(mp377_ctx::kPointsMont, sizeof(affine) * n * ncomp);
   xyzz* res = (xyzz*)ctx->scratch(mp377_ctx::kMsmOut, sizeof(xyzz) * ncomp);
   int* bad = (int*)ctx->scratch(mp377_ctx::kFlags, 256);
@@ -143,7 +145,7 @@ static int32_t msm_device_common(mp377_ctx* ctx, const void* d_points, const voi
   CK377(points_to_mont((const uint32_t*)d_points, mont, n * ncomp, bad, ctx->stream), "points_to_mont");
   ctx->launches += n ? 1 : 0;
   MsmJob job{0, 0, (uint32_t)n};
-  CK377(msm_run(ctx->ws, (const uint32_t*)d_scalars, n, mont, ncomp, &job, 1, c, res, ctx->stream), "msm_run");
+  CK377(msm_run(ctx->ws, (const uint32_t*)d_scalars, n, mont, ncomp, &job, 1, c, res, ctx->stream, w_begin, w_count), "msm_run");
   ctx->launches += msm_last_launches(ctx->ws);
   CK377(xyzz_to_canonical(res, (uint32_t*)d_out, ncomp, ctx->stream), "xyzz_to_canonical");
   ctx->launches += 1;
@@ -188,6 +190,15 @@ extern "C" int32_t mp377_msm_g1_device(mp377_ctx* ctx, const void* d_bases, cons
 extern "C" int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
                                        int32_t window_bits, void* d_out) {
   return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
+}
+
+// Window-range split of one MSM across GPUs: the partial
+//   sum_{w in [w_begin, w_begin + w_count)} 2^(c (w - w_begin)) * (window sum w),
+// so that  MSM = sum over ranks of 2^(c * w_begin_r) * partial_r  (see mental-poker_b200/dist.py).
+extern "C" int32_t mp377_msm_g1_windows_device(mp377_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                                               int32_t window_bits, int32_t w_begin, int32_t w_count, void* d_out) {
+  if (window_bits < 2 || window_bits > 16) return ctx ? ctx->fail(MP_ERR_INVALID_ARG, "explicit window_bits required") : MP_ERR_INVALID_ARG;
+  return msm_device_common(ctx, d_bases, d_scalars, n, 1, window_bits, d_out, w_begin, w_count);
 }
 
 extern "C" int32_t mp377_profile_enable(mp377_ctx* ctx, int32_t on) {

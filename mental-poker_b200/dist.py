@@ -34,16 +34,16 @@ def fold_scalars(window_bits, num_windows, world):
     return out
 
 
-def window_split_msm(partial_fn, fold_fn, window_bits, num_windows, group=None):
-    """Generic driver.  `partial_fn(w_begin, w_count) -> 64 bytes` computes this rank's partial
-    (canonical affine, all-zero = identity); `fold_fn(points_bytes, scalars_bytes) -> 64 bytes`
-    evaluates a small MSM.  Returns the full MSM result on every rank."""
+def window_split_msm(partial_fn, fold_fn, window_bits, num_windows, group=None, point_bytes=64):
+    """Generic driver.  `partial_fn(w_begin, w_count) -> point_bytes bytes` computes this rank's partial
+    (canonical affine, all-zero = identity); `fold_fn(points_bytes, scalars_bytes)` evaluates a small MSM.
+    Returns the full MSM result on every rank.  point_bytes: 64 (Stark curve) or 96 (BLS12-377 G1)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, e = window_range(num_windows, rank, world)
-    mine = partial_fn(b, e - b) if e > b else bytes(64)
-    assert len(mine) == 64
+    mine = partial_fn(b, e - b) if e > b else bytes(point_bytes)
+    assert len(mine) == point_bytes
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)

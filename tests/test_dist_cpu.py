@@ -33,18 +33,26 @@ def _signed_digits(k, c, W):
     return out
 
 
-def _worker(rank, world, port, c, q):
+def _worker(rank, world, port, c, q, curve="stark"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     import __graft_entry__ as g
     pkg = g.load_package()
-    from oracle.py import stark
-    from _util import chain_points, pb, b32
+    if curve == "stark":
+        from oracle.py import stark
+        from _util import chain_points, pb, b32
+        PB, scalar_bits = 64, 253
+    else:  # second curve: 96-byte points, 253-bit group order (+1 bit for the signed recoding)
+        from oracle.py import bls12_377 as stark
+        from _util_bls12_377 import chain_points, pb, b32
+        stark.point_from_bytes64 = stark.point_from_bytes
+        PB, scalar_bits = 96, 254
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     s0, s1, pts, st = chain_points(24, 5)
     ks = [st.scalar() for _ in range(24)]
-    W = (253 + c - 1) // c
+    ks[0] = stark.N - 1
+    W = (scalar_bits + c - 1) // c
     digs = [_signed_digits(k, c, W) for k in ks]
 
     def partial(w_begin, w_count):  # sum_w 2^(c (w - w_begin)) * sum_i d_{i,w} P_i
@@ -57,23 +65,23 @@ def _worker(rank, world, port, c, q):
 
     def fold(points, scalars):
         n = len(scalars) // 32
-        P = [stark.point_from_bytes64(points[64 * i:64 * i + 64]) for i in range(n)]
+        P = [stark.point_from_bytes64(points[PB * i:PB * i + PB]) for i in range(n)]
         K = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(n)]
         return pb(stark.msm(P, K))
 
-    got = pkg.dist.window_split_msm(partial, fold, c, W)
+    got = pkg.dist.window_split_msm(partial, fold, c, W, point_bytes=PB)
     want = pb(stark.msm(pts, ks))
     q.put((rank, got == want, pkg.dist.shard_range(4096, rank, world)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,c", [(2, 16), (3, 13)])
-def test_window_split_msm_gloo(world, c, pkg):
+@pytest.mark.parametrize("world,c,curve", [(2, 16, "stark"), (3, 13, "stark"), (2, 16, "bls12_377")])
+def test_window_split_msm_gloo(world, c, curve, pkg):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, c, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, c, q, curve)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in range(world))

@@ -158,6 +158,32 @@ def test_pedersen_commit_batch(ctx377, pkg):
         ctx377.pedersen_commit_batch(b32(1) * 151, b32(1), 151)  # longer than the key
 
 
+@pytest.mark.parametrize("c,world", [(8, 3), (13, 2), (16, 8), (16, 5)])
+def test_msm_window_range_split(ctx377, pkg, c, world):
+    """Window-range split (multi-GPU path of SURVEY 8(e)) emulated on one GPU: per-'rank' partials + fold."""
+    import torch
+    n = 500
+    s0, s1, pts, st = chain_points(n, 21)
+    ks = scalars(st, n, "uniform")
+    ks[0], ks[1] = 0, R - 1
+    dev = torch.device("cuda:0")
+    d_pts = torch.frombuffer(bytearray(b"".join(map(pb, pts))), dtype=torch.uint8).to(dev)
+    d_sc = torch.frombuffer(bytearray(b"".join(map(b32, ks))), dtype=torch.uint8).to(dev)
+    d_out = torch.zeros(96, dtype=torch.uint8, device=dev)
+    W = ctx377.msm_num_windows(c)
+    assert W == (254 + c - 1) // c
+    points, scs = b"", b""
+    for r, s in pkg.dist.fold_scalars(c, W, world):
+        b, e = pkg.dist.window_range(W, r, world)
+        ctx377.msm_g1_windows_device(d_pts.data_ptr(), d_sc.data_ptr(), n, d_out.data_ptr(), c, b, e - b)
+        ctx377.sync()
+        points += bytes(d_out.cpu().numpy().tobytes())
+        scs += s
+    got = ctx377.msm_g1(points, scs, 0)
+    e = sum(k * (s0 + i * s1) for i, k in enumerate(ks)) % R
+    assert got == pb(bls.mul(bls.G, e))
+
+
 def test_kernels_were_launched(ctx377):
     msm_case(ctx377, 64, 0)
     assert ctx377.launches > 0
