@@ -262,9 +262,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # keep stdout to the single JSON line: fd 1 is pointed at stderr for the whole run (NCCL prints its
+    # version banner to stdout whatever NCCL_DEBUG_FILE says -- the 2-GPU outputs of earlier builds start
+    # with it) and the line itself goes to a duplicate of the original descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the single JSON line: whatever NCCL_DEBUG level the box sets, its banner /
-        # log goes to stderr instead of stdout
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)
@@ -422,7 +426,8 @@ def main():
             sm, sn = sample_shape(m, n)
             val, desc, legs = cpu_sample(m, n, sm, sn, threads=1)
             line["cpu_baseline"] = dict(value=val, unit=UNIT, cores=1, kind="port", sample=desc)
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out)
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
