@@ -16,9 +16,53 @@ prove->verify == Ok, and a wrong output deck fails with "Hadamard Product (5.1)"
 
 Everything here is plain Python big-int code meant to be obviously correct, not fast.
 """
+import contextlib
+
 from . import stark
+from . import transcript as _transcript
 from .stark import N as Q  # scalar-field modulus
 from .transcript import FiatShamirRng, SHUFFLE_RNG_SEED
+
+POINT_BYTES = 64  # C-ABI affine point of the active curve (x || y)
+
+
+class _Bls12_377Group:
+    """The names this module uses from `stark`, over BLS12-377 G1 (the reference's second instantiation,
+    examples/parameter_selection.rs:25-29): 48-byte coordinates, so the ark `ToBytes` point is
+    x || y || infinity = 97 bytes and the C-ABI point 96 bytes; scalars stay 32 bytes."""
+
+    def __init__(self):
+        from . import bls12_377 as b
+        self.P, self.N, self.INF, self.G = b.P, b.N, None, b.G
+        self.add, self.mul, self.msm, self.neg, self.sub = b.add, b.mul, b.msm, b.neg, b.sub
+        self.point_to_bytes64, self.point_from_bytes64 = b.point_to_bytes, b.point_from_bytes
+        self.fe_to_bytes = b.scalar_to_bytes  # only scalars are written through this name here
+        self._fq = b.fe_to_bytes
+
+    def fe_from_bytes(self, buf):
+        return int.from_bytes(buf, "little")
+
+    def point_to_bytes65(self, pt):
+        if pt is None:
+            return self._fq(0) + self._fq(1) + b"\x01"
+        return self._fq(pt[0]) + self._fq(pt[1]) + b"\x00"
+
+
+@contextlib.contextmanager
+def curve(name):
+    """`with curve("bls12_377"): ...` runs this module's protocol over BLS12-377 G1 instead of the Stark
+    curve (group, scalar field of the challenges, byte widths).  Test infrastructure: not re-entrant."""
+    global stark, Q, POINT_BYTES, CT_ZERO
+    assert name in ("stark", "bls12_377")
+    saved = (stark, Q, POINT_BYTES, _transcript.SCALAR_MODULUS)
+    if name == "bls12_377":
+        stark = _Bls12_377Group()
+        Q, POINT_BYTES = stark.N, 96
+        _transcript.SCALAR_MODULUS = stark.N
+    try:
+        yield stark
+    finally:
+        stark, Q, POINT_BYTES, _transcript.SCALAR_MODULUS = saved
 
 # verification status codes (shared with include/mpshuffle.h)
 OK = 0
@@ -429,7 +473,7 @@ def _f32(v):
 
 
 def proof_len(m, n):
-    return (11 * m + 8) * 64 + (5 * n + 9) * 32
+    return (11 * m + 8) * POINT_BYTES + (5 * n + 9) * 32
 
 
 def proof_to_bytes(pf):
@@ -454,8 +498,8 @@ def proof_from_bytes(buf, m, n):
     pos = [0]
 
     def pt():
-        p = stark.point_from_bytes64(buf[pos[0]:pos[0] + 64])
-        pos[0] += 64
+        p = stark.point_from_bytes64(buf[pos[0]:pos[0] + POINT_BYTES])
+        pos[0] += POINT_BYTES
         return p
 
     def fr():

@@ -65,17 +65,25 @@ class ChaCha20Rng:
         return lo | (hi << 32)
 
 
+# scalar field the challenges are drawn from: the Stark curve's by default; `bayer_groth.curve(...)`
+# switches it together with the group (second instantiation: ark_bls12_377::Fr, 253 bits)
+SCALAR_MODULUS = stark.N
+
+
 def fr_rand(rng):
     """ark-ff 0.3 `Fp256::rand` (SURVEY.md A1): draw 4 x u64 (limb 0 first) as the raw
-    Montgomery representation, clear the top REPR_SHAVE_BITS = 4 bits, accept iff < modulus.
+    Montgomery representation, clear the top REPR_SHAVE_BITS = 256 - bitlen(modulus) bits
+    (4 for the Stark scalar field, 3 for BLS12-377's), accept iff < modulus.
     Returns the canonical value raw * R^-1 mod n."""
-    rinv = pow(stark.R256, -1, stark.N)
+    n = SCALAR_MODULUS
+    rinv = pow(1 << 256, -1, n)
+    shave = 256 - n.bit_length()
     while True:
         limbs = [rng.next_u64() for _ in range(4)]
-        limbs[3] &= 0xFFFFFFFFFFFFFFFF >> 4
+        limbs[3] &= 0xFFFFFFFFFFFFFFFF >> shave
         raw = limbs[0] | (limbs[1] << 64) | (limbs[2] << 128) | (limbs[3] << 192)
-        if raw < stark.N:
-            return raw * rinv % stark.N
+        if raw < n:
+            return raw * rinv % n
 
 
 class FiatShamirRng:

@@ -52,3 +52,21 @@ def scalars(st, n, kind="uniform"):
     if kind == "same":
         return [st.scalar()] * n
     raise ValueError(kind)
+
+
+def instance(m, n, seed):
+    """A seeded shuffle instance over BLS12-377 G1 (same recipe as _util.instance); call it inside
+    `with bayer_groth.curve("bls12_377")`."""
+    from oracle.py import bayer_groth as bg
+    N = m * n
+    s0, s1, pts, st = chain_points(n + 3 + 2 * N, seed)
+    pp = bg.Params(m, n, bls.G, pts[:n], pts[n], pts[n + 1])
+    pk = pts[n + 2]
+    deck = [(pts[n + 3 + 2 * i], pts[n + 4 + 2 * i]) for i in range(N)]
+    perm = list(range(N))
+    for i in range(N - 1, 0, -1):  # Fisher-Yates from the same stream
+        j = st.below(i + 1)
+        perm[i], perm[j] = perm[j], perm[i]
+    rho = [st.scalar() for _ in range(N)]
+    rnd = [st.scalar() for _ in range(bg.prover_randomness_len(m, n))]
+    return pp, pk, deck, perm, rho, rnd

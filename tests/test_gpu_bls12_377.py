@@ -184,6 +184,63 @@ def test_msm_window_range_split(ctx377, pkg, c, world):
     assert got == pb(bls.mul(bls.G, e))
 
 
+def test_shuffle_verifier_group_work_on_gpu(ctx377, monkeypatch):
+    """The NEXT row in miniature: `verify_shuffle` over BLS12-377 with the oracle's host logic (transcript, scalar
+    algebra, check order) and every group computation of the verifier -- Pedersen commitments, the ciphertext
+    MSMs, the point linear combinations -- executed by the GPU group layer through the C ABI.  Valid proofs must
+    verify, tampered ones must fail in the same sub-argument as with the pure big-int oracle."""
+    import copy
+    from oracle.py import bayer_groth as bg
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_shuffle_vectors.json")))
+    pt = bls.point_from_bytes
+    for fx in gold["shuffle"]:
+        m, n = fx["m"], fx["n"]
+        N = m * n
+        raw = {k: bytes.fromhex(fx[k]) for k in ("enc_g", "ck_g", "ck_h", "ghat", "pk", "deck", "deck2", "proof")}
+        with bg.curve("bls12_377") as grp:
+            pp = bg.Params(m, n, pt(raw["enc_g"]), [pt(raw["ck_g"][96 * i:96 * i + 96]) for i in range(n)],
+                           pt(raw["ck_h"]), pt(raw["ghat"]))
+            pk = pt(raw["pk"])
+            deck = [(pt(raw["deck"][192 * i:192 * i + 96]), pt(raw["deck"][192 * i + 96:192 * i + 192])) for i in range(N)]
+            deck2 = [(pt(raw["deck2"][192 * i:192 * i + 96]), pt(raw["deck2"][192 * i + 96:192 * i + 192])) for i in range(N)]
+            proof = bg.proof_from_bytes(raw["proof"], m, n)
+            # what the pure oracle says, before anything is patched
+            bad = copy.deepcopy(proof)
+            bad["multiexp"]["tau"] = (bad["multiexp"]["tau"] + 1) % R
+            bad2 = copy.deepcopy(proof)
+            bad2["product"]["svp"]["r"] = (bad2["product"]["svp"]["r"] + 1) % R
+            wrong_deck = deck2[1:] + deck2[:1]
+            want = [bg.shuffle_verify(pp, pk, deck, deck2, proof), bg.shuffle_verify(pp, pk, deck, deck2, bad),
+                    bg.shuffle_verify(pp, pk, deck, deck2, bad2), bg.shuffle_verify(pp, pk, deck, wrong_deck, proof)]
+            assert want[0] == bg.OK and want[1] == bg.ERR_MULTIEXP and want[2] == bg.ERR_SVP and want[3] != bg.OK
+            # route the group work through the GPU
+            calls = {"msm": 0, "ct_msm": 0, "commit": 0}
+            ctx377.set_commit_key(raw["ck_h"] + raw["ck_g"])
+
+            def gpu_msm(points, scalars):
+                calls["msm"] += 1
+                return pt(ctx377.msm_g1(b"".join(map(pb, points)), b"".join(b32(k % R) for k in scalars)))
+
+            def gpu_ct_msm(cts, scalars):
+                calls["ct_msm"] += 1
+                cts, scalars = list(cts), list(scalars)
+                out = ctx377.ct_msm(b"".join(pb(c[0]) + pb(c[1]) for c in cts), b"".join(b32(k % R) for k in scalars))
+                return (pt(out[:96]), pt(out[96:]))
+
+            def gpu_commit(pp_, values, r):
+                calls["commit"] += 1
+                return pt(ctx377.pedersen_commit_batch(b"".join(b32(v % R) for v in values), b32(r % R), len(values)))
+
+            monkeypatch.setattr(grp, "msm", gpu_msm)
+            monkeypatch.setattr(bg, "ct_msm", gpu_ct_msm)
+            monkeypatch.setattr(bg, "commit", gpu_commit)
+            got = [bg.shuffle_verify(pp, pk, deck, deck2, proof), bg.shuffle_verify(pp, pk, deck, deck2, bad),
+                   bg.shuffle_verify(pp, pk, deck, deck2, bad2), bg.shuffle_verify(pp, pk, deck, wrong_deck, proof)]
+            monkeypatch.undo()
+        assert got == want, (m, n, got, want)
+        assert calls["ct_msm"] >= 2 and calls["commit"] >= 3 and calls["msm"] >= 1, calls
+
+
 def test_kernels_were_launched(ctx377):
     msm_case(ctx377, 64, 0)
     assert ctx377.launches > 0

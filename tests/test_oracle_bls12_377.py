@@ -90,3 +90,25 @@ def test_c_restatement_matches_python_oracle():
     # identity points and cancelling pairs
     p = pts[0]
     assert co.msm(pb(p) + pb(bls.neg(p)) + pb(None), b32(7) + b32(7) + b32(9), 1, 0) == bytes(96)
+
+
+def test_shuffle_protocol_over_bls12_377():
+    """The protocol oracle instantiated over the second curve (`bayer_groth.curve`): the committed fixture
+    re-derives byte for byte, verifies, and tampering is caught; the Stark instantiation is untouched afterwards."""
+    import copy
+    from oracle.py import bayer_groth as bg, stark
+    from _util_bls12_377 import instance
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_shuffle_vectors.json")))
+    fx = gold["shuffle"][0]
+    with bg.curve("bls12_377"):
+        pp, pk, deck, perm, rho, rnd = instance(fx["m"], fx["n"], fx["seed"])
+        deck2, proof = bg.shuffle_and_remask(pp, pk, deck, rho, perm, rnd)
+        buf = bg.proof_to_bytes(proof)
+        assert buf.hex() == fx["proof"] and len(buf) == bg.proof_len(fx["m"], fx["n"]) == (11 * fx["m"] + 8) * 96 + (5 * fx["n"] + 9) * 32
+        assert b"".join(pb(c[0]) + pb(c[1]) for c in deck2).hex() == fx["deck2"]
+        assert bg.shuffle_verify(pp, pk, deck, deck2, bg.proof_from_bytes(buf, fx["m"], fx["n"])) == bg.OK
+        bad = copy.deepcopy(proof)
+        bad["product"]["hadamard"]["zero"]["t"] = (bad["product"]["hadamard"]["zero"]["t"] + 1) % bls.N
+        assert bg.shuffle_verify(pp, pk, deck, deck2, bad) == bg.ERR_ZERO
+        assert bg.shuffle_verify(pp, pk, deck, deck2[1:] + deck2[:1], proof) != bg.OK
+    assert bg.stark is stark and bg.Q == stark.N and bg.POINT_BYTES == 64
