@@ -55,6 +55,15 @@ int32_t mp377_msm_g1_device(mp377_ctx* ctx, const void* d_bases, const void* d_s
 int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_scalars, uint64_t n,
                             int32_t window_bits, void* d_out);
 
+/* Batch of MSMs over one point array and one scalar array (MultiExponentiationArgument's diagonal products:
+ * m(m+1) inner products <row of n ciphertexts, row of n scalars>, one launch sequence for all of them):
+ *   out[j] = sum_{t < len_j} scalars[scalar_off_j + t] * points[point_off_j + t]       (per component)
+ * jobs = njobs x (scalar_off, point_off, len) as uint32; ncomp = 1 (96-byte points) or 2 (192-byte ciphertexts);
+ * out = njobs * ncomp * 96 bytes. */
+int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_t n_points, int32_t ncomp,
+                       const uint8_t* scalars, uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs,
+                       int32_t window_bits, uint8_t* out);
+
 /* Window-range split of ONE MSM across GPUs: rank r computes the windows
  * [w_begin, w_begin + w_count) of the mp377_msm_num_windows(window_bits) windows end to end and returns
  *   P_r = sum_w 2^(c (w - w_begin)) * (window sum w);   MSM = sum_r 2^(c * w_begin_r) * P_r

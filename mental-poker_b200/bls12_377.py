@@ -26,6 +26,7 @@ SIGNATURES = {
     "mp377_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
     "mp377_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp377_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp377_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, ctypes.POINTER(ctypes.c_uint32), _u64, _i32, _cp]),
     "mp377_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
     "mp377_set_commit_key": (_i32, [_vp, _cp, _u64]),
     "mp377_pedersen_commit_batch": (_i32, [_vp, _cp, _cp, _u64, _u64, _cp]),
@@ -110,6 +111,14 @@ class Context:
 
     def ct_msm_device(self, d_deck, d_scalars, n, d_out, window_bits=0):
         _check(self.h, lib.mp377_ct_msm_device(self.h, d_deck, d_scalars, n, window_bits, d_out))
+
+    def msm_jobs(self, points: bytes, scalars: bytes, jobs, ncomp=1, window_bits=0) -> bytes:
+        """jobs: list of (scalar_off, point_off, len); returns len(jobs) * ncomp points."""
+        n_points, n_scalars = len(points) // (POINT_BYTES * ncomp), len(scalars) // SCALAR_BYTES
+        flat = (ctypes.c_uint32 * (3 * len(jobs)))(*[v for j in jobs for v in j])
+        out = ctypes.create_string_buffer(max(1, POINT_BYTES * ncomp * len(jobs)))
+        _check(self.h, lib.mp377_msm_jobs(self.h, points, n_points, ncomp, scalars, n_scalars, flat, len(jobs), window_bits, out))
+        return out.raw[:POINT_BYTES * ncomp * len(jobs)]
 
     def msm_g1_windows_device(self, d_bases, d_scalars, n, d_out, window_bits, w_begin, w_count):
         _check(self.h, lib.mp377_msm_g1_windows_device(self.h, d_bases, d_scalars, n, window_bits, w_begin, w_count, d_out))

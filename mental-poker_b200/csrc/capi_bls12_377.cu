@@ -192,6 +192,59 @@ extern "C" int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const
   return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
 }
 
+// Batch of MSMs over ONE point array and ONE scalar array (kernel family K2 of SURVEY.md 2b, the
+// `mp_msm_batch_shared_bases` of section 8(b)): job j = sum_t scalars[scalar_off_j + t] * points[point_off_j + t],
+// t < len_j.  The multi-exponentiation argument's diagonal products are m(m+1) such jobs over the rows of the
+// shuffled deck (reference call site mod.rs:409-415 -> MultiExponentiationArgument); one launch sequence
+// evaluates all of them.  jobs: njobs x (scalar_off, point_off, len) as uint32.  out: njobs * ncomp points.
+extern "C" int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_t n_points, int32_t ncomp,
+                                  const uint8_t* scalars, uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs,
+                                  int32_t window_bits, uint8_t* out) {
+  if (!ctx || !jobs || !out || (!points && n_points) || (!scalars && n_scalars)) return MP_ERR_INVALID_ARG;
+  if (ncomp != 1 && ncomp != 2) return ctx->fail(MP_ERR_INVALID_ARG, "ncomp must be 1 (G1) or 2 (ciphertexts)");
+  if (njobs == 0) return MP_OK;
+  if (njobs >= (1u << 24) || n_points >= (1ull << 31) || n_scalars >= (1ull << 31))
+    return ctx->fail(MP_ERR_INVALID_ARG, "batch too large");
+  std::vector<MsmJob> h_jobs(njobs);
+  uint64_t total = 0;
+  for (uint64_t j = 0; j < njobs; j++) {
+    h_jobs[j] = MsmJob{jobs[3 * j], jobs[3 * j + 1], jobs[3 * j + 2]};
+    if ((uint64_t)h_jobs[j].scalar_off + h_jobs[j].len > n_scalars || (uint64_t)h_jobs[j].point_off + h_jobs[j].len > n_points)
+      return ctx->fail(MP_ERR_INVALID_ARG, "job %llu reaches outside the arrays", (unsigned long long)j);
+    total += h_jobs[j].len;
+  }
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int c = window_bits > 0 ? window_bits : msm_pick_window(total / njobs, njobs);
+  if (c < 2 || c > 16) return ctx->fail(MP_ERR_INVALID_ARG, "window_bits %d out of range [2,16]", c);
+  ctx->last_window = c;
+  const size_t pbytes = (size_t)n_points * kPt * ncomp, sbytes = (size_t)n_scalars * 32;
+  uint8_t* d_in = (uint8_t*)ctx->scratch(mp377_ctx::kStageIn, pbytes + sbytes + 256);
+  affine* mont = (affine*)ctx->scratch(mp377_ctx::kPointsMont, sizeof(affine) * n_points * ncomp);
+  xyzz* res = (xyzz*)ctx->scratch(mp377_ctx::kMsmOut, sizeof(xyzz) * njobs * ncomp);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(mp377_ctx::kStageOut, kPt * njobs * ncomp);
+  int* bad = (int*)ctx->scratch(mp377_ctx::kFlags, 256);
+  if (!d_in || !mont || !res || !d_out || !bad) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  if (pbytes) CK377(cudaMemcpyAsync(d_in, points, pbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D points");
+  if (sbytes) CK377(cudaMemcpyAsync(d_in + pbytes, scalars, sbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D scalars");
+  CK377(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream), "memset");
+  CK377(points_to_mont((const uint32_t*)d_in, mont, n_points * ncomp, bad, ctx->stream), "points_to_mont");
+  ctx->launches += n_points ? 1 : 0;
+  CK377(msm_run(ctx->ws, (const uint32_t*)(d_in + pbytes), n_scalars, mont, ncomp, h_jobs.data(), (int)njobs, c, res, ctx->stream),
+        "msm_run (jobs)");
+  ctx->launches += msm_last_launches(ctx->ws);
+  CK377(xyzz_to_canonical(res, (uint32_t*)d_out, njobs * ncomp, ctx->stream), "xyzz_to_canonical");
+  ctx->launches += 1;
+  int h_bad = 0;
+  CK377(cudaMemcpyAsync(out, d_out, kPt * njobs * ncomp, cudaMemcpyDeviceToHost, ctx->stream), "D2H results");
+  CK377(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H flag");
+  CK377(cudaStreamSynchronize(ctx->stream), "MSM jobs");
+  if (h_bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of BLS12-377 G1");
+  ctx->last_ec_adds = 0;
+  for (auto& j : h_jobs) ctx->last_ec_adds += scheduled_ec_adds(j.len, c, ncomp);
+  return MP_OK;
+}
+
 // Window-range split of one MSM across GPUs: the partial
 //   sum_{w in [w_begin, w_begin + w_count)} 2^(c (w - w_begin)) * (window sum w),
 // so that  MSM = sum over ranks of 2^(c * w_begin_r) * partial_r  (see mental-poker_b200/dist.py).

@@ -184,6 +184,31 @@ def test_msm_window_range_split(ctx377, pkg, c, world):
     assert got == pb(bls.mul(bls.G, e))
 
 
+def test_msm_jobs_diagonal_products(ctx377, pkg):
+    """Batched MSM jobs over shared arrays, in the shape of the multi-exponentiation argument's diagonal products:
+    every (deck row i, scalar row j) pair of an (m = 4, n = 25) instance -- the reference benchmark's 300-card deck is
+    (12, 25) -- as one call, 2 components; plus ragged / empty / overlapping jobs."""
+    m, n = 4, 25
+    s0, s1, pts, st = chain_points(2 * m * n, 17)
+    logs = [(s0 + i * s1) % R for i in range(2 * m * n)]
+    ks = [st.scalar() for _ in range((m + 1) * n)]
+    deck = b"".join(map(pb, pts))
+    jobs = [(j * n, i * n, n) for i in range(m) for j in range(m + 1)]
+    out = ctx377.msm_jobs(deck, b"".join(map(b32, ks)), jobs, ncomp=2)
+    for q, (so, po, ln) in enumerate(jobs):
+        for comp in range(2):
+            e = sum(ks[so + t] * logs[2 * (po + t) + comp] for t in range(ln)) % R
+            assert out[192 * q + 96 * comp:192 * q + 96 * comp + 96] == pb(bls.mul(bls.G, e)), (q, comp)
+    assert ctx377.launches > 0
+    jobs = [(0, 0, 1), (3, 7, 0), (5, 2, 40), (0, 0, 100), (10, 150, 50)]
+    out = ctx377.msm_jobs(deck, b"".join(map(b32, ks)), jobs, ncomp=1, window_bits=7)
+    for q, (so, po, ln) in enumerate(jobs):
+        e = sum(ks[so + t] * logs[po + t] for t in range(ln)) % R
+        assert out[96 * q:96 * q + 96] == pb(bls.mul(bls.G, e)), q
+    with pytest.raises(pkg.MpError):
+        ctx377.msm_jobs(deck, b"".join(map(b32, ks)), [(0, 190, 20)], ncomp=1)  # reaches past the points
+
+
 def test_shuffle_verifier_group_work_on_gpu(ctx377, monkeypatch):
     """The NEXT row in miniature: `verify_shuffle` over BLS12-377 with the oracle's host logic (transcript, scalar
     algebra, check order) and every group computation of the verifier -- Pedersen commitments, the ciphertext
