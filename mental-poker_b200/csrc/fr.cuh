@@ -1,4 +1,5 @@
-// Scalar field F_n of the Stark curve (n = group order, 252 bits), 8 x 32-bit limbs,
+// Scalar field F_n of the curve fq.cuh selects (Stark: n = group order, 252 bits; under MP_CURVE_BLS12_377
+// the 253-bit ark_bls12_377::Fr -- same limb count, only the constants differ), 8 x 32-bit limbs,
 // Montgomery form with R = 2^256, always fully reduced (< n).  This is the field the
 // reference's protocol scalars live in (`C::ScalarField`, ark-ff 0.3 `Fp256`; reference
 // barnett-smart-card-protocol/src/lib.rs:43, Cargo.toml:12).  n has no
@@ -21,7 +22,25 @@ struct fr {
   uint32_t v[8];
 };
 
+#ifdef MP_CURVE_BLS12_377
+// r = 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001 (253 bits), ark_bls12_377::Fr
+#define MP_FR_NINV 0xffffffffu
+static constexpr int kFrShaveBits = 3;  // ark-ff REPR_SHAVE_BITS = 256 - 253
+MP_HD uint32_t fr_modulus_limb(int i) {
+  switch (i) {
+    case 0: return 0x00000001u;
+    case 1: return 0x0a118000u;
+    case 2: return 0xd0000001u;
+    case 3: return 0x59aa76feu;
+    case 4: return 0x5c37b001u;
+    case 5: return 0x60b44d1eu;
+    case 6: return 0x9a2ca556u;
+    default: return 0x12ab655eu;
+  }
+}
+#else
 #define MP_FR_NINV 0xe8bde631u
+static constexpr int kFrShaveBits = 4;  // ark-ff REPR_SHAVE_BITS = 256 - 252
 
 MP_HD uint32_t fr_modulus_limb(int i) {
   switch (i) {
@@ -35,6 +54,7 @@ MP_HD uint32_t fr_modulus_limb(int i) {
     default: return 0x08000000u;
   }
 }
+#endif
 
 MP_HD fr fr_zero() {
   fr r;
@@ -42,6 +62,20 @@ MP_HD fr fr_zero() {
   for (int i = 0; i < 8; i++) r.v[i] = 0;
   return r;
 }
+#ifdef MP_CURVE_BLS12_377
+MP_HD fr fr_one() {  // R mod r
+  fr r;
+  r.v[0] = 0xfffffff3u; r.v[1] = 0x7d1c7fffu; r.v[2] = 0x6ffffff2u; r.v[3] = 0x7257f50fu;
+  r.v[4] = 0x512c0feeu; r.v[5] = 0x16d81575u; r.v[6] = 0x2bbb9a9du; r.v[7] = 0x0d4bda32u;
+  return r;
+}
+MP_HD fr fr_r2() {  // R^2 mod r
+  fr r;
+  r.v[0] = 0xb861857bu; r.v[1] = 0x25d577bau; r.v[2] = 0x8860591fu; r.v[3] = 0xcc2c27b5u;
+  r.v[4] = 0xe5dc8593u; r.v[5] = 0xa7cc008fu; r.v[6] = 0xeff1c939u; r.v[7] = 0x011fdae7u;
+  return r;
+}
+#else
 MP_HD fr fr_one() {  // R mod n
   fr r;
   r.v[0] = 0xf4fca74fu; r.v[1] = 0x51925a0bu; r.v[2] = 0x6df16beeu; r.v[3] = 0xc75ec4b4u;
@@ -54,6 +88,7 @@ MP_HD fr fr_r2() {  // R^2 mod n
   r.v[4] = 0xf78bbabbu; r.v[5] = 0xbaf0ab4cu; r.v[6] = 0x2333766eu; r.v[7] = 0x07d9e57cu;
   return r;
 }
+#endif
 
 MP_HD bool fr_is_zero(const fr& a) {
   uint32_t o = 0;
@@ -95,7 +130,7 @@ MP_HD fr fr_add(const fr& a, const fr& b) {
     s.v[i] = (uint32_t)c;
     c >>= 32;
   }
-  return fr_cond_sub(s, (uint32_t)c);  // n < 2^252: the sum never carries, c == 0
+  return fr_cond_sub(s, (uint32_t)c);  // n < 2^253: the sum never carries, c == 0
 }
 MP_HD fr fr_sub(const fr& a, const fr& b) {
   fr d;

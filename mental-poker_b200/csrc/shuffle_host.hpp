@@ -21,14 +21,20 @@
 
 namespace mp {
 
+// Byte widths of the curve fq.cuh selects: a C-ABI point is x || y (64 bytes on the Stark curve, 96 on
+// BLS12-377 G1), a ciphertext two points; scalars are 32 bytes on both.  Everything below is written
+// against these, so this header compiles for either instantiation (tests/test_host_verify_plan.py runs both).
+static constexpr size_t kPointBytes = 8 * (size_t)kFqLimbs;
+static constexpr size_t kCtBytes = 2 * kPointBytes;
+
 // DLCards `Parameters` as the host sees them (reference mod.rs:37-61)
 struct ShuffleParamsHost {
   int m = 0, n = 0;
-  std::vector<uint8_t> ck64;  // (n+1) * 64 canonical: h, g_1 .. g_n   (MSM order of a commitment)
-  uint8_t enc_g[64], ghat[64], gsum[64];  // gsum = g_1 + .. + g_n  (com(c,..,c; 0) = c * gsum)
+  std::vector<uint8_t> ck64;  // (n+1) points canonical: h, g_1 .. g_n   (MSM order of a commitment)
+  uint8_t enc_g[kPointBytes], ghat[kPointBytes], gsum[kPointBytes];  // gsum = g_1 + .. + g_n  (com(c,..,c; 0) = c * gsum)
 };
 
-inline uint64_t shuffle_proof_len(int32_t m, int32_t n) { return (uint64_t)(11 * m + 8) * 64 + (uint64_t)(5 * n + 9) * 32; }
+inline uint64_t shuffle_proof_len(int32_t m, int32_t n) { return (uint64_t)(11 * m + 8) * kPointBytes + (uint64_t)(5 * n + 9) * 32; }
 inline uint64_t shuffle_randomness_len(int32_t m, int32_t n) { return (uint64_t)11 * m + (uint64_t)5 * n; }
 
 // ------------------------------------------------------------------------------------------
@@ -68,13 +74,13 @@ inline bool all_zero(const uint8_t* p, size_t n) {
 
 // A batch of small G1 MSM jobs assembled on the host: job = list of (point, scalar) terms.
 struct TermList {
-  std::vector<uint8_t> pts;    // 64 B canonical per term
+  std::vector<uint8_t> pts;    // one canonical point (kPointBytes) per term
   std::vector<uint32_t> scal;  // 8 words canonical per term
   std::vector<MsmJob> jobs;
   uint32_t start = 0;
   uint32_t count() const { return (uint32_t)(scal.size() / 8); }
   void term(const uint8_t* p64, const fr& s) {
-    pts.insert(pts.end(), p64, p64 + 64);
+    pts.insert(pts.end(), p64, p64 + kPointBytes);
     uint32_t w[8];
     fr_to_canonical(s, w);
     scal.insert(scal.end(), w, w + 8);
@@ -91,7 +97,7 @@ struct TermList {
 struct Layout {
   size_t cA, cB, cb, hB, zpts, za, zb, zr, zs, zt, svpts, sva, svb, svr, svs, mepts, meE, mea, mer, meb, mes, metau, end;
   Layout(int m, int n) {
-    const size_t P = 64, F = 32;
+    const size_t P = kPointBytes, F = 32;
     cA = 0; cB = cA + m * P; cb = cB + m * P; hB = cb + P; zpts = hB + m * P;
     za = zpts + (2 * (size_t)m + 3) * P; zb = za + n * F; zr = zb + n * F; zs = zr + F; zt = zs + F;
     svpts = zt + F; sva = svpts + 3 * P; svb = sva + n * F; svr = svb + n * F; svs = svr + F;
@@ -109,7 +115,7 @@ inline void absorb_statement_head(Transcript& fs, const ShuffleParamsHost* S, co
   fs.feed_label("shuffle_argument");
   fs.feed_points64(S->enc_g, 1);
   fs.feed_points64(pk, 1);
-  fs.feed_points64(S->ck64.data() + 64, (size_t)S->n);
+  fs.feed_points64(S->ck64.data() + kPointBytes, (size_t)S->n);
   fs.feed_points64(S->ck64.data(), 1);
   fs.feed_points64(S->ghat, 1);
   fs.feed_points64(deck, 2 * N);
@@ -172,8 +178,8 @@ inline void append_g1_checks(TermList& tl, const ShuffleParamsHost* S, const uin
                              const Challenges& ch, HostChecks* hc) {
   const int m = S->m, n = S->n;
   const uint8_t* ck_h = S->ck64.data();
-  auto ck_g = [&](int j) { return S->ck64.data() + 64 * (size_t)(j + 1); };  // g_{j+1}, j = 0..n-1
-  auto P = [&](size_t off, size_t i) { return proof + off + 64 * i; };
+  auto ck_g = [&](int j) { return S->ck64.data() + kPointBytes * (size_t)(j + 1); };  // g_{j+1}, j = 0..n-1
+  auto P = [&](size_t off, size_t i) { return proof + off + kPointBytes * i; };
   const fr &y = ch.y, &z = ch.z, &xh = ch.xh, &yh = ch.yh, &xs = ch.xs;
   const std::vector<fr> xzp = h_powers(ch.xz, 2 * m + 1);
   const std::vector<fr> xhp = h_powers(xh, m);
@@ -247,12 +253,12 @@ inline void append_g1_checks(TermList& tl, const ShuffleParamsHost* S, const uin
   tl.term(ck_h, fr_neg(me_s));
   tl.term(ck_g(0), fr_neg(me_b));
   tl.close_job();
-  hc->hadamard_bytes_ok = memcmp(P(L.hB, m - 1), P(L.cb, 0), 64) == 0;
-  hc->zero_bytes_ok = all_zero(P(L.zpts, 2 + m + 1), 64);
+  hc->hadamard_bytes_ok = memcmp(P(L.hB, m - 1), P(L.cb, 0), kPointBytes) == 0;
+  hc->zero_bytes_ok = all_zero(P(L.zpts, 2 + m + 1), kPointBytes);
   hc->svp_first_ok = fr_eq(sv_b[0], sv_a[0]);
   hc->svp_last = sv_b[n - 1];
   hc->xs = xs;
-  hc->multiexp_bytes_ok = all_zero(P(L.mepts, 1 + m), 64);
+  hc->multiexp_bytes_ok = all_zero(P(L.mepts, 1 + m), kPointBytes);
 }
 
 // The two ciphertext equations of the verifier for ONE proof, with host-computed scalars (the
@@ -260,7 +266,7 @@ inline void append_g1_checks(TermList& tl, const ShuffleParamsHost* S, const uin
 //   eq 0:  sum_i x^i C_i  +  (-1) E_m                                              == O   (Chat == E_m)
 //   eq 1:  sum_ij -(xm^{m-i} a_j) C'_ij  +  sum_k xm^k E_k - tau (g, pk) - b (O, ghat) == O
 // sx, s2: N canonical scalars for deck / shuffled deck; ss: 2m + 3 scalars for the small
-// ciphertext points written to small_pts (128 B each): E_m | E_0..E_{2m-1} | (g, pk) | (O, ghat).
+// ciphertext points written to small_pts (kCtBytes each): E_m | E_0..E_{2m-1} | (g, pk) | (O, ghat).
 // Also returns bstar = prod_{i=1..N} (y i + x^i - z), the product-argument statement.
 inline void build_ct_plan(const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* proof, const Layout& L,
                           const Challenges& ch, uint32_t* sx, uint32_t* s2, uint32_t* ss, uint8_t* small_pts, fr* bstar) {
@@ -284,13 +290,13 @@ inline void build_ct_plan(const ShuffleParamsHost* S, const uint8_t* pk, const u
   for (int k = 0; k < 2 * m; k++) fr_to_canonical(xmp[k], ss + 8 * (size_t)(1 + k));
   fr_to_canonical(fr_neg(h_fr(proof + L.metau)), ss + 8 * (size_t)(1 + 2 * m));
   fr_to_canonical(fr_neg(h_fr(proof + L.meb)), ss + 8 * (size_t)(2 + 2 * m));
-  memcpy(small_pts, proof + L.meE + 128 * (size_t)m, 128);
-  memcpy(small_pts + 128, proof + L.meE, 2 * (size_t)m * 128);
-  uint8_t* t = small_pts + 128 * (size_t)(1 + 2 * m);
-  memcpy(t, S->enc_g, 64);
-  memcpy(t + 64, pk, 64);
-  memset(t + 128, 0, 64);
-  memcpy(t + 192, S->ghat, 64);
+  memcpy(small_pts, proof + L.meE + kCtBytes * (size_t)m, kCtBytes);
+  memcpy(small_pts + kCtBytes, proof + L.meE, 2 * (size_t)m * kCtBytes);
+  uint8_t* t = small_pts + kCtBytes * (size_t)(1 + 2 * m);
+  memcpy(t, S->enc_g, kPointBytes);
+  memcpy(t + kPointBytes, pk, kPointBytes);
+  memset(t + 2 * kPointBytes, 0, kPointBytes);
+  memcpy(t + 3 * kPointBytes, S->ghat, kPointBytes);
 }
 
 // Verdict in the order the reference reaches the checks (product argument first: Hadamard ->

@@ -329,28 +329,31 @@ class Transcript {
   void begin() { pending_.reset(); }
   void feed(const void* data, size_t len) { pending_.update(data, len); }
   void feed_label(const char* s) { pending_.update(s, strlen(s)); }
-  // 64-byte C-ABI points (all-zero = identity) -> the 65-byte ark-ec encoding, serialized in
-  // blocks of 64 points so the hash sees few, large updates
+  // C-ABI points (x || y, kPointBytes = 64 on the Stark curve / 96 on BLS12-377; all-zero = identity) -> the
+  // ark-ec `ToBytes` encoding x || y || infinity flag, serialized in blocks of 64 points so the hash sees
+  // few, large updates.  (The name keeps its Stark-curve origin.)
   void feed_points64(const uint8_t* pts, size_t count) {
-    uint8_t buf[64 * 65];
+    constexpr size_t PB = 8 * kFqLimbs, FB = PB / 2;
+    uint8_t buf[64 * (PB + 1)];
     while (count > 0) {
       size_t take = count < 64 ? count : 64;
       uint8_t* b = buf;
-      for (size_t i = 0; i < take; i++, b += 65) {
-        const uint8_t* p = pts + 64 * i;
-        uint64_t w[8];
-        memcpy(w, p, 64);
-        if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
-          memset(b, 0, 65);  // identity = (0, 1, infinity)
-          b[32] = 1;
-          b[64] = 1;
+      for (size_t i = 0; i < take; i++, b += PB + 1) {
+        const uint8_t* p = pts + PB * i;
+        uint64_t w[PB / 8], any = 0;
+        memcpy(w, p, PB);
+        for (size_t k = 0; k < PB / 8; k++) any |= w[k];
+        if (any == 0) {
+          memset(b, 0, PB + 1);  // identity = (0, 1, infinity)
+          b[FB] = 1;
+          b[PB] = 1;
         } else {
-          memcpy(b, p, 64);
-          b[64] = 0;
+          memcpy(b, p, PB);
+          b[PB] = 0;
         }
       }
-      pending_.update(buf, take * 65);
-      pts += 64 * take;
+      pending_.update(buf, take * (PB + 1));
+      pts += PB * take;
       count -= take;
     }
   }
@@ -363,7 +366,7 @@ class Transcript {
     for (;;) {
       uint64_t l[4];
       for (int i = 0; i < 4; i++) l[i] = rng_.next_u64();
-      l[3] &= 0xFFFFFFFFFFFFFFFFull >> 4;
+      l[3] &= 0xFFFFFFFFFFFFFFFFull >> kFrShaveBits;
       fr c;
       for (int i = 0; i < 4; i++) {
         c.v[2 * i] = (uint32_t)l[i];

@@ -59,3 +59,54 @@ void h_dbl_affine(const uint32_t* p, uint32_t* out) {
   affine_to_canonical(xyzz_to_affine(xyzz_dbl_affine(affine_from_canonical(p))), out);
 }
 }
+
+// ---- host-only verifier plan (csrc/shuffle_host.hpp) over this curve: 96-byte points, ark_bls12_377::Fr
+// challenges (3 shaved bits), 97-byte points in the transcript.  Same wrapper as tests/host/host_shim.cpp.
+#include "../../mental-poker_b200/csrc/shuffle_host.hpp"
+extern "C" {
+int h_point_bytes() { return (int)kPointBytes; }
+void h_fs_challenges(const uint8_t* data, uint64_t len, int count, uint8_t* out) {
+  Transcript fs;
+  if (len) { fs.begin(); fs.feed(data, len / 2); fs.feed(data + len / 2, len - len / 2); fs.end(); }
+  for (int i = 0; i < count; i++) { fr c = fs.challenge(); uint32_t w[8]; fr_to_canonical(c, w); memcpy(out + 32 * i, w, 32); }
+}
+void h_fr_mul_canonical(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  fr x = fr_from_canonical(a), y = fr_from_canonical(b);
+  fr_to_canonical(fr_mul(x, y), out);
+}
+int h_verify_plan(int m, int n, const uint8_t* enc_g, const uint8_t* ck_g, const uint8_t* ck_h, const uint8_t* ghat,
+                  const uint8_t* gsum, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint8_t* proof,
+                  uint8_t* g1_pts, uint8_t* g1_scal, int* job_lens, uint8_t* sx, uint8_t* s2, uint8_t* ss, uint8_t* small_pts,
+                  int* host_flags) {
+  const size_t PB = kPointBytes;
+  ShuffleParamsHost S;
+  S.m = m; S.n = n;
+  S.ck64.resize((size_t)(n + 1) * PB);
+  memcpy(S.ck64.data(), ck_h, PB);
+  memcpy(S.ck64.data() + PB, ck_g, (size_t)n * PB);
+  memcpy(S.enc_g, enc_g, PB); memcpy(S.ghat, ghat, PB); memcpy(S.gsum, gsum, PB);
+  const Layout L(m, n);
+  const size_t N = (size_t)m * n;
+  const Challenges ch = derive_challenges(&S, pk, deck, deck2, N, proof, L);
+  TermList tl;
+  HostChecks hc;
+  append_g1_checks(tl, &S, proof, L, ch, &hc);
+  memcpy(g1_pts, tl.pts.data(), tl.pts.size());
+  memcpy(g1_scal, tl.scal.data(), tl.scal.size() * 4);
+  for (int j = 0; j < kG1Checks; j++) job_lens[j] = (int)tl.jobs[j].len;
+  fr bstar;
+  build_ct_plan(&S, pk, proof, L, ch, (uint32_t*)sx, (uint32_t*)s2, (uint32_t*)ss, small_pts, &bstar);
+  host_flags[0] = hc.hadamard_bytes_ok; host_flags[1] = hc.zero_bytes_ok; host_flags[2] = hc.svp_first_ok;
+  host_flags[3] = fr_eq(hc.svp_last, fr_mul(hc.xs, bstar)); host_flags[4] = hc.multiexp_bytes_ok;
+  return (int)tl.count();
+}
+int h_verdict(const int* g1_id, int ct_ok, const int* host_flags) {
+  HostChecks hc;
+  hc.hadamard_bytes_ok = host_flags[0]; hc.zero_bytes_ok = host_flags[1]; hc.svp_first_ok = host_flags[2];
+  hc.multiexp_bytes_ok = host_flags[4];
+  hc.xs = fr_one(); hc.svp_last = host_flags[3] ? fr_mul(fr_one(), fr_one()) : fr_zero();
+  bool ids[kG1Checks];
+  for (int j = 0; j < kG1Checks; j++) ids[j] = g1_id[j] != 0;
+  return verdict(hc, fr_one(), ids, ct_ok != 0);
+}
+}

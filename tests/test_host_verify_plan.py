@@ -10,23 +10,36 @@ import subprocess
 
 import pytest
 
-from oracle.py import stark, bayer_groth as bg
+from oracle.py import stark as _stark, bayer_groth as bg
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json")))
+GOLDS = {"stark": json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json"))),
+         "bls12_377": json.load(open(os.path.join(ROOT, "tests", "golden", "bls12_377_shuffle_vectors.json")))}
 h = bytes.fromhex
+# the module-level names below are rebound per curve by the `shim` fixture: the same test bodies run the host plan of
+# the Stark instantiation and of the BLS12-377 one (csrc/shuffle_host.hpp compiled with -DMP_CURVE_BLS12_377)
+stark, GOLD, PB = _stark, GOLDS["stark"], 64
 
 
-@pytest.fixture(scope="module")
-def shim(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("shim") / "host_shim.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", out,
-                           os.path.join(ROOT, "tests", "host", "host_shim.cpp")])
-    return ctypes.CDLL(out)
+@pytest.fixture(scope="module", params=["stark", "bls12_377"])
+def shim(request, tmp_path_factory):
+    global stark, GOLD, PB
+    name = request.param
+    out = str(tmp_path_factory.mktemp("shim_" + name) / "host_shim.so")
+    src, flags = ("host_shim.cpp", []) if name == "stark" else ("host_shim_bls12_377.cpp", ["-DMP_CURVE_BLS12_377"])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", *flags, "-o", out,
+                           os.path.join(ROOT, "tests", "host", src)])
+    with bg.curve(name) as grp:
+        stark, GOLD, PB = grp, GOLDS[name], 64 if name == "stark" else 96
+        lib = ctypes.CDLL(out)
+        if name != "stark":
+            assert lib.h_point_bytes() == 96
+        yield lib
+    stark, GOLD, PB = _stark, GOLDS["stark"], 64
 
 
 def pts(buf):
-    return [stark.point_from_bytes64(buf[64 * i:64 * i + 64]) for i in range(len(buf) // 64)]
+    return [stark.point_from_bytes64(buf[PB * i:PB * i + PB]) for i in range(len(buf) // PB)]
 
 
 def scs(buf):
@@ -41,10 +54,10 @@ def run_plan(shim, fx, deck2=None, proof=None):
     for p in pts(ck_g):
         gsum = stark.add(gsum, p)
     T1 = 8 * m + 5 * n + 19
-    g1_pts, g1_scal = ctypes.create_string_buffer(T1 * 64), ctypes.create_string_buffer(T1 * 32)
+    g1_pts, g1_scal = ctypes.create_string_buffer(T1 * PB), ctypes.create_string_buffer(T1 * 32)
     lens, flags = (ctypes.c_int * 8)(), (ctypes.c_int * 5)()
     sx, s2 = ctypes.create_string_buffer(N * 32), ctypes.create_string_buffer(N * 32)
-    ss, small = ctypes.create_string_buffer((2 * m + 3) * 32), ctypes.create_string_buffer((2 * m + 3) * 128)
+    ss, small = ctypes.create_string_buffer((2 * m + 3) * 32), ctypes.create_string_buffer((2 * m + 3) * 2 * PB)
     deck, deck2 = h(fx["deck"]), deck2 or h(fx["deck2"])
     cnt = shim.h_verify_plan(m, n, h(fx["enc_g"]), ck_g, h(fx["ck_h"]), h(fx["ghat"]), stark.point_to_bytes64(gsum),
                              h(fx["pk"]), deck, deck2, proof or h(fx["proof"]), g1_pts, g1_scal, lens, sx, s2, ss, small, flags)
@@ -80,7 +93,7 @@ def test_verdicts_match_oracle_on_bad_inputs(shim):
     deck = [tuple(pts(h(fx["deck"]))[2 * i:2 * i + 2]) for i in range(m * n)]
     good2 = h(fx["deck2"])
     # wrong shuffled deck (rotate the cards): reference negative case -> Hadamard
-    wrong = good2[128:] + good2[:128]
+    wrong = good2[2 * PB:] + good2[:2 * PB]
     proof = h(fx["proof"])
     cases = [(wrong, proof)]
     for off in (len(proof) - 1 - 32 * 3, len(proof) - 32 * (n + 4) - 1):   # multi-exp r, multi-exp a_n
