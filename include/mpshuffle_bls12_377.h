@@ -6,8 +6,9 @@
  * These entry points are the group layer of that instantiation: the
  * variable-base MSM, the 2-component ciphertext MSM and the fixed-base batched Pedersen commitment
  * that ShuffleArgument::{prove,verify} / MultiExponentiationArgument / PedersenCommitment::commit
- * reduce to (call sites mod.rs:397-415,427-442; commit key setup mod.rs:111).  The protocol driver
- * above them (mp_shuffle_*) is Stark-curve only so far.
+ * reduce to (call sites mod.rs:397-415,427-442; commit key setup mod.rs:111), plus verify_shuffle built on
+ * them with host-side scalars (mp377_shuffle_verify).  The prover and the device-resident / batched protocol
+ * drivers (mp_shuffle_*) are Stark-curve only so far.
  *
  * Conventions are those of mpshuffle.h with the sizes of this curve:
  *   - base-field element: 48 bytes little-endian canonical (ark-ff 0.3 `Fp384` `ToBytes`);
@@ -63,6 +64,18 @@ int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_sc
 int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_t n_points, int32_t ncomp,
                        const uint8_t* scalars, uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs,
                        int32_t window_bits, uint8_t* out);
+
+/* BarnettSmartProtocol::verify_shuffle over this curve (reference src/lib.rs:191-197, impl mod.rs:420-443;
+ * Parameters = (m, n, enc generator, commit key g_1..g_n / h, extra generator), mod.rs:37-61).  Returns
+ * MP_OK, an MP_VERIFY_* code (mp_verify_status_string gives the reference's message, e.g.
+ * "Hadamard Product (5.1)"), or MP_ERR_*.  Proof layout: the flat layout of mpshuffle.h with 96-byte
+ * points, mp377_proof_len(m, n) = (11m + 8) * 96 + (5n + 9) * 32 bytes.  Host-scalar path: the O(N) scalar
+ * work and the transcript run on the calling thread, the group work on the GPU. */
+uint64_t mp377_proof_len(int32_t m, int32_t n);
+int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g /* 96 */,
+                             const uint8_t* ck_g /* n*96 */, const uint8_t* ck_h /* 96 */, const uint8_t* ghat /* 96 */,
+                             const uint8_t* pk /* 96 */, const uint8_t* deck /* m*n*192 */,
+                             const uint8_t* shuffled_deck /* m*n*192 */, const uint8_t* proof);
 
 /* Window-range split of ONE MSM across GPUs: rank r computes the windows
  * [w_begin, w_begin + w_count) of the mp377_msm_num_windows(window_bits) windows end to end and returns

@@ -26,6 +26,8 @@ SIGNATURES = {
     "mp377_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
     "mp377_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp377_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp377_proof_len": (_u64, [_i32, _i32]),
+    "mp377_shuffle_verify": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp, _cp, _cp, _cp, _cp]),
     "mp377_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, ctypes.POINTER(ctypes.c_uint32), _u64, _i32, _cp]),
     "mp377_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
     "mp377_set_commit_key": (_i32, [_vp, _cp, _u64]),
@@ -126,6 +128,14 @@ class Context:
     @staticmethod
     def msm_num_windows(window_bits):
         return lib.mp377_msm_num_windows(window_bits)
+
+    # --- protocol
+    def verify_shuffle(self, m, n, enc_g, ck_g, ck_h, ghat, pk, deck, shuffled_deck, proof) -> int:
+        """-> 0 or an MP_VERIFY_* code (lib.mp_verify_status_string gives the reference's message)."""
+        N = m * n
+        assert len(ck_g) == n * POINT_BYTES and len(deck) == len(shuffled_deck) == 2 * N * POINT_BYTES
+        assert len(proof) == lib.mp377_proof_len(m, n)
+        return _check(self.h, lib.mp377_shuffle_verify(self.h, m, n, enc_g, ck_g, ck_h, ghat, pk, deck, shuffled_deck, proof))
 
     # --- Pedersen
     def set_commit_key(self, ck: bytes):

@@ -18,6 +18,7 @@
 
 #include "../../include/mpshuffle_bls12_377.h"
 #include "msm.cuh"
+#include "shuffle_host.hpp"
 
 #ifndef MP_CURVE_BLS12_377
 #error "capi_bls12_377.cu must be compiled with -DMP_CURVE_BLS12_377 -Dmp=mp_bls12_377"
@@ -243,6 +244,70 @@ extern "C" int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_
   ctx->last_ec_adds = 0;
   for (auto& j : h_jobs) ctx->last_ec_adds += scheduled_ec_adds(j.len, c, ncomp);
   return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// verify_shuffle over this curve (BarnettSmartProtocol::verify_shuffle, reference src/lib.rs:191-197, impl
+// mod.rs:420-443, instantiated as in examples/parameter_selection.rs:25-29).  The host half is the curve-generic
+// csrc/shuffle_host.hpp -- transcript, challenges, every verifier check rewritten as "sum scalar * point == O"
+// (CPU-tested for both curves in tests/test_host_verify_plan.py) -- with the O(N) scalars computed on the host;
+// the group work is two launch sequences of the batched MSM above: the eight commitment-space equations as
+// eight G1 jobs, the two ciphertext equations as two 2-component jobs.  (The Stark-curve verifier additionally
+// moves the O(N) scalar work to device kernels and keeps decks resident; that driver is not built for this
+// curve yet.)
+// ------------------------------------------------------------------------------------------
+extern "C" uint64_t mp377_proof_len(int32_t m, int32_t n) { return shuffle_proof_len(m, n); }
+
+extern "C" int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
+                                        const uint8_t* ck_h, const uint8_t* ghat, const uint8_t* pk, const uint8_t* deck,
+                                        const uint8_t* shuffled_deck, const uint8_t* proof) {
+  if (!ctx || !enc_g || !ck_g || !ck_h || !ghat || !pk || !deck || !shuffled_deck || !proof) return MP_ERR_INVALID_ARG;
+  if (m < 1 || n < 2 || (uint64_t)m * n >= (1ull << 26)) return ctx->fail(MP_ERR_INVALID_ARG, "unsupported (m, n) = (%d, %d)", m, n);
+  const size_t N = (size_t)m * n;
+  int launches = 0;
+  // gsum = g_1 + .. + g_n (commitments to constant vectors are c * gsum); also validates the key
+  ShuffleParamsHost S;
+  S.m = m;
+  S.n = n;
+  {
+    std::vector<uint8_t> ones((size_t)n * 32, 0);
+    for (int j = 0; j < n; j++) ones[32 * (size_t)j] = 1;
+    int32_t st = msm_host_common(ctx, ck_g, ones.data(), (uint64_t)n, 1, 0, S.gsum);
+    if (st != MP_OK) return st;
+    launches += ctx->launches;
+  }
+  S.ck64.resize((size_t)(n + 1) * kPt);
+  memcpy(S.ck64.data(), ck_h, kPt);
+  memcpy(S.ck64.data() + kPt, ck_g, (size_t)n * kPt);
+  memcpy(S.enc_g, enc_g, kPt);
+  memcpy(S.ghat, ghat, kPt);
+  const Layout L(m, n);
+  const Challenges ch = derive_challenges(&S, pk, deck, shuffled_deck, N, proof, L);
+  // the eight commitment-space equations
+  TermList tl;
+  HostChecks hc;
+  append_g1_checks(tl, &S, proof, L, ch, &hc);
+  static_assert(sizeof(MsmJob) == 12, "MsmJob is three uint32");
+  std::vector<uint8_t> g1_out((size_t)kG1Checks * kPt);
+  int32_t st = mp377_msm_jobs(ctx, tl.pts.data(), tl.count(), 1, (const uint8_t*)tl.scal.data(), tl.count(),
+                              (const uint32_t*)tl.jobs.data(), (uint64_t)kG1Checks, 0, g1_out.data());
+  if (st != MP_OK) return st;
+  launches += ctx->launches;
+  bool g1_id[kG1Checks];
+  for (int j = 0; j < kG1Checks; j++) g1_id[j] = all_zero(g1_out.data() + (size_t)j * kPt, kPt);
+  // the two ciphertext equations, each one contiguous 2-component job (layout: assemble_ct_jobs)
+  std::vector<uint8_t> cts;
+  std::vector<uint32_t> scal;
+  uint32_t ct_jobs[6];
+  fr bstar;
+  assemble_ct_jobs(&S, pk, deck, shuffled_deck, proof, L, ch, cts, scal, ct_jobs, &bstar);
+  const size_t nct = scal.size() / 8;
+  uint8_t ct_out[2 * kCtBytes];
+  st = mp377_msm_jobs(ctx, cts.data(), nct, 2, (const uint8_t*)scal.data(), nct, ct_jobs, 2, 0, ct_out);
+  if (st != MP_OK) return st;
+  launches += ctx->launches;
+  ctx->launches = launches;
+  return verdict(hc, bstar, g1_id, all_zero(ct_out, sizeof ct_out));
 }
 
 // Window-range split of one MSM across GPUs: the partial

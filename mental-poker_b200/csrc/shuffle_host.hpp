@@ -299,6 +299,32 @@ inline void build_ct_plan(const ShuffleParamsHost* S, const uint8_t* pk, const u
   memcpy(t + 3 * kPointBytes, S->ghat, kPointBytes);
 }
 
+// The same two equations laid out as TWO CONTIGUOUS 2-component MSM jobs over one ciphertext array and one scalar
+// array (the form a batched-MSM entry point takes; used by the host-scalar verifier of capi_bls12_377.cu):
+//   cts  = deck (N) | E_m | deck' (N) | E_0..E_{2m-1} | (g, pk) | (O, ghat)          2N + 2m + 3 ciphertexts
+//   scal = x^i (N)  | -1  | -(xm^{m-i} a_j) (N) | xm^k .. | -tau | -b                  same order, 8 words each
+//   jobs = (0, 0, N + 1), (N + 1, N + 1, N + 2m + 2)   as (scalar_off, point_off, len)
+inline void assemble_ct_jobs(const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
+                             const uint8_t* proof, const Layout& L, const Challenges& ch, std::vector<uint8_t>& cts,
+                             std::vector<uint32_t>& scal, uint32_t jobs[6], fr* bstar) {
+  const size_t N = (size_t)S->m * S->n, nsmall = 2 * (size_t)S->m + 3, nct = 2 * N + nsmall;
+  std::vector<uint8_t> small(nsmall * kCtBytes);
+  std::vector<uint32_t> sx(8 * N), s2(8 * N), ss(8 * nsmall);
+  build_ct_plan(S, pk, proof, L, ch, sx.data(), s2.data(), ss.data(), small.data(), bstar);
+  cts.resize(nct * kCtBytes);
+  scal.resize(8 * nct);
+  memcpy(cts.data(), deck, N * kCtBytes);
+  memcpy(cts.data() + N * kCtBytes, small.data(), kCtBytes);
+  memcpy(cts.data() + (N + 1) * kCtBytes, deck2, N * kCtBytes);
+  memcpy(cts.data() + (2 * N + 1) * kCtBytes, small.data() + kCtBytes, (nsmall - 1) * kCtBytes);
+  memcpy(scal.data(), sx.data(), 32 * N);
+  memcpy(scal.data() + 8 * N, ss.data(), 32);
+  memcpy(scal.data() + 8 * (N + 1), s2.data(), 32 * N);
+  memcpy(scal.data() + 8 * (2 * N + 1), ss.data() + 8, 32 * (nsmall - 1));
+  jobs[0] = 0; jobs[1] = 0; jobs[2] = (uint32_t)(N + 1);
+  jobs[3] = (uint32_t)(N + 1); jobs[4] = (uint32_t)(N + 1); jobs[5] = (uint32_t)(N + nsmall - 1);
+}
+
 // Verdict in the order the reference reaches the checks (product argument first: Hadamard ->
 // zero -> single-value product; then multi-exponentiation).  g1_id[0..8): H1 Z1 Z2 Z3 S1 S2 M1 M2;
 // ct_ok: both ciphertext equations (Chat == E_m and the multi-exp opening) hold.

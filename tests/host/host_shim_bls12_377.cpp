@@ -100,6 +100,27 @@ int h_verify_plan(int m, int n, const uint8_t* enc_g, const uint8_t* ck_g, const
   host_flags[3] = fr_eq(hc.svp_last, fr_mul(hc.xs, bstar)); host_flags[4] = hc.multiexp_bytes_ok;
   return (int)tl.count();
 }
+// the two ciphertext equations as the contiguous jobs mp377_shuffle_verify launches (assemble_ct_jobs)
+int h_ct_jobs(int m, int n, const uint8_t* enc_g, const uint8_t* ck_g, const uint8_t* ck_h, const uint8_t* ghat,
+              const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2, const uint8_t* proof, uint8_t* cts_out,
+              uint8_t* scal_out, uint32_t* jobs_out) {
+  const size_t PB = kPointBytes;
+  ShuffleParamsHost S;
+  S.m = m; S.n = n;
+  S.ck64.resize((size_t)(n + 1) * PB);
+  memcpy(S.ck64.data(), ck_h, PB);
+  memcpy(S.ck64.data() + PB, ck_g, (size_t)n * PB);
+  memcpy(S.enc_g, enc_g, PB); memcpy(S.ghat, ghat, PB); memset(S.gsum, 0, PB);
+  const Layout L(m, n);
+  const Challenges ch = derive_challenges(&S, pk, deck, deck2, (size_t)m * n, proof, L);
+  std::vector<uint8_t> cts;
+  std::vector<uint32_t> scal;
+  fr bstar;
+  assemble_ct_jobs(&S, pk, deck, deck2, proof, L, ch, cts, scal, jobs_out, &bstar);
+  memcpy(cts_out, cts.data(), cts.size());
+  memcpy(scal_out, scal.data(), scal.size() * 4);
+  return (int)(scal.size() / 8);
+}
 int h_verdict(const int* g1_id, int ct_ok, const int* host_flags) {
   HostChecks hc;
   hc.hadamard_bytes_ok = host_flags[0]; hc.zero_bytes_ok = host_flags[1]; hc.svp_first_ok = host_flags[2];

@@ -266,6 +266,58 @@ def test_shuffle_verifier_group_work_on_gpu(ctx377, monkeypatch):
         assert calls["ct_msm"] >= 2 and calls["commit"] >= 3 and calls["msm"] >= 1, calls
 
 
+def test_verify_shuffle_c_abi(ctx377, pkg):
+    """`mp377_shuffle_verify`: BarnettSmartProtocol::verify_shuffle over BLS12-377 through the C ABI (host half =
+    csrc/shuffle_host.hpp, group work = the batched MSM).  Valid fixtures verify; a rotated output deck, flipped
+    proof bytes in each sub-argument and a proof for another statement get the verdict of the big-int oracle --
+    the reference's negative test expects "Hadamard Product (5.1)" for a wrong deck (tests.rs:213-226)."""
+    from oracle.py import bayer_groth as bg
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_shuffle_vectors.json")))
+    pt = bls.point_from_bytes
+    for fx in gold["shuffle"]:
+        m, n = fx["m"], fx["n"]
+        N = m * n
+        raw = {k: bytes.fromhex(fx[k]) for k in ("enc_g", "ck_g", "ck_h", "ghat", "pk", "deck", "deck2", "proof")}
+        args = (m, n, raw["enc_g"], raw["ck_g"], raw["ck_h"], raw["ghat"], raw["pk"], raw["deck"])
+        assert pkg.lib.mp377_proof_len(m, n) == len(raw["proof"])
+        assert ctx377.verify_shuffle(*args, raw["deck2"], raw["proof"]) == 0
+        assert ctx377.launches > 0
+        cases = [(raw["deck2"][192:] + raw["deck2"][:192], raw["proof"])]
+        plen = len(raw["proof"])
+        for off in (plen - 1 - 32 * 3, plen - 32 * (n + 4) - 1,              # multi-exp r, multi-exp a_n
+                    (11 * m + 8) * 96 - 96 * (4 * m + 2 * m + 1) - 32 * (2 * n + 2) - 40):  # inside the SVP block
+            p2 = bytearray(raw["proof"])
+            p2[off] ^= 1
+            cases.append((raw["deck2"], bytes(p2)))
+        with bg.curve("bls12_377"):
+            pp = bg.Params(m, n, pt(raw["enc_g"]), [pt(raw["ck_g"][96 * i:96 * i + 96]) for i in range(n)],
+                           pt(raw["ck_h"]), pt(raw["ghat"]))
+            pk = pt(raw["pk"])
+            cts = lambda b: [(pt(b[192 * i:192 * i + 96]), pt(b[192 * i + 96:192 * i + 192])) for i in range(N)]
+            deck = cts(raw["deck"])
+            for d2, pf in cases:
+                try:
+                    parsed = bg.proof_from_bytes(pf, m, n)
+                    if not all(bls.is_on_curve(q) for q in parsed["c_A"] + parsed["c_B"]):
+                        continue
+                    want = bg.shuffle_verify(pp, pk, deck, cts(d2), parsed)
+                except Exception:
+                    continue  # the flipped byte broke a point encoding: the C ABI reports MP_ERR_NOT_ON_CURVE instead
+                try:
+                    got = ctx377.verify_shuffle(*args, d2, pf)
+                except pkg.MpError as e:
+                    assert e.code == -3
+                    continue
+                assert got == want != 0, (m, n, got, want)
+        assert pkg.lib.mp_verify_status_string(1) == b"Hadamard Product (5.1)"
+    # the wrong-deck case is the reference's own negative test and must be caught as a verification failure
+    fx = gold["shuffle"][1]
+    raw = {k: bytes.fromhex(fx[k]) for k in ("enc_g", "ck_g", "ck_h", "ghat", "pk", "deck", "deck2", "proof")}
+    st = ctx377.verify_shuffle(fx["m"], fx["n"], raw["enc_g"], raw["ck_g"], raw["ck_h"], raw["ghat"], raw["pk"], raw["deck"],
+                               raw["deck2"][192:] + raw["deck2"][:192], raw["proof"])
+    assert st > 0
+
+
 def test_kernels_were_launched(ctx377):
     msm_case(ctx377, 64, 0)
     assert ctx377.launches > 0

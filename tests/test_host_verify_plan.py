@@ -106,3 +106,28 @@ def test_verdicts_match_oracle_on_bad_inputs(shim):
                                  bg.proof_from_bytes(pf, m, n))
         got, *_ = run_plan(shim, fx, d2, pf)
         assert got == want != 0
+
+
+def test_contiguous_ciphertext_jobs(shim):
+    """`assemble_ct_jobs` (the layout mp377_shuffle_verify hands to the batched MSM): both 2-component jobs sum to the
+    identity for a valid proof and not for a rotated output deck."""
+    if PB != 96:
+        pytest.skip("only the BLS12-377 shim exports h_ct_jobs")
+    fx = GOLD["shuffle"][1]
+    m, n = fx["m"], fx["n"]
+    N = m * n
+    nct = 2 * N + 2 * m + 3
+    good2 = h(fx["deck2"])
+    for d2, expect in ((good2, True), (good2[2 * PB:] + good2[:2 * PB], False)):
+        cts, scal = ctypes.create_string_buffer(nct * 2 * PB), ctypes.create_string_buffer(nct * 32)
+        jobs = (ctypes.c_uint32 * 6)()
+        cnt = shim.h_ct_jobs(m, n, h(fx["enc_g"]), h(fx["ck_g"]), h(fx["ck_h"]), h(fx["ghat"]), h(fx["pk"]), h(fx["deck"]), d2,
+                             h(fx["proof"]), cts, scal, jobs)
+        assert cnt == nct and list(jobs) == [0, 0, N + 1, N + 1, N + 1, N + 2 * m + 2]
+        P, K = pts(cts.raw), scs(scal.raw)
+        ok = True
+        for so, po, ln in (tuple(jobs[:3]), tuple(jobs[3:])):
+            for comp in (0, 1):
+                acc = stark.msm(P[2 * po + comp:2 * (po + ln):2], K[so:so + ln])
+                ok = ok and acc is stark.INF
+        assert ok == expect
