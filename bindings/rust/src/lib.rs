@@ -105,6 +105,12 @@ extern "C" {
     pub fn mp377_ct_msm(ctx: *mut Mp377Ctx, deck: *const u8, scalars: *const u8, n: u64, window_bits: i32, out: *mut u8) -> i32;
     pub fn mp377_set_commit_key(ctx: *mut Mp377Ctx, ck: *const u8, len: u64) -> i32;
     pub fn mp377_pedersen_commit_batch(ctx: *mut Mp377Ctx, values: *const u8, blinds: *const u8, k: u64, len: u64, out: *mut u8) -> i32;
+    pub fn mp377_msm_jobs(ctx: *mut Mp377Ctx, points: *const u8, n_points: u64, ncomp: i32, scalars: *const u8, n_scalars: u64,
+                          jobs: *const u32, njobs: u64, window_bits: i32, out: *mut u8) -> i32;
+    // BarnettSmartProtocol::verify_shuffle over BLS12-377 (lib.rs:191-197): 0 = Ok(()), > 0 = failed check, < 0 = error
+    pub fn mp377_proof_len(m: i32, n: i32) -> u64;
+    pub fn mp377_shuffle_verify(ctx: *mut Mp377Ctx, m: i32, n: i32, enc_g: *const u8, ck_g: *const u8, ck_h: *const u8, ghat: *const u8,
+                                pk: *const u8, deck: *const u8, shuffled: *const u8, proof: *const u8) -> i32;
 }
 
 /// Sketch of the two overridden trait methods (generic bounds elided):

@@ -6,9 +6,9 @@
 // second copy of msm.cu are compiled with -DMP_CURVE_BLS12_377 -Dmp=mp_bls12_377: the same Pippenger
 // pipeline (msm.cu), the same XYZZ group law (ec.cuh, a = 0 branch) over the 12-limb field of
 // fq_bls12_377.cuh, linked into libmpshuffle.so next to the Stark-curve build.  Built so far: the group
-// layer under the protocol -- variable-base MSM, ciphertext (2-component) MSM, fixed-base batched
-// Pedersen commitments -- i.e. the kernels all of ShuffleArgument::{prove,verify} reduce to; the
-// protocol driver above them is still Stark-only (its byte layouts are 32-byte coordinates).
+// layer under the protocol -- variable-base MSM, ciphertext (2-component) MSM, batched MSM jobs, fixed-base
+// batched Pedersen commitments -- i.e. the kernels all of ShuffleArgument::{prove,verify} reduce to, and
+// verify_shuffle on top of them (host-scalar form); the prover and the device-resident drivers are Stark-only.
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
