@@ -32,3 +32,18 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "proofs/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["metric"] == bench.METRIC and d["higher_is_better"] is True
+
+
+def test_bls12_377_generator_constant():
+    # the second-curve section of the bench builds its inputs from this constant (x || y, 48-byte LE coordinates)
+    from oracle.py import bls12_377 as bls
+    assert bytes.fromhex(bench.GEN_BLS12_377) == bls.point_to_bytes(bls.G)
+
+
+def test_our_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
