@@ -77,6 +77,18 @@ int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t
                              const uint8_t* pk /* 96 */, const uint8_t* deck /* m*n*192 */,
                              const uint8_t* shuffled_deck /* m*n*192 */, const uint8_t* proof);
 
+/* Wire format, serialising half (ark-serialize 0.3 compressed encodings, as mp_points_compress / mp_deck_serialize /
+ * mp_proof_serialize of mpshuffle.h): compressed point = x (48 bytes LE) with flags in the top bits of the last byte
+ * (bit 7: y is the larger of (y, -y); bit 6: infinity); Vec<MaskedCard> = u64 LE length | c1 | c2 per card; proof =
+ * the flat layout with every point compressed, (11m + 8) * 48 + (5n + 9) * 32 bytes -- the quantity the reference's
+ * benchmark prints (examples/parameter_selection.rs:93-96).  Host byte handling, no context.  Deserialising is not
+ * built for this curve yet. */
+int32_t mp377_points_compress(const uint8_t* points /* n*96 */, uint64_t n, uint8_t* out /* n*48 */);
+uint64_t mp377_deck_serialized_len(uint64_t n_cards);
+int32_t mp377_deck_serialize(const uint8_t* deck /* n_cards*192 */, uint64_t n_cards, uint8_t* out);
+uint64_t mp377_proof_serialized_len(int32_t m, int32_t n);
+int32_t mp377_proof_serialize(int32_t m, int32_t n, const uint8_t* proof, uint8_t* out);
+
 /* Window-range split of ONE MSM across GPUs: rank r computes the windows
  * [w_begin, w_begin + w_count) of the mp377_msm_num_windows(window_bits) windows end to end and returns
  *   P_r = sum_w 2^(c (w - w_begin)) * (window sum w);   MSM = sum_r 2^(c * w_begin_r) * P_r

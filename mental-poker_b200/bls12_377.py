@@ -26,6 +26,11 @@ SIGNATURES = {
     "mp377_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
     "mp377_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp377_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp377_points_compress": (_i32, [_cp, _u64, _cp]),
+    "mp377_deck_serialized_len": (_u64, [_u64]),
+    "mp377_deck_serialize": (_i32, [_cp, _u64, _cp]),
+    "mp377_proof_serialized_len": (_u64, [_i32, _i32]),
+    "mp377_proof_serialize": (_i32, [_i32, _i32, _cp, _cp]),
     "mp377_proof_len": (_u64, [_i32, _i32]),
     "mp377_shuffle_verify": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp, _cp, _cp, _cp, _cp]),
     "mp377_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, ctypes.POINTER(ctypes.c_uint32), _u64, _i32, _cp]),
@@ -50,6 +55,28 @@ def _check(h, code):
         msg = lib.mp377_last_error_string(h)
         raise MpError(code, msg.decode() if msg else "")
     return code
+
+
+# --- wire format, serialising half: host byte handling, no context, no GPU
+def points_compress(points: bytes) -> bytes:
+    n = len(points) // POINT_BYTES
+    out = ctypes.create_string_buffer(max(1, FQ_BYTES * n))
+    assert lib.mp377_points_compress(points, n, out) == 0
+    return out.raw[:FQ_BYTES * n]
+
+
+def deck_serialize(deck: bytes) -> bytes:
+    n = len(deck) // (2 * POINT_BYTES)
+    out = ctypes.create_string_buffer(lib.mp377_deck_serialized_len(n))
+    assert lib.mp377_deck_serialize(deck, n, out) == 0
+    return out.raw
+
+
+def proof_serialize(m: int, n: int, proof: bytes) -> bytes:
+    assert len(proof) == lib.mp377_proof_len(m, n)
+    out = ctypes.create_string_buffer(lib.mp377_proof_serialized_len(m, n))
+    assert lib.mp377_proof_serialize(m, n, proof, out) == 0
+    return out.raw
 
 
 class Context:

@@ -19,6 +19,7 @@
 #include "../../include/mpshuffle_bls12_377.h"
 #include "msm.cuh"
 #include "shuffle_host.hpp"
+#include "wire_host.hpp"
 
 #ifndef MP_CURVE_BLS12_377
 #error "capi_bls12_377.cu must be compiled with -DMP_CURVE_BLS12_377 -Dmp=mp_bls12_377"
@@ -308,6 +309,30 @@ extern "C" int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, co
   launches += ctx->launches;
   ctx->launches = launches;
   return verdict(hc, bstar, g1_id, all_zero(ct_out, sizeof ct_out));
+}
+
+// ------------------------------------------------------------------------------------------
+// wire format, serialising half (ark-serialize 0.3 compressed encodings; host byte handling as on the Stark
+// curve, csrc/wire_host.hpp): 48-byte compressed points.  Deserialising needs a square root in F_q per point
+// (q - 1 = 2^46 * odd) and is not built for this curve yet.
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t mp377_points_compress(const uint8_t* points, uint64_t n, uint8_t* out) {
+  if ((!points || !out) && n) return MP_ERR_INVALID_ARG;
+  for (uint64_t i = 0; i < n; i++) wire_compress_point(points + kWirePt * i, out + kWireFe * i);
+  return MP_OK;
+}
+extern "C" uint64_t mp377_deck_serialized_len(uint64_t n_cards) { return wire_deck_len(n_cards); }
+extern "C" int32_t mp377_deck_serialize(const uint8_t* deck, uint64_t n_cards, uint8_t* out) {
+  if (!out || (!deck && n_cards)) return MP_ERR_INVALID_ARG;
+  memcpy(out, &n_cards, 8);  // u64 little-endian length prefix of Vec<MaskedCard>
+  for (uint64_t i = 0; i < 2 * n_cards; i++) wire_compress_point(deck + kWirePt * i, out + 8 + kWireFe * i);
+  return MP_OK;
+}
+extern "C" uint64_t mp377_proof_serialized_len(int32_t m, int32_t n) { return wire_proof_len(m, n); }
+extern "C" int32_t mp377_proof_serialize(int32_t m, int32_t n, const uint8_t* proof, uint8_t* out) {
+  if (!proof || !out || m < 1 || n < 1) return MP_ERR_INVALID_ARG;
+  wire_proof_serialize(m, n, proof, out);
+  return MP_OK;
 }
 
 // Window-range split of one MSM across GPUs: the partial

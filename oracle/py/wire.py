@@ -64,3 +64,40 @@ def deck_deserialize(b):
     if len(b) != 8 + 64 * n:
         raise ValueError("length prefix does not match the buffer")
     return [(decompress(b[8 + 64 * i:40 + 64 * i]), decompress(b[40 + 64 * i:72 + 64 * i])) for i in range(n)]
+
+
+# ----------------------------------------------------------------------------- second curve (BLS12-377 G1)
+def compress_generic(pt, curve):
+    """Same encoding over any `weierstrass.Curve`: x in `curve.fe_bytes` little-endian bytes, flags in the top bits of
+    the last byte (BLS12-377: 377-bit prime in 48 bytes, bits 377..383 free)."""
+    nb = curve.fe_bytes
+    if pt is None:
+        return bytes(nb - 1) + bytes([FLAG_INF])
+    x, y = pt
+    b = bytearray(int(x).to_bytes(nb, "little"))
+    if y > curve.P - y:
+        b[nb - 1] |= FLAG_LARGER
+    return bytes(b)
+
+
+def deck_serialize_generic(deck, curve):
+    out = len(deck).to_bytes(8, "little")
+    for c1, c2 in deck:
+        out += compress_generic(c1, curve) + compress_generic(c2, curve)
+    return out
+
+
+def proof_serialize_generic(flat_proof, m, n, curve):
+    """The flat C-ABI proof (points of 2 * fe_bytes, 32-byte scalars) with every point compressed."""
+    runs = [(True, 5 * m + 4), (False, 2 * n + 3), (True, 3), (False, 2 * n + 2), (True, 6 * m + 1), (False, n + 4)]
+    pb, out, pos = 2 * curve.fe_bytes, b"", 0
+    for is_pts, count in runs:
+        if is_pts:
+            for _ in range(count):
+                out += compress_generic(curve.point_from_bytes(flat_proof[pos:pos + pb]), curve)
+                pos += pb
+        else:
+            out += flat_proof[pos:pos + 32 * count]
+            pos += 32 * count
+    assert pos == len(flat_proof)
+    return out

@@ -112,3 +112,33 @@ def test_shuffle_protocol_over_bls12_377():
         assert bg.shuffle_verify(pp, pk, deck, deck2, bad) == bg.ERR_ZERO
         assert bg.shuffle_verify(pp, pk, deck, deck2[1:] + deck2[:1], proof) != bg.OK
     assert bg.stark is stark and bg.Q == stark.N and bg.POINT_BYTES == 64
+
+
+def test_wire_serialisation_of_the_second_curve(pkg):
+    """Serialising half of the wire format over BLS12-377 (csrc/wire_host.hpp through mp377_points_compress /
+    mp377_deck_serialize / mp377_proof_serialize: host byte handling, no GPU) against oracle/py/wire.py; and the one
+    thing the reference itself says about proof sizes -- examples/parameter_selection.rs:10 "notice how proof size
+    hits a minimum at m=10, n=30" among its five splits of 300 cards."""
+    from oracle.py import wire
+    b377 = pkg.bls12_377
+    rnd = random.Random(8)
+    pts = [bls.mul(bls.G, rnd.randrange(1, bls.N)) for _ in range(12)] + [None]
+    pts += [bls.neg(p) for p in pts[:6]]
+    flat = b"".join(map(pb, pts))
+    want = b"".join(wire.compress_generic(p, bls.CURVE) for p in pts)
+    assert b377.points_compress(flat) == want and len(want) == 48 * len(pts)
+    # y and -y differ exactly in the "larger" flag
+    for p in pts[:6]:
+        a, b = wire.compress_generic(p, bls.CURVE), wire.compress_generic(bls.neg(p), bls.CURVE)
+        assert a[:47] == b[:47] and (a[47] ^ b[47]) == 0x80
+    deck = [(pts[2 * i], pts[2 * i + 1]) for i in range(6)]
+    deck_bytes = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+    assert b377.deck_serialize(deck_bytes) == wire.deck_serialize_generic(deck, bls.CURVE)
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_shuffle_vectors.json")))
+    for fx in gold["shuffle"]:
+        proof = bytes.fromhex(fx["proof"])
+        ser = b377.proof_serialize(fx["m"], fx["n"], proof)
+        assert ser == wire.proof_serialize_generic(proof, fx["m"], fx["n"], bls.CURVE)
+        assert len(ser) == (11 * fx["m"] + 8) * 48 + (5 * fx["n"] + 9) * 32 == pkg.lib.mp377_proof_serialized_len(fx["m"], fx["n"])
+    sizes = {(m, n): pkg.lib.mp377_proof_serialized_len(m, n) for m, n in [(2, 150), (6, 50), (10, 30), (12, 25), (30, 10)]}
+    assert min(sizes, key=sizes.get) == (10, 30)

@@ -65,3 +65,40 @@ def test_c_oracle_matches_python():
     out, st = co.points_decompress(comp + b"".join(h(b) for b in GOLD["rejected"]))
     assert out[:len(pts)] == pts and st[:len(GOLD["points"])] == [0] * len(GOLD["points"])
     assert st[len(GOLD["points"]):] == [2, 2, 2, 1, 1, 1]
+
+
+def test_library_serialisers_without_a_gpu(pkg):
+    """mp_points_compress / mp_deck_serialize / mp_proof_serialize are host byte handling (csrc/wire_host.hpp): the
+    built library itself, no context, against the golden vectors and the oracle's encoder."""
+    import ctypes
+    import json as _json
+    import os as _os
+    from oracle.py import stark as _stark, wire as _wire, bayer_groth as _bg
+    here = _os.path.dirname(__file__)
+    gold = _json.load(open(_os.path.join(here, "golden", "wire_vectors.json")))
+    lib = pkg.lib
+    pts = b"".join(bytes.fromhex(fx["point"]) for fx in gold["points"])
+    comp = b"".join(bytes.fromhex(fx["compressed"]) for fx in gold["points"])
+    out = ctypes.create_string_buffer(len(comp))
+    assert lib.mp_points_compress(pts, len(pts) // 64, out) == 0 and out.raw == comp
+    deck = bytes.fromhex(gold["deck"])
+    out = ctypes.create_string_buffer(lib.mp_deck_serialized_len(len(deck) // 128))
+    assert lib.mp_deck_serialize(deck, len(deck) // 128, out) == 0 and out.raw == bytes.fromhex(gold["deck_serialized"])
+    shuf = _json.load(open(_os.path.join(here, "golden", "oracle_vectors.json")))["shuffle"]
+    for fx in shuf[:2]:
+        m, n, proof = fx["m"], fx["n"], bytes.fromhex(fx["proof"])
+        assert lib.mp_proof_serialized_len(m, n) == (11 * m + 8) * 32 + (5 * n + 9) * 32
+        out = ctypes.create_string_buffer(lib.mp_proof_serialized_len(m, n))
+        assert lib.mp_proof_serialize(m, n, proof, out) == 0
+        # every point of the flat proof compressed in place, scalars copied: re-derive with the oracle's encoder
+        runs = [(True, 5 * m + 4), (False, 2 * n + 3), (True, 3), (False, 2 * n + 2), (True, 6 * m + 1), (False, n + 4)]
+        want, pos = b"", 0
+        for is_pts, count in runs:
+            for _ in range(count):
+                if is_pts:
+                    want += _wire.compress(_stark.point_from_bytes64(proof[pos:pos + 64]))
+                    pos += 64
+                else:
+                    want += proof[pos:pos + 32]
+                    pos += 32
+        assert out.raw == want
