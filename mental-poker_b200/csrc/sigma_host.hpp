@@ -23,32 +23,36 @@ inline constexpr const char* kSeedMasking = "Masking Proof";             // mod.
 inline constexpr const char* kSeedRemasking = "Remasking Proof";         // mod.rs:82
 inline constexpr const char* kSeedReveal = "Reveal Proof";               // mod.rs:83
 
-inline constexpr size_t kCpProofLen = 160;       // a (64) | b (64) | r (32)
-inline constexpr size_t kSchnorrProofLen = 96;   // commit (64) | opening (32)
+// widths of the curve fq.cuh selects: C-ABI point = x || y = 64 bytes (Stark) / 96 bytes (BLS12-377 G1); the
+// transcript absorbs the ark-ec `ToBytes` form x || y || infinity flag, one byte longer
+inline constexpr size_t kSigmaPt = 8 * (size_t)kFqLimbs, kSigmaPtFs = kSigmaPt + 1;
+inline constexpr size_t kCpProofLen = 2 * kSigmaPt + 32;   // a | b | r          (160 bytes on the Stark curve)
+inline constexpr size_t kSchnorrProofLen = kSigmaPt + 32;  // commit | opening   (96 bytes on the Stark curve)
 
 // c = challenge after absorbing  "chaum_pedersen" | g | h | s0 | s1 | a | b  into a transcript seeded
 // with `seeded` (passed by value: from_seed is hashed once per batch, not once per proof)
-// 64-byte C-ABI point (all-zero = identity) -> the 65-byte ark-ec encoding the transcript absorbs
-inline void point65(const uint8_t* p64, uint8_t* out65) {
-  uint64_t w[8];
-  memcpy(w, p64, 64);
-  if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
-    memset(out65, 0, 65);  // identity = (0, 1, infinity)
-    out65[32] = 1;
-    out65[64] = 1;
+// C-ABI point (all-zero = identity) -> the ark-ec encoding the transcript absorbs
+inline void point65(const uint8_t* p, uint8_t* out) {
+  uint64_t w[kSigmaPt / 8], any = 0;
+  memcpy(w, p, kSigmaPt);
+  for (size_t k = 0; k < kSigmaPt / 8; k++) any |= w[k];
+  if (any == 0) {
+    memset(out, 0, kSigmaPtFs);  // identity = (0, 1, infinity)
+    out[kSigmaPt / 2] = 1;
+    out[kSigmaPt] = 1;
   } else {
-    memcpy(out65, p64, 64);
-    out65[64] = 0;
+    memcpy(out, p, kSigmaPt);
+    out[kSigmaPt] = 0;
   }
 }
 
 inline fr cp_challenge(Transcript seeded, const uint8_t* g, const uint8_t* h, const uint8_t* s0, const uint8_t* s1,
                        const uint8_t* a, const uint8_t* b) {
-  // one 404-byte message, fed in one piece: the long-input Blake2s path takes six of its seven blocks
-  uint8_t msg[14 + 6 * 65];
+  // one 404-byte message (Stark curve), fed in one piece: the long-input Blake2s path takes six of its seven blocks
+  uint8_t msg[14 + 6 * kSigmaPtFs];
   memcpy(msg, "chaum_pedersen", 14);
   const uint8_t* pts[6] = {g, h, s0, s1, a, b};
-  for (int k = 0; k < 6; k++) point65(pts[k], msg + 14 + 65 * k);
+  for (int k = 0; k < 6; k++) point65(pts[k], msg + 14 + kSigmaPtFs * k);
   seeded.begin();
   seeded.feed(msg, sizeof msg);
   seeded.end();

@@ -131,3 +131,19 @@ int h_verdict(const int* g1_id, int ct_ok, const int* host_flags) {
   return verdict(hc, fr_one(), ids, ct_ok != 0);
 }
 }
+
+// ---- host half of the batched sigma protocols (csrc/sigma_host.hpp) over this curve
+#include "../../mental-poker_b200/csrc/sigma_host.hpp"
+extern "C" {
+void h_cp_challenge(int which, const uint8_t* g, const uint8_t* h, const uint8_t* s0, const uint8_t* s1, const uint8_t* a,
+                    const uint8_t* b, uint8_t* out) {
+  const char* seed = which == 0 ? kSeedMasking : which == 1 ? kSeedRemasking : kSeedReveal;
+  fr_to_bytes(cp_challenge(Transcript(seed, strlen(seed)), g, h, s0, s1, a, b), out);
+}
+void h_schnorr_challenge(const uint8_t* info, uint64_t info_len, const uint8_t* g, const uint8_t* pk, const uint8_t* commit,
+                         uint8_t* out) {
+  fr_to_bytes(schnorr_challenge(info, info_len, g, pk, commit), out);
+}
+int h_fr_bytes_canonical(const uint8_t* b) { return fr_bytes_canonical(b); }
+int h_sigma_proof_lens(int which) { return which == 0 ? (int)kCpProofLen : (int)kSchnorrProofLen; }
+}
