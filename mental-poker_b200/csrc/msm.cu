@@ -239,15 +239,26 @@ __global__ void __launch_bounds__(64) k_table_shift(const affine* __restrict__ b
 // thread per base: normalise its W shifted copies to affine Montgomery with ONE inversion
 // (Montgomery's trick over the W values of ZZ*ZZZ); the identity stays (0,0)
 static constexpr int kMaxTableWindows = 64;
+// MODE (experiment knob, scripts/sanitize.sh): 0 = per-thread prefix array in local memory, multiplication as
+// compiled for this curve (a call on the 12-limb build); 1 = prefix array in global scratch; 2 = local array,
+// multiplications of this kernel inlined.
+#ifdef MP_CURVE_BLS12_377
+#define MP_TN_MUL(MODE, a, b) ((MODE) == 2 ? fq_mul_inline(a, b) : fq_mul(a, b))
+#else
+#define MP_TN_MUL(MODE, a, b) fq_mul(a, b)
+#endif
+template <int MODE>
 __global__ void __launch_bounds__(64) k_table_normalise(const xyzz* __restrict__ tmp, uint32_t nb, uint32_t first,
-                                                        uint32_t count, int W, affine* __restrict__ table) {
+                                                        uint32_t count, int W, affine* __restrict__ table,
+                                                        fq* __restrict__ pre_all) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  fq pre[kMaxTableWindows];  // pre[w] = product of z_0 .. z_w (z = ZZ*ZZZ, or 1 for the identity)
+  fq pre_local[MODE == 1 ? 1 : kMaxTableWindows];  // pre[w] = product of z_0 .. z_w (z = ZZ*ZZZ, or 1 for the identity)
+  fq* pre = MODE == 1 ? pre_all + (size_t)i * kMaxTableWindows : pre_local;
   fq acc = fq_one();
   for (int w = 0; w < W; w++) {
     xyzz p = xyzz_load(tmp + (size_t)w * count + i);
-    if (!xyzz_is_identity(p)) acc = fq_mul(acc, fq_mul(p.ZZ, p.ZZZ));
+    if (!xyzz_is_identity(p)) acc = MP_TN_MUL(MODE, acc, MP_TN_MUL(MODE, p.ZZ, p.ZZZ));
     pre[w] = acc;
   }
   fq inv = fq_inv(acc);  // 1 / (z_0 * ... * z_{W-1})
@@ -258,11 +269,11 @@ __global__ void __launch_bounds__(64) k_table_normalise(const xyzz* __restrict__
       a.x = fq_zero();
       a.y = fq_zero();
     } else {
-      fq z = fq_mul(p.ZZ, p.ZZZ);
-      fq iz = w > 0 ? fq_mul(inv, pre[w - 1]) : inv;  // 1 / z_w
-      inv = fq_mul(inv, z);                            // drop z_w from the running inverse
-      a.x = fq_reduce_full(fq_mul(p.X, fq_mul(iz, p.ZZZ)));
-      a.y = fq_reduce_full(fq_mul(p.Y, fq_mul(iz, p.ZZ)));
+      fq z = MP_TN_MUL(MODE, p.ZZ, p.ZZZ);
+      fq iz = w > 0 ? MP_TN_MUL(MODE, inv, pre[w - 1]) : inv;  // 1 / z_w
+      inv = MP_TN_MUL(MODE, inv, z);                            // drop z_w from the running inverse
+      a.x = fq_reduce_full(MP_TN_MUL(MODE, p.X, MP_TN_MUL(MODE, iz, p.ZZZ)));
+      a.y = fq_reduce_full(MP_TN_MUL(MODE, p.Y, MP_TN_MUL(MODE, iz, p.ZZ)));
     }
     uint4* d = reinterpret_cast<uint4*>(table + (size_t)w * nb + first + i);
     const uint4* s = reinterpret_cast<const uint4*>(&a);
@@ -294,9 +305,15 @@ cudaError_t msm_build_table(MsmWorkspace* ws, const affine* d_bases, uint32_t nb
   xyzz* tmp;
   MP_CK(ws->get(13, (size_t)W * count, &tmp));
   k_table_shift<<<(count + 63) / 64, 64, 0, stream>>>(d_bases, nb, first, count, c, W, tmp);
-  static const bool trick = [] { const char* e = getenv("MP_TABLE_TRICK"); return e ? atoi(e) != 0 : kFqLimbs <= 8; }();
-  if (trick)
-    k_table_normalise<<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
+  static const int trick = [] { const char* e = getenv("MP_TABLE_TRICK"); return e ? atoi(e) : (kFqLimbs <= 8 ? 1 : 0); }();
+  if (trick == 2) {
+    fq* pre;
+    MP_CK(ws->get(15, (size_t)count * kMaxTableWindows, &pre));
+    k_table_normalise<1><<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table, pre);
+  } else if (trick == 3)
+    k_table_normalise<2><<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table, nullptr);
+  else if (trick)
+    k_table_normalise<0><<<(count + 63) / 64, 64, 0, stream>>>(tmp, nb, first, count, W, d_table, nullptr);
   else
     k_table_normalise_each<<<(unsigned)(((uint64_t)W * count + 63) / 64), 64, 0, stream>>>(tmp, nb, first, count, W, d_table);
   return cudaGetLastError();
@@ -714,12 +731,37 @@ __global__ void __launch_bounds__(64) k_reduce_group(const xyzz* __restrict__ se
 }
 
 // block-wide sum of one xyzz per thread (kWinThreads threads); result valid in thread 0
-__device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem /* kWinThreads/32 entries */) {
+// MODE (experiment knob of k_reduce_win, see scripts/sanitize.sh): 0 = divergent call after the shuffle (as
+// written in round 1); 1 = the same + __syncwarp() after the call; 2 = every lane makes the call (lanes that
+// must not add pass the identity); 3 = exchange through shared memory instead of shuffles.
+template <int MODE>
+__device__ __forceinline__ void lane_add(xyzz& v, const xyzz& o, bool take) {
+  if (MODE == 2) {
+    xyzz q = take ? o : xyzz_identity();
+    xyzz_add_ni(v, q);
+  } else {
+    if (take) xyzz_add_ni(v, o);
+    if (MODE == 1) __syncwarp();
+  }
+}
+template <int MODE>
+__device__ __forceinline__ xyzz lane_down(const xyzz& v, int delta, xyzz* xch /* [kWinThreads] or null */) {
+  if (MODE == 3) {
+    __syncthreads();
+    xch[threadIdx.x] = v;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    return lane + delta < 32 ? xch[threadIdx.x + delta] : v;  // out of range: own value, like shfl.down
+  }
+  return xyzz_shfl_down(v, delta);
+}
+template <int MODE>
+__device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem /* kWinThreads/32 entries */, xyzz* xch) {
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
   for (int d = 16; d >= 1; d >>= 1) {
-    xyzz o = xyzz_shfl_down(v, d);
-    if (lane < d) xyzz_add_ni(v, o);
+    xyzz o = lane_down<MODE>(v, d, xch);
+    lane_add<MODE>(v, o, lane < d);
   }
   __syncthreads();
   if (lane == 0) smem[warp] = v;
@@ -733,11 +775,13 @@ __device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem /* kWinThreads/32 entries */) 
 
 // Block per (window, comp):  out = sum_s T_s + L * sum_s s * S_s.
 // sum_s s*S_s = sum_{i>=0} Suf_A(i) with A[i] = S_{i+1}: block-wide suffix scan.
+template <int MODE>
 __global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restrict__ segS,
                                                             const xyzz* __restrict__ segT,
                                                             uint32_t nseg, uint32_t L, int ncomp,
-                                                            xyzz* __restrict__ win_out) {
+                                                            xyzz* __restrict__ win_out, xyzz* __restrict__ xch_all) {
   __shared__ xyzz smem[kWinThreads / 32];
+  xyzz* xch = MODE == 3 ? xch_all + (size_t)blockIdx.x * kWinThreads : nullptr;  // global scratch stands in for smem
   const uint32_t comp = blockIdx.x % ncomp;
   const uint64_t win = blockIdx.x / ncomp;
   const xyzz* S = segS + win * nseg * ncomp + comp;
@@ -762,11 +806,11 @@ __global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restri
   xyzz inc = run;
 #pragma unroll 1
   for (int d = 1; d < 32; d <<= 1) {
-    xyzz o = xyzz_shfl_down(inc, d);
-    if (lane + d < 32) xyzz_add_ni(inc, o);
+    xyzz o = lane_down<MODE>(inc, d, xch);
+    lane_add<MODE>(inc, o, lane + d < 32);
   }
   if (lane == 0) smem[warp] = inc;  // warp total
-  xyzz above = xyzz_shfl_down(inc, 1);
+  xyzz above = lane_down<MODE>(inc, 1, xch);
   if (lane == 31) above = xyzz_identity();
   __syncthreads();
   for (int w = warp + 1; w < kWinThreads / 32; w++) xyzz_add_ni(above, smem[w]);
@@ -774,8 +818,8 @@ __global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restri
   // U_t = lsum + ipt * above
   for (uint32_t k = 1; k < ipt; k <<= 1) xyzz_dbl_ni(above);
   xyzz_add_ni(lsum, above);
-  xyzz U = block_sum_xyzz(lsum, smem);
-  xyzz Tt = block_sum_xyzz(tsum, smem);
+  xyzz U = block_sum_xyzz<MODE>(lsum, smem, xch);
+  xyzz Tt = block_sum_xyzz<MODE>(tsum, smem, xch);
   if (threadIdx.x == 0) {
     for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(U);
     xyzz_add_ni(Tt, U);
@@ -983,7 +1027,14 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
   } else if (nseg <= 32) {
     k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
   } else {
-    k_reduce_win<<<(unsigned)(nwin * ncomp), kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out);
+    static const int win_mode = [] { const char* e = getenv("MP_WIN_BLOCK"); return e ? atoi(e) : 0; }();
+    xyzz* xch = nullptr;
+    if (win_mode == 4) MP_CK(ws->get(14, nwin * ncomp * (size_t)kWinThreads, &xch));
+    const unsigned wb = (unsigned)(nwin * ncomp);
+    if (win_mode == 2) k_reduce_win<1><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
+    else if (win_mode == 3) k_reduce_win<2><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
+    else if (win_mode == 4) k_reduce_win<3><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
+    else k_reduce_win<0><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
   }
   k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, Wb, c, ncomp, d_out);
   ws->launches += 3;

@@ -2,11 +2,13 @@
 logs for the 2^20-term MSM, prove -> verify round trips and the reference's negative case on a
 2^16-card deck, window-range split == single launch."""
 import ctypes
+import os
 import random
 
 import numpy as np
 import pytest
 
+from oracle import c_oracle
 from oracle.py import stark
 from _util import b32, pb
 
@@ -53,18 +55,36 @@ def test_msm_2p20_known_discrete_logs(ctx, pkg):
     assert ctx.msm_g1(points, scs, 0) == want
 
 
-def test_shuffle_2p16_round_trip_and_negative(ctx, pkg, monkeypatch):
-    m, n = 128, 512
+def make_big_instance(ctx, m, n, seed):
+    """Synthetic instance with every point generated on the GPU (s*G for seeded scalars s)."""
     Nc = m * n
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(seed)
     npts = (n + 3) + 2 * Nc
     pts = ctx.dbg_scalar_mul(G64 * npts, rand_scalars(rng, npts))
     P = lambda i: pts[64 * i:64 * (i + 1)]
-    ck_g, ck_h, ghat, pk, deck = pts[:64 * n], P(n), P(n + 1), P(n + 2), pts[64 * (n + 3):]
-    perm = [int(v) for v in rng.permutation(Nc)]
-    rho, rand = rand_scalars(rng, Nc), rand_scalars(rng, 11 * m + 5 * n)
-    ctx.set_params(m, n, G64, ck_g, ck_h, ghat)
-    deck2, proof = ctx.shuffle_and_remask(pk, deck, perm, rho, rand)
+    return dict(m=m, n=n, N=Nc, ck_g=pts[:64 * n], ck_h=P(n), ghat=P(n + 1), pk=P(n + 2), deck=pts[64 * (n + 3):],
+                perm=[int(v) for v in rng.permutation(Nc)], rho=rand_scalars(rng, Nc), rand=rand_scalars(rng, 11 * m + 5 * n))
+
+
+@pytest.fixture(scope="module")
+def headline(ctx):
+    """BASELINE.json's headline configuration: one 2^16-card deck at (m, n) = (128, 512), proved once on
+    the GPU through the host-buffer C ABI.  Shared by the tests below."""
+    inst = make_big_instance(ctx, 128, 512, 5)
+    ctx.set_params(128, 512, G64, inst["ck_g"], inst["ck_h"], inst["ghat"])
+    inst["deck2"], inst["proof"] = ctx.shuffle_and_remask(inst["pk"], inst["deck"], inst["perm"], inst["rho"], inst["rand"])
+    return inst
+
+
+def oracle_args(inst):
+    return (inst["m"], inst["n"], G64, inst["ck_g"], inst["ck_h"], inst["ghat"], inst["pk"])
+
+
+def test_shuffle_2p16_round_trip_and_negative(ctx, pkg, headline, monkeypatch):
+    inst = headline
+    m, n, Nc = inst["m"], inst["n"], inst["N"]
+    pk, deck, perm, rho, rand, deck2, proof = (inst[k] for k in ("pk", "deck", "perm", "rho", "rand", "deck2", "proof"))
+    ctx.set_params(m, n, G64, inst["ck_g"], inst["ck_h"], inst["ghat"])
     assert ctx.verify_shuffle(pk, deck, deck2, proof) == 0
     # remask semantics on a sample of cards: out[i] - deck[perm[i]] == rho_i * (g, pk)
     rho_i = ints(rho)
@@ -93,6 +113,90 @@ def test_shuffle_2p16_round_trip_and_negative(ctx, pkg, monkeypatch):
     bad = bytearray(proof)
     bad[-1 - 32 * 3] ^= 1
     assert ctx.verify_shuffle(pk, deck, deck2, bytes(bad)) == 4
+
+
+def test_shuffle_2p16_gpu_proof_against_the_c_oracle(ctx, headline):
+    """The headline configuration against the ORACLE, not against the CUDA path itself: the C restatement
+    (all host threads, Pippenger for its big sums) accepts the GPU's (128, 512) proof -- which checks every
+    one of the 1 416 proof points and 2 569 scalars, the 7-level Karatsuba plan included, through the
+    oracle's own transcript and equations -- and both verifiers give the same verdict on the reference's
+    negative case (tests.rs:213-226) and on tampered proofs."""
+    inst = headline
+    co = c_oracle.COracle(threads=os.cpu_count() or 1, msm_mode=1)
+    a = oracle_args(inst)
+    pk, deck, deck2, proof = inst["pk"], inst["deck"], inst["deck2"], inst["proof"]
+    ctx.set_params(inst["m"], inst["n"], G64, inst["ck_g"], inst["ck_h"], inst["ghat"])
+    assert deck2 == co.remask(G64, pk, deck, inst["perm"], inst["rho"])
+    assert co.verify(*a, deck, deck2, proof) == 0
+    wrong = deck[128:] + deck[:128]
+    tampered = []
+    m, n = inst["m"], inst["n"]
+    f1 = 64 * (5 * m + 4)                       # proof layout: points | 2n+3 scalars | 3 points | 2n+2 scalars | 6m+1 points | n+4 scalars
+    f2 = f1 + 32 * (2 * n + 3) + 64 * 3
+    f3 = f2 + 32 * (2 * n + 2) + 64 * (6 * m + 1)
+    assert f3 + 32 * (n + 4) == len(proof)
+    for off in (f1 + 7, f1 + 32 * (n + 1) + 3, f2 + 32 * 5 + 1, f2 + 32 * (2 * n + 1), f3 + 32 * 2 + 9, len(proof) - 1 - 32 * 3):
+        bad = bytearray(proof)
+        bad[off] ^= 1
+        tampered.append(bytes(bad))
+    sw = bytearray(proof)                      # two proof points exchanged (both still on the curve)
+    sw[0:64], sw[64:128] = proof[64:128], proof[0:64]
+    tampered.append(bytes(sw))
+    seen = set()
+    for d2, pr in [(wrong, proof)] + [(deck2, t) for t in tampered]:
+        want = co.verify(*a, deck, d2, pr)
+        got = ctx.verify_shuffle(pk, deck, d2, pr)
+        assert got == want != 0
+        seen.add(got)
+    assert 1 in seen and len(seen) >= 2
+
+
+def test_shuffle_2p16_resident_entry_points(ctx, pkg, headline):
+    """mp_shuffle_and_remask_resident / mp_shuffle_verify_resident / mp_shuffle_prove_resident -- the entry
+    points bench.py's `value` times -- give the bytes of the host-buffer path (which the test above checks
+    against the oracle) and the same verdicts."""
+    import torch
+    inst = headline
+    lib = pkg.lib
+    m, n, Nc = inst["m"], inst["n"], inst["N"]
+    pk, deck, deck2, proof = inst["pk"], inst["deck"], inst["deck2"], inst["proof"]
+    ctx.set_params(m, n, G64, inst["ck_g"], inst["ck_h"], inst["ghat"])
+    dev = torch.device("cuda:0")
+    d_deck = torch.frombuffer(bytearray(deck), dtype=torch.uint8).to(dev)
+    d_deck2 = torch.frombuffer(bytearray(deck2), dtype=torch.uint8).to(dev)
+    perm_arr = (ctypes.c_uint32 * Nc)(*inst["perm"])
+    out_deck = ctypes.create_string_buffer(128 * Nc)
+    out_proof = ctypes.create_string_buffer(lib.mp_proof_len(m, n))
+    pkg.check(ctx.h, lib.mp_shuffle_and_remask_resident(ctx.h, pk, deck, perm_arr, inst["rho"], inst["rand"], out_deck, out_proof,
+                                                        d_deck.data_ptr()))
+    assert out_deck.raw == deck2 and out_proof.raw == proof
+    out_proof2 = ctypes.create_string_buffer(lib.mp_proof_len(m, n))
+    pkg.check(ctx.h, lib.mp_shuffle_prove_resident(ctx.h, pk, deck, deck2, perm_arr, inst["rho"], inst["rand"], out_proof2,
+                                                   d_deck2.data_ptr()))
+    assert out_proof2.raw == proof
+    assert lib.mp_shuffle_verify_resident(ctx.h, pk, deck, deck2, proof, d_deck.data_ptr(), d_deck2.data_ptr()) == 0
+    wrong = deck[128:] + deck[:128]
+    d_wrong = torch.frombuffer(bytearray(wrong), dtype=torch.uint8).to(dev)
+    assert lib.mp_shuffle_verify_resident(ctx.h, pk, deck, wrong, proof, d_deck.data_ptr(), d_wrong.data_ptr()) == 1
+    bad = bytearray(proof)
+    bad[-1 - 32 * 3] ^= 1
+    assert lib.mp_shuffle_verify_resident(ctx.h, pk, deck, deck2, bytes(bad), d_deck.data_ptr(), d_deck2.data_ptr()) == 4
+
+
+@pytest.mark.parametrize("m,n,seed", [(64, 128, 21), (128, 512, 5)])
+def test_large_deck_proof_is_byte_exact_vs_c_oracle(ctx, m, n, seed, request):
+    """Byte-for-byte proof parity on the large-deck code path (device scalar kernels, Karatsuba diagonal plan
+    with 6 levels at m = 64 and 7 levels / 2 187 leaves at m = 128 -- the headline configuration itself),
+    against the C restatement's prover on all host threads (about 10 s and 1.5-3 min)."""
+    if (m, n) == (128, 512):
+        inst = request.getfixturevalue("headline")
+    else:
+        inst = make_big_instance(ctx, m, n, seed)
+        ctx.set_params(m, n, G64, inst["ck_g"], inst["ck_h"], inst["ghat"])
+        inst["deck2"], inst["proof"] = ctx.shuffle_and_remask(inst["pk"], inst["deck"], inst["perm"], inst["rho"], inst["rand"])
+    co = c_oracle.COracle(threads=os.cpu_count() or 1, msm_mode=1)
+    want = co.prove(*oracle_args(inst), inst["deck"], inst["deck2"], inst["perm"], inst["rho"], inst["rand"])
+    assert inst["proof"] == want
 
 
 def test_usage_errors(ctx, pkg):
