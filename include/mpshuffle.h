@@ -75,6 +75,15 @@ int32_t mp_msm_g1(mp_ctx* ctx, const uint8_t* bases /* n*64 */, const uint8_t* s
 /* Ciphertext MSM: out = sum_i scalars[i] * deck[i] component-wise (2 G1 MSMs sharing digits). */
 int32_t mp_ct_msm(mp_ctx* ctx, const uint8_t* deck /* n*128 */, const uint8_t* scalars /* n*32 */,
                   uint64_t n, int32_t window_bits, uint8_t* out /* 128 */);
+/* Batch of MSMs over one point array and one scalar array -- SURVEY.md section 8(b)'s
+ * `mp_msm_batch_shared_bases`, the surface of `MultiExponentiationArgument` named in BASELINE.json: its diagonal
+ * products are m(m+1) inner products <row of n ciphertexts, row of n scalars> (reference call site
+ * mod.rs:409-415), evaluated here by ONE launch sequence:
+ *   out[j] = sum_{t < len_j} scalars[scalar_off_j + t] * points[point_off_j + t]       (per component)
+ * jobs = njobs x (scalar_off, point_off, len) as uint32; ncomp = 1 (64-byte points) or 2 (128-byte ciphertexts);
+ * out = njobs * ncomp * 64 bytes.  Jobs may overlap and share points or scalars. */
+int32_t mp_msm_jobs(mp_ctx* ctx, const uint8_t* points, uint64_t n_points, int32_t ncomp, const uint8_t* scalars,
+                    uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs, int32_t window_bits, uint8_t* out);
 /* Same with device-resident inputs/outputs (canonical byte layout), asynchronous. */
 int32_t mp_msm_g1_device(mp_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
                          int32_t window_bits, void* d_out);
@@ -183,6 +192,21 @@ int32_t mp_shuffle_and_remask_resident(mp_ctx* ctx, const uint8_t* pk, const uin
 int32_t mp_shuffle_prove_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
                                   const uint8_t* shuffled_deck, const uint32_t* perm, const uint8_t* rho,
                                   const uint8_t* randomness, uint8_t* proof_out, const void* d_shuffled_deck);
+
+/* The two batch entry points with the decks ALREADY resident in HBM (d_decks / d_shuffled_decks = device
+ * pointers to batch * N * 128 canonical bytes, same layout as the host buffers).  The device copies are used
+ * for decks above the small-deck threshold (8 192 cards), where the batch runs the single-proof path on a few
+ * worker contexts so that one deck's serial statement hash (host) overlaps the other decks' kernels (device);
+ * smaller decks are staged from the host buffers (a few KB each).  Proofs and verdicts are identical to the
+ * host-buffer calls.  bench.py's `value` is measured through these two. */
+int32_t mp_shuffle_and_remask_batch_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                                             const uint8_t* rhos, const uint8_t* randomness, uint64_t batch,
+                                             uint8_t* out_decks, uint8_t* proofs, int32_t host_threads,
+                                             const void* d_decks);
+int32_t mp_shuffle_verify_batch_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks,
+                                         const uint8_t* shuffled_decks, const uint8_t* proofs, uint64_t batch,
+                                         int32_t* statuses, int32_t host_threads, const void* d_decks,
+                                         const void* d_shuffled_decks);
 
 /* ---- batched sigma protocols either side of the shuffle -----------
  * n independent items per call; item i uses the i-th entry of every array.  The generator g is the

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mp_last_kernel_launches": (_i32, [_vp]),
     "mp_msm_g1": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
     "mp_ct_msm": (_i32, [_vp, _cp, _cp, _u64, _i32, _cp]),
+    "mp_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, _vp, _u64, _i32, _cp]),
     "mp_msm_g1_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp_ct_msm_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "mp_msm_num_windows": (_i32, [_i32]),
@@ -43,6 +44,8 @@ SIGNATURES = {
     "mp_shuffle_verify": (_i32, [_vp, _cp, _cp, _cp, _cp]),
     "mp_shuffle_and_remask_batch": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _u64, _cp, _cp, _i32]),
     "mp_shuffle_verify_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp_shuffle_and_remask_batch_resident": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _u64, _cp, _cp, _i32, _vp]),
+    "mp_shuffle_verify_batch_resident": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32, _vp, _vp]),
     "mp_shuffle_verify_resident": (_i32, [_vp, _cp, _cp, _cp, _cp, _vp, _vp]),
     "mp_shuffle_and_remask_resident": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp, _vp]),
     "mp_shuffle_prove_resident": (_i32, [_vp, _cp, _cp, _cp, _vp, _cp, _cp, _cp, _vp]),
@@ -139,6 +142,15 @@ class Context:
         out = ctypes.create_string_buffer(128)
         check(self.h, lib.mp_ct_msm(self.h, deck, scalars, n, window_bits, out))
         return out.raw
+
+    def msm_jobs(self, points: bytes, scalars: bytes, jobs, ncomp=1, window_bits=0) -> bytes:
+        """jobs: list of (scalar_off, point_off, len).  -> len(jobs) * ncomp points (MultiExponentiationArgument's
+        batched inner products; SURVEY.md 8(b) mp_msm_batch_shared_bases)"""
+        flat = (ctypes.c_uint32 * (3 * len(jobs)))(*[v for j in jobs for v in j])
+        out = ctypes.create_string_buffer(64 * ncomp * max(len(jobs), 1))
+        check(self.h, lib.mp_msm_jobs(self.h, points, len(points) // (64 * ncomp), ncomp, scalars, len(scalars) // 32,
+                                      flat, len(jobs), window_bits, out))
+        return out.raw[:64 * ncomp * len(jobs)]
 
     # --- MSM (device pointers, asynchronous on self.stream)
     def msm_g1_device(self, d_bases, d_scalars, n, d_out, window_bits=0):

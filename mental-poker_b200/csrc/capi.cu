@@ -193,6 +193,60 @@ extern "C" int32_t mp_ct_msm_device(mp_ctx* ctx, const void* d_deck, const void*
   return msm_device_common(ctx, d_deck, d_scalars, n, 2, window_bits, d_out);
 }
 
+// K2 of SURVEY.md section 2b / `mp_msm_batch_shared_bases` of section 8(b): a batch of MSMs over ONE point array
+// and ONE scalar array -- job j = sum_{t < len_j} scalars[scalar_off_j + t] * points[point_off_j + t] -- in one
+// launch sequence (one digit pass, one sort, one accumulation for all jobs).  The multi-exponentiation argument's
+// diagonal products are m(m+1) such jobs over the rows of the shuffled deck (reference call site mod.rs:409-415
+// -> MultiExponentiationArgument).  jobs: njobs x (scalar_off, point_off, len) as uint32.  out: njobs * ncomp points.
+extern "C" int32_t mp_msm_jobs(mp_ctx* ctx, const uint8_t* points, uint64_t n_points, int32_t ncomp, const uint8_t* scalars,
+                               uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs, int32_t window_bits, uint8_t* out) {
+  if (!ctx || !jobs || !out || (!points && n_points) || (!scalars && n_scalars)) return MP_ERR_INVALID_ARG;
+  if (ncomp != 1 && ncomp != 2) return ctx->fail(MP_ERR_INVALID_ARG, "ncomp must be 1 (G1) or 2 (ciphertexts)");
+  if (njobs == 0) return MP_OK;
+  if (njobs >= (1u << 24) || n_points >= (1ull << 31) || n_scalars >= (1ull << 31))
+    return ctx->fail(MP_ERR_INVALID_ARG, "batch too large");
+  static_assert(sizeof(MsmJob) == 12, "MsmJob is three uint32");
+  std::vector<MsmJob> h_jobs(njobs);
+  uint64_t total = 0;
+  for (uint64_t j = 0; j < njobs; j++) {
+    h_jobs[j] = MsmJob{jobs[3 * j], jobs[3 * j + 1], jobs[3 * j + 2]};
+    if ((uint64_t)h_jobs[j].scalar_off + h_jobs[j].len > n_scalars || (uint64_t)h_jobs[j].point_off + h_jobs[j].len > n_points)
+      return ctx->fail(MP_ERR_INVALID_ARG, "job %llu reaches outside the arrays", (unsigned long long)j);
+    total += h_jobs[j].len;
+  }
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  const int c = window_bits > 0 ? window_bits : msm_pick_window(total / njobs, njobs);
+  if (c < 2 || c > 16) return ctx->fail(MP_ERR_INVALID_ARG, "window_bits %d out of range [2,16]", c);
+  ctx->last_window = c;
+  const size_t pbytes = (size_t)n_points * 64 * ncomp, sbytes = (size_t)n_scalars * 32;
+  uint8_t* d_in = (uint8_t*)ctx->scratch(mp_ctx::kSlotStageIn, pbytes + sbytes + 256);
+  affine* mont = (affine*)ctx->scratch(mp_ctx::kSlotPointsMont, sizeof(affine) * n_points * ncomp);
+  xyzz* res = (xyzz*)ctx->scratch(mp_ctx::kSlotMsmOut, sizeof(xyzz) * njobs * ncomp);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(mp_ctx::kSlotStageOut, 64 * njobs * ncomp);
+  int* bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  if (!d_in || !mont || !res || !d_out || !bad) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  cudaError_t e;
+  if (pbytes && (e = cudaMemcpyAsync(d_in, points, pbytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "H2D points");
+  if (sbytes && (e = cudaMemcpyAsync(d_in + pbytes, scalars, sbytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "H2D scalars");
+  if ((e = cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "memset");
+  if ((e = points_to_mont((const uint32_t*)d_in, mont, n_points * ncomp, bad, ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "points_to_mont");
+  ctx->launches += n_points ? 1 : 0;
+  if ((e = msm_run(ctx->ws, (const uint32_t*)(d_in + pbytes), n_scalars, mont, ncomp, h_jobs.data(), (int)njobs, c, res, ctx->stream)) != cudaSuccess)
+    return ctx->cuda_fail(e, "msm_run (jobs)");
+  ctx->launches += msm_last_launches(ctx->ws);
+  if ((e = xyzz_to_canonical(res, (uint32_t*)d_out, njobs * ncomp, ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "xyzz_to_canonical");
+  ctx->launches += 1;
+  int h_bad = 0;
+  if ((e = cudaMemcpyAsync(out, d_out, 64 * njobs * ncomp, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "D2H results");
+  if ((e = cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "D2H flag");
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return ctx->cuda_fail(e, "MSM jobs");
+  if (h_bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of the Stark curve");
+  ctx->last_ec_adds = 0;
+  for (auto& j : h_jobs) ctx->last_ec_adds += scheduled_ec_adds(j.len, c, ncomp);
+  return MP_OK;
+}
+
 extern "C" int32_t mp_profile_enable(mp_ctx* ctx, int32_t on) {
   if (!ctx) return MP_ERR_INVALID_ARG;
   msm_profile_enable(ctx->ws, on != 0);
@@ -294,6 +348,18 @@ extern "C" int32_t mp_shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const
                                            const uint8_t* shuffled_decks, const uint8_t* proofs, uint64_t batch,
                                            int32_t* statuses, int32_t host_threads) {
   return shuffle_verify_batch(ctx, pk, decks, shuffled_decks, proofs, batch, statuses, host_threads);
+}
+extern "C" int32_t mp_shuffle_and_remask_batch_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                                                        const uint8_t* rhos, const uint8_t* randomness, uint64_t batch,
+                                                        uint8_t* out_decks, uint8_t* proofs, int32_t host_threads,
+                                                        const void* d_decks) {
+  return shuffle_prove_batch(ctx, pk, decks, perms, rhos, randomness, batch, out_decks, proofs, host_threads, d_decks);
+}
+extern "C" int32_t mp_shuffle_verify_batch_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks,
+                                                    const uint8_t* shuffled_decks, const uint8_t* proofs, uint64_t batch,
+                                                    int32_t* statuses, int32_t host_threads, const void* d_decks,
+                                                    const void* d_shuffled_decks) {
+  return shuffle_verify_batch(ctx, pk, decks, shuffled_decks, proofs, batch, statuses, host_threads, d_decks, d_shuffled_decks);
 }
 extern "C" int32_t mp_shuffle_verify_resident(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck,
                                               const uint8_t* shuffled_deck, const uint8_t* proof, const void* d_deck,

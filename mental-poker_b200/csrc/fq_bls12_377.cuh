@@ -484,17 +484,16 @@ MP_HD fq fq_mul_inline(const fq& a, const fq& b) {
 // times into a mixed addition the accumulate loop would be 200 KB of straight-line code and run out of the
 // instruction cache (measured: the inlined form reached 0.86 G additions/s, a third of what its IMAD.WIDE
 // count allows).  The call passes 24 + 12 words through the ABI -- under 5 % of the body.
-static __device__ __noinline__ void fq_mul_call(fq* r, const fq* a, const fq* b) {
-  const fq x = *a, y = *b;  // operands into registers before anything is written: r may alias a or b
-  const fq z = fq_mul_inline(x, y);
-  *r = z;
-}
+// Operands and result travel BY VALUE.  The round-1 form took three pointers (fq* r, const fq* a, const fq* b);
+// with it the NVVM optimiser merged the stack slot of a loop-carried accumulator with the slot of an unrelated
+// product -- PTX of `z = fq_mul(p.ZZ, p.ZZZ); acc = fq_mul(acc, z);` read `call fq_mul_call(%rd27, %rd27, %rd27)`,
+// i.e. acc = z * z -- which is what broke k_table_normalise and k_reduce_win on this build (DESIGN.md section 16,
+// scripts/repro/).  Values have no address to merge.
+static __device__ __noinline__ fq fq_mul_call(const fq a, const fq b) { return fq_mul_inline(a, b); }
 #endif
 MP_HD fq fq_mul(const fq& a, const fq& b) {
 #ifdef __CUDA_ARCH__
-  fq r;
-  fq_mul_call(&r, &a, &b);
-  return r;
+  return fq_mul_call(a, b);
 #else
   return fq_mul_inline(a, b);
 #endif

@@ -122,8 +122,15 @@ int msm_pick_window(uint64_t avg_len, uint64_t njobs) {
 // ------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void xyzz_add_ni(xyzz& acc, const xyzz& q) { xyzz_add(acc, q); }
-__device__ __noinline__ void xyzz_dbl_ni(xyzz& acc) { acc = xyzz_dbl(acc); }
+// Out-of-line group operations for the latency-bound tail kernels (one copy of the 14-multiplication addition per
+// kernel instead of one per call site).  Operands and result travel BY VALUE: the round-1 helpers took references
+// (xyzz& acc, const xyzz& q), and NVVM's stack-slot merging of address-taken, loop-carried structs passed to
+// __noinline__ functions produced wrong code on the 12-limb build (see fq_bls12_377.cuh fq_mul_call and
+// DESIGN.md section 16) -- values have no address to merge.
+__device__ __noinline__ xyzz xyzz_add_v(const xyzz acc, const xyzz q) { xyzz r = acc; xyzz_add(r, q); return r; }
+__device__ __noinline__ xyzz xyzz_dbl_v(const xyzz acc) { return xyzz_dbl(acc); }
+#define xyzz_add_ni(acc, q) ((acc) = xyzz_add_v((acc), (q)))
+#define xyzz_dbl_ni(acc) ((acc) = xyzz_dbl_v((acc)))
 
 __device__ __forceinline__ xyzz xyzz_load(const xyzz* p) {
   xyzz r;

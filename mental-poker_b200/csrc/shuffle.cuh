@@ -50,8 +50,10 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
                        const uint8_t* proof, const void* deck_src = nullptr, const void* deck2_src = nullptr);
 
 // B independent proofs under the same parameters and public key, verified in lockstep.
+// (d_decks / d_decks2: optional device copies of the decks, B * N * 128 bytes each, used by the large-deck path)
 int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
-                             const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads);
+                             const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads,
+                             const void* d_decks = nullptr, const void* d_decks2 = nullptr);
 
 // Batched sigma protocols either side of the shuffle (sigma.cu)
 int32_t sigma_mask_batch(mp_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* r, const uint8_t* omega,
@@ -80,6 +82,6 @@ int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t*
 bool shuffle_uses_small_deck_path(uint64_t n_cards);
 int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                             const uint8_t* rhos, const uint8_t* rands, uint64_t B, uint8_t* out_decks,
-                            uint8_t* proofs, int32_t host_threads);
+                            uint8_t* proofs, int32_t host_threads, const void* d_decks = nullptr);
 
 }  // namespace mp

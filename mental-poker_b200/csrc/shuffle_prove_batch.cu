@@ -391,7 +391,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
 
 int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                             const uint8_t* rhos, const uint8_t* rands, uint64_t B, uint8_t* out_decks,
-                            uint8_t* proofs, int32_t host_threads) {
+                            uint8_t* proofs, int32_t host_threads, const void* d_decks) {
   if (!ctx || !pk || (B && (!decks || !perms || !rhos || !rands || !out_decks || !proofs))) return MP_ERR_INVALID_ARG;
   ShuffleState* S = ctx->shuffle;
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
@@ -425,7 +425,7 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
     const void* d_shuffled = nullptr;
     Transcript fs;
     int32_t st = shuffle_remask(w, pk, decks + i * N * 128, perms + i * N, rhos + i * N * 32, N, out_decks + i * N * 128,
-                                nullptr, &d_shuffled, &fs);
+                                d_decks ? (const uint8_t*)d_decks + i * N * 128 : nullptr, &d_shuffled, &fs);
     int l = w->launches;
     if (st == MP_OK) {
       st = shuffle_prove(w, pk, decks + i * N * 128, out_decks + i * N * 128, perms + i * N, rhos + i * N * 32,

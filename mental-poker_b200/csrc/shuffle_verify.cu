@@ -257,7 +257,8 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
 }
 
 int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
-                             const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads) {
+                             const uint8_t* proofs, uint64_t B, int32_t* statuses, int32_t host_threads,
+                             const void* d_decks, const void* d_decks2) {
   if (!ctx || !pk || (B && (!decks || !decks2 || !proofs || !statuses))) return MP_ERR_INVALID_ARG;
   ShuffleState* S = ctx->shuffle;
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
@@ -271,7 +272,9 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
     int P = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
     P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, 8, B}));
     return run_on_workers(ctx, P, B, [&](mp_ctx* w, uint64_t p) {
-      int32_t st = shuffle_verify(w, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen);
+      int32_t st = shuffle_verify(w, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen,
+                                  d_decks ? (const uint8_t*)d_decks + p * N * 128 : nullptr,
+                                  d_decks2 ? (const uint8_t*)d_decks2 + p * N * 128 : nullptr);
       if (st >= 0) statuses[p] = st;
       return st < 0 ? st : MP_OK;
     });

@@ -877,6 +877,23 @@ int oc_msm(const uint8_t* points, const uint8_t* scalars, uint64_t n, int ncomp,
   free(p); free(k);
   return 0;
 }
+/* out[i] = scalars[i] * base  (builds synthetic instances for the full-size CPU legs of bench.py and the tests) */
+int oc_scalar_mul_batch(const uint8_t* base, const uint8_t* scalars, uint64_t n, uint8_t* out) {
+  oracle_init();
+  aff b;
+  aff_from_bytes64(&b, base);
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1)
+  for (uint64_t i = 0; i < n; i++) {
+    fe r;
+    fe_from_bytes(&r, scalars + 32 * i, &FR);
+    jac j;
+    aff_mul(&j, &b, &r);
+    aff a;
+    jac_to_aff(&a, &j);
+    aff_to_bytes64(out + 64 * i, &a);
+  }
+  return 0;
+}
 int oc_on_curve(const uint8_t* point) { oracle_init(); aff a; aff_from_bytes64(&a, point); return aff_on_curve(&a); }
 int oc_pedersen_commit(int n, const uint8_t* ck_g, const uint8_t* ck_h, const uint8_t* values, int len, const uint8_t* r,
                        uint8_t* out) {

@@ -19,6 +19,7 @@ def load():
     lib = ctypes.CDLL(_SO)
     cp, u64, i32, vp = ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p
     lib.oc_msm.argtypes = [cp, cp, u64, i32, i32, cp]
+    lib.oc_scalar_mul_batch.argtypes = [cp, cp, u64, cp]
     lib.oc_remask.argtypes = [cp, cp, cp, vp, cp, u64, cp]
     lib.oc_shuffle_prove.argtypes = [i32, i32, cp, cp, cp, cp, cp, cp, cp, vp, cp, cp, cp]
     lib.oc_shuffle_verify.argtypes = [i32, i32, cp, cp, cp, cp, cp, cp, cp, cp]
@@ -68,6 +69,13 @@ class COracle:
         n = len(scalars) // 32
         out = ctypes.create_string_buffer(64 * ncomp)
         self.lib.oc_msm(points, scalars, n, ncomp, mode, out)
+        return out.raw
+
+    def scalar_mul_batch(self, base, scalars):
+        """-> scalars[i] * base for every 32-byte scalar (synthetic-instance generator, all threads)"""
+        n = len(scalars) // 32
+        out = ctypes.create_string_buffer(64 * n)
+        self.lib.oc_scalar_mul_batch(base, scalars, n, out)
         return out.raw
 
     def remask(self, enc_g, pk, deck, perm, rho):
