@@ -51,7 +51,9 @@ static __device__ __forceinline__ affine ld_affine(const affine* p) {
   for (int i = 0; i < 4; i++) d[i] = __ldg(s + i);
   return r;
 }
-static __device__ __noinline__ void xyzz_add_call(xyzz& acc, const xyzz& q) { xyzz_add(acc, q); }
+// by value: see msm.cu xyzz_add_v (NVVM merges stack slots of by-pointer noinline arguments)
+static __device__ __noinline__ xyzz xyzz_add_val(const xyzz acc, const xyzz q) { xyzz r = acc; xyzz_add(r, q); return r; }
+#define xyzz_add_call(acc, q) ((acc) = xyzz_add_val((acc), (q)))
 
 // Block b: leaf = b / chunks, 128 consecutive (column, component) slots of that leaf's row.  Rows of
 // the deck are 2n consecutive affine points, so a warp reads 32 consecutive 64-byte records per step.

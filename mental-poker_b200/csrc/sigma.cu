@@ -71,9 +71,14 @@ __device__ __forceinline__ affine ld_point(const affine* p) {
   for (int i = 0; i < 4; i++) d[i] = s[i];
   return r;
 }
-static __device__ __noinline__ void madd_call(xyzz& acc, const affine& q) { xyzz_madd(acc, q); }
-static __device__ __noinline__ void dbl_call(xyzz& acc) { acc = xyzz_dbl(acc); }
-static __device__ __noinline__ void add_call(xyzz& acc, const xyzz& q) { xyzz_add(acc, q); }
+// out-of-line group operations, operands and result BY VALUE: see msm.cu xyzz_add_v (NVVM merges the stack slots of
+// address-taken structs passed by pointer to noinline functions)
+static __device__ __noinline__ xyzz madd_val(const xyzz acc, const affine q) { xyzz r = acc; xyzz_madd(r, q); return r; }
+static __device__ __noinline__ xyzz dbl_val(const xyzz acc) { return xyzz_dbl(acc); }
+static __device__ __noinline__ xyzz add_val(const xyzz acc, const xyzz q) { xyzz r = acc; xyzz_add(r, q); return r; }
+#define madd_call(acc, q) ((acc) = madd_val((acc), (q)))
+#define dbl_call(acc) ((acc) = dbl_val((acc)))
+#define add_call(acc, q) ((acc) = add_val((acc), (q)))
 
 // flags: 1 = write canonical bytes to out_canon[job], 2 = write identity flag to out_flag[job]
 __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs, uint32_t njobs, affine* __restrict__ arena,

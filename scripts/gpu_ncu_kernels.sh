@@ -3,7 +3,7 @@
 # (ordinals taken from the launch list of the same command, gpurun_out/launches_shuffle_2p16.csv).
 # Raw pages are exported to CSV on the box; only the report of the dominant kernel travels back.
 mkdir -p gpurun_out/ncu
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch52 0 --pipeline-decks 0 --msm-logn 16"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch52 0 --msm-logn 16"
 cap() {  # name regex skip
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 \
       -f -o /tmp/prof_$1 $CMD > /tmp/ncu_$1.log 2>&1

@@ -10,8 +10,8 @@ timeout 120 python scripts/microbench_bls12_377.py > /dev/null 2>&1
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; head -c 400 gpurun_out/bench.json; echo; tail -3 gpurun_out/bench.err
 timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 500 gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_shuffle_2p16.csv \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch52 0 --pipeline-decks 0 --sigma-cards 0 --bls12-377-logn 0 --msm-logn 20 > gpurun_out/ncu_bench.log 2>&1
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch52 0 --pipeline-decks 0 --bls12-377-logn 0 --msm-logn 16"
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch52 0 --sigma-cards 0 --bls12-377-logn 0 --msm-logn 20 > gpurun_out/ncu_bench.log 2>&1
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch52 0 --bls12-377-logn 0 --msm-logn 16"
 cap() {  # name regex skip count [command]
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 \
       -f -o gpurun_out/ncu/prof_$1 ${5:-$CMD} > /tmp/ncu_$1.log 2>&1
