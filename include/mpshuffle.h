@@ -48,11 +48,21 @@ typedef struct mp_ctx mp_ctx;
  * remasking.rs:110-112, reveal.rs:80-82) and "Schnorr Identification" (tests.rs:72-77) */
 #define MP_VERIFY_CHAUM_PEDERSEN 5
 #define MP_VERIFY_SCHNORR 6
+/* batch verifiers only: item i is malformed -- a point off the curve / not canonical, or a scalar >= the group
+ * order -- the per-item form of MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_CANONICAL, so that one bad item does not fail the
+ * other items of the batch (the reference fails only the offending item, at deserialisation) */
+#define MP_VERIFY_MALFORMED 7
 /* usage / runtime errors */
 #define MP_ERR_INVALID_ARG (-1)
 #define MP_ERR_CUDA (-2)
 #define MP_ERR_NOT_ON_CURVE (-3)
 #define MP_ERR_NO_PARAMS (-4)
+/* a scalar of an untrusted input (a proof) is not a canonical residue, i.e. >= the group order: ark-serialize's
+ * CanonicalDeserialize rejects such bytes before the reference's verifier ever sees them (s and s + order would
+ * otherwise both verify -- proof malleability) */
+#define MP_ERR_NOT_CANONICAL (-5)
+/* BLS12-377 only (the Stark curve has cofactor 1): a point is on the curve but outside the order-r subgroup G1 */
+#define MP_ERR_NOT_IN_SUBGROUP (-6)
 
 /* ---- context ------------------------------------------------------------------------ */
 /* Creates a context bound to CUDA device `device` (owns a stream and device scratch). */
@@ -267,7 +277,14 @@ uint64_t mp_deck_serialized_len(uint64_t n_cards);
 int32_t mp_deck_serialize(const uint8_t* deck /* n_cards*128 */, uint64_t n_cards, uint8_t* out);
 /* *n_cards: in = capacity of out_deck in cards, out = cards in the buffer */
 int32_t mp_deck_deserialize(mp_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards);
-/* the flat proof with every point compressed: (11m+8)*32 + (5n+9)*32 bytes */
+/* REPOSITORY-PRIVATE proof container: the flat proof of this header with every point compressed and every
+ * scalar as it is -- (11m+8)*32 + (5n+9)*32 bytes, NO length prefixes.  It is NOT the byte stream
+ * `ZKProofShuffle::serialize` produces upstream: that struct is a nest of Vec<> fields (one u64 length prefix
+ * each, order and nesting defined in the absent proof-essentials crate), so upstream's `serialized_size()` is
+ * larger by 8 bytes per Vec field and the bytes do not round-trip with a Rust peer.  The element encodings
+ * (compressed points, canonical scalars, the Vec<MaskedCard> deck format above) are ark-serialize 0.3's; only the
+ * proof's framing is this repository's own.  Deserialisation validates like ark-serialize: points on the curve,
+ * scalars below the group order (MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_CANONICAL). */
 uint64_t mp_proof_serialized_len(int32_t m, int32_t n);
 int32_t mp_proof_serialize(int32_t m, int32_t n, const uint8_t* proof, uint8_t* out);
 int32_t mp_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof);

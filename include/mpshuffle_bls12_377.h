@@ -14,8 +14,10 @@
  *   - base-field element: 48 bytes little-endian canonical (ark-ff 0.3 `Fp384` `ToBytes`);
  *   - scalar: 32 bytes little-endian canonical, < r (253 bits);
  *   - affine G1 point: 96 bytes x || y, identity = 96 zero bytes ((0,0) is not on y^2 = x^3 + 1);
- *     ciphertext = c1 || c2 = 192 bytes.  Points are checked to be canonical and on the curve
- *     (not for subgroup membership: G1 has cofactor 0x170b5d44300000000000000000000000);
+ *     ciphertext = c1 || c2 = 192 bytes.  Points are checked to be canonical and on the curve by every entry
+ *     point; the group-layer entry points (MSM, commitments) do NOT test subgroup membership (G1 has cofactor
+ *     0x170b5d44300000000000000000000000) -- mp377_subgroup_check does, and mp377_shuffle_verify applies it to
+ *     every untrusted point, as ark-ec's CanonicalDeserialize does on the reference's side;
  *   - status codes MP_OK / MP_ERR_* of mpshuffle.h; no CPU fallback.
  */
 #ifndef MPSHUFFLE_BLS12_377_H
@@ -65,11 +67,19 @@ int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_t n_points,
                        const uint8_t* scalars, uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs,
                        int32_t window_bits, uint8_t* out);
 
+/* Subgroup membership of n canonical points (n * 96 bytes): MP_OK iff every point is a canonical point of the curve
+ * and lies in the order-r subgroup G1; otherwise MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_IN_SUBGROUP.  statuses (optional,
+ * n entries): 0 = in G1, 1 = not a canonical curve point, 2 = on the curve but outside G1.  One 127-bit
+ * double-and-add per point (endomorphism test phi(P) == -[u^2]P, as ark-bls12-377 does). */
+int32_t mp377_subgroup_check(mp377_ctx* ctx, const uint8_t* points, uint64_t n, int32_t* statuses);
+
 /* BarnettSmartProtocol::verify_shuffle over this curve (reference src/lib.rs:191-197, impl mod.rs:420-443;
  * Parameters = (m, n, enc generator, commit key g_1..g_n / h, extra generator), mod.rs:37-61).  Returns
  * MP_OK, an MP_VERIFY_* code (mp_verify_status_string gives the reference's message, e.g.
  * "Hadamard Product (5.1)"), or MP_ERR_*.  Proof layout: the flat layout of mpshuffle.h with 96-byte
- * points, mp377_proof_len(m, n) = (11m + 8) * 96 + (5n + 9) * 32 bytes.  Host-scalar path: the O(N) scalar
+ * points, mp377_proof_len(m, n) = (11m + 8) * 96 + (5n + 9) * 32 bytes.  Untrusted inputs are validated as the
+ * reference's deserialiser would: every point canonical, on the curve and in G1 (MP_ERR_NOT_ON_CURVE /
+ * MP_ERR_NOT_IN_SUBGROUP), every proof scalar below r (MP_ERR_NOT_CANONICAL).  Host-scalar path: the O(N) scalar
  * work and the transcript run on the calling thread, the group work on the GPU. */
 uint64_t mp377_proof_len(int32_t m, int32_t n);
 int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g /* 96 */,
@@ -80,8 +90,10 @@ int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t
 /* Wire format, serialising half (ark-serialize 0.3 compressed encodings, as mp_points_compress / mp_deck_serialize /
  * mp_proof_serialize of mpshuffle.h): compressed point = x (48 bytes LE) with flags in the top bits of the last byte
  * (bit 7: y is the larger of (y, -y); bit 6: infinity); Vec<MaskedCard> = u64 LE length | c1 | c2 per card; proof =
- * the flat layout with every point compressed, (11m + 8) * 48 + (5n + 9) * 32 bytes -- the quantity the reference's
- * benchmark prints (examples/parameter_selection.rs:93-96).  Host byte handling, no context.  Deserialising is not
+ * the REPOSITORY-PRIVATE container of mpshuffle.h (flat layout, every point compressed, no Vec length prefixes),
+ * (11m + 8) * 48 + (5n + 9) * 32 bytes -- close to, but not, what the reference's benchmark prints with
+ * `serialized_size()` (examples/parameter_selection.rs:93-96), which adds 8 bytes per Vec field of the upstream
+ * proof struct.  Host byte handling, no context.  Deserialising is not
  * built for this curve yet. */
 int32_t mp377_points_compress(const uint8_t* points /* n*96 */, uint64_t n, uint8_t* out /* n*48 */);
 uint64_t mp377_deck_serialized_len(uint64_t n_cards);

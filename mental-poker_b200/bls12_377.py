@@ -32,6 +32,7 @@ SIGNATURES = {
     "mp377_proof_serialized_len": (_u64, [_i32, _i32]),
     "mp377_proof_serialize": (_i32, [_i32, _i32, _cp, _cp]),
     "mp377_proof_len": (_u64, [_i32, _i32]),
+    "mp377_subgroup_check": (_i32, [_vp, _cp, _u64, ctypes.POINTER(_i32)]),
     "mp377_shuffle_verify": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp, _cp, _cp, _cp, _cp]),
     "mp377_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, ctypes.POINTER(ctypes.c_uint32), _u64, _i32, _cp]),
     "mp377_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
@@ -163,6 +164,13 @@ class Context:
         assert len(ck_g) == n * POINT_BYTES and len(deck) == len(shuffled_deck) == 2 * N * POINT_BYTES
         assert len(proof) == lib.mp377_proof_len(m, n)
         return _check(self.h, lib.mp377_shuffle_verify(self.h, m, n, enc_g, ck_g, ck_h, ghat, pk, deck, shuffled_deck, proof))
+
+    def subgroup_check(self, points: bytes):
+        """-> (return code, per-point statuses: 0 in G1, 1 not a canonical curve point, 2 outside the subgroup)"""
+        n = len(points) // POINT_BYTES
+        st = (_i32 * max(n, 1))()
+        rc = lib.mp377_subgroup_check(self.h, points, n, st)
+        return rc, list(st)[:n]
 
     # --- Pedersen
     def set_commit_key(self, ck: bytes):

@@ -86,6 +86,7 @@ extern "C" const char* mp_verify_status_string(int32_t status) {
     case MP_VERIFY_MULTIEXP: return "Multi Exponentiation (4)";
     case MP_VERIFY_CHAUM_PEDERSEN: return "Chaum-Pedersen";
     case MP_VERIFY_SCHNORR: return "Schnorr Identification";
+    case MP_VERIFY_MALFORMED: return "malformed input (point off the curve or non-canonical bytes)";
     default: return "unknown";
   }
 }

@@ -257,6 +257,88 @@ extern "C" int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_
 // moves the O(N) scalar work to device kernels and keeps decks resident; that driver is not built for this
 // curve yet.)
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Subgroup membership.  E(F_q) has cofactor h = 0x170b5d44300000000000000000000000; the protocol lives in the
+// order-r subgroup G1, and every verifier scalar is reduced mod r, so points with a cofactor-torsion component must
+// not reach the verifier (small-subgroup malleability).  In the reference every point arrives through ark-ec 0.3
+// `CanonicalDeserialize`, which rejects them (is_in_correct_subgroup_assuming_on_curve).  Test used here -- the one
+// ark-bls12-377 uses too (M. Scott, "A note on group membership tests for G1, G2 and GT on BLS pairing-friendly
+// curves"): with the endomorphism phi(x, y) = (beta x, y), beta a primitive cube root of unity in F_q,
+//     P in G1  <=>  phi(P) == -[u^2] P,      u = 0x8508c00000000001 (the BLS parameter),
+// i.e. one 127-bit double-and-add (Hamming weight 22) per point instead of a 253-bit one.  Checked against
+// big-int arithmetic in tests/test_oracle_bls12_377.py for subgroup points, random curve points, pure torsion
+// points and G1 + torsion.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k377_subgroup_check(const affine* __restrict__ pts, uint64_t n, int* __restrict__ bad,
+                                                           uint64_t per_item) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  affine P;
+  {
+    const uint4* s = reinterpret_cast<const uint4*>(pts + i);
+    uint4* d = reinterpret_cast<uint4*>(&P);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(affine) / 16); k++) d[k] = __ldg(s + k);
+  }
+  if (affine_is_identity(P)) return;  // the identity is in every subgroup
+  const uint32_t u2[4] = {0x00000001u, 0x0a118000u, 0x90000001u, 0x452217ccu};  // u^2, 127 bits
+  xyzz acc = xyzz_identity();
+#pragma unroll 1
+  for (int bit = 126; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((u2[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, P);
+  }
+  // phi(P) == -acc   <=>   acc.X == beta x ZZ  and  acc.Y == -(y ZZZ)      (acc = O cannot equal -phi(P) != O)
+  fq beta;  // beta * R mod q
+  {
+    const uint32_t b[12] = {0x5a7b8727u, 0x2c766f92u, 0x253d58b5u, 0x03d7f6b0u, 0xec122131u, 0x838ec0deu,
+                            0xf658bb10u, 0xbd5eb3e9u, 0x6ed3e52eu, 0x6942bd12u, 0xdd04ed6au, 0x01673786u};
+#pragma unroll
+    for (int k = 0; k < 12; k++) beta.v[k] = b[k];
+  }
+  bool ok = !xyzz_is_identity(acc);
+  if (ok) {
+    const fq lx = fq_reduce_full(acc.X), rx = fq_reduce_full(fq_mul(fq_mul(beta, P.x), acc.ZZ));
+    const fq ly = fq_reduce_full(acc.Y), ry = fq_reduce_full(fq_neg2(fq_mul(P.y, acc.ZZZ)));
+    ok = fq_eq_raw(lx, rx) && fq_eq_raw(ly, ry);
+  }
+  if (!ok) atomicExch(bad + (per_item ? i / per_item : 0), 1);
+}
+
+// points: canonical, n * 96 bytes (host).  Sets *in_subgroup = 1 iff every point is a canonical point of the curve AND
+// lies in G1.  statuses (optional, n entries): 0 = in G1, 1 = not on the curve / not canonical, 2 = on the curve but
+// outside G1.
+extern "C" int32_t mp377_subgroup_check(mp377_ctx* ctx, const uint8_t* points, uint64_t n, int32_t* statuses) {
+  if (!ctx || (!points && n)) return MP_ERR_INVALID_ARG;
+  if (n == 0) return MP_OK;
+  if (n >= (1ull << 31)) return ctx->fail(MP_ERR_INVALID_ARG, "too many points");
+  cudaSetDevice(ctx->device);
+  ctx->launches = 0;
+  uint8_t* d_in = (uint8_t*)ctx->scratch(mp377_ctx::kStageIn, n * kPt + 256);
+  affine* mont = (affine*)ctx->scratch(mp377_ctx::kPointsMont, sizeof(affine) * n);
+  int* flags = (int*)ctx->scratch(mp377_ctx::kScal, 2 * n * sizeof(int) + 256);
+  if (!d_in || !mont || !flags) return ctx->fail(MP_ERR_CUDA, "device allocation failed");
+  CK377(cudaMemcpyAsync(d_in, points, n * kPt, cudaMemcpyHostToDevice, ctx->stream), "H2D points");
+  CK377(cudaMemsetAsync(flags, 0, 2 * n * sizeof(int), ctx->stream), "memset");
+  CK377(points_to_mont_items((const uint32_t*)d_in, mont, n, flags, 1, ctx->stream), "points_to_mont");
+  k377_subgroup_check<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(mont, n, flags + n, 1);
+  CK377(cudaGetLastError(), "k377_subgroup_check");
+  ctx->launches = 2;
+  std::vector<int> h(2 * n);
+  CK377(cudaMemcpyAsync(h.data(), flags, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H flags");
+  CK377(cudaStreamSynchronize(ctx->stream), "subgroup check");
+  int32_t worst = MP_OK;
+  for (uint64_t i = 0; i < n; i++) {
+    const int32_t st = h[i] ? 1 : (h[n + i] ? 2 : 0);
+    if (statuses) statuses[i] = st;
+    if (st == 1) worst = MP_ERR_NOT_ON_CURVE;
+    else if (st == 2 && worst == MP_OK) worst = MP_ERR_NOT_IN_SUBGROUP;
+  }
+  if (worst == MP_ERR_NOT_ON_CURVE) return ctx->fail(worst, "a point is not a canonical point of BLS12-377 G1's curve");
+  if (worst == MP_ERR_NOT_IN_SUBGROUP) return ctx->fail(worst, "a point is on the curve but outside the order-r subgroup G1");
+  return MP_OK;
+}
+
 extern "C" uint64_t mp377_proof_len(int32_t m, int32_t n) { return shuffle_proof_len(m, n); }
 
 extern "C" int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
@@ -283,6 +365,21 @@ extern "C" int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, co
   memcpy(S.enc_g, enc_g, kPt);
   memcpy(S.ghat, ghat, kPt);
   const Layout L(m, n);
+  if (!proof_scalars_canonical(proof, L))
+    return ctx->fail(MP_ERR_NOT_CANONICAL, "a scalar of the proof is not below the group order");
+  {
+    // every untrusted point -- public key, both decks, the 11m + 8 proof points -- and the parameters must lie in G1
+    // (what `CanonicalDeserialize` enforces on the reference's side of this call)
+    std::vector<uint8_t> all;
+    all.reserve((4 * N + 11 * (size_t)m + 8 + (size_t)n + 4) * kPt);
+    auto put = [&](const uint8_t* p, size_t count) { all.insert(all.end(), p, p + count * kPt); };
+    put(pk, 1); put(enc_g, 1); put(ghat, 1); put(ck_h, 1); put(ck_g, (size_t)n);
+    put(deck, 2 * N); put(shuffled_deck, 2 * N);
+    put(proof, L.za / kPt); put(proof + L.svpts, 3); put(proof + L.mepts, (L.mea - L.mepts) / kPt);
+    int32_t sg = mp377_subgroup_check(ctx, all.data(), all.size() / kPt, nullptr);
+    if (sg != MP_OK) return sg;
+    launches += ctx->launches;
+  }
   const Challenges ch = derive_challenges(&S, pk, deck, shuffled_deck, N, proof, L);
   // the eight commitment-space equations
   TermList tl;

@@ -166,9 +166,11 @@ __device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz& v, int delta) {
 // ------------------------------------------------------------------------------------------
 // ingest / export
 // ------------------------------------------------------------------------------------------
+// bad: one flag for the whole array (per_item == 0) or one flag per run of `per_item` consecutive points (the
+// batch verifiers: the points of proof p occupy [p * per_item, (p + 1) * per_item))
 __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restrict__ in,
                                                         affine* __restrict__ out, uint64_t n,
-                                                        int* __restrict__ bad) {
+                                                        int* __restrict__ bad, uint64_t per_item) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t w[kPointWords];
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restri
     uint32_t bx, by;
     fq_sub_raw(cx, fq_kp(1), &bx);
     fq_sub_raw(cy, fq_kp(1), &by);
-    if (!bx || !by || !affine_on_curve(p)) atomicExch(bad, 1);
+    if (!bx || !by || !affine_on_curve(p)) atomicExch(bad + (per_item ? i / per_item : 0), 1);
   }
   uint4* d = reinterpret_cast<uint4*>(out + i);
   const uint4* ps = reinterpret_cast<const uint4*>(&p);
@@ -199,7 +201,13 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint32_t* __restri
 cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,
                            cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  k_points_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_canonical, d_out, n, d_bad);
+  k_points_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_canonical, d_out, n, d_bad, 0);
+  return cudaGetLastError();
+}
+cudaError_t points_to_mont_items(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad_items,
+                                 uint64_t per_item, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  k_points_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_canonical, d_out, n, d_bad_items, per_item);
   return cudaGetLastError();
 }
 

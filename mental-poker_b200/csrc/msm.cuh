@@ -71,6 +71,9 @@ cudaError_t msm_profile_collect(MsmWorkspace* ws, double* ms, uint64_t* adds, ui
 // canonical 64-byte points -> Montgomery affine (validating on-curve; bad points set *d_bad)
 cudaError_t points_to_mont(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad,
                            cudaStream_t stream);
+// per-item form: d_bad_items[i / per_item] is set when point i is rejected (the batch verifiers, one flag per proof)
+cudaError_t points_to_mont_items(const uint32_t* d_canonical, affine* d_out, uint64_t n, int* d_bad_items,
+                                 uint64_t per_item, cudaStream_t stream);
 // XYZZ -> canonical 64-byte affine (x || y, all-zero = identity); one inversion per point
 cudaError_t xyzz_to_canonical(const xyzz* d_in, uint32_t* d_out, uint64_t n, cudaStream_t stream);
 

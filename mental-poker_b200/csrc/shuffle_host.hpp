@@ -45,6 +45,16 @@ inline fr h_fr(const uint8_t* b) {
   memcpy(w, b, 32);
   return fr_from_canonical(w);
 }
+// canonical 32-byte scalar, i.e. below the group order?  (ark-serialize rejects anything else at deserialisation)
+inline bool h_fr_is_canonical(const uint8_t* b) {
+  uint32_t w[8];
+  memcpy(w, b, 32);
+  for (int i = 7; i >= 0; i--) {
+    const uint32_t mi = fr_modulus_limb(i);
+    if (w[i] != mi) return w[i] < mi;
+  }
+  return false;
+}
 inline void h_fr_out(const fr& a, uint8_t* b) {
   uint32_t w[8];
   fr_to_canonical(a, w);
@@ -105,6 +115,17 @@ struct Layout {
     mer = mea + n * F; meb = mer + F; mes = meb + F; metau = mes + F; end = metau + F;
   }
 };
+
+// Every one of the 5n + 9 scalars of a proof must be a canonical residue: h_fr() would reduce s + order to s
+// silently and the proof would still verify (malleability); the reference never sees such a proof because
+// `Proof: CanonicalDeserialize` (bounds at reference src/lib.rs:45-71) rejects the bytes.
+inline bool proof_scalars_canonical(const uint8_t* proof, const Layout& L) {
+  const size_t runs[3][2] = {{L.za, L.svpts}, {L.sva, L.mepts}, {L.mea, L.end}};
+  for (auto& r : runs)
+    for (size_t off = r[0]; off < r[1]; off += 32)
+      if (!h_fr_is_canonical(proof + off)) return false;
+  return true;
+}
 
 // The statement absorb is ONE Blake2s over  label | parameters | pk | deck | deck' | c_A | seed  --
 // serial by construction and, at 2^16 cards, 17 MB.  It is fed in two parts so that the prover can

@@ -75,6 +75,7 @@ enum Slot {  // ctx->scratch slots owned by this file
   sFrA, sFrB, sFrD, sFrBv, sFrXpow, sFrAme, sFrTmp0, sFrTmp1, sFrTmp2, sFrPairs, sFrSmall,
   sPerm, sRho, sCanonOut, sCtTable,
   sKaraTmp, sKaraPts, sKaraScal, sKaraOut,
+  sBadItems,
 };
 
 #define CK(x)                                                    \

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) k_build_table(const uint32_t* __restrict_
   int j = g / kTabDigits;
   uint32_t d = (uint32_t)(g % kTabDigits) + 1;
   affine P = affine_from_canonical(base_canon);
-  if (g == 0 && !affine_on_curve(P)) atomicExch(bad, 1);
+  if (g == 0 && !affine_on_curve(P)) atomicOr(bad, 1);   // bit 0: a point is off the curve
   xyzz acc = xyzz_identity();
   for (int bit = 7; bit >= 0; bit--) {
     acc = xyzz_dbl(acc);
@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(128) k_remask(const uint32_t* __restrict__ dec
   uint64_t i = g >> 1;
   int comp = (int)(g & 1);
   uint64_t src = perm[i];
-  if (src >= N) { atomicExch(bad, 2); return; }
+  if (src >= N) { atomicOr(bad, 2); return; }           // bit 1: permutation entry out of range
   affine card = affine_from_canonical(deck_canon + (src * 2 + comp) * 16);
-  if (!affine_on_curve(card)) atomicExch(bad, 1);
+  if (!affine_on_curve(card)) atomicOr(bad, 1);
   uint32_t k[8];
   {
     // reduce rho below the group order is the caller's contract; a 256-bit value still works
@@ -126,6 +126,7 @@ int32_t shuffle_ensure_pk_table(mp_ctx* ctx, const uint8_t* pk) {
   uint8_t* d_pk = (uint8_t*)ctx->scratch(sSmallUp, 256);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_pk); NEED(d_bad);
+  S->tab_pk_valid = false;  // the table is being overwritten: valid again only once the device has accepted pk
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
   CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, ctx->stream));
   CK(build_table(S, 1, d_pk, d_bad, ctx->stream));
@@ -133,7 +134,6 @@ int32_t shuffle_ensure_pk_table(mp_ctx* ctx, const uint8_t* pk) {
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  S->tab_pk_valid = false;
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not on the Stark curve");
   memcpy(S->tab_pk, pk, 64);
   S->tab_pk_valid = true;
@@ -265,11 +265,13 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_deck); NEED(d_out); NEED(d_perm); NEED(d_rho); NEED(d_pk); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  if (!S->tab_pk_valid || memcmp(S->tab_pk, pk, 64) != 0) {  // the pk table is cached across calls
+  // the pk table is cached across calls; it is marked valid only AFTER the device has validated pk (flag clean
+  // at the synchronisation below) -- any early return in between leaves the cache invalid
+  const bool rebuild_pk = !S->tab_pk_valid || memcmp(S->tab_pk, pk, 64) != 0;
+  if (rebuild_pk) {
+    S->tab_pk_valid = false;
     CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, ctx->stream));
     CK(build_table(S, 1, d_pk, d_bad, ctx->stream));
-    memcpy(S->tab_pk, pk, 64);
-    S->tab_pk_valid = true;
     ctx->launches += 1;
   }
   CK(cudaMemcpyAsync(d_deck, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
@@ -284,11 +286,13 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (fs_head) absorb_statement_head(*fs_head, S, pk, deck, N);  // host hashing overlaps the copies and the kernel
   CK(cudaStreamSynchronize(ctx->stream));
-  if (bad == 2) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry out of range");
-  if (bad) {
-    S->tab_pk_valid = false;
-    return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
+  // distinct bits (atomicOr): an out-of-range permutation entry can no longer hide an off-curve key or card
+  if (bad & 1) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
+  if (rebuild_pk) {  // pk validated by k_build_table: the table may be reused by later calls
+    memcpy(S->tab_pk, pk, 64);
+    S->tab_pk_valid = true;
   }
+  if (bad & 2) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry out of range");
   if (d_out_ret) *d_out_ret = d_out;
   return MP_OK;
 }

@@ -20,6 +20,8 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n;
   const Layout L(m, n);
+  if (!proof_scalars_canonical(proof, L))
+    return ctx->fail(MP_ERR_NOT_CANONICAL, "a scalar of the proof is not below the group order");
 
   // ---- 1. start moving the decks (independent of every challenge)
   const size_t T = 2 * N + 2 * (size_t)m + 3;  // CT arena: deck | E_m | deck2 | E_0..E_{2m-1} | (g,pk) | (O,ghat)
@@ -158,11 +160,12 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
   std::vector<uint32_t> g1_scal(Bs * T1 * 8), ct_scal(ct_total * 8);
   std::vector<HostChecks> hcs(Bs);
   std::vector<fr> bstars(Bs);
-  std::vector<int> bad_layout(Bs, 0);
+  std::vector<int> bad_layout(Bs, 0), malformed(Bs, 0);
   auto work = [&](size_t p) {
     const uint8_t* deck = decks + p * N * 128;
     const uint8_t* deck2 = decks2 + p * N * 128;
     const uint8_t* proof = proofs + p * plen;
+    malformed[p] = !proof_scalars_canonical(proof, L);  // reported per item; the group work below still runs
     const Challenges ch = derive_challenges(S, pk, deck, deck2, N, proof, L);
     TermList tl;
     append_g1_checks(tl, S, proof, L, ch, &hcs[p]);
@@ -196,20 +199,23 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
   uint32_t* d_g1_scal = (uint32_t*)ctx->scratch(sG1Scal, Bs * T1 * 32);
   xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, Bs * kG1Checks * sizeof(xyzz));
   uint8_t* d_flags = (uint8_t*)ctx->scratch(sResults, Bs * 12 + 64);
-  int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
+  int* d_bad = (int*)ctx->scratch(sBadItems, Bs * sizeof(int) + 64);  // one flag per proof: a point of it is off the curve
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_g1_canon); NEED(d_g1_mont);
   NEED(d_g1_scal); NEED(d_g1_out); NEED(d_flags); NEED(d_bad);
   cudaStream_t st = ctx->stream;
-  CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(d_bad, 0, Bs * sizeof(int), st));
   CK(cudaMemcpyAsync(d_ct_canon, decks, Bs * N * 128, cudaMemcpyDefault, st));
   CK(cudaMemcpyAsync(d_ct_canon + Bs * N * 128, decks2, Bs * N * 128, cudaMemcpyDefault, st));
   CK(cudaMemcpyAsync(d_ct_canon + 2 * Bs * N * 128, sm_pts.data(), sm_pts.size(), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_ct_scal, ct_scal.data(), ct_scal.size() * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_g1_canon, g1_pts.data(), g1_pts.size(), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_g1_scal, g1_scal.data(), g1_scal.size() * 4, cudaMemcpyHostToDevice, st));
-  CK(points_to_mont((const uint32_t*)d_ct_canon, d_ct_mont, ct_total * 2, d_bad, st));
-  CK(points_to_mont((const uint32_t*)d_g1_canon, d_g1_mont, Bs * T1, d_bad, st));
-  ctx->launches += 2;
+  // arena = decks | shuffled decks | per-proof small entries: three runs with their own points-per-proof
+  CK(points_to_mont_items((const uint32_t*)d_ct_canon, d_ct_mont, Bs * N * 2, d_bad, N * 2, st));
+  CK(points_to_mont_items((const uint32_t*)(d_ct_canon + Bs * N * 128), d_ct_mont + Bs * N * 2, Bs * N * 2, d_bad, N * 2, st));
+  CK(points_to_mont_items((const uint32_t*)(d_ct_canon + 2 * Bs * N * 128), d_ct_mont + 4 * Bs * N, Bs * SM * 2, d_bad, SM * 2, st));
+  CK(points_to_mont_items((const uint32_t*)d_g1_canon, d_g1_mont, Bs * T1, d_bad, T1, st));
+  ctx->launches += 4;
   // ciphertext jobs: per proof (deck, E_m) -> group 0, (deck', small tail) -> group 1
   std::vector<MsmJob> jobs(Bs * 4);
   for (size_t p = 0; p < Bs; p++) {
@@ -242,12 +248,14 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
   CK(cudaGetLastError());
   ctx->launches += 2;
   std::vector<uint8_t> flags(Bs * 12);
-  int bad = 0;
+  std::vector<int> bad(Bs, 0);
   CK(cudaMemcpyAsync(flags.data(), d_flags, Bs * 12, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(bad.data(), d_bad, Bs * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck or proof point in the batch is not a canonical point of the Stark curve");
   for (size_t p = 0; p < Bs; p++) {
+    // a malformed item (point off the curve / not canonical, scalar >= the group order) fails on its own, as the
+    // reference's deserialiser would fail it, and does not take the rest of the batch with it
+    if (bad[p] || malformed[p]) { statuses[p] = MP_VERIFY_MALFORMED; continue; }
     bool g1_id[kG1Checks];
     for (int j = 0; j < kG1Checks; j++) g1_id[j] = flags[Bs * 4 + p * kG1Checks + j] != 0;
     const uint8_t* cf = &flags[p * 4];
@@ -275,6 +283,7 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
       int32_t st = shuffle_verify(w, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen,
                                   d_decks ? (const uint8_t*)d_decks + p * N * 128 : nullptr,
                                   d_decks2 ? (const uint8_t*)d_decks2 + p * N * 128 : nullptr);
+      if (st == MP_ERR_NOT_ON_CURVE || st == MP_ERR_NOT_CANONICAL) st = MP_VERIFY_MALFORMED;  // this item only
       if (st >= 0) statuses[p] = st;
       return st < 0 ? st : MP_OK;
     });

@@ -177,6 +177,9 @@ int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t*
       q += 64 * r.count;
       out_proof += 64 * r.count;
     } else {
+      // field elements: ark-serialize rejects non-canonical encodings (value >= the group order) at deserialisation
+      for (size_t k = 0; k < r.count; k++)
+        if (!h_fr_is_canonical(p + 32 * k)) return ctx->fail(MP_ERR_NOT_CANONICAL, "a scalar of the proof is not below the group order");
       memcpy(out_proof, p, 32 * r.count);
       out_proof += 32 * r.count;
     }

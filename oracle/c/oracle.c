@@ -821,6 +821,20 @@ int oc_shuffle_prove(int m, int n, const uint8_t* enc_g, const uint8_t* ck_g, co
 int oc_shuffle_verify(int m, int n, const uint8_t* enc_g, const uint8_t* ck_g, const uint8_t* ck_h, const uint8_t* ghat,
                       const uint8_t* pk, const uint8_t* deck_b, const uint8_t* deck2_b, const uint8_t* proof) {
   oracle_init();
+  {
+    /* `Proof: CanonicalDeserialize` (reference src/lib.rs:45-71): ark-serialize rejects a scalar >= the group order
+     * before the verifier runs; -5 = MP_ERR_NOT_CANONICAL of include/mpshuffle.h.  Scalar runs of the flat layout:
+     * 2n+3 after 5m+4 points, 2n+2 after 3 more points, n+4 after 6m+1 more points. */
+    const size_t runs[3][2] = {{64 * (5 * (size_t)m + 4), 2 * (size_t)n + 3},
+                               {64 * (5 * (size_t)m + 7) + 32 * (2 * (size_t)n + 3), 2 * (size_t)n + 2},
+                               {64 * (11 * (size_t)m + 8) + 32 * (4 * (size_t)n + 5), (size_t)n + 4}};
+    for (int r = 0; r < 3; r++)
+      for (size_t k = 0; k < runs[r][1]; k++) {
+        uint64_t c[4];
+        memcpy(c, proof + runs[r][0] + 32 * k, 32);
+        if (limbs_geq(c, FR.m)) return -5;
+      }
+  }
   params_t pp;
   load_params(&pp, m, n, enc_g, ck_g, ck_h, ghat, pk);
   size_t Nc = (size_t)m * n;

@@ -493,6 +493,10 @@ def proof_to_bytes(pf):
     return out
 
 
+class NonCanonicalScalar(ValueError):
+    """a serialized scalar is not a canonical residue (what ark-serialize's deserialiser rejects)"""
+
+
 def proof_from_bytes(buf, m, n):
     assert len(buf) == proof_len(m, n)
     pos = [0]
@@ -505,6 +509,10 @@ def proof_from_bytes(buf, m, n):
     def fr():
         v = stark.fe_from_bytes(buf[pos[0]:pos[0] + 32])
         pos[0] += 32
+        # `Proof: CanonicalDeserialize` (reference src/lib.rs:45-71): ark-serialize rejects a field element whose
+        # integer is >= the modulus -- s and s + order must not both be accepted (proof malleability)
+        if v >= stark.N:
+            raise NonCanonicalScalar("proof scalar >= group order")
         return v
 
     pf = dict(c_A=[pt() for _ in range(m)], c_B=[pt() for _ in range(m)])

@@ -284,7 +284,7 @@ def test_verify_shuffle_c_abi(ctx377, pkg):
         assert ctx377.launches > 0
         cases = [(raw["deck2"][192:] + raw["deck2"][:192], raw["proof"])]
         plen = len(raw["proof"])
-        for off in (plen - 1 - 32 * 3, plen - 32 * (n + 4) - 1,              # multi-exp r, multi-exp a_n
+        for off in (plen - 32 * 4, plen - 32 * 5,                            # multi-exp r, multi-exp a_n (low bytes: stay canonical)
                     (11 * m + 8) * 96 - 96 * (4 * m + 2 * m + 1) - 32 * (2 * n + 2) - 40):  # inside the SVP block
             p2 = bytearray(raw["proof"])
             p2[off] ^= 1
@@ -355,3 +355,84 @@ def test_msm_2p18_linearity(ctx377):
         res.append(bls.point_from_bytes(bytes(d_out.cpu().numpy())))
     assert bls.is_on_curve(res[0]) and res[0] is not None
     assert bls.add(res[0], res[1]) == res[2]
+
+
+SHUF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_shuffle_vectors.json")))
+
+
+def _torsion_point():
+    """a point of E(F_q) outside G1: r * (random curve point) is a non-trivial cofactor-torsion point"""
+    rr = random.Random(77)
+    while True:
+        x = rr.randrange(bls.Q)
+        y2 = (x * x * x + 1) % bls.Q
+        if pow(y2, (bls.Q - 1) // 2, bls.Q) != 1:
+            continue
+        # q = 1 mod 4: Tonelli-Shanks
+        q, s2 = bls.Q - 1, 0
+        while q % 2 == 0:
+            q //= 2; s2 += 1
+        z = 2
+        while pow(z, (bls.Q - 1) // 2, bls.Q) != bls.Q - 1:
+            z += 1
+        mm, c, t, r_ = s2, pow(z, q, bls.Q), pow(y2, q, bls.Q), pow(y2, (q + 1) // 2, bls.Q)
+        while t != 1:
+            i, tt = 0, t
+            while tt != 1:
+                tt = tt * tt % bls.Q; i += 1
+            b = pow(c, 1 << (mm - i - 1), bls.Q)
+            mm, c = i, b * b % bls.Q
+            t, r_ = t * c % bls.Q, r_ * b % bls.Q
+        P = (x, r_)
+        assert bls.is_on_curve(P)
+        acc = None
+        for bit in bin(bls.N)[2:]:          # plain double-and-add: bls.mul would reduce the scalar mod r
+            acc = bls.add(acc, acc)
+            if bit == "1":
+                acc = bls.add(acc, P)
+        if acc is not None:
+            return P, acc
+
+
+def test_subgroup_check(ctx377, pkg):
+    """G1 membership (the check ark-ec's CanonicalDeserialize performs on the reference's side): subgroup points and
+    the identity pass; a random curve point, a pure cofactor-torsion point and G1 + torsion are on the curve but
+    rejected; an off-curve point is reported as such."""
+    P, T = _torsion_point()
+    good = PTS[:5] + [None]
+    bad = [P, T, bls.add(PTS[0], T)]
+    off = bytearray(pb(PTS[1])); off[7] ^= 1
+    rc, st = ctx377.subgroup_check(b"".join(map(pb, good)))
+    assert rc == 0 and st == [0] * 6
+    rc, st = ctx377.subgroup_check(b"".join(map(pb, good + bad)))
+    assert rc == -6 and st == [0] * 6 + [2, 2, 2]
+    rc, st = ctx377.subgroup_check(b"".join(map(pb, good + bad)) + bytes(off))
+    assert rc == -3 and st == [0] * 6 + [2, 2, 2, 1]
+    # the generic MSM entry accepts the torsion point (on the curve) -- membership is the verifier's job
+    assert len(ctx377.msm_g1(pb(T), b32(5))) == 96
+
+
+def test_shuffle_verify_rejects_torsion_and_non_canonical_inputs(ctx377, pkg):
+    """mp377_shuffle_verify validates untrusted inputs like the reference's deserialiser: a deck or proof point with a
+    cofactor-torsion component -> MP_ERR_NOT_IN_SUBGROUP; a proof scalar >= r -> MP_ERR_NOT_CANONICAL."""
+    fx = SHUF["shuffle"][0]
+    hx = bytes.fromhex
+    m, n = fx["m"], fx["n"]
+    args = [m, n, hx(fx["enc_g"]), hx(fx["ck_g"]), hx(fx["ck_h"]), hx(fx["ghat"]), hx(fx["pk"]), hx(fx["deck"]), hx(fx["deck2"]), hx(fx["proof"])]
+    assert ctx377.verify_shuffle(*args) == 0
+    _, T = _torsion_point()
+    for which, off in ((8, 96), (9, 0), (6, 0)):          # a shuffled-deck point, the first proof point, the public key
+        buf = bytearray(args[which])
+        pt = bls.point_from_bytes(bytes(buf[off:off + 96]))
+        buf[off:off + 96] = pb(bls.add(pt, T))
+        a2 = list(args); a2[which] = bytes(buf)
+        with pytest.raises(pkg.MpError) as e:
+            ctx377.verify_shuffle(*a2)
+        assert e.value.code == -6, which
+    proof = args[9]
+    off = 96 * (5 * m + 4) + 32 * 2
+    s = int.from_bytes(proof[off:off + 32], "little")
+    a2 = list(args); a2[9] = proof[:off] + (s + bls.N).to_bytes(32, "little") + proof[off + 32:]
+    with pytest.raises(pkg.MpError) as e:
+        ctx377.verify_shuffle(*a2)
+    assert e.value.code == -5

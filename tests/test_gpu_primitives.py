@@ -146,3 +146,35 @@ def test_msm_window_range_split(ctx, pkg, c, world):
     got = ctx.msm_g1(points, scs, 0)
     e = sum(k * (s0 + i * s1) for i, k in enumerate(ks)) % N
     assert got == pb(stark.mul(stark.G, e))
+
+
+def test_msm_jobs_diagonal_products(ctx, pkg):
+    """K2 / `mp_msm_batch_shared_bases` of SURVEY.md section 8(b) on the Stark curve: batched MSM jobs over shared
+    arrays in the shape of the multi-exponentiation argument's diagonal products -- every (deck row i, scalar row j)
+    pair of an (m = 4, n = 13) instance, the reference's own test shape -- as one call with 2 components, against
+    known discrete logs and the C oracle's ciphertext MSM; plus ragged / empty / overlapping jobs."""
+    from oracle import c_oracle
+    m, n = 4, 13
+    s0, s1, pts, st = chain_points(2 * m * n, 17)
+    logs = [(s0 + i * s1) % N for i in range(2 * m * n)]
+    ks = [st.scalar() for _ in range((m + 1) * n)]
+    deck = b"".join(map(pb, pts))
+    kb = b"".join(map(b32, ks))
+    jobs = [(j * n, i * n, n) for i in range(m) for j in range(m + 1)]
+    out = ctx.msm_jobs(deck, kb, jobs, ncomp=2)
+    co = c_oracle.COracle()
+    for q, (so, po, ln) in enumerate(jobs):
+        for comp in range(2):
+            e = sum(ks[so + t] * logs[2 * (po + t) + comp] for t in range(ln)) % N
+            assert out[128 * q + 64 * comp:128 * q + 64 * comp + 64] == pb(stark.mul(stark.G, e)), (q, comp)
+        if q % 7 == 0:
+            assert out[128 * q:128 * q + 128] == co.msm(deck[128 * po:128 * (po + ln)], kb[32 * so:32 * (so + ln)], 2, 0)
+    assert ctx.launches > 0
+    jobs = [(0, 0, 1), (3, 7, 0), (5, 2, 40), (0, 0, 60), (10, 50, 50)]
+    out = ctx.msm_jobs(deck, kb, jobs, ncomp=1, window_bits=7)
+    for q, (so, po, ln) in enumerate(jobs):
+        e = sum(ks[so + t] * logs[po + t] for t in range(ln)) % N
+        assert out[64 * q:64 * q + 64] == pb(stark.mul(stark.G, e)), q
+    with pytest.raises(pkg.MpError):
+        ctx.msm_jobs(deck, kb, [(0, 90, 20)], ncomp=1)   # reaches past the points
+    assert ctx.msm_jobs(deck, kb, [], ncomp=2) == b""

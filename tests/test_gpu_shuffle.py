@@ -274,3 +274,95 @@ def test_prove_batch_is_byte_identical_to_single_calls(ctx, m, n, B, workers, mo
     bad[5] = 10 ** 6
     with _pt.raises(Exception):
         ctx.shuffle_and_remask_batch(pk, decks, bad, rhos, rands, host_threads=2)
+
+
+def _scalar_offsets(m, n):
+    """byte offsets of the 5n + 9 scalars of the flat proof layout"""
+    f1 = 64 * (5 * m + 4)
+    f2 = f1 + 32 * (2 * n + 3) + 64 * 3
+    f3 = f2 + 32 * (2 * n + 2) + 64 * (6 * m + 1)
+    return [f1 + 32 * k for k in range(2 * n + 3)] + [f2 + 32 * k for k in range(2 * n + 2)] + [f3 + 32 * k for k in range(n + 4)]
+
+
+def test_non_canonical_proof_scalars_are_rejected(ctx, pkg):
+    """s and s + order must not both verify (proof malleability): ark-serialize's CanonicalDeserialize rejects a
+    scalar >= the group order before the reference's verifier runs; here the C ABI returns MP_ERR_NOT_CANONICAL,
+    as the oracle does, for EVERY scalar position of the proof."""
+    fx = GOLD["shuffle"][2]
+    setup_ctx(ctx, fx)
+    m, n = fx["m"], fx["n"]
+    co = c_oracle.COracle()
+    args = (m, n, h(fx["enc_g"]), h(fx["ck_g"]), h(fx["ck_h"]), h(fx["ghat"]), h(fx["pk"]))
+    proof = h(fx["proof"])
+    offs = _scalar_offsets(m, n)
+    assert len(offs) == 5 * n + 9 and offs[-1] + 32 == len(proof)
+    for off in offs:
+        s = int.from_bytes(proof[off:off + 32], "little")
+        assert s < stark.N
+        if s + stark.N >= 1 << 256:
+            continue
+        p2 = proof[:off] + (s + stark.N).to_bytes(32, "little") + proof[off + 32:]
+        assert co.verify(*args, h(fx["deck"]), h(fx["deck2"]), p2) == -5
+        with pytest.raises(pkg.MpError) as e:
+            ctx.verify_shuffle(h(fx["pk"]), h(fx["deck"]), h(fx["deck2"]), p2)
+        assert e.value.code == -5, off
+    # the Python oracle agrees
+    with pytest.raises(bg.NonCanonicalScalar):
+        bg.proof_from_bytes(p2, m, n)
+    # the repository's proof container refuses the same bytes at deserialisation
+    with pytest.raises(pkg.MpError) as e:
+        ctx.proof_deserialize(m, n, ctx.proof_serialize(m, n, p2))
+    assert e.value.code == -5
+    assert ctx.proof_deserialize(m, n, ctx.proof_serialize(m, n, proof)) == proof
+
+
+@pytest.mark.parametrize("m,n,B", [(3, 4, 6)])
+def test_verify_batch_reports_malformed_items_individually(ctx, pkg, m, n, B, monkeypatch):
+    """One malformed proof (a scalar >= the order; a point off the curve) must not block the other players' proofs:
+    statuses[i] = MP_VERIFY_MALFORMED (7) for that item, the rest of the batch is verified as usual -- in the
+    lockstep implementation and on the worker-context path of large decks."""
+    (enc_g, ck_g, ck_h, ghat, pk), decks, decks2, proofs = _batch(m, n, list(range(70, 70 + B)))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    plen, dlen = len(proofs) // B, 128 * m * n
+    bad = bytearray(proofs)
+    off = plen * 1 + _scalar_offsets(m, n)[3]                       # item 1: scalar + order
+    s = int.from_bytes(bad[off:off + 32], "little")
+    bad[off:off + 32] = (s + stark.N).to_bytes(32, "little")
+    bad[plen * 3 + 5] ^= 1                                          # item 3: proof point off the curve
+    bad[plen * 4 - 1 - 32 * 3] ^= 1                                 # item 3 again (irrelevant) ...
+    bad_decks2 = bytearray(decks2)
+    bad_decks2[4 * dlen + 70] ^= 1                                  # item 4: a shuffled-deck point off the curve
+    bad[plen * 6 - 1 - 32 * 3] ^= 1                                 # item 5: well-formed but wrong -> multi-exp (4)
+    want = [0, 7, 0, 7, 7, 4]
+    assert ctx.verify_shuffle_batch(pk, decks, bytes(bad_decks2), bytes(bad), host_threads=2) == want
+    assert pkg.lib.mp_verify_status_string(7).startswith(b"malformed")
+    monkeypatch.setenv("MP_SMALL_DECK_MAX", "0")                    # the large-deck path: single-proof verifier on worker contexts
+    assert ctx.verify_shuffle_batch(pk, decks, bytes(bad_decks2), bytes(bad), host_threads=2) == want
+    monkeypatch.delenv("MP_SMALL_DECK_MAX")
+    # the single-proof entry points name the defect
+    for i, code in ((1, -5), (3, -3), (4, -3)):
+        with pytest.raises(pkg.MpError) as e:
+            ctx.verify_shuffle(pk, decks[i * dlen:(i + 1) * dlen], bytes(bad_decks2[i * dlen:(i + 1) * dlen]), bytes(bad[i * plen:(i + 1) * plen]))
+        assert e.value.code == code
+
+
+def test_remask_flags_do_not_hide_each_other(ctx, pkg):
+    """An out-of-range permutation entry and an off-curve public key in the same call: the off-curve key must be
+    reported (and must not be cached as a valid table); then the same bad key alone; then a good key."""
+    fx = GOLD["shuffle"][0]
+    setup_ctx(ctx, fx)
+    N = fx["m"] * fx["n"]
+    bad_pk = bytearray(h(fx["pk"]))
+    bad_pk[3] ^= 1
+    bad_perm = list(fx["perm"])
+    bad_perm[0] = N + 5
+    with pytest.raises(pkg.MpError) as e:
+        ctx.remask(bytes(bad_pk), h(fx["deck"]), bad_perm, h(fx["rho"]))
+    assert e.value.code == -3
+    with pytest.raises(pkg.MpError) as e:      # the garbage table of the rejected key must not have been cached
+        ctx.remask(bytes(bad_pk), h(fx["deck"]), fx["perm"], h(fx["rho"]))
+    assert e.value.code == -3
+    with pytest.raises(pkg.MpError) as e:
+        ctx.remask(h(fx["pk"]), h(fx["deck"]), bad_perm, h(fx["rho"]))
+    assert e.value.code == -1
+    assert ctx.remask(h(fx["pk"]), h(fx["deck"]), fx["perm"], h(fx["rho"])).hex() == fx["deck2"]

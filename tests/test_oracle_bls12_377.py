@@ -142,3 +142,67 @@ def test_wire_serialisation_of_the_second_curve(pkg):
         assert len(ser) == (11 * fx["m"] + 8) * 48 + (5 * fx["n"] + 9) * 32 == pkg.lib.mp377_proof_serialized_len(fx["m"], fx["n"])
     sizes = {(m, n): pkg.lib.mp377_proof_serialized_len(m, n) for m, n in [(2, 150), (6, 50), (10, 30), (12, 25), (30, 10)]}
     assert min(sizes, key=sizes.get) == (10, 30)
+
+
+def test_g1_membership_test_by_endomorphism():
+    """The subgroup test the GPU verifier applies to untrusted BLS12-377 points (csrc/capi_bls12_377.cu
+    k377_subgroup_check; the one ark-bls12-377 uses for CanonicalDeserialize): phi(P) == -[u^2]P with
+    phi(x, y) = (beta x, y).  Big-int check of the constants and of the test's behaviour on subgroup points, random
+    curve points, pure cofactor-torsion points and G1 + torsion."""
+    import random
+    Q, R = bls.Q, bls.N
+    u = 0x8508c00000000001
+    assert u == bls.X_PARAM and (u * u).bit_length() == 127 and bin(u * u).count("1") == 22
+    assert u * u == 0x452217cc900000010a11800000000001
+    beta = 0x1ae3a4617c510eabc8756ba8f8c524eb8882a75cc9bc8e359064ee822fb5bffd1e945779fffffffffffffffffffffff
+    assert beta != 1 and pow(beta, 3, Q) == 1
+    # the Montgomery constant in the kernel (beta * 2^384 mod q, little-endian words)
+    words = [0x5a7b8727, 0x2c766f92, 0x253d58b5, 0x03d7f6b0, 0xec122131, 0x838ec0de, 0xf658bb10, 0xbd5eb3e9, 0x6ed3e52e,
+             0x6942bd12, 0xdd04ed6a, 0x01673786]
+    assert sum(w << (32 * i) for i, w in enumerate(words)) == beta * (1 << 384) % Q
+
+    def smul(P, k):  # plain double-and-add (bls.mul reduces the scalar mod r, which is wrong outside G1)
+        acc = None
+        for bit in bin(k)[2:]:
+            acc = bls.add(acc, acc)
+            if bit == "1":
+                acc = bls.add(acc, P)
+        return acc
+
+    def member(P):
+        if P is None:
+            return True
+        T = smul(P, u * u)
+        return T is not None and (beta * P[0] % Q, P[1]) == bls.neg(T)
+
+    rnd = random.Random(3)
+    assert all(member(bls.mul(bls.G, rnd.randrange(1, R))) for _ in range(4))
+    found = 0
+    while found < 3:
+        x = rnd.randrange(Q)
+        y2 = (x * x * x + 1) % Q
+        if pow(y2, (Q - 1) // 2, Q) != 1:
+            continue
+        # square root by Tonelli-Shanks (q - 1 = 2^46 * odd)
+        q, s = Q - 1, 0
+        while q % 2 == 0:
+            q //= 2
+            s += 1
+        z = 2
+        while pow(z, (Q - 1) // 2, Q) != Q - 1:
+            z += 1
+        m, c, t, r = s, pow(z, q, Q), pow(y2, q, Q), pow(y2, (q + 1) // 2, Q)
+        while t != 1:
+            i, tt = 0, t
+            while tt != 1:
+                tt = tt * tt % Q
+                i += 1
+            b = pow(c, 1 << (m - i - 1), Q)
+            m, c = i, b * b % Q
+            t, r = t * c % Q, r * b % Q
+        P = (x, r)
+        assert bls.is_on_curve(P) and not member(P)
+        T = smul(P, R)
+        if T is not None:
+            assert smul(T, bls.COFACTOR) is None and not member(T) and not member(bls.add(bls.G, T))
+            found += 1

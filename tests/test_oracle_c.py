@@ -121,3 +121,27 @@ def test_threads_do_not_change_results(co):
     assert co.prove(*a, h(fx["deck"]), h(fx["deck2"]), fx["perm"], h(fx["rho"]), h(fx["rand"])).hex() == fx["proof"]
     assert co.verify(*a, h(fx["deck"]), h(fx["deck2"]), h(fx["proof"])) == 0
     co.set(threads=1)
+
+
+def test_non_canonical_proof_scalars_are_rejected_by_both_oracles(co):
+    """`Proof: CanonicalDeserialize` (reference src/lib.rs:45-71): a scalar >= the group order never reaches the
+    reference's verifier.  Both restatements reject it (-5 = MP_ERR_NOT_CANONICAL / NonCanonicalScalar)."""
+    import pytest
+    from oracle.py import bayer_groth as bg, stark
+    fx = GOLD["shuffle"][0]
+    m, n = fx["m"], fx["n"]
+    h = bytes.fromhex
+    args = (m, n, h(fx["enc_g"]), h(fx["ck_g"]), h(fx["ck_h"]), h(fx["ghat"]), h(fx["pk"]), h(fx["deck"]), h(fx["deck2"]))
+    proof = h(fx["proof"])
+    assert co.verify(*args, proof) == 0
+    f1 = 64 * (5 * m + 4)
+    f2 = f1 + 32 * (2 * n + 3) + 64 * 3
+    f3 = f2 + 32 * (2 * n + 2) + 64 * (6 * m + 1)
+    for off in (f1, f1 + 32 * (2 * n + 2), f2, f2 + 32 * (2 * n + 1), f3, len(proof) - 32):
+        s = int.from_bytes(proof[off:off + 32], "little")
+        p2 = proof[:off] + (s + stark.N).to_bytes(32, "little") + proof[off + 32:]
+        assert co.verify(*args, p2) == -5
+        with pytest.raises(bg.NonCanonicalScalar):
+            bg.proof_from_bytes(p2, m, n)
+    # points are untouched by the check: the first point run ends where the first scalar run starts
+    assert co.verify(*args, proof[:f1 - 1] + bytes([proof[f1 - 1] ^ 0x80]) + proof[f1:]) != -5
