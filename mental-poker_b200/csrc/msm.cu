@@ -842,25 +842,86 @@ __global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restri
   }
 }
 
-// Thread per (job, comp): Horner over the job's W window sums.  253 dependent doublings are the
-// latency floor of every MSM call, so the group operations are inlined here (registers only,
-// no ABI calls) and the loop is kept rolled.
+// ------------------------------------------------------------------------------------------
+// Horner fold over a job's W window sums: the one inherently serial piece of a (non-table) MSM -- c*(W-1) ~ 240
+// dependent doublings.  A doubling is ten field multiplications of which only three are on its critical path, so
+// a QUAD of lanes owns one (job, comp) accumulator -- lane 0 holds X, lane 1 Y, lane 2 ZZ, lane 3 ZZZ -- and runs
+// dbl-2008-s-1 in three multiplication levels, every level ONE uniform fq_mul / fq_sqr whose operands each lane
+// picks for its role, results exchanged with quad-masked shuffles:
+//   level 1 (squares)   XX = X^2          | V = (2Y)^2       | ZZ2 = ZZ^2 (a = 1)  | --
+//   level 2             S = X V           | W = U V          | ZZ3 = V ZZ          | MM = M^2,  M = 3 XX (+ ZZ2)
+//   level 3             t = M (S - X3)    | WY = W Y         | --                  | ZZZ3 = W ZZZ     X3 = MM - 2S
+//   then                X3                | Y3 = t - WY      | ZZ3                 | ZZZ3
+// ~2 000 cycles per doubling instead of ~6 000 for one thread.  The W - 1 additions of the window sums gather the
+// accumulator into every lane of the quad and run the complete xyzz_add redundantly (all special cases kept).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ fq fq_shfl(uint32_t mask, const fq& v, int src) {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < kFqLimbs; i++) r.v[i] = __shfl_sync(mask, v.v[i], src);
+  return r;
+}
+__device__ __forceinline__ fq fq_select(bool c, const fq& a, const fq& b) {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < kFqLimbs; i++) r.v[i] = c ? a.v[i] : b.v[i];
+  return r;
+}
+// one doubling of the quad's accumulator (not the identity); `home` = this lane's coordinate
+__device__ __forceinline__ void quad_dbl(fq& home, int role, int base, uint32_t mask) {
+  const fq U = fq_add(home, home);                                  // lane 1: 2Y  [4]
+  const fq s1 = fq_sqr(role == 1 ? U : home);                       // XX | V | ZZ2 | (unused)
+  const fq XX = fq_shfl(mask, s1, base), V = fq_shfl(mask, s1, base + 1);
+#if MP_CURVE_A_IS_ZERO
+  const fq M = fq_reduce_weak(fq_add(fq_add(XX, XX), XX));
+#else
+  const fq ZZ2 = fq_shfl(mask, s1, base + 2);
+  const fq M = fq_reduce_weak(fq_add(fq_add(XX, XX), fq_add(XX, ZZ2)));
+#endif
+  const fq a2 = fq_select(role == 3, M, role == 1 ? U : home);
+  const fq s2 = fq_mul(a2, fq_select(role == 3, M, V));             // S | W | ZZ3 | MM
+  const fq S = fq_shfl(mask, s2, base), Wv = fq_shfl(mask, s2, base + 1), MM = fq_shfl(mask, s2, base + 3);
+  const fq X3 = fq_reduce_weak(fq_sub(MM, fq_add(S, S), 4));
+  const fq s3 = fq_mul(fq_select(role == 0, M, Wv), fq_select(role == 0, fq_sub(S, X3, 2), home));  // t | WY | -- | ZZZ3
+  const fq t = fq_shfl(mask, s3, base);
+  // Y == 0 (mod p) would make ZZ3 == 0 (mod p): the result is the identity, stored as exact zero words
+  const bool dead = __shfl_sync(mask, (int)fq_is_zero_mod_p_2(s2), base + 2) != 0;
+  fq out = role == 0 ? X3 : (role == 1 ? fq_reduce_weak(fq_sub(t, s3, 2)) : (role == 2 ? s2 : s3));
+  home = dead ? fq_zero() : out;
+}
+__device__ __forceinline__ xyzz quad_gather(const fq& home, int base, uint32_t mask) {
+  xyzz r;
+  r.X = fq_shfl(mask, home, base); r.Y = fq_shfl(mask, home, base + 1);
+  r.ZZ = fq_shfl(mask, home, base + 2); r.ZZZ = fq_shfl(mask, home, base + 3);
+  return r;
+}
+__device__ __forceinline__ fq quad_home(const xyzz& p, int role) {
+  return role == 0 ? p.X : (role == 1 ? p.Y : (role == 2 ? p.ZZ : p.ZZZ));
+}
+
+// Quad per (job, comp); a block of 32 threads folds 8 of them.
 __global__ void __launch_bounds__(32) k_fold(const xyzz* __restrict__ win_out, int njobs, int W,
                                              int c, int ncomp, xyzz* __restrict__ out) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= njobs * ncomp) return;
-  int job = g / ncomp, comp = g % ncomp;
-  xyzz acc = xyzz_load(win_out + ((uint64_t)(job * W + W - 1)) * ncomp + comp);
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const uint32_t mask = 0xfu << base;
+  const int g = blockIdx.x * 8 + (lane >> 2);
+  if (g >= njobs * ncomp) return;  // whole quads leave together
+  const int job = g / ncomp, comp = g % ncomp;
+  fq home = quad_home(xyzz_load(win_out + ((uint64_t)(job * W + W - 1)) * ncomp + comp), role);
 #pragma unroll 1
   for (int w = W - 2; w >= 0; w--) {
-    if (!xyzz_is_identity(acc)) {
+    const bool is_id = fq_is_zero_raw(fq_shfl(mask, home, base + 2));
+    if (!is_id) {
 #pragma unroll 1
-      for (int k = 0; k < c; k++) acc = xyzz_dbl(acc);
+      for (int k = 0; k < c; k++) quad_dbl(home, role, base, mask);
     }
-    xyzz v = xyzz_load(win_out + ((uint64_t)(job * W + w)) * ncomp + comp);
-    xyzz_add(acc, v);
+    xyzz acc = quad_gather(home, base, mask);
+    const xyzz v = xyzz_load(win_out + ((uint64_t)(job * W + w)) * ncomp + comp);
+    acc = xyzz_add_v(acc, v);
+    home = quad_home(acc, role);
   }
-  xyzz_store(out + g, acc);
+  const xyzz res = quad_gather(home, base, mask);
+  if (role == 0) xyzz_store(out + g, res);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1051,7 +1112,7 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     else if (win_mode == 4) k_reduce_win<3><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
     else k_reduce_win<0><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
   }
-  k_fold<<<(unsigned)((njobs * ncomp + 31) / 32), 32, 0, stream>>>(win_out, njobs, Wb, c, ncomp, d_out);
+  k_fold<<<(unsigned)((njobs * ncomp + 7) / 8), 32, 0, stream>>>(win_out, njobs, Wb, c, ncomp, d_out);
   ws->launches += 3;
   return cudaGetLastError();
 }
