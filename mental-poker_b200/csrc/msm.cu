@@ -18,7 +18,6 @@ static constexpr int kChunkMin = 32;      // sorted entries per accumulate threa
 static constexpr int kChunkMax = 128;     // ... when the launch still fills the chip several times over
 static constexpr int kAccThreads = 128;   // accumulate block size
 static constexpr int kSegLen = 16;        // buckets per k_reduce_seg thread
-static constexpr int kWinThreads = 256;   // k_reduce_win block size
 static constexpr uint32_t kNoDigit = 0xffffffffu;
 // record sizes of the curve selected in fq.cuh (Stark: 8-limb coordinates, BLS12-377: 12)
 static constexpr int kPointWords = 2 * kFqLimbs;                 // canonical x || y
@@ -154,15 +153,6 @@ __device__ __forceinline__ affine affine_load(const affine* p) {
   for (int i = 0; i < kAffVec; i++) d[i] = __ldg(s + i);
   return r;
 }
-__device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz& v, int delta) {
-  xyzz r;
-  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
-  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4 * kXyzzVec; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
-  return r;
-}
-
 // ------------------------------------------------------------------------------------------
 // ingest / export
 // ------------------------------------------------------------------------------------------
@@ -637,7 +627,7 @@ __global__ void __launch_bounds__(kAccThreads, MINBLOCKS)
 // split between bucket_sums[b] (the run that started inside a chunk) and the `part` of every
 // chunk whose first entry lies in the bucket.  The first such chunk ("leader") folds the parts
 // into bucket_sums[b]; only buckets that contain a chunk boundary are touched at all.
-__global__ void __launch_bounds__(128) k_stitch(const uint32_t* __restrict__ offsets, uint64_t nbuckets,
+__global__ void __launch_bounds__(128, 4) k_stitch(const uint32_t* __restrict__ offsets, uint64_t nbuckets,
                                                 const uint32_t* __restrict__ chunk_bucket, int ncomp,
                                                 xyzz* __restrict__ bucket_sums, const xyzz* __restrict__ part,
                                                 uint32_t kChunk) {
@@ -653,7 +643,7 @@ __global__ void __launch_bounds__(128) k_stitch(const uint32_t* __restrict__ off
   if (offsets[b] % kChunk != 0) acc = xyzz_load(bucket_sums + (uint64_t)b * ncomp + comp);
   for (uint64_t u = t; u < nchunks && chunk_bucket[u] == b; u++) {
     xyzz p = xyzz_load(part + u * ncomp + comp);
-    xyzz_add_ni(acc, p);
+    xyzz_add(acc, p);  // inlined: nearly every thread of a single large MSM adds exactly one partial
   }
   xyzz_store(bucket_sums + (uint64_t)b * ncomp + comp, acc);
 }
@@ -687,37 +677,12 @@ __global__ void __launch_bounds__(128, 3) k_reduce_seg(const uint32_t* __restric
   xyzz_store(segT + g, acc);
 }
 
-// Small-nseg variant of the per-window combine: thread per (window, comp), serial over the
-// window's segments.  out = sum_s T_s + L * sum_s s * S_s.
-__global__ void __launch_bounds__(64) k_reduce_win_serial(const xyzz* __restrict__ segS,
-                                                          const xyzz* __restrict__ segT, uint64_t nwincomp,
-                                                          uint32_t nseg, uint32_t L, int ncomp,
-                                                          xyzz* __restrict__ win_out) {
-  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nwincomp) return;
-  const uint32_t comp = (uint32_t)(g % ncomp);
-  const uint64_t win = g / ncomp;
-  const xyzz* S = segS + win * nseg * ncomp + comp;
-  const xyzz* T = segT + win * nseg * ncomp + comp;
-  xyzz run = xyzz_identity(), lsum = xyzz_identity(), tsum = xyzz_load(T);
-  for (uint32_t s = nseg - 1; s >= 1; s--) {
-    xyzz a = xyzz_load(S + (uint64_t)s * ncomp);
-    xyzz_add_ni(run, a);
-    xyzz_add_ni(lsum, run);
-    xyzz tv = xyzz_load(T + (uint64_t)s * ncomp);
-    xyzz_add_ni(tsum, tv);
-  }
-  for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(lsum);
-  xyzz_add_ni(tsum, lsum);
-  xyzz_store(win_out + g, tsum);
-}
-
 // Hierarchical form of the same combine: thread per (window, group of G consecutive segments, comp) folds
 // its group into ONE segment of length L*G (G a power of two),
 //   S' = sum_i S_i,   T' = sum_i T_i + L * sum_i i * S_i     (i = index inside the group),
 // because a bucket at offset j of sub-segment i has weight i*L + (j+1) in the merged segment.  Applying it
-// until one segment per window is left yields T' = the window sum.  Serial per thread, no cross-lane
-// traffic: used by the 12-limb build, where the block-wide kernel below does not reproduce it (see DESIGN).
+// until one segment per window is left yields T' = the window sum.  One thread per group: the form for launches
+// with many windows (batches of small jobs); k_reduce_group_quad is the same recurrence for few.
 __global__ void __launch_bounds__(64) k_reduce_group(const xyzz* __restrict__ segS, const xyzz* __restrict__ segT,
                                                      uint64_t nwin, uint32_t nseg, uint32_t G, uint32_t L, int ncomp,
                                                      xyzz* __restrict__ outS, xyzz* __restrict__ outT) {
@@ -743,103 +708,6 @@ __global__ void __launch_bounds__(64) k_reduce_group(const xyzz* __restrict__ se
   xyzz_add_ni(tsum, lsum);
   xyzz_store(outS + g, run);
   xyzz_store(outT + g, tsum);
-}
-
-// block-wide sum of one xyzz per thread (kWinThreads threads); result valid in thread 0
-// MODE (experiment knob of k_reduce_win, see scripts/sanitize.sh): 0 = divergent call after the shuffle (as
-// written in round 1); 1 = the same + __syncwarp() after the call; 2 = every lane makes the call (lanes that
-// must not add pass the identity); 3 = exchange through shared memory instead of shuffles.
-template <int MODE>
-__device__ __forceinline__ void lane_add(xyzz& v, const xyzz& o, bool take) {
-  if (MODE == 2) {
-    xyzz q = take ? o : xyzz_identity();
-    xyzz_add_ni(v, q);
-  } else {
-    if (take) xyzz_add_ni(v, o);
-    if (MODE == 1) __syncwarp();
-  }
-}
-template <int MODE>
-__device__ __forceinline__ xyzz lane_down(const xyzz& v, int delta, xyzz* xch /* [kWinThreads] or null */) {
-  if (MODE == 3) {
-    __syncthreads();
-    xch[threadIdx.x] = v;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    return lane + delta < 32 ? xch[threadIdx.x + delta] : v;  // out of range: own value, like shfl.down
-  }
-  return xyzz_shfl_down(v, delta);
-}
-template <int MODE>
-__device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem /* kWinThreads/32 entries */, xyzz* xch) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    xyzz o = lane_down<MODE>(v, d, xch);
-    lane_add<MODE>(v, o, lane < d);
-  }
-  __syncthreads();
-  if (lane == 0) smem[warp] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kWinThreads / 32; w++) xyzz_add_ni(v, smem[w]);
-  }
-  __syncthreads();
-  return v;
-}
-
-// Block per (window, comp):  out = sum_s T_s + L * sum_s s * S_s.
-// sum_s s*S_s = sum_{i>=0} Suf_A(i) with A[i] = S_{i+1}: block-wide suffix scan.
-template <int MODE>
-__global__ void __launch_bounds__(kWinThreads) k_reduce_win(const xyzz* __restrict__ segS,
-                                                            const xyzz* __restrict__ segT,
-                                                            uint32_t nseg, uint32_t L, int ncomp,
-                                                            xyzz* __restrict__ win_out, xyzz* __restrict__ xch_all) {
-  __shared__ xyzz smem[kWinThreads / 32];
-  xyzz* xch = MODE == 3 ? xch_all + (size_t)blockIdx.x * kWinThreads : nullptr;  // global scratch stands in for smem
-  const uint32_t comp = blockIdx.x % ncomp;
-  const uint64_t win = blockIdx.x / ncomp;
-  const xyzz* S = segS + win * nseg * ncomp + comp;
-  const xyzz* T = segT + win * nseg * ncomp + comp;
-  const uint32_t ipt = (nseg + kWinThreads - 1) / kWinThreads;  // power of two (nseg, threads are)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // local suffix sums over A[tid*ipt .. tid*ipt+ipt)
-  xyzz run = xyzz_identity(), lsum = xyzz_identity(), tsum = xyzz_identity();
-  for (int q = (int)ipt - 1; q >= 0; q--) {
-    uint32_t i = threadIdx.x * ipt + q;      // index into A
-    if (i + 1 < nseg) {
-      xyzz a = xyzz_load(S + (uint64_t)(i + 1) * ncomp);
-      xyzz_add_ni(run, a);
-    }
-    xyzz_add_ni(lsum, run);
-    if (i < nseg) {
-      xyzz tv = xyzz_load(T + (uint64_t)i * ncomp);
-      xyzz_add_ni(tsum, tv);
-    }
-  }
-  // exclusive suffix scan of `run` over threads: above = sum_{t' > tid} run_{t'}
-  xyzz inc = run;
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    xyzz o = lane_down<MODE>(inc, d, xch);
-    lane_add<MODE>(inc, o, lane + d < 32);
-  }
-  if (lane == 0) smem[warp] = inc;  // warp total
-  xyzz above = lane_down<MODE>(inc, 1, xch);
-  if (lane == 31) above = xyzz_identity();
-  __syncthreads();
-  for (int w = warp + 1; w < kWinThreads / 32; w++) xyzz_add_ni(above, smem[w]);
-  __syncthreads();
-  // U_t = lsum + ipt * above
-  for (uint32_t k = 1; k < ipt; k <<= 1) xyzz_dbl_ni(above);
-  xyzz_add_ni(lsum, above);
-  xyzz U = block_sum_xyzz<MODE>(lsum, smem, xch);
-  xyzz Tt = block_sum_xyzz<MODE>(tsum, smem, xch);
-  if (threadIdx.x == 0) {
-    for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(U);
-    xyzz_add_ni(Tt, U);
-    xyzz_store(win_out + blockIdx.x, Tt);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -897,6 +765,69 @@ __device__ __forceinline__ xyzz quad_gather(const fq& home, int base, uint32_t m
 }
 __device__ __forceinline__ fq quad_home(const xyzz& p, int role) {
   return role == 0 ? p.X : (role == 1 ? p.Y : (role == 2 ? p.ZZ : p.ZZZ));
+}
+
+// acc += q for the quad's accumulator; q is fully present in every lane of the quad.  add-2008-s in FOUR
+// multiplication levels (a thread needs fourteen multiplications in a row):
+//   level 1   U1 = X1 q.ZZ      | S1 = Y1 q.ZZZ        | U2 = q.X ZZ1         | S2 = q.Y ZZZ1         P = U2-U1, R = S2-S1
+//   level 2   PP = P^2          | RR = R^2             | ZZ12 = ZZ1 q.ZZ      | ZZZ12 = ZZZ1 q.ZZZ
+//   level 3   Q = U1 PP         | PPP = P PP           | ZZ3 = ZZ12 PP        | (PPP)                 X3 = RR - PPP - 2Q
+//   level 4   --                | t1 = R (Q - X3)      | t2 = S1 PPP          | ZZZ3 = ZZZ12 PPP      Y3 = t1 - t2
+// Identities are handled before level 1; equal x-coordinates (doubling / cancellation, seen at level 3) fall back
+// to the complete single-thread formula on the gathered accumulator.
+__device__ __forceinline__ void quad_add(fq& home, const xyzz& q, int role, int base, uint32_t mask) {
+  if (xyzz_is_identity(q)) return;                                   // quad-uniform: q is the same in all four lanes
+  if (fq_is_zero_raw(fq_shfl(mask, home, base + 2))) { home = quad_home(q, role); return; }
+  const fq s1 = fq_mul(home, role == 0 ? q.ZZ : (role == 1 ? q.ZZZ : (role == 2 ? q.X : q.Y)));
+  const fq U1 = fq_shfl(mask, s1, base), S1 = fq_shfl(mask, s1, base + 1);
+  const fq P = fq_sub(fq_shfl(mask, s1, base + 2), U1, 2), R = fq_sub(fq_shfl(mask, s1, base + 3), S1, 2);  // [4]
+  const fq a2 = role == 0 ? P : (role == 1 ? R : home);
+  const fq s2 = fq_mul(a2, role == 0 ? P : (role == 1 ? R : (role == 2 ? q.ZZ : q.ZZZ)));
+  const fq PP = fq_shfl(mask, s2, base), RR = fq_shfl(mask, s2, base + 1);
+  const fq s3 = fq_mul(role == 0 ? U1 : (role == 2 ? s2 : P), PP);
+  if (__shfl_sync(mask, (int)fq_is_zero_mod_p_2(s3), base + 2)) {    // P == 0 (mod p): same x
+    xyzz acc = quad_gather(home, base, mask);
+    acc = xyzz_add_v(acc, q);
+    home = quad_home(acc, role);
+    return;
+  }
+  const fq Q = fq_shfl(mask, s3, base), PPP = fq_shfl(mask, s3, base + 1);
+  const fq X3 = fq_reduce_weak(fq_sub(RR, fq_add(PPP, fq_add(Q, Q)), 6));
+  const fq s4 = fq_mul(role == 1 ? R : (role == 2 ? S1 : s2), role == 1 ? fq_sub(Q, X3, 2) : PPP);
+  const fq t2 = fq_shfl(mask, s4, base + 2);
+  home = role == 0 ? X3 : (role == 1 ? fq_reduce_weak(fq_sub(s4, t2, 2)) : (role == 2 ? s3 : s4));
+}
+
+// Quad form of k_reduce_group for launches too small to fill the chip with one thread per group (a single large
+// MSM has 16 windows): same recurrence, every group operation cooperative.
+__global__ void __launch_bounds__(128) k_reduce_group_quad(const xyzz* __restrict__ segS, const xyzz* __restrict__ segT,
+                                                           uint64_t nwin, uint32_t nseg, uint32_t G, uint32_t L, int ncomp,
+                                                           xyzz* __restrict__ outS, xyzz* __restrict__ outT) {
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const uint32_t mask = 0xfu << base;
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const uint32_t ngroups = nseg / G;
+  if (g >= nwin * ngroups * ncomp) return;  // whole quads leave together
+  const uint32_t comp = (uint32_t)(g % ncomp);
+  const uint64_t wg = g / ncomp;
+  const uint64_t win = wg / ngroups, grp = wg % ngroups;
+  const xyzz* S = segS + (win * nseg + grp * G) * ncomp + comp;
+  const xyzz* T = segT + (win * nseg + grp * G) * ncomp + comp;
+  fq run = fq_zero(), lsum = fq_zero(), tsum = quad_home(xyzz_load(T), role);
+#pragma unroll 1
+  for (uint32_t i = G - 1; i >= 1; i--) {
+    quad_add(run, xyzz_load(S + (uint64_t)i * ncomp), role, base, mask);
+    quad_add(lsum, quad_gather(run, base, mask), role, base, mask);
+    quad_add(tsum, xyzz_load(T + (uint64_t)i * ncomp), role, base, mask);
+  }
+  quad_add(run, xyzz_load(S), role, base, mask);  // S' includes sub-segment 0 (weight 0 in lsum)
+  if (!fq_is_zero_raw(fq_shfl(mask, lsum, base + 2))) {
+#pragma unroll 1
+    for (uint32_t k = 1; k < L; k <<= 1) quad_dbl(lsum, role, base, mask);
+  }
+  quad_add(tsum, quad_gather(lsum, base, mask), role, base, mask);
+  const xyzz rS = quad_gather(run, base, mask), rT = quad_gather(tsum, base, mask);
+  if (role == 0) { xyzz_store(outS + g, rS); xyzz_store(outT + g, rT); }
 }
 
 // Quad per (job, comp); a block of 32 threads folds 8 of them.
@@ -1073,44 +1004,35 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     ws->launches++;
   }
   k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
-  static const bool force_serial = [] { const char* e = getenv("MP_WIN_SERIAL"); return e && atoi(e) != 0; }();
-  static const bool force_block = [] { const char* e = getenv("MP_WIN_BLOCK"); return e && atoi(e) != 0; }();
-  // 12-limb build (and MP_WIN_SERIAL=1 on either curve, which cross-checks it against the block-wide kernel):
-  // fold groups of 4 segments, level after level, until one segment per window is left -- its T' is the
-  // window sum.  A level is 4 iterations of 3 additions per thread; the serial combine of 32 segments
-  // (96 dependent additions of ~14 field multiplications at ~1.2 us each) took 1.4 ms, two levels of 32
-  // took 2.1 ms each -- 2048 segments now fold in six levels of ~0.2 ms.
-  const bool hier = ((kFqLimbs > 8 && !force_block) || force_serial) && nseg > 4;
-  if (hier) {
+  // Per-window combine of the segment sums: fold groups of 4 segments, level after level, until one segment per
+  // window is left -- its T' is the window sum (ONE kernel family for both curves; the block-wide shuffle-scan
+  // kernel of round 1 is gone).  A level with few groups runs the quad-cooperative kernel.
+  {
     xyzz *ping, *pong;
-    const size_t lvl = nwin * (nseg / 4) * ncomp;  // outputs of the first (largest) level
-    MP_CK(ws->get(14, 2 * lvl, &ping));            // [S | T] of the even levels
-    MP_CK(ws->get(15, 2 * lvl, &pong));            // [S | T] of the odd levels
+    const size_t lvl = nwin * ((nseg + 3) / 4) * ncomp;  // outputs of the first (largest) level
+    MP_CK(ws->get(14, 2 * lvl, &ping));                  // [S | T] of the even levels
+    MP_CK(ws->get(15, 2 * lvl, &pong));                  // [S | T] of the odd levels
+    static const uint64_t quad_below = [] { const char* e = getenv("MP_QUAD_BELOW"); return e ? strtoull(e, nullptr, 10) : 40000ull; }();
     const xyzz *curS = segS, *curT = segT;
     uint32_t cur_nseg = nseg, cur_L = L;
-    for (int level = 0; cur_nseg > 1; level++) {
+    int level = 0;
+    do {
       const uint32_t G = std::min<uint32_t>(4, cur_nseg);
       xyzz* buf = (level & 1) ? pong : ping;
       const bool last = cur_nseg == G;
-      const uint64_t threads = nwin * (cur_nseg / G) * ncomp;
-      k_reduce_group<<<(unsigned)((threads + 63) / 64), 64, 0, stream>>>(curS, curT, nwin, cur_nseg, G, cur_L, ncomp, buf,
-                                                                         last ? win_out : buf + lvl);
+      const uint64_t groups = nwin * (cur_nseg / G) * ncomp;
+      if (groups < quad_below)
+        k_reduce_group_quad<<<(unsigned)((groups * 4 + 127) / 128), 128, 0, stream>>>(curS, curT, nwin, cur_nseg, G, cur_L, ncomp, buf,
+                                                                                   last ? win_out : buf + lvl);
+      else
+        k_reduce_group<<<(unsigned)((groups + 63) / 64), 64, 0, stream>>>(curS, curT, nwin, cur_nseg, G, cur_L, ncomp, buf,
+                                                                        last ? win_out : buf + lvl);
       ws->launches++;
       curS = buf; curT = buf + lvl;
       cur_nseg /= G; cur_L *= G;
-    }
+      level++;
+    } while (cur_nseg > 1);
     ws->launches -= 1;  // the tally below counts one combine launch
-  } else if (nseg <= 32) {
-    k_reduce_win_serial<<<(unsigned)((nwin * ncomp + 63) / 64), 64, 0, stream>>>(segS, segT, nwin * ncomp, nseg, L, ncomp, win_out);
-  } else {
-    static const int win_mode = [] { const char* e = getenv("MP_WIN_BLOCK"); return e ? atoi(e) : 0; }();
-    xyzz* xch = nullptr;
-    if (win_mode == 4) MP_CK(ws->get(14, nwin * ncomp * (size_t)kWinThreads, &xch));
-    const unsigned wb = (unsigned)(nwin * ncomp);
-    if (win_mode == 2) k_reduce_win<1><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
-    else if (win_mode == 3) k_reduce_win<2><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
-    else if (win_mode == 4) k_reduce_win<3><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
-    else k_reduce_win<0><<<wb, kWinThreads, 0, stream>>>(segS, segT, nseg, L, ncomp, win_out, xch);
   }
   k_fold<<<(unsigned)((njobs * ncomp + 7) / 8), 32, 0, stream>>>(win_out, njobs, Wb, c, ncomp, d_out);
   ws->launches += 3;

@@ -16,7 +16,7 @@
 //                    bucket -> perfectly load balanced for ANY digit distribution
 //   k_stitch         fold the partial sums of bucket runs that straddle chunk boundaries
 //   k_reduce_seg     per segment of L buckets: S = sum, T = sum (i+1) * B_i (running sums)
-//   k_reduce_win     per window: block-wide suffix scan over segment sums (warp shuffles)
+//   k_reduce_group(_quad)  per window: groups of 4 segment sums folded level after level (thread or quad per group)
 //   k_fold           per job: Horner over windows (c doublings each)
 #pragma once
 #include <cuda_runtime.h>

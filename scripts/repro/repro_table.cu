@@ -9,17 +9,29 @@
 #include "../../mental-poker_b200/csrc/msm.cu"
 using namespace mp;
 
+// round 1's calling convention of the out-of-line multiplication (pointers); fq_mul() now passes by value
+#ifdef MP_CURVE_BLS12_377
+static __device__ __noinline__ void fq_mul_ptr(fq* r, const fq* a, const fq* b) { const fq x = *a, y = *b; const fq z = fq_mul_inline(x, y); *r = z; }
+#else
+static __device__ __noinline__ void fq_mul_ptr(fq* r, const fq* a, const fq* b) { const fq x = *a, y = *b; const fq z = fq_mul(x, y); *r = z; }
+#endif
+template <bool BYPTR> __device__ __forceinline__ fq t_mul(const fq& a, const fq& b) {
+  if (BYPTR) { fq r; fq_mul_ptr(&r, &a, &b); return r; }
+  return fq_mul(a, b);
+}
+
 struct Dump { fq acc_after[64]; fq z[64]; fq inv0; fq iz[64]; fq inv_after[64]; affine a[64]; };
 
+template <bool BYPTR>
 __global__ void k_trace(const xyzz* tmp, int W, Dump* d) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   fq pre[64];
   fq acc = fq_one();
   for (int w = 0; w < W; w++) {
     xyzz p = xyzz_load(tmp + w);
-    fq z = fq_mul(p.ZZ, p.ZZZ);
+    fq z = t_mul<BYPTR>(p.ZZ, p.ZZZ);
     d->z[w] = z;
-    if (!xyzz_is_identity(p)) acc = fq_mul(acc, z);
+    if (!xyzz_is_identity(p)) acc = t_mul<BYPTR>(acc, z);
     pre[w] = acc;
     d->acc_after[w] = acc;
   }
@@ -27,13 +39,13 @@ __global__ void k_trace(const xyzz* tmp, int W, Dump* d) {
   d->inv0 = inv;
   for (int w = W - 1; w >= 0; w--) {
     xyzz p = xyzz_load(tmp + w);
-    fq z = fq_mul(p.ZZ, p.ZZZ);
-    fq iz = w > 0 ? fq_mul(inv, pre[w - 1]) : inv;
-    inv = fq_mul(inv, z);
+    fq z = t_mul<BYPTR>(p.ZZ, p.ZZZ);
+    fq iz = w > 0 ? t_mul<BYPTR>(inv, pre[w - 1]) : inv;
+    inv = t_mul<BYPTR>(inv, z);
     d->iz[w] = iz;
     d->inv_after[w] = inv;
-    d->a[w].x = fq_reduce_full(fq_mul(p.X, fq_mul(iz, p.ZZZ)));
-    d->a[w].y = fq_reduce_full(fq_mul(p.Y, fq_mul(iz, p.ZZ)));
+    d->a[w].x = fq_reduce_full(t_mul<BYPTR>(p.X, t_mul<BYPTR>(iz, p.ZZZ)));
+    d->a[w].y = fq_reduce_full(t_mul<BYPTR>(p.Y, t_mul<BYPTR>(iz, p.ZZ)));
   }
 }
 
@@ -90,19 +102,28 @@ int main() {
   cudaMalloc(&d_tmp, sizeof(xyzz) * W); cudaMalloc(&d_dump, sizeof(Dump));
   cudaMemcpy(d_tmp, tmp.data(), sizeof(xyzz) * W, cudaMemcpyHostToDevice);
   cudaMemset(d_dump, 0, sizeof(Dump));
-  k_trace<<<1, 32>>>(d_tmp, W, d_dump);
-  Dump g; cudaError_t e = cudaMemcpy(&g, d_dump, sizeof(Dump), cudaMemcpyDeviceToHost);
-  printf("curve limbs=%d W=%d cuda=%s\n", kFqLimbs, W, cudaGetErrorString(e));
   int bad = 0;
-  for (int i = 0; i < W; i++) {
-    if (!eq(g.z[i], h.z[i])) { printf("z[%d] words differ (mod q equal: %d)\n", i, (int)eqmod(g.z[i], h.z[i])); bad++; }
-    if (!eq(g.acc_after[i], h.acc_after[i])) { printf("acc[%d] words differ (mod q equal: %d)\n", i, (int)eqmod(g.acc_after[i], h.acc_after[i])); bad++; }
-  }
-  if (!eq(g.inv0, h.inv0)) { printf("inv0 words differ (mod q equal: %d)\n", (int)eqmod(g.inv0, h.inv0)); bad++; }
-  for (int i = W - 1; i >= 0; i--) {
-    if (!eq(g.iz[i], h.iz[i])) { printf("iz[%d] words differ (mod q equal: %d)\n", i, (int)eqmod(g.iz[i], h.iz[i])); bad++; }
-    if (!eq(g.inv_after[i], h.inv_after[i])) { printf("inv_after[%d] words differ (mod q equal: %d)\n", i, (int)eqmod(g.inv_after[i], h.inv_after[i])); bad++; }
-    if (!eq(g.a[i].x, h.a[i].x) || !eq(g.a[i].y, h.a[i].y)) { printf("a[%d] differs\n", i); bad++; }
+  for (int byptr = 1; byptr >= 0; byptr--) {
+    cudaMemset(d_dump, 0, sizeof(Dump));
+    if (byptr) k_trace<true><<<1, 32>>>(d_tmp, W, d_dump); else k_trace<false><<<1, 32>>>(d_tmp, W, d_dump);
+    Dump g; cudaError_t e = cudaMemcpy(&g, d_dump, sizeof(Dump), cudaMemcpyDeviceToHost);
+    printf("curve limbs=%d W=%d, prefix-product trace with the multiplication helper taking %s (cuda=%s)\n", kFqLimbs, W,
+           byptr ? "POINTERS (round 1)" : "VALUES (now)", cudaGetErrorString(e));
+    int wrong = 0, first = -1;
+    for (int i = 0; i < W; i++) {
+      if (!eq(g.z[i], h.z[i])) { printf("  z[%d] words differ (mod q equal: %d)\n", i, (int)eqmod(g.z[i], h.z[i])); wrong++; }
+      if (!eq(g.acc_after[i], h.acc_after[i])) { if (first < 0) first = i; wrong++; }
+    }
+    if (first >= 0) printf("  acc[%d] = acc[%d] * z[%d] is the first value that differs from the host (mod q equal: %d)\n", first, first - 1, first,
+                           (int)eqmod(g.acc_after[first], h.acc_after[first]));
+    if (!eq(g.inv0, h.inv0)) wrong++;
+    for (int i = W - 1; i >= 0; i--) {
+      if (!eq(g.iz[i], h.iz[i])) wrong++;
+      if (!eq(g.inv_after[i], h.inv_after[i])) wrong++;
+      if (!eq(g.a[i].x, h.a[i].x) || !eq(g.a[i].y, h.a[i].y)) wrong++;
+    }
+    printf("  %d traced values differ from the host\n", wrong);
+    if (!byptr) bad += wrong;  // the by-value form must be right; the by-pointer form documents the defect
   }
   {  // one multiplication in isolation: the first pair the trace gets wrong
     fq *d_a, *d_b, *d_o; cudaMalloc(&d_a, sizeof(fq)); cudaMalloc(&d_b, sizeof(fq)); cudaMalloc(&d_o, sizeof(fq) * 64);
@@ -137,7 +158,7 @@ int main() {
       if (mode == 0) k_table_normalise<0><<<1, 64>>>(d_x, nb, 0, nb, W, d_t2, nullptr);
       if (mode == 1) k_table_normalise<1><<<1, 64>>>(d_x, nb, 0, nb, W, d_t2, d_pre);
       if (mode == 2) k_table_normalise<2><<<1, 64>>>(d_x, nb, 0, nb, W, d_t2, nullptr);
-      e = cudaMemcpy(t2.data(), d_t2, sizeof(affine) * nb * W, cudaMemcpyDeviceToHost);
+      cudaError_t e = cudaMemcpy(t2.data(), d_t2, sizeof(affine) * nb * W, cudaMemcpyDeviceToHost);
       int diff = 0, first = -1;
       for (size_t k = 0; k < t1.size(); k++) if (memcmp(&t1[k], &t2[k], sizeof(affine))) { if (first < 0) first = (int)k; diff++; }
       printf("k_table_normalise<%d> vs _each: %d of %zu entries differ (first %d = window %d base %d) cuda=%s\n", mode, diff, t1.size(), first,

@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE (root-cause harness): k_reduce_win of msm.cu against the closed form
 //   out = sum_s T_s + L * sum_s s * S_s
-// evaluated on the host with the same field / group code, plus a traced copy of the kernel that writes the
-// per-thread intermediates (run, above) so the first wrong value can be named.
+// evaluated on the host with the same field / group code: a frozen copy of round 1's kernel over by-reference and
+// over by-value helpers (with the per-thread intermediates run / above written out), and the combine kernels msm.cu
+// ships now (k_reduce_group, k_reduce_group_quad).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 [-DMP_CURVE_BLS12_377 -Dmp=mp_bls12_377] \
 //        --expt-relaxed-constexpr scripts/repro/repro_win.cu -o scripts/repro/repro_win_{377,stark}
 #include <stdio.h>
@@ -10,10 +11,42 @@
 #include "../../mental-poker_b200/csrc/msm.cu"
 using namespace mp;
 
+// ---- frozen copy of round 1's k_reduce_win (msm.cu no longer has it: both curves now share k_reduce_group[_quad]).
+// BYREF = the round-1 helpers, xyzz passed by reference to __noinline__ functions: miscompiled on the 12-limb build.
+// !BYREF = the same kernel over by-value helpers: correct on both builds.
+static constexpr int kWinThreads = 256;
+__device__ __noinline__ void add_ref(xyzz& acc, const xyzz& q) { xyzz_add(acc, q); }
+__device__ __noinline__ void dbl_ref(xyzz& acc) { acc = xyzz_dbl(acc); }
+template <bool BYREF> __device__ __forceinline__ void t_add(xyzz& acc, const xyzz& q) { if (BYREF) add_ref(acc, q); else acc = xyzz_add_v(acc, q); }
+template <bool BYREF> __device__ __forceinline__ void t_dbl(xyzz& acc) { if (BYREF) dbl_ref(acc); else acc = xyzz_dbl_v(acc); }
+__device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz& v, int delta) {
+  xyzz r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4 * kXyzzVec; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  return r;
+}
+template <bool BYREF>
+__device__ xyzz block_sum_xyzz(xyzz v, xyzz* smem) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    xyzz o = xyzz_shfl_down(v, d);
+    if (lane < d) t_add<BYREF>(v, o);
+  }
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int w = 1; w < kWinThreads / 32; w++) t_add<BYREF>(v, smem[w]);
+  __syncthreads();
+  return v;
+}
 struct Trace { xyzz run, inc, above, U; };
-
-__global__ void __launch_bounds__(kWinThreads) k_trace_win(const xyzz* __restrict__ segS, const xyzz* __restrict__ segT, uint32_t nseg,
-                                                           uint32_t L, int ncomp, xyzz* __restrict__ win_out, Trace* tr) {
+template <bool BYREF>
+__global__ void __launch_bounds__(kWinThreads) k_reduce_win_r1(const xyzz* __restrict__ segS, const xyzz* __restrict__ segT, uint32_t nseg,
+                                                              uint32_t L, int ncomp, xyzz* __restrict__ win_out, Trace* tr) {
   __shared__ xyzz smem[kWinThreads / 32];
   const uint32_t comp = blockIdx.x % ncomp;
   const uint64_t win = blockIdx.x / ncomp;
@@ -24,33 +57,31 @@ __global__ void __launch_bounds__(kWinThreads) k_trace_win(const xyzz* __restric
   xyzz run = xyzz_identity(), lsum = xyzz_identity(), tsum = xyzz_identity();
   for (int q = (int)ipt - 1; q >= 0; q--) {
     uint32_t i = threadIdx.x * ipt + q;
-    if (i + 1 < nseg) { xyzz a = xyzz_load(S + (uint64_t)(i + 1) * ncomp); xyzz_add_ni(run, a); }
-    xyzz_add_ni(lsum, run);
-    if (i < nseg) { xyzz tv = xyzz_load(T + (uint64_t)i * ncomp); xyzz_add_ni(tsum, tv); }
+    if (i + 1 < nseg) { xyzz a = xyzz_load(S + (uint64_t)(i + 1) * ncomp); t_add<BYREF>(run, a); }
+    t_add<BYREF>(lsum, run);
+    if (i < nseg) { xyzz tv = xyzz_load(T + (uint64_t)i * ncomp); t_add<BYREF>(tsum, tv); }
   }
-  tr[threadIdx.x].run = run;
+  if (tr) tr[threadIdx.x].run = run;
   xyzz inc = run;
 #pragma unroll 1
   for (int d = 1; d < 32; d <<= 1) {
     xyzz o = xyzz_shfl_down(inc, d);
-    if (lane + d < 32) xyzz_add_ni(inc, o);
+    if (lane + d < 32) t_add<BYREF>(inc, o);
   }
-  tr[threadIdx.x].inc = inc;
   if (lane == 0) smem[warp] = inc;
   xyzz above = xyzz_shfl_down(inc, 1);
   if (lane == 31) above = xyzz_identity();
   __syncthreads();
-  for (int w = warp + 1; w < kWinThreads / 32; w++) xyzz_add_ni(above, smem[w]);
+  for (int w = warp + 1; w < kWinThreads / 32; w++) t_add<BYREF>(above, smem[w]);
   __syncthreads();
-  tr[threadIdx.x].above = above;
-  for (uint32_t k = 1; k < ipt; k <<= 1) xyzz_dbl_ni(above);
-  xyzz_add_ni(lsum, above);
-  tr[threadIdx.x].U = lsum;
-  xyzz U = block_sum_xyzz<0>(lsum, smem, nullptr);
-  xyzz Tt = block_sum_xyzz<0>(tsum, smem, nullptr);
+  if (tr) tr[threadIdx.x].above = above;
+  for (uint32_t k = 1; k < ipt; k <<= 1) t_dbl<BYREF>(above);
+  t_add<BYREF>(lsum, above);
+  xyzz U = block_sum_xyzz<BYREF>(lsum, smem);
+  xyzz Tt = block_sum_xyzz<BYREF>(tsum, smem);
   if (threadIdx.x == 0) {
-    for (uint32_t k = 1; k < L; k <<= 1) xyzz_dbl_ni(U);
-    xyzz_add_ni(Tt, U);
+    for (uint32_t k = 1; k < L; k <<= 1) t_dbl<BYREF>(U);
+    t_add<BYREF>(Tt, U);
     xyzz_store(win_out + blockIdx.x, Tt);
   }
 }
@@ -101,12 +132,13 @@ int main() {
     xyzz got;
     for (int mode = 0; mode < 2; mode++) {
       cudaMemset(dOut, 0, sizeof(xyzz) * 4);
-      if (mode == 0) k_reduce_win<0><<<1, kWinThreads>>>(dS, dT, nseg, L, 1, dOut, nullptr);
-      else k_trace_win<<<1, kWinThreads>>>(dS, dT, nseg, L, 1, dOut, dTr);
+      if (mode == 0) k_reduce_win_r1<true><<<1, kWinThreads>>>(dS, dT, nseg, L, 1, dOut, dTr);
+      else k_reduce_win_r1<false><<<1, kWinThreads>>>(dS, dT, nseg, L, 1, dOut, nullptr);
       cudaError_t e = cudaMemcpy(&got, dOut, sizeof(xyzz), cudaMemcpyDeviceToHost);
       bool ok = same_point(got, want);
-      total_bad += !ok;
-      printf("limbs=%d nseg=%u %s: %s (cuda=%s)\n", kFqLimbs, nseg, mode ? "k_trace_win" : "k_reduce_win<0>", ok ? "ok" : "WRONG", cudaGetErrorString(e));
+      if (mode == 1) total_bad += !ok;   // the by-value form must be right; the by-reference form documents the defect
+      printf("limbs=%d nseg=%u round-1 k_reduce_win, helpers %s: %s (cuda=%s)\n", kFqLimbs, nseg,
+             mode ? "BY VALUE    " : "BY REFERENCE", ok ? "ok" : "WRONG", cudaGetErrorString(e));
     }
     std::vector<Trace> tr(kWinThreads);
     cudaMemcpy(tr.data(), dTr, sizeof(Trace) * kWinThreads, cudaMemcpyDeviceToHost);
@@ -128,6 +160,16 @@ int main() {
       }
       cudaMemcpy(&got, dOut, sizeof(xyzz), cudaMemcpyDeviceToHost);
       printf("   k_reduce_group levels: %s\n", same_point(got, want) ? "ok" : "WRONG");
+      total_bad += !same_point(got, want);
+      curS = dS; curT = dT; cur_nseg = nseg; cur_L = L;
+      for (int level = 0; cur_nseg > 1; level++) {
+        const uint32_t Gp = cur_nseg < 4 ? cur_nseg : 4; xyzz* buf = (level & 1) ? pong : ping; const bool last = cur_nseg == Gp;
+        k_reduce_group_quad<<<(cur_nseg / Gp * 4 + 127) / 128, 128>>>(curS, curT, 1, cur_nseg, Gp, cur_L, 1, buf, last ? dOut : buf + lvl);
+        curS = buf; curT = buf + lvl; cur_nseg /= Gp; cur_L *= Gp;
+      }
+      cudaMemcpy(&got, dOut, sizeof(xyzz), cudaMemcpyDeviceToHost);
+      printf("   k_reduce_group_quad levels: %s\n", same_point(got, want) ? "ok" : "WRONG");
+      total_bad += !same_point(got, want);
     }
   }
   printf(total_bad ? "FAIL %d\n" : "PASS\n", total_bad);

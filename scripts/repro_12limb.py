@@ -1,7 +1,7 @@
 """Repro of the two msm.cu kernels that misbehaved on the 12-limb (BLS12-377) build in round 1.
 
-    MP_WIN_BLOCK={1,2,3,4}   python scripts/repro_12limb.py win     # k_reduce_win<MODE 0..3>
-    MP_TABLE_TRICK={1,2,3}   python scripts/repro_12limb.py table   # k_table_normalise<MODE 0..2>
+    python scripts/repro_12limb.py win     # variable-base MSM at c = 10..16 (per-window combine levels)
+    MP_TABLE_TRICK={0,1,2,3} python scripts/repro_12limb.py table   # fixed-base tables: _each / k_table_normalise<0..2>
 
 Every case has a known answer (chain points with known discrete logs), so no oracle library is needed on the
 GPU box.  Prints one line per case and a final PASS/FAIL.  Driven by scripts/sanitize.sh."""
