@@ -63,6 +63,8 @@ typedef struct mp_ctx mp_ctx;
 #define MP_ERR_NOT_CANONICAL (-5)
 /* BLS12-377 only (the Stark curve has cofactor 1): a point is on the curve but outside the order-r subgroup G1 */
 #define MP_ERR_NOT_IN_SUBGROUP (-6)
+/* NCCL is not available (libnccl.so.2 could not be loaded) or a collective failed */
+#define MP_ERR_NCCL (-7)
 
 /* ---- context ------------------------------------------------------------------------ */
 /* Creates a context bound to CUDA device `device` (owns a stream and device scratch). */
@@ -112,6 +114,42 @@ int32_t mp_msm_g1_windows_device(mp_ctx* ctx, const void* d_bases, const void* d
  * and the window width it used. */
 uint64_t mp_last_msm_ec_adds(mp_ctx* ctx);
 int32_t mp_last_msm_window(mp_ctx* ctx);
+
+/* ---- multi-GPU --------------------------------------------------------------
+ * One context per GPU -- one process per GPU, or one thread per GPU inside one process -- joined by an NCCL
+ * communicator.  Rank 0 calls mp_comm_unique_id and hands the 128 bytes to the other ranks over the host's own
+ * channel (MPI, a socket, torch.distributed, a Rust mpsc); every rank then calls mp_comm_init on its context
+ * (collective).  NCCL is bound at run time: without libnccl.so.2 these calls return MP_ERR_NCCL and everything
+ * else keeps working.  A context without a communicator behaves as rank 0 of 1. */
+#define MP_COMM_ID_BYTES 128
+int32_t mp_comm_unique_id(uint8_t* id_out /* MP_COMM_ID_BYTES */);
+int32_t mp_comm_init(mp_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id /* MP_COMM_ID_BYTES */);
+int32_t mp_comm_destroy(mp_ctx* ctx);
+int32_t mp_comm_size(mp_ctx* ctx);
+int32_t mp_comm_rank(mp_ctx* ctx);
+/* ONE variable-base MSM split by window range (BASELINE config 5).  Collective: every rank passes the same
+ * device-resident inputs; rank r runs windows shard(W, r, nranks) end to end, the 128-byte XYZZ partials are
+ * all-gathered on the context's stream (no host synchronisation) and folded by one small kernel; every rank
+ * receives the canonical result in d_out (64 bytes, device).  Asynchronous on the context's stream. */
+int32_t mp_msm_g1_multi_device(mp_ctx* ctx, const void* d_bases, const void* d_scalars, uint64_t n,
+                               int32_t window_bits, void* d_out);
+/* Batch of independent proofs, proof-index split (BASELINE config 4): every rank verifies ITS `batch_per_rank`
+ * proofs (decks / shuffled_decks / proofs = this rank's shard) with mp_shuffle_verify_batch -- no data-path
+ * collective -- and the verdicts are all-gathered: statuses_all receives nranks * batch_per_rank entries, rank-major,
+ * on every rank. */
+int32_t mp_shuffle_verify_batch_multi(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* shuffled_decks,
+                                      const uint8_t* proofs, uint64_t batch_per_rank, int32_t* statuses_all,
+                                      int32_t host_threads);
+/* ONE large proof across the GPUs of the communicator (config 3).  Collective: every rank makes the same call on
+ * the same inputs and receives the same bytes / verdict as the single-GPU entry point would return.  The prover's
+ * diagonal ciphertext products (Karatsuba leaf products: independent MSMs, ~70 % of its device time at 2^16 cards)
+ * are split by leaf index and their results all-gathered; the verifier's two ciphertext equations run on two
+ * ranks.  Decks below the large-deck threshold (8 192 cards) run unsplit on every rank. */
+int32_t mp_shuffle_and_remask_multi(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                    const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck,
+                                    uint8_t* proof_out);
+int32_t mp_shuffle_verify_multi(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* shuffled_deck,
+                                const uint8_t* proof);
 
 /* ---- shuffle protocol (the reference's hot path) ------------------------------------------
  * Data layouts.  A deck is N = m*n ElGamal ciphertexts, 128 bytes each (c1 || c2).  Scalars

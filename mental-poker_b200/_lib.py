@@ -32,6 +32,15 @@ SIGNATURES = {
     "mp_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
     "mp_last_msm_ec_adds": (_u64, [_vp]),
     "mp_last_msm_window": (_i32, [_vp]),
+    "mp_comm_unique_id": (_i32, [_cp]),
+    "mp_comm_init": (_i32, [_vp, _i32, _i32, _cp]),
+    "mp_comm_destroy": (_i32, [_vp]),
+    "mp_comm_size": (_i32, [_vp]),
+    "mp_comm_rank": (_i32, [_vp]),
+    "mp_msm_g1_multi_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "mp_shuffle_verify_batch_multi": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp_shuffle_and_remask_multi": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp]),
+    "mp_shuffle_verify_multi": (_i32, [_vp, _cp, _cp, _cp, _cp]),
     "mp_ctx_set_params": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp]),
     "mp_params_m": (_i32, [_vp]),
     "mp_params_n": (_i32, [_vp]),
@@ -127,6 +136,42 @@ class Context:
     @property
     def launches(self):
         return lib.mp_last_kernel_launches(self.h)
+
+    # --- multi-GPU (NCCL communicator behind the C ABI)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.mp_comm_unique_id(buf)
+        if rc != 0:
+            raise MpError(rc, "mp_comm_unique_id failed (NCCL not available)")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid: bytes):
+        check(self.h, lib.mp_comm_init(self.h, nranks, rank, uid))
+
+    def comm_destroy(self):
+        check(self.h, lib.mp_comm_destroy(self.h))
+
+    def msm_g1_multi_device(self, d_bases, d_scalars, n, d_out, window_bits=0):
+        check(self.h, lib.mp_msm_g1_multi_device(self.h, d_bases, d_scalars, n, window_bits, d_out))
+
+    def shuffle_and_remask_multi(self, pk, deck, perm, rho, rand):
+        N = self.m * self.n
+        arr = (ctypes.c_uint32 * N)(*perm)
+        deck2 = ctypes.create_string_buffer(128 * N)
+        proof = ctypes.create_string_buffer(lib.mp_proof_len(self.m, self.n))
+        check(self.h, lib.mp_shuffle_and_remask_multi(self.h, pk, deck, arr, rho, rand, deck2, proof))
+        return deck2.raw, proof.raw
+
+    def verify_shuffle_multi(self, pk, deck, deck2, proof) -> int:
+        return check(self.h, lib.mp_shuffle_verify_multi(self.h, pk, deck, deck2, proof))
+
+    def verify_shuffle_batch_multi(self, pk, decks, decks2, proofs, nranks, host_threads=0):
+        plen = lib.mp_proof_len(self.m, self.n)
+        B = len(proofs) // plen
+        st = (_i32 * (B * nranks))()
+        check(self.h, lib.mp_shuffle_verify_batch_multi(self.h, pk, decks, decks2, proofs, B, st, host_threads))
+        return list(st)
 
     # --- MSM (host buffers)
     def msm_g1(self, bases: bytes, scalars: bytes, window_bits=0) -> bytes:

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/mpshuffle.h"
+#include "comm.cuh"
 #include "ctx.cuh"
 #include "msm.cuh"
 #include "shuffle.cuh"
@@ -61,6 +62,7 @@ extern "C" void mp_ctx_destroy(mp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
   msm_workspace_destroy(ctx->ws);
   if (ctx->shuffle) shuffle_state_destroy(ctx->shuffle);
   for (auto& b : ctx->bufs)

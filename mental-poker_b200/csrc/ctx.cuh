@@ -11,11 +11,15 @@ struct MsmWorkspace;
 struct ShuffleState;
 }
 
+struct mp_comm;  // NCCL communicator of a multi-GPU job (comm.cu); null = single GPU
+
 struct mp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   mp::MsmWorkspace* ws = nullptr;
   mp::ShuffleState* shuffle = nullptr;  // protocol parameters + staging (shuffle_internal.cuh)
+  mp_comm* comm = nullptr;
+  bool collective = false;  // set for the duration of a *_multi protocol call (comm.cuh)
   std::string err = "";
   int launches = 0;
   uint64_t last_ec_adds = 0;

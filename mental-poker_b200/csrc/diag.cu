@@ -11,6 +11,7 @@
 //
 // The point rows depend on no challenge: diag_karatsuba_points() is queued right after the deck
 // upload and runs while the host hashes the statement.
+#include "comm.cuh"
 #include "diag.cuh"
 
 #include "shuffle_internal.cuh"
@@ -238,22 +239,32 @@ int32_t diag_karatsuba_products(mp_ctx* ctx, const uint32_t* d_rows_canon, xyzz*
   const uint64_t nscal = (uint64_t)(nleaf + 1) * n;  // leaf rows, then a0
   const affine* pts = (const affine*)ctx->scratch(sKaraPts, (uint64_t)nleaf * 2 * n * sizeof(affine));
   uint32_t* scal = (uint32_t*)ctx->scratch(sKaraScal, nscal * 32);
-  xyzz* R = (xyzz*)ctx->scratch(sKaraOut, (uint64_t)P.njobs() * 2 * sizeof(xyzz));
+  // One large proof across GPUs (mp_shuffle_and_remask_multi): the leaf products are independent
+  // MSMs, so rank r of G evaluates jobs [r * per, (r + 1) * per) and the 256-byte results are all-gathered in place
+  // on this stream; everything else of the proof runs identically on every rank.
+  const int G = comm_collective(ctx) ? comm_size(ctx) : 1, rank = G > 1 ? comm_rank(ctx) : 0;
+  const uint64_t njobs = P.njobs(), per = (njobs + G - 1) / G;
+  xyzz* R = (xyzz*)ctx->scratch(sKaraOut, per * G * 2 * sizeof(xyzz));
   NEED(pts); NEED(scal); NEED(R);
   const uint64_t total = (uint64_t)nleaf * n;
   k_kara_scalars<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_rows_canon, D->d_mask, D->d_val, m, 1u << P.levels, n, total, scal);
   CK(cudaMemcpyAsync(scal + total * 8, d_rows_canon, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
   ctx->launches += 1;
-  std::vector<MsmJob> jobs((size_t)P.njobs());
+  std::vector<MsmJob> jobs((size_t)njobs);
   for (uint32_t l = 0; l < nleaf; l++) jobs[l] = MsmJob{l * n, l * n, n};
   for (uint32_t i = 1; i <= m; i++) jobs[nleaf + i - 1] = MsmJob{nleaf * n, P.single[m - i] * n, n};  // <C_i, a0>, C_i = P_{m-i}
   const int c = msm_pick_window((uint64_t)n, jobs.size());
   // a launch sequence stays below the 2^32-entry limit of the sort (entries = terms * windows)
   const uint64_t max_jobs = std::max<uint64_t>(1, ((1ull << 31) / (uint64_t)msm_num_windows(c)) / n);
-  for (uint64_t j0 = 0; j0 < jobs.size(); j0 += max_jobs) {
-    const uint64_t cnt = std::min<uint64_t>(max_jobs, jobs.size() - j0);
+  const uint64_t mine0 = std::min<uint64_t>(njobs, rank * per), mine1 = std::min<uint64_t>(njobs, (rank + 1) * per);
+  for (uint64_t j0 = mine0; j0 < mine1; j0 += max_jobs) {
+    const uint64_t cnt = std::min<uint64_t>(max_jobs, mine1 - j0);
     CK(msm_run(ws, scal, nscal, pts, 2, jobs.data() + j0, (int)cnt, c, R + 2 * j0, st));
     ctx->launches += msm_last_launches(ws);
+  }
+  if (G > 1) {
+    int32_t rc2 = comm_allgather(ctx, R, per * 2 * sizeof(xyzz), st);
+    if (rc2 != MP_OK) return rc2;
   }
   k_kara_combine<<<4 * m, kCombThreads, 0, st>>>(R, D->d_row_start, D->d_entries, d_E);
   CK(cudaGetLastError());

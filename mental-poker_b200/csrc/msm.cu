@@ -855,6 +855,35 @@ __global__ void __launch_bounds__(32) k_fold(const xyzz* __restrict__ win_out, i
   if (role == 0) xyzz_store(out + g, res);
 }
 
+// Fold of the per-rank partials of a window-range split (comm.cu):  out = sum_r 2^(c * w_begin_r) * P_r, evaluated as
+// a Horner chain from the highest rank down -- shifts.s[r] = doublings between rank r + 1's partial and rank r's.
+struct FoldShifts { int s[64]; };
+__global__ void __launch_bounds__(32) k_fold_ranges(const xyzz* __restrict__ parts, int nranks, int ncomp, FoldShifts shifts,
+                                                    xyzz* __restrict__ out) {
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const uint32_t mask = 0xfu << base;
+  const int comp = blockIdx.x * 8 + (lane >> 2);
+  if (comp >= ncomp) return;
+  fq home = quad_home(xyzz_load(parts + (size_t)(nranks - 1) * ncomp + comp), role);
+#pragma unroll 1
+  for (int r = nranks - 2; r >= 0; r--) {
+    if (!fq_is_zero_raw(fq_shfl(mask, home, base + 2))) {
+#pragma unroll 1
+      for (int k = 0; k < shifts.s[r]; k++) quad_dbl(home, role, base, mask);
+    }
+    quad_add(home, xyzz_load(parts + (size_t)r * ncomp + comp), role, base, mask);
+  }
+  const xyzz res = quad_gather(home, base, mask);
+  if (role == 0) xyzz_store(out + comp, res);
+}
+cudaError_t msm_fold_ranges(const xyzz* d_parts, int nranks, int ncomp, const int* shifts, xyzz* d_out, cudaStream_t stream) {
+  if (nranks < 1 || nranks > 64) return cudaErrorInvalidValue;
+  FoldShifts fs;
+  for (int r = 0; r < 64; r++) fs.s[r] = r < nranks ? shifts[r] : 0;
+  k_fold_ranges<<<(unsigned)((ncomp + 7) / 8), 32, 0, stream>>>(d_parts, nranks, ncomp, fs, d_out);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------

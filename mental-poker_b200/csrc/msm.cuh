@@ -47,6 +47,9 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
 //   sum_{w in range} 2^(c*(w - w_begin)) * (window sum w)
 // so that  full MSM = sum over ranges of 2^(c*w_begin) * partial  (window-range split across GPUs).
 inline int msm_num_windows(int c) { return (kScalarBits + c - 1) / c; }
+// out[comp] = sum_r 2^(shift below r) * parts[r * ncomp + comp]: Horner from the highest rank, shifts[r] doublings
+// between rank r + 1's partial and rank r's (window-range split across GPUs; nranks <= 64)
+cudaError_t msm_fold_ranges(const xyzz* d_parts, int nranks, int ncomp, const int* shifts, xyzz* d_out, cudaStream_t stream);
 
 // Fixed-base mode (Pedersen commitments over a constant key).  msm_build_table fills
 //   d_table[w * nb + first + i] = 2^(c*w) * d_bases[first + i],  w < msm_num_windows(c), i < count

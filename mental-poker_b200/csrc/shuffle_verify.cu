@@ -1,6 +1,7 @@
 // verify_shuffle on the GPU (reference DLCards::verify_shuffle, mod.rs:420-443): single proof with
 // device-side O(N) scalars, and the lockstep batch.  The checks themselves are built by the
 // host-only shuffle_host.hpp.  See shuffle.cuh for the design notes.
+#include "comm.cuh"
 #include "shuffle_internal.cuh"
 
 namespace mp {
@@ -28,7 +29,10 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, T * 128);
   affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, T * 2 * sizeof(affine));
   uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, T * 32);
-  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, 4 * sizeof(xyzz));
+  // one large proof across GPUs (mp_shuffle_verify_multi): the two ciphertext equations go to ranks 0 and 1, the
+  // 2 x 128-byte results are all-gathered; the G1 jobs and the transcript run on every rank
+  const int G = comm_collective(ctx) ? comm_size(ctx) : 1, rank = G > 1 ? comm_rank(ctx) : 0;
+  xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, (size_t)std::max(4, 2 * G) * sizeof(xyzz));
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
@@ -96,8 +100,18 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   //   job 0:  sum x^i C_i - E_m                                        == O   (Chat == E_m)
   //   job 1:  sum x^k E_k - Enc(b*ghat; tau) - sum (x^{m-i} a_j) C'_ij  == O
   MsmJob ct_jobs[2] = {{0, 0, (uint32_t)(N + 1)}, {(uint32_t)(N + 1), (uint32_t)(N + 1), (uint32_t)(N + 2 * m + 2)}};
-  CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N, 2), d_ct_out, ctx->stream));
-  ctx->launches += msm_last_launches(ctx->ws);
+  if (G == 1) {
+    CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs, 2, msm_pick_window(N, 2), d_ct_out, ctx->stream));
+    ctx->launches += msm_last_launches(ctx->ws);
+  } else {
+    CK(cudaMemsetAsync(d_ct_out, 0, (size_t)2 * G * sizeof(xyzz), ctx->stream));  // ranks >= 2 contribute identities
+    if (rank < 2) {
+      CK(msm_run(ctx->ws, d_ct_scal, T, d_ct_mont, 2, ct_jobs + rank, 1, msm_pick_window(N, 1), d_ct_out + 2 * rank, ctx->stream));
+      ctx->launches += msm_last_launches(ctx->ws);
+    }
+    int32_t rcg = comm_allgather(ctx, d_ct_out, 2 * sizeof(xyzz), ctx->stream);  // [rank 0: job 0 | rank 1: job 1 | ...]
+    if (rcg != MP_OK) return rcg;
+  }
 
   CK(cudaStreamWaitEvent(ctx->stream, S->ev_join, 0));  // join: G1 results are ready for the copies below
 
