@@ -311,6 +311,13 @@ def main():
     lib = pkg.lib
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    if world > 1:
+        # the library's own NCCL communicator (mp_comm_*): rank 0 makes the id, torch.distributed only carries its 128 bytes
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(pkg.Context.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
     # Q decks: same parameters and key, independent decks / permutations / randomness
     inst = make_instance(ctx, m, n, seed=1 + rank)
@@ -417,6 +424,41 @@ def main():
     ctx.profile_enable(False)
     lat_p, lat_v = lat_p / max(1, args.latency_steps), lat_v / max(1, args.latency_steps)
 
+    # one large proof across the GPUs of the job: every rank proves and verifies THE SAME deck
+    # (rank 0's), the prover's leaf products split by rank over the library's NCCL communicator
+    one_proof = None
+    if world > 1:
+        try:
+            ctx0 = pkg.Context(local_rank) if rank != 0 else None  # rank 0's instance on every rank
+            inst0 = make_instance(ctx0 if ctx0 is not None else ctx, m, n, seed=1)
+            if ctx0 is not None:
+                ctx0.close()
+            ctx.set_params(m, n, inst0["enc_g"], inst0["ck_g"], inst0["ck_h"], inst0["ghat"])  # one statement, every rank
+            perm0 = (ctypes.c_uint32 * N)(*inst0["perm"])
+            mp_t, mv_t = [], []
+            for it in range(4):
+                dist.barrier()
+                t0 = time.perf_counter()
+                pkg.check(ctx.h, lib.mp_shuffle_and_remask_multi(ctx.h, inst0["pk"], inst0["deck"], perm0, inst0["rho"], inst0["rand"],
+                                                                 deck2_buf, proof_buf))
+                t1 = time.perf_counter()
+                rc = pkg.check(ctx.h, lib.mp_shuffle_verify_multi(ctx.h, inst0["pk"], inst0["deck"], deck2_buf, proof_buf))
+                t2 = time.perf_counter()
+                if rc != 0:
+                    raise SystemExit("bench: multi-GPU verify rejected a valid proof")
+                if it >= 1:
+                    mp_t.append(t1 - t0)
+                    mv_t.append(t2 - t1)
+            t = torch.tensor([min(mp_t), min(mv_t)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            one_proof = dict(n_gpus=world, prove_ms=t[0].item() * 1e3, verify_ms=t[1].item() * 1e3,
+                             single_gpu_prove_ms=lat_p * 1e3, single_gpu_verify_ms=lat_v * 1e3,
+                             proof_sha=__import__("hashlib").sha256(proof_buf.raw).hexdigest()[:16],
+                             note="mp_shuffle_and_remask_multi + mp_shuffle_verify_multi, host buffers, wall clock, max over ranks; "
+                                  "the serial Blake2s statement hash (~23 ms each) is not split")
+        except Exception as e:
+            one_proof = dict(error=repr(e))
+
     # integer-pipe denominators measured in this run: bare IMAD.WIDE and bare XYZZ mixed additions
     def microbench(which, iters):
         best = 0.0
@@ -515,14 +557,16 @@ def main():
         # BASELINE configs 4 and 5 last, compact, so that they survive in the tail of the driver's record
         line["secondary"] = dict(
             msm=compact(msm_res, ["terms", "window_bits", "n_gpus", "ms", "ec_adds", "ec_adds_per_s", "accumulate_adds_per_s", "scaling", "error"]),
+            one_proof_multi_gpu=one_proof,
             batch52=compact(b52, ["batch", "m", "n", "n_gpus", "proofs_per_s", "proofs_per_s_all_gpus", "prove_per_s", "verify_per_s",
                                   "all_verified", "host_threads", "single_proof_latency", "error"]))
         print(json.dumps(line), file=json_out)
         json_out.flush()
     if world > 1:
         dist.barrier()
+    ctx.close()  # tears the library's communicator down as well
+    if world > 1:
         dist.destroy_process_group()
-    ctx.close()
 
 
 def compact(d, keys):
@@ -817,9 +861,10 @@ def bls12_377_bench(pkg, torch, dev, logn, cpu_baseline):
 
 
 def msm_microbench(ctx, torch, dev, stream, logn, pkg=None, world=1, rank=0):
-    """2^logn-term variable-base MSM (BASELINE config 5).  world > 1: window-range split -- every
-    rank computes its share of the windows on replicated inputs, the 64-byte partials are
-    all-gathered over NCCL and folded by one tiny MSM (strong scaling of ONE MSM)."""
+    """2^logn-term variable-base MSM (BASELINE config 5).  world > 1: window-range split through the library's own
+    multi-GPU entry point (mp_msm_g1_multi_device): every rank computes its share of the windows on replicated
+    inputs, the 128-byte XYZZ partials are all-gathered over NCCL on the context's stream -- no host
+    synchronisation in between -- and folded by one small kernel (strong scaling of ONE MSM)."""
     import numpy as np
     import torch.distributed as dist
     n = 1 << logn
@@ -830,17 +875,9 @@ def msm_microbench(ctx, torch, dev, stream, logn, pkg=None, world=1, rank=0):
     out = torch.zeros(64, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     c = 16 if logn >= 19 else (13 if logn >= 15 else 10)
-    W = pkg.lib.mp_msm_num_windows(c)
-    if world > 1:
-        fold = pkg.dist.fold_scalars(c, W, world)
-        fold_sc = torch.frombuffer(bytearray(b"".join(s for _, s in fold)), dtype=torch.uint8).to(dev)
-        owners = [r for r, _ in fold]
-        gathered = torch.zeros(world * 64, dtype=torch.uint8, device=dev)
-        wb, we = pkg.dist.window_range(W, rank, world)
     times = []
     ctx.profile_enable(True)
     ctx.profile_collect()
-    adds_mine = 0
     for it in range(6):
         flush.fill_(1)
         torch.cuda.synchronize()
@@ -851,14 +888,7 @@ def msm_microbench(ctx, torch, dev, stream, logn, pkg=None, world=1, rank=0):
         if world == 1:
             ctx.msm_g1_device(bases.data_ptr(), scal.data_ptr(), n, out.data_ptr(), c)
         else:
-            if we > wb:
-                ctx.msm_g1_windows_device(bases.data_ptr(), scal.data_ptr(), n, out.data_ptr(), c, wb, we - wb)
-            adds_mine = ctx.last_msm_ec_adds if we > wb else 0
-            ctx.sync()
-            dist.all_gather_into_tensor(gathered, out)           # 64 B per rank over NVLink
-            torch.cuda.current_stream().synchronize()
-            pts = torch.cat([gathered[64 * r:64 * r + 64] for r in owners]).contiguous()
-            ctx.msm_g1_device(pts.data_ptr(), fold_sc.data_ptr(), len(owners), out.data_ptr(), 4)
+            ctx.msm_g1_multi_device(bases.data_ptr(), scal.data_ptr(), n, out.data_ptr(), c)
         e1.record(stream)
         e1.synchronize()
         ms = e0.elapsed_time(e1)
@@ -867,20 +897,19 @@ def msm_microbench(ctx, torch, dev, stream, logn, pkg=None, world=1, rank=0):
     acc_ms, acc_adds, acc_n = ctx.profile_collect()
     ctx.profile_enable(False)
     best = min(times)
+    adds = ctx.last_msm_ec_adds
     if world > 1:
         t = torch.tensor([best], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         best = t.item()
-        a = torch.tensor([float(adds_mine)], dtype=torch.float64, device=dev)
+        a = torch.tensor([float(adds)], dtype=torch.float64, device=dev)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
         adds = int(a.item())
-        result = bytes(out.cpu().numpy().tobytes()).hex()
-    else:
-        adds = ctx.last_msm_ec_adds
-        result = bytes(out.cpu().numpy().tobytes()).hex()
+    result = bytes(out.cpu().numpy().tobytes()).hex()
     return dict(terms=n, window_bits=c, n_gpus=world, ms=best, ec_adds=adds, ec_adds_per_s=adds / (best / 1e3),
                 accumulate_ms_avg=acc_ms / max(acc_n, 1), accumulate_adds_per_s=acc_adds / (acc_ms / 1e3) if acc_ms else None,
-                result_x_prefix=result[:16], scaling="strong (window-range split, all-gather of partials)" if world > 1 else "single GPU",
+                result_x_prefix=result[:16],
+                scaling="strong (window-range split, NCCL all-gather of XYZZ partials on the stream + one fold kernel, mp_msm_g1_multi_device)" if world > 1 else "single GPU",
                 note="device-resident canonical inputs -> canonical affine result, includes Montgomery conversion + on-curve check")
 
 
