@@ -7,8 +7,9 @@
  * variable-base MSM, the 2-component ciphertext MSM and the fixed-base batched Pedersen commitment
  * that ShuffleArgument::{prove,verify} / MultiExponentiationArgument / PedersenCommitment::commit
  * reduce to (call sites mod.rs:397-415,427-442; commit key setup mod.rs:111), plus verify_shuffle built on
- * them with host-side scalars (mp377_shuffle_verify).  The prover and the device-resident / batched protocol
- * drivers (mp_shuffle_*) are Stark-curve only so far.
+ * them with host-side scalars (mp377_shuffle_verify), and shuffle_and_remask (mp377_shuffle_and_remask[_batch]: the
+ * Stark build's lockstep prover compiled against this field).  The device-scalar large-deck drivers, the sigma
+ * protocols' device half and point decompression are Stark-curve only.
  *
  * Conventions are those of mpshuffle.h with the sizes of this curve:
  *   - base-field element: 48 bytes little-endian canonical (ark-ff 0.3 `Fp384` `ToBytes`);
@@ -66,6 +67,24 @@ int32_t mp377_ct_msm_device(mp377_ctx* ctx, const void* d_deck, const void* d_sc
 int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_t n_points, int32_t ncomp,
                        const uint8_t* scalars, uint64_t n_scalars, const uint32_t* jobs, uint64_t njobs,
                        int32_t window_bits, uint8_t* out);
+
+/* BarnettSmartProtocol::{setup, shuffle_and_remask} over this curve (reference src/lib.rs:74-78,181-188; impl
+ * mod.rs:105-121,380-418; the instantiation and the call the reference's benchmark harness times,
+ * examples/parameter_selection.rs:25-29,78-96).  Same contract as mp_ctx_set_params / mp_remask_batch /
+ * mp_shuffle_and_remask / mp_shuffle_and_remask_batch of mpshuffle.h with 96-byte points and 192-byte ciphertexts:
+ * proof_out receives mp377_proof_len(m, n) bytes, randomness = mp377_prover_randomness_len(m, n) = 11m + 5n scalars
+ * drawn by the caller in the order of SURVEY.md Appendix B.6; proofs are byte-identical to the oracle's.  Decks up
+ * to 8 192 cards (the lockstep, host-scalar prover; the device-scalar large-deck prover is Stark-only). */
+int32_t mp377_ctx_set_params(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g /* 96 */, const uint8_t* ck_g /* n*96 */,
+                             const uint8_t* ck_h /* 96 */, const uint8_t* ghat /* 96 */);
+uint64_t mp377_prover_randomness_len(int32_t m, int32_t n);
+int32_t mp377_remask_batch(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm, const uint8_t* rho,
+                           uint64_t n_cards, uint8_t* out_deck);
+int32_t mp377_shuffle_and_remask(mp377_ctx* ctx, const uint8_t* pk /* 96 */, const uint8_t* deck /* m*n*192 */, const uint32_t* perm,
+                                 const uint8_t* rho /* m*n*32 */, const uint8_t* randomness, uint8_t* out_deck, uint8_t* proof_out);
+int32_t mp377_shuffle_and_remask_batch(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                                       const uint8_t* rhos, const uint8_t* randomness, uint64_t batch, uint8_t* out_decks,
+                                       uint8_t* proofs, int32_t host_threads);
 
 /* Subgroup membership of n canonical points (n * 96 bytes): MP_OK iff every point is a canonical point of the curve
  * and lies in the order-r subgroup G1; otherwise MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_IN_SUBGROUP.  statuses (optional,

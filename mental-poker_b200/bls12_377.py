@@ -32,6 +32,11 @@ SIGNATURES = {
     "mp377_proof_serialized_len": (_u64, [_i32, _i32]),
     "mp377_proof_serialize": (_i32, [_i32, _i32, _cp, _cp]),
     "mp377_proof_len": (_u64, [_i32, _i32]),
+    "mp377_ctx_set_params": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp]),
+    "mp377_prover_randomness_len": (_u64, [_i32, _i32]),
+    "mp377_remask_batch": (_i32, [_vp, _cp, _cp, _vp, _cp, _u64, _cp]),
+    "mp377_shuffle_and_remask": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp]),
+    "mp377_shuffle_and_remask_batch": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _u64, _cp, _cp, _i32]),
     "mp377_subgroup_check": (_i32, [_vp, _cp, _u64, ctypes.POINTER(_i32)]),
     "mp377_shuffle_verify": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp, _cp, _cp, _cp, _cp]),
     "mp377_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, ctypes.POINTER(ctypes.c_uint32), _u64, _i32, _cp]),
@@ -164,6 +169,39 @@ class Context:
         assert len(ck_g) == n * POINT_BYTES and len(deck) == len(shuffled_deck) == 2 * N * POINT_BYTES
         assert len(proof) == lib.mp377_proof_len(m, n)
         return _check(self.h, lib.mp377_shuffle_verify(self.h, m, n, enc_g, ck_g, ck_h, ghat, pk, deck, shuffled_deck, proof))
+
+    # --- BarnettSmartProtocol::{setup, shuffle_and_remask} over this curve
+    def set_params(self, m, n, enc_g, ck_g, ck_h, ghat):
+        assert len(ck_g) == n * POINT_BYTES
+        _check(self.h, lib.mp377_ctx_set_params(self.h, m, n, enc_g, ck_g, ck_h, ghat))
+        self.m, self.n = m, n
+
+    def remask(self, pk, deck, perm, rho) -> bytes:
+        n = len(perm)
+        arr = (ctypes.c_uint32 * n)(*perm)
+        out = ctypes.create_string_buffer(2 * POINT_BYTES * n)
+        _check(self.h, lib.mp377_remask_batch(self.h, pk, deck, arr, rho, n, out))
+        return out.raw
+
+    def shuffle_and_remask(self, pk, deck, perm, rho, rand):
+        """-> (shuffled deck bytes, proof bytes)"""
+        N = self.m * self.n
+        assert len(perm) == N and len(deck) == 2 * POINT_BYTES * N and len(rho) == 32 * N
+        assert len(rand) == 32 * lib.mp377_prover_randomness_len(self.m, self.n)
+        arr = (ctypes.c_uint32 * N)(*perm)
+        deck2 = ctypes.create_string_buffer(2 * POINT_BYTES * N)
+        proof = ctypes.create_string_buffer(lib.mp377_proof_len(self.m, self.n))
+        _check(self.h, lib.mp377_shuffle_and_remask(self.h, pk, deck, arr, rho, rand, deck2, proof))
+        return deck2.raw, proof.raw
+
+    def shuffle_and_remask_batch(self, pk, decks, perms, rhos, rands, host_threads=0):
+        N = self.m * self.n
+        B = len(perms) // N
+        arr = (ctypes.c_uint32 * (N * B))(*perms)
+        out = ctypes.create_string_buffer(2 * POINT_BYTES * N * B)
+        proofs = ctypes.create_string_buffer(lib.mp377_proof_len(self.m, self.n) * B)
+        _check(self.h, lib.mp377_shuffle_and_remask_batch(self.h, pk, decks, arr, rhos, rands, B, out, proofs, host_threads))
+        return out.raw, proofs.raw
 
     def subgroup_check(self, points: bytes):
         """-> (return code, per-point statuses: 0 in G1, 1 not a canonical curve point, 2 outside the subgroup)"""

@@ -20,56 +20,8 @@ using namespace mp;
 // ------------------------------------------------------------------------------------------
 // context plumbing
 // ------------------------------------------------------------------------------------------
-int32_t mp_ctx::fail(int32_t code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  err = buf;
-  return code;
-}
-int32_t mp_ctx::cuda_fail(cudaError_t e, const char* where) {
-  return fail(MP_ERR_CUDA, "CUDA error in %s: %s", where, cudaGetErrorString(e));
-}
-
-extern "C" int32_t mp_ctx_create(mp_ctx** out, int32_t device) {
-  if (!out) return MP_ERR_INVALID_ARG;
-  *out = nullptr;
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
-    fprintf(stderr, "mpshuffle: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
-            e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
-    return MP_ERR_CUDA;
-  }
-  e = cudaSetDevice(device);
-  if (e != cudaSuccess) return MP_ERR_CUDA;
-  mp_ctx* ctx = new mp_ctx();
-  ctx->device = device;
-  // Stream priorities were measured and rejected (round 1): with the main stream above the bulk stream
-  // (ShuffleState::bulk) the block scheduler holds back the bulk kernel's pending blocks whenever a
-  // main-stream kernel is waiting for resources, the SMs drain, and the bulk kernel's launch time grows
-  // by exactly what the small kernels took (12.8 vs 10.1 ms) -- same end-to-end time, muddier kernels.
-  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete ctx; return MP_ERR_CUDA; }
-  ctx->ws = msm_workspace_create();
-  *out = ctx;
-  return MP_OK;
-}
-
-extern "C" void mp_ctx_destroy(mp_ctx* ctx) {
-  if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  comm_destroy(ctx);
-  msm_workspace_destroy(ctx->ws);
-  if (ctx->shuffle) shuffle_state_destroy(ctx->shuffle);
-  for (auto& b : ctx->bufs)
-    if (b.ptr) cudaFree(b.ptr);
-  cudaStreamDestroy(ctx->stream);
-  delete ctx;
-}
+extern "C" int32_t mp_ctx_create(mp_ctx** out, int32_t device) { return ctx_create(out, device); }
+extern "C" void mp_ctx_destroy(mp_ctx* ctx) { ctx_destroy(ctx); }
 
 extern "C" void* mp_ctx_stream(mp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int32_t mp_ctx_sync(mp_ctx* ctx) {
@@ -95,20 +47,6 @@ extern "C" const char* mp_verify_status_string(int32_t status) {
 extern "C" int32_t mp_last_kernel_launches(mp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t mp_last_msm_ec_adds(mp_ctx* ctx) { return ctx ? ctx->last_ec_adds : 0; }
 extern "C" int32_t mp_last_msm_window(mp_ctx* ctx) { return ctx ? ctx->last_window : 0; }
-
-void* mp_ctx::scratch(int slot, size_t bytes) {
-  if ((size_t)slot >= bufs.size()) bufs.resize(slot + 1);
-  auto& b = bufs[slot];
-  if (b.cap < bytes) {
-    if (b.ptr) cudaFree(b.ptr);
-    b.ptr = nullptr;
-    b.cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    if (cudaMalloc(&b.ptr, want) != cudaSuccess) return nullptr;
-    b.cap = want;
-  }
-  return b.ptr;
-}
 
 // ------------------------------------------------------------------------------------------
 // MSM entry points

@@ -17,7 +17,9 @@
 #include <vector>
 
 #include "../../include/mpshuffle_bls12_377.h"
+#include "ctx.cuh"
 #include "msm.cuh"
+#include "shuffle.cuh"
 #include "shuffle_host.hpp"
 #include "wire_host.hpp"
 
@@ -34,6 +36,9 @@ struct mp377_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   MsmWorkspace* ws = nullptr;
+  // protocol-driver context of this curve (parameters, fixed-base tables, staging): the engine context type the
+  // Stark build calls mp_ctx, compiled a second time under its own name (Makefile: -Dmp_ctx=mp377_pctx)
+  mp_ctx* prover = nullptr;
   std::string err;
   int launches = 0;
   uint64_t last_ec_adds = 0;
@@ -100,6 +105,7 @@ extern "C" void mp377_ctx_destroy(mp377_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   msm_workspace_destroy(ctx->ws);
+  if (ctx->prover) ctx_destroy(ctx->prover);
   for (auto& b : ctx->bufs)
     if (b.ptr) cudaFree(b.ptr);
   cudaStreamDestroy(ctx->stream);
@@ -257,6 +263,44 @@ extern "C" int32_t mp377_msm_jobs(mp377_ctx* ctx, const uint8_t* points, uint64_
 // moves the O(N) scalar work to device kernels and keeps decks resident; that driver is not built for this
 // curve yet.)
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// shuffle_and_remask over this curve (BarnettSmartProtocol::shuffle_and_remask, reference src/lib.rs:181-188, impl
+// mod.rs:380-418, instantiated as in examples/parameter_selection.rs:25-29 -- the call the reference's only
+// benchmark harness times).  The protocol driver is the SAME source as the Stark build's lockstep prover
+// (shuffle_setup.cu: parameters, fixed-base tables, remasking; shuffle_prove_batch.cu: the rounds of the argument
+// with host-side scalar algebra and every group operation in batched MSM launches), compiled a second time against
+// the 12-limb field; proofs are byte-identical to oracle/py/bayer_groth.py under curve("bls12_377").
+// ------------------------------------------------------------------------------------------
+static int32_t prover_status(mp377_ctx* ctx, int32_t st) {
+  if (st < 0 && ctx->prover) ctx->err = ctx->prover->err;
+  if (ctx->prover) ctx->launches = ctx->prover->launches;
+  return st;
+}
+extern "C" int32_t mp377_ctx_set_params(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc_g, const uint8_t* ck_g,
+                                        const uint8_t* ck_h, const uint8_t* ghat) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  if (!ctx->prover && ctx_create(&ctx->prover, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create the prover context");
+  return prover_status(ctx, shuffle_set_params(ctx->prover, m, n, enc_g, ck_g, ck_h, ghat));
+}
+extern "C" uint64_t mp377_prover_randomness_len(int32_t m, int32_t n) { return shuffle_randomness_len(m, n); }
+extern "C" int32_t mp377_remask_batch(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm, const uint8_t* rho,
+                                      uint64_t n_cards, uint8_t* out_deck) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  if (!ctx->prover) return ctx->fail(MP_ERR_NO_PARAMS, "mp377_ctx_set_params has not been called");
+  return prover_status(ctx, shuffle_remask(ctx->prover, pk, deck, perm, rho, n_cards, out_deck));
+}
+extern "C" int32_t mp377_shuffle_and_remask_batch(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
+                                                  const uint8_t* rhos, const uint8_t* randomness, uint64_t batch, uint8_t* out_decks,
+                                                  uint8_t* proofs, int32_t host_threads) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  if (!ctx->prover) return ctx->fail(MP_ERR_NO_PARAMS, "mp377_ctx_set_params has not been called");
+  return prover_status(ctx, shuffle_prove_batch(ctx->prover, pk, decks, perms, rhos, randomness, batch, out_decks, proofs, host_threads));
+}
+extern "C" int32_t mp377_shuffle_and_remask(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
+                                            const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck, uint8_t* proof_out) {
+  return mp377_shuffle_and_remask_batch(ctx, pk, deck, perm, rho, randomness, 1, out_deck, proof_out, 1);
+}
+
 // ------------------------------------------------------------------------------------------
 // Subgroup membership.  E(F_q) has cofactor h = 0x170b5d44300000000000000000000000; the protocol lives in the
 // order-r subgroup G1, and every verifier scalar is reduced mod r, so points with a cofactor-torsion component must

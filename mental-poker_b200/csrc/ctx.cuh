@@ -35,3 +35,10 @@ struct mp_ctx {
   int32_t fail(int32_t code, const char* fmt, ...);
   int32_t cuda_fail(cudaError_t e, const char* where);
 };
+
+namespace mp {
+// in-library create / destroy (pctx.cu): what mp_ctx_create / mp_ctx_destroy wrap, and what the protocol drivers use
+// for their worker contexts (they must not go through the extern "C" names: those exist once, for the Stark curve)
+int32_t ctx_create(mp_ctx** out, int32_t device);
+void ctx_destroy(mp_ctx* ctx);
+}  // namespace mp

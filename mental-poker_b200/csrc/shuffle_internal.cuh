@@ -23,7 +23,7 @@ struct ShuffleState : ShuffleParamsHost {
   // fixed-base table of those n + 4 bases for the commitment jobs: tab_ck[w*(n+4) + i] = 2^(c*w) * base_i
   affine* d_tab_ck = nullptr;
   int tab_c = 0;
-  uint8_t ck_pk[64];          // public key currently in slot n + 3 of d_ck / d_tab_ck
+  uint8_t ck_pk[kPointBytes];  // public key currently in slot n + 3 of d_ck / d_tab_ck
   bool ck_pk_valid = false;
   cudaEvent_t ev = nullptr;   // marks small device->host copies the host waits for mid-stream
   // second stream + MSM workspace: independent launch sequences (the verifier's commitment-space
@@ -39,7 +39,7 @@ struct ShuffleState : ShuffleParamsHost {
   cudaEvent_t ev_bulk_go = nullptr, ev_bulk_done = nullptr;
   // fixed-base tables for remasking: tab[base][j][d-1] = d * 2^(8j) * base, base 0 = g, 1 = pk
   affine* d_tab = nullptr;
-  uint8_t tab_pk[64];
+  uint8_t tab_pk[kPointBytes];
   bool tab_pk_valid = false;
   // worker contexts of mp_shuffle_prove_batch (own stream / workspace each; same parameters)
   std::vector<mp_ctx*> workers;
@@ -62,8 +62,10 @@ struct ShuffleState : ShuffleParamsHost {
     if (bulk) cudaStreamDestroy(bulk);
     if (bulk_ws) msm_workspace_destroy(bulk_ws);
     if (d_tab) cudaFree(d_tab);
-    if (diag) diag_device_destroy(diag);
-    for (mp_ctx* w : workers) mp_ctx_destroy(w);
+#ifndef MP_CURVE_BLS12_377
+    if (diag) diag_device_destroy(diag);  // (the Karatsuba plan belongs to the large-deck prover: Stark build only)
+#endif
+    for (mp_ctx* w : workers) ctx_destroy(w);
   }
 };
 
@@ -134,14 +136,14 @@ int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn) {
   ShuffleState* S = ctx->shuffle;
   while ((int)S->workers.size() < P) {
     mp_ctx* w = nullptr;
-    if (mp_ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");
+    if (ctx_create(&w, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create worker context");
     S->workers.push_back(w);
     S->worker_gen.push_back(0);
   }
   for (int t = 0; t < P; t++) {
     if (S->worker_gen[t] == S->params_gen) continue;
-    int32_t st = shuffle_set_params(S->workers[t], S->m, S->n, S->enc_g, S->ck64.data() + 64, S->ck64.data(), S->ghat);
-    if (st != MP_OK) return ctx->fail(st, "worker set_params failed: %s", mp_last_error_string(S->workers[t]));
+    int32_t st = shuffle_set_params(S->workers[t], S->m, S->n, S->enc_g, S->ck64.data() + kPointBytes, S->ck64.data(), S->ghat);
+    if (st != MP_OK) return ctx->fail(st, "worker set_params failed: %s", S->workers[t]->err.c_str());
     S->worker_gen[t] = S->params_gen;
   }
   std::atomic<uint64_t> next{0};
@@ -156,7 +158,7 @@ int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn) {
       launches.fetch_add(w->launches);
       if (st < 0) {
         int32_t expected = MP_OK;
-        if (first_err.compare_exchange_strong(expected, st)) ctx->fail(st, "item %llu: %s", (unsigned long long)i, mp_last_error_string(w));
+        if (first_err.compare_exchange_strong(expected, st)) ctx->fail(st, "item %llu: %s", (unsigned long long)i, w->err.c_str());
         break;
       }
     }

@@ -76,24 +76,24 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
 
   // ---- device buffers
   const size_t rows_max = std::max<size_t>(SC, (size_t)m * tot);
-  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, (Bs * N + 2) * 128);   // holds the remasked decks already
+  uint8_t* d_ct_canon = (uint8_t*)ctx->scratch(sCtCanon, (Bs * N + 2) * kCtBytes);   // holds the remasked decks already
   affine* d_ct_mont = (affine*)ctx->scratch(sCtMont, (Bs * N + 2) * 2 * sizeof(affine));
   uint32_t* d_ct_scal = (uint32_t*)ctx->scratch(sCtScal, Bs * (N + n) * 32);
   xyzz* d_ct_out = (xyzz*)ctx->scratch(sCtOut, Bs * 4 * (size_t)m * sizeof(xyzz));
   uint32_t* d_g1_scal = (uint32_t*)ctx->scratch(sG1Scal, Bs * rows_max * 32 + 64);
   xyzz* d_g1_out = (xyzz*)ctx->scratch(sG1Out, Bs * JC * sizeof(xyzz));
-  uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, Bs * (JC + 4 * (size_t)m) * 64);
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, Bs * (JC + 4 * (size_t)m) * kPointBytes);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_ct_canon); NEED(d_ct_mont); NEED(d_ct_scal); NEED(d_ct_out); NEED(d_g1_scal); NEED(d_g1_out); NEED(d_canon); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
   // pk column of the fixed-base table
-  if (!S->ck_pk_valid || memcmp(S->ck_pk, pk, 64) != 0) {
+  if (!S->ck_pk_valid || memcmp(S->ck_pk, pk, kPointBytes) != 0) {
     uint8_t* d_pk = (uint8_t*)ctx->scratch(sSmallUp, 256);
     NEED(d_pk);
-    CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pk, pk, kPointBytes, cudaMemcpyHostToDevice, st));
     CK(points_to_mont((const uint32_t*)d_pk, S->d_ck + (n + 3), 1, d_bad, st));
     CK(msm_build_table(ctx->ws, S->d_ck, nb, (uint32_t)(n + 3), 1, S->tab_c, S->d_tab_ck, st));
-    memcpy(S->ck_pk, pk, 64);
+    memcpy(S->ck_pk, pk, kPointBytes);
     S->ck_pk_valid = true;
     launches += 3;
   }
@@ -112,8 +112,8 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     launches += msm_last_launches(ctx->ws);
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, npoints_out, st));
     launches += 1;
-    h_pts.resize(npoints_out * 64);
-    CK(cudaMemcpyAsync(h_pts.data(), d_canon, npoints_out * 64, cudaMemcpyDeviceToHost, st));
+    h_pts.resize(npoints_out * kPointBytes);
+    CK(cudaMemcpyAsync(h_pts.data(), d_canon, npoints_out * kPointBytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return MP_OK;
   };
@@ -159,8 +159,8 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   parallel_for(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
-    memcpy(proof + L.cA, &h_pts[p * (size_t)m * 64], (size_t)m * 64);
-    absorb_statement(h.fs, S, pk, decks + p * N * 128, out_decks + p * N * 128, N, proof + L.cA);
+    memcpy(proof + L.cA, &h_pts[p * (size_t)m * kPointBytes], (size_t)m * kPointBytes);
+    absorb_statement(h.fs, S, pk, decks + p * N * kCtBytes, out_decks + p * N * kCtBytes, N, proof + L.cA);
     h.x = h.fs.challenge();
     std::vector<fr> xp = h_powers(h.x, (int)N + 1);
     h.b.resize(N);
@@ -183,7 +183,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   parallel_for(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
-    memcpy(proof + L.cB, &h_pts[p * (size_t)m * 64], (size_t)m * 64);
+    memcpy(proof + L.cB, &h_pts[p * (size_t)m * kPointBytes], (size_t)m * kPointBytes);
     h.fs.begin(); h.fs.feed_label("shuffle_argument_b"); h.fs.feed_points64(proof + L.cB, m); h.fs.end();
     h.y = h.fs.challenge();
     h.z = h.fs.challenge();
@@ -265,9 +265,9 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
                                                                      2 * m, totalE);
     CK(cudaGetLastError());
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, Bs * JC, st));
-    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)(d_canon + Bs * JC * 64), totalE, st));
+    CK(xyzz_to_canonical(d_ct_out, (uint32_t*)(d_canon + Bs * JC * kPointBytes), totalE, st));
     launches += 3;
-    h_pts.resize((Bs * JC + totalE) * 64);
+    h_pts.resize((Bs * JC + totalE) * kPointBytes);
     CK(cudaMemcpyAsync(h_pts.data(), d_canon, h_pts.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
@@ -277,12 +277,12 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   parallel_for(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
-    const uint8_t* g1 = &h_pts[p * JC * 64];
-    memcpy(proof + L.hB, g1, (size_t)m * 64);
-    memcpy(proof + L.cb, g1 + 64 * (size_t)(m - 1), 64);
-    memcpy(proof + L.svpts, g1 + 64 * (size_t)m, 3 * 64);
-    memcpy(proof + L.mepts, g1 + 64 * (size_t)(m + 3), (size_t)(2 * m + 1) * 64);
-    memcpy(proof + L.meE, &h_pts[(Bs * JC + p * 4 * (size_t)m) * 64], 4 * (size_t)m * 64);
+    const uint8_t* g1 = &h_pts[p * JC * kPointBytes];
+    memcpy(proof + L.hB, g1, (size_t)m * kPointBytes);
+    memcpy(proof + L.cb, g1 + kPointBytes * (size_t)(m - 1), kPointBytes);
+    memcpy(proof + L.svpts, g1 + kPointBytes * (size_t)m, 3 * kPointBytes);
+    memcpy(proof + L.mepts, g1 + kPointBytes * (size_t)(m + 3), (size_t)(2 * m + 1) * kPointBytes);
+    memcpy(proof + L.meE, &h_pts[(Bs * JC + p * 4 * (size_t)m) * kPointBytes], 4 * (size_t)m * kPointBytes);
     h.fs.begin(); h.fs.feed_label("hadamard_argument"); h.fs.feed_points64(proof + L.cb, 1); h.fs.feed_points64(proof + L.hB, m); h.fs.end();
     h.xh = h.fs.challenge();
     h.yh = h.fs.challenge();
@@ -337,7 +337,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   parallel_for(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
-    memcpy(proof + L.zpts, &h_pts[p * (size_t)JD * 64], (size_t)JD * 64);
+    memcpy(proof + L.zpts, &h_pts[p * (size_t)JD * kPointBytes], (size_t)JD * kPointBytes);
     h.fs.begin(); h.fs.feed_label("zero_argument"); h.fs.feed_points64(proof + L.zpts, 2 * (size_t)m + 3); h.fs.end();
     const fr xz = h.fs.challenge();
     h.fs.begin(); h.fs.feed_label("single_value_product_argument"); h.fs.feed_points64(proof + L.svpts, 3); h.fs.end();
@@ -400,7 +400,11 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n), rlen = shuffle_randomness_len(m, n) * 32;
   int P = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+#ifdef MP_CURVE_BLS12_377
+  if (N <= small_deck_max()) {
+#else
   if (N <= small_deck_max() && !getenv("MP_BATCH_WORKERS")) {
+#endif
     // small decks: lockstep over sub-batches (job grid <= 65535 per launch; bounded staging memory)
     const int threads = std::max(1, std::min(P, 64));
     const size_t per_proof_jobs = (size_t)(m + 4 + 6 * m);
@@ -417,6 +421,11 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
     ctx->launches = total;
     return MP_OK;
   }
+#ifdef MP_CURVE_BLS12_377
+  // second curve: the lockstep prover above is the whole implementation (host-scalar form; the device-scalar
+  // large-deck prover with its Karatsuba plan is built for the Stark curve only)
+  return ctx->fail(MP_ERR_INVALID_ARG, "decks above %zu cards are not supported on this curve", small_deck_max());
+#else
   // large decks (or MP_BATCH_WORKERS set): concurrent worker contexts running the single-proof path.
   // For 2^16-card decks a few workers are enough to hide each proof's serial Blake2s statement
   // absorb (host) behind the other proofs' kernels (device).
@@ -434,6 +443,7 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
     }
     return st;
   });
+#endif
 }
 
 }  // namespace mp

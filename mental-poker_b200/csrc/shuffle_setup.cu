@@ -5,6 +5,8 @@
 
 namespace mp {
 
+static constexpr int kPointWords = 2 * kFqLimbs;  // u32 words of a canonical point (x || y)
+
 void shuffle_state_destroy(ShuffleState* s) { delete s; }
 MsmWorkspace* shuffle_bulk_workspace(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->bulk_ws : nullptr; }
 int32_t shuffle_m(const mp_ctx* ctx) { return ctx && ctx->shuffle ? ctx->shuffle->m : 0; }
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) k_remask(const uint32_t* __restrict__ dec
   int comp = (int)(g & 1);
   uint64_t src = perm[i];
   if (src >= N) { atomicOr(bad, 2); return; }           // bit 1: permutation entry out of range
-  affine card = affine_from_canonical(deck_canon + (src * 2 + comp) * 16);
+  affine card = affine_from_canonical(deck_canon + (src * 2 + comp) * kPointWords);
   if (!affine_on_curve(card)) atomicOr(bad, 1);
   uint32_t k[8];
   {
@@ -93,21 +95,21 @@ __global__ void __launch_bounds__(128) k_remask(const uint32_t* __restrict__ dec
       affine e;
       uint4* dst = reinterpret_cast<uint4*>(&e);
 #pragma unroll
-      for (int q = 0; q < 4; q++) dst[q] = __ldg(s + q);
+      for (int q = 0; q < (int)(sizeof(affine) / 16); q++) dst[q] = __ldg(s + q);
       xyzz_madd(acc, e);
     }
   }
   affine r = xyzz_to_affine(acc);
-  uint32_t w[16];
+  uint32_t w[kPointWords];
   if (affine_is_identity(r)) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) w[q] = 0;
+    for (int q = 0; q < kPointWords; q++) w[q] = 0;
   } else {
     affine_to_canonical(r, w);
   }
-  uint4* o = reinterpret_cast<uint4*>(out_canon + g * 16);
+  uint4* o = reinterpret_cast<uint4*>(out_canon + g * kPointWords);
 #pragma unroll
-  for (int q = 0; q < 4; q++) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  for (int q = 0; q < kPointWords / 4; q++) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
 // (re)builds the table of base `which` (0 = g, 1 = pk) from 64 canonical bytes already on the device
@@ -122,20 +124,20 @@ static cudaError_t build_table(ShuffleState* S, int which, const uint8_t* d_base
 
 int32_t shuffle_ensure_pk_table(mp_ctx* ctx, const uint8_t* pk) {
   ShuffleState* S = ctx->shuffle;
-  if (S->tab_pk_valid && memcmp(S->tab_pk, pk, 64) == 0) return MP_OK;
+  if (S->tab_pk_valid && memcmp(S->tab_pk, pk, kPointBytes) == 0) return MP_OK;
   uint8_t* d_pk = (uint8_t*)ctx->scratch(sSmallUp, 256);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_pk); NEED(d_bad);
   S->tab_pk_valid = false;  // the table is being overwritten: valid again only once the device has accepted pk
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_pk, pk, kPointBytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(build_table(S, 1, d_pk, d_bad, ctx->stream));
   ctx->launches += 1;
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not on the Stark curve");
-  memcpy(S->tab_pk, pk, 64);
+  memcpy(S->tab_pk, pk, kPointBytes);
   S->tab_pk_valid = true;
   return MP_OK;
 }
@@ -148,12 +150,12 @@ int32_t run_g1_jobs(mp_ctx* ctx, const TermList& tl, xyzz** d_out_ret, int* d_ba
   if (!ws) ws = ctx->ws;
   uint32_t T = tl.count();
   int J = (int)tl.jobs.size();
-  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)T * 64 + 64);
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)T * kPointBytes + 64);
   affine* d_mont = (affine*)ctx->scratch(sG1Mont, (size_t)T * sizeof(affine) + 64);
   uint32_t* d_scal = (uint32_t*)ctx->scratch(sG1Scal, (size_t)T * 32 + 64);
   xyzz* d_out = (xyzz*)ctx->scratch(sG1Out, (size_t)J * sizeof(xyzz) + 64);
   NEED(d_canon); NEED(d_mont); NEED(d_scal); NEED(d_out);
-  CK(cudaMemcpyAsync(d_canon, tl.pts.data(), (size_t)T * 64, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d_canon, tl.pts.data(), (size_t)T * kPointBytes, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d_scal, tl.scal.data(), (size_t)T * 32, cudaMemcpyHostToDevice, stream));
   CK(points_to_mont((const uint32_t*)d_canon, d_mont, T, d_bad, stream));
   ctx->launches += 1;
@@ -175,11 +177,11 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   ShuffleState* S = ctx->shuffle;
   S->m = 0;
   S->n = 0;
-  S->ck64.resize((size_t)(n + 1) * 64);
-  memcpy(S->ck64.data(), ck_h, 64);
-  memcpy(S->ck64.data() + 64, ck_g, (size_t)n * 64);
-  memcpy(S->enc_g, enc_g, 64);
-  memcpy(S->ghat, ghat, 64);
+  S->ck64.resize((size_t)(n + 1) * kPointBytes);
+  memcpy(S->ck64.data(), ck_h, kPointBytes);
+  memcpy(S->ck64.data() + kPointBytes, ck_g, (size_t)n * kPointBytes);
+  memcpy(S->enc_g, enc_g, kPointBytes);
+  memcpy(S->ghat, ghat, kPointBytes);
   if (S->d_ck) cudaFree(S->d_ck);
   S->d_ck = nullptr;
   CK(cudaMalloc(&S->d_ck, sizeof(affine) * (size_t)(n + 4)));
@@ -201,25 +203,25 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
   TermList tl;
-  for (int j = 1; j <= n; j++) tl.term(S->ck64.data() + 64 * (size_t)j, fr_one());
+  for (int j = 1; j <= n; j++) tl.term(S->ck64.data() + kPointBytes * (size_t)j, fr_one());
   tl.close_job();
   tl.term(ck_h, fr_one()); tl.term(enc_g, fr_one()); tl.term(ghat, fr_one());  // validation only
   tl.close_job();
   xyzz* d_out = nullptr;
   int32_t st = run_g1_jobs(ctx, tl, &d_out, d_bad);
   if (st != MP_OK) return st;
-  uint8_t* d_res = (uint8_t*)ctx->scratch(sCanonOut, 64 + 64);
+  uint8_t* d_res = (uint8_t*)ctx->scratch(sCanonOut, kPointBytes + 64);
   NEED(d_res);
   CK(xyzz_to_canonical(d_out, (uint32_t*)d_res, 1, ctx->stream));
   ctx->launches += 1;
   // Montgomery copy of the commit key for the prover's commitment jobs
-  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)(n + 3) * 64);
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sG1Canon, (size_t)(n + 3) * kPointBytes);
   NEED(d_canon);
-  CK(cudaMemcpyAsync(d_canon, S->ck64.data(), (size_t)(n + 1) * 64, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_canon + (size_t)(n + 1) * 64, enc_g, 64, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_canon + (size_t)(n + 2) * 64, ghat, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_canon, S->ck64.data(), (size_t)(n + 1) * kPointBytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_canon + (size_t)(n + 1) * kPointBytes, enc_g, kPointBytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_canon + (size_t)(n + 2) * kPointBytes, ghat, kPointBytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(points_to_mont((const uint32_t*)d_canon, S->d_ck, (uint64_t)n + 3, d_bad, ctx->stream));
-  CK(build_table(S, 0, d_canon + (size_t)(n + 1) * 64, d_bad, ctx->stream));  // remask table of g
+  CK(build_table(S, 0, d_canon + (size_t)(n + 1) * kPointBytes, d_bad, ctx->stream));  // remask table of g
   S->tab_pk_valid = false;
   // fixed-base table for the commitment jobs (the pk column is filled per call)
   S->tab_c = msm_pick_table_window((uint64_t)n + 1);
@@ -231,7 +233,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   S->ck_pk_valid = false;
   ctx->launches += 4;
   int bad = 0;
-  CK(cudaMemcpyAsync(S->gsum, d_res, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(S->gsum, d_res, kPointBytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a parameter point is not a canonical point of the Stark curve");
@@ -258,7 +260,7 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   // input deck staged in the sCtMont slot, output in sCtCanon: exactly where shuffle_prove wants
   // the shuffled deck, so shuffle_and_remask does not move it twice
   uint8_t* d_deck = (uint8_t*)ctx->scratch(sCtMont, (N + 2) * 2 * sizeof(affine));
-  uint8_t* d_out = (uint8_t*)ctx->scratch(sCtCanon, (N + 2) * 128);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(sCtCanon, (N + 2) * kCtBytes);
   uint32_t* d_perm = (uint32_t*)ctx->scratch(sPerm, N * 4);
   uint8_t* d_rho = (uint8_t*)ctx->scratch(sRho, N * 32 + 64);
   uint8_t* d_pk = (uint8_t*)ctx->scratch(sSmallUp, 256);
@@ -267,14 +269,14 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
   // the pk table is cached across calls; it is marked valid only AFTER the device has validated pk (flag clean
   // at the synchronisation below) -- any early return in between leaves the cache invalid
-  const bool rebuild_pk = !S->tab_pk_valid || memcmp(S->tab_pk, pk, 64) != 0;
+  const bool rebuild_pk = !S->tab_pk_valid || memcmp(S->tab_pk, pk, kPointBytes) != 0;
   if (rebuild_pk) {
     S->tab_pk_valid = false;
-    CK(cudaMemcpyAsync(d_pk, pk, 64, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_pk, pk, kPointBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(build_table(S, 1, d_pk, d_bad, ctx->stream));
     ctx->launches += 1;
   }
-  CK(cudaMemcpyAsync(d_deck, deck_src, N * 128, cudaMemcpyDefault, ctx->stream));
+  CK(cudaMemcpyAsync(d_deck, deck_src, N * kCtBytes, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(d_perm, perm, N * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_rho, rho, N * 32, cudaMemcpyHostToDevice, ctx->stream));
   k_remask<<<(unsigned)((2 * N + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t*)d_deck, d_perm, (const uint32_t*)d_rho,
@@ -282,14 +284,14 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(cudaGetLastError());
   ctx->launches += 1;
   int bad = 0;
-  CK(cudaMemcpyAsync(out_deck, d_out, N * 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_deck, d_out, N * kCtBytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (fs_head) absorb_statement_head(*fs_head, S, pk, deck, N);  // host hashing overlaps the copies and the kernel
   CK(cudaStreamSynchronize(ctx->stream));
   // distinct bits (atomicOr): an out-of-range permutation entry can no longer hide an off-curve key or card
   if (bad & 1) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
   if (rebuild_pk) {  // pk validated by k_build_table: the table may be reused by later calls
-    memcpy(S->tab_pk, pk, 64);
+    memcpy(S->tab_pk, pk, kPointBytes);
     S->tab_pk_valid = true;
   }
   if (bad & 2) return ctx->fail(MP_ERR_INVALID_ARG, "permutation entry out of range");
@@ -328,7 +330,7 @@ int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* 
   fr* d_rows = (fr*)ctx->scratch(sFrTmp1, (k * len + k) * 32 + 64);
   uint32_t* d_scal = (uint32_t*)ctx->scratch(sG1Scal, k * (S->n + 1) * 32);
   xyzz* d_res = (xyzz*)ctx->scratch(sG1Out, k * sizeof(xyzz));
-  uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, k * 64);
+  uint8_t* d_canon = (uint8_t*)ctx->scratch(sCanonOut, k * kPointBytes);
   NEED(d_in); NEED(d_rows); NEED(d_scal); NEED(d_res); NEED(d_canon);
   if (len) CK(cudaMemcpyAsync(d_in, values, k * len * 32, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_in + k * len * 8, blinds, k * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -338,7 +340,7 @@ int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* 
   if (st != MP_OK) return st;
   CK(xyzz_to_canonical(d_res, (uint32_t*)d_canon, k, ctx->stream));
   ctx->launches += 1;
-  CK(cudaMemcpyAsync(out, d_canon, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out, d_canon, k * kPointBytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MP_OK;
 }

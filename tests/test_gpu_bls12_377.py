@@ -436,3 +436,73 @@ def test_shuffle_verify_rejects_torsion_and_non_canonical_inputs(ctx377, pkg):
     with pytest.raises(pkg.MpError) as e:
         ctx377.verify_shuffle(*a2)
     assert e.value.code == -5
+
+
+def _raw(fx):
+    return {k: bytes.fromhex(fx[k]) for k in ("enc_g", "ck_g", "ck_h", "ghat", "pk", "deck", "deck2", "proof", "rho", "rand")}
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_shuffle_and_remask_is_byte_exact_vs_golden(ctx377, idx):
+    """`mp377_shuffle_and_remask`: BarnettSmartProtocol::shuffle_and_remask over BLS12-377 (the call the reference's
+    benchmark harness times, examples/parameter_selection.rs:78-96).  Shuffled deck and proof are byte-identical to the
+    oracle's (`bayer_groth.curve("bls12_377")`) on identical decks, permutations and randomness; the proof verifies."""
+    fx = SHUF["shuffle"][idx]
+    r = _raw(fx)
+    m, n = fx["m"], fx["n"]
+    ctx377.set_params(m, n, r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"])
+    assert ctx377.remask(r["pk"], r["deck"], fx["perm"], r["rho"]) == r["deck2"]
+    deck2, proof = ctx377.shuffle_and_remask(r["pk"], r["deck"], fx["perm"], r["rho"], r["rand"])
+    assert ctx377.launches > 0
+    assert deck2 == r["deck2"]
+    assert proof == r["proof"]
+    assert ctx377.verify_shuffle(m, n, r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"], r["pk"], r["deck"], deck2, proof) == 0
+
+
+def test_shuffle_and_remask_300_cards_reference_benchmark_shape(ctx377):
+    """The reference's own benchmark: a 300-card deck over BLS12-377 G1 (examples/parameter_selection.rs:31-43), at
+    (m, n) = (10, 30) -- its proof-size optimum -- and (30, 10).  Inputs regenerated from the seed; proof bytes against
+    the committed oracle proofs (tests/golden/make_bls12_377_shuffle_300_golden.py); round trip through the verifier;
+    a batch of two decks equals two single calls."""
+    import hashlib
+    from _util_bls12_377 import instance
+    from oracle.py import bayer_groth as bg
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_shuffle_300_vectors.json")))
+    for fx in gold["shuffle"]:
+        m, n = fx["m"], fx["n"]
+        with bg.curve("bls12_377"):
+            pp, pk, deck, perm, rho, rnd = instance(m, n, fx["seed"])
+        enc_g, ck_g, ck_h, ghat = pb(pp.enc_g), b"".join(map(pb, pp.ck_g)), pb(pp.ck_h), pb(pp.ghat)
+        deck_b = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+        rho_b, rnd_b = b"".join(map(b32, rho)), b"".join(map(b32, rnd))
+        ctx377.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+        deck2, proof = ctx377.shuffle_and_remask(pb(pk), deck_b, perm, rho_b, rnd_b)
+        assert hashlib.sha256(deck2).hexdigest() == fx["deck2_sha256"]
+        assert proof.hex() == fx["proof"]
+        assert ctx377.verify_shuffle(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, deck2, proof) == 0
+        wrong = deck2[192:] + deck2[:192]
+        assert ctx377.verify_shuffle(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, wrong, proof) == 1   # "Hadamard Product (5.1)"
+        if (m, n) == (10, 30):
+            perm2 = perm[1:] + perm[:1]
+            d2b, pfb = ctx377.shuffle_and_remask_batch(pb(pk), deck_b * 2, perm + perm2, rho_b * 2, rnd_b * 2, host_threads=2)
+            assert d2b[:len(deck2)] == deck2 and pfb[:len(proof)] == proof
+            d2c, pfc = ctx377.shuffle_and_remask(pb(pk), deck_b, perm2, rho_b, rnd_b)
+            assert d2b[len(deck2):] == d2c and pfb[len(proof):] == pfc
+            assert ctx377.verify_shuffle(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, d2c, pfc) == 0
+
+
+def test_prover_usage_errors(ctx377, pkg):
+    fresh = pkg.bls12_377.Context(0)
+    buf = bytes(96)
+    assert pkg.lib.mp377_shuffle_and_remask(fresh.h, buf, buf, None, buf, buf, None, None) == -4   # MP_ERR_NO_PARAMS
+    fx = SHUF["shuffle"][0]
+    r = _raw(fx)
+    bad = bytearray(r["ck_h"]); bad[5] ^= 1
+    with pytest.raises(pkg.MpError) as e:
+        fresh.set_params(fx["m"], fx["n"], r["enc_g"], r["ck_g"], bytes(bad), r["ghat"])
+    assert e.value.code == -3
+    fresh.set_params(fx["m"], fx["n"], r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"])
+    perm = list(fx["perm"]); perm[0] = 99
+    with pytest.raises(pkg.MpError):
+        fresh.shuffle_and_remask(r["pk"], r["deck"], perm, r["rho"], r["rand"])
+    fresh.close()
