@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(128, 4) k_stitch(const uint32_t* __restrict__ 
 // Thread per (window, segment, comp): running-sum sweep over the segment's L buckets from the top,
 //   S = sum of the segment's buckets,   T = sum_{i=0..L-1} (i+1) * B_i.
 // Empty buckets are recognised from the offsets (bucket_sums is never zero-filled).
-__global__ void __launch_bounds__(128, 3) k_reduce_seg(const uint32_t* __restrict__ offsets,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_reduce_seg(const uint32_t* __restrict__ offsets,
                                                     const xyzz* __restrict__ bucket_sums, uint64_t nwin,
                                                     uint32_t B, uint32_t L, int ncomp,
                                                     xyzz* __restrict__ segS, xyzz* __restrict__ segT) {
@@ -1032,7 +1033,13 @@ cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scal
     k_stitch<<<(unsigned)((max_chunks * ncomp + 127) / 128), 128, 0, stream>>>(offsets, nbuckets, chunk_bucket, ncomp, bucket_sums, part, kChunk);
     ws->launches++;
   }
-  k_reduce_seg<<<(unsigned)((nwin * nseg * ncomp + 127) / 128), 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
+  {
+    static const int seg_mb = [] { const char* e = getenv("MP_SEG_MINBLOCKS"); return e ? atoi(e) : 3; }();
+    const unsigned sb = (unsigned)((nwin * nseg * ncomp + 127) / 128);
+    if (seg_mb >= 4) k_reduce_seg<4><<<sb, 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
+    else if (seg_mb <= 2) k_reduce_seg<2><<<sb, 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
+    else k_reduce_seg<3><<<sb, 128, 0, stream>>>(offsets, bucket_sums, nwin, B, L, ncomp, segS, segT);
+  }
   // Per-window combine of the segment sums: fold groups of 4 segments, level after level, until one segment per
   // window is left -- its T' is the window sum (ONE kernel family for both curves; the block-wide shuffle-scan
   // kernel of round 1 is gone).  A level with few groups runs the quad-cooperative kernel.
