@@ -4,7 +4,7 @@ and MSM EC-adds/s, next to the CPU reference path on the same box).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
 
-One step = `--decks` (default 6) independent synthetic N-card decks, each put through one
+One step = `--decks` (default 8) independent synthetic N-card decks, each put through one
 `shuffle_and_remask` (permute + remask + ShuffleArgument::prove) and one `verify_shuffle` of its output, by
 the two batch entry points of the C ABI: a few worker contexts overlap one deck's serial Blake2s statement
 hash (host) with the other decks' kernels (device).  Default workload: 2^16 cards, (m, n) = (128, 512) -- the
@@ -258,7 +258,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--m", type=int, default=128)
     ap.add_argument("--n", type=int, default=512)
-    ap.add_argument("--decks", type=int, default=6, help="independent decks per step (pipelined over worker contexts)")
+    ap.add_argument("--decks", type=int, default=8, help="independent decks per step (pipelined over worker contexts)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=600.0,
                     help="--impl reference: run the full-size faithful prover only if it is predicted to fit this many seconds")
@@ -339,8 +339,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
+    phase = dict(prove=0.0, verify=0.0, n=0)
+
     def step(resident):
         # BarnettSmartProtocol::shuffle_and_remask (permute + remask + prove) for every deck ...
+        t_a = time.perf_counter()
         if resident:
             rc = lib.mp_shuffle_and_remask_batch_resident(ctx.h, inst["pk"], decks, perm_p, rhos, rands, Q, out_decks, proofs,
                                                           host_threads, d_decks.data_ptr())
@@ -348,6 +351,7 @@ def main():
             rc = lib.mp_shuffle_and_remask_batch(ctx.h, inst["pk"], decks, perm_p, rhos, rands, Q, out_decks, proofs, host_threads)
         pkg.check(ctx.h, rc)
         launches = ctx.launches
+        t_b = time.perf_counter()
         # ... then BarnettSmartProtocol::verify_shuffle on every output
         if resident:
             rc = lib.mp_shuffle_verify_batch_resident(ctx.h, inst["pk"], decks, out_decks, proofs, Q, statuses, host_threads,
@@ -357,6 +361,11 @@ def main():
         pkg.check(ctx.h, rc)
         if any(statuses):
             raise SystemExit(f"bench: verify_shuffle rejected a valid proof (statuses {list(statuses)})")
+        t_c = time.perf_counter()
+        if resident:
+            phase["prove"] += t_b - t_a
+            phase["verify"] += t_c - t_b
+            phase["n"] += 1
         return launches + ctx.launches
 
     def timed_steps(resident, steps):
@@ -380,6 +389,7 @@ def main():
     for _ in range(args.warmup):
         step(True)
         step(False)
+    phase.update(prove=0.0, verify=0.0, n=0)
     # ---- `value`: decks resident in HBM
     barrier()
     with ClockSampler(local_rank) as clocks:
@@ -540,6 +550,8 @@ def main():
                     e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=Q * (128 * N + plen),
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=clocks.summary(), roofline=roofline,
+                    phases=dict(prove_ms_per_step=1e3 * phase["prove"] / max(phase["n"], 1), verify_ms_per_step=1e3 * phase["verify"] / max(phase["n"], 1),
+                                note="host wall clock of the two batch calls inside the steps of `value`"),
                     latency=dict(prove_ms=lat_p * 1e3, verify_ms=lat_v * 1e3, proofs_per_s_sequential=1.0 / (lat_p + lat_v),
                                  note="one deck at a time through mp_shuffle_and_remask_resident + mp_shuffle_verify_resident (round 1's headline step)"))
         if not args.no_cpu_baseline and world == 1:
