@@ -224,7 +224,14 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   CK(build_table(S, 0, d_canon + (size_t)(n + 1) * kPointBytes, d_bad, ctx->stream));  // remask table of g
   S->tab_pk_valid = false;
   // fixed-base table for the commitment jobs (the pk column is filled per call)
-  S->tab_c = msm_pick_table_window((uint64_t)n + 1);
+  // One bucket set per job in table mode, so the window is a compromise over the prover's job mix: per proof
+  // 3m + 6 row commitments of n + 1 terms and 8m + 1 one- / two-term jobs (c_B_k, Enc(b_k ghat; tau_k), c_D_k), each
+  // of which pays the whole 2^(c-1)-bucket reduction.  Sizing for the rows alone (c = 11 at n = 512) made the
+  // small jobs 1.2 ms of bucket sweeps per 2^16-card proof; the job-weighted length gives c = 9.
+  {
+    const uint64_t rows = 3 * (uint64_t)m + 6, small = 8 * (uint64_t)m + 1;
+    S->tab_c = msm_pick_table_window((rows * ((uint64_t)n + 1) + small * 2) / (rows + small));
+  }
   if (S->d_tab_ck) cudaFree(S->d_tab_ck);
   S->d_tab_ck = nullptr;
   CK(cudaMalloc(&S->d_tab_ck, sizeof(affine) * (size_t)msm_num_windows(S->tab_c) * (size_t)(n + 4)));
