@@ -477,9 +477,9 @@ def main():
             best = max(best, ops / (t_ms / 1e3))
         return best
     try:
-        imad_wide_peak, madd_peak = microbench(0, 2000), microbench(3, 300)
+        imad_wide_peak, madd_peak, imad_cc_peak = microbench(0, 2000), microbench(3, 300), microbench(5, 1000)
     except Exception:
-        imad_wide_peak = madd_peak = None
+        imad_wide_peak = madd_peak = imad_cc_peak = None
 
     # MSM microbench (BASELINE config 5), collective when world > 1: run it on every rank
     try:
@@ -538,6 +538,10 @@ def main():
                                       achieved_imad_wide_per_s=(adds_per_s * imad_per_add if adds_per_s else None),
                                       peak_measured=imad_wide_peak, peak_source="mp_dbg_bench(0): bare IMAD.WIDE loop, this run",
                                       frac=(adds_per_s * imad_per_add / imad_wide_peak if adds_per_s and imad_wide_peak else None),
+                                      peak_carry_chained=imad_cc_peak,
+                                      frac_of_carry_chained=(adds_per_s * imad_per_add / imad_cc_peak if adds_per_s and imad_cc_peak else None),
+                                      peak_carry_chained_source="mp_dbg_bench(5): IMAD.WIDE in mad.lo.cc / madc.hi.cc chains (the only form a "
+                                                                "multi-limb product can use), this run",
                                       madd_microbench_per_s=madd_peak,
                                       madd_microbench_frac=(adds_per_s / madd_peak if adds_per_s and madd_peak else None)),
                         note="integer-pipe bound kernel (10 field multiplications per 68 B): the HBM fraction is structurally low, "
