@@ -259,6 +259,9 @@ def main():
     ap.add_argument("--m", type=int, default=128)
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--decks", type=int, default=8, help="independent decks per step (pipelined over worker contexts)")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
+                    help="verify each step's own proofs after proving them (two phases) instead of verifying the previous step's "
+                         "proofs while this step's decks are proved")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=600.0,
                     help="--impl reference: run the full-size faithful prover only if it is predicted to fit this many seconds")
@@ -280,8 +283,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"{N}-card deck shuffle prove+verify, (m,n)=({m},{n}), Stark curve"
     config = dict(workload=workload, m=m, n=n, cards=N, decks_per_step=Q, l2="flushed between steps (256 MiB write)",
-                  step=f"{Q} independent decks per GPU: mp_shuffle_and_remask_batch then mp_shuffle_verify_batch (each deck proved and "
-                       "verified once; worker contexts overlap one deck's serial Blake2s statement hash with the other decks' kernels)",
+                  step=(f"{Q} independent decks per GPU per step: mp_shuffle_and_remask_batch of this step's decks on one context WHILE "
+                        f"mp_shuffle_verify_batch checks the previous step's {Q} proofs on a second context (every deck proved once and verified "
+                        "once; worker contexts overlap the serial Blake2s statement hashes with other decks' kernels)") if args.overlap else
+                       (f"{Q} independent decks per GPU per step: mp_shuffle_and_remask_batch, then mp_shuffle_verify_batch of the same decks"),
                   sharding="proof-index split: independent decks per GPU, no data-path collective" if world > 1 else "single GPU")
 
     if args.impl == "reference":
@@ -340,33 +345,60 @@ def main():
     torch.cuda.synchronize()
 
     phase = dict(prove=0.0, verify=0.0, n=0)
+    # Two contexts on this GPU, as a service that proves and verifies streams of decks would hold them: `ctx` proves,
+    # `ctx_v` verifies.  A step proves this step's Q decks and verifies the Q proofs of the PREVIOUS step at the same
+    # time (every deck is proved once and verified once; the first timed step verifies the last warm-up step's proofs).
+    # The verifier's serial statement hashes then overlap the prover's kernels instead of leaving the device idle.
+    ctx_v = pkg.Context(local_rank)
+    ctx_v.set_params(m, n, inst["enc_g"], inst["ck_g"], inst["ck_h"], inst["ghat"])
+    bufs = [(out_decks, proofs), (ctypes.create_string_buffer(128 * N * Q), ctypes.create_string_buffer(plen * Q))]
+    bufs[1][0].raw, bufs[1][1].raw = out_decks.raw, proofs.raw   # "previous step" of the very first step: the set-up pass
+    state = dict(k=0)
+    prove_threads = verify_threads = max(1, host_threads // 2) if args.overlap else host_threads
+
+    def prove_call(resident, out_d, out_p):
+        if resident:
+            return lib.mp_shuffle_and_remask_batch_resident(ctx.h, inst["pk"], decks, perm_p, rhos, rands, Q, out_d, out_p,
+                                                            prove_threads, d_decks.data_ptr())
+        return lib.mp_shuffle_and_remask_batch(ctx.h, inst["pk"], decks, perm_p, rhos, rands, Q, out_d, out_p, prove_threads)
+
+    def verify_call(resident, in_d, in_p):
+        if resident:
+            return lib.mp_shuffle_verify_batch_resident(ctx_v.h, inst["pk"], decks, in_d, in_p, Q, statuses, verify_threads,
+                                                        d_decks.data_ptr(), d_decks2.data_ptr())
+        return lib.mp_shuffle_verify_batch(ctx_v.h, inst["pk"], decks, in_d, in_p, Q, statuses, verify_threads)
 
     def step(resident):
-        # BarnettSmartProtocol::shuffle_and_remask (permute + remask + prove) for every deck ...
+        k = state["k"]
+        state["k"] = k + 1
+        cur, prev = bufs[k % 2], bufs[(k + 1) % 2]
         t_a = time.perf_counter()
-        if resident:
-            rc = lib.mp_shuffle_and_remask_batch_resident(ctx.h, inst["pk"], decks, perm_p, rhos, rands, Q, out_decks, proofs,
-                                                          host_threads, d_decks.data_ptr())
+        if args.overlap:
+            res = {}
+
+            def vrun():
+                res["rc"] = verify_call(resident, *prev)       # BarnettSmartProtocol::verify_shuffle, previous step's proofs
+                res["t"] = time.perf_counter()
+            th = threading.Thread(target=vrun)
+            th.start()
+            rc = prove_call(resident, *cur)                    # BarnettSmartProtocol::shuffle_and_remask, this step's decks
+            t_b = time.perf_counter()
+            th.join()
+            pkg.check(ctx.h, rc)
+            pkg.check(ctx_v.h, res["rc"])
+            t_p, t_v = t_b - t_a, res["t"] - t_a
         else:
-            rc = lib.mp_shuffle_and_remask_batch(ctx.h, inst["pk"], decks, perm_p, rhos, rands, Q, out_decks, proofs, host_threads)
-        pkg.check(ctx.h, rc)
-        launches = ctx.launches
-        t_b = time.perf_counter()
-        # ... then BarnettSmartProtocol::verify_shuffle on every output
-        if resident:
-            rc = lib.mp_shuffle_verify_batch_resident(ctx.h, inst["pk"], decks, out_decks, proofs, Q, statuses, host_threads,
-                                                      d_decks.data_ptr(), d_decks2.data_ptr())
-        else:
-            rc = lib.mp_shuffle_verify_batch(ctx.h, inst["pk"], decks, out_decks, proofs, Q, statuses, host_threads)
-        pkg.check(ctx.h, rc)
+            pkg.check(ctx.h, prove_call(resident, *cur))
+            t_b = time.perf_counter()
+            pkg.check(ctx_v.h, verify_call(resident, *cur))
+            t_p, t_v = t_b - t_a, time.perf_counter() - t_b
         if any(statuses):
             raise SystemExit(f"bench: verify_shuffle rejected a valid proof (statuses {list(statuses)})")
-        t_c = time.perf_counter()
         if resident:
-            phase["prove"] += t_b - t_a
-            phase["verify"] += t_c - t_b
+            phase["prove"] += t_p
+            phase["verify"] += t_v
             phase["n"] += 1
-        return launches + ctx.launches
+        return ctx.launches + ctx_v.launches
 
     def timed_steps(resident, steps):
         total_ms, launches = 0.0, 0
@@ -555,7 +587,9 @@ def main():
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=clocks.summary(), roofline=roofline,
                     phases=dict(prove_ms_per_step=1e3 * phase["prove"] / max(phase["n"], 1), verify_ms_per_step=1e3 * phase["verify"] / max(phase["n"], 1),
-                                note="host wall clock of the two batch calls inside the steps of `value`"),
+                                overlapped=bool(args.overlap), prove_worker_threads=prove_threads, verify_worker_threads=verify_threads,
+                                note="host wall clock of the two batch calls inside the steps of `value`" +
+                                     (" (they run concurrently: a step lasts as long as the longer one)" if args.overlap else "")),
                     latency=dict(prove_ms=lat_p * 1e3, verify_ms=lat_v * 1e3, proofs_per_s_sequential=1.0 / (lat_p + lat_v),
                                  note="one deck at a time through mp_shuffle_and_remask_resident + mp_shuffle_verify_resident (round 1's headline step)"))
         if not args.no_cpu_baseline and world == 1:
@@ -580,6 +614,7 @@ def main():
         json_out.flush()
     if world > 1:
         dist.barrier()
+    ctx_v.close()
     ctx.close()  # tears the library's communicator down as well
     if world > 1:
         dist.destroy_process_group()

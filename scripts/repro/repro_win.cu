@@ -127,6 +127,7 @@ int main() {
     xyzz *dS, *dT, *dOut; Trace* dTr;
     cudaMalloc(&dS, sizeof(xyzz) * nseg); cudaMalloc(&dT, sizeof(xyzz) * nseg); cudaMalloc(&dOut, sizeof(xyzz) * 4);
     cudaMalloc(&dTr, sizeof(Trace) * kWinThreads);
+    cudaMemset(dTr, 0, sizeof(Trace) * kWinThreads);  // only .run and .above are written by the kernel
     cudaMemcpy(dS, S.data(), sizeof(xyzz) * nseg, cudaMemcpyHostToDevice);
     cudaMemcpy(dT, T.data(), sizeof(xyzz) * nseg, cudaMemcpyHostToDevice);
     xyzz got;
