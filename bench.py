@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="verify each step's own proofs after proving them (two phases) instead of verifying the previous step's "
                          "proofs while this step's decks are proved")
+    ap.add_argument("--workers", type=int, default=8, help="worker contexts per batch call of the headline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=600.0,
                     help="--impl reference: run the full-size faithful prover only if it is predicted to fit this many seconds")
@@ -354,7 +355,9 @@ def main():
     bufs = [(out_decks, proofs), (ctypes.create_string_buffer(128 * N * Q), ctypes.create_string_buffer(plen * Q))]
     bufs[1][0].raw, bufs[1][1].raw = out_decks.raw, proofs.raw   # "previous step" of the very first step: the set-up pass
     state = dict(k=0)
-    prove_threads = verify_threads = max(1, host_threads // 2) if args.overlap else host_threads
+    # worker CONTEXTS of the two large-deck batch calls, not compute threads: each spends most of its time blocked on the
+    # device (CPU demand ~ 2 x 23.5 ms of Blake2s + ~5 ms per proof), so their number is not divided by the rank count
+    prove_threads = verify_threads = args.workers
 
     def prove_call(resident, out_d, out_p):
         if resident:
