@@ -505,4 +505,12 @@ def test_prover_usage_errors(ctx377, pkg):
     perm = list(fx["perm"]); perm[0] = 99
     with pytest.raises(pkg.MpError):
         fresh.shuffle_and_remask(r["pk"], r["deck"], perm, r["rho"], r["rand"])
+    # decks above the lockstep prover's limit (8 192 cards) are refused on this curve, not mis-proved
+    m, n = 64, 256
+    pts = fresh.dbg_scalar_mul(pb(bls.G) * (n + 3), b"".join(b32(rnd.randrange(1, R)) for _ in range(n + 3)))
+    fresh.set_params(m, n, pb(bls.G), pts[:96 * n], pts[96 * n:96 * (n + 1)], pts[96 * (n + 1):96 * (n + 2)])
+    N = m * n
+    with pytest.raises(pkg.MpError) as e:
+        fresh.shuffle_and_remask(pts[96 * (n + 2):], pts[:96] * (2 * N), list(range(N)), bytes(32 * N), bytes(32 * (11 * m + 5 * n)))
+    assert e.value.code == -1 and b"not supported" in pkg.lib.mp377_last_error_string(fresh.h)
     fresh.close()

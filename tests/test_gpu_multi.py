@@ -131,3 +131,40 @@ def test_batch_verdicts_are_all_gathered(pkg, ctx, nranks):
         return c.verify_shuffle_batch_multi(pk, *shards[r], nranks, host_threads=2)
     for res in run_ranks(pkg, nranks, body):
         assert res == want
+
+
+def test_multi_entry_points_degenerate_to_one_rank(pkg, ctx):
+    """Without a communicator a context is rank 0 of 1: the collective entry points give the single-GPU results
+    (this is what runs on a 1-GPU box; the real collectives are the tests above)."""
+    import torch
+    assert pkg.lib.mp_comm_size(ctx.h) == 1 and pkg.lib.mp_comm_rank(ctx.h) == 0
+    n = 3000
+    rng = np.random.default_rng(8)
+    pts = ctx.dbg_scalar_mul(G64 * n, rand_scalars(rng, n))
+    ks = rand_scalars(rng, n)
+    want = ctx.msm_g1(pts, ks, 0)
+    dev = torch.device("cuda:0")
+    d_pts = torch.frombuffer(bytearray(pts), dtype=torch.uint8).to(dev)
+    d_ks = torch.frombuffer(bytearray(ks), dtype=torch.uint8).to(dev)
+    d_out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    for wbits in (0, 9, 16):
+        ctx.msm_g1_multi_device(d_pts.data_ptr(), d_ks.data_ptr(), n, d_out.data_ptr(), wbits)
+        ctx.sync()
+        assert bytes(d_out.cpu().numpy().tobytes()) == want
+    # protocol entry points: golden 52-card instance
+    import json, os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.json")))["shuffle"][2]
+    h = bytes.fromhex
+    ctx.set_params(fx["m"], fx["n"], h(fx["enc_g"]), h(fx["ck_g"]), h(fx["ck_h"]), h(fx["ghat"]))
+    deck2, proof = ctx.shuffle_and_remask_multi(h(fx["pk"]), h(fx["deck"]), fx["perm"], h(fx["rho"]), h(fx["rand"]))
+    assert deck2.hex() == fx["deck2"] and proof.hex() == fx["proof"]
+    assert ctx.verify_shuffle_multi(h(fx["pk"]), h(fx["deck"]), deck2, proof) == 0
+    assert ctx.verify_shuffle_batch_multi(h(fx["pk"]), h(fx["deck"]) * 2, deck2 * 2, proof * 2, 1) == [0, 0]
+
+
+def test_comm_init_needs_a_valid_shape(pkg):
+    c = pkg.Context(0)
+    with pytest.raises(pkg.MpError):
+        c.comm_init(2, 5, bytes(128))       # rank outside [0, nranks)
+    c.comm_destroy()                        # no communicator: a no-op
+    c.close()
