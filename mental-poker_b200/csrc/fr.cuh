@@ -25,6 +25,7 @@ struct fr {
 #ifdef MP_CURVE_BLS12_377
 // r = 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001 (253 bits), ark_bls12_377::Fr
 #define MP_FR_NINV 0xffffffffu
+#define MP_FR_NINV64 0x0a117fffffffffffull
 static constexpr int kFrShaveBits = 3;  // ark-ff REPR_SHAVE_BITS = 256 - 253
 MP_HD uint32_t fr_modulus_limb(int i) {
   switch (i) {
@@ -40,6 +41,7 @@ MP_HD uint32_t fr_modulus_limb(int i) {
 }
 #else
 #define MP_FR_NINV 0xe8bde631u
+#define MP_FR_NINV64 0xbb6b3c4ce8bde631ull
 static constexpr int kFrShaveBits = 4;  // ark-ff REPR_SHAVE_BITS = 256 - 252
 
 MP_HD uint32_t fr_modulus_limb(int i) {
@@ -154,8 +156,53 @@ MP_HD fr fr_sub(const fr& a, const fr& b) {
 }
 MP_HD fr fr_neg(const fr& a) { return fr_sub(fr_zero(), a); }
 
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__)
+// HOST form of the product below: the same CIOS over 4 x 64-bit limbs (unsigned __int128 products, mulx/adx on x86).
+// The transcripts' scalar algebra, the lockstep provers and the verifier plans run on host threads; with the 32-bit
+// form a 52-card proof cost 0.17 ms of host arithmetic, which is what bounded the batched provers once several GPUs
+// shared one host.  Same result: both compute a*b/2^256 mod n, fully reduced.
+// -n^-1 mod 2^64 as a per-curve literal (MP_FR_NINV64 beside MP_FR_NINV): a function-local static here would be one
+// symbol shared by every library in the process that includes this header, and the two curves' values differ.
+static_assert((uint32_t)MP_FR_NINV64 == MP_FR_NINV, "64-bit and 32-bit Montgomery constants disagree");
+inline uint64_t fr_ninv64() { return MP_FR_NINV64; }
+#endif
+
 // CIOS Montgomery product, output fully reduced
 MP_HD fr fr_mul(const fr& a, const fr& b) {
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__)
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], M[4], t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    A[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+    B[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+    M[i] = (uint64_t)fr_modulus_limb(2 * i) | ((uint64_t)fr_modulus_limb(2 * i + 1) << 32);
+  }
+  const uint64_t ninv = fr_ninv64();
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)t[j] + (u128)A[j] * B[i];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    const uint64_t q = t[0] * ninv;
+    c = ((u128)t[0] + (u128)q * M[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)t[j] + (u128)q * M[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  fr r64;
+  for (int i = 0; i < 4; i++) { r64.v[2 * i] = (uint32_t)t[i]; r64.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+  return fr_cond_sub(r64, (uint32_t)t[4]);
+#else
   uint32_t t[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) t[i] = 0;
@@ -187,6 +234,7 @@ MP_HD fr fr_mul(const fr& a, const fr& b) {
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = t[i];
   return fr_cond_sub(r, t[8]);
+#endif
 }
 MP_HD fr fr_sqr(const fr& a) { return fr_mul(a, a); }
 

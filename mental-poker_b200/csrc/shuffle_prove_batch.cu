@@ -1,5 +1,7 @@
 // shuffle_and_remask for batches (BASELINE config: batch of independent 52-card proofs): the
 // lockstep small-deck prover and the worker-context dispatcher for large decks.
+#include <chrono>
+
 #include "shuffle_internal.cuh"
 
 namespace mp {
@@ -73,6 +75,15 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     if (rc != MP_OK) return rc;
   }
   int launches = ctx->launches;
+  // MP_TRACE_BATCH=1: wall time of the host phases (transcripts + scalar algebra on `threads` threads) and of the
+  // device phases (upload, MSM launches, download, synchronise) of this sub-batch, to stderr
+  static const bool trace_on = [] { const char* e = getenv("MP_TRACE_BATCH"); return e && atoi(e) != 0; }();
+  double t_host = 0, t_dev = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  auto t_mark = now();
+  auto host_done = [&] { t_host += since(t_mark); t_mark = now(); };
+  auto dev_done = [&] { t_dev += since(t_mark); t_mark = now(); };
 
   // ---- device buffers
   const size_t rows_max = std::max<size_t>(SC, (size_t)m * tot);
@@ -107,6 +118,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   std::vector<MsmJob> jobs;
 
   auto run_commit_jobs = [&](size_t n_scalars, size_t njobs_total, size_t npoints_out) -> int32_t {
+    host_done();
     CK(cudaMemcpyAsync(d_g1_scal, h_scal.data(), n_scalars * 32, cudaMemcpyHostToDevice, st));
     CK(msm_run(ctx->ws, d_g1_scal, n_scalars, S->d_tab_ck, 1, jobs.data(), (int)njobs_total, S->tab_c, d_g1_out, st, 0, -1, nb));
     launches += msm_last_launches(ctx->ws);
@@ -115,6 +127,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     h_pts.resize(npoints_out * kPointBytes);
     CK(cudaMemcpyAsync(h_pts.data(), d_canon, npoints_out * kPointBytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    dev_done();
     return MP_OK;
   };
   int32_t rc;
@@ -244,6 +257,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
         diag[p * 2 * m + k] = MsmJob{(uint32_t)(p * (N + n) + (size_t)(k - m + i0) * n), (uint32_t)(p * N + (size_t)(i0 - 1) * n),
                                      (uint32_t)((size_t)(i1 - i0 + 1) * n)};
       }
+    host_done();
     CK(cudaMemcpyAsync(d_ct_scal, h_ct_scal.data(), h_ct_scal.size() * 4, cudaMemcpyHostToDevice, st));
     CK(msm_run(ctx->ws, d_ct_scal, Bs * (N + n), d_ct_mont, 2, diag.data(), (int)diag.size(), msm_pick_window(N / 2 + 1, diag.size()), d_ct_out, st));
     launches += msm_last_launches(ctx->ws);
@@ -270,6 +284,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     h_pts.resize((Bs * JC + totalE) * kPointBytes);
     CK(cudaMemcpyAsync(h_pts.data(), d_canon, h_pts.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    dev_done();
   }
 
   // ---- round D: Hadamard challenges; zero-argument rows, diagonals and commitments
@@ -381,8 +396,11 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     h_fr_out(h_dot(xmp.data(), h.me_tau.data(), 2 * m), proof + L.metau);
   });
   int bad = 0;
+  host_done();
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  dev_done();
+  if (trace_on) fprintf(stderr, "prove_sub_batch: %zu proofs, %d threads: host phases %.2f ms, device phases %.2f ms\n", Bs, threads, t_host, t_dev);
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not a canonical point of the Stark curve");
   ctx->launches = launches;
   return MP_OK;
