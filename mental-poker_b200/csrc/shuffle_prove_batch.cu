@@ -134,7 +134,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
 
   // ---- round A: c_A[k] = com(chunk_k(a); r_k)
   h_scal.assign(Bs * (size_t)m * tot * 8, 0);
-  parallel_for(Bs, threads, [&](size_t p) {
+  S->pool.run(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     RandCursor rcur{rands + p * rlen};
     h.r = rcur.vec(m);
@@ -169,7 +169,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   if ((rc = run_commit_jobs(Bs * (size_t)m * tot, Bs * (size_t)m, Bs * (size_t)m)) != MP_OK) return rc;
 
   // ---- round B: x; b_i = x^{perm[i]+1}; c_B[k] = com(chunk_k(b); s_k)
-  parallel_for(Bs, threads, [&](size_t p) {
+  S->pool.run(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
     memcpy(proof + L.cA, &h_pts[p * (size_t)m * kPointBytes], (size_t)m * kPointBytes);
@@ -180,7 +180,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     for (size_t i = 0; i < N; i++) h.b[i] = xp[perms[p * N + i] + 1];
   });
   // (h_scal is shared: fill it after the transcripts so round A's data is no longer needed)
-  parallel_for(Bs, threads, [&](size_t p) {
+  S->pool.run(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     for (int k = 0; k < m; k++) {
       uint32_t* dst = &h_scal[((p * m + k) * (size_t)tot) * 8];
@@ -193,7 +193,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   // ---- round C: y, z; product-argument rows, SVP and multi-exp first messages, diagonal ciphertexts
   h_scal.assign(Bs * (size_t)SC * 8, 0);
   std::vector<uint32_t> h_ct_scal(Bs * (N + n) * 8);
-  parallel_for(Bs, threads, [&](size_t p) {
+  S->pool.run(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
     memcpy(proof + L.cB, &h_pts[p * (size_t)m * kPointBytes], (size_t)m * kPointBytes);
@@ -289,7 +289,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
 
   // ---- round D: Hadamard challenges; zero-argument rows, diagonals and commitments
   h_scal.assign(Bs * (size_t)SD * 8, 0);
-  parallel_for(Bs, threads, [&](size_t p) {
+  S->pool.run(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
     const uint8_t* g1 = &h_pts[p * JC * kPointBytes];
@@ -349,7 +349,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   if ((rc = run_commit_jobs(Bs * (size_t)SD, jobs.size(), Bs * (size_t)JD)) != MP_OK) return rc;
 
   // ---- remaining challenges and all responses (host)
-  parallel_for(Bs, threads, [&](size_t p) {
+  S->pool.run(Bs, threads, [&](size_t p) {
     ProverHost& h = H[p];
     uint8_t* proof = proofs + p * plen;
     memcpy(proof + L.zpts, &h_pts[p * (size_t)JD * kPointBytes], (size_t)JD * kPointBytes);
@@ -428,16 +428,10 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
     const size_t per_proof_jobs = (size_t)(m + 4 + 6 * m);
     size_t sub = std::min<size_t>({(size_t)4096, (size_t)60000 / per_proof_jobs, std::max<size_t>(1, ((size_t)1 << 22) / N)});
     sub = std::max<size_t>(sub, 1);
-    int total = 0;
-    for (uint64_t p0 = 0; p0 < B; p0 += sub) {
-      size_t Bs = (size_t)std::min<uint64_t>(sub, B - p0);
-      int32_t st = prove_sub_batch(ctx, pk, decks + p0 * N * 128, perms + p0 * N, rhos + p0 * N * 32, rands + p0 * rlen, Bs,
-                                   out_decks + p0 * N * 128, proofs + p0 * plen, threads);
-      if (st != MP_OK) return st;
-      total += ctx->launches;
-    }
-    ctx->launches = total;
-    return MP_OK;
+    return run_chunks(ctx, B, sub, [&](mp_ctx* w, uint64_t p0, size_t Bs) {
+      return prove_sub_batch(w, pk, decks + p0 * N * kCtBytes, perms + p0 * N, rhos + p0 * N * 32, rands + p0 * rlen, Bs,
+                             out_decks + p0 * N * kCtBytes, proofs + p0 * plen, threads);
+    });
   }
 #ifdef MP_CURVE_BLS12_377
   // second curve: the lockstep prover above is the whole implementation (host-scalar form; the device-scalar

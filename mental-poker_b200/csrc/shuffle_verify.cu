@@ -189,17 +189,7 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
     build_ct_plan(S, pk, proof, L, ch, &ct_scal[(p * N) * 8], &ct_scal[(Bs * N + p * N) * 8], &ct_scal[(2 * Bs * N + p * SM) * 8],
                   &sm_pts[p * SM * 128], &bstars[p]);
   };
-  if (threads <= 1 || Bs < 4) {
-    for (size_t p = 0; p < Bs; p++) work(p);
-  } else {
-    std::vector<std::thread> pool;
-    std::atomic<size_t> next{0};
-    for (int t = 0; t < threads; t++)
-      pool.emplace_back([&] {
-        for (size_t p = next.fetch_add(1); p < Bs; p = next.fetch_add(1)) work(p);
-      });
-    for (auto& th : pool) th.join();
-  }
+  S->pool.run(Bs, Bs < 4 ? 1 : threads, work);
   for (size_t p = 0; p < Bs; p++)
     if (bad_layout[p]) return ctx->fail(MP_ERR_INVALID_ARG, "internal: unexpected verifier term count");
 
@@ -306,15 +296,9 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
   threads = std::max(1, std::min(threads, 64));
   // sub-batches bounded by the job grid (<= 65535 jobs per launch) and ~2^25 ciphertext terms
   size_t sub = std::min<size_t>(4096, std::max<size_t>(1, ((size_t)1 << 24) / N));
-  for (uint64_t p0 = 0; p0 < B; p0 += sub) {
-    size_t Bs = (size_t)std::min<uint64_t>(sub, B - p0);
-    int launches = ctx->launches;
-    int32_t st = verify_sub_batch(ctx, pk, decks + p0 * N * 128, decks2 + p0 * N * 128, proofs + p0 * plen, Bs,
-                                  statuses + p0, threads);
-    (void)launches;
-    if (st != MP_OK) return st;
-  }
-  return MP_OK;
+  return run_chunks(ctx, B, sub, [&](mp_ctx* w, uint64_t p0, size_t Bs) {
+    return verify_sub_batch(w, pk, decks + p0 * N * 128, decks2 + p0 * N * 128, proofs + p0 * plen, Bs, statuses + p0, threads);
+  });
 }
 
 // ------------------------------------------------------------------------------------------

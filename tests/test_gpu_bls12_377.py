@@ -491,6 +491,29 @@ def test_shuffle_and_remask_300_cards_reference_benchmark_shape(ctx377):
             assert ctx377.verify_shuffle(m, n, enc_g, ck_g, ck_h, ghat, pb(pk), deck_b, d2c, pfc) == 0
 
 
+def test_batch_split_over_two_worker_contexts_equals_single_calls(ctx377):
+    """A batch large enough to be cut into chunks that two worker contexts prove concurrently (host phases of one
+    chunk beside the device phases of the other, csrc/shuffle_internal.cuh run_chunks): every proof equals the
+    single-call proof for the same inputs, which the golden test above pins to the oracle."""
+    fx = SHUF["shuffle"][0]
+    r = _raw(fx)
+    m, n, B = fx["m"], fx["n"], 260
+    N = m * n
+    ctx377.set_params(m, n, r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"])
+    perms = []
+    for i in range(B):
+        k = i % N
+        perms += fx["perm"][k:] + fx["perm"][:k]
+    rhos = b"".join(r["rho"][32 * (i % N):] + r["rho"][:32 * (i % N)] for i in range(B))
+    d2b, pfb = ctx377.shuffle_and_remask_batch(r["pk"], r["deck"] * B, perms, rhos, r["rand"] * B, host_threads=4)
+    dl, pl = len(r["deck"]), len(r["proof"])
+    assert d2b[:dl] == r["deck2"] and pfb[:pl] == r["proof"]
+    for i in (1, 129, 130, 259):
+        d, p = ctx377.shuffle_and_remask(r["pk"], r["deck"], perms[N * i:N * (i + 1)], rhos[32 * N * i:32 * N * (i + 1)], r["rand"])
+        assert d == d2b[dl * i:dl * (i + 1)] and p == pfb[pl * i:pl * (i + 1)], i
+        assert ctx377.verify_shuffle(m, n, r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"], r["pk"], r["deck"], d, p) == 0
+
+
 def test_prover_usage_errors(ctx377, pkg):
     fresh = pkg.bls12_377.Context(0)
     buf = bytes(96)

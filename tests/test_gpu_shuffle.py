@@ -237,6 +237,47 @@ def test_verify_batch_matches_single_and_oracle(ctx, m, n, B):
     assert single == want
 
 
+def test_batches_split_over_two_worker_contexts(ctx):
+    """Batches of >= 256 small decks are cut into chunks that two worker contexts work through concurrently (one chunk
+    in its host phases while the other is on the device; csrc/shuffle_internal.cuh run_chunks).  Proofs equal the
+    single-call proofs, one of them the C oracle's; the batched verifier (chunked the same way) returns the oracle's
+    verdicts with a tampered proof in each chunk."""
+    m, n, B = 2, 3, 260
+    N = m * n
+    co = c_oracle.COracle(msm_mode=1)
+    pp0, pk0, deck, perm, rho, rnd = instance(m, n, 77)
+    enc_g, ck_g, ck_h, ghat, pk = pb(pp0.enc_g), b"".join(map(pb, pp0.ck_g)), pb(pp0.ck_h), pb(pp0.ghat), pb(pk0)
+    deck_b = b"".join(pb(c[0]) + pb(c[1]) for c in deck)
+    rho_b, rnd_b = b"".join(map(b32, rho)), b"".join(map(b32, rnd))
+    perms, rhos, rands = [], b"", b""
+    for i in range(B):
+        k = i % N
+        perms += perm[k:] + perm[:k]
+        rhos += rho_b[32 * k:] + rho_b[:32 * k]
+        j = 32 * (i % (len(rnd_b) // 32))
+        rands += rnd_b[j:] + rnd_b[:j]
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    out_decks, proofs = ctx.shuffle_and_remask_batch(pk, deck_b * B, perms, rhos, rands, host_threads=4)
+    dl, pl, rl = len(deck_b), len(proofs) // B, len(rnd_b)
+    for i in (0, 129, 130, 259):
+        d, p = ctx.shuffle_and_remask(pk, deck_b, perms[N * i:N * (i + 1)], rhos[32 * N * i:32 * N * (i + 1)], rands[rl * i:rl * (i + 1)])
+        assert d == out_decks[dl * i:dl * (i + 1)] and p == proofs[pl * i:pl * (i + 1)], i
+    i = 130
+    want = co.prove(m, n, enc_g, ck_g, ck_h, ghat, pk, deck_b, out_decks[dl * i:dl * (i + 1)], perms[N * i:N * (i + 1)],
+                    rhos[32 * N * i:32 * N * (i + 1)], rands[rl * i:rl * (i + 1)])
+    assert want == proofs[pl * i:pl * (i + 1)]
+    assert ctx.verify_shuffle_batch(pk, deck_b * B, out_decks, proofs, host_threads=4) == [0] * B
+    bad = bytearray(proofs)
+    tampered = (3, 129, 130, 259)
+    for i in tampered:
+        bad[pl * (i + 1) - 1 - 32 * 3] ^= 1        # multi-exp response r
+    got = ctx.verify_shuffle_batch(pk, deck_b * B, out_decks, bytes(bad), host_threads=4)
+    for i in range(B):
+        assert got[i] == (0 if i not in tampered else
+                          co.verify(m, n, enc_g, ck_g, ck_h, ghat, pk, deck_b, out_decks[dl * i:dl * (i + 1)], bytes(bad[pl * i:pl * (i + 1)]))), i
+    assert all(got[i] != 0 for i in tampered)
+
+
 @pytest.mark.parametrize("m,n,B,workers", [(3, 4, 9, False), (3, 4, 9, True), (4, 13, 6, False), (2, 2, 3, False)])
 def test_prove_batch_is_byte_identical_to_single_calls(ctx, m, n, B, workers, monkeypatch):
     # two implementations behind mp_shuffle_and_remask_batch: the lockstep prover (default for
