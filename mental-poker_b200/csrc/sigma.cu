@@ -192,6 +192,25 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
   }
 }
 
+// Resident blocks per SM of k_lincomb, capped through an (unused) dynamic shared memory request.  A thread keeps up to
+// 2 KB of multiples tables in local memory; at the 3 blocks per SM the registers allow, the resident threads' frames
+// are 148 x 384 x 2.7 KB = 154 MB -- more than the L2 holds, so the table reads of the two-base jobs went to HBM
+// (ncu, 65 536 verify_reveal jobs: 3.9 GB of DRAM traffic at 3 blocks per SM, 0.27 GB at 2, 0.05 GB at 1; round 1
+// measured 8.6 GB).  The kernel is bound by its dependent multiplication chains, not by that traffic: the eight
+// launches of the six batched calls take 36.9 / 36.7 / 46.0 ms at 3 / 2 / 1 blocks per SM, and a 128-register build at
+// 4 blocks per SM was slower (and moved 8.4 GB).  Default 2; MP_LINCOMB_BLOCKS = 0 removes the cap.
+static size_t lincomb_smem() {
+  static const size_t bytes = [] {
+    const char* e = getenv("MP_LINCOMB_BLOCKS");
+    const int blocks = e ? atoi(e) : 2;
+    if (blocks <= 0) return (size_t)0;
+    const size_t b = (size_t)(227 * 1024) / (size_t)blocks - 1024;   // 1 KB per block is reserved by the system
+    cudaFuncSetAttribute(k_lincomb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+    return b;
+  }();
+  return bytes;
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -277,8 +296,8 @@ struct SigmaCall {
     if (h_flags) NEED(d_flags);
     CK(cudaMemcpyAsync(d_kinds, kinds.data(), sizeof(JobKind) * nk, cudaMemcpyHostToDevice, st));
     k_make_jobs<<<(nj + 255) / 256, 256, 0, st>>>(d_kinds, nk, (uint32_t)n, (uint32_t*)d_jobs);
-    k_lincomb<<<(nj + 127) / 128, 128, 0, st>>>(d_jobs, nj, d_arena, d_scal, S->d_tab, (h_canon ? 1 : 0) | (h_flags ? 2 : 0), d_out,
-                                                d_flags);
+    k_lincomb<<<(nj + 127) / 128, 128, lincomb_smem(), st>>>(d_jobs, nj, d_arena, d_scal, S->d_tab, (h_canon ? 1 : 0) | (h_flags ? 2 : 0),
+                                                             d_out, d_flags);
     CK(cudaGetLastError());
     ctx->launches += 2;
     if (h_canon) CK(cudaMemcpyAsync(h_canon, d_out, (size_t)nj * 64, cudaMemcpyDeviceToHost, st));
