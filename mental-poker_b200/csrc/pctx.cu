@@ -73,6 +73,8 @@ void ctx_destroy(mp_ctx* ctx) {
   if (ctx->shuffle) shuffle_state_destroy(ctx->shuffle);
   for (auto& b : ctx->bufs)
     if (b.ptr) cudaFree(b.ptr);
+  if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
+  if (ctx->mark_ev) cudaEventDestroy(ctx->mark_ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

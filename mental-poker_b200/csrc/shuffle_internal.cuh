@@ -205,8 +205,9 @@ inline size_t small_deck_max() {
 
 // Runs fn(worker, i) for i in [0, B) on P worker contexts (own stream / workspace / tables each),
 // one host thread per worker.  Returns the first error; ctx->launches = total kernel launches.
+// `sleeping_waits`: the workers' host waits sleep instead of spinning (ctx.cuh stream_wait).
 template <typename F>
-int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn) {
+int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn, bool sleeping_waits = false) {
   ShuffleState* S = ctx->shuffle;
   while ((int)S->workers.size() < P) {
     mp_ctx* w = nullptr;
@@ -226,6 +227,7 @@ int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn) {
   auto run = [&](int t) {
     mp_ctx* w = S->workers[t];
     cudaSetDevice(w->device);
+    w->blocking = sleeping_waits;
     for (uint64_t i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
       if (first_err.load() != MP_OK) break;
       int32_t st = fn(w, i);

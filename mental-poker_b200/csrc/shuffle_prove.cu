@@ -143,7 +143,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, m, st));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(proof_out + L.cA, d_canon, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(S->ev, st));
+  CK(mark_record(ctx, S->ev, st));
   // Every shuffled-deck point is multiplied by m + 1 scalar rows in the diagonal MSMs, so
   // pre-shifting it once (table[w] = 2^(c w) * point) pays: all windows of a job then share ONE
   // bucket set -- one bucket reduction per job instead of W, no fold doublings, and a wider
@@ -168,7 +168,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   Transcript& fs = fs_started ? *fs_started : fs_local;
   if (!fs_started) absorb_statement_head(fs, S, pk, deck, N);
   absorb_statement_deck2(fs, deck2, N);
-  CK(cudaEventSynchronize(S->ev));  // c_A is on the host; the table / leaf-row kernels continue
+  CK(mark_wait(ctx, S->ev));  // c_A is on the host; the table / leaf-row kernels continue
   trace.mark("statement hashed up to c_A; c_A on host");
   absorb_statement_tail(fs, proof_out + L.cA, m);
   const fr x = fs.challenge();
@@ -217,7 +217,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, m, st));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(proof_out + L.cB, d_canon, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(stream_wait(ctx, st));
   trace.mark("round B: c_B on host");
   fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof_out + L.cB, m); fs.end();
   const fr y = fs.challenge();
@@ -240,9 +240,9 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   fr* h_col = reinterpret_cast<fr*>(h_pin);
   CK(cudaMemcpyAsync(h_col, d_Bv + (size_t)(m - 1) * n, sizeof(fr) * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_col + n, d_partials + fr_reduce_blocks(N), sizeof(fr), cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(S->ev, st));
+  CK(mark_record(ctx, S->ev, st));
 
-  CK(cudaEventSynchronize(S->ev));  // col / rho* are on the host
+  CK(mark_wait(ctx, S->ev));  // col / rho* are on the host
   trace.mark("round C.1: product column on host");
   std::vector<fr> col(h_col, h_col + n);
   const fr rho_star = fr_neg(h_col[n]);
@@ -306,7 +306,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(cudaMemcpyAsync(proof_out + L.svpts, d_canon2 + (size_t)m * 64, 3 * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proof_out + L.mepts, d_canon2 + (size_t)(m + 3) * 64, (size_t)(2 * m + 1) * 64, cudaMemcpyDeviceToHost, st));
   }
-  CK(cudaStreamSynchronize(st));
+  CK(stream_wait(ctx, st));
   trace.mark("round C.5: commitment batch on host");
   memcpy(proof_out + L.cb, proof_out + L.hB + 64 * (size_t)(m - 1), 64);  // c_b = c_B[m-1]
   fs.begin(); fs.feed_label("hadamard_argument"); fs.feed_points64(proof_out + L.cb, 1); fs.feed_points64(proof_out + L.hB, m); fs.end();
@@ -360,7 +360,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(xyzz_to_canonical(d_g1_out, (uint32_t*)d_canon, 2 * (size_t)m + 3, st));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(proof_out + L.zpts, d_canon, (2 * (size_t)m + 3) * 64, cudaMemcpyDeviceToHost, st));
-    if (trace.on) { CK(cudaStreamSynchronize(st)); trace.mark("round D: zero-argument commitments on host"); }
+    if (trace.on) { CK(stream_wait(ctx, st)); trace.mark("round D: zero-argument commitments on host"); }
     // join the bulk stream: E_k = diag_k + Enc(b_k*ghat; tau_k), needed for the last absorb below
     CK(cudaStreamWaitEvent(st, S->ev_bulk_done, 0));
     k_combine_E<<<(4 * m + 63) / 64, 64, 0, st>>>(d_ct_out, d_enc, d_enc + 2 * m, 2 * m);
@@ -369,7 +369,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
     CK(xyzz_to_canonical(d_ct_out, (uint32_t*)d_canonE, 4 * (size_t)m, st));
     ctx->launches += 2;
     CK(cudaMemcpyAsync(proof_out + L.meE, d_canonE, 4 * (size_t)m * 64, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_wait(ctx, st));
   }
   trace.mark("round D + E_k on host");
   fs.begin(); fs.feed_label("zero_argument"); fs.feed_points64(proof_out + L.zpts, 2 * (size_t)m + 3); fs.end();
@@ -437,7 +437,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   }
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(stream_wait(ctx, st));
   trace.mark("responses on host");
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not a canonical point of the Stark curve");
   return MP_OK;

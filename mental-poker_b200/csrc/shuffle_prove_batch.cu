@@ -126,7 +126,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     launches += 1;
     h_pts.resize(npoints_out * kPointBytes);
     CK(cudaMemcpyAsync(h_pts.data(), d_canon, npoints_out * kPointBytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_wait(ctx, st));
     dev_done();
     return MP_OK;
   };
@@ -283,7 +283,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
     launches += 3;
     h_pts.resize((Bs * JC + totalE) * kPointBytes);
     CK(cudaMemcpyAsync(h_pts.data(), d_canon, h_pts.size(), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_wait(ctx, st));
     dev_done();
   }
 
@@ -398,7 +398,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   int bad = 0;
   host_done();
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(stream_wait(ctx, st));
   dev_done();
   if (trace_on) fprintf(stderr, "prove_sub_batch: %zu proofs, %d threads: host phases %.2f ms, device phases %.2f ms\n", Bs, threads, t_host, t_dev);
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not a canonical point of the Stark curve");
@@ -459,7 +459,7 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
       w->launches += l;
     }
     return st;
-  });
+  }, /*sleeping_waits=*/P > 1);
 #endif
 }
 

@@ -135,7 +135,7 @@ int32_t shuffle_ensure_pk_table(mp_ctx* ctx, const uint8_t* pk) {
   ctx->launches += 1;
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(stream_wait(ctx, ctx->stream));
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not on the Stark curve");
   memcpy(S->tab_pk, pk, kPointBytes);
   S->tab_pk_valid = true;
@@ -242,7 +242,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   int bad = 0;
   CK(cudaMemcpyAsync(S->gsum, d_res, kPointBytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(stream_wait(ctx, ctx->stream));
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a parameter point is not a canonical point of the Stark curve");
   S->m = m;
   S->n = n;
@@ -294,7 +294,7 @@ int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(cudaMemcpyAsync(out_deck, d_out, N * kCtBytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (fs_head) absorb_statement_head(*fs_head, S, pk, deck, N);  // host hashing overlaps the copies and the kernel
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(stream_wait(ctx, ctx->stream));
   // distinct bits (atomicOr): an out-of-range permutation entry can no longer hide an off-curve key or card
   if (bad & 1) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck point or the public key is not on the Stark curve");
   if (rebuild_pk) {  // pk validated by k_build_table: the table may be reused by later calls
@@ -348,7 +348,7 @@ int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* 
   CK(xyzz_to_canonical(d_res, (uint32_t*)d_canon, k, ctx->stream));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(out, d_canon, k * kPointBytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(stream_wait(ctx, ctx->stream));
   return MP_OK;
 }
 

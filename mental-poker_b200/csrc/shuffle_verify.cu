@@ -123,7 +123,7 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   CK(cudaMemcpyAsync(h_res + sizeof(fr), d_g1_out, (size_t)J * sizeof(xyzz), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(h_res + sizeof(fr) + (size_t)J * sizeof(xyzz), d_ct_out, 4 * sizeof(xyzz), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(h_res + sizeof(fr) + (size_t)(J + 4) * sizeof(xyzz), d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(stream_wait(ctx, ctx->stream));
   int bad;
   memcpy(&bad, h_res + sizeof(fr) + (size_t)(J + 4) * sizeof(xyzz), sizeof(int));
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a deck or proof point is not a canonical point of the Stark curve");
@@ -255,7 +255,7 @@ static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* d
   std::vector<int> bad(Bs, 0);
   CK(cudaMemcpyAsync(flags.data(), d_flags, Bs * 12, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(bad.data(), d_bad, Bs * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(stream_wait(ctx, st));
   for (size_t p = 0; p < Bs; p++) {
     // a malformed item (point off the curve / not canonical, scalar >= the group order) fails on its own, as the
     // reference's deserialiser would fail it, and does not take the rest of the batch with it
@@ -290,7 +290,7 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
       if (st == MP_ERR_NOT_ON_CURVE || st == MP_ERR_NOT_CANONICAL) st = MP_VERIFY_MALFORMED;  // this item only
       if (st >= 0) statuses[p] = st;
       return st < 0 ? st : MP_OK;
-    });
+    }, /*sleeping_waits=*/P > 1);
   }
   int threads = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
   threads = std::max(1, std::min(threads, 64));

@@ -304,7 +304,7 @@ struct SigmaCall {
     if (h_flags) CK(cudaMemcpyAsync(h_flags, d_flags, (size_t)nj, cudaMemcpyDeviceToHost, st));
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_wait(ctx, st));
     if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of the Stark curve");
     return MP_OK;
   }

@@ -136,7 +136,7 @@ int32_t wire_points_decompress(mp_ctx* ctx, const uint8_t* in, uint64_t n, uint8
     st.resize(n);
     CK(cudaMemcpyAsync(st.data(), d_status, n, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(stream_wait(ctx, ctx->stream));
   if (statuses)
     for (uint64_t i = 0; i < n; i++) statuses[i] = st[i];
   if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a compressed point is malformed or not on the Stark curve");
