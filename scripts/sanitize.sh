@@ -31,4 +31,11 @@ for tool in synccheck memcheck; do
   timeout 500 $CS --tool $tool --print-limit 20 python -m pytest tests/test_gpu_shuffle.py -m gpu -x -q -k "golden and host_scalars or negative_case" > $OUT/shuffle_$tool.log 2>&1
   echo "shuffle tests $tool: $(grep -E 'ERROR SUMMARY' $OUT/shuffle_$tool.log | tail -1) / $(tail -1 $OUT/shuffle_$tool.log)" >> $SUM
 done
+# --- the MSM pipeline of both curves (quad-cooperative fold / combine kernels use quad-masked shuffles) and the sigma kernel
+for tool in synccheck racecheck; do
+  timeout 500 $CS --tool $tool --print-limit 20 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_bls12_377.py -m gpu -x -q -k "msm_small or msm_golden or msm_jobs or ct_msm" > $OUT/msm_$tool.log 2>&1
+  echo "msm tests (both curves) $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/msm_$tool.log | tail -1) / $(tail -1 $OUT/msm_$tool.log)" >> $SUM
+done
+timeout 500 $CS --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_sigma.py -m gpu -x -q -k "golden or vs_oracle" > $OUT/sigma_memcheck.log 2>&1
+echo "sigma tests memcheck: $(grep -E 'ERROR SUMMARY' $OUT/sigma_memcheck.log | tail -1) / $(tail -1 $OUT/sigma_memcheck.log)" >> $SUM
 cat $SUM
