@@ -86,6 +86,39 @@ int32_t mp377_shuffle_and_remask_batch(mp377_ctx* ctx, const uint8_t* pk, const 
                                        const uint8_t* rhos, const uint8_t* randomness, uint64_t batch, uint8_t* out_decks,
                                        uint8_t* proofs, int32_t host_threads);
 
+/* Batched sigma protocols either side of the shuffle over this curve: BarnettSmartProtocol::{mask, verify_mask, remask,
+ * verify_remask, compute_reveal_token, verify_reveal, prove_key_ownership, verify_key_ownership} (reference
+ * src/lib.rs:88-175, impl mod.rs:132-354), n independent items per call.  Same contract as mp_mask_batch ...
+ * mp_key_ownership_verify_batch of mpshuffle.h with 96-byte points: Chaum-Pedersen proof = a (96) | b (96) | r (32) =
+ * 224 bytes, Schnorr proof = commit (96) | opening (32) = 128 bytes; the generator is enc_g of mp377_ctx_set_params
+ * (which must have been called).  statuses[i] = MP_OK or MP_VERIFY_CHAUM_PEDERSEN / MP_VERIFY_SCHNORR.  The verifiers
+ * reject the call with MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_IN_SUBGROUP if any point they are handed (keys, cards,
+ * ciphertexts, tokens, proof commitments) is not a canonical point of G1, as the reference's deserialiser would;
+ * the provers take their inputs as trusted (on-curve is still checked).  Bytes are identical to oracle/py/sigma.py
+ * under curve("bls12_377"). */
+int32_t mp377_mask_batch(mp377_ctx* ctx, const uint8_t* shared_key /* 96 */, const uint8_t* cards /* n*96 */,
+                         const uint8_t* r /* n*32 */, const uint8_t* omega /* n*32 */, uint64_t n,
+                         uint8_t* out_masked /* n*192 */, uint8_t* out_proofs /* n*224 */, int32_t host_threads);
+int32_t mp377_verify_mask_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* masked,
+                                const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t mp377_remask_prove_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck /* n*192 */,
+                                 const uint8_t* alpha /* n*32 */, const uint8_t* omega /* n*32 */, uint64_t n,
+                                 uint8_t* out_deck /* n*192 */, uint8_t* out_proofs /* n*224 */, int32_t host_threads);
+int32_t mp377_verify_remask_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* remasked,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t mp377_reveal_batch(mp377_ctx* ctx, const uint8_t* sk /* 32 */, const uint8_t* pk /* 96 */,
+                           const uint8_t* masked /* n*192 */, const uint8_t* omega /* n*32 */, uint64_t n,
+                           uint8_t* out_tokens /* n*96 */, uint8_t* out_proofs /* n*224 */, int32_t host_threads);
+int32_t mp377_verify_reveal_batch(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* tokens, const uint8_t* masked,
+                                  const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads);
+int32_t mp377_key_ownership_prove_batch(mp377_ctx* ctx, const uint8_t* pks /* n*96 */, const uint8_t* sks /* n*32 */,
+                                        const uint8_t* infos, const uint64_t* info_offsets /* n+1 */,
+                                        const uint8_t* omega /* n*32 */, uint64_t n, uint8_t* out_proofs /* n*128 */,
+                                        int32_t host_threads);
+int32_t mp377_key_ownership_verify_batch(mp377_ctx* ctx, const uint8_t* pks, const uint8_t* infos,
+                                         const uint64_t* info_offsets, const uint8_t* proofs, uint64_t n,
+                                         int32_t* statuses, int32_t host_threads);
+
 /* Subgroup membership of n canonical points (n * 96 bytes): MP_OK iff every point is a canonical point of the curve
  * and lies in the order-r subgroup G1; otherwise MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_IN_SUBGROUP.  statuses (optional,
  * n entries): 0 = in G1, 1 = not a canonical curve point, 2 = on the curve but outside G1.  One 127-bit

@@ -10,6 +10,7 @@ _vp, _i32, _u64, _cp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.
 _pd, _pu64 = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64)
 
 FQ_BYTES, POINT_BYTES, SCALAR_BYTES = 48, 96, 32
+CP_PROOF_BYTES, SCHNORR_PROOF_BYTES = 2 * POINT_BYTES + 32, POINT_BYTES + 32   # a | b | r ; commit | opening
 
 # name -> (restype, argtypes); must list every symbol include/mpshuffle_bls12_377.h declares
 SIGNATURES = {
@@ -38,6 +39,14 @@ SIGNATURES = {
     "mp377_shuffle_and_remask": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _cp, _cp]),
     "mp377_shuffle_and_remask_batch": (_i32, [_vp, _cp, _cp, _vp, _cp, _cp, _u64, _cp, _cp, _i32]),
     "mp377_subgroup_check": (_i32, [_vp, _cp, _u64, ctypes.POINTER(_i32)]),
+    "mp377_mask_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, _cp, _cp, _i32]),
+    "mp377_verify_mask_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp377_remask_prove_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, _cp, _cp, _i32]),
+    "mp377_verify_remask_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp377_reveal_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, _cp, _cp, _i32]),
+    "mp377_verify_reveal_batch": (_i32, [_vp, _cp, _cp, _cp, _cp, _u64, ctypes.POINTER(_i32), _i32]),
+    "mp377_key_ownership_prove_batch": (_i32, [_vp, _cp, _cp, _cp, ctypes.POINTER(_u64), _cp, _u64, _cp, _i32]),
+    "mp377_key_ownership_verify_batch": (_i32, [_vp, _cp, _cp, ctypes.POINTER(_u64), _cp, _u64, ctypes.POINTER(_i32), _i32]),
     "mp377_shuffle_verify": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp, _cp, _cp, _cp, _cp]),
     "mp377_msm_jobs": (_i32, [_vp, _cp, _u64, _i32, _cp, _u64, ctypes.POINTER(ctypes.c_uint32), _u64, _i32, _cp]),
     "mp377_msm_g1_windows_device": (_i32, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp]),
@@ -209,6 +218,72 @@ class Context:
         st = (_i32 * max(n, 1))()
         rc = lib.mp377_subgroup_check(self.h, points, n, st)
         return rc, list(st)[:n]
+
+    # --- batched sigma protocols either side of the shuffle (reference mod.rs:132-354), 96-byte points:
+    #     Chaum-Pedersen proof = a | b | r = 224 bytes, Schnorr proof = commit | opening = 128 bytes
+    def _statuses(self, fn, n, *args, host_threads=0):
+        st = (_i32 * max(n, 1))()
+        _check(self.h, fn(self.h, *args, n, st, host_threads))
+        return list(st)[:n]
+
+    def mask_batch(self, shared_key, cards, r, omega, host_threads=0):
+        """-> (masked cards n*192, Chaum-Pedersen proofs n*224)"""
+        n = len(r) // 32
+        assert len(cards) == POINT_BYTES * n and len(omega) == 32 * n
+        out, proofs = ctypes.create_string_buffer(2 * POINT_BYTES * n), ctypes.create_string_buffer(CP_PROOF_BYTES * n)
+        _check(self.h, lib.mp377_mask_batch(self.h, shared_key, cards, r, omega, n, out, proofs, host_threads))
+        return out.raw, proofs.raw
+
+    def verify_mask_batch(self, shared_key, cards, masked, proofs, host_threads=0):
+        n = len(proofs) // CP_PROOF_BYTES
+        assert len(cards) == POINT_BYTES * n and len(masked) == 2 * POINT_BYTES * n
+        return self._statuses(lib.mp377_verify_mask_batch, n, shared_key, cards, masked, proofs, host_threads=host_threads)
+
+    def remask_prove_batch(self, shared_key, deck, alpha, omega, host_threads=0):
+        n = len(alpha) // 32
+        assert len(deck) == 2 * POINT_BYTES * n and len(omega) == 32 * n
+        out, proofs = ctypes.create_string_buffer(2 * POINT_BYTES * n), ctypes.create_string_buffer(CP_PROOF_BYTES * n)
+        _check(self.h, lib.mp377_remask_prove_batch(self.h, shared_key, deck, alpha, omega, n, out, proofs, host_threads))
+        return out.raw, proofs.raw
+
+    def verify_remask_batch(self, shared_key, deck, remasked, proofs, host_threads=0):
+        n = len(proofs) // CP_PROOF_BYTES
+        assert len(deck) == len(remasked) == 2 * POINT_BYTES * n
+        return self._statuses(lib.mp377_verify_remask_batch, n, shared_key, deck, remasked, proofs, host_threads=host_threads)
+
+    def reveal_batch(self, sk, pk, masked, omega, host_threads=0):
+        """-> (reveal tokens n*96, Chaum-Pedersen proofs n*224) of one player for n masked cards"""
+        n = len(omega) // 32
+        assert len(masked) == 2 * POINT_BYTES * n and len(sk) == 32 and len(pk) == POINT_BYTES
+        tokens, proofs = ctypes.create_string_buffer(POINT_BYTES * n), ctypes.create_string_buffer(CP_PROOF_BYTES * n)
+        _check(self.h, lib.mp377_reveal_batch(self.h, sk, pk, masked, omega, n, tokens, proofs, host_threads))
+        return tokens.raw, proofs.raw
+
+    def verify_reveal_batch(self, pk, tokens, masked, proofs, host_threads=0):
+        n = len(proofs) // CP_PROOF_BYTES
+        assert len(tokens) == POINT_BYTES * n and len(masked) == 2 * POINT_BYTES * n
+        return self._statuses(lib.mp377_verify_reveal_batch, n, pk, tokens, masked, proofs, host_threads=host_threads)
+
+    @staticmethod
+    def _infos(infos):
+        off = [0]
+        for b in infos:
+            off.append(off[-1] + len(b))
+        return b"".join(infos), (_u64 * len(off))(*off)
+
+    def key_ownership_prove_batch(self, pks, sks, infos, omega, host_threads=0):
+        n = len(infos)
+        assert len(pks) == POINT_BYTES * n and len(sks) == 32 * n and len(omega) == 32 * n
+        blob, off = self._infos(infos)
+        proofs = ctypes.create_string_buffer(SCHNORR_PROOF_BYTES * n)
+        _check(self.h, lib.mp377_key_ownership_prove_batch(self.h, pks, sks, blob, off, omega, n, proofs, host_threads))
+        return proofs.raw
+
+    def key_ownership_verify_batch(self, pks, infos, proofs, host_threads=0):
+        n = len(infos)
+        assert len(pks) == POINT_BYTES * n and len(proofs) == SCHNORR_PROOF_BYTES * n
+        blob, off = self._infos(infos)
+        return self._statuses(lib.mp377_key_ownership_verify_batch, n, pks, blob, off, proofs, host_threads=host_threads)
 
     # --- Pedersen
     def set_commit_key(self, ck: bytes):

@@ -13,7 +13,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <initializer_list>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mpshuffle_bls12_377.h"
@@ -299,6 +301,87 @@ extern "C" int32_t mp377_shuffle_and_remask_batch(mp377_ctx* ctx, const uint8_t*
 extern "C" int32_t mp377_shuffle_and_remask(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm,
                                             const uint8_t* rho, const uint8_t* randomness, uint8_t* out_deck, uint8_t* proof_out) {
   return mp377_shuffle_and_remask_batch(ctx, pk, deck, perm, rho, randomness, 1, out_deck, proof_out, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched sigma protocols either side of the shuffle over this curve (SURVEY.md section 8(f) ranks 1 + 3):
+// BarnettSmartProtocol::{mask, verify_mask, remask, verify_remask, compute_reveal_token, verify_reveal,
+// prove_key_ownership, verify_key_ownership} (reference src/lib.rs:88-175, impl mod.rs:132-354) for n items per call.
+// Same source as the Stark build (sigma.cu: one k_lincomb launch per pass, sigma_host.hpp: the per-proof Fiat-Shamir
+// transcripts on host threads), compiled against the 12-limb field; the verifiers first put every untrusted point
+// through the G1 membership test, as the reference's deserialiser would.
+// ------------------------------------------------------------------------------------------
+static constexpr size_t kSigPt = 96, kSigCp = 2 * kSigPt + 32, kSigSchnorr = kSigPt + 32;
+#define NEED_PROVER(ctx)                                                                                     \
+  do {                                                                                                       \
+    if (!(ctx)) return MP_ERR_INVALID_ARG;                                                                   \
+    if (!(ctx)->prover) return (ctx)->fail(MP_ERR_NO_PARAMS, "mp377_ctx_set_params has not been called");    \
+  } while (0)
+// G1 membership of the points a sigma verifier is handed: `whole` arrays of contiguous points plus the leading
+// `lead` bytes of each of n proof records of `rec` bytes
+static int32_t sigma_points_in_g1(mp377_ctx* ctx, std::initializer_list<std::pair<const uint8_t*, uint64_t>> whole,
+                                  const uint8_t* proofs, uint64_t n, size_t rec, size_t lead) {
+  std::vector<uint8_t> all;
+  for (const auto& w : whole)
+    if (w.first && w.second) all.insert(all.end(), w.first, w.first + w.second * kSigPt);
+  if (proofs)
+    for (uint64_t i = 0; i < n; i++) all.insert(all.end(), proofs + rec * i, proofs + rec * i + lead);
+  return all.empty() ? MP_OK : mp377_subgroup_check(ctx, all.data(), all.size() / kSigPt, nullptr);
+}
+extern "C" int32_t mp377_mask_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* r,
+                                    const uint8_t* omega, uint64_t n, uint8_t* out_masked, uint8_t* out_proofs, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  return prover_status(ctx, sigma_mask_batch(ctx->prover, shared_key, cards, r, omega, n, out_masked, out_proofs, host_threads));
+}
+extern "C" int32_t mp377_verify_mask_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* masked,
+                                           const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  if (!shared_key || (n && (!cards || !masked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  int32_t sg = sigma_points_in_g1(ctx, {{shared_key, 1}, {cards, n}, {masked, 2 * n}}, proofs, n, kSigCp, 2 * kSigPt);
+  if (sg != MP_OK) return sg;
+  return prover_status(ctx, sigma_verify_mask_batch(ctx->prover, shared_key, cards, masked, proofs, n, statuses, host_threads));
+}
+extern "C" int32_t mp377_remask_prove_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* alpha,
+                                            const uint8_t* omega, uint64_t n, uint8_t* out_deck, uint8_t* out_proofs,
+                                            int32_t host_threads) {
+  NEED_PROVER(ctx);
+  return prover_status(ctx, sigma_remask_prove_batch(ctx->prover, shared_key, deck, alpha, omega, n, out_deck, out_proofs, host_threads));
+}
+extern "C" int32_t mp377_verify_remask_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* remasked,
+                                             const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  if (!shared_key || (n && (!deck || !remasked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  int32_t sg = sigma_points_in_g1(ctx, {{shared_key, 1}, {deck, 2 * n}, {remasked, 2 * n}}, proofs, n, kSigCp, 2 * kSigPt);
+  if (sg != MP_OK) return sg;
+  return prover_status(ctx, sigma_verify_remask_batch(ctx->prover, shared_key, deck, remasked, proofs, n, statuses, host_threads));
+}
+extern "C" int32_t mp377_reveal_batch(mp377_ctx* ctx, const uint8_t* sk, const uint8_t* pk, const uint8_t* masked,
+                                      const uint8_t* omega, uint64_t n, uint8_t* out_tokens, uint8_t* out_proofs, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  return prover_status(ctx, sigma_reveal_batch(ctx->prover, sk, pk, masked, omega, n, out_tokens, out_proofs, host_threads));
+}
+extern "C" int32_t mp377_verify_reveal_batch(mp377_ctx* ctx, const uint8_t* pk, const uint8_t* tokens, const uint8_t* masked,
+                                             const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  if (!pk || (n && (!tokens || !masked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  int32_t sg = sigma_points_in_g1(ctx, {{pk, 1}, {tokens, n}, {masked, 2 * n}}, proofs, n, kSigCp, 2 * kSigPt);
+  if (sg != MP_OK) return sg;
+  return prover_status(ctx, sigma_verify_reveal_batch(ctx->prover, pk, tokens, masked, proofs, n, statuses, host_threads));
+}
+extern "C" int32_t mp377_key_ownership_prove_batch(mp377_ctx* ctx, const uint8_t* pks, const uint8_t* sks, const uint8_t* infos,
+                                                   const uint64_t* info_offsets, const uint8_t* omega, uint64_t n,
+                                                   uint8_t* out_proofs, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  return prover_status(ctx, sigma_key_ownership_prove_batch(ctx->prover, pks, sks, infos, info_offsets, omega, n, out_proofs, host_threads));
+}
+extern "C" int32_t mp377_key_ownership_verify_batch(mp377_ctx* ctx, const uint8_t* pks, const uint8_t* infos,
+                                                    const uint64_t* info_offsets, const uint8_t* proofs, uint64_t n,
+                                                    int32_t* statuses, int32_t host_threads) {
+  NEED_PROVER(ctx);
+  if (n && (!pks || !info_offsets || !proofs || !statuses)) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
+  int32_t sg = sigma_points_in_g1(ctx, {{pks, n}}, proofs, n, kSigSchnorr, kSigPt);
+  if (sg != MP_OK) return sg;
+  return prover_status(ctx, sigma_key_ownership_verify_batch(ctx->prover, pks, infos, info_offsets, proofs, n, statuses, host_threads));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -401,7 +401,7 @@ int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, co
   CK(stream_wait(ctx, st));
   dev_done();
   if (trace_on) fprintf(stderr, "prove_sub_batch: %zu proofs, %d threads: host phases %.2f ms, device phases %.2f ms\n", Bs, threads, t_host, t_dev);
-  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not a canonical point of the Stark curve");
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not a canonical point of the curve");
   ctx->launches = launches;
   return MP_OK;
 }

@@ -243,7 +243,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
   CK(cudaMemcpyAsync(S->gsum, d_res, kPointBytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(stream_wait(ctx, ctx->stream));
-  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a parameter point is not a canonical point of the Stark curve");
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a parameter point is not a canonical point of the curve");
   S->m = m;
   S->n = n;
   S->params_gen++;

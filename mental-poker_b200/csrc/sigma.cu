@@ -20,6 +20,8 @@
 namespace mp {
 
 static constexpr uint32_t kNone = 0xffffffffu;
+static constexpr int kLcPointWords = 2 * kFqLimbs;  // canonical x || y of one point, 32-bit words
+static constexpr size_t PB = kPointBytes, CB = kCtBytes;  // C-ABI point / ciphertext: 64 / 128 bytes (Stark), 96 / 192 (BLS12-377)
 struct LcJob {
   uint32_t var_pt[2];  // arena indices of the variable bases (kNone = unused)
   uint32_t var_sc[2];  // scalar indices for them
@@ -68,7 +70,7 @@ __device__ __forceinline__ affine ld_point(const affine* p) {
   const uint4* s = reinterpret_cast<const uint4*>(p);
   uint4* d = reinterpret_cast<uint4*>(&r);
 #pragma unroll
-  for (int i = 0; i < 4; i++) d[i] = s[i];
+  for (int i = 0; i < (int)(sizeof(affine) / 16); i++) d[i] = s[i];
   return r;
 }
 // out-of-line group operations, operands and result BY VALUE: see msm.cu xyzz_add_v (NVVM merges the stack slots of
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
         const uint4* s = reinterpret_cast<const uint4*>(T + w * kTabDigits8 + (d - 1));
         uint4* dst = reinterpret_cast<uint4*>(&e);
 #pragma unroll
-        for (int q = 0; q < 4; q++) dst[q] = __ldg(s + q);
+        for (int q = 0; q < (int)(sizeof(affine) / 16); q++) dst[q] = __ldg(s + q);
         madd_call(acc, e);
       }
     }
@@ -175,19 +177,19 @@ __global__ void __launch_bounds__(128) k_lincomb(const LcJob* __restrict__ jobs,
       uint4* d = reinterpret_cast<uint4*>(arena + j.out_pt);
       const uint4* s = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
-      for (int q = 0; q < 4; q++) d[q] = s[q];
+      for (int q = 0; q < (int)(sizeof(affine) / 16); q++) d[q] = s[q];
     }
     if (flags & 1) {
-      uint32_t w[16];
+      uint32_t w[kLcPointWords];
       if (affine_is_identity(r)) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) w[q] = 0;
+        for (int q = 0; q < kLcPointWords; q++) w[q] = 0;
       } else {
         affine_to_canonical(r, w);
       }
-      uint4* o = reinterpret_cast<uint4*>(out_canon + (size_t)g * 16);
+      uint4* o = reinterpret_cast<uint4*>(out_canon + (size_t)g * kLcPointWords);
 #pragma unroll
-      for (int q = 0; q < 4; q++) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      for (int q = 0; q < kLcPointWords / 4; q++) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
   }
 }
@@ -238,7 +240,7 @@ struct SigmaCall {
     n_in = in_points;
     n_arena = in_points + reserved_points;
     n_scal = scalars;
-    d_canon = (uint8_t*)ctx->scratch(sSigCanon, n_in * 64 + 64);
+    d_canon = (uint8_t*)ctx->scratch(sSigCanon, n_in * PB + 64);
     d_arena = (affine*)ctx->scratch(sSigArena, n_arena * sizeof(affine) + 64);
     d_scal = (uint32_t*)ctx->scratch(sSigScal, n_scal * 32 + 64);
     d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
@@ -257,7 +259,7 @@ struct SigmaCall {
   // `records` rows of `width` bytes, `pitch` bytes apart in a staged (device) buffer -> arena slot / scalar `first`
   int32_t points_from(uint64_t first, const uint8_t* d_src, uint64_t records, size_t width, size_t pitch) {
     if (!records) return MP_OK;
-    CK(cudaMemcpy2DAsync(d_canon + first * 64, width, d_src, pitch, width, records, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(d_canon + first * PB, width, d_src, pitch, width, records, cudaMemcpyDeviceToDevice, st));
     return MP_OK;
   }
   int32_t scalars_from(uint64_t first, const uint8_t* d_src, uint64_t count, size_t pitch) {
@@ -268,7 +270,7 @@ struct SigmaCall {
   // contiguous caller buffers go straight to their place
   int32_t put_points(uint64_t first, const uint8_t* src, uint64_t count) {
     if (!count) return MP_OK;
-    CK(cudaMemcpyAsync(d_canon + first * 64, src, count * 64, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_canon + first * PB, src, count * PB, cudaMemcpyHostToDevice, st));
     return MP_OK;
   }
   int32_t put_scalars(uint64_t first, const uint8_t* src, uint64_t count) {
@@ -288,7 +290,7 @@ struct SigmaCall {
     if (!nj) return MP_OK;
     JobKind* d_kinds = (JobKind*)ctx->scratch(sSigKinds, sizeof(JobKind) * 16);
     LcJob* d_jobs = (LcJob*)ctx->scratch(sSigJobs, (size_t)nj * sizeof(LcJob));
-    uint32_t* d_out = h_canon ? (uint32_t*)ctx->scratch(sSigOut, (size_t)nj * 64) : nullptr;
+    uint32_t* d_out = h_canon ? (uint32_t*)ctx->scratch(sSigOut, (size_t)nj * PB) : nullptr;
     uint8_t* d_flags = h_flags ? (uint8_t*)ctx->scratch(sSigFlags, (size_t)nj + 64) : nullptr;
     NEED(d_kinds); NEED(d_jobs);
     if (nk > 16) return ctx->fail(MP_ERR_INVALID_ARG, "internal: too many job kinds");
@@ -300,12 +302,12 @@ struct SigmaCall {
                                                              d_out, d_flags);
     CK(cudaGetLastError());
     ctx->launches += 2;
-    if (h_canon) CK(cudaMemcpyAsync(h_canon, d_out, (size_t)nj * 64, cudaMemcpyDeviceToHost, st));
+    if (h_canon) CK(cudaMemcpyAsync(h_canon, d_out, (size_t)nj * PB, cudaMemcpyDeviceToHost, st));
     if (h_flags) CK(cudaMemcpyAsync(h_flags, d_flags, (size_t)nj, cudaMemcpyDeviceToHost, st));
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(stream_wait(ctx, st));
-    if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of the Stark curve");
+    if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "an input point is not a canonical point of the curve");
     return MP_OK;
   }
 };
@@ -371,25 +373,25 @@ static int32_t cp_fixed_prove(mp_ctx* ctx, bool remask, const uint8_t* pk, const
     kinds[4].set(fFixSc1, 0).set(fAddPt, 0);
   }
   ShuffleState* S = ctx->shuffle;
-  uint8_t* res = pinned(S, kinds.size() * n * 64);
+  uint8_t* res = pinned(S, kinds.size() * n * PB);
   if (!res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
   if ((rc = sc.run(kinds, n, res, nullptr)) != MP_OK) return rc;
   const char* seed = remask ? kSeedRemasking : kSeedMasking;
   const Transcript seeded(seed, strlen(seed));
-  auto R = [&](int kind, uint64_t i) { return res + ((size_t)kind * n + i) * 64; };
+  auto R = [&](int kind, uint64_t i) { return res + ((size_t)kind * n + i) * PB; };
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
     const fr c = cp_challenge(seeded, S->enc_g, pk, R(0, i), R(1, i), R(2, i), R(3, i));
     const fr r = fr_add(fr_from_bytes(omega + 32 * i), fr_mul(c, fr_from_bytes(wit + 32 * i)));
     uint8_t* p = proofs + kCpProofLen * i;
-    memcpy(p, R(2, i), 64);
-    memcpy(p + 64, R(3, i), 64);
-    fr_to_bytes(r, p + 128);
+    memcpy(p, R(2, i), PB);
+    memcpy(p + PB, R(3, i), PB);
+    fr_to_bytes(r, p + 2 * PB);
     if (remask) {
-      memcpy(out + 128 * i, R(4, i), 64);
-      memcpy(out + 128 * i + 64, R(5, i), 64);
+      memcpy(out + CB * i, R(4, i), PB);
+      memcpy(out + CB * i + PB, R(5, i), PB);
     } else {
-      memcpy(out + 128 * i, R(0, i), 64);
-      memcpy(out + 128 * i + 64, R(4, i), 64);
+      memcpy(out + CB * i, R(0, i), PB);
+      memcpy(out + CB * i + PB, R(4, i), PB);
     }
   });
   return MP_OK;
@@ -411,8 +413,8 @@ static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, cons
   if ((rc = sc.put_points(oIn, in, per * n)) != MP_OK) return rc;
   if ((rc = sc.put_points(oOut, out, 2 * n)) != MP_OK) return rc;
   if ((rc = sc.stage(0, proofs, n * kCpProofLen, &d_proofs)) != MP_OK) return rc;
-  if ((rc = sc.points_from(oAB, d_proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
-  if ((rc = sc.scalars_from(0, d_proofs + 128, n, kCpProofLen)) != MP_OK) return rc;  // scalars [0, n): responses r
+  if ((rc = sc.points_from(oAB, d_proofs, n, 2 * PB, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.scalars_from(0, d_proofs + 2 * PB, n, kCpProofLen)) != MP_OK) return rc;  // scalars [0, n): responses r
   if ((rc = sc.ingest()) != MP_OK) return rc;
   // pass 1: the statement.  mask: s0 = out.c1 (no job), s1 = out.c2 - card;  remask: s = out - in
   std::vector<JobKind> kinds;
@@ -424,7 +426,7 @@ static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, cons
     kinds[0].set(fAddPt, oOut + 1, 2).set(fSubPt, oIn).set(fOutPt, oS + n);
   }
   ShuffleState* S = ctx->shuffle;
-  const size_t stmt_bytes = kinds.size() * n * 64;
+  const size_t stmt_bytes = kinds.size() * n * PB;
   uint8_t* pin = pinned(S, stmt_bytes + 2 * n + 64);
   if (!pin) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
   uint8_t *stmt = pin, *flags = pin + stmt_bytes;
@@ -435,11 +437,11 @@ static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, cons
   std::vector<uint8_t> negc((size_t)n * 32), canon_ok((size_t)n);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
     const uint8_t* p = proofs + kCpProofLen * i;
-    const uint8_t* s0 = remask ? stmt + 64 * i : out + 128 * i;
-    const uint8_t* s1 = remask ? stmt + 64 * (n + i) : stmt + 64 * i;
-    const fr c = cp_challenge(seeded, S->enc_g, pk, s0, s1, p, p + 64);
+    const uint8_t* s0 = remask ? stmt + PB * i : out + CB * i;
+    const uint8_t* s1 = remask ? stmt + PB * (n + i) : stmt + PB * i;
+    const fr c = cp_challenge(seeded, S->enc_g, pk, s0, s1, p, p + PB);
     fr_to_bytes(fr_neg(c), negc.data() + 32 * i);
-    canon_ok[i] = fr_bytes_canonical(p + 128);
+    canon_ok[i] = fr_bytes_canonical(p + 2 * PB);
   });
   if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;  // scalars [n, 2n): -c
   kinds.assign(2, JobKind());
@@ -478,8 +480,8 @@ int32_t sigma_reveal_batch(mp_ctx* ctx, const uint8_t* sk, const uint8_t* pk, co
   SigmaCall sc;
   if ((rc = sc.init(ctx, n, 0, n + 1)) != MP_OK) return rc;
   const uint8_t* d_masked;
-  if ((rc = sc.stage(0, masked, n * 128, &d_masked)) != MP_OK) return rc;
-  if ((rc = sc.points_from(0, d_masked, n, 64, 128)) != MP_OK) return rc;  // c1 of every card
+  if ((rc = sc.stage(0, masked, n * CB, &d_masked)) != MP_OK) return rc;
+  if ((rc = sc.points_from(0, d_masked, n, PB, CB)) != MP_OK) return rc;  // c1 of every card
   if ((rc = sc.put_scalars(0, omega, n)) != MP_OK) return rc;
   if ((rc = sc.put_scalars(n, sk, 1)) != MP_OK) return rc;
   if ((rc = sc.ingest()) != MP_OK) return rc;
@@ -488,20 +490,20 @@ int32_t sigma_reveal_batch(mp_ctx* ctx, const uint8_t* sk, const uint8_t* pk, co
   kinds[1].set(fVarPt0, 0).set(fVarSc0, 0);
   kinds[2].set(fFixSc0, 0);
   ShuffleState* S = ctx->shuffle;
-  uint8_t* res = pinned(S, 3 * n * 64);
+  uint8_t* res = pinned(S, 3 * n * PB);
   if (!res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
   if ((rc = sc.run(kinds, n, res, nullptr)) != MP_OK) return rc;
   const Transcript seeded(kSeedReveal, strlen(kSeedReveal));
   const fr skf = fr_from_bytes(sk);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
-    const uint8_t *tok = res + 64 * i, *a = res + 64 * (n + i), *b = res + 64 * (2 * n + i);
-    const fr c = cp_challenge(seeded, masked + 128 * i, S->enc_g, tok, pk, a, b);
+    const uint8_t *tok = res + PB * i, *a = res + PB * (n + i), *b = res + PB * (2 * n + i);
+    const fr c = cp_challenge(seeded, masked + CB * i, S->enc_g, tok, pk, a, b);
     const fr r = fr_add(fr_from_bytes(omega + 32 * i), fr_mul(c, skf));
-    memcpy(out_tokens + 64 * i, tok, 64);
+    memcpy(out_tokens + PB * i, tok, PB);
     uint8_t* p = out_proofs + kCpProofLen * i;
-    memcpy(p, a, 64);
-    memcpy(p + 64, b, 64);
-    fr_to_bytes(r, p + 128);
+    memcpy(p, a, PB);
+    memcpy(p + PB, b, PB);
+    fr_to_bytes(r, p + 2 * PB);
   });
   return MP_OK;
 }
@@ -517,22 +519,22 @@ int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t*
   SigmaCall sc;
   if ((rc = sc.init(ctx, 4 * n + 1, 0, 2 * n)) != MP_OK) return rc;
   const uint8_t *d_masked, *d_proofs;
-  if ((rc = sc.stage(0, masked, n * 128, &d_masked)) != MP_OK) return rc;
+  if ((rc = sc.stage(0, masked, n * CB, &d_masked)) != MP_OK) return rc;
   if ((rc = sc.stage(1, proofs, n * kCpProofLen, &d_proofs)) != MP_OK) return rc;
-  if ((rc = sc.points_from(oC1, d_masked, n, 64, 128)) != MP_OK) return rc;
+  if ((rc = sc.points_from(oC1, d_masked, n, PB, CB)) != MP_OK) return rc;
   if ((rc = sc.put_points(oTok, tokens, n)) != MP_OK) return rc;
-  if ((rc = sc.points_from(oAB, d_proofs, n, 128, kCpProofLen)) != MP_OK) return rc;
+  if ((rc = sc.points_from(oAB, d_proofs, n, 2 * PB, kCpProofLen)) != MP_OK) return rc;
   if ((rc = sc.put_points(oPk, pk, 1)) != MP_OK) return rc;
-  if ((rc = sc.scalars_from(0, d_proofs + 128, n, kCpProofLen)) != MP_OK) return rc;  // scalars [0, n): r
+  if ((rc = sc.scalars_from(0, d_proofs + 2 * PB, n, kCpProofLen)) != MP_OK) return rc;  // scalars [0, n): r
   if ((rc = sc.ingest()) != MP_OK) return rc;
   ShuffleState* S = ctx->shuffle;
   const Transcript seeded(kSeedReveal, strlen(kSeedReveal));
   std::vector<uint8_t> negc((size_t)n * 32), canon_ok((size_t)n);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {  // overlaps the uploads
     const uint8_t* p = proofs + kCpProofLen * i;
-    const fr c = cp_challenge(seeded, masked + 128 * i, S->enc_g, tokens + 64 * i, pk, p, p + 64);
+    const fr c = cp_challenge(seeded, masked + CB * i, S->enc_g, tokens + PB * i, pk, p, p + PB);
     fr_to_bytes(fr_neg(c), negc.data() + 32 * i);
-    canon_ok[i] = fr_bytes_canonical(p + 128);
+    canon_ok[i] = fr_bytes_canonical(p + 2 * PB);
   });
   if ((rc = sc.put_scalars(n, negc.data(), n)) != MP_OK) return rc;  // scalars [n, 2n): -c
   std::vector<JobKind> kinds(2);  // r c1 - c token - a  |  r g - c pk - b
@@ -559,17 +561,17 @@ int32_t sigma_key_ownership_prove_batch(mp_ctx* ctx, const uint8_t* pks, const u
   std::vector<JobKind> kinds(1);  // commit = omega g
   kinds[0].set(fFixSc0, 0);
   ShuffleState* S = ctx->shuffle;
-  uint8_t* res = pinned(S, n * 64);
+  uint8_t* res = pinned(S, n * PB);
   if (!res) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
   if ((rc = sc.run(kinds, n, res, nullptr)) != MP_OK) return rc;
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
-    const uint8_t* commit = res + 64 * i;
+    const uint8_t* commit = res + PB * i;
     const fr c = schnorr_challenge(infos ? infos + info_off[i] : nullptr, (size_t)(info_off[i + 1] - info_off[i]), S->enc_g,
-                                   pks + 64 * i, commit);
+                                   pks + PB * i, commit);
     const fr op = fr_sub(fr_from_bytes(omega + 32 * i), fr_mul(c, fr_from_bytes(sks + 32 * i)));
     uint8_t* p = out_proofs + kSchnorrProofLen * i;
-    memcpy(p, commit, 64);
-    fr_to_bytes(op, p + 64);
+    memcpy(p, commit, PB);
+    fr_to_bytes(op, p + PB);
   });
   return MP_OK;
 }
@@ -585,17 +587,17 @@ int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const 
   const uint8_t* d_proofs;
   if ((rc = sc.put_points(0, pks, n)) != MP_OK) return rc;
   if ((rc = sc.stage(0, proofs, n * kSchnorrProofLen, &d_proofs)) != MP_OK) return rc;
-  if ((rc = sc.points_from(n, d_proofs, n, 64, kSchnorrProofLen)) != MP_OK) return rc;
-  if ((rc = sc.scalars_from(0, d_proofs + 64, n, kSchnorrProofLen)) != MP_OK) return rc;
+  if ((rc = sc.points_from(n, d_proofs, n, PB, kSchnorrProofLen)) != MP_OK) return rc;
+  if ((rc = sc.scalars_from(0, d_proofs + PB, n, kSchnorrProofLen)) != MP_OK) return rc;
   if ((rc = sc.ingest()) != MP_OK) return rc;
   ShuffleState* S = ctx->shuffle;
   std::vector<uint8_t> cs((size_t)n * 32), canon_ok((size_t)n);
   for_items(n, host_thread_count(host_threads, n), [&](uint64_t i) {
     const uint8_t* p = proofs + kSchnorrProofLen * i;
     const fr c = schnorr_challenge(infos ? infos + info_off[i] : nullptr, (size_t)(info_off[i + 1] - info_off[i]), S->enc_g,
-                                   pks + 64 * i, p);
+                                   pks + PB * i, p);
     fr_to_bytes(c, cs.data() + 32 * i);
-    canon_ok[i] = fr_bytes_canonical(p + 64);
+    canon_ok[i] = fr_bytes_canonical(p + PB);
   });
   if ((rc = sc.put_scalars(n, cs.data(), n)) != MP_OK) return rc;
   std::vector<JobKind> kinds(1);  // opening g + c pk - commit == O

@@ -22,6 +22,8 @@ behavioural: prove -> verify == Ok, and a wrong statement fails with "Chaum-Pede
 Point encoding inside an absorb: ark-ec 0.3 `ToBytes` for affine points, 65 bytes (as in
 oracle/py/transcript.py); labels are raw ASCII.
 """
+import contextlib
+
 from . import stark
 from .stark import N as Q
 from .transcript import FiatShamirRng
@@ -37,6 +39,21 @@ ERR_SCHNORR = 6               # "Schnorr Identification"   (tests.rs:72-77)
 ERR_STRINGS = {ERR_CHAUM_PEDERSEN: "Chaum-Pedersen", ERR_SCHNORR: "Schnorr Identification"}
 
 P65 = stark.point_to_bytes65
+
+
+@contextlib.contextmanager
+def curve(name):
+    """`with curve("bls12_377"): ...` runs these protocols over BLS12-377 G1 (group, challenge field, byte widths), the
+    reference's second instantiation (examples/parameter_selection.rs:25-29).  Test infrastructure: not re-entrant."""
+    global stark, Q, P65
+    from . import bayer_groth as bg
+    saved = (stark, Q, P65)
+    with bg.curve(name) as grp:
+        stark, Q, P65 = grp, grp.N, grp.point_to_bytes65
+        try:
+            yield grp
+        finally:
+            stark, Q, P65 = saved
 
 
 # ----------------------------------------------------------------------------- the two protocols

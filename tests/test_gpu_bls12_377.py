@@ -514,6 +514,100 @@ def test_batch_split_over_two_worker_contexts_equals_single_calls(ctx377):
         assert ctx377.verify_shuffle(m, n, r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"], r["pk"], r["deck"], d, p) == 0
 
 
+SIG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_sigma_vectors.json")))
+
+
+@pytest.fixture
+def sctx377(ctx377):
+    fx = SHUF["shuffle"][0]
+    r = _raw(fx)    # any commitment key will do: the sigma protocols only use the ElGamal generator g
+    ctx377.set_params(fx["m"], fx["n"], bytes.fromhex(SIG["g"]), r["ck_g"], r["ck_h"], r["ghat"])
+    return ctx377
+
+
+def test_sigma_mask_remask_golden_and_negative_cases(sctx377):
+    """`mp377_mask_batch` ... `mp377_verify_remask_batch` (BarnettSmartProtocol::mask / verify_mask / remask /
+    verify_remask over BLS12-377; reference mod.rs:182-299): bytes against the oracle's golden vectors
+    (tests/golden/make_bls12_377_sigma_golden.py: identity card, zero and maximal scalars included), the reference's
+    negative cases (masking.rs:96-105, remasking.rs:103-112), a non-canonical response."""
+    from oracle.py import bls12_377 as bls
+    h = bytes.fromhex
+    cat = lambda key, rows: b"".join(h(r[key]) for r in rows)
+    le = lambda key, rows: b"".join(int(r[key], 16).to_bytes(32, "little") for r in rows)
+    shared = h(SIG["shared_key"])
+    M, R = SIG["mask"], SIG["remask"]
+    masked, proofs = sctx377.mask_batch(shared, cat("card", M), le("r", M), le("omega", M))
+    assert masked == cat("masked", M) and proofs == cat("proof", M)
+    assert sctx377.launches > 0
+    assert sctx377.verify_mask_batch(shared, cat("card", M), masked, proofs) == [0] * len(M)
+    bad = bytearray(proofs); bad[224 + 194] ^= 1          # response scalar of proof 1
+    assert sctx377.verify_mask_batch(shared, cat("card", M), masked, bytes(bad)) == [0, 5] + [0] * (len(M) - 2)
+    swapped = masked[192:384] + masked[:192] + masked[384:]
+    assert sctx377.verify_mask_batch(shared, cat("card", M), swapped, proofs)[:2] == [5, 5]
+    big = bytearray(proofs); big[192:224] = (bls.N + 5).to_bytes(32, "little")   # non-canonical response
+    assert sctx377.verify_mask_batch(shared, cat("card", M), masked, bytes(big))[0] == 5
+    out, rproofs = sctx377.remask_prove_batch(shared, cat("original", R), le("alpha", R), le("omega", R))
+    assert out == cat("remasked", R) and rproofs == cat("proof", R)
+    assert sctx377.verify_remask_batch(shared, cat("original", R), out, rproofs) == [0] * len(R)
+    assert sctx377.verify_remask_batch(shared, cat("original", R), out[192:] + out[:192], rproofs).count(5) >= len(R) - 1
+
+
+def test_sigma_reveal_and_key_ownership_golden_and_negative_cases(sctx377, pkg):
+    """compute_reveal_token / verify_reveal / prove_key_ownership / verify_key_ownership over BLS12-377 (reference
+    mod.rs:132-165, 301-354; negative cases reveal.rs:73-82, tests.rs:72-77), and the G1 membership test the
+    verifiers apply to what they are handed."""
+    h = bytes.fromhex
+    cat = lambda key, rows: b"".join(h(r[key]) for r in rows)
+    le = lambda key, rows: b"".join(int(r[key], 16).to_bytes(32, "little") for r in rows)
+    V, K = SIG["reveal"], SIG["key_ownership"]
+    for fx in V:
+        sk, om = int(fx["sk"], 16).to_bytes(32, "little"), int(fx["omega"], 16).to_bytes(32, "little")
+        tok, pf = sctx377.reveal_batch(sk, h(fx["pk"]), h(fx["masked"]), om)
+        assert tok == h(fx["token"]) and pf == h(fx["proof"])
+        assert sctx377.verify_reveal_batch(h(fx["pk"]), tok, h(fx["masked"]), pf) == [0]
+        assert sctx377.verify_reveal_batch(h(fx["pk"]), h(V[0]["pk"]), h(fx["masked"]), pf) == [5]
+    infos = [h(r["info"]) for r in K]
+    kp = sctx377.key_ownership_prove_batch(cat("pk", K), le("sk", K), infos, le("omega", K))
+    assert kp == cat("proof", K)
+    assert sctx377.key_ownership_verify_batch(cat("pk", K), infos, kp) == [0] * len(K)
+    assert sctx377.key_ownership_verify_batch(cat("pk", K), infos[::-1], kp) == [6, 0, 6]
+    # a token that is on the curve but outside G1 is refused before any verification, like upstream's deserialiser
+    _, T = _torsion_point()
+    fx = V[0]
+    tok_bad = pb(bls.add(bls.point_from_bytes(h(fx["token"])), T))
+    with pytest.raises(pkg.MpError) as e:
+        sctx377.verify_reveal_batch(h(fx["pk"]), tok_bad, h(fx["masked"]), h(fx["proof"]))
+    assert e.value.code == -6
+    kp_bad = pb(T) + kp[96:]        # commitment of the first Schnorr proof replaced by a torsion point
+    with pytest.raises(pkg.MpError) as e:
+        sctx377.key_ownership_verify_batch(cat("pk", K), infos, kp_bad)
+    assert e.value.code == -6
+
+
+def test_sigma_batch_round_trip(sctx377):
+    """A batch of 300 cards (the reference benchmark's deck size) masked, remasked and revealed; every proof verifies,
+    one tampered item per call is the only one refused."""
+    import numpy as np
+    rng = np.random.default_rng(377)
+    def scal(k):
+        a = rng.integers(0, 256, size=(k, 32), dtype=np.uint8); a[:, 31] &= 0x0f
+        return a.tobytes()
+    n = 300
+    g = bytes.fromhex(SIG["g"])
+    sk = scal(1)
+    pk = sctx377.dbg_scalar_mul(g, sk)
+    cards = sctx377.dbg_scalar_mul(g * n, scal(n))
+    masked, p1 = sctx377.mask_batch(pk, cards, scal(n), scal(n))
+    assert sctx377.verify_mask_batch(pk, cards, masked, p1) == [0] * n
+    out, p2 = sctx377.remask_prove_batch(pk, masked, scal(n), scal(n))
+    assert sctx377.verify_remask_batch(pk, masked, out, p2) == [0] * n
+    tok, p3 = sctx377.reveal_batch(sk, pk, out, scal(n))
+    assert sctx377.verify_reveal_batch(pk, tok, out, p3) == [0] * n
+    bad = bytearray(p3); bad[224 * 7 + 200] ^= 1
+    st = sctx377.verify_reveal_batch(pk, tok, out, bytes(bad))
+    assert st[7] == 5 and st.count(0) == n - 1
+
+
 def test_prover_usage_errors(ctx377, pkg):
     fresh = pkg.bls12_377.Context(0)
     buf = bytes(96)

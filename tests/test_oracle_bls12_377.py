@@ -206,3 +206,39 @@ def test_g1_membership_test_by_endomorphism():
         if T is not None:
             assert smul(T, bls.COFACTOR) is None and not member(T) and not member(bls.add(bls.G, T))
             found += 1
+
+
+def test_sigma_golden_vectors_are_the_oracles():
+    """tests/golden/bls12_377_sigma_vectors.json (what the GPU is compared with) re-derived from oracle/py/sigma.py over
+    this curve: every mask / reveal / key-ownership proof, verified by the oracle, and the reference's negative cases
+    (masking.rs:96-105, reveal.rs:73-82, tests.rs:72-77)."""
+    import json, os
+    from oracle.py import sigma
+    from _util_bls12_377 import pb
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_sigma_vectors.json")))
+    hx = bytes.fromhex
+    with sigma.curve("bls12_377"):
+        g, shared = bls.point_from_bytes(hx(gold["g"])), bls.point_from_bytes(hx(gold["shared_key"]))
+        assert g == bls.G
+        for fx in gold["mask"]:
+            card = bls.point_from_bytes(hx(fx["card"]))
+            masked, proof = sigma.mask(g, shared, card, int(fx["r"], 16), int(fx["omega"], 16))
+            assert (pb(masked[0]) + pb(masked[1])).hex() == fx["masked"] and sigma.cp_proof_bytes(proof).hex() == fx["proof"]
+            assert sigma.verify_mask(g, shared, card, masked, proof) == sigma.OK
+            assert sigma.verify_mask(g, shared, bls.add(card, g), masked, proof) == sigma.ERR_CHAUM_PEDERSEN
+        for fx in gold["reveal"]:
+            masked = (bls.point_from_bytes(hx(fx["masked"])[:96]), bls.point_from_bytes(hx(fx["masked"])[96:]))
+            pk = bls.point_from_bytes(hx(fx["pk"]))
+            token, proof = sigma.compute_reveal_token(g, int(fx["sk"], 16), pk, masked, int(fx["omega"], 16))
+            assert pb(token).hex() == fx["token"] and sigma.cp_proof_bytes(proof).hex() == fx["proof"]
+            assert sigma.verify_reveal(g, pk, token, masked, proof) == sigma.OK
+            assert sigma.verify_reveal(g, pk, bls.add(token, g), masked, proof) == sigma.ERR_CHAUM_PEDERSEN
+        for fx in gold["key_ownership"]:
+            pk = bls.point_from_bytes(hx(fx["pk"]))
+            proof = sigma.prove_key_ownership(g, pk, int(fx["sk"], 16), hx(fx["info"]), int(fx["omega"], 16))
+            assert sigma.schnorr_proof_bytes(proof).hex() == fx["proof"]
+            assert sigma.verify_key_ownership(g, pk, hx(fx["info"]), proof) == sigma.OK
+            assert sigma.verify_key_ownership(g, pk, hx(fx["info"]) + b"x", proof) == sigma.ERR_SCHNORR
+    # the context manager restored the Stark curve
+    from oracle.py import stark
+    assert sigma.Q == stark.N
