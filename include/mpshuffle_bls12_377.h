@@ -139,19 +139,27 @@ int32_t mp377_shuffle_verify(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t
                              const uint8_t* pk /* 96 */, const uint8_t* deck /* m*n*192 */,
                              const uint8_t* shuffled_deck /* m*n*192 */, const uint8_t* proof);
 
-/* Wire format, serialising half (ark-serialize 0.3 compressed encodings, as mp_points_compress / mp_deck_serialize /
- * mp_proof_serialize of mpshuffle.h): compressed point = x (48 bytes LE) with flags in the top bits of the last byte
- * (bit 7: y is the larger of (y, -y); bit 6: infinity); Vec<MaskedCard> = u64 LE length | c1 | c2 per card; proof =
- * the REPOSITORY-PRIVATE container of mpshuffle.h (flat layout, every point compressed, no Vec length prefixes),
- * (11m + 8) * 48 + (5n + 9) * 32 bytes -- close to, but not, what the reference's benchmark prints with
- * `serialized_size()` (examples/parameter_selection.rs:93-96), which adds 8 bytes per Vec field of the upstream
- * proof struct.  Host byte handling, no context.  Deserialising is not
- * built for this curve yet. */
+/* Wire format (ark-serialize 0.3 compressed encodings, as the wire-format section of mpshuffle.h): compressed point =
+ * x (48 bytes LE) with flags in the top bits of the last byte (bit 7: y is the larger of (y, -y); bit 6: infinity);
+ * Vec<MaskedCard> = u64 LE length | c1 | c2 per card; proof = the REPOSITORY-PRIVATE container of mpshuffle.h (flat
+ * layout, every point compressed, no Vec length prefixes), (11m + 8) * 48 + (5n + 9) * 32 bytes -- close to, but not,
+ * what the reference's benchmark prints with `serialized_size()` (examples/parameter_selection.rs:93-96), which adds
+ * 8 bytes per Vec field of the upstream proof struct.  Serialising is host byte handling and needs no context.
+ * DEserialising runs on the GPU: one square root in F_q per point (q - 1 = 2^46 * t; windowed Tonelli-Shanks), then
+ * the G1 membership test, as ark-serialize's CanonicalDeserialize does for this curve.  mp377_points_decompress
+ * fills statuses[i] (may be NULL) with 0 ok, 1 malformed encoding (x >= q, stray flag bits), 2 x not on the curve,
+ * 3 on the curve but outside G1, writes rejected items as 96 zero bytes and returns MP_ERR_NOT_ON_CURVE /
+ * MP_ERR_NOT_IN_SUBGROUP; mp377_proof_deserialize also rejects scalars >= r (MP_ERR_NOT_CANONICAL). */
 int32_t mp377_points_compress(const uint8_t* points /* n*96 */, uint64_t n, uint8_t* out /* n*48 */);
 uint64_t mp377_deck_serialized_len(uint64_t n_cards);
 int32_t mp377_deck_serialize(const uint8_t* deck /* n_cards*192 */, uint64_t n_cards, uint8_t* out);
 uint64_t mp377_proof_serialized_len(int32_t m, int32_t n);
 int32_t mp377_proof_serialize(int32_t m, int32_t n, const uint8_t* proof, uint8_t* out);
+int32_t mp377_points_decompress(mp377_ctx* ctx, const uint8_t* in /* n*48 */, uint64_t n, uint8_t* out /* n*96 */,
+                                int32_t* statuses /* n or NULL */);
+/* *n_cards: in = capacity of out_deck in cards, out = cards in the buffer */
+int32_t mp377_deck_deserialize(mp377_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards);
+int32_t mp377_proof_deserialize(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof);
 
 /* Window-range split of ONE MSM across GPUs: rank r computes the windows
  * [w_begin, w_begin + w_count) of the mp377_msm_num_windows(window_bits) windows end to end and returns

@@ -32,6 +32,9 @@ SIGNATURES = {
     "mp377_deck_serialize": (_i32, [_cp, _u64, _cp]),
     "mp377_proof_serialized_len": (_u64, [_i32, _i32]),
     "mp377_proof_serialize": (_i32, [_i32, _i32, _cp, _cp]),
+    "mp377_points_decompress": (_i32, [_vp, _cp, _u64, _cp, ctypes.POINTER(_i32)]),
+    "mp377_deck_deserialize": (_i32, [_vp, _cp, _u64, _cp, _pu64]),
+    "mp377_proof_deserialize": (_i32, [_vp, _i32, _i32, _cp, _cp]),
     "mp377_proof_len": (_u64, [_i32, _i32]),
     "mp377_ctx_set_params": (_i32, [_vp, _i32, _i32, _cp, _cp, _cp, _cp]),
     "mp377_prover_randomness_len": (_u64, [_i32, _i32]),
@@ -218,6 +221,32 @@ class Context:
         st = (_i32 * max(n, 1))()
         rc = lib.mp377_subgroup_check(self.h, points, n, st)
         return rc, list(st)[:n]
+
+    # --- wire format, deserialising half (square roots + G1 membership on the GPU)
+    def points_decompress(self, data: bytes, want_statuses=False):
+        """n*48 compressed bytes -> n*96 bytes; raises MpError if any item is rejected unless want_statuses, in which
+        case -> (points, statuses: 0 ok, 1 malformed, 2 not on the curve, 3 outside G1, return code), as `_lib.Context`"""
+        n = len(data) // FQ_BYTES
+        assert len(data) == FQ_BYTES * n
+        out = ctypes.create_string_buffer(POINT_BYTES * max(n, 1))
+        st = (_i32 * max(n, 1))()
+        rc = lib.mp377_points_decompress(self.h, data, n, out, st)
+        if want_statuses:
+            return out.raw[:POINT_BYTES * n], list(st)[:n], rc
+        _check(self.h, rc)
+        return out.raw[:POINT_BYTES * n]
+
+    def deck_deserialize(self, data: bytes) -> bytes:
+        n = ctypes.c_uint64((len(data) - 8) // (2 * FQ_BYTES) if len(data) >= 8 else 0)
+        out = ctypes.create_string_buffer(2 * POINT_BYTES * max(n.value, 1))
+        _check(self.h, lib.mp377_deck_deserialize(self.h, data, len(data), out, ctypes.byref(n)))
+        return out.raw[:2 * POINT_BYTES * n.value]
+
+    def proof_deserialize(self, m: int, n: int, data: bytes) -> bytes:
+        assert len(data) == lib.mp377_proof_serialized_len(m, n)
+        out = ctypes.create_string_buffer(lib.mp377_proof_len(m, n))
+        _check(self.h, lib.mp377_proof_deserialize(self.h, m, n, data, out))
+        return out.raw
 
     # --- batched sigma protocols either side of the shuffle (reference mod.rs:132-354), 96-byte points:
     #     Chaum-Pedersen proof = a | b | r = 224 bytes, Schnorr proof = commit | opening = 128 bytes

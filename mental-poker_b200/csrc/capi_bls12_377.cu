@@ -559,6 +559,65 @@ extern "C" int32_t mp377_proof_serialize(int32_t m, int32_t n, const uint8_t* pr
   return MP_OK;
 }
 
+// Deserialising half (wire.cu compiled for this curve: one square root in F_q per point, two-adicity 46, then the G1
+// membership test ark-serialize applies to every deserialised point).  statuses: 0 ok, 1 malformed encoding, 2 x is
+// not the abscissa of a curve point, 3 on the curve but outside G1.
+static int32_t wire_status(mp377_ctx* ctx, int32_t st) {
+  if (!ctx->prover) return st;
+  if (st < 0) ctx->err = ctx->prover->err;
+  ctx->launches = ctx->prover->launches;
+  return st;
+}
+static int32_t need_wire_ctx(mp377_ctx* ctx) {
+  if (!ctx) return MP_ERR_INVALID_ARG;
+  if (!ctx->prover && ctx_create(&ctx->prover, ctx->device) != MP_OK) return ctx->fail(MP_ERR_CUDA, "cannot create the protocol context");
+  return MP_OK;
+}
+extern "C" int32_t mp377_points_decompress(mp377_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, int32_t* statuses) {
+  int32_t rc = need_wire_ctx(ctx);
+  if (rc != MP_OK) return rc;
+  rc = wire_status(ctx, wire_points_decompress(ctx->prover, in, n, out, statuses));
+  if (rc != MP_OK || n == 0) return rc;
+  const int launches = ctx->launches;
+  std::vector<int32_t> sg(n);
+  rc = mp377_subgroup_check(ctx, out, n, sg.data());
+  ctx->launches += launches;
+  if (rc == MP_OK) return MP_OK;
+  for (uint64_t i = 0; i < n; i++)
+    if (sg[i]) {
+      if (statuses) statuses[i] = 3;
+      memset(out + kPt * i, 0, kPt);
+    }
+  return rc;
+}
+extern "C" int32_t mp377_deck_deserialize(mp377_ctx* ctx, const uint8_t* in, uint64_t in_len, uint8_t* out_deck, uint64_t* n_cards) {
+  int32_t rc = need_wire_ctx(ctx);
+  if (rc != MP_OK) return rc;
+  rc = wire_status(ctx, wire_deck_deserialize(ctx->prover, in, in_len, out_deck, n_cards));
+  if (rc != MP_OK || *n_cards == 0) return rc;
+  const int launches = ctx->launches;
+  rc = mp377_subgroup_check(ctx, out_deck, 2 * *n_cards, nullptr);
+  ctx->launches += launches;
+  return rc;
+}
+extern "C" int32_t mp377_proof_deserialize(mp377_ctx* ctx, int32_t m, int32_t n, const uint8_t* in, uint8_t* out_proof) {
+  int32_t rc = need_wire_ctx(ctx);
+  if (rc != MP_OK) return rc;
+  rc = wire_status(ctx, wire_proof_deserialize(ctx->prover, m, n, in, out_proof));
+  if (rc != MP_OK) return rc;
+  const int launches = ctx->launches;
+  std::vector<uint8_t> pts;
+  const uint8_t* p = out_proof;
+  for (const WireRun& r : wire_proof_runs(m, n)) {
+    const size_t len = (r.points ? kPt : 32) * r.count;
+    if (r.points) pts.insert(pts.end(), p, p + len);
+    p += len;
+  }
+  rc = mp377_subgroup_check(ctx, pts.data(), pts.size() / kPt, nullptr);
+  ctx->launches += launches;
+  return rc;
+}
+
 // Window-range split of one MSM across GPUs: the partial
 //   sum_{w in [w_begin, w_begin + w_count)} 2^(c (w - w_begin)) * (window sum w),
 // so that  MSM = sum over ranks of 2^(c * w_begin_r) * partial_r  (see mental-poker_b200/dist.py).

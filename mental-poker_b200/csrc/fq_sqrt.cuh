@@ -8,7 +8,39 @@
 
 namespace mp {
 
+#ifdef MP_CURVE_BLS12_377
+// Second curve: q - 1 = 2^46 * t with t odd (331 bits).  The same windowed method with 2-bit windows (46 = 23 * 2):
+// 23 digits, tables of a few hundred bytes; the cost is the exponentiation a^((t-1)/2) (330 squarings).
+static constexpr int kTwoAdicity = 46;
+static constexpr int kSqrtWin = 2;
+// 5^t mod q (5 is the smallest non-residue): a primitive 2^46-th root of unity, Montgomery form (R = 2^384)
+MP_HD fq fq_sqrt_root() {
+  const uint32_t w[kFqLimbs] = {0x8bb191f2u, 0x68f876aau, 0xa6722e51u, 0x254e4780u, 0x1f8a0eafu, 0xa818ea19u,
+                                0x1d8d5057u, 0x2c1a6dd3u, 0xa0df931bu, 0xcce5a0cbu, 0xc8cf8495u, 0x00ba7904u};
+  fq r;
+  for (int i = 0; i < kFqLimbs; i++) r.v[i] = w[i];
+  return r;
+}
+// (q - 1) / 2, canonical: y is "the larger of (y, -y)" iff y > this
+MP_HD uint32_t fq_half_limb(int i) {
+  const uint32_t w[kFqLimbs] = {0x00000000u, 0x42846000u, 0x18000000u, 0x0b85aea2u, 0xdd04a400u, 0x8f79b117u,
+                                0x807a89c7u, 0x8d116cf9u, 0x3650a49du, 0x631d82e0u, 0x0be28875u, 0x00d71d23u};
+  return w[i];
+}
+// a^((t - 1) / 2): plain square-and-multiply over the 330-bit exponent (same control flow for every input)
+MP_HD fq fq_sqrt_w(const fq& a) {
+  const uint32_t e[11] = {0x00010a11u, 0xba886000u, 0x90002e16u, 0xc45f7412u, 0x271e3de6u, 0xb3e601eau,
+                          0x92763445u, 0x0b80d942u, 0x21d58c76u, 0x748c2f8au, 0x0000035cu};
+  fq w = a;                                   // bit 329 is set
+  for (int i = 328; i >= 0; i--) {
+    w = fq_sqr(w);
+    if ((e[i >> 5] >> (i & 31)) & 1u) w = fq_mul(w, a);
+  }
+  return w;
+}
+#else
 static constexpr int kTwoAdicity = 192;
+static constexpr int kSqrtWin = 8;
 
 // 3^t mod p, t = 2^59 + 17: a primitive 2^192-th root of unity, Montgomery form
 MP_HD fq fq_sqrt_root() {
@@ -17,6 +49,19 @@ MP_HD fq fq_sqrt_root() {
   r.v[4] = 0x60505574u; r.v[5] = 0x0a35c5beu; r.v[6] = 0xc47afc26u; r.v[7] = 0x07222e32u;
   return r;
 }
+// (p - 1) / 2 = 2^250 + 17 * 2^191, canonical: y is "the larger of (y, -y)" iff y > this
+MP_HD uint32_t fq_half_limb(int i) {
+  const uint32_t w[kFqLimbs] = {0, 0, 0, 0, 0, 0x80000000u, 0x00000008u, 0x04000000u};
+  return w[i];
+}
+// a^((t - 1) / 2) = a^(2^58 + 8)
+MP_HD fq fq_sqrt_w(const fq& a) {
+  fq a8 = fq_sqr(fq_sqr(fq_sqr(a)));
+  fq w = a8;
+  for (int i = 3; i < 58; i++) w = fq_sqr(w);
+  return fq_mul(w, a8);
+}
+#endif
 // (the curve coefficient b * R mod p is fq_curve_b() of fq.cuh)
 
 // T[i] = root^(2^i), fully reduced (191 dependent squarings, once per context)
@@ -34,11 +79,7 @@ MP_HD bool fq_is_one(const fq& a) { return fq_eq_raw(fq_reduce_full(a), fq_one()
 MP_HD fq fq_sqrt(const fq& a, const fq* T, bool* ok) {
   *ok = true;
   if (fq_is_zero_raw(fq_reduce_full(a))) return fq_zero();
-  // w = a^(2^58 + 8)
-  fq a8 = fq_sqr(fq_sqr(fq_sqr(a)));
-  fq w = a8;
-  for (int i = 3; i < 58; i++) w = fq_sqr(w);
-  w = fq_mul(w, a8);
+  const fq w = fq_sqrt_w(a);
   fq x = fq_mul(a, w);
   fq b = fq_mul(x, w);
   int v = kTwoAdicity;
@@ -51,7 +92,7 @@ MP_HD fq fq_sqrt(const fq& a, const fq* T, bool* ok) {
     } while (k < v && !fq_is_one(t2));
     if (k >= v) { *ok = false; return fq_zero(); }
     x = fq_mul(x, T[kTwoAdicity - 1 - k]);
-    b = fq_mul(b, T[kTwoAdicity - k]);   // T[192 - k] = T[191 - k]^2; k >= 1 so the index is <= 191
+    b = fq_mul(b, T[kTwoAdicity - k]);   // T[s - k] = T[s - 1 - k]^2; k >= 1 so the index is <= s - 1
     v = k;
   }
   return x;
@@ -70,7 +111,8 @@ MP_HD fq fq_sqrt(const fq& a, const fq* T, bool* ok) {
 // ~4 600 data-dependent squarings for the loop above: on a GPU the lanes of a warp stay together.
 // The result is checked (x^2 == a), which is also how non-residues are recognised.
 // ------------------------------------------------------------------------------------------
-static constexpr int kSqrtWin = 8, kSqrtDigits = kTwoAdicity / kSqrtWin, kSqrtRadix = 1 << kSqrtWin;
+static constexpr int kSqrtDigits = kTwoAdicity / kSqrtWin, kSqrtRadix = 1 << kSqrtWin;
+static_assert(kSqrtDigits * kSqrtWin == kTwoAdicity, "window width must divide the two-adicity");
 struct SqrtTables {
   const fq* U;         // [(d - 1) * 256 + v], d = 1 .. 23
   const fq* V;         // [i * 256 + v], i = 0 .. 23   (i = 0: even v only)
@@ -122,10 +164,7 @@ MP_HD fq fq_sqrt_win(const fq& a, const SqrtTables& tb, bool* ok) {
   *ok = true;
   const fq ar = fq_reduce_full(a);
   if (fq_is_zero_raw(ar)) return fq_zero();
-  fq a8 = fq_sqr(fq_sqr(fq_sqr(ar)));
-  fq w = a8;
-  for (int i = 3; i < 58; i++) w = fq_sqr(w);
-  w = fq_mul(w, a8);
+  const fq w = fq_sqrt_w(ar);
   fq x = fq_mul(ar, w);
   fq bj[kSqrtDigits];
   bj[0] = fq_mul(x, w);

@@ -32,21 +32,25 @@ __global__ void __launch_bounds__(128) k_decompress(const uint32_t* __restrict__
                                                     uint32_t* __restrict__ out, uint8_t* __restrict__ status, int* __restrict__ bad) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t w[8];
+  constexpr int L = kFqLimbs;   // 8 (Stark) / 12 (BLS12-377): x is L words, flags in the top two bits of the last one
+  uint32_t w[L];
   {
-    const uint4* p = reinterpret_cast<const uint4*>(in + i * 8);
-    uint4 lo = __ldg(p), hi = __ldg(p + 1);
-    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
-  }
-  const uint32_t flags = w[7] >> 30;  // bit 1 = larger, bit 0 = infinity
-  w[7] &= 0x3fffffffu;
-  uint32_t res[16];
+    const uint4* p = reinterpret_cast<const uint4*>(in + i * L);
 #pragma unroll
-  for (int k = 0; k < 16; k++) res[k] = 0;
+    for (int q = 0; q < L / 4; q++) {
+      const uint4 v = __ldg(p + q);
+      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+  }
+  const uint32_t flags = w[L - 1] >> 30;  // bit 1 = larger, bit 0 = infinity
+  w[L - 1] &= 0x3fffffffu;
+  uint32_t res[2 * L];
+#pragma unroll
+  for (int k = 0; k < 2 * L; k++) res[k] = 0;
   uint8_t st = 0;
   fq xc;
 #pragma unroll
-  for (int k = 0; k < 8; k++) xc.v[k] = w[k];
+  for (int k = 0; k < L; k++) xc.v[k] = w[k];
   if (flags & 1u) {
     if (!fq_is_zero_raw(xc) || (flags & 2u)) st = 1;
   } else {
@@ -56,7 +60,11 @@ __global__ void __launch_bounds__(128) k_decompress(const uint32_t* __restrict__
       st = 1;  // x >= p
     } else {
       const fq xm = fq_reduce_full(fq_to_mont(xc));
-      const fq rhs = fq_add(fq_add(fq_mul(fq_sqr(xm), xm), xm), fq_curve_b());  // [2] + [1] + [1]
+#ifdef MP_CURVE_BLS12_377
+      const fq rhs = fq_add(fq_mul(fq_sqr(xm), xm), fq_curve_b());               // y^2 = x^3 + 1
+#else
+      const fq rhs = fq_add(fq_add(fq_mul(fq_sqr(xm), xm), xm), fq_curve_b());  // y^2 = x^3 + x + b   [2] + [1] + [1]
+#endif
       bool ok;
       const fq y = fq_sqrt_win(fq_reduce_weak(rhs), tb, &ok);
       if (!ok) {
@@ -65,8 +73,8 @@ __global__ void __launch_bounds__(128) k_decompress(const uint32_t* __restrict__
         fq yc = fq_from_mont(y);  // canonical
         // larger of (y, p - y)  <=>  y > (p - 1) / 2
         fq half;
-        half.v[0] = 0; half.v[1] = 0; half.v[2] = 0; half.v[3] = 0; half.v[4] = 0;
-        half.v[5] = 0x80000000u; half.v[6] = 0x00000008u; half.v[7] = 0x04000000u;
+#pragma unroll
+        for (int k = 0; k < L; k++) half.v[k] = fq_half_limb(k);
         uint32_t le;  // borrow of half - y: set iff y > half
         fq_sub_raw(half, yc, &le);
         if ((le != 0) != ((flags & 2u) != 0)) {
@@ -74,15 +82,15 @@ __global__ void __launch_bounds__(128) k_decompress(const uint32_t* __restrict__
           yc = fq_is_zero_raw(yc) ? yc : fq_sub_raw(fq_kp(1), yc, &bw);
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) { res[k] = w[k]; res[8 + k] = yc.v[k]; }
+        for (int k = 0; k < L; k++) { res[k] = w[k]; res[L + k] = yc.v[k]; }
       }
     }
   }
   if (st) atomicExch(bad, 1);
   if (status) status[i] = st;
-  uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+  uint4* o = reinterpret_cast<uint4*>(out + i * 2 * L);
 #pragma unroll
-  for (int q = 0; q < 4; q++) o[q] = make_uint4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+  for (int q = 0; q < 2 * L / 4; q++) o[q] = make_uint4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -90,7 +98,7 @@ __global__ void __launch_bounds__(128) k_decompress(const uint32_t* __restrict__
 // ------------------------------------------------------------------------------------------
 enum WireSlot { sWireIn = 200, sWireOut, sWireStatus, sWireTable };
 
-// device-resident decompression: d_in n*32 bytes -> d_out n*64 bytes (+ per-item status), asynchronous
+// device-resident decompression: d_in n*kWireFe bytes -> d_out n*kWirePt bytes (+ per-item status), asynchronous
 static int32_t decompress_device(mp_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint8_t* d_status, int* d_bad) {
   // one slot: T | Tinv | U | V | lut
   const size_t fq_count = 2 * (size_t)kTwoAdicity + kSqrtUCount + kSqrtVCount;
@@ -119,16 +127,16 @@ int32_t wire_points_decompress(mp_ctx* ctx, const uint8_t* in, uint64_t n, uint8
   cudaSetDevice(ctx->device);
   ctx->launches = 0;
   if (n == 0) return MP_OK;
-  uint8_t* d_in = (uint8_t*)ctx->scratch(sWireIn, n * 32);
-  uint8_t* d_out = (uint8_t*)ctx->scratch(sWireOut, n * 64);
+  uint8_t* d_in = (uint8_t*)ctx->scratch(sWireIn, n * kWireFe);
+  uint8_t* d_out = (uint8_t*)ctx->scratch(sWireOut, n * kWirePt);
   uint8_t* d_status = (uint8_t*)ctx->scratch(sWireStatus, n + 64);
   int* d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
   NEED(d_in); NEED(d_out); NEED(d_status); NEED(d_bad);
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  CK(cudaMemcpyAsync(d_in, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in, in, n * kWireFe, cudaMemcpyHostToDevice, ctx->stream));
   int32_t rc = decompress_device(ctx, d_in, n, d_out, d_status, d_bad);
   if (rc != MP_OK) return rc;
-  CK(cudaMemcpyAsync(out, d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out, d_out, n * kWirePt, cudaMemcpyDeviceToHost, ctx->stream));
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<uint8_t> st;
@@ -139,7 +147,7 @@ int32_t wire_points_decompress(mp_ctx* ctx, const uint8_t* in, uint64_t n, uint8
   CK(stream_wait(ctx, ctx->stream));
   if (statuses)
     for (uint64_t i = 0; i < n; i++) statuses[i] = st[i];
-  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a compressed point is malformed or not on the Stark curve");
+  if (bad) return ctx->fail(MP_ERR_NOT_ON_CURVE, "a compressed point is malformed or not on the curve");
   return MP_OK;
 }
 
@@ -159,13 +167,14 @@ int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t*
   if (!ctx || !in || !out_proof || m < 1 || n < 1) return MP_ERR_INVALID_ARG;
   // gather the compressed points, decompress them in one launch, scatter into the flat layout
   const size_t npts = 11 * (size_t)m + 8;
-  std::vector<uint8_t> comp(npts * 32), pts(npts * 64);
+  std::vector<uint8_t> comp(npts * kWireFe), pts(npts * kWirePt);
   {
     const uint8_t* p = in;
     uint8_t* c = comp.data();
     for (const WireRun& r : wire_proof_runs(m, n)) {
-      if (r.points) { memcpy(c, p, 32 * r.count); c += 32 * r.count; }
-      p += 32 * r.count;
+      const size_t len = (r.points ? kWireFe : 32) * r.count;
+      if (r.points) { memcpy(c, p, len); c += len; }
+      p += len;
     }
   }
   int32_t rc = wire_points_decompress(ctx, comp.data(), npts, pts.data(), nullptr);
@@ -173,9 +182,9 @@ int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t*
   const uint8_t *p = in, *q = pts.data();
   for (const WireRun& r : wire_proof_runs(m, n)) {
     if (r.points) {
-      memcpy(out_proof, q, 64 * r.count);
-      q += 64 * r.count;
-      out_proof += 64 * r.count;
+      memcpy(out_proof, q, kWirePt * r.count);
+      q += kWirePt * r.count;
+      out_proof += kWirePt * r.count;
     } else {
       // field elements: ark-serialize rejects non-canonical encodings (value >= the group order) at deserialisation
       for (size_t k = 0; k < r.count; k++)
@@ -183,7 +192,7 @@ int32_t wire_proof_deserialize(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t*
       memcpy(out_proof, p, 32 * r.count);
       out_proof += 32 * r.count;
     }
-    p += 32 * r.count;
+    p += (r.points ? kWireFe : 32) * r.count;
   }
   return MP_OK;
 }

@@ -101,3 +101,71 @@ def proof_serialize_generic(flat_proof, m, n, curve):
             pos += 32 * count
     assert pos == len(flat_proof)
     return out
+
+
+def sqrt_mod(a, p):
+    """A square root of a mod the odd prime p (Tonelli-Shanks), or None for a non-residue."""
+    a %= p
+    if a == 0:
+        return 0
+    if pow(a, (p - 1) // 2, p) != 1:
+        return None
+    q, s = p - 1, 0
+    while q % 2 == 0:
+        q //= 2
+        s += 1
+    z = 2
+    while pow(z, (p - 1) // 2, p) != p - 1:
+        z += 1
+    m, c, t, r = s, pow(z, q, p), pow(a, q, p), pow(a, (q + 1) // 2, p)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % p
+            i += 1
+        b = pow(c, 1 << (m - i - 1), p)
+        m, c = i, b * b % p
+        t, r = t * c % p, r * b % p
+    return r
+
+
+def decompress_generic(b, curve, subgroup_check=True):
+    """Inverse of compress_generic, validating as ark-serialize 0.3 does: canonical x, no stray flag bits, x on the curve,
+    and (for a curve with a cofactor) the point in the order-N subgroup.  Raises ValueError otherwise."""
+    nb = curve.fe_bytes
+    assert len(b) == nb
+    flags = b[nb - 1] & 0xC0
+    x = int.from_bytes(b[:nb - 1] + bytes([b[nb - 1] & 0x3F]), "little")
+    if flags & FLAG_INF:
+        if x != 0 or flags & FLAG_LARGER:
+            raise ValueError("bad infinity encoding")
+        return None
+    if x >= curve.P:
+        raise ValueError("x not canonical")
+    y = sqrt_mod(x * x * x + curve.A * x + curve.B, curve.P)
+    if y is None:
+        raise ValueError("x is not the abscissa of a curve point")
+    if (y > curve.P - y) != bool(flags & FLAG_LARGER):
+        y = (curve.P - y) % curve.P
+    if subgroup_check and not in_subgroup((x, y), curve):
+        raise ValueError("point outside the prime-order subgroup")
+    return (x, y)
+
+
+def in_subgroup(pt, curve):
+    """N * pt == O by plain double-and-add (`curve.mul` reduces its scalar mod N, so it cannot be used for this)."""
+    acc = None
+    for bit in bin(curve.N)[2:]:
+        acc = curve.add(acc, acc)
+        if bit == "1":
+            acc = curve.add(acc, pt)
+    return acc is None
+
+
+def deck_deserialize_generic(b, curve):
+    nb = curve.fe_bytes
+    n = int.from_bytes(b[:8], "little")
+    if len(b) != 8 + 2 * nb * n:
+        raise ValueError("length prefix does not match the buffer")
+    at = lambda k: decompress_generic(b[8 + nb * k:8 + nb * (k + 1)], curve)
+    return [(at(2 * i), at(2 * i + 1)) for i in range(n)]

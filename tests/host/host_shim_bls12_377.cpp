@@ -147,3 +147,53 @@ void h_schnorr_challenge(const uint8_t* info, uint64_t info_len, const uint8_t* 
 int h_fr_bytes_canonical(const uint8_t* b) { return fr_bytes_canonical(b); }
 int h_sigma_proof_lens(int which) { return which == 0 ? (int)kCpProofLen : (int)kSchnorrProofLen; }
 }
+
+// ---- wire format over this curve: square roots in F_q (csrc/fq_sqrt.cuh: two-adicity 46, 2-bit windows)
+#include "../../mental-poker_b200/csrc/fq_sqrt.cuh"
+extern "C" {
+// canonical a -> canonical root; returns 1 if a is a square, 0 otherwise
+int h_fq_sqrt(const uint32_t* a, uint32_t* out) {
+  static fq T[kTwoAdicity];
+  static bool ready = false;
+  if (!ready) { fq_sqrt_table(T); ready = true; }
+  fq x; memcpy(x.v, a, 48);
+  bool ok;
+  fq r = fq_sqrt(fq_reduce_full(fq_to_mont(x)), T, &ok);
+  fq c = fq_from_mont(r);
+  memcpy(out, c.v, 48);
+  return ok ? 1 : 0;
+}
+// the windowed form the GPU runs; *distinct_keys = number of distinct lut keys (must be kSqrtRadix = 4)
+int h_fq_sqrt_win(const uint32_t* a, uint32_t* out, int* distinct_keys) {
+  static fq T[kTwoAdicity], Tinv[kTwoAdicity];
+  static std::vector<fq> U(kSqrtUCount), V(kSqrtVCount);
+  static std::vector<uint8_t> lut(65536, 0xff), hit(65536, 0);
+  static bool ready = false;
+  static int keys = 0;
+  if (!ready) {
+    fq_sqrt_table(T);
+    fq_sqrt_inverse_table(T, Tinv);
+    for (size_t g = 0; g < kSqrtUCount + kSqrtVCount + kSqrtRadix; g++) fq_sqrt_fill_entry(T, Tinv, g, U.data(), V.data(), lut.data());
+    for (uint32_t j = 0; j < (uint32_t)kSqrtRadix; j++) {
+      fq acc = fq_one();
+      for (int k = 0; k < kSqrtWin; k++)
+        if ((j >> k) & 1u) acc = fq_mul(acc, T[kTwoAdicity - kSqrtWin + k]);
+      uint32_t key = fq_sqrt_key(fq_reduce_full(acc));
+      if (!hit[key]) { hit[key] = 1; keys++; }
+    }
+    ready = true;
+  }
+  *distinct_keys = keys;
+  fq x; memcpy(x.v, a, 48);
+  bool ok;
+  SqrtTables tb{U.data(), V.data(), lut.data()};
+  fq r = fq_sqrt_win(fq_reduce_full(fq_to_mont(x)), tb, &ok);
+  fq c = fq_from_mont(r);
+  memcpy(out, c.v, 48);
+  return ok ? 1 : 0;
+}
+int h_fq_half_is_half(const uint32_t* q_minus_1_over_2) {
+  for (int i = 0; i < kFqLimbs; i++) if (fq_half_limb(i) != q_minus_1_over_2[i]) return 0;
+  return 1;
+}
+}

@@ -608,6 +608,67 @@ def test_sigma_batch_round_trip(sctx377):
     assert st[7] == 5 and st.count(0) == n - 1
 
 
+WIRE = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_wire_vectors.json")))
+
+
+def test_wire_decompress_golden_deck_and_rejections(ctx377, pkg):
+    """Deserialising half of the wire format over BLS12-377 (`mp377_points_decompress`, `mp377_deck_deserialize`;
+    ark-serialize's CanonicalDeserialize behind every type of reference src/lib.rs:45-71): square roots in F_q and the
+    G1 membership test on the GPU, against the oracle's golden vectors, with the status code of every rejected
+    encoding (off-curve abscissas, x >= q, stray bits, bad infinity encodings, a curve point outside G1)."""
+    from mental_poker_b200 import bls12_377 as b377
+    h = bytes.fromhex
+    pts = b"".join(h(fx["point"]) for fx in WIRE["points"])
+    comp = b"".join(h(fx["compressed"]) for fx in WIRE["points"])
+    assert b377.points_compress(pts) == comp
+    assert ctx377.points_decompress(comp) == pts
+    assert ctx377.launches > 0
+    assert ctx377.deck_deserialize(h(WIRE["deck_serialized"])) == h(WIRE["deck"])
+    k = len(WIRE["points"])
+    curve_only = [i for i, s in enumerate(WIRE["rejected_statuses"]) if s != 3]
+    bad = comp + b"".join(h(WIRE["rejected"][i]) for i in curve_only)
+    out, st, rc = ctx377.points_decompress(bad, want_statuses=True)
+    assert rc == -3 and st[:k] == [0] * k and st[k:] == [WIRE["rejected_statuses"][i] for i in curve_only]
+    assert out[:len(pts)] == pts and out[len(pts):] == bytes(96 * len(curve_only))
+    torsion = [h(WIRE["rejected"][i]) for i, s in enumerate(WIRE["rejected_statuses"]) if s == 3]
+    out, st, rc = ctx377.points_decompress(comp + torsion[0], want_statuses=True)
+    assert rc == -6 and st == [0] * k + [3] and out == pts + bytes(96)
+    with pytest.raises(pkg.MpError):
+        ctx377.points_decompress(bad)
+    with pytest.raises(pkg.MpError):                       # length prefix says 9 cards, buffer holds 8
+        ctx377.deck_deserialize((9).to_bytes(8, "little") + h(WIRE["deck_serialized"])[8:])
+    assert ctx377.points_decompress(b"") == b"" and ctx377.deck_deserialize(bytes(8)) == b""
+
+
+def test_wire_round_trip_of_proof_and_decks_still_verifies(ctx377):
+    """serialize -> deserialize of the golden shuffle proof and both decks gives back the same bytes, which verify;
+    a non-canonical scalar in the serialised proof is refused at deserialisation; 4 096 random points round-trip."""
+    from mental_poker_b200 import bls12_377 as b377
+    import numpy as np
+    fx = SHUF["shuffle"][0]
+    r = _raw(fx)
+    m, n = fx["m"], fx["n"]
+    ser = b377.proof_serialize(m, n, r["proof"])
+    assert len(ser) == (11 * m + 8) * 48 + (5 * n + 9) * 32
+    proof = ctx377.proof_deserialize(m, n, ser)
+    assert proof == r["proof"]
+    deck = ctx377.deck_deserialize(b377.deck_serialize(r["deck"]))
+    deck2 = ctx377.deck_deserialize(b377.deck_serialize(r["deck2"]))
+    assert deck == r["deck"] and deck2 == r["deck2"]
+    assert ctx377.verify_shuffle(m, n, r["enc_g"], r["ck_g"], r["ck_h"], r["ghat"], r["pk"], deck, deck2, proof) == 0
+    off = (5 * m + 4) * 48                                    # first scalar of the serialised proof
+    s = int.from_bytes(ser[off:off + 32], "little")
+    big = ser[:off] + (s + bls.N).to_bytes(32, "little") + ser[off + 32:]
+    with pytest.raises(Exception) as e:
+        ctx377.proof_deserialize(m, n, big)
+    assert e.value.code == -5
+    rng = np.random.default_rng(48)
+    k = 4096
+    a = rng.integers(0, 256, size=(k, 32), dtype=np.uint8); a[:, 31] &= 0x0f
+    pts = ctx377.dbg_scalar_mul(pb(bls.G) * k, a.tobytes())
+    assert ctx377.points_decompress(b377.points_compress(pts)) == pts
+
+
 def test_prover_usage_errors(ctx377, pkg):
     fresh = pkg.bls12_377.Context(0)
     buf = bytes(96)

@@ -88,3 +88,37 @@ def test_compression_and_proof_serialisation(shim):
                 else:
                     want += proof[pos:pos + 32]; pos += 32
         assert pos == len(proof) and buf.raw == want
+
+
+def test_sqrt_over_bls12_377_matches_big_ints(tmp_path_factory):
+    """csrc/fq_sqrt.cuh compiled for the second curve (q - 1 = 2^46 * t: 23 windows of 2 bits, exponent (t-1)/2 by
+    square-and-multiply): textbook and windowed forms against big-int arithmetic -- r^2 == a for squares, refusal for
+    non-residues, elements of small 2-power order, and the (q-1)/2 constant behind the "larger y" flag."""
+    from oracle.py import bls12_377 as bls
+    out_so = str(tmp_path_factory.mktemp("shim377w") / "host_shim_bls12_377.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMP_CURVE_BLS12_377", "-o", out_so,
+                           os.path.join(ROOT, "tests", "host", "host_shim_bls12_377.cpp")])
+    lib = ctypes.CDLL(out_so)
+    Q = bls.Q
+    w = lambda x: (ctypes.c_uint32 * 12)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
+    assert lib.h_fq_half_is_half(w((Q - 1) // 2)) == 1
+    rnd = random.Random(6)
+    out = (ctypes.c_uint32 * 12)()
+    keys = ctypes.c_int(0)
+    t = (Q - 1) >> 46
+    zeta = pow(5, t, Q)
+    assert pow(zeta, 1 << 45, Q) == Q - 1
+    cases = [0, 1, 4, Q - 1, 2, 3, 5] + [rnd.randrange(Q) for _ in range(40)] + [rnd.randrange(Q) ** 2 % Q for _ in range(25)]
+    cases += [pow(zeta, 1 << s, Q) for s in (0, 1, 2, 3, 22, 23, 43, 44, 45)] + [pow(zeta, 3 << s, Q) for s in (0, 1, 7, 40)]
+    squares = nonsquares = 0
+    for a in cases:
+        is_sq = a == 0 or pow(a, (Q - 1) // 2, Q) == 1
+        for fn in ("plain", "win"):
+            ok = lib.h_fq_sqrt(w(a), out) if fn == "plain" else lib.h_fq_sqrt_win(w(a), out, ctypes.byref(keys))
+            r = sum(int(out[i]) << (32 * i) for i in range(12))
+            assert bool(ok) == is_sq, (fn, a)
+            if ok:
+                assert r * r % Q == a and r < Q, (fn, a)
+        squares += is_sq
+        nonsquares += not is_sq
+    assert keys.value == 4 and squares >= 30 and nonsquares >= 15

@@ -4,6 +4,8 @@ import json
 import os
 import random
 
+import pytest
+
 from sympy import isprime
 
 from oracle.py import bls12_377 as bls
@@ -242,3 +244,24 @@ def test_sigma_golden_vectors_are_the_oracles():
     # the context manager restored the Stark curve
     from oracle.py import stark
     assert sigma.Q == stark.N
+
+
+def test_wire_golden_vectors_are_the_oracles():
+    """tests/golden/bls12_377_wire_vectors.json against oracle/py/wire.py: every point decompresses to itself, the deck
+    round-trips, every rejected encoding is refused -- including the curve point outside G1, which only the subgroup
+    test catches."""
+    import json, os
+    from oracle.py import wire
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bls12_377_wire_vectors.json")))
+    hx = bytes.fromhex
+    for fx in gold["points"]:
+        p = bls.point_from_bytes(hx(fx["point"]))
+        assert wire.compress_generic(p, bls.CURVE) == hx(fx["compressed"])
+        assert wire.decompress_generic(hx(fx["compressed"]), bls.CURVE) == p
+    deck = wire.deck_deserialize_generic(hx(gold["deck_serialized"]), bls.CURVE)
+    assert b"".join(pb(a) + pb(b) for a, b in deck) == hx(gold["deck"])
+    for enc, st in zip(gold["rejected"], gold["rejected_statuses"]):
+        with pytest.raises(ValueError):
+            wire.decompress_generic(hx(enc), bls.CURVE)
+        if st == 3:
+            assert wire.decompress_generic(hx(enc), bls.CURVE, subgroup_check=False) is not None
