@@ -892,6 +892,37 @@ def bls12_377_bench(pkg, torch, dev, logn, cpu_baseline):
     res["reference_benchmark_shape"] = dict(
         source="examples/parameter_selection.rs:31-43,78-96 (BLS12-377 G1, 300 cards): shuffle_and_remask end to end + verify_shuffle",
         timing="host wall clock around mp377_shuffle_and_remask / mp377_shuffle_verify (host buffers), best of 3", shapes=shapes)
+    # the rest of the trait over this curve at the reference benchmark's deck size and at a 2^14-card deck: the six
+    # batched sigma calls (mod.rs:182-354) and deserialisation of a serialised deck (square roots + G1 membership)
+    try:
+        sig = {}
+        sk = rand_scalars(rng, 1)
+        pk1 = ctx.dbg_scalar_mul(g96, sk)
+        for cards_n in (300, 16384):
+            cards = ctx.dbg_scalar_mul(g96 * cards_n, rand_scalars(rng, cards_n))
+            sc = [rand_scalars(rng, cards_n) for _ in range(6)]
+            for it in range(2):
+                t = [time.perf_counter()]
+                masked, p1 = ctx.mask_batch(pk1, cards, sc[0], sc[1]); t.append(time.perf_counter())
+                s1 = ctx.verify_mask_batch(pk1, cards, masked, p1); t.append(time.perf_counter())
+                out, p2 = ctx.remask_prove_batch(pk1, masked, sc[2], sc[3]); t.append(time.perf_counter())
+                s2 = ctx.verify_remask_batch(pk1, masked, out, p2); t.append(time.perf_counter())
+                tok, p3 = ctx.reveal_batch(sk, pk1, out, sc[4]); t.append(time.perf_counter())
+                s3 = ctx.verify_reveal_batch(pk1, tok, out, p3); t.append(time.perf_counter())
+            names = ["mask", "verify_mask", "remask", "verify_remask", "reveal", "verify_reveal"]
+            e = {nm + "_ms": (t[k + 1] - t[k]) * 1e3 for k, nm in enumerate(names)}
+            e["all_verified"] = not (any(s1) or any(s2) or any(s3))
+            e["proofs_per_s"] = 3 * cards_n / (t[6] - t[0])
+            ser = pkg.bls12_377.deck_serialize(out)
+            t0 = time.perf_counter()
+            back = ctx.deck_deserialize(ser)
+            e["deck_deserialize_ms"] = (time.perf_counter() - t0) * 1e3
+            e["deck_round_trip_ok"] = back == out
+            sig[str(cards_n)] = e
+        res["sigma_and_wire"] = dict(timing="host wall clock around each mp377_* call (host buffers), second pass; verifiers and "
+                                            "deserialisation include the G1 membership test of every point", cards=sig)
+    except Exception as ex:
+        res["sigma_and_wire"] = dict(error=repr(ex))
     mb = {}
     for which, name, iters in [(0, "fq_mul", 1000), (1, "madd", 300)]:
         best = 0

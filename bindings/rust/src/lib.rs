@@ -111,6 +111,30 @@ extern "C" {
     pub fn mp377_proof_len(m: i32, n: i32) -> u64;
     pub fn mp377_shuffle_verify(ctx: *mut Mp377Ctx, m: i32, n: i32, enc_g: *const u8, ck_g: *const u8, ck_h: *const u8, ghat: *const u8,
                                 pk: *const u8, deck: *const u8, shuffled: *const u8, proof: *const u8) -> i32;
+    // BarnettSmartProtocol::{mask, verify_mask, remask, verify_remask, compute_reveal_token, verify_reveal, prove_key_ownership,
+    // verify_key_ownership} (lib.rs:88-175) for n items per call: Chaum-Pedersen proof = a | b | r = 224 bytes, Schnorr = 128
+    pub fn mp377_mask_batch(ctx: *mut Mp377Ctx, shared_key: *const u8, cards: *const u8, r: *const u8, omega: *const u8, n: u64,
+                            out_masked: *mut u8, out_proofs: *mut u8, host_threads: i32) -> i32;
+    pub fn mp377_verify_mask_batch(ctx: *mut Mp377Ctx, shared_key: *const u8, cards: *const u8, masked: *const u8, proofs: *const u8,
+                                   n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    pub fn mp377_remask_prove_batch(ctx: *mut Mp377Ctx, shared_key: *const u8, deck: *const u8, alpha: *const u8, omega: *const u8,
+                                    n: u64, out_deck: *mut u8, out_proofs: *mut u8, host_threads: i32) -> i32;
+    pub fn mp377_verify_remask_batch(ctx: *mut Mp377Ctx, shared_key: *const u8, deck: *const u8, remasked: *const u8,
+                                     proofs: *const u8, n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    pub fn mp377_reveal_batch(ctx: *mut Mp377Ctx, sk: *const u8, pk: *const u8, masked: *const u8, omega: *const u8, n: u64,
+                              out_tokens: *mut u8, out_proofs: *mut u8, host_threads: i32) -> i32;
+    pub fn mp377_verify_reveal_batch(ctx: *mut Mp377Ctx, pk: *const u8, tokens: *const u8, masked: *const u8, proofs: *const u8,
+                                     n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    pub fn mp377_key_ownership_prove_batch(ctx: *mut Mp377Ctx, pks: *const u8, sks: *const u8, infos: *const u8,
+                                           info_offsets: *const u64, omega: *const u8, n: u64, out_proofs: *mut u8,
+                                           host_threads: i32) -> i32;
+    pub fn mp377_key_ownership_verify_batch(ctx: *mut Mp377Ctx, pks: *const u8, infos: *const u8, info_offsets: *const u64,
+                                            proofs: *const u8, n: u64, statuses: *mut i32, host_threads: i32) -> i32;
+    // CanonicalDeserialize of points / decks / proofs (lib.rs:45-71): square roots + G1 membership on the GPU
+    pub fn mp377_points_decompress(ctx: *mut Mp377Ctx, input: *const u8 /* n*48 */, n: u64, out: *mut u8 /* n*96 */,
+                                   statuses: *mut i32) -> i32;
+    pub fn mp377_deck_deserialize(ctx: *mut Mp377Ctx, input: *const u8, in_len: u64, out_deck: *mut u8, n_cards: *mut u64) -> i32;
+    pub fn mp377_proof_deserialize(ctx: *mut Mp377Ctx, m: i32, n: i32, input: *const u8, out_proof: *mut u8) -> i32;
 }
 
 // =============================================================================================================

@@ -8,8 +8,10 @@
  * that ShuffleArgument::{prove,verify} / MultiExponentiationArgument / PedersenCommitment::commit
  * reduce to (call sites mod.rs:397-415,427-442; commit key setup mod.rs:111), plus verify_shuffle built on
  * them with host-side scalars (mp377_shuffle_verify), and shuffle_and_remask (mp377_shuffle_and_remask[_batch]: the
- * Stark build's lockstep prover compiled against this field).  The device-scalar large-deck drivers, the sigma
- * protocols' device half and point decompression are Stark-curve only.
+ * Stark build's lockstep prover compiled against this field), the batched sigma protocols either side of the shuffle
+ * (mp377_mask_batch ... mp377_key_ownership_verify_batch) and the wire format in both directions (mp377_points_compress /
+ * _decompress, deck and proof (de)serialisers).  Only the device-scalar large-deck prover (decks above 8 192 cards) and
+ * the resident-buffer entry points are Stark-curve only.
  *
  * Conventions are those of mpshuffle.h with the sizes of this curve:
  *   - base-field element: 48 bytes little-endian canonical (ark-ff 0.3 `Fp384` `ToBytes`);
