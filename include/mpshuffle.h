@@ -262,8 +262,11 @@ int32_t mp_shuffle_verify_batch_resident(mp_ctx* ctx, const uint8_t* pk, const u
  * 160 bytes, Schnorr = commit (64) | opening (32) = 96 bytes.  `omega` is the prover's randomness (one
  * scalar per proof, drawn by the caller from its own RNG in item order -- the library never owns an
  * RNG).  statuses[i] receives MP_OK or MP_VERIFY_CHAUM_PEDERSEN / MP_VERIFY_SCHNORR.  The per-proof
- * Fiat-Shamir transcripts run on `host_threads` CPU threads (0 = all hardware threads); a point off
- * the curve anywhere in the batch fails the call with MP_ERR_NOT_ON_CURVE.
+ * Fiat-Shamir transcripts run on `host_threads` CPU threads (0 = all hardware threads).  Verifiers: an
+ * item with a point off the curve or a non-canonical coordinate gets statuses[i] = MP_VERIFY_MALFORMED and
+ * the other items are still checked (the reference's deserialiser would refuse that one message); a bad
+ * KEY -- shared by the whole call -- fails the call with MP_ERR_NOT_ON_CURVE, as does any bad input of a
+ * prover.
  *
  *   mp_mask_batch / mp_verify_mask_batch       BarnettSmartProtocol::mask / verify_mask
  *                                              reference src/lib.rs:115-133, impl mod.rs:182-240

@@ -93,10 +93,11 @@ int32_t mp377_shuffle_and_remask_batch(mp377_ctx* ctx, const uint8_t* pk, const 
  * src/lib.rs:88-175, impl mod.rs:132-354), n independent items per call.  Same contract as mp_mask_batch ...
  * mp_key_ownership_verify_batch of mpshuffle.h with 96-byte points: Chaum-Pedersen proof = a (96) | b (96) | r (32) =
  * 224 bytes, Schnorr proof = commit (96) | opening (32) = 128 bytes; the generator is enc_g of mp377_ctx_set_params
- * (which must have been called).  statuses[i] = MP_OK or MP_VERIFY_CHAUM_PEDERSEN / MP_VERIFY_SCHNORR.  The verifiers
- * reject the call with MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_IN_SUBGROUP if any point they are handed (keys, cards,
- * ciphertexts, tokens, proof commitments) is not a canonical point of G1, as the reference's deserialiser would;
- * the provers take their inputs as trusted (on-curve is still checked).  Bytes are identical to oracle/py/sigma.py
+ * (which must have been called).  statuses[i] = MP_OK, MP_VERIFY_CHAUM_PEDERSEN / MP_VERIFY_SCHNORR, or
+ * MP_VERIFY_MALFORMED for an item one of whose points (card, ciphertext, token, proof commitment) is not a canonical
+ * point of G1 -- every point a verifier is handed goes through the membership test first, as the reference's
+ * deserialiser would do, and a refused item does not stop the others; a bad KEY fails the call with
+ * MP_ERR_NOT_ON_CURVE / MP_ERR_NOT_IN_SUBGROUP.  The provers take their inputs as trusted (on-curve is still checked).  Bytes are identical to oracle/py/sigma.py
  * under curve("bls12_377"). */
 int32_t mp377_mask_batch(mp377_ctx* ctx, const uint8_t* shared_key /* 96 */, const uint8_t* cards /* n*96 */,
                          const uint8_t* r /* n*32 */, const uint8_t* omega /* n*32 */, uint64_t n,

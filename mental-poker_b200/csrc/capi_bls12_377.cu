@@ -317,16 +317,46 @@ static constexpr size_t kSigPt = 96, kSigCp = 2 * kSigPt + 32, kSigSchnorr = kSi
     if (!(ctx)) return MP_ERR_INVALID_ARG;                                                                   \
     if (!(ctx)->prover) return (ctx)->fail(MP_ERR_NO_PARAMS, "mp377_ctx_set_params has not been called");    \
   } while (0)
-// G1 membership of the points a sigma verifier is handed: `whole` arrays of contiguous points plus the leading
-// `lead` bytes of each of n proof records of `rec` bytes
-static int32_t sigma_points_in_g1(mp377_ctx* ctx, std::initializer_list<std::pair<const uint8_t*, uint64_t>> whole,
-                                  const uint8_t* proofs, uint64_t n, size_t rec, size_t lead) {
+// G1 membership of the points a sigma verifier is handed.  `arrays`: contiguous points, `per` of them per item
+// (per == 0: call-level points such as keys -- a bad one fails the call); `proofs`: the leading `lead` bytes of each of
+// n records of `rec` bytes.  item_bad[i] is set for items with a point that is not a canonical point of G1: those fail
+// alone with MP_VERIFY_MALFORMED, as the reference's deserialiser would fail them, and the rest of the batch is checked.
+struct SigmaPts { const uint8_t* p; uint64_t count; uint64_t per; };
+static int32_t sigma_points_in_g1(mp377_ctx* ctx, std::initializer_list<SigmaPts> arrays, const uint8_t* proofs, uint64_t n,
+                                  size_t rec, size_t lead, std::vector<uint8_t>& item_bad) {
+  item_bad.assign(n, 0);
   std::vector<uint8_t> all;
-  for (const auto& w : whole)
-    if (w.first && w.second) all.insert(all.end(), w.first, w.first + w.second * kSigPt);
+  std::vector<int64_t> owner;   // item index, or -1 for a call-level point
+  for (const auto& a : arrays) {
+    if (!a.p || !a.count) continue;
+    all.insert(all.end(), a.p, a.p + a.count * kSigPt);
+    for (uint64_t k = 0; k < a.count; k++) owner.push_back(a.per ? (int64_t)(k / a.per) : -1);
+  }
   if (proofs)
-    for (uint64_t i = 0; i < n; i++) all.insert(all.end(), proofs + rec * i, proofs + rec * i + lead);
-  return all.empty() ? MP_OK : mp377_subgroup_check(ctx, all.data(), all.size() / kSigPt, nullptr);
+    for (uint64_t i = 0; i < n; i++) {
+      all.insert(all.end(), proofs + rec * i, proofs + rec * i + lead);
+      for (size_t k = 0; k < lead / kSigPt; k++) owner.push_back((int64_t)i);
+    }
+  if (all.empty()) return MP_OK;
+  std::vector<int32_t> st(owner.size());
+  const int32_t rc = mp377_subgroup_check(ctx, all.data(), owner.size(), st.data());
+  if (rc == MP_OK) return MP_OK;
+  if (rc != MP_ERR_NOT_ON_CURVE && rc != MP_ERR_NOT_IN_SUBGROUP) return rc;
+  for (size_t k = 0; k < owner.size(); k++) {
+    if (!st[k]) continue;
+    if (owner[k] < 0) return st[k] == 1 ? MP_ERR_NOT_ON_CURVE : MP_ERR_NOT_IN_SUBGROUP;   // ctx->err was set by the check
+    item_bad[(size_t)owner[k]] = 1;
+  }
+  return MP_OK;
+}
+// an off-curve point of a flagged item would fail the whole inner call through its call-level points only; the
+// inner verifier flags off-curve item points itself, and the items flagged here are overridden afterwards
+static int32_t sigma_finish(mp377_ctx* ctx, int32_t rc, const std::vector<uint8_t>& item_bad, int32_t* statuses) {
+  rc = prover_status(ctx, rc);
+  if (rc == MP_OK)
+    for (size_t i = 0; i < item_bad.size(); i++)
+      if (item_bad[i]) statuses[i] = MP_VERIFY_MALFORMED;
+  return rc;
 }
 extern "C" int32_t mp377_mask_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* cards, const uint8_t* r,
                                     const uint8_t* omega, uint64_t n, uint8_t* out_masked, uint8_t* out_proofs, int32_t host_threads) {
@@ -337,9 +367,10 @@ extern "C" int32_t mp377_verify_mask_batch(mp377_ctx* ctx, const uint8_t* shared
                                            const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
   NEED_PROVER(ctx);
   if (!shared_key || (n && (!cards || !masked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
-  int32_t sg = sigma_points_in_g1(ctx, {{shared_key, 1}, {cards, n}, {masked, 2 * n}}, proofs, n, kSigCp, 2 * kSigPt);
+  std::vector<uint8_t> item_bad;
+  int32_t sg = sigma_points_in_g1(ctx, {{shared_key, 1, 0}, {cards, n, 1}, {masked, 2 * n, 2}}, proofs, n, kSigCp, 2 * kSigPt, item_bad);
   if (sg != MP_OK) return sg;
-  return prover_status(ctx, sigma_verify_mask_batch(ctx->prover, shared_key, cards, masked, proofs, n, statuses, host_threads));
+  return sigma_finish(ctx, sigma_verify_mask_batch(ctx->prover, shared_key, cards, masked, proofs, n, statuses, host_threads), item_bad, statuses);
 }
 extern "C" int32_t mp377_remask_prove_batch(mp377_ctx* ctx, const uint8_t* shared_key, const uint8_t* deck, const uint8_t* alpha,
                                             const uint8_t* omega, uint64_t n, uint8_t* out_deck, uint8_t* out_proofs,
@@ -351,9 +382,10 @@ extern "C" int32_t mp377_verify_remask_batch(mp377_ctx* ctx, const uint8_t* shar
                                              const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
   NEED_PROVER(ctx);
   if (!shared_key || (n && (!deck || !remasked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
-  int32_t sg = sigma_points_in_g1(ctx, {{shared_key, 1}, {deck, 2 * n}, {remasked, 2 * n}}, proofs, n, kSigCp, 2 * kSigPt);
+  std::vector<uint8_t> item_bad;
+  int32_t sg = sigma_points_in_g1(ctx, {{shared_key, 1, 0}, {deck, 2 * n, 2}, {remasked, 2 * n, 2}}, proofs, n, kSigCp, 2 * kSigPt, item_bad);
   if (sg != MP_OK) return sg;
-  return prover_status(ctx, sigma_verify_remask_batch(ctx->prover, shared_key, deck, remasked, proofs, n, statuses, host_threads));
+  return sigma_finish(ctx, sigma_verify_remask_batch(ctx->prover, shared_key, deck, remasked, proofs, n, statuses, host_threads), item_bad, statuses);
 }
 extern "C" int32_t mp377_reveal_batch(mp377_ctx* ctx, const uint8_t* sk, const uint8_t* pk, const uint8_t* masked,
                                       const uint8_t* omega, uint64_t n, uint8_t* out_tokens, uint8_t* out_proofs, int32_t host_threads) {
@@ -364,9 +396,10 @@ extern "C" int32_t mp377_verify_reveal_batch(mp377_ctx* ctx, const uint8_t* pk, 
                                              const uint8_t* proofs, uint64_t n, int32_t* statuses, int32_t host_threads) {
   NEED_PROVER(ctx);
   if (!pk || (n && (!tokens || !masked || !proofs || !statuses))) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
-  int32_t sg = sigma_points_in_g1(ctx, {{pk, 1}, {tokens, n}, {masked, 2 * n}}, proofs, n, kSigCp, 2 * kSigPt);
+  std::vector<uint8_t> item_bad;
+  int32_t sg = sigma_points_in_g1(ctx, {{pk, 1, 0}, {tokens, n, 1}, {masked, 2 * n, 2}}, proofs, n, kSigCp, 2 * kSigPt, item_bad);
   if (sg != MP_OK) return sg;
-  return prover_status(ctx, sigma_verify_reveal_batch(ctx->prover, pk, tokens, masked, proofs, n, statuses, host_threads));
+  return sigma_finish(ctx, sigma_verify_reveal_batch(ctx->prover, pk, tokens, masked, proofs, n, statuses, host_threads), item_bad, statuses);
 }
 extern "C" int32_t mp377_key_ownership_prove_batch(mp377_ctx* ctx, const uint8_t* pks, const uint8_t* sks, const uint8_t* infos,
                                                    const uint64_t* info_offsets, const uint8_t* omega, uint64_t n,
@@ -379,9 +412,10 @@ extern "C" int32_t mp377_key_ownership_verify_batch(mp377_ctx* ctx, const uint8_
                                                     int32_t* statuses, int32_t host_threads) {
   NEED_PROVER(ctx);
   if (n && (!pks || !info_offsets || !proofs || !statuses)) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
-  int32_t sg = sigma_points_in_g1(ctx, {{pks, n}}, proofs, n, kSigSchnorr, kSigPt);
+  std::vector<uint8_t> item_bad;
+  int32_t sg = sigma_points_in_g1(ctx, {{pks, n, 1}}, proofs, n, kSigSchnorr, kSigPt, item_bad);
   if (sg != MP_OK) return sg;
-  return prover_status(ctx, sigma_key_ownership_verify_batch(ctx->prover, pks, infos, info_offsets, proofs, n, statuses, host_threads));
+  return sigma_finish(ctx, sigma_key_ownership_verify_batch(ctx->prover, pks, infos, info_offsets, proofs, n, statuses, host_threads), item_bad, statuses);
 }
 
 // ------------------------------------------------------------------------------------------

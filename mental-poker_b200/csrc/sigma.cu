@@ -216,7 +216,7 @@ static size_t lincomb_smem() {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags, sSigKinds, sSigStage0, sSigStage1, sSigStage2 };
+enum SigmaSlot { sSigCanon = sKaraOut + 1, sSigArena, sSigScal, sSigJobs, sSigOut, sSigFlags, sSigKinds, sSigStage0, sSigStage1, sSigStage2, sSigBadPts };
 
 // One batched call: a point arena (uploaded canonical points -> Montgomery, plus reserved result slots),
 // a scalar array, and launches of k_lincomb over job lists expanded on the device.  Caller buffers are
@@ -232,8 +232,9 @@ struct SigmaCall {
   affine* d_arena = nullptr;
   uint32_t* d_scal = nullptr;
   int* d_bad = nullptr;
+  int* d_bad_pts = nullptr;  // verifiers: one flag per input point, so that a malformed item fails alone
 
-  int32_t init(mp_ctx* c, uint64_t in_points, uint64_t reserved_points, uint64_t scalars) {
+  int32_t init(mp_ctx* c, uint64_t in_points, uint64_t reserved_points, uint64_t scalars, bool per_point_flags = false) {
     ctx = c;
     S = c->shuffle;
     st = c->stream;
@@ -246,6 +247,19 @@ struct SigmaCall {
     d_bad = (int*)ctx->scratch(mp_ctx::kSlotFlags, 256);
     NEED(d_canon); NEED(d_arena); NEED(d_scal); NEED(d_bad);
     CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if (per_point_flags && n_in) {
+      d_bad_pts = (int*)ctx->scratch(sSigBadPts, n_in * sizeof(int));
+      NEED(d_bad_pts);
+      CK(cudaMemsetAsync(d_bad_pts, 0, n_in * sizeof(int), st));
+    }
+    return MP_OK;
+  }
+  // per-point "not a canonical point of the curve" flags of the ingested points (after the last run)
+  int32_t bad_points(std::vector<int>& h) {
+    h.assign(n_in, 0);
+    if (!d_bad_pts || !n_in) return MP_OK;
+    CK(cudaMemcpyAsync(h.data(), d_bad_pts, n_in * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(stream_wait(ctx, st));
     return MP_OK;
   }
   // uploads a caller buffer whole into staging slot `which` (0..2); *d receives the device copy
@@ -279,7 +293,8 @@ struct SigmaCall {
     return MP_OK;
   }
   int32_t ingest() {  // canonical -> Montgomery, canonical + on-curve validation
-    CK(points_to_mont((const uint32_t*)d_canon, d_arena, n_in, d_bad, st));
+    if (d_bad_pts) CK(points_to_mont_items((const uint32_t*)d_canon, d_arena, n_in, d_bad_pts, 1, st));
+    else CK(points_to_mont((const uint32_t*)d_canon, d_arena, n_in, d_bad, st));
     ctx->launches += 1;
     return MP_OK;
   }
@@ -408,7 +423,7 @@ static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, cons
   const uint64_t per = remask ? 2 : 1;
   const uint64_t oIn = 0, oOut = per * n, oAB = oOut + 2 * n, oS = oAB + 2 * n;
   SigmaCall sc;
-  if ((rc = sc.init(ctx, oS, 2 * n, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.init(ctx, oS, 2 * n, 2 * n, true)) != MP_OK) return rc;
   const uint8_t* d_proofs;
   if ((rc = sc.put_points(oIn, in, per * n)) != MP_OK) return rc;
   if ((rc = sc.put_points(oOut, out, 2 * n)) != MP_OK) return rc;
@@ -449,7 +464,14 @@ static int32_t cp_fixed_verify(mp_ctx* ctx, bool remask, const uint8_t* pk, cons
   if (remask) kinds[0].set(fVarPt0, oS); else kinds[0].set(fVarPt0, oOut, 2);
   kinds[1].set(fFixSc1, 0).set(fVarPt0, oS + n).set(fVarSc0, n).set(fSubPt, oAB + 1, 2);
   if ((rc = sc.run(kinds, n, nullptr, flags)) != MP_OK) return rc;
-  for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
+  std::vector<int> bad;
+  if ((rc = sc.bad_points(bad)) != MP_OK) return rc;
+  for (uint64_t i = 0; i < n; i++) {
+    // an item with a point off the curve / not canonical fails on its own, as the reference's deserialiser would fail it
+    bool malformed = bad[oOut + 2 * i] || bad[oOut + 2 * i + 1] || bad[oAB + 2 * i] || bad[oAB + 2 * i + 1];
+    for (uint64_t k = 0; k < per; k++) malformed = malformed || bad[oIn + per * i + k];
+    statuses[i] = malformed ? MP_VERIFY_MALFORMED : (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
+  }
   return MP_OK;
 }
 
@@ -517,7 +539,7 @@ int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t*
   // arena: [c1: n] [tokens: n] [a, b: 2n] [pk]
   const uint64_t oC1 = 0, oTok = n, oAB = 2 * n, oPk = 4 * n;
   SigmaCall sc;
-  if ((rc = sc.init(ctx, 4 * n + 1, 0, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.init(ctx, 4 * n + 1, 0, 2 * n, true)) != MP_OK) return rc;
   const uint8_t *d_masked, *d_proofs;
   if ((rc = sc.stage(0, masked, n * CB, &d_masked)) != MP_OK) return rc;
   if ((rc = sc.stage(1, proofs, n * kCpProofLen, &d_proofs)) != MP_OK) return rc;
@@ -543,7 +565,13 @@ int32_t sigma_verify_reveal_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t*
   uint8_t* flags = pinned(S, 2 * n + 64);
   if (!flags) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
   if ((rc = sc.run(kinds, n, nullptr, flags)) != MP_OK) return rc;
-  for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
+  std::vector<int> bad;
+  if ((rc = sc.bad_points(bad)) != MP_OK) return rc;
+  if (bad[oPk]) return ctx->fail(MP_ERR_NOT_ON_CURVE, "the public key is not a canonical point of the curve");
+  for (uint64_t i = 0; i < n; i++) {
+    const bool malformed = bad[oC1 + i] || bad[oTok + i] || bad[oAB + 2 * i] || bad[oAB + 2 * i + 1];
+    statuses[i] = malformed ? MP_VERIFY_MALFORMED : (flags[i] && flags[n + i] && canon_ok[i]) ? MP_OK : MP_VERIFY_CHAUM_PEDERSEN;
+  }
   return MP_OK;
 }
 
@@ -583,7 +611,7 @@ int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const 
   if (n && (!pks || !info_off || !proofs || !statuses)) return ctx->fail(MP_ERR_INVALID_ARG, "null argument");
   if (n == 0) return MP_OK;
   SigmaCall sc;  // arena: [pk: n] [commit: n];  scalars: [opening: n] [c: n]
-  if ((rc = sc.init(ctx, 2 * n, 0, 2 * n)) != MP_OK) return rc;
+  if ((rc = sc.init(ctx, 2 * n, 0, 2 * n, true)) != MP_OK) return rc;
   const uint8_t* d_proofs;
   if ((rc = sc.put_points(0, pks, n)) != MP_OK) return rc;
   if ((rc = sc.stage(0, proofs, n * kSchnorrProofLen, &d_proofs)) != MP_OK) return rc;
@@ -605,7 +633,10 @@ int32_t sigma_key_ownership_verify_batch(mp_ctx* ctx, const uint8_t* pks, const 
   uint8_t* flags = pinned(S, n + 64);
   if (!flags) return ctx->fail(MP_ERR_CUDA, "pinned allocation failed");
   if ((rc = sc.run(kinds, n, nullptr, flags)) != MP_OK) return rc;
-  for (uint64_t i = 0; i < n; i++) statuses[i] = (flags[i] && canon_ok[i]) ? MP_OK : MP_VERIFY_SCHNORR;
+  std::vector<int> bad;
+  if ((rc = sc.bad_points(bad)) != MP_OK) return rc;
+  for (uint64_t i = 0; i < n; i++)
+    statuses[i] = (bad[i] || bad[n + i]) ? MP_VERIFY_MALFORMED : (flags[i] && canon_ok[i]) ? MP_OK : MP_VERIFY_SCHNORR;
   return MP_OK;
 }
 

@@ -571,17 +571,23 @@ def test_sigma_reveal_and_key_ownership_golden_and_negative_cases(sctx377, pkg):
     assert kp == cat("proof", K)
     assert sctx377.key_ownership_verify_batch(cat("pk", K), infos, kp) == [0] * len(K)
     assert sctx377.key_ownership_verify_batch(cat("pk", K), infos[::-1], kp) == [6, 0, 6]
-    # a token that is on the curve but outside G1 is refused before any verification, like upstream's deserialiser
+    # what ark-serialize would refuse at deserialisation fails per ITEM (status 7, "malformed"), not per call: a token /
+    # a Schnorr commitment on the curve but outside G1, a token off the curve; a bad KEY (call-level) fails the call
     _, T = _torsion_point()
-    fx = V[0]
-    tok_bad = pb(bls.add(bls.point_from_bytes(h(fx["token"])), T))
+    toks = b"".join(h(fx["token"]) for fx in V[:3])
+    maskeds, pfs = b"".join(h(fx["masked"]) for fx in V[:3]), b"".join(h(fx["proof"]) for fx in V[:3])
+    pk0 = h(V[0]["pk"])
+    want = [0 if fx["pk"] == V[0]["pk"] else 5 for fx in V[:3]]
+    assert sctx377.verify_reveal_batch(pk0, toks, maskeds, pfs) == want
+    tok_bad = toks[:96] + pb(bls.add(bls.point_from_bytes(toks[96:192]), T)) + toks[192:]
+    assert sctx377.verify_reveal_batch(pk0, tok_bad, maskeds, pfs) == [want[0], 7, want[2]]
+    off_curve = bytearray(toks); off_curve[2 * 96 + 50] ^= 1
+    assert sctx377.verify_reveal_batch(pk0, bytes(off_curve), maskeds, pfs) == [want[0], want[1], 7]
     with pytest.raises(pkg.MpError) as e:
-        sctx377.verify_reveal_batch(h(fx["pk"]), tok_bad, h(fx["masked"]), h(fx["proof"]))
+        sctx377.verify_reveal_batch(pb(bls.add(bls.point_from_bytes(pk0), T)), toks, maskeds, pfs)
     assert e.value.code == -6
     kp_bad = pb(T) + kp[96:]        # commitment of the first Schnorr proof replaced by a torsion point
-    with pytest.raises(pkg.MpError) as e:
-        sctx377.key_ownership_verify_batch(cat("pk", K), infos, kp_bad)
-    assert e.value.code == -6
+    assert sctx377.key_ownership_verify_batch(cat("pk", K), infos, kp_bad) == [7, 0, 0]
 
 
 def test_sigma_batch_round_trip(sctx377):

@@ -64,6 +64,36 @@ def test_reveal_and_key_ownership_golden_and_negative_cases(sctx):
     assert st == [6, 0, 6] and sctx.status_string(6) == "Schnorr Identification"
 
 
+def test_malformed_items_fail_alone(sctx):
+    """A point off the curve (or a non-canonical coordinate) in ONE item of a verifier batch gives that item status 7
+    ("malformed", what the reference's deserialiser would refuse) and leaves the verdicts of the others untouched; a
+    bad key -- shared by the whole call -- fails the call."""
+    shared = h(GOLD["shared_key"])
+    M, R, V, K = GOLD["mask"], GOLD["remask"], GOLD["reveal"], GOLD["key_ownership"]
+    cards, masked, proofs = cat("card", M), cat("masked", M), cat("proof", M)
+    n = len(M)
+    for buf_idx, off in ((0, 64 * 2 + 5), (1, 128 * 3 + 70), (2, 160 * 1 + 3), (2, 160 * 4 + 64 + 9)):
+        bufs = [bytearray(cards), bytearray(masked), bytearray(proofs)]
+        bufs[buf_idx][off] ^= 1
+        item = off // (64, 128, 160)[buf_idx]
+        st = sctx.verify_mask_batch(shared, bytes(bufs[0]), bytes(bufs[1]), bytes(bufs[2]))
+        assert st == [7 if i == item else 0 for i in range(n)], (buf_idx, off)
+    big_x = bytearray(masked); big_x[128 * 2:128 * 2 + 32] = (stark.P + 1).to_bytes(32, "little")   # x >= p
+    assert sctx.verify_mask_batch(shared, cards, bytes(big_x), proofs)[2] == 7
+    orig, out, rp = cat("original", R), cat("remasked", R), cat("proof", R)
+    bad = bytearray(orig); bad[128 * 1 + 64 + 1] ^= 1
+    assert sctx.verify_remask_batch(shared, bytes(bad), out, rp) == [7 if i == 1 else 0 for i in range(len(R))]
+    fx = V[0]
+    tok = bytearray(h(fx["token"])); tok[40] ^= 1
+    assert sctx.verify_reveal_batch(h(fx["pk"]), bytes(tok), h(fx["masked"]), h(fx["proof"])) == [7]
+    kp = bytearray(cat("proof", K)); kp[96 * 2 + 7] ^= 1
+    assert sctx.key_ownership_verify_batch(cat("pk", K), [h(r["info"]) for r in K], bytes(kp)) == [0, 0, 7]
+    badkey = bytearray(shared); badkey[3] ^= 1
+    with pytest.raises(Exception) as e:
+        sctx.verify_mask_batch(bytes(badkey), cards, masked, proofs)
+    assert e.value.code == -3
+
+
 def rand_scalars(rng, k):
     a = rng.integers(0, 256, size=(k, 32), dtype=np.uint8)
     a[:, 31] &= 0x07
