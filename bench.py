@@ -355,9 +355,12 @@ def main():
     bufs = [(out_decks, proofs), (ctypes.create_string_buffer(128 * N * Q), ctypes.create_string_buffer(plen * Q))]
     bufs[1][0].raw, bufs[1][1].raw = out_decks.raw, proofs.raw   # "previous step" of the very first step: the set-up pass
     state = dict(k=0)
-    # worker CONTEXTS of the two large-deck batch calls, not compute threads: each spends most of its time blocked on the
-    # device (CPU demand ~ 2 x 23.5 ms of Blake2s + ~5 ms per proof), so their number is not divided by the rank count
-    prove_threads = verify_threads = args.workers
+    # host_threads of the two large-deck batch calls = the CPU threads each may keep busy: this rank's share of the host,
+    # halved when the two calls run concurrently.  The library runs 8 worker contexts per call whatever the budget (they
+    # sleep while their kernels run) and, when the budget is below that, hashes the statements of the 8 decks together
+    # (multi-stream Blake2s) instead of one serial 23.5 ms pass per worker -- which is what a shared host cannot afford
+    prove_threads = verify_threads = max(2, host_threads // 2) if args.overlap else max(2, host_threads)
+    os.environ.setdefault("MP_PROVE_WORKERS", str(args.workers))   # read by the library at its first large-deck batch call
 
     def prove_call(resident, out_d, out_p):
         if resident:

@@ -46,8 +46,12 @@ int32_t shuffle_commit_batch(mp_ctx* ctx, const uint8_t* values, const uint8_t* 
 int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
                       const uint32_t* perm, const uint8_t* rho, const uint8_t* rand, uint8_t* proof_out,
                       const void* deck2_src = nullptr, Transcript* fs_started = nullptr);
+struct StatementHashes;
+// (hashes / hash_index: the batch verifier's shared statement hashes, shuffle_internal.cuh; the transcript of this proof
+//  then continues from hashes->wait(hash_index) instead of hashing the statement itself)
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                       const uint8_t* proof, const void* deck_src = nullptr, const void* deck2_src = nullptr);
+                       const uint8_t* proof, const void* deck_src = nullptr, const void* deck2_src = nullptr,
+                       StatementHashes* hashes = nullptr, uint64_t hash_index = 0);
 
 // B independent proofs under the same parameters and public key, verified in lockstep.
 // (d_decks / d_decks2: optional device copies of the decks, B * N * 128 bytes each, used by the large-deck path)

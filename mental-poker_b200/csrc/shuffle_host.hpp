@@ -142,6 +142,17 @@ inline void absorb_statement_head(Transcript& fs, const ShuffleParamsHost* S, co
   fs.feed_points64(deck, 2 * N);
 }
 inline void absorb_statement_deck2(Transcript& fs, const uint8_t* deck2, size_t N) { fs.feed_points64(deck2, 2 * N); }
+// the head for up to 8 proofs of a batch at once (same parameters and key, decks[l] = the input deck of lane l)
+inline void absorb_statement_head_lanes(TranscriptLanes& tl, const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* const* decks,
+                                        size_t N) {
+  tl.feed_label_all("shuffle_argument");
+  tl.feed_points64_all(S->enc_g, 1);
+  tl.feed_points64_all(pk, 1);
+  tl.feed_points64_all(S->ck64.data() + kPointBytes, (size_t)S->n);
+  tl.feed_points64_all(S->ck64.data(), 1);
+  tl.feed_points64_all(S->ghat, 1);
+  tl.feed_points64(decks, 2 * N);
+}
 inline void absorb_statement_tail(Transcript& fs, const uint8_t* cA, int m) {
   fs.feed_points64(cA, (size_t)m);
   fs.end();
@@ -161,12 +172,19 @@ struct Challenges {
 };
 
 // Every challenge derives from statement + proof bytes (no device round trip).
+// (stmt_started: a hasher that has already absorbed the statement up to and including the shuffled deck -- the batch
+//  verifier hashes those 17 MB for several proofs at once, shuffle_internal.cuh StatementHashes)
 inline Challenges derive_challenges(const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                                    size_t N, const uint8_t* proof, const Layout& L) {
+                                    size_t N, const uint8_t* proof, const Layout& L, const Blake2s* stmt_started = nullptr) {
   const int m = S->m;
   Challenges ch;
   Transcript fs;
-  absorb_statement(fs, S, pk, deck, deck2, N, proof + L.cA);
+  if (stmt_started) {
+    fs.adopt_pending(*stmt_started);
+    absorb_statement_tail(fs, proof + L.cA, m);
+  } else {
+    absorb_statement(fs, S, pk, deck, deck2, N, proof + L.cA);
+  }
   ch.x = fs.challenge();
   fs.begin(); fs.feed_label("shuffle_argument_b"); fs.feed_points64(proof + L.cB, m); fs.end();
   ch.y = fs.challenge();

@@ -182,6 +182,62 @@ int32_t run_on_workers(mp_ctx* ctx, int P, uint64_t B, F&& fn, bool sleeping_wai
 }
 
 
+// Statement hashes of a large-deck batch, shared.  Every proof's transcript starts with one serial Blake2s pass over the
+// statement (parameters, key, input deck, shuffled deck: 17 MB at 2^16 cards, 23.5 ms of one core) -- once in the
+// prover, once in the verifier.  With a core per worker that costs nothing extra; when several GPUs' workers share a
+// host it is what the GPUs wait for.  Here one background thread hashes the statements of up to
+// eight proofs AT ONCE (Blake2sLanes: one vector lane per proof, ~4x the bytes per core-second) and the workers pick up
+// their hasher when they need it.  Prover: the head (up to the input deck); the shuffled deck, which only exists after
+// the remask kernel, is still hashed by the worker.  Verifier: everything up to the proof.
+struct StatementHashes {
+  std::vector<Blake2s> started;
+  std::vector<char> ready;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::thread th;
+  // decks2 == nullptr: head only
+  void start(const ShuffleParamsHost* S, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2, size_t N, uint64_t B) {
+    started.resize(B);
+    ready.assign(B, 0);
+    th = std::thread([=] {
+      const size_t stride = N * kCtBytes;
+      for (uint64_t g0 = 0; g0 < B; g0 += Blake2sLanes::kLanes) {
+        const int K = (int)std::min<uint64_t>(Blake2sLanes::kLanes, B - g0);
+        TranscriptLanes tl(K);
+        const uint8_t *d1[Blake2sLanes::kLanes], *d2[Blake2sLanes::kLanes];
+        for (int l = 0; l < K; l++) {
+          d1[l] = decks + (g0 + l) * stride;
+          d2[l] = decks2 ? decks2 + (g0 + l) * stride : nullptr;
+        }
+        absorb_statement_head_lanes(tl, S, pk, d1, N);
+        if (decks2) tl.feed_points64(d2, 2 * N);
+        std::lock_guard<std::mutex> lk(mu);
+        for (int l = 0; l < K; l++) {
+          tl.extract(l, &started[g0 + l]);
+          ready[g0 + l] = 1;
+        }
+        cv.notify_all();
+      }
+    });
+  }
+  const Blake2s& wait(uint64_t i) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return ready[i] != 0; });
+    return started[i];
+  }
+  ~StatementHashes() {
+    if (th.joinable()) th.join();
+  }
+};
+// shared hashing on?  MP_HASH_LANES=0 / 1 forces it; otherwise on when the caller's thread budget (host_threads) is
+// below the number of worker contexts: the workers then cannot each have a core for their own 23.5 ms pass
+inline bool share_statement_hashes(int host_threads, int workers) {
+  const char* e = getenv("MP_HASH_LANES");   // read per call: the tests switch it
+  if (e) return atoi(e) != 0;
+  const int budget = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+  return workers > 1 && budget < workers;
+}
+
 // Small-deck batches: fn(worker, p0, count) over [0, B) in chunks of at most `sub` proofs.  A sub-batch alternates host
 // phases (transcripts, scalar algebra on host threads) and device phases (the batched MSMs), so one sub-batch at a time
 // leaves the GPU idle for the host share of the wall time (measured at 512 x 52 cards, 16 threads: 6.0 ms host beside

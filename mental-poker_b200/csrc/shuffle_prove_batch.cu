@@ -446,14 +446,21 @@ int32_t shuffle_prove_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks
   // MSM workspace at 2^16 cards.  Measured at 2^16 cards on one B200 (16 vCPUs): 30.2 / 34.2 / 36.5 / 36.4 proofs/s
   // with 3 / 6 / 8 / 12 contexts; host_threads caps it when several ranks share a host
   static const uint64_t large_workers = [] { const char* e = getenv("MP_PROVE_WORKERS"); return e ? strtoull(e, nullptr, 10) : 8ull; }();
-  P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, (uint64_t)(N > small_deck_max() ? large_workers : 32), B}));
+  // (worker contexts sleep while their kernels run: for real large decks their number is not the caller's thread budget;
+  //  the budget decides whether each worker hashes its own statement head or the heads are shared, StatementHashes)
+  if (N > small_deck_max()) P = host_threads == 1 ? 1 : (int)std::max<uint64_t>(1, std::min<uint64_t>(large_workers, B));
+  else P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, (uint64_t)32, B}));
+  StatementHashes hashes;
+  const bool shared = share_statement_hashes(host_threads, P);
+  if (shared) hashes.start(S, pk, decks, nullptr, N, B);
   return run_on_workers(ctx, P, B, [&](mp_ctx* w, uint64_t i) {
     const void* d_shuffled = nullptr;
     Transcript fs;
     int32_t st = shuffle_remask(w, pk, decks + i * N * 128, perms + i * N, rhos + i * N * 32, N, out_decks + i * N * 128,
-                                d_decks ? (const uint8_t*)d_decks + i * N * 128 : nullptr, &d_shuffled, &fs);
+                                d_decks ? (const uint8_t*)d_decks + i * N * 128 : nullptr, &d_shuffled, shared ? nullptr : &fs);
     int l = w->launches;
     if (st == MP_OK) {
+      if (shared) fs.adopt_pending(hashes.wait(i));   // the head of the statement, hashed with the other decks'
       st = shuffle_prove(w, pk, decks + i * N * 128, out_decks + i * N * 128, perms + i * N, rhos + i * N * 32,
                          rands + i * rlen, proofs + i * plen, d_shuffled, &fs);
       w->launches += l;

@@ -10,7 +10,8 @@ namespace mp {
 // verify
 // ------------------------------------------------------------------------------------------
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
-                       const uint8_t* proof, const void* deck_src, const void* deck2_src) {
+                       const uint8_t* proof, const void* deck_src, const void* deck2_src, StatementHashes* hashes,
+                       uint64_t hash_index) {
   if (!ctx || !pk || !deck || !deck2 || !proof) return MP_ERR_INVALID_ARG;
   if (!deck_src) deck_src = deck;     // host copy doubles as the transfer source
   if (!deck2_src) deck2_src = deck2;  // (a device pointer here means the deck is already resident in HBM)
@@ -53,7 +54,7 @@ int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, cons
   ctx->launches += 1;
 
   // ---- 2. transcript: every challenge derives from statement + proof bytes
-  const Challenges ch = derive_challenges(S, pk, deck, deck2, N, proof, L);
+  const Challenges ch = derive_challenges(S, pk, deck, deck2, N, proof, L, hashes ? &hashes->wait(hash_index) : nullptr);
   const fr &x = ch.x, &y = ch.y, &z = ch.z, &xm = ch.xm;
 
   // ---- 3. the commitment-space checks as small G1 jobs (host builds O(m + n) scalars), issued on
@@ -281,12 +282,16 @@ int32_t shuffle_verify_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck
   if (N > small_deck_max()) {
     // large decks: the single-proof verifier per deck, on a few worker contexts so that one
     // proof's serial statement hash (host) overlaps the other proofs' MSMs (device)
-    int P = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
-    P = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)P, 8, B}));
+    // worker contexts sleep while their kernels run, so their number is not the caller's thread budget; the budget
+    // decides whether each worker hashes its own statement or the hashes are shared (StatementHashes)
+    const int P = (int)std::max<uint64_t>(1, std::min<uint64_t>(host_threads == 1 ? 1 : 8, B));
+    StatementHashes hashes;
+    const bool shared = share_statement_hashes(host_threads, P);
+    if (shared) hashes.start(S, pk, decks, decks2, N, B);
     return run_on_workers(ctx, P, B, [&](mp_ctx* w, uint64_t p) {
       int32_t st = shuffle_verify(w, pk, decks + p * N * 128, decks2 + p * N * 128, proofs + p * plen,
                                   d_decks ? (const uint8_t*)d_decks + p * N * 128 : nullptr,
-                                  d_decks2 ? (const uint8_t*)d_decks2 + p * N * 128 : nullptr);
+                                  d_decks2 ? (const uint8_t*)d_decks2 + p * N * 128 : nullptr, shared ? &hashes : nullptr, p);
       if (st == MP_ERR_NOT_ON_CURVE || st == MP_ERR_NOT_CANONICAL) st = MP_VERIFY_MALFORMED;  // this item only
       if (st >= 0) statuses[p] = st;
       return st < 0 ? st : MP_OK;

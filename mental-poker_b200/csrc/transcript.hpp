@@ -76,6 +76,7 @@ class Blake2s {
   }
 
  private:
+  friend class Blake2sLanes;  // the multi-stream form below reads and writes (h, t, buffered tail)
   static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
   // The statement absorb of a 2^16-card proof hashes ~17 MB on ONE core and nothing on the GPU can
   // start before it ends, so the compression function matters: on x86 hosts with AVX2 a 4-lane
@@ -265,6 +266,183 @@ class Blake2s {
   size_t fill_;
 };
 
+// Up to 8 Blake2s streams of EQUAL length hashed in lockstep: lane l of every vector register holds stream l, so one
+// pass of the compression function advances all of them (AVX2; rotations are single instructions with AVX-512VL).
+// A batch of 2^16-card proofs spends 2 x 23.5 ms of one core per proof on its two statement hashes (17 MB each, one
+// serial Blake2s stream at 793 MB/s), and with several GPUs' workers on one host that hashing is what the GPUs wait
+// for; the streams of different proofs are independent, so eight of them cost about one and a half times one.
+// Same bytes in, same digests out as eight Blake2s objects: update() mirrors Blake2s::update (the last block stays
+// buffered for finish), and the state of a lane can be moved into a Blake2s at any point (`extract`).
+class Blake2sLanes {
+ public:
+  static constexpr int kLanes = 8;
+  explicit Blake2sLanes(int lanes) : lanes_(lanes) {
+    for (int l = 0; l < kLanes; l++) st_[l].reset();
+  }
+  int lanes() const { return lanes_; }
+  // the same bytes for every lane (labels, parameters)
+  void update_all(const void* data, size_t len) {
+    const uint8_t* p[kLanes];
+    for (int l = 0; l < kLanes; l++) p[l] = static_cast<const uint8_t*>(data);
+    update(p, len);
+  }
+  // data[l] = `len` bytes for lane l (l < lanes())
+  void update(const uint8_t* const* data, size_t len) {
+    if (len == 0) return;
+    const uint8_t* in[kLanes];
+    for (int l = 0; l < kLanes; l++) in[l] = data[l < lanes_ ? l : 0];
+    size_t fill = st_[0].fill_;
+    if (fill > 0) {
+      size_t take = 64 - fill;
+      if (take > len) take = len;
+      for (int l = 0; l < lanes_; l++) {
+        memcpy(st_[l].buf_ + fill, in[l], take);
+        st_[l].fill_ = fill + take;
+        in[l] += take;
+      }
+      len -= take;
+      if (len == 0) return;  // keep a possibly-final block buffered
+      const uint8_t* b[kLanes];
+      for (int l = 0; l < kLanes; l++) b[l] = st_[l < lanes_ ? l : 0].buf_;
+      compress_blocks(b, 1);
+      for (int l = 0; l < lanes_; l++) st_[l].fill_ = 0;
+    }
+    if (len > 64) {  // all full blocks but the last
+      const size_t nblocks = (len - 1) / 64;
+      compress_blocks(in, nblocks);
+      for (int l = 0; l < kLanes; l++) in[l] += 64 * nblocks;
+      len -= 64 * nblocks;
+    }
+    for (int l = 0; l < lanes_; l++) {
+      memcpy(st_[l].buf_, in[l], len);
+      st_[l].fill_ = len;
+    }
+  }
+  // lane l's stream so far, as a single-stream hasher that can go on absorbing
+  void extract(int l, Blake2s* out) const { *out = st_[l]; }
+  static bool vectorised() {
+#ifdef MP_BLAKE2S_X86
+    static const bool ok = __builtin_cpu_supports("avx2") && !getenv("MP_BLAKE2S_LANES_SCALAR");
+    return ok;
+#else
+    return false;
+#endif
+  }
+
+ private:
+  // nblocks full, non-final blocks from in[l] for every lane
+  void compress_blocks(const uint8_t* const* in, size_t nblocks) {
+#ifdef MP_BLAKE2S_X86
+    if (vectorised()) {
+      if (Blake2s::use_avx512()) compress_blocks_avx512vl(in, nblocks);
+      else compress_blocks_avx2(in, nblocks);
+      return;
+    }
+#endif
+    for (int l = 0; l < lanes_; l++) {
+      const uint8_t* p = in[l];
+      for (size_t b = 0; b < nblocks; b++, p += 64) {
+        st_[l].t_ += 64;
+        st_[l].compress(p, false);
+      }
+    }
+  }
+#ifdef MP_BLAKE2S_X86
+#define MP_LANES_BODY(ROR)                                                                                         \
+    const __m256i iv0 = _mm256_set1_epi32((int)0x6A09E667u), iv1 = _mm256_set1_epi32((int)0xBB67AE85u),              \
+                  iv2 = _mm256_set1_epi32((int)0x3C6EF372u), iv3 = _mm256_set1_epi32((int)0xA54FF53Au),              \
+                  iv4 = _mm256_set1_epi32((int)0x510E527Fu), iv5 = _mm256_set1_epi32((int)0x9B05688Cu),              \
+                  iv6 = _mm256_set1_epi32((int)0x1F83D9ABu), iv7 = _mm256_set1_epi32((int)0x5BE0CD19u);              \
+    __m256i h[8];                                                                                                  \
+    {                                                                                                              \
+      alignas(32) uint32_t tmp[8][8];                                                                              \
+      for (int w = 0; w < 8; w++)                                                                                  \
+        for (int l = 0; l < 8; l++) tmp[w][l] = st_[l].h_[w];                                                      \
+      for (int w = 0; w < 8; w++) h[w] = _mm256_load_si256((const __m256i*)tmp[w]);                                \
+    }                                                                                                              \
+    uint64_t t = st_[0].t_;                                                                                        \
+    for (size_t blk = 0; blk < nblocks; blk++) {                                                                   \
+      t += 64;                                                                                                     \
+      __m256i m[16];                                                                                               \
+      for (int half = 0; half < 2; half++) {                                                                       \
+        __m256i r[8];                                                                                              \
+        for (int l = 0; l < 8; l++) r[l] = _mm256_loadu_si256((const __m256i*)(in[l] + 64 * blk + 32 * half));     \
+        const __m256i t0 = _mm256_unpacklo_epi32(r[0], r[1]), t1 = _mm256_unpackhi_epi32(r[0], r[1]);              \
+        const __m256i t2 = _mm256_unpacklo_epi32(r[2], r[3]), t3 = _mm256_unpackhi_epi32(r[2], r[3]);              \
+        const __m256i t4 = _mm256_unpacklo_epi32(r[4], r[5]), t5 = _mm256_unpackhi_epi32(r[4], r[5]);              \
+        const __m256i t6 = _mm256_unpacklo_epi32(r[6], r[7]), t7 = _mm256_unpackhi_epi32(r[6], r[7]);              \
+        const __m256i u0 = _mm256_unpacklo_epi64(t0, t2), u1 = _mm256_unpackhi_epi64(t0, t2);                      \
+        const __m256i u2 = _mm256_unpacklo_epi64(t1, t3), u3 = _mm256_unpackhi_epi64(t1, t3);                      \
+        const __m256i u4 = _mm256_unpacklo_epi64(t4, t6), u5 = _mm256_unpackhi_epi64(t4, t6);                      \
+        const __m256i u6 = _mm256_unpacklo_epi64(t5, t7), u7 = _mm256_unpackhi_epi64(t5, t7);                      \
+        m[8 * half + 0] = _mm256_permute2x128_si256(u0, u4, 0x20);                                                 \
+        m[8 * half + 1] = _mm256_permute2x128_si256(u1, u5, 0x20);                                                 \
+        m[8 * half + 2] = _mm256_permute2x128_si256(u2, u6, 0x20);                                                 \
+        m[8 * half + 3] = _mm256_permute2x128_si256(u3, u7, 0x20);                                                 \
+        m[8 * half + 4] = _mm256_permute2x128_si256(u0, u4, 0x31);                                                 \
+        m[8 * half + 5] = _mm256_permute2x128_si256(u1, u5, 0x31);                                                 \
+        m[8 * half + 6] = _mm256_permute2x128_si256(u2, u6, 0x31);                                                 \
+        m[8 * half + 7] = _mm256_permute2x128_si256(u3, u7, 0x31);                                                 \
+      }                                                                                                            \
+      __m256i v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];              \
+      __m256i v8 = iv0, v9 = iv1, v10 = iv2, v11 = iv3;                                                            \
+      __m256i v12 = _mm256_xor_si256(iv4, _mm256_set1_epi32((int)(uint32_t)t));                                    \
+      __m256i v13 = _mm256_xor_si256(iv5, _mm256_set1_epi32((int)(uint32_t)(t >> 32)));                            \
+      __m256i v14 = iv6, v15 = iv7;                                                                                \
+      MP_LR(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);                                                 \
+      MP_LR(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);                                                 \
+      MP_LR(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);                                                 \
+      MP_LR(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);                                                 \
+      MP_LR(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);                                                 \
+      MP_LR(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);                                                 \
+      MP_LR(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);                                                 \
+      MP_LR(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);                                                 \
+      MP_LR(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);                                                 \
+      MP_LR(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);                                                 \
+      h[0] = _mm256_xor_si256(h[0], _mm256_xor_si256(v0, v8));                                                     \
+      h[1] = _mm256_xor_si256(h[1], _mm256_xor_si256(v1, v9));                                                     \
+      h[2] = _mm256_xor_si256(h[2], _mm256_xor_si256(v2, v10));                                                    \
+      h[3] = _mm256_xor_si256(h[3], _mm256_xor_si256(v3, v11));                                                    \
+      h[4] = _mm256_xor_si256(h[4], _mm256_xor_si256(v4, v12));                                                    \
+      h[5] = _mm256_xor_si256(h[5], _mm256_xor_si256(v5, v13));                                                    \
+      h[6] = _mm256_xor_si256(h[6], _mm256_xor_si256(v6, v14));                                                    \
+      h[7] = _mm256_xor_si256(h[7], _mm256_xor_si256(v7, v15));                                                    \
+    }                                                                                                              \
+    {                                                                                                              \
+      alignas(32) uint32_t tmp[8][8];                                                                              \
+      for (int w = 0; w < 8; w++) _mm256_store_si256((__m256i*)tmp[w], h[w]);                                      \
+      for (int l = 0; l < 8; l++) {                                                                                \
+        for (int w = 0; w < 8; w++) st_[l].h_[w] = tmp[w][l];                                                      \
+        st_[l].t_ = t;                                                                                             \
+      }                                                                                                            \
+    }
+#define MP_LG(a, b, c, d, x, y)                                                         \
+  a = _mm256_add_epi32(_mm256_add_epi32(a, b), m[x]); d = ROR(_mm256_xor_si256(d, a), 16); \
+  c = _mm256_add_epi32(c, d);                         b = ROR(_mm256_xor_si256(b, c), 12); \
+  a = _mm256_add_epi32(_mm256_add_epi32(a, b), m[y]); d = ROR(_mm256_xor_si256(d, a), 8);  \
+  c = _mm256_add_epi32(c, d);                         b = ROR(_mm256_xor_si256(b, c), 7)
+#define MP_LR(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15)                      \
+  MP_LG(v0, v4, v8, v12, s0, s1); MP_LG(v1, v5, v9, v13, s2, s3); MP_LG(v2, v6, v10, v14, s4, s5);       \
+  MP_LG(v3, v7, v11, v15, s6, s7); MP_LG(v0, v5, v10, v15, s8, s9); MP_LG(v1, v6, v11, v12, s10, s11);  \
+  MP_LG(v2, v7, v8, v13, s12, s13); MP_LG(v3, v4, v9, v14, s14, s15)
+  __attribute__((target("avx2"))) void compress_blocks_avx2(const uint8_t* const* in, size_t nblocks) {
+#define ROR(x, n) _mm256_or_si256(_mm256_srli_epi32((x), (n)), _mm256_slli_epi32((x), 32 - (n)))
+    MP_LANES_BODY(ROR)
+#undef ROR
+  }
+  __attribute__((target("avx2,avx512f,avx512vl"))) void compress_blocks_avx512vl(const uint8_t* const* in, size_t nblocks) {
+#define ROR(x, n) _mm256_ror_epi32((x), (n))
+    MP_LANES_BODY(ROR)
+#undef ROR
+  }
+#undef MP_LR
+#undef MP_LG
+#undef MP_LANES_BODY
+#endif
+  int lanes_;
+  Blake2s st_[kLanes];  // per lane: h, t, buffered tail (unused lanes shadow lane 0 and are never read back)
+};
+
 // rand_chacha `ChaCha20Rng`: 20 rounds, 64-bit block counter in words 12..13, stream id 0
 class ChaCha20Stream {
  public:
@@ -333,30 +511,36 @@ class Transcript {
   // ark-ec `ToBytes` encoding x || y || infinity flag, serialized in blocks of 64 points so the hash sees
   // few, large updates.  (The name keeps its Stark-curve origin.)
   void feed_points64(const uint8_t* pts, size_t count) {
-    constexpr size_t PB = 8 * kFqLimbs, FB = PB / 2;
-    uint8_t buf[64 * (PB + 1)];
+    uint8_t buf[kEncChunk * kEncPoint];
     while (count > 0) {
-      size_t take = count < 64 ? count : 64;
-      uint8_t* b = buf;
-      for (size_t i = 0; i < take; i++, b += PB + 1) {
-        const uint8_t* p = pts + PB * i;
-        uint64_t w[PB / 8], any = 0;
-        memcpy(w, p, PB);
-        for (size_t k = 0; k < PB / 8; k++) any |= w[k];
-        if (any == 0) {
-          memset(b, 0, PB + 1);  // identity = (0, 1, infinity)
-          b[FB] = 1;
-          b[PB] = 1;
-        } else {
-          memcpy(b, p, PB);
-          b[PB] = 0;
-        }
-      }
-      pending_.update(buf, take * (PB + 1));
-      pts += PB * take;
+      const size_t take = count < kEncChunk ? count : kEncChunk;
+      encode_points(pts, take, buf);
+      pending_.update(buf, take * kEncPoint);
+      pts += kEncIn * take;
       count -= take;
     }
   }
+  // `take` C-ABI points -> their ark-ec `ToBytes` encodings, back to back
+  static constexpr size_t kEncIn = 8 * kFqLimbs, kEncPoint = kEncIn + 1, kEncChunk = 64;
+  static void encode_points(const uint8_t* pts, size_t take, uint8_t* b) {
+    constexpr size_t PB = kEncIn, FB = PB / 2;
+    for (size_t i = 0; i < take; i++, b += PB + 1) {
+      const uint8_t* p = pts + PB * i;
+      uint64_t w[PB / 8], any = 0;
+      memcpy(w, p, PB);
+      for (size_t k = 0; k < PB / 8; k++) any |= w[k];
+      if (any == 0) {
+        memset(b, 0, PB + 1);  // identity = (0, 1, infinity)
+        b[FB] = 1;
+        b[PB] = 1;
+      } else {
+        memcpy(b, p, PB);
+        b[PB] = 0;
+      }
+    }
+  }
+  // continue an absorb whose first bytes were hashed elsewhere (TranscriptLanes below): replaces begin()
+  void adopt_pending(const Blake2s& started) { pending_ = started; }
   void end() {
     pending_.update(seed_, 32);
     pending_.finish(seed_);
@@ -386,6 +570,49 @@ class Transcript {
   uint8_t seed_[32];
   ChaCha20Stream rng_;
   Blake2s pending_;
+};
+
+// The first part of ONE absorb of up to 8 transcripts whose inputs have the same shape (the statements of the proofs of
+// a batch: same parameters, decks of the same size), hashed in lockstep by Blake2sLanes.  hand_over(l, fs) moves lane
+// l's hasher into `fs`, which goes on with feed() / feed_points64() / end() as if it had absorbed the bytes itself.
+class TranscriptLanes {
+ public:
+  explicit TranscriptLanes(int lanes) : h_(lanes) {}
+  void feed_all(const void* data, size_t len) { h_.update_all(data, len); }
+  void feed_label_all(const char* s) { h_.update_all(s, strlen(s)); }
+  void feed_points64_all(const uint8_t* pts, size_t count) {
+    const uint8_t* p[Blake2sLanes::kLanes];
+    for (int l = 0; l < Blake2sLanes::kLanes; l++) p[l] = pts;
+    feed_points64(p, count);
+  }
+  // pts[l] = `count` C-ABI points of lane l
+  void feed_points64(const uint8_t* const* pts, size_t count) {
+    const int L = h_.lanes();
+    const uint8_t* src[Blake2sLanes::kLanes];
+    for (int l = 0; l < L; l++) src[l] = pts[l];
+    const bool shared = [&] { for (int l = 1; l < L; l++) if (pts[l] != pts[0]) return false; return true; }();
+    const uint8_t* enc[Blake2sLanes::kLanes];
+    while (count > 0) {
+      const size_t take = count < Transcript::kEncChunk ? count : Transcript::kEncChunk;
+      for (int l = 0; l < L; l++) {
+        if (l == 0 || !shared) Transcript::encode_points(src[l], take, buf_[l]);
+        enc[l] = shared ? buf_[0] : buf_[l];
+        src[l] += Transcript::kEncIn * take;
+      }
+      h_.update(enc, take * Transcript::kEncPoint);
+      count -= take;
+    }
+  }
+  void extract(int lane, Blake2s* out) const { h_.extract(lane, out); }
+  void hand_over(int lane, Transcript* fs) const {
+    Blake2s b;
+    h_.extract(lane, &b);
+    fs->adopt_pending(b);
+  }
+
+ private:
+  Blake2sLanes h_;
+  uint8_t buf_[Blake2sLanes::kLanes][Transcript::kEncChunk * Transcript::kEncPoint];
 };
 
 }  // namespace mp

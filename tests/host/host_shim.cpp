@@ -84,6 +84,55 @@ void h_fs_points_challenge(const uint8_t* pts, uint64_t count, uint8_t* out) {
 }
 }
 
+// ---- multi-stream Blake2s (Blake2sLanes / TranscriptLanes of csrc/transcript.hpp)
+extern "C" {
+// `lanes` streams of `len` bytes (stream l at data + l * stride), fed in pieces of `piece` bytes; out = lanes * 32 digest bytes.
+// mode 0: vectorised if the CPU allows, 1: also finish through extract() after only `cut` bytes went through the lanes
+void h_blake2s_lanes(const uint8_t* data, uint64_t stride, uint64_t len, int lanes, uint64_t piece, uint64_t cut, uint8_t* out) {
+  Blake2sLanes mb(lanes);
+  if (cut > len) cut = len;
+  const uint8_t* p[Blake2sLanes::kLanes];
+  for (uint64_t off = 0; off < cut;) {
+    const uint64_t take = piece < cut - off ? piece : cut - off;
+    for (int l = 0; l < lanes; l++) p[l] = data + l * stride + off;
+    mb.update(p, take);
+    off += take;
+  }
+  for (int l = 0; l < lanes; l++) {
+    Blake2s h;
+    mb.extract(l, &h);
+    h.update(data + l * stride + cut, len - cut);   // the rest goes through the single-stream hasher
+    h.finish(out + 32 * l);
+  }
+}
+int h_blake2s_lanes_vectorised() { return Blake2sLanes::vectorised() ? 1 : 0; }
+// lanes transcripts: label | shared points | per-lane points (lockstep), then per lane: more points + end -> one challenge each
+void h_fs_lanes_challenges(const uint8_t* shared_pts, uint64_t n_shared, const uint8_t* lane_pts, uint64_t n_lane, int lanes,
+                           const uint8_t* tail_pts, uint64_t n_tail, uint8_t* out) {
+  TranscriptLanes tl(lanes);
+  tl.feed_label_all("label");
+  tl.feed_points64_all(shared_pts, n_shared);
+  const uint8_t* p[Blake2sLanes::kLanes];
+  for (int l = 0; l < lanes; l++) p[l] = lane_pts + 64 * n_lane * l;
+  tl.feed_points64(p, n_lane);
+  for (int l = 0; l < lanes; l++) {
+    Transcript fs;
+    tl.hand_over(l, &fs);
+    fs.feed_points64(tail_pts, n_tail);
+    fs.end();
+    fr c = fs.challenge(); uint32_t w[8]; fr_to_canonical(c, w); memcpy(out + 32 * l, w, 32);
+  }
+}
+// the same through one ordinary transcript per lane
+void h_fs_single_challenge(const uint8_t* shared_pts, uint64_t n_shared, const uint8_t* lane_pts, uint64_t n_lane,
+                           const uint8_t* tail_pts, uint64_t n_tail, uint8_t* out) {
+  Transcript fs;
+  fs.begin(); fs.feed_label("label"); fs.feed_points64(shared_pts, n_shared); fs.feed_points64(lane_pts, n_lane);
+  fs.feed_points64(tail_pts, n_tail); fs.end();
+  fr c = fs.challenge(); uint32_t w[8]; fr_to_canonical(c, w); memcpy(out, w, 32);
+}
+}
+
 // ---- host-only verifier plan (csrc/shuffle_host.hpp): challenges, the eight commitment-space
 // jobs and the two ciphertext equations of one proof, returned as flat (point, scalar) lists
 #include "../../mental-poker_b200/csrc/shuffle_host.hpp"

@@ -237,6 +237,33 @@ def test_verify_batch_matches_single_and_oracle(ctx, m, n, B):
     assert single == want
 
 
+@pytest.mark.parametrize("lanes", ["0", "1"])
+def test_large_deck_batch_verifier_with_shared_statement_hashes(ctx, lanes, monkeypatch):
+    """The large-deck batch verifier (worker contexts running the single-proof verifier; forced at a small size through
+    MP_SMALL_DECK_MAX) with each worker hashing its own statement and with the statements of up to eight proofs hashed
+    together (multi-stream Blake2s): the oracle's verdicts either way, valid and tampered proofs, 10 proofs = lane groups
+    of 8 + 2."""
+    monkeypatch.setenv("MP_SMALL_DECK_MAX", "0")
+    monkeypatch.setenv("MP_HASH_LANES", lanes)
+    m, n, B = 3, 4, 10
+    (enc_g, ck_g, ck_h, ghat, pk), decks, decks2, proofs = _batch(m, n, list(range(60, 60 + B)))
+    ctx.set_params(m, n, enc_g, ck_g, ck_h, ghat)
+    plen, dlen = len(proofs) // B, 128 * m * n
+    assert ctx.verify_shuffle_batch(pk, decks, decks2, proofs, host_threads=4) == [0] * B
+    bad = bytearray(proofs)
+    bad[plen * 2 - 1 - 32 * 3] ^= 1          # multi-exp response r of proof 1
+    o9 = plen * 9                            # proof 9 (second lane group): the first two points of c_A swapped -- still
+    bad[o9:o9 + 64], bad[o9 + 64:o9 + 128] = proofs[o9 + 64:o9 + 128], proofs[o9:o9 + 64]   # curve points, another first challenge
+    bad_decks2 = bytearray(decks2)
+    bad_decks2[4 * dlen:5 * dlen] = decks2[5 * dlen:6 * dlen]
+    got = ctx.verify_shuffle_batch(pk, decks, bytes(bad_decks2), bytes(bad), host_threads=4)
+    co = c_oracle.COracle(msm_mode=1)
+    want = [co.verify(m, n, enc_g, ck_g, ck_h, ghat, pk, decks[i * dlen:(i + 1) * dlen],
+                      bytes(bad_decks2[i * dlen:(i + 1) * dlen]), bytes(bad[i * plen:(i + 1) * plen])) for i in range(B)]
+    assert got == want
+    assert got[1] == 4 and got[4] == 1 and got[9] != 0 and got.count(0) == B - 3
+
+
 def test_batches_split_over_two_worker_contexts(ctx):
     """Batches of >= 256 small decks are cut into chunks that two worker contexts work through concurrently (one chunk
     in its host phases while the other is on the device; csrc/shuffle_internal.cuh run_chunks).  Proofs equal the
@@ -278,12 +305,15 @@ def test_batches_split_over_two_worker_contexts(ctx):
     assert all(got[i] != 0 for i in tampered)
 
 
-@pytest.mark.parametrize("m,n,B,workers", [(3, 4, 9, False), (3, 4, 9, True), (4, 13, 6, False), (2, 2, 3, False)])
+@pytest.mark.parametrize("m,n,B,workers", [(3, 4, 9, False), (3, 4, 9, True), (3, 4, 11, "lanes"), (4, 13, 6, False), (2, 2, 3, False)])
 def test_prove_batch_is_byte_identical_to_single_calls(ctx, m, n, B, workers, monkeypatch):
     # two implementations behind mp_shuffle_and_remask_batch: the lockstep prover (default for
-    # small decks) and concurrent worker contexts (large decks, or forced by MP_BATCH_WORKERS)
+    # small decks) and concurrent worker contexts (large decks, or forced by MP_BATCH_WORKERS) -- the latter with
+    # each worker hashing its own statement, or ("lanes") with the statement heads of up to eight decks hashed
+    # together by the multi-stream Blake2s (csrc/shuffle_internal.cuh StatementHashes: 11 decks = lane groups of 8 + 3)
     if workers:
         monkeypatch.setenv("MP_BATCH_WORKERS", "1")
+        monkeypatch.setenv("MP_HASH_LANES", "1" if workers == "lanes" else "0")
     co = c_oracle.COracle(msm_mode=1)
     pp0, pk0, *_ = instance(m, n, 50)
     enc_g, ck_g, ck_h, ghat, pk = pb(pp0.enc_g), b"".join(map(pb, pp0.ck_g)), pb(pp0.ck_h), pb(pp0.ghat), pb(pk0)

@@ -128,3 +128,44 @@ def test_host_transcript_matches_oracle(shim):
     fs = FiatShamirRng()
     fs.absorb(b"label" + b"".join(stark.point_to_bytes65(p) for p in pts))
     assert out.raw == stark.fe_to_bytes(fs.challenge())
+
+
+def test_multi_stream_blake2s_equals_single_streams(shim, tmp_path):
+    """Blake2sLanes (csrc/transcript.hpp: up to 8 equal-length streams hashed in lockstep, AVX2 / AVX-512VL) against
+    hashlib for every lane count, lengths around the block and buffering boundaries, odd piece sizes, and a hand-over to
+    the single-stream hasher in the middle of a stream; the scalar fallback through MP_BLAKE2S_LANES_SCALAR in a
+    subprocess-free way is the same code path as lanes == 1 on a CPU without AVX2, so it is driven here by forcing it."""
+    import hashlib, random
+    rnd = random.Random(9)
+    shim.h_blake2s_lanes.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64,
+                                     ctypes.c_uint64, ctypes.c_char_p]
+    stride = 5000
+    data = bytes(rnd.getrandbits(8) for _ in range(8 * stride))
+    out = ctypes.create_string_buffer(8 * 32)
+    for lanes in range(1, 9):
+        for ln in (0, 1, 63, 64, 65, 127, 128, 129, 1000, 4096, 4999):
+            for piece, cut in ((64, ln), (1, ln), (37, ln), (4160, ln), (5000, ln), (200, ln // 2), (64, 64), (4160, 0)):
+                shim.h_blake2s_lanes(data, stride, ln, lanes, max(piece, 1), min(cut, ln), out)
+                for l in range(lanes):
+                    want = hashlib.blake2s(data[l * stride:l * stride + ln]).digest()
+                    assert out.raw[32 * l:32 * l + 32] == want, (lanes, ln, piece, cut, l)
+
+
+def test_transcript_lanes_hand_over(shim):
+    """TranscriptLanes: the first part of an absorb hashed for several transcripts at once, then handed to ordinary
+    transcripts that finish it -- the challenges equal those of transcripts that absorbed everything themselves."""
+    import random
+    rnd = random.Random(10)
+    pts = lambda k: bytes(rnd.getrandbits(8) for _ in range(64 * k))
+    for lanes, n_shared, n_lane, n_tail in ((1, 3, 5, 2), (3, 70, 129, 1), (8, 515, 300, 4), (8, 1, 64, 0), (5, 0, 1, 1)):
+        shared, lane, tail = pts(n_shared), pts(n_lane * lanes), pts(n_tail)
+        if n_lane > 2:                                 # an identity point in lane 0 (all-zero bytes -> (0, 1, infinity))
+            lane = bytes(64) + lane[64:]
+        got = ctypes.create_string_buffer(32 * lanes)
+        shim.h_fs_lanes_challenges(shared, ctypes.c_uint64(n_shared), lane, ctypes.c_uint64(n_lane), lanes, tail,
+                                   ctypes.c_uint64(n_tail), got)
+        for l in range(lanes):
+            want = ctypes.create_string_buffer(32)
+            shim.h_fs_single_challenge(shared, ctypes.c_uint64(n_shared), lane[64 * n_lane * l:64 * n_lane * (l + 1)],
+                                       ctypes.c_uint64(n_lane), tail, ctypes.c_uint64(n_tail), want)
+            assert got.raw[32 * l:32 * l + 32] == want.raw, (lanes, l)
