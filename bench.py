@@ -593,7 +593,7 @@ def main():
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=clocks.summary(), roofline=roofline,
                     phases=dict(prove_ms_per_step=1e3 * phase["prove"] / max(phase["n"], 1), verify_ms_per_step=1e3 * phase["verify"] / max(phase["n"], 1),
-                                overlapped=bool(args.overlap), prove_worker_threads=prove_threads, verify_worker_threads=verify_threads,
+                                overlapped=bool(args.overlap), worker_contexts_per_call=int(os.environ.get("MP_PROVE_WORKERS", args.workers)), prove_host_threads=prove_threads, verify_host_threads=verify_threads,
                                 note="host wall clock of the two batch calls inside the steps of `value`" +
                                      (" (they run concurrently: a step lasts as long as the longer one)" if args.overlap else "")),
                     latency=dict(prove_ms=lat_p * 1e3, verify_ms=lat_v * 1e3, proofs_per_s_sequential=1.0 / (lat_p + lat_v),
