@@ -357,7 +357,7 @@ def main():
     state = dict(k=0)
     # host_threads of the two large-deck batch calls = the CPU threads each may keep busy: this rank's share of the host,
     # halved when the two calls run concurrently.  The library runs 8 worker contexts per call whatever the budget (they
-    # sleep while their kernels run) and, when the budget is below that, hashes the statements of the 8 decks together
+    # sleep while their kernels run) and, when the budget is below half of that, hashes the statements of the 8 decks together
     # (multi-stream Blake2s) instead of one serial 23.5 ms pass per worker -- which is what a shared host cannot afford
     prove_threads = verify_threads = max(2, host_threads // 2) if args.overlap else max(2, host_threads)
     os.environ.setdefault("MP_PROVE_WORKERS", str(args.workers))   # read by the library at its first large-deck batch call

@@ -217,7 +217,7 @@ int32_t mp_shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, c
  * proof is byte-identical to the single-call result.  `host_threads` (0 = all hardware threads) is the
  * number of CPU threads the call may keep BUSY.  Decks above 8 192 cards run on up to 8 worker contexts
  * whatever the budget (a worker sleeps while its kernels run; host_threads == 1 means one worker); when
- * the budget is below the number of workers -- several GPUs' callers sharing one host -- the serial
+ * the budget is below half the number of workers -- several GPUs' callers sharing one host -- the serial
  * Blake2s passes over the statements (17 MB per proof at 2^16 cards) are computed for up to eight proofs
  * at once by one thread (multi-stream Blake2s) instead of one pass per worker.  The batch verifier below
  * treats host_threads the same way.  Small decks: the thread count of the per-proof host phases. */

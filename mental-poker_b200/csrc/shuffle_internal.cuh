@@ -230,12 +230,14 @@ struct StatementHashes {
   }
 };
 // shared hashing on?  MP_HASH_LANES=0 / 1 forces it; otherwise on when the caller's thread budget (host_threads) is
-// below the number of worker contexts: the workers then cannot each have a core for their own 23.5 ms pass
+// below HALF the number of worker contexts.  Measured on one B200 with the process pinned to 16 / 8 / 6 / 4 vCPUs
+// (two concurrent batch calls of 8 workers each, so the budget per call is half of that): own pass per worker 43.3 /
+// 41.0 / 38.3 / 33.8 proofs/s, shared 40.6 / 40.3 / 40.3 / 39.1 -- the cross-over is between 4 and 3 threads per call.
 inline bool share_statement_hashes(int host_threads, int workers) {
   const char* e = getenv("MP_HASH_LANES");   // read per call: the tests switch it
   if (e) return atoi(e) != 0;
   const int budget = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
-  return workers > 1 && budget < workers;
+  return workers > 1 && 2 * budget < workers;
 }
 
 // Small-deck batches: fn(worker, p0, count) over [0, B) in chunks of at most `sub` proofs.  A sub-batch alternates host
