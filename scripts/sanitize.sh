@@ -36,6 +36,13 @@ for tool in synccheck racecheck; do
   timeout 500 $CS --tool $tool --print-limit 20 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_bls12_377.py -m gpu -x -q -k "msm_small or msm_golden or msm_jobs or ct_msm" > $OUT/msm_$tool.log 2>&1
   echo "msm tests (both curves) $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/msm_$tool.log | tail -1) / $(tail -1 $OUT/msm_$tool.log)" >> $SUM
 done
-timeout 500 $CS --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_sigma.py -m gpu -x -q -k "golden or vs_oracle" > $OUT/sigma_memcheck.log 2>&1
-echo "sigma tests memcheck: $(grep -E 'ERROR SUMMARY' $OUT/sigma_memcheck.log | tail -1) / $(tail -1 $OUT/sigma_memcheck.log)" >> $SUM
+timeout 500 $CS --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_sigma.py -m gpu -x -q -k "golden or vs_oracle or malformed" > $OUT/sigma_memcheck.log 2>&1
+echo "sigma tests memcheck: $(grep -E 'ERROR SUMMARY' $OUT/sigma_memcheck.log | tail -1) / $(grep -E 'passed|failed' $OUT/sigma_memcheck.log | tail -1)" >> $SUM
+# --- second curve: sigma protocols, wire-format deserialisation (square roots + G1 membership), chunked batch prover
+for tool in memcheck synccheck; do
+  timeout 500 $CS --tool $tool --print-limit 20 python -m pytest tests/test_gpu_bls12_377.py -m gpu -x -q -k "sigma or wire or golden" > $OUT/bls_sigma_wire_$tool.log 2>&1
+  echo "BLS12-377 sigma / wire / prover tests $tool: $(grep -E 'ERROR SUMMARY' $OUT/bls_sigma_wire_$tool.log | tail -1) / $(grep -E 'passed|failed' $OUT/bls_sigma_wire_$tool.log | tail -1)" >> $SUM
+done
+timeout 500 $CS --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_shuffle.py -m gpu -x -q -k "lanes or shared_statement or split_over" > $OUT/batch_memcheck.log 2>&1
+echo "batch drivers (chunked, shared hashes) memcheck: $(grep -E 'ERROR SUMMARY' $OUT/batch_memcheck.log | tail -1) / $(grep -E 'passed|failed' $OUT/batch_memcheck.log | tail -1)" >> $SUM
 cat $SUM
