@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "msm.cuh"
+#include "nvtx_ranges.hpp"
 
 namespace mp {
 
@@ -892,6 +893,7 @@ cudaError_t msm_fold_ranges(const xyzz* d_parts, int nranks, int ncomp, const in
 cudaError_t msm_run(MsmWorkspace* ws, const uint32_t* d_scalars, uint64_t n_scalars,
                     const affine* d_points, int ncomp, const MsmJob* h_jobs, int njobs, int c,
                     xyzz* d_out, cudaStream_t stream, int w_begin, int w_count, uint32_t table_nb) {
+  NvtxRange nvtx(table_nb ? "msm_run (fixed-base table)" : "msm_run");
   ws->launches = 0;
   if (njobs <= 0) return cudaSuccess;
   if (ncomp != 1 && ncomp != 2) return cudaErrorInvalidValue;

@@ -14,6 +14,7 @@
 #include "frvec.cuh"
 #include "host_pool.hpp"
 #include "msm.cuh"
+#include "nvtx_ranges.hpp"
 #include "shuffle.cuh"
 #include "shuffle_host.hpp"
 
@@ -200,6 +201,7 @@ struct StatementHashes {
     started.resize(B);
     ready.assign(B, 0);
     th = std::thread([=] {
+      NvtxRange nvtx("statement hashes, 8 lanes");
       const size_t stride = N * kCtBytes;
       for (uint64_t g0 = 0; g0 < B; g0 += Blake2sLanes::kLanes) {
         const int K = (int)std::min<uint64_t>(Blake2sLanes::kLanes, B - g0);

@@ -23,6 +23,7 @@ struct ProveTrace {
   bool on = getenv("MP_TRACE") != nullptr;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   void mark(const char* what) const {
+    nvtx_mark(what);
     if (on) fprintf(stderr, "[prove] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
   }
 };
@@ -35,6 +36,7 @@ int32_t shuffle_prove(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const
   if (!S || S->m == 0) return ctx->fail(MP_ERR_NO_PARAMS, "mp_ctx_set_params has not been called");
   cudaSetDevice(ctx->device);
   ctx->launches = 0;
+  NvtxRange nvtx("shuffle_prove");
   const ProveTrace trace;
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n;

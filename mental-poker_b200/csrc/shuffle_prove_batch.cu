@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(64) k_combine_E_batch(xyzz* __restrict__ E, co
 int32_t prove_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint32_t* perms,
                                const uint8_t* rhos, const uint8_t* rands, size_t Bs, uint8_t* out_decks, uint8_t* proofs,
                                int threads) {
+  NvtxRange nvtx("prove_sub_batch");
   ShuffleState* S = ctx->shuffle;
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n, plen = shuffle_proof_len(m, n), rlen = shuffle_randomness_len(m, n) * 32;

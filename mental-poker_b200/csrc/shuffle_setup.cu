@@ -255,6 +255,7 @@ int32_t shuffle_set_params(mp_ctx* ctx, int32_t m, int32_t n, const uint8_t* enc
 // ------------------------------------------------------------------------------------------
 int32_t shuffle_remask(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint32_t* perm, const uint8_t* rho,
                        uint64_t N, uint8_t* out_deck, const void* deck_src, const void** d_out_ret, Transcript* fs_head) {
+  NvtxRange nvtx("shuffle_remask");
   if (!deck_src) deck_src = deck;
   if (d_out_ret) *d_out_ret = nullptr;
   if (!ctx || !pk || (N && (!deck || !perm || !rho || !out_deck))) return MP_ERR_INVALID_ARG;

@@ -12,6 +12,7 @@ namespace mp {
 int32_t shuffle_verify(mp_ctx* ctx, const uint8_t* pk, const uint8_t* deck, const uint8_t* deck2,
                        const uint8_t* proof, const void* deck_src, const void* deck2_src, StatementHashes* hashes,
                        uint64_t hash_index) {
+  NvtxRange nvtx("shuffle_verify");
   if (!ctx || !pk || !deck || !deck2 || !proof) return MP_ERR_INVALID_ARG;
   if (!deck_src) deck_src = deck;     // host copy doubles as the transfer source
   if (!deck2_src) deck2_src = deck2;  // (a device pointer here means the deck is already resident in HBM)
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(64) k_group_identity(const xyzz* __restrict__ 
 
 static int32_t verify_sub_batch(mp_ctx* ctx, const uint8_t* pk, const uint8_t* decks, const uint8_t* decks2,
                                 const uint8_t* proofs, size_t Bs, int32_t* statuses, int threads) {
+  NvtxRange nvtx("verify_sub_batch");
   ShuffleState* S = ctx->shuffle;
   const int m = S->m, n = S->n;
   const size_t N = (size_t)m * n;
